@@ -1,0 +1,918 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY.  Only tests/, __graft_entry__.smoke() and bench.py's
+// cpu_baseline / --impl reference legs may load this library; nothing under ezpz_b200/ does.
+//
+// CPU restatement of the ezpz 0.2.27 solve path (the reference is Rust and cannot be built in this
+// image: no cargo/rustc, and its linear algebra is the un-vendored crate faer 0.24.0):
+//   * Model::new pattern build           ezpz/src/solver.rs:192-265   -> build_pattern()
+//   * Model::residual / refresh_jacobian ezpz/src/solver.rs:318-440   -> Model::residual/refresh_jacobian
+//   * solve_levenberg_marquardt          ezpz/src/solver/newton.rs:29-145 -> Model::solve_lm()
+//   * solve_inner / priority loop        ezpz/src/lib.rs:148-370      -> solve_inner()/solve_priority()
+//   * freedom_analysis                   ezpz/src/solver/find_dof.rs:15-104 -> freedom_analysis()
+//
+// PARITY STATUS.  Pinned against every known answer the reference's own tests hold for this path
+// (tests/test_oracle_pins.py: kernel known answers constraints.rs:2742-2956, iteration counts
+// tests.rs:1090-1127,1506-1766, fixture outcomes tests.rs:131-746, error/priority semantics
+// tests.rs:39-128).  AT THE FAER BOUNDARY PARITY IS UNPINNED: no reference test fixes the factor,
+// the step vector, lambda sequences or sum-of-squares values, and faer's elimination order / SIMD
+// summation order cannot be reproduced here.  The linear algebra below therefore follows a WRITTEN
+// arithmetic-order spec that the CUDA path implements independently:
+//   A[i][j] = sum over rows r ascending of fma(J[r][i], J[r][j], acc), acc starts at +0.0; then
+//             A[i][i] += lambda (one rounding);
+//   b[j]    = sum over rows r ascending (CSC order) of fma(J[r][j], -r[r], acc), acc from +0.0;
+//   L       = natural-order sparse Cholesky on the symbolic pattern of A:
+//             L[i][j] = (A[i][j] - sum_{k<j, k in row i and row j} L[i][k]*L[j][k]) * rinv[j], the sum
+//             taken as acc = fma(-L[i][k], L[j][k], acc) with k ascending, acc starts at A[i][j];
+//             pivot: acc = A[i][i] then fma(-L[i][k], L[i][k], acc), k ascending;
+//             the factorisation fails ("LltError::Numeric") iff !(acc > 0) or acc is not finite;
+//             rinv[i] = 1.0 / sqrt(acc) (IEEE sqrt, then IEEE divide) — one divide per column, every
+//             other "division by the pivot" is a multiplication by rinv;
+//   y, d    = forward / backward substitution with the same fma(-l, v, acc) pattern, k ascending,
+//             finished by acc * rinv[i];
+//   S       = sum r_i^2 as acc = acc + r_i*r_i (two roundings each, as Rust's .map(|x| x*x).sum()).
+// Constraint residuals and partials are evaluated without any contraction (Rust semantics).
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+#include "constraints_ref.h"
+
+namespace orc {
+
+struct Cfg {
+    uint64_t max_iterations;
+    double residual_tolerance;
+    double step_tolerance;
+    double initial_lambda;
+};
+
+enum Err : int32_t {
+    OK = 0, E_NOT_FOUND = 1, E_WRONG_NUMBER_GUESSES = 2, E_MISSING_GUESS = 3, E_MATRIX = 4, E_FAER = 5,
+    E_SOLVE = 6, E_SVD = 7, E_EMPTY = 8, E_INVALID = 10
+};
+
+struct ErrDetail {
+    uint64_t constraint_id = 0;
+    uint32_t variable = 0;
+};
+
+// ------------------------------------------------------------------------------------------
+// Pattern of J: solver.rs:217-265 (pairs -> sort + dedup -> CSC); CSR is its transpose.
+struct Pattern {
+    uint32_t m = 0, n = 0;
+    std::vector<uint32_t> cons_row0;  // first row of each constraint, n_cons+1 entries
+    std::vector<uint32_t> csc_col_ptr, csc_row_idx;
+    std::vector<uint32_t> csr_row_ptr, csr_col_idx;
+    std::vector<uint32_t> csr_to_csc;  // position in CSC value array of each CSR entry
+};
+
+static int32_t validate_variables(const Rec* cons, const uint64_t* cons_ids, uint32_t n_cons,
+                                  const uint32_t* var_ids, uint32_t n_vars, ErrDetail* det) {
+    // solver.rs:142-189.  var_ids == NULL means ids 0..n_vars-1.
+    std::vector<uint32_t> row0, row1;
+    for (uint32_t ci = 0; ci < n_cons; ++ci) {
+        row0.clear();
+        row1.clear();
+        nonzeroes(cons[ci], row0, row1);
+        for (auto* row : {&row0, &row1}) {
+            for (uint32_t v : *row) {
+                bool found;
+                if (var_ids) found = std::find(var_ids, var_ids + n_vars, v) != var_ids + n_vars;
+                else found = v < n_vars;
+                if (!found) {
+                    if (det) {
+                        det->constraint_id = cons_ids ? cons_ids[ci] : ci;
+                        det->variable = v;
+                    }
+                    return E_MISSING_GUESS;
+                }
+            }
+        }
+    }
+    return OK;
+}
+
+static int32_t build_pattern(const Rec* cons, uint32_t n_cons, uint32_t n_vars, Pattern& P) {
+    P.n = n_vars;
+    P.cons_row0.assign(n_cons + 1, 0);
+    std::vector<std::pair<uint32_t, uint32_t>> pairs;  // (col, row) so that sorting gives CSC order
+    std::vector<uint32_t> rows[2];
+    uint32_t row_num = 0;
+    for (uint32_t ci = 0; ci < n_cons; ++ci) {
+        rows[0].clear();
+        rows[1].clear();
+        nonzeroes(cons[ci], rows[0], rows[1]);
+        P.cons_row0[ci] = row_num;
+        int dim = residual_dim(cons[ci]);
+        for (int k = 0; k < dim; ++k) {
+            uint32_t this_row = row_num++;
+            for (uint32_t var : rows[k]) {
+                if (var >= n_vars) return E_MATRIX;  // faer CreationError::OutOfBounds
+                pairs.emplace_back(var, this_row);
+            }
+        }
+    }
+    P.cons_row0[n_cons] = row_num;
+    P.m = row_num;
+    std::sort(pairs.begin(), pairs.end());
+    pairs.erase(std::unique(pairs.begin(), pairs.end()), pairs.end());
+    size_t nnz = pairs.size();
+    P.csc_col_ptr.assign(n_vars + 1, 0);
+    P.csc_row_idx.resize(nnz);
+    for (size_t k = 0; k < nnz; ++k) {
+        P.csc_col_ptr[pairs[k].first + 1]++;
+        P.csc_row_idx[k] = pairs[k].second;
+    }
+    for (uint32_t j = 0; j < n_vars; ++j) P.csc_col_ptr[j + 1] += P.csc_col_ptr[j];
+    // CSR = transpose.
+    P.csr_row_ptr.assign(P.m + 1, 0);
+    for (size_t k = 0; k < nnz; ++k) P.csr_row_ptr[pairs[k].second + 1]++;
+    for (uint32_t r = 0; r < P.m; ++r) P.csr_row_ptr[r + 1] += P.csr_row_ptr[r];
+    P.csr_col_idx.resize(nnz);
+    P.csr_to_csc.resize(nnz);
+    std::vector<uint32_t> fill(P.csr_row_ptr.begin(), P.csr_row_ptr.end() - 1);
+    for (size_t k = 0; k < nnz; ++k) {  // CSC order is col-ascending, so each row fills col-ascending
+        uint32_t r = pairs[k].second;
+        P.csr_col_idx[fill[r]] = pairs[k].first;
+        P.csr_to_csc[fill[r]] = (uint32_t)k;
+        fill[r]++;
+    }
+    return OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Symbolic + numeric sparse Cholesky in natural order, row-by-row (up-looking).
+struct Chol {
+    uint32_t n = 0;
+    // Lower triangle of A by rows: for row i, columns j <= i ascending (diagonal always present, last).
+    std::vector<uint32_t> a_row_ptr, a_col;
+    // For each A entry (i,j): the list of (csc index in col i, csc index in col j) products, rows ascending.
+    std::vector<uint32_t> a_prod_ptr;
+    std::vector<uint32_t> a_prod_i, a_prod_j;
+    std::vector<double> a_val;
+    // L by rows: strictly-lower columns ascending, then the diagonal stored separately.
+    std::vector<uint32_t> l_row_ptr, l_col;
+    std::vector<double> l_val, l_diag;  // l_diag holds rinv[i] = 1/L[i][i]
+    // Column view of strictly-lower L: for column j, the entries (row k > j) ascending -> index into l_val.
+    std::vector<uint32_t> l_colptr, l_colrow, l_colidx;
+    // position of A(i,j) inside row i of L (or UINT32_MAX for the diagonal)
+    std::vector<uint32_t> a_to_l;
+    std::vector<double> w;  // dense work row
+    std::vector<uint32_t> mark;
+
+    void analyse(const Pattern& P) {
+        n = P.n;
+        // Pattern of lower(A) = lower(JtJ) + diag.
+        std::vector<std::vector<uint32_t>> rows(n);
+        for (uint32_t r = 0; r < P.m; ++r) {
+            for (uint32_t a = P.csr_row_ptr[r]; a < P.csr_row_ptr[r + 1]; ++a)
+                for (uint32_t b = P.csr_row_ptr[r]; b <= a; ++b) rows[P.csr_col_idx[a]].push_back(P.csr_col_idx[b]);
+        }
+        a_row_ptr.assign(n + 1, 0);
+        a_col.clear();
+        for (uint32_t i = 0; i < n; ++i) {
+            rows[i].push_back(i);
+            std::sort(rows[i].begin(), rows[i].end());
+            rows[i].erase(std::unique(rows[i].begin(), rows[i].end()), rows[i].end());
+            a_col.insert(a_col.end(), rows[i].begin(), rows[i].end());
+            a_row_ptr[i + 1] = (uint32_t)a_col.size();
+        }
+        a_val.assign(a_col.size(), 0.0);
+        // Product lists: intersect CSC columns i and j (both row-ascending).
+        a_prod_ptr.assign(a_col.size() + 1, 0);
+        a_prod_i.clear();
+        a_prod_j.clear();
+        for (uint32_t i = 0; i < n; ++i) {
+            for (uint32_t e = a_row_ptr[i]; e < a_row_ptr[i + 1]; ++e) {
+                uint32_t j = a_col[e];
+                uint32_t pi = P.csc_col_ptr[i], pie = P.csc_col_ptr[i + 1];
+                uint32_t pj = P.csc_col_ptr[j], pje = P.csc_col_ptr[j + 1];
+                while (pi < pie && pj < pje) {
+                    uint32_t ri = P.csc_row_idx[pi], rj = P.csc_row_idx[pj];
+                    if (ri == rj) {
+                        a_prod_i.push_back(pi);
+                        a_prod_j.push_back(pj);
+                        ++pi;
+                        ++pj;
+                    } else if (ri < rj) ++pi;
+                    else ++pj;
+                }
+                a_prod_ptr[e + 1] = (uint32_t)a_prod_i.size();
+            }
+        }
+        // Symbolic factorisation: row i of L = row i of A, plus, for every j in the row, the part of
+        // column j of L that lies strictly between j and i... computed the simple way: process the row's
+        // columns in ascending order with a sorted set, adding the later rows-of-column entries.
+        std::vector<std::vector<uint32_t>> lrows(n), lcols(n);
+        std::vector<uint32_t> smark(n, UINT32_MAX);
+        for (uint32_t i = 0; i < n; ++i) {
+            std::vector<uint32_t>& row = lrows[i];
+            for (uint32_t e = a_row_ptr[i]; e < a_row_ptr[i + 1]; ++e) {
+                uint32_t j = a_col[e];
+                if (j < i && smark[j] != i) {
+                    smark[j] = i;
+                    row.push_back(j);
+                }
+            }
+            // closure: if L[i][j] != 0 and L[k][j] != 0 with j < k < i then L[i][k] != 0
+            std::sort(row.begin(), row.end());
+            for (size_t q = 0; q < row.size(); ++q) {
+                uint32_t j = row[q];
+                bool added = false;
+                for (uint32_t k : lcols[j]) {
+                    if (k < i && smark[k] != i) {
+                        smark[k] = i;
+                        row.push_back(k);
+                        added = true;
+                    }
+                }
+                if (added) std::sort(row.begin() + q + 1, row.end());
+            }
+            for (uint32_t j : row) lcols[j].push_back(i);
+        }
+        l_row_ptr.assign(n + 1, 0);
+        l_col.clear();
+        for (uint32_t i = 0; i < n; ++i) {
+            l_col.insert(l_col.end(), lrows[i].begin(), lrows[i].end());
+            l_row_ptr[i + 1] = (uint32_t)l_col.size();
+        }
+        l_val.assign(l_col.size(), 0.0);
+        l_diag.assign(n, 0.0);
+        // column view
+        l_colptr.assign(n + 1, 0);
+        for (uint32_t c : l_col) l_colptr[c + 1]++;
+        for (uint32_t j = 0; j < n; ++j) l_colptr[j + 1] += l_colptr[j];
+        l_colrow.resize(l_col.size());
+        l_colidx.resize(l_col.size());
+        std::vector<uint32_t> fill(l_colptr.begin(), l_colptr.end() - 1);
+        for (uint32_t i = 0; i < n; ++i)
+            for (uint32_t e = l_row_ptr[i]; e < l_row_ptr[i + 1]; ++e) {
+                uint32_t j = l_col[e];
+                l_colrow[fill[j]] = i;
+                l_colidx[fill[j]] = e;
+                fill[j]++;
+            }
+        w.assign(n, 0.0);
+        mark.assign(n, UINT32_MAX);
+    }
+
+    // A = JtJ + lambda*I  (newton.rs:73-83), lower triangle only.
+    void assemble(const std::vector<double>& jvals, double lambda) {
+        for (uint32_t i = 0; i < n; ++i)
+            for (uint32_t e = a_row_ptr[i]; e < a_row_ptr[i + 1]; ++e) {
+                double acc = 0.0;
+                for (uint32_t p = a_prod_ptr[e]; p < a_prod_ptr[e + 1]; ++p)
+                    acc = std::fma(jvals[a_prod_i[p]], jvals[a_prod_j[p]], acc);
+                if (a_col[e] == i) acc = acc + lambda;
+                a_val[e] = acc;
+            }
+    }
+
+    // Returns false on "LltError::Numeric".
+    bool factor() {
+        std::fill(mark.begin(), mark.end(), UINT32_MAX);
+        for (uint32_t i = 0; i < n; ++i) {
+            uint32_t lb = l_row_ptr[i], le = l_row_ptr[i + 1];
+            for (uint32_t e = lb; e < le; ++e) {
+                w[l_col[e]] = 0.0;  // structural fill entries start from A[i][j] = 0
+                mark[l_col[e]] = i;
+            }
+            double aii = 0.0;
+            for (uint32_t e = a_row_ptr[i]; e < a_row_ptr[i + 1]; ++e) {
+                if (a_col[e] == i) aii = a_val[e];
+                else w[a_col[e]] = a_val[e];
+            }
+            for (uint32_t e = lb; e < le; ++e) {
+                uint32_t j = l_col[e];
+                double acc = w[j];
+                for (uint32_t q = l_row_ptr[j]; q < l_row_ptr[j + 1]; ++q) {  // k ascending, k in row j
+                    uint32_t k = l_col[q];
+                    if (mark[k] != i) continue;  // ... and in row i
+                    acc = std::fma(-w[k], l_val[q], acc);
+                }
+                double lij = acc * l_diag[j];
+                w[j] = lij;
+                l_val[e] = lij;
+            }
+            double acc = aii;
+            for (uint32_t e = lb; e < le; ++e) acc = std::fma(-l_val[e], l_val[e], acc);
+            if (!(acc > 0.0) || !std::isfinite(acc)) return false;
+            l_diag[i] = 1.0 / std::sqrt(acc);  // rinv
+        }
+        return true;
+    }
+
+    // d = L^-T L^-1 b, in place.
+    void solve(std::vector<double>& b) const {
+        for (uint32_t i = 0; i < n; ++i) {
+            double acc = b[i];
+            for (uint32_t e = l_row_ptr[i]; e < l_row_ptr[i + 1]; ++e) acc = std::fma(-l_val[e], b[l_col[e]], acc);
+            b[i] = acc * l_diag[i];
+        }
+        for (uint32_t ii = n; ii-- > 0;) {
+            double acc = b[ii];
+            for (uint32_t q = l_colptr[ii]; q < l_colptr[ii + 1]; ++q)
+                acc = std::fma(-l_val[l_colidx[q]], b[l_colrow[q]], acc);
+            b[ii] = acc * l_diag[ii];
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------
+struct Model {
+    const Rec* cons;
+    const double* param_override;  // optional: per-constraint p0 override
+    uint32_t n_cons;
+    Pattern P;
+    Chol chol;
+    std::vector<double> jvals;          // CSC order
+    std::vector<uint32_t> degen_count;  // per constraint: number of Warning::Degenerate pushed
+    JRow row0, row1;
+
+    Rec effective(uint32_t ci) const {
+        Rec c = cons[ci];
+        if (param_override) c.p0 = param_override[ci];
+        return c;
+    }
+
+    // solver.rs:318-356
+    void residual(const double* x, double* out) {
+        uint32_t row_num = 0;
+        for (uint32_t ci = 0; ci < n_cons; ++ci) {
+            Rec c = effective(ci);
+            bool degenerate = false;
+            double r[2] = {0.0, 0.0};
+            orc::residual(c, x, &r[0], &r[1], &degenerate);
+            if (degenerate) degen_count[ci]++;
+            int dim = residual_dim(c);
+            for (int k = 0; k < dim; ++k) out[row_num++] = c.weight * r[k];
+        }
+    }
+
+    // solver.rs:359-440
+    void refresh_jacobian(const double* x) {
+        std::fill(jvals.begin(), jvals.end(), 0.0);
+        uint32_t row_num = 0;
+        for (uint32_t ci = 0; ci < n_cons; ++ci) {
+            Rec c = effective(ci);
+            bool degenerate = false;
+            row0.clear();
+            row1.clear();
+            jacobian_rows(c, x, row0, row1, &degenerate);
+            if (degenerate) degen_count[ci]++;
+            int dim = residual_dim(c);
+            for (int k = 0; k < dim; ++k) {
+                uint32_t this_row = row_num++;
+                const JRow& row = k == 0 ? row0 : row1;
+                for (const JVar& jv : row) {
+                    double weighted = c.weight * jv.pd;
+                    uint32_t col = jv.id;
+                    uint32_t idx = P.csc_col_ptr[col];
+                    while (P.csc_row_idx[idx] != this_row) ++idx;  // linear search, solver.rs:412-418
+                    jvals[idx] += weighted;
+                }
+            }
+        }
+    }
+
+    // newton.rs:29-145.  Returns OK or E_EMPTY.
+    int32_t solve_lm(double* x, const Cfg& cfg, uint64_t* iterations, bool* converged,
+                     std::vector<double>* trace) {
+        uint32_t m = P.m, n = P.n;
+        std::vector<double> r(m, 0.0), rn(m, 0.0), d(n, 0.0);
+        double lambda = cfg.initial_lambda;
+        residual(x, r.data());
+        refresh_jacobian(x);
+        double residual_sq = 0.0;
+        for (uint32_t i = 0; i < m; ++i) residual_sq = residual_sq + r[i] * r[i];
+        for (uint64_t it = 0; it < cfg.max_iterations; ++it) {
+            if (m == 0) return E_EMPTY;
+            double largest = std::fabs(r[0]);
+            for (uint32_t i = 1; i < m; ++i) largest = orc_fmax(largest, std::fabs(r[i]));
+            if (largest <= cfg.residual_tolerance) {
+                *iterations = it;
+                *converged = true;
+                return OK;
+            }
+            chol.assemble(jvals, lambda);
+            for (uint32_t j = 0; j < n; ++j) {  // b = Jt * (-r)
+                double acc = 0.0;
+                for (uint32_t e = P.csc_col_ptr[j]; e < P.csc_col_ptr[j + 1]; ++e)
+                    acc = std::fma(jvals[e], -r[P.csc_row_idx[e]], acc);
+                d[j] = acc;
+            }
+            if (!chol.factor()) {
+                if (trace) { trace->push_back(lambda); trace->push_back(residual_sq); trace->push_back(-1.0); trace->push_back(-1.0); }
+                lambda *= 10.0;
+                continue;
+            }
+            chol.solve(d);
+            double step = 0.0;  // unwrap_or(0.0) for n == 0
+            if (n > 0) {
+                step = std::fabs(d[0]);
+                for (uint32_t j = 1; j < n; ++j) step = orc_fmax(step, std::fabs(d[j]));
+            }
+            for (uint32_t j = 0; j < n; ++j) x[j] += d[j];
+            residual(x, rn.data());
+            double next_sq = 0.0;
+            for (uint32_t i = 0; i < m; ++i) next_sq = next_sq + rn[i] * rn[i];
+            if (trace) { trace->push_back(lambda); trace->push_back(residual_sq); trace->push_back(next_sq); trace->push_back(step); }
+            if (next_sq < residual_sq) {
+                r.swap(rn);
+                refresh_jacobian(x);
+                residual_sq = next_sq;
+                lambda *= 0.1;
+            } else {
+                for (uint32_t j = 0; j < n; ++j) x[j] -= d[j];
+                lambda *= 10.0;
+            }
+            if (step <= cfg.step_tolerance) {
+                *iterations = it;
+                *converged = true;
+                return OK;
+            }
+        }
+        *iterations = cfg.max_iterations;
+        *converged = false;
+        return OK;
+    }
+};
+
+// ------------------------------------------------------------------------------------------
+// find_dof.rs:15-104.  Dense column-pivoted Householder QR; the participation norms are the diagonal
+// of the orthogonal projector onto null(J), so they do not depend on which orthonormal basis is used.
+static int32_t freedom_analysis(const Model& M, std::vector<uint32_t>& under) {
+    uint32_t m = M.P.m, n = M.P.n;
+    under.clear();
+    std::vector<double> A((size_t)m * n, 0.0);  // column-major
+    for (uint32_t j = 0; j < n; ++j)
+        for (uint32_t e = M.P.csc_col_ptr[j]; e < M.P.csc_col_ptr[j + 1]; ++e)
+            A[(size_t)j * m + M.P.csc_row_idx[e]] = M.jvals[e];
+    uint32_t ndiag = std::min(m, n);
+    if (ndiag == 0) return E_EMPTY;
+    std::vector<uint32_t> perm(n);
+    for (uint32_t j = 0; j < n; ++j) perm[j] = j;
+    std::vector<double> rdiag(ndiag, 0.0);
+    for (uint32_t k = 0; k < ndiag; ++k) {
+        // pivot: largest remaining column norm
+        uint32_t best = k;
+        double bestn = -1.0;
+        for (uint32_t j = k; j < n; ++j) {
+            double s = 0.0;
+            for (uint32_t i = k; i < m; ++i) s += A[(size_t)j * m + i] * A[(size_t)j * m + i];
+            if (s > bestn) {
+                bestn = s;
+                best = j;
+            }
+        }
+        if (best != k) {
+            for (uint32_t i = 0; i < m; ++i) std::swap(A[(size_t)k * m + i], A[(size_t)best * m + i]);
+            std::swap(perm[k], perm[best]);
+        }
+        double* col = &A[(size_t)k * m];
+        double norm = std::sqrt(bestn);
+        if (norm == 0.0) {
+            rdiag[k] = 0.0;
+            continue;
+        }
+        double alpha = col[k] > 0 ? -norm : norm;
+        // v = x - alpha e1 (stored in place below the diagonal), normalised so that v[k] = 1
+        double vk = col[k] - alpha;
+        for (uint32_t i = k + 1; i < m; ++i) col[i] /= vk;
+        double tau = -vk / alpha;  // = 2 / (v^T v) with v[k] = 1
+        col[k] = alpha;
+        rdiag[k] = alpha;
+        for (uint32_t j = k + 1; j < n; ++j) {
+            double* cj = &A[(size_t)j * m];
+            double s = cj[k];
+            for (uint32_t i = k + 1; i < m; ++i) s += col[i] * cj[i];
+            s *= tau;
+            cj[k] -= s;
+            for (uint32_t i = k + 1; i < m; ++i) cj[i] -= s * col[i];
+        }
+    }
+    auto R = [&](uint32_t i, uint32_t j) { return A[(size_t)j * m + i]; };  // valid for i <= j, i < ndiag
+    double largest = std::fabs(rdiag[0]);
+    for (uint32_t i = 1; i < ndiag; ++i) largest = orc_fmax(largest, std::fabs(rdiag[i]));
+    double tolerance = 1e-8 * largest;
+    uint32_t rank = 0;
+    while (rank < ndiag && std::fabs(rdiag[rank]) > tolerance) ++rank;
+    uint32_t nullity = n - rank;
+    if (nullity == 0) return OK;
+    // Basis of null(J P^T): columns z_f with z[rank+f] = 1 and R11 x = -R12 e_f.
+    std::vector<double> N((size_t)n * nullity, 0.0);  // column-major n x nullity, rows in permuted order
+    for (uint32_t f = 0; f < nullity; ++f) {
+        uint32_t free_var = rank + f;
+        double* z = &N[(size_t)f * n];
+        z[free_var] = 1.0;
+        for (uint32_t ii = rank; ii-- > 0;) {
+            double rhs = R(ii, free_var);
+            for (uint32_t j = ii + 1; j < rank; ++j) rhs += R(ii, j) * z[j];
+            double diagonal = R(ii, ii);
+            if (std::fabs(diagonal) <= tolerance) return E_EMPTY;
+            z[ii] = -rhs / diagonal;
+        }
+    }
+    // Orthonormalise (modified Gram-Schmidt, twice) and accumulate squared row norms.
+    for (uint32_t f = 0; f < nullity; ++f) {
+        double* z = &N[(size_t)f * n];
+        for (int pass = 0; pass < 2; ++pass)
+            for (uint32_t g = 0; g < f; ++g) {
+                const double* q = &N[(size_t)g * n];
+                double s = 0.0;
+                for (uint32_t i = 0; i < n; ++i) s += q[i] * z[i];
+                for (uint32_t i = 0; i < n; ++i) z[i] -= s * q[i];
+            }
+        double s = 0.0;
+        for (uint32_t i = 0; i < n; ++i) s += z[i] * z[i];
+        s = std::sqrt(s);
+        for (uint32_t i = 0; i < n; ++i) z[i] /= s;
+    }
+    std::vector<double> participation(n, 0.0);  // indexed by ORIGINAL variable
+    for (uint32_t f = 0; f < nullity; ++f)
+        for (uint32_t i = 0; i < n; ++i) participation[perm[i]] += N[(size_t)f * n + i] * N[(size_t)f * n + i];
+    double max_p = 0.0;
+    for (uint32_t j = 0; j < n; ++j) max_p = orc_fmax(max_p, participation[j]);
+    double var_tol = 1e-3 * max_p;
+    double squared_tol = var_tol * var_tol;
+    for (uint32_t j = 0; j < n; ++j)
+        if (participation[j] > squared_tol) under.push_back(j);
+    return OK;
+}
+
+// ------------------------------------------------------------------------------------------
+struct Outcome {
+    std::vector<double> final_values;
+    std::vector<uint64_t> unsatisfied;  // ORIGINAL request indices
+    std::vector<uint32_t> degen_count;  // per constraint of the solved subset, by original index
+    std::vector<uint32_t> underconstrained;
+    uint64_t iterations = 0;
+    bool converged = false;
+    uint32_t priority_solved = 0;
+    uint32_t num_vars = 0, num_eqs = 0;
+};
+
+// lib.rs:265-356 for one priority level.  `cons` already has sides resolved.
+static int32_t solve_inner(const Rec* cons, const uint64_t* cons_ids, const uint32_t* prios, uint32_t n_cons,
+                           const uint32_t* var_ids, const double* guesses, uint32_t n_vars,
+                           const double* param_override, const Cfg& cfg, bool analysis, Outcome& out,
+                           ErrDetail* det, std::vector<double>* trace) {
+    out.num_vars = n_vars;
+    out.num_eqs = 0;
+    for (uint32_t ci = 0; ci < n_cons; ++ci) out.num_eqs += residual_dim(cons[ci]);
+    int32_t rc = validate_variables(cons, cons_ids, n_cons, var_ids, n_vars, det);
+    if (rc != OK) return rc;
+    Model M;
+    M.cons = cons;
+    M.param_override = param_override;
+    M.n_cons = n_cons;
+    rc = build_pattern(cons, n_cons, n_vars, M.P);
+    if (rc != OK) return rc;
+    M.jvals.assign(M.P.csc_row_idx.size(), 0.0);
+    M.degen_count.assign(n_cons, 0);
+    M.chol.analyse(M.P);
+    out.final_values.assign(guesses, guesses + n_vars);
+    rc = M.solve_lm(out.final_values.data(), cfg, &out.iterations, &out.converged, trace);
+    if (rc != OK) return rc;
+    out.unsatisfied.clear();
+    for (uint32_t ci = 0; ci < n_cons; ++ci) {  // lib.rs:305-327: UNWEIGHTED residuals
+        Rec c = M.effective(ci);
+        double r[2] = {0.0, 0.0};
+        bool degenerate = false;
+        residual(c, out.final_values.data(), &r[0], &r[1], &degenerate);
+        int dim = residual_dim(c);
+        bool sat = std::fabs(r[0]) < EPSILON;
+        if (dim == 2) sat = sat && (std::fabs(r[1]) < EPSILON);
+        if (!sat) out.unsatisfied.push_back(cons_ids ? cons_ids[ci] : ci);
+    }
+    out.degen_count = M.degen_count;
+    out.underconstrained.clear();
+    if (analysis) {
+        rc = freedom_analysis(M, out.underconstrained);
+        if (rc != OK) return rc;
+    }
+    uint32_t lowest = 0;
+    for (uint32_t ci = 0; ci < n_cons; ++ci) lowest = std::max(lowest, prios ? prios[ci] : 0u);
+    out.priority_solved = lowest;
+    return OK;
+}
+
+// lib.rs:148-263
+static int32_t solve_priority(const Rec* cons_in, const uint32_t* prios, uint32_t n_cons, const uint32_t* var_ids,
+                              const double* guesses, uint32_t n_vars, const Cfg& cfg, bool analysis, Outcome& out,
+                              ErrDetail* det) {
+    if (n_cons == 0) {
+        out = Outcome();
+        out.final_values.assign(guesses, guesses + n_vars);
+        out.converged = true;
+        return OK;
+    }
+    uint32_t max_id = 0;
+    for (uint32_t k = 0; k < n_vars; ++k) max_id = std::max(max_id, var_ids ? var_ids[k] : k);
+    // Values indexed by id.  Ids referenced by a constraint but missing from the guesses read 0.0 here and are
+    // rejected later by validate_variables; ids beyond max_id would panic in the reference (index out of
+    // bounds) — the oracle extends the table with zeros instead.
+    uint32_t table = max_id + 1;
+    for (uint32_t ci = 0; ci < n_cons; ++ci)
+        for (int k = 0; k < 8; ++k) table = std::max(table, cons_in[ci].ids[k] + 1);
+    std::vector<double> initial_values(table, 0.0);
+    for (uint32_t k = 0; k < n_vars; ++k) initial_values[var_ids ? var_ids[k] : k] = guesses[k];
+    std::vector<Rec> cons(cons_in, cons_in + n_cons);
+    for (Rec& c : cons) set_from_initial_values(c, initial_values.data());
+    std::vector<uint32_t> levels;
+    for (uint32_t ci = 0; ci < n_cons; ++ci) levels.push_back(prios ? prios[ci] : 0u);
+    std::sort(levels.begin(), levels.end());
+    levels.erase(std::unique(levels.begin(), levels.end()), levels.end());
+    bool have = false;
+    Outcome best;
+    for (uint32_t level : levels) {
+        std::vector<Rec> subset;
+        std::vector<uint64_t> ids;
+        std::vector<uint32_t> ps;
+        for (uint32_t ci = 0; ci < n_cons; ++ci) {
+            uint32_t p = prios ? prios[ci] : 0u;
+            if (p <= level) {
+                subset.push_back(cons[ci]);
+                ids.push_back(ci);
+                ps.push_back(p);
+            }
+        }
+        Outcome cur;
+        int32_t rc = solve_inner(subset.data(), ids.data(), ps.data(), (uint32_t)subset.size(), var_ids, guesses,
+                                 n_vars, nullptr, cfg, analysis, cur, det, nullptr);
+        if (rc != OK) {
+            if (have) {
+                out = best;
+                return OK;
+            }
+            out = cur;
+            return rc;
+        }
+        // degen_count is per subset position; expand to original indices
+        std::vector<uint32_t> dc(n_cons, 0);
+        for (size_t q = 0; q < ids.size(); ++q) dc[ids[q]] = cur.degen_count[q];
+        cur.degen_count = dc;
+        if (!cur.unsatisfied.empty()) {
+            out = have ? best : cur;
+            return OK;
+        }
+        best = cur;
+        have = true;
+    }
+    out = best;
+    return OK;
+}
+
+}  // namespace orc
+
+// ==========================================================================================
+// C interface (ctypes-friendly).
+extern "C" {
+
+typedef struct orc_outcome {
+    double* final_values;       // [n_vars]
+    uint64_t* unsatisfied;      // [n_cons]
+    uint32_t n_unsatisfied;
+    uint32_t* degen_count;      // [n_cons] optional
+    uint32_t* underconstrained; // [n_vars] optional
+    uint32_t n_underconstrained;
+    uint64_t iterations;
+    uint32_t converged;
+    uint32_t priority_solved;
+    uint32_t num_vars, num_eqs;
+    uint64_t err_constraint_id;
+    uint32_t err_variable;
+} orc_outcome_t;
+
+static void export_outcome(const orc::Outcome& o, const orc::ErrDetail& det, uint32_t n_cons, orc_outcome_t* out) {
+    if (out->final_values && !o.final_values.empty())
+        std::memcpy(out->final_values, o.final_values.data(), o.final_values.size() * sizeof(double));
+    out->n_unsatisfied = (uint32_t)o.unsatisfied.size();
+    if (out->unsatisfied) std::copy(o.unsatisfied.begin(), o.unsatisfied.end(), out->unsatisfied);
+    if (out->degen_count) {
+        for (uint32_t c = 0; c < n_cons; ++c) out->degen_count[c] = c < o.degen_count.size() ? o.degen_count[c] : 0;
+    }
+    out->n_underconstrained = (uint32_t)o.underconstrained.size();
+    if (out->underconstrained) std::copy(o.underconstrained.begin(), o.underconstrained.end(), out->underconstrained);
+    out->iterations = o.iterations;
+    out->converged = o.converged ? 1 : 0;
+    out->priority_solved = o.priority_solved;
+    out->num_vars = o.num_vars;
+    out->num_eqs = o.num_eqs;
+    out->err_constraint_id = det.constraint_id;
+    out->err_variable = det.variable;
+}
+
+// ezpz::solve / ezpz::solve_analysis (lib.rs:80-144).  priorities may be NULL (all 0).
+int32_t orc_solve(const orc::Rec* cons, const uint32_t* priorities, uint32_t n_cons, const uint32_t* var_ids,
+                  const double* guesses, uint32_t n_vars, const orc::Cfg* cfg, int32_t analysis,
+                  orc_outcome_t* out) {
+    orc::Outcome o;
+    orc::ErrDetail det;
+    int32_t rc = orc::solve_priority(cons, priorities, n_cons, var_ids, guesses, n_vars, *cfg, analysis != 0, o, &det);
+    export_outcome(o, det, n_cons, out);
+    return rc;
+}
+
+// One solve_inner call with sides ALREADY resolved or left as given (Undefined behaves as Left / Exterior),
+// optional per-constraint p0 override, optional trace of (lambda, S, S', step) per iteration.
+int32_t orc_solve_inner(const orc::Rec* cons, uint32_t n_cons, const double* guesses, uint32_t n_vars,
+                        const double* param_override, const orc::Cfg* cfg, int32_t analysis, int32_t resolve_sides,
+                        orc_outcome_t* out, double* trace, uint32_t trace_cap, uint32_t* trace_len) {
+    std::vector<orc::Rec> c(cons, cons + n_cons);
+    if (resolve_sides) {
+        for (orc::Rec& r : c) {
+            bool ok = true;
+            for (int k = 0; k < 8; ++k) ok = ok && r.ids[k] < n_vars;
+            if (ok) orc::set_from_initial_values(r, guesses);
+        }
+    }
+    orc::Outcome o;
+    orc::ErrDetail det;
+    std::vector<double> tr;
+    int32_t rc = orc::solve_inner(c.data(), nullptr, nullptr, n_cons, nullptr, guesses, n_vars, param_override, *cfg,
+                                  analysis != 0, o, &det, trace ? &tr : nullptr);
+    export_outcome(o, det, n_cons, out);
+    if (trace && trace_len) {
+        uint32_t k = (uint32_t)std::min<size_t>(tr.size(), trace_cap);
+        std::memcpy(trace, tr.data(), k * sizeof(double));
+        *trace_len = k;
+    }
+    return rc;
+}
+
+// Pattern artefact.  Call with NULL arrays to get sizes.
+int32_t orc_pattern(const orc::Rec* cons, uint32_t n_cons, uint32_t n_vars, uint32_t* m, uint64_t* nnz,
+                    uint32_t* csc_col_ptr, uint32_t* csc_row_idx, uint32_t* csr_row_ptr, uint32_t* csr_col_idx,
+                    uint32_t* cons_row0) {
+    orc::Pattern P;
+    int32_t rc = orc::validate_variables(cons, nullptr, n_cons, nullptr, n_vars, nullptr);
+    if (rc != orc::OK) return rc;
+    rc = orc::build_pattern(cons, n_cons, n_vars, P);
+    if (rc != orc::OK) return rc;
+    *m = P.m;
+    *nnz = P.csc_row_idx.size();
+    if (csc_col_ptr) std::copy(P.csc_col_ptr.begin(), P.csc_col_ptr.end(), csc_col_ptr);
+    if (csc_row_idx) std::copy(P.csc_row_idx.begin(), P.csc_row_idx.end(), csc_row_idx);
+    if (csr_row_ptr) std::copy(P.csr_row_ptr.begin(), P.csr_row_ptr.end(), csr_row_ptr);
+    if (csr_col_idx) std::copy(P.csr_col_idx.begin(), P.csr_col_idx.end(), csr_col_idx);
+    if (cons_row0) std::copy(P.cons_row0.begin(), P.cons_row0.end(), cons_row0);
+    return orc::OK;
+}
+
+// Pattern of lower(A) (by rows == upper by columns) and of L (strictly lower, by rows).  NULL arrays -> sizes.
+int32_t orc_pattern_chol(const orc::Rec* cons, uint32_t n_cons, uint32_t n_vars, uint64_t* nnz_a, uint64_t* nnz_l,
+                         uint32_t* a_row_ptr, uint32_t* a_col, uint32_t* l_row_ptr, uint32_t* l_col) {
+    orc::Pattern P;
+    int32_t rc = orc::build_pattern(cons, n_cons, n_vars, P);
+    if (rc != orc::OK) return rc;
+    orc::Chol ch;
+    ch.analyse(P);
+    *nnz_a = ch.a_col.size();
+    *nnz_l = ch.l_col.size();
+    if (a_row_ptr) std::copy(ch.a_row_ptr.begin(), ch.a_row_ptr.end(), a_row_ptr);
+    if (a_col) std::copy(ch.a_col.begin(), ch.a_col.end(), a_col);
+    if (l_row_ptr) std::copy(ch.l_row_ptr.begin(), ch.l_row_ptr.end(), l_row_ptr);
+    if (l_col) std::copy(ch.l_col.begin(), ch.l_col.end(), l_col);
+    return orc::OK;
+}
+
+// One evaluation: weighted residuals r[m], Jacobian values in CSC order, degenerate flags
+// (bit0 residual, bit1 Jacobian).  Sides are used as given.
+int32_t orc_eval(const orc::Rec* cons, uint32_t n_cons, uint32_t n_vars, const double* x, double* r, double* jac_csc,
+                 uint8_t* degen) {
+    orc::Model M;
+    M.cons = cons;
+    M.param_override = nullptr;
+    M.n_cons = n_cons;
+    int32_t rc = orc::build_pattern(cons, n_cons, n_vars, M.P);
+    if (rc != orc::OK) return rc;
+    M.jvals.assign(M.P.csc_row_idx.size(), 0.0);
+    M.degen_count.assign(n_cons, 0);
+    M.residual(x, r);
+    std::vector<uint32_t> after_res = M.degen_count;
+    M.refresh_jacobian(x);
+    std::copy(M.jvals.begin(), M.jvals.end(), jac_csc);
+    if (degen)
+        for (uint32_t c = 0; c < n_cons; ++c)
+            degen[c] = (uint8_t)((after_res[c] ? 1 : 0) | ((M.degen_count[c] - after_res[c]) ? 2 : 0));
+    return orc::OK;
+}
+
+// One damped step at x: returns A (lower, by rows), L (strict lower by rows + diag) and d.  For debugging parity.
+int32_t orc_step(const orc::Rec* cons, uint32_t n_cons, uint32_t n_vars, const double* x, double lambda, double* a_val,
+                 double* l_val, double* l_diag, double* d_out, int32_t* factor_ok) {
+    orc::Model M;
+    M.cons = cons;
+    M.param_override = nullptr;
+    M.n_cons = n_cons;
+    int32_t rc = orc::build_pattern(cons, n_cons, n_vars, M.P);
+    if (rc != orc::OK) return rc;
+    M.jvals.assign(M.P.csc_row_idx.size(), 0.0);
+    M.degen_count.assign(n_cons, 0);
+    M.chol.analyse(M.P);
+    std::vector<double> r(M.P.m), d(n_vars);
+    M.residual(x, r.data());
+    M.refresh_jacobian(x);
+    M.chol.assemble(M.jvals, lambda);
+    for (uint32_t j = 0; j < n_vars; ++j) {
+        double acc = 0.0;
+        for (uint32_t e = M.P.csc_col_ptr[j]; e < M.P.csc_col_ptr[j + 1]; ++e)
+            acc = std::fma(M.jvals[e], -r[M.P.csc_row_idx[e]], acc);
+        d[j] = acc;
+    }
+    bool ok = M.chol.factor();
+    *factor_ok = ok ? 1 : 0;
+    if (ok) M.chol.solve(d);
+    if (a_val) std::copy(M.chol.a_val.begin(), M.chol.a_val.end(), a_val);
+    if (l_val) std::copy(M.chol.l_val.begin(), M.chol.l_val.end(), l_val);
+    if (l_diag) std::copy(M.chol.l_diag.begin(), M.chol.l_diag.end(), l_diag);
+    if (d_out) std::copy(d.begin(), d.end(), d_out);
+    return orc::OK;
+}
+
+// CPU baseline: `batch` independent solves of one structure on `nthreads` host threads.
+//   hoist_analysis == 0: every solve repeats Model::new (what the reference does, lib.rs:279);
+//   hoist_analysis == 1: pattern + symbolic analysis done once per thread and reused.
+// status bit0 converged, bit1 unsatisfied, bit2 degenerate.
+int32_t orc_solve_batch(const orc::Rec* cons, uint32_t n_cons, uint32_t n_vars, const orc::Cfg* cfg, uint64_t batch,
+                        const double* guesses, const double* params, double* finals, uint32_t* iterations,
+                        uint8_t* status, uint32_t nthreads, int32_t hoist_analysis) {
+    if (nthreads == 0) nthreads = std::max(1u, std::thread::hardware_concurrency());
+    std::atomic<uint64_t> next(0);
+    std::atomic<int32_t> err(0);
+    auto worker = [&]() {
+        const uint64_t chunk = 64;
+        orc::Model hoisted;
+        bool have_model = false;
+        std::vector<orc::Rec> c(n_cons);
+        for (;;) {
+            uint64_t b0 = next.fetch_add(chunk);
+            if (b0 >= batch) break;
+            uint64_t b1 = std::min(batch, b0 + chunk);
+            for (uint64_t b = b0; b < b1; ++b) {
+                const double* g = guesses + b * n_vars;
+                const double* po = params ? params + b * n_cons : nullptr;
+                std::copy(cons, cons + n_cons, c.begin());
+                for (orc::Rec& r : c) orc::set_from_initial_values(r, g);
+                orc::Outcome o;
+                int32_t rc;
+                if (!hoist_analysis) {
+                    orc::ErrDetail det;
+                    rc = orc::solve_inner(c.data(), nullptr, nullptr, n_cons, nullptr, g, n_vars, po, *cfg, false, o,
+                                          &det, nullptr);
+                } else {
+                    if (!have_model) {
+                        hoisted.n_cons = n_cons;
+                        rc = orc::build_pattern(c.data(), n_cons, n_vars, hoisted.P);
+                        if (rc != orc::OK) { err = rc; return; }
+                        hoisted.jvals.assign(hoisted.P.csc_row_idx.size(), 0.0);
+                        hoisted.chol.analyse(hoisted.P);
+                        have_model = true;
+                    }
+                    hoisted.cons = c.data();
+                    hoisted.param_override = po;
+                    hoisted.degen_count.assign(n_cons, 0);
+                    o.final_values.assign(g, g + n_vars);
+                    rc = hoisted.solve_lm(o.final_values.data(), *cfg, &o.iterations, &o.converged, nullptr);
+                    if (rc == orc::OK) {
+                        for (uint32_t ci = 0; ci < n_cons; ++ci) {
+                            orc::Rec cc = hoisted.effective(ci);
+                            double r[2] = {0.0, 0.0};
+                            bool dg = false;
+                            orc::residual(cc, o.final_values.data(), &r[0], &r[1], &dg);
+                            bool sat = std::fabs(r[0]) < orc::EPSILON;
+                            if (orc::residual_dim(cc) == 2) sat = sat && std::fabs(r[1]) < orc::EPSILON;
+                            if (!sat) o.unsatisfied.push_back(ci);
+                        }
+                        o.degen_count = hoisted.degen_count;
+                    }
+                }
+                if (rc != orc::OK) { err = rc; return; }
+                std::copy(o.final_values.begin(), o.final_values.end(), finals + b * n_vars);
+                iterations[b] = (uint32_t)o.iterations;
+                bool dg = false;
+                for (uint32_t v : o.degen_count) dg = dg || v;
+                status[b] = (uint8_t)((o.converged ? 1 : 0) | (o.unsatisfied.empty() ? 0 : 2) | (dg ? 4 : 0));
+            }
+        }
+    };
+    std::vector<std::thread> th;
+    for (uint32_t t = 1; t < nthreads; ++t) th.emplace_back(worker);
+    worker();
+    for (auto& t : th) t.join();
+    return err.load();
+}
+
+// Scalar functions, exported so tests can compare the device versions bit for bit.
+double orc_fn_hypot(double x, double y) { return orc::orc_hypot(x, y); }
+double orc_fn_sin(double x) { return orc::orc_sin(x); }
+double orc_fn_cos(double x) { return orc::orc_cos(x); }
+double orc_fn_atan2(double y, double x) { return orc::orc_atan2(y, x); }
+uint32_t orc_hardware_threads(void) { return std::max(1u, std::thread::hardware_concurrency()); }
+
+}  // extern "C"
