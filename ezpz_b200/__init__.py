@@ -1,0 +1,676 @@
+"""ezpz_b200 — Python host-side mirror of the `ezpz` crate's public API over libezpz_b200.so.
+
+Names, argument meaning and error behaviour follow the reference (ezpz/src/lib.rs:5-18):
+`Constraint`, `ConstraintRequest`, `Config`, `IdGenerator`, datums, `solve`, `solve_analysis`,
+`textual.Problem` / `ConstraintSystem`.  On top of that, `Structure` and `Context` expose the batched
+device API (one structure analysed once, many problems solved in one launch).
+
+Everything numeric runs on the GPU through the C ABI; there is no CPU path in this package.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import native
+from .native import REC_DTYPE
+
+EPSILON = 1e-4  # ezpz/src/lib.rs:43
+
+# ---- kinds (ezpz/src/constraints.rs:37-93) --------------------------------------------------------
+(K_LINE_TANGENT_TO_CIRCLE, K_CIRCLE_TANGENT_TO_CIRCLE, K_DISTANCE, K_DISTANCE_VAR, K_VERTICAL_DISTANCE,
+ K_HORIZONTAL_DISTANCE, K_VERTICAL, K_HORIZONTAL, K_LINES_AT_ANGLE, K_FIXED, K_SCALAR_EQUAL,
+ K_POINTS_COINCIDENT, K_CIRCLE_RADIUS, K_LINES_EQUAL_LENGTH, K_ARC_RADIUS, K_ARC, K_MIDPOINT,
+ K_POINT_LINE_DISTANCE, K_VERTICAL_POINT_LINE_DISTANCE, K_HORIZONTAL_POINT_LINE_DISTANCE, K_SYMMETRIC,
+ K_POINT_ARC_COINCIDENT, K_ARC_LENGTH, K_ARC_ANGLE, K_POINTS_AT_ANGLE) = range(25)
+
+KIND_NAMES = ["LineTangentToCircle", "CircleTangentToCircle", "Distance", "DistanceVar", "VerticalDistance",
+              "HorizontalDistance", "Vertical", "Horizontal", "LinesAtAngle", "Fixed", "ScalarEqual",
+              "PointsCoincident", "CircleRadius", "LinesEqualLength", "ArcRadius", "Arc", "Midpoint",
+              "PointLineDistance", "VerticalPointLineDistance", "HorizontalPointLineDistance", "Symmetric",
+              "PointArcCoincident", "ArcLength", "ArcAngle", "PointsAtAngle"]
+ROWS = [1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 2, 1, 1, 2, 1, 2, 1, 1, 1, 2, 2, 2, 1, 2]  # residual_dim
+
+
+class LineSide:
+    Undefined, Left, Right = 0, 1, 2
+
+
+class CircleSide:
+    Undefined, Exterior, Interior = 0, 1, 2
+
+
+# ---- datums (ezpz/src/datatypes/inputs.rs, id.rs) -------------------------------------------------
+class IdGenerator:
+    def __init__(self):
+        self.next = 0
+
+    def next_id(self):
+        out = self.next
+        self.next += 1
+        return out
+
+
+class DatumDistance:
+    def __init__(self, id):
+        self.id = id
+
+    def all_variables(self):
+        return [self.id]
+
+
+class DatumPoint:
+    def __init__(self, ids=None, x_id=None, y_id=None):
+        if isinstance(ids, IdGenerator):
+            self.x_id, self.y_id = ids.next_id(), ids.next_id()
+        else:
+            self.x_id, self.y_id = x_id, y_id
+
+    @staticmethod
+    def new_xy(x, y):
+        return DatumPoint(x_id=x, y_id=y)
+
+    def id_x(self):
+        return self.x_id
+
+    def id_y(self):
+        return self.y_id
+
+    def all_variables(self):
+        return [self.x_id, self.y_id]
+
+
+class DatumLineSegment:
+    def __init__(self, p0, p1):
+        self.p0, self.p1 = p0, p1
+
+    def all_variables(self):
+        return self.p0.all_variables() + self.p1.all_variables()
+
+
+class DatumCircle:
+    def __init__(self, center, radius):
+        self.center, self.radius = center, radius
+
+    def all_variables(self):
+        return self.center.all_variables() + [self.radius.id]
+
+
+class DatumCircularArc:
+    def __init__(self, center, start, end):
+        self.center, self.start, self.end = center, start, end
+
+    def all_variables(self):  # start, end, CENTER (inputs.rs:183-192)
+        return self.start.all_variables() + self.end.all_variables() + self.center.all_variables()
+
+
+class Angle:  # datatypes.rs:31-89
+    def __init__(self, val, degrees):
+        self.val, self.degrees = float(val), degrees
+
+    @staticmethod
+    def from_degrees(d):
+        return Angle(d, True)
+
+    @staticmethod
+    def from_radians(r):
+        return Angle(r, False)
+
+    def to_degrees(self):
+        return self.val if self.degrees else self.val * (180.0 / math.pi)
+
+    def to_radians(self):
+        return self.val * (math.pi / 180.0) if self.degrees else self.val
+
+    def __str__(self):
+        return f"{self.val}deg" if self.degrees else f"{self.val}rad"
+
+
+class AngleKind:
+    PARALLEL, PERPENDICULAR, OTHER = 0, 1, 2
+
+    def __init__(self, kind, angle=None):
+        self.kind, self.angle = kind, angle
+
+    @staticmethod
+    def Parallel():
+        return AngleKind(AngleKind.PARALLEL)
+
+    @staticmethod
+    def Perpendicular():
+        return AngleKind(AngleKind.PERPENDICULAR)
+
+    @staticmethod
+    def Other(angle):
+        return AngleKind(AngleKind.OTHER, angle)
+
+
+def angle_sincos(radians):
+    """(sin, cos) with the bits of libm::sincos (Rotation2::from_angle_radians, vector.rs:116-120)."""
+    s, c = C.c_double(), C.c_double()
+    native.lib().ezpz_b200_angle_sincos(radians, C.byref(s), C.byref(c))
+    return s.value, c.value
+
+
+def _rot(kind):  # rotation_for_angle_kind (constraints.rs:2641-2647) -> (flags, cos, sin)
+    if kind.kind == AngleKind.PARALLEL:
+        return 0, 1.0, 0.0
+    if kind.kind == AngleKind.PERPENDICULAR:
+        return 1, 0.0, 1.0
+    s, c = angle_sincos(kind.angle.to_radians())
+    return 2, c, s
+
+
+class Constraint:
+    """One constraint in the flat 64-byte form (include/ezpz_b200.h).  Constructors are named after the
+    variants of `enum Constraint` and take the same arguments in the same order."""
+
+    def __init__(self, kind, ids, p0=0.0, p1=0.0, flags=0, angle=None):
+        self.kind, self.ids, self.p0, self.p1, self.flags = kind, list(ids), float(p0), float(p1), flags
+        self.angle = angle  # kept for the lint
+
+    def residual_dim(self):
+        return ROWS[self.kind]
+
+    def constraint_kind(self):
+        return KIND_NAMES[self.kind]
+
+    def __repr__(self):
+        return f"{KIND_NAMES[self.kind]}(ids={self.ids}, p0={self.p0}, p1={self.p1}, flags={self.flags})"
+
+    # -- variants
+    @staticmethod
+    def LineTangentToCircle(line, circle, side=LineSide.Undefined):
+        return Constraint(K_LINE_TANGENT_TO_CIRCLE, line.all_variables() + circle.all_variables(), flags=side)
+
+    @staticmethod
+    def CircleTangentToCircle(a, b, side=CircleSide.Undefined):
+        return Constraint(K_CIRCLE_TANGENT_TO_CIRCLE, a.all_variables() + b.all_variables(), flags=side)
+
+    @staticmethod
+    def Distance(p0, p1, d):
+        return Constraint(K_DISTANCE, p0.all_variables() + p1.all_variables(), d)
+
+    @staticmethod
+    def DistanceVar(p, q, d):
+        return Constraint(K_DISTANCE_VAR, p.all_variables() + q.all_variables() + [d.id])
+
+    @staticmethod
+    def VerticalDistance(p0, p1, d):
+        return Constraint(K_VERTICAL_DISTANCE, p0.all_variables() + p1.all_variables(), d)
+
+    @staticmethod
+    def HorizontalDistance(p0, p1, d):
+        return Constraint(K_HORIZONTAL_DISTANCE, p0.all_variables() + p1.all_variables(), d)
+
+    @staticmethod
+    def Vertical(line):
+        return Constraint(K_VERTICAL, line.all_variables())
+
+    @staticmethod
+    def Horizontal(line):
+        return Constraint(K_HORIZONTAL, line.all_variables())
+
+    @staticmethod
+    def LinesAtAngle(l0, l1, kind):
+        f, c, s = _rot(kind)
+        return Constraint(K_LINES_AT_ANGLE, l0.all_variables() + l1.all_variables(), c, s, f, angle=kind.angle)
+
+    @staticmethod
+    def Fixed(id, v):
+        return Constraint(K_FIXED, [id], v)
+
+    @staticmethod
+    def ScalarEqual(a, b):
+        return Constraint(K_SCALAR_EQUAL, [a, b])
+
+    @staticmethod
+    def PointsCoincident(p0, p1):
+        return Constraint(K_POINTS_COINCIDENT, p0.all_variables() + p1.all_variables())
+
+    @staticmethod
+    def CircleRadius(circle, r):
+        return Constraint(K_CIRCLE_RADIUS, circle.all_variables(), r)
+
+    @staticmethod
+    def LinesEqualLength(l0, l1):
+        return Constraint(K_LINES_EQUAL_LENGTH, l0.all_variables() + l1.all_variables())
+
+    @staticmethod
+    def ArcRadius(arc, r):
+        return Constraint(K_ARC_RADIUS, arc.all_variables(), r)
+
+    @staticmethod
+    def Arc(arc):
+        return Constraint(K_ARC, arc.all_variables())
+
+    @staticmethod
+    def Midpoint(line, point):
+        return Constraint(K_MIDPOINT, line.all_variables() + point.all_variables())
+
+    @staticmethod
+    def PointLineDistance(point, line, d):
+        return Constraint(K_POINT_LINE_DISTANCE, point.all_variables() + line.all_variables(), d)
+
+    @staticmethod
+    def VerticalPointLineDistance(point, line, d):
+        return Constraint(K_VERTICAL_POINT_LINE_DISTANCE, point.all_variables() + line.all_variables(), d)
+
+    @staticmethod
+    def HorizontalPointLineDistance(point, line, d):
+        return Constraint(K_HORIZONTAL_POINT_LINE_DISTANCE, point.all_variables() + line.all_variables(), d)
+
+    @staticmethod
+    def Symmetric(line, a, b):
+        return Constraint(K_SYMMETRIC, line.all_variables() + a.all_variables() + b.all_variables())
+
+    @staticmethod
+    def PointArcCoincident(arc, point):
+        return Constraint(K_POINT_ARC_COINCIDENT, arc.all_variables() + point.all_variables())
+
+    @staticmethod
+    def ArcLength(arc, d):
+        return Constraint(K_ARC_LENGTH, arc.all_variables(), d)
+
+    @staticmethod
+    def ArcAngle(arc, angle):
+        s, c = angle_sincos(angle.to_radians())
+        return Constraint(K_ARC_ANGLE, arc.all_variables(), c, s, angle=angle)
+
+    @staticmethod
+    def PointsAtAngle(p0, p1, p2, kind):
+        f, c, s = _rot(kind)
+        return Constraint(K_POINTS_AT_ANGLE, p0.all_variables() + p1.all_variables() + p2.all_variables(), c, s, f,
+                          angle=kind.angle)
+
+    # -- composites (constraints/composite.rs:10-60)
+    @staticmethod
+    def lines_parallel(lines):
+        return Constraint.LinesAtAngle(lines[0], lines[1], AngleKind.Parallel())
+
+    @staticmethod
+    def lines_perpendicular(lines):
+        return Constraint.LinesAtAngle(lines[0], lines[1], AngleKind.Perpendicular())
+
+    @staticmethod
+    def point_bisects_arc(arc, point):
+        return [Constraint.PointArcCoincident(arc, point),
+                Constraint.Symmetric(DatumLineSegment(arc.center, point), arc.start, arc.end)]
+
+    @staticmethod
+    def parallel_lines_distance(lines, distance):
+        return [Constraint.lines_parallel(lines), Constraint.PointLineDistance(lines[0].p0, lines[1], distance)]
+
+    @staticmethod
+    def circle_arc_coincident(circle, arc):
+        return [Constraint.PointsCoincident(circle.center, arc.center),
+                Constraint.LinesEqualLength(DatumLineSegment(arc.center, arc.start),
+                                            DatumLineSegment(arc.center, arc.end))]
+
+
+class ConstraintRequest:  # constraint_request.rs:13-91
+    def __init__(self, constraint, priority=0, weight=1.0):
+        self.constraint, self.priority, self.weight = constraint, priority, weight
+
+    @staticmethod
+    def new(constraint, priority):
+        return ConstraintRequest(constraint, priority)
+
+    @staticmethod
+    def highest_priority(constraint):
+        return ConstraintRequest(constraint, 0)
+
+    def with_weight(self, weight):
+        return ConstraintRequest(self.constraint, self.priority, weight)
+
+
+class Config:  # solver.rs:31-81
+    def __init__(self, max_iterations=35, residual_tolerance=1e-8, step_tolerance=1e-12, initial_lambda=1e-9):
+        self.max_iterations, self.residual_tolerance = max_iterations, residual_tolerance
+        self.step_tolerance, self.initial_lambda = step_tolerance, initial_lambda
+
+    def _with(self, **kw):
+        c = Config(self.max_iterations, self.residual_tolerance, self.step_tolerance, self.initial_lambda)
+        for k, v in kw.items():
+            setattr(c, k, v)
+        return c
+
+    def with_max_iterations(self, v):
+        return self._with(max_iterations=v)
+
+    def with_convergence_tolerance(self, v):
+        return self._with(residual_tolerance=v)
+
+    def with_step_tolerance(self, v):
+        return self._with(step_tolerance=v)
+
+    def with_initial_lambda(self, v):
+        return self._with(initial_lambda=v)
+
+    def _native(self):
+        return native.Config(int(self.max_iterations), float(self.residual_tolerance), float(self.step_tolerance),
+                             float(self.initial_lambda))
+
+
+def records(constraints, weights=None):
+    """list[Constraint] -> contiguous numpy array of 64-byte records."""
+    arr = np.zeros(len(constraints), dtype=REC_DTYPE)
+    for i, c in enumerate(constraints):
+        arr[i]["kind"] = c.kind
+        arr[i]["flags"] = c.flags
+        ids = list(c.ids) + [0] * (8 - len(c.ids))
+        arr[i]["ids"] = ids
+        arr[i]["p0"] = c.p0
+        arr[i]["p1"] = c.p1
+        arr[i]["weight"] = 1.0 if weights is None else weights[i]
+    return arr
+
+
+# ---- errors / outcomes (error.rs, solve_outcome.rs, warnings.rs) ----------------------------------
+class EzpzError(Exception):
+    def __init__(self, status, detail=None):
+        self.status = status
+        self.name = native.status_name(status)
+        self.constraint_id = detail.constraint_id if detail is not None else 0
+        self.variable = detail.variable if detail is not None else 0
+        self.message = detail.message.decode(errors="replace") if detail is not None else ""
+        super().__init__(f"{self.name}: {self.message}")
+
+
+class FailureOutcome(EzpzError):
+    """Err(FailureOutcome{error, warnings, num_vars, num_eqs}) (solve_outcome.rs:136-181)."""
+
+    def __init__(self, status, detail, warnings, num_vars, num_eqs):
+        super().__init__(status, detail)
+        self.warnings, self.num_vars, self.num_eqs = warnings, num_vars, num_eqs
+
+
+class Warning:
+    Degenerate, ShouldBeParallel, ShouldBePerpendicular = 0, 1, 2
+
+    def __init__(self, about_constraint, content, count=1, angle_deg=float("nan")):
+        self.about_constraint, self.content, self.count, self.angle_deg = about_constraint, content, count, angle_deg
+
+    def __repr__(self):
+        names = ["Degenerate", "ShouldBeParallel", "ShouldBePerpendicular"]
+        return f"Warning(about_constraint={self.about_constraint}, {names[self.content]})"
+
+
+class SolveOutcome:
+    def __init__(self, final_values, unsatisfied, iterations, converged, warnings, priority_solved,
+                 underconstrained=None, path_used=0):
+        self.final_values_, self.unsatisfied_ = final_values, unsatisfied
+        self.iterations_, self.converged_ = iterations, converged
+        self.warnings_, self.priority_solved_ = warnings, priority_solved
+        self.underconstrained_ = underconstrained
+        self.path_used = path_used
+
+    def unsatisfied(self):
+        return self.unsatisfied_
+
+    def converged(self):
+        return self.converged_
+
+    def final_values(self):
+        return self.final_values_
+
+    def iterations(self):
+        return self.iterations_
+
+    def warnings(self):
+        return self.warnings_
+
+    def priority_solved(self):
+        return self.priority_solved_
+
+    def is_satisfied(self):
+        return not self.unsatisfied_
+
+    def is_unsatisfied(self):
+        return bool(self.unsatisfied_)
+
+    def final_value_point(self, p):
+        return (self.final_values_[p.id_x()], self.final_values_[p.id_y()])
+
+    def final_value_distance(self, d):
+        return self.final_values_[d.id]
+
+    def final_value_circle(self, c):
+        return {"center": self.final_value_point(c.center), "radius": self.final_values_[c.radius.id]}
+
+    def final_value_arc(self, a):
+        return {"a": self.final_value_point(a.start), "b": self.final_value_point(a.end),
+                "center": self.final_value_point(a.center)}
+
+    # FreedomAnalysis (analysis.rs:22-68)
+    def is_underconstrained(self):
+        return bool(self.underconstrained_)
+
+    def underconstrained(self):
+        return self.underconstrained_
+
+
+# ---- device objects -------------------------------------------------------------------------------
+class Structure:
+    """ezpz_structure_t: one sketch topology analysed once (replaces Model::new per solve)."""
+
+    def __init__(self, recs, n_vars, var_ids=None):
+        L = native.lib()
+        if not isinstance(recs, np.ndarray):
+            recs = records(recs)
+        self.recs = np.ascontiguousarray(recs)
+        self.n_cons, self.n_vars = len(self.recs), int(n_vars)
+        vi = None if var_ids is None else np.ascontiguousarray(var_ids, dtype=np.uint32)
+        h = C.c_void_p()
+        det = native.ErrorDetail()
+        rc = L.ezpz_b200_structure_create(native.ptr(self.recs), self.n_cons, native.ptr(vi), self.n_vars,
+                                          C.byref(h), C.byref(det))
+        if rc != 0:
+            raise EzpzError(rc, det)
+        self.handle = h
+        m, n, nj, na, nl, ncomp = C.c_uint32(), C.c_uint32(), C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint32()
+        L.ezpz_b200_structure_dims(h, C.byref(m), C.byref(n), C.byref(nj), C.byref(na), C.byref(nl), C.byref(ncomp))
+        self.m, self.n, self.nnz, self.nnz_a, self.nnz_l, self.n_components = (m.value, n.value, nj.value, na.value,
+                                                                               nl.value, ncomp.value)
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                native.lib().ezpz_b200_structure_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    def _arr(self, p, count):
+        if count == 0:
+            return np.zeros(0, np.uint32)
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint32)), shape=(count,)).copy()
+
+    def pattern(self):
+        """The parity artefact: sorted, deduplicated pattern of J in CSC and CSR."""
+        a, b, c, d = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+        native.lib().ezpz_b200_structure_pattern(self.handle, C.byref(a), C.byref(b), C.byref(c), C.byref(d))
+        r0 = C.c_void_p()
+        native.lib().ezpz_b200_structure_rows(self.handle, C.byref(r0))
+        return dict(m=self.m, nnz=self.nnz, csc_col_ptr=self._arr(a, self.n + 1), csc_row_idx=self._arr(b, self.nnz),
+                    csr_row_ptr=self._arr(c, self.m + 1), csr_col_idx=self._arr(d, self.nnz),
+                    cons_row0=self._arr(r0, self.n_cons + 1))
+
+    def pattern_a(self):
+        a, b, c, d = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+        native.lib().ezpz_b200_structure_pattern_a(self.handle, C.byref(a), C.byref(b), C.byref(c), C.byref(d))
+        return dict(a_col_ptr=self._arr(a, self.n + 1), a_row_idx=self._arr(b, self.nnz_a),
+                    l_col_ptr=self._arr(c, self.n + 1), l_row_idx=self._arr(d, self.nnz_l))
+
+
+class BatchResult:
+    pass
+
+
+class Context:
+    """ezpz_context_t: one CUDA device + stream + workspace."""
+
+    def __init__(self, device=0):
+        h = C.c_void_p()
+        det = native.ErrorDetail()
+        rc = native.lib().ezpz_b200_context_create(int(device), C.byref(h), C.byref(det))
+        if rc != 0:
+            raise EzpzError(rc, det)
+        self.handle = h
+        self.device = device
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                native.lib().ezpz_b200_context_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    @property
+    def launches(self):
+        return int(native.lib().ezpz_b200_context_launches(self.handle))
+
+    def synchronize(self):
+        native.lib().ezpz_b200_context_synchronize(self.handle)
+
+    def solve_batch(self, st, guesses, params=None, config=None, want_unsat=True, want_degen=False, want_jacobian=False):
+        g = np.ascontiguousarray(guesses, dtype=np.float64).reshape(-1, st.n_vars)
+        B = g.shape[0]
+        cfg = (config or Config())._native()
+        res = BatchResult()
+        res.final_values = np.empty_like(g)
+        res.iterations = np.empty(B, np.uint32)
+        res.status = np.empty(B, np.uint8)
+        uw = (st.n_cons + 31) // 32
+        res.unsat_mask = np.zeros((B, uw), np.uint32) if want_unsat else None
+        res.degen_count = np.zeros((B, st.n_cons), np.uint32) if want_degen else None
+        res.jacobian = np.zeros((B, st.nnz), np.float64) if want_jacobian else None
+        p = None if params is None else np.ascontiguousarray(params, dtype=np.float64)
+        io = native.BatchIO(native.ptr(g), native.ptr(p), native.ptr(res.final_values), native.ptr(res.iterations),
+                            native.ptr(res.status), native.ptr(res.unsat_mask), native.ptr(res.degen_count),
+                            native.ptr(res.jacobian))
+        det = native.ErrorDetail()
+        rc = native.lib().ezpz_b200_solve_batch(self.handle, st.handle, C.byref(cfg), B, C.byref(io), C.byref(det))
+        if rc != 0:
+            raise EzpzError(rc, det)
+        return res
+
+    def solve_batch_device(self, st, io_ptrs, batch, config=None, stream=0):
+        """Device-pointer form.  io_ptrs: dict of int device addresses (guesses, final_values, iterations,
+        status required)."""
+        cfg = (config or Config())._native()
+        io = native.BatchIO(*[C.c_void_p(io_ptrs.get(k) or None) for k in
+                              ("guesses", "params", "final_values", "iterations", "status", "unsat_mask",
+                               "degen_count", "jacobian")])
+        det = native.ErrorDetail()
+        rc = native.lib().ezpz_b200_solve_batch_device(self.handle, st.handle, C.byref(cfg), int(batch), C.byref(io),
+                                                       C.c_void_p(stream or None), C.byref(det))
+        if rc != 0:
+            raise EzpzError(rc, det)
+
+    def solve_one(self, st, guesses, config=None, want_jacobian=False):
+        g = np.ascontiguousarray(guesses, dtype=np.float64)
+        cfg = (config or Config())._native()
+        res = BatchResult()
+        res.final_values = np.empty_like(g)
+        it, status, path, lin = np.zeros(1, np.uint32), np.zeros(1, np.uint8), np.zeros(1, np.int32), np.zeros(1, np.uint32)
+        res.unsat_mask = np.zeros((st.n_cons + 31) // 32, np.uint32)
+        res.degen_count = np.zeros(st.n_cons, np.uint32)
+        res.jacobian = np.zeros(st.nnz, np.float64) if want_jacobian else None
+        io = native.OneIO(native.ptr(g), native.ptr(res.final_values), native.ptr(it), native.ptr(status),
+                          native.ptr(res.unsat_mask), native.ptr(res.degen_count), native.ptr(res.jacobian),
+                          native.ptr(path), native.ptr(lin))
+        det = native.ErrorDetail()
+        rc = native.lib().ezpz_b200_solve_one(self.handle, st.handle, C.byref(cfg), C.byref(io), C.byref(det))
+        if rc != 0:
+            raise EzpzError(rc, det)
+        res.iterations, res.status, res.path_used, res.lin_iters = int(it[0]), int(status[0]), int(path[0]), int(lin[0])
+        res.converged = bool(res.status & 1)
+        res.unsatisfied = [c for c in range(st.n_cons) if res.unsat_mask[c >> 5] >> (c & 31) & 1]
+        return res
+
+    def evaluate(self, st, x):
+        """One residual + Jacobian evaluation through the device assembly kernel (parity/debug entry)."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        r, jc, jr = np.zeros(st.m), np.zeros(st.nnz), np.zeros(st.nnz)
+        dg = np.zeros(st.n_cons, np.uint8)
+        det = native.ErrorDetail()
+        rc = native.lib().ezpz_b200_eval(self.handle, st.handle, native.ptr(x), native.ptr(r), native.ptr(jc),
+                                         native.ptr(jr), native.ptr(dg), C.byref(det))
+        if rc != 0:
+            raise EzpzError(rc, det)
+        return r, jc, jr, dg
+
+    def freedom_analysis(self, st, jacobian):
+        j = np.ascontiguousarray(jacobian, dtype=np.float64).reshape(-1, st.nnz)
+        B = j.shape[0]
+        mask = np.zeros((B, (st.n_vars + 31) // 32), np.uint32)
+        det = native.ErrorDetail()
+        rc = native.lib().ezpz_b200_freedom_analysis(self.handle, st.handle, B, native.ptr(j), native.ptr(mask),
+                                                     C.byref(det))
+        if rc != 0:
+            raise EzpzError(rc, det)
+        return mask
+
+
+_default_ctx = None
+
+
+def default_context():
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = Context(0)
+    return _default_ctx
+
+
+def _solve(reqs, initial_guesses, config, analysis, ctx=None):
+    L = native.lib()
+    cons = [r.constraint for r in reqs]
+    recs = records(cons, [r.weight for r in reqs])
+    n_cons = len(reqs)
+    prios = np.ascontiguousarray([r.priority for r in reqs], dtype=np.uint32)
+    angles = np.full(max(n_cons, 1), np.nan)
+    for i, c in enumerate(cons):
+        if c.kind == K_LINES_AT_ANGLE and c.flags == 2 and c.angle is not None:
+            angles[i] = c.angle.to_degrees()
+    ids = np.ascontiguousarray([g[0] for g in initial_guesses], dtype=np.uint32)
+    vals = np.ascontiguousarray([g[1] for g in initial_guesses], dtype=np.float64)
+    n_vars = len(vals)
+    fv = np.zeros(max(n_vars, 1))
+    un = np.zeros(max(n_cons, 1), np.uint64)
+    uc = np.zeros(max(n_vars, 1), np.uint32)
+    wcap = n_cons * 2 + 8
+    warr = (native.WarningRec * wcap)()
+    out = native.OutcomeRec()
+    out.final_values, out.unsatisfied, out.underconstrained = fv.ctypes.data, un.ctypes.data, uc.ctypes.data
+    out.warnings, out.warnings_cap = C.addressof(warr), wcap
+    det = native.ErrorDetail()
+    cfg = (config or Config())._native()
+    handle = None
+    if n_cons:
+        handle = (ctx or default_context()).handle
+    rc = L.ezpz_b200_solve(handle, native.ptr(recs) if n_cons else None, native.ptr(prios) if n_cons else None,
+                           native.ptr(angles), n_cons, native.ptr(ids) if n_vars else None,
+                           native.ptr(vals) if n_vars else None, n_vars, C.byref(cfg), 1 if analysis else 0,
+                           C.byref(out), C.byref(det))
+    warnings = [Warning(None if warr[k].about_constraint < 0 else int(warr[k].about_constraint), int(warr[k].kind),
+                        int(warr[k].count), warr[k].angle_deg) for k in range(min(out.n_warnings, wcap))]
+    if rc != 0:
+        raise FailureOutcome(rc, det, warnings, out.num_vars, out.num_eqs)
+    return SolveOutcome(fv[:n_vars].copy(), [int(v) for v in un[:out.n_unsatisfied]], int(out.iterations),
+                        bool(out.converged), warnings, int(out.priority_solved),
+                        [int(v) for v in uc[:out.n_underconstrained]] if analysis else None, int(out.path_used))
+
+
+def solve(reqs, initial_guesses, config=None, ctx=None):
+    """ezpz::solve (lib.rs:80-87).  `initial_guesses`: list of (id, value)."""
+    return _solve(reqs, initial_guesses, config, False, ctx)
+
+
+def solve_analysis(reqs, initial_guesses, config=None, ctx=None):
+    """ezpz::solve_analysis (lib.rs:134-144)."""
+    return _solve(reqs, initial_guesses, config, True, ctx)
+
+
+from . import textual  # noqa: E402,F401

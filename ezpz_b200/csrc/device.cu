@@ -1,0 +1,659 @@
+// device.cu — CUDA side of libezpz_b200.so for sm_100a: contexts, device copies of an analysed
+// structure, the batched small-system Levenberg–Marquardt kernel and the assembly kernel.
+//
+// Compile: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false -DEZPZ_NO_FMAD=1 (see
+// __graft_entry__.build()).  -fmad=false because the constraint formulas must round exactly as the
+// reference's Rust does (no contraction); the linear-algebra phases ask for fused multiply-adds
+// explicitly through __fma_rn, following the arithmetic-order spec in DESIGN.md §3.
+//
+// Kernels
+//   lm_small_kernel   one THREAD per problem; the whole LM loop of ezpz/src/solver/newton.rs:29-145 plus
+//                     the post-solve check of ezpz/src/lib.rs:305-327 runs on the device.  Per-problem
+//                     state (x, r, r_next, J values, A/L values, step) lives in shared memory laid out
+//                     [slot][thread] so that a warp's access to one slot is one conflict-free 256-byte
+//                     row.  All threads of a launch share one structure, so the constraint loop and the
+//                     linear-algebra tape (structure.cpp) are warp-uniform: no divergence except in the
+//                     degenerate-geometry branches and in the iteration count.
+//   assemble_kernel   one thread per constraint over a single system in global memory: residuals and
+//                     Jacobian values scattered through precomputed slots (Model::residual +
+//                     Model::refresh_jacobian, ezpz/src/solver.rs:318-440).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "eval.cuh"
+#include "structure.h"
+
+using namespace ezs;
+
+#include "device.h"
+
+namespace {
+
+__constant__ uint8_t c_rows[EZPZ_K_COUNT];
+__constant__ uint8_t c_emit_len[EZPZ_K_COUNT][2];
+
+struct SmallArgs {
+    const DevCons* cons;
+    const uint32_t* tape;
+    const double* guesses;
+    const double* params;
+    double* finals;
+    uint32_t* iterations;
+    uint8_t* status;
+    uint32_t* unsat;
+    uint32_t* degen;
+    double* jac;
+    uint64_t batch;
+    double residual_tolerance, step_tolerance, initial_lambda;
+    uint32_t max_iterations;
+    uint32_t n_cons, n, m, W, X0, R0, RN0, J0, L0, D0, S0, n_ops, unsat_words, nnz;
+};
+
+struct SmemX {
+    const double* p;
+    uint32_t stride;
+    __device__ __forceinline__ double operator()(uint32_t id) const { return p[id * stride]; }
+};
+struct GlobalX {
+    const double* p;
+    __device__ __forceinline__ double operator()(uint32_t id) const { return __ldg(p + id); }
+};
+
+// One pass over all constraints of this thread's problem.
+//   RES: write weight*residual to V[rdst + row] and count Warning::Degenerate of Model::residual
+//   JAC: write the Jacobian values and count Warning::Degenerate of Model::refresh_jacobian
+template <bool RES, bool JAC>
+__device__ __forceinline__ void eval_all(const SmallArgs& a, double* V, uint32_t stride, uint32_t rdst,
+                                         const double* __restrict__ prow, uint32_t* __restrict__ degen_row,
+                                         bool& any_degen) {
+    const SmemX X{V + a.X0 * stride, stride};
+    for (uint32_t c = 0; c < a.n_cons; ++c) {
+        const DevCons& dc = a.cons[c];
+        const uint32_t kind = dc.kind;
+        uint32_t side = dc.flags;
+        if (dc.side_slot != 0xffffffffu) side = (uint32_t)V[(a.S0 + dc.side_slot) * stride];
+        const double p0 = prow ? prow[c] : dc.p0;
+        ezd::EvalOut o;
+        ezd::eval_constraint<JAC>(kind, side, dc.ids, p0, dc.p1, X, o);
+        const double w = dc.weight;
+        const uint32_t rows = c_rows[kind];
+        uint32_t ndeg = 0;
+        if (RES) {
+            V[(rdst + dc.row0) * stride] = w * o.res[0];
+            if (rows == 2) V[(rdst + dc.row0 + 1) * stride] = w * o.res[1];
+            if (o.res_degen) ++ndeg;
+        }
+        if (JAC) {
+            if (o.jac_degen) ++ndeg;
+#pragma unroll
+            for (int row = 0; row < 2; ++row) {
+                if (row < (int)rows) {
+                    const uint32_t len = c_emit_len[kind][row];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        if (k < (int)len) {
+                            const uint32_t s = dc.slot[row][k];
+                            double* dst = V + (a.J0 + (s & ~kAccumulate)) * stride;
+                            if (s & kAccumulate) {
+                                if (o.emit[row]) *dst = *dst + w * o.pd[row][k];
+                            } else {
+                                *dst = o.emit[row] ? 0.0 + w * o.pd[row][k] : 0.0;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        if (ndeg) {
+            any_degen = true;
+            if (degen_row) degen_row[c] += ndeg;
+        }
+    }
+}
+
+// The linear-algebra tape of one LM iteration: A = JtJ + lambda*I, b = -Jt r, A = L Lt, L y = b, Lt d = y.
+// Returns true when a pivot was not positive and finite ("LltError::Numeric", newton.rs:96-99).
+__device__ __forceinline__ bool run_tape(const uint32_t* __restrict__ tape, uint32_t n_ops, double* V,
+                                         uint32_t stride, double lambda) {
+    bool fail = false;
+    const uint32_t* p = tape;
+    for (uint32_t op = 0; op < n_ops; ++op) {
+        const uint32_t h0 = __ldg(p), h1 = __ldg(p + 1);
+        p += 2;
+        const uint32_t dst = h0 & 0xffffu, np = h0 >> 16;
+        const uint32_t fin = h1 & 0xffffu, code = h1 >> 16;
+        double acc = (code & OP_INIT_DST) ? V[dst * stride] : 0.0;
+        if (code & OP_NEGATE) {
+            for (uint32_t i = 0; i < np; ++i) {
+                const uint32_t w = __ldg(p + i);
+                acc = __fma_rn(-V[(w & 0xffffu) * stride], V[(w >> 16) * stride], acc);
+            }
+        } else {
+            for (uint32_t i = 0; i < np; ++i) {
+                const uint32_t w = __ldg(p + i);
+                acc = __fma_rn(V[(w & 0xffffu) * stride], V[(w >> 16) * stride], acc);
+            }
+        }
+        p += np;
+        const uint32_t fk = (code >> OP_FIN_SHIFT) & 3u;
+        if (fk == OP_FIN_LAMBDA) {
+            acc = __dadd_rn(acc, lambda);
+        } else if (fk == OP_FIN_MUL) {
+            acc = __dmul_rn(acc, V[fin * stride]);
+        } else if (fk == OP_FIN_PIVOT) {
+            if (!(acc > 0.0) || !ezm::ez_isfinite(acc)) fail = true;
+            acc = __ddiv_rn(1.0, __dsqrt_rn(acc));
+        }
+        V[dst * stride] = acc;
+    }
+    return fail;
+}
+
+__global__ void __launch_bounds__(256) lm_small_kernel(const SmallArgs a) {
+    extern __shared__ double smem[];
+    const uint32_t stride = blockDim.x;
+    const uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= a.batch) return;  // no block-wide barrier below: every thread owns its shared-memory column
+    double* V = smem + threadIdx.x;
+    const double* __restrict__ prow = a.params ? a.params + b * a.n_cons : nullptr;
+    uint32_t* __restrict__ degen_row = a.degen ? a.degen + b * a.n_cons : nullptr;
+    bool any_degen = false;
+
+    {  // initial guesses (lib.rs:275: values are positional == by id)
+        const double* __restrict__ g = a.guesses + b * a.n;
+        for (uint32_t j = 0; j < a.n; ++j) V[(a.X0 + j) * stride] = g[j];
+    }
+    if (degen_row)
+        for (uint32_t c = 0; c < a.n_cons; ++c) degen_row[c] = 0;
+    {  // Constraint::set_from_initial_values (lib.rs:183-186)
+        const SmemX X{V + a.X0 * stride, stride};
+        for (uint32_t c = 0; c < a.n_cons; ++c) {
+            const DevCons& dc = a.cons[c];
+            if (dc.side_slot != 0xffffffffu)
+                V[(a.S0 + dc.side_slot) * stride] = (double)ezd::resolve_side(dc.kind, dc.flags, dc.ids, X);
+        }
+    }
+
+    // newton.rs:29-145
+    double lambda = a.initial_lambda;
+    eval_all<true, true>(a, V, stride, a.R0, prow, degen_row, any_degen);
+    double S = 0.0;
+    for (uint32_t i = 0; i < a.m; ++i) {
+        const double r = V[(a.R0 + i) * stride];
+        S = S + r * r;
+    }
+    uint32_t iterations = a.max_iterations;
+    bool converged = false;
+    for (uint32_t it = 0; it < a.max_iterations; ++it) {
+        double largest = ezm::ez_abs(V[a.R0 * stride]);
+        for (uint32_t i = 1; i < a.m; ++i) largest = ezm::ez_fmax(largest, ezm::ez_abs(V[(a.R0 + i) * stride]));
+        if (largest <= a.residual_tolerance) {
+            iterations = it;
+            converged = true;
+            break;
+        }
+        if (run_tape(a.tape, a.n_ops, V, stride, lambda)) {
+            lambda *= 10.0;
+            continue;
+        }
+        double step = ezm::ez_abs(V[a.D0 * stride]);
+        for (uint32_t j = 1; j < a.n; ++j) step = ezm::ez_fmax(step, ezm::ez_abs(V[(a.D0 + j) * stride]));
+        for (uint32_t j = 0; j < a.n; ++j) V[(a.X0 + j) * stride] += V[(a.D0 + j) * stride];
+        eval_all<true, false>(a, V, stride, a.RN0, prow, degen_row, any_degen);
+        double S2 = 0.0;
+        for (uint32_t i = 0; i < a.m; ++i) {
+            const double r = V[(a.RN0 + i) * stride];
+            S2 = S2 + r * r;
+        }
+        if (S2 < S) {
+            for (uint32_t i = 0; i < a.m; ++i) V[(a.R0 + i) * stride] = V[(a.RN0 + i) * stride];
+            eval_all<false, true>(a, V, stride, a.R0, prow, degen_row, any_degen);
+            S = S2;
+            lambda *= 0.1;
+        } else {
+            for (uint32_t j = 0; j < a.n; ++j) V[(a.X0 + j) * stride] -= V[(a.D0 + j) * stride];
+            lambda *= 10.0;
+        }
+        if (step <= a.step_tolerance) {
+            iterations = it;
+            converged = true;
+            break;
+        }
+    }
+
+    // lib.rs:305-327: unweighted residuals at the final point, |r| < 1e-4 per component
+    bool any_unsat = false;
+    {
+        const SmemX X{V + a.X0 * stride, stride};
+        uint32_t* __restrict__ urow = a.unsat ? a.unsat + b * a.unsat_words : nullptr;
+        uint32_t word = 0;
+        for (uint32_t c = 0; c < a.n_cons; ++c) {
+            const DevCons& dc = a.cons[c];
+            uint32_t side = dc.flags;
+            if (dc.side_slot != 0xffffffffu) side = (uint32_t)V[(a.S0 + dc.side_slot) * stride];
+            const double p0 = prow ? prow[c] : dc.p0;
+            ezd::EvalOut o;
+            ezd::eval_constraint<false>(dc.kind, side, dc.ids, p0, dc.p1, X, o);
+            bool sat = ezm::ez_abs(o.res[0]) < ezd::kEps;
+            if (c_rows[dc.kind] == 2) sat = sat && (ezm::ez_abs(o.res[1]) < ezd::kEps);
+            if (!sat) {
+                any_unsat = true;
+                word |= 1u << (c & 31u);
+            }
+            if ((c & 31u) == 31u || c + 1 == a.n_cons) {
+                if (urow) urow[c >> 5] = word;
+                word = 0;
+            }
+        }
+    }
+    {
+        double* __restrict__ f = a.finals + b * a.n;
+        for (uint32_t j = 0; j < a.n; ++j) f[j] = V[(a.X0 + j) * stride];
+    }
+    if (a.jac) {  // Jacobian cached at the last accepted point (what freedom_analysis reads)
+        double* __restrict__ jo = a.jac + b * a.nnz;
+        for (uint32_t k = 0; k < a.nnz; ++k) jo[k] = V[(a.J0 + k) * stride];
+    }
+    a.iterations[b] = iterations;
+    a.status[b] = (uint8_t)((converged ? EZPZ_ST_CONVERGED : 0u) | (any_unsat ? EZPZ_ST_UNSATISFIED : 0u) |
+                            (any_degen ? EZPZ_ST_DEGENERATE : 0u));
+}
+
+// ---- assembly over one system in global memory ----------------------------------------------------
+struct AsmArgs {
+    const DevCons* cons;
+    const double* x;
+    double* r;        // [m] weighted residuals, or nullptr
+    double* jvals;    // [nnz] CSC order, or nullptr
+    uint8_t* degen;   // [n_cons] bit0 residual, bit1 Jacobian, or nullptr
+    uint32_t n_cons;
+};
+
+template <bool JAC>
+__global__ void __launch_bounds__(256) assemble_kernel(const AsmArgs a) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= a.n_cons) return;
+    const DevCons dc = a.cons[c];
+    const GlobalX X{a.x};
+    const uint32_t side = ezd::resolve_side(dc.kind, dc.flags, dc.ids, X);
+    ezd::EvalOut o;
+    ezd::eval_constraint<JAC>(dc.kind, side, dc.ids, dc.p0, dc.p1, X, o);
+    const uint32_t rows = c_rows[dc.kind];
+    const double w = dc.weight;
+    if (a.r) {
+        a.r[dc.row0] = w * o.res[0];
+        if (rows == 2) a.r[dc.row0 + 1] = w * o.res[1];
+    }
+    if (JAC && a.jvals) {
+#pragma unroll
+        for (int row = 0; row < 2; ++row) {
+            if (row < (int)rows) {
+                const uint32_t len = c_emit_len[dc.kind][row];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    if (k < (int)len) {
+                        const uint32_t s = dc.slot[row][k];
+                        double* dst = a.jvals + (s & ~kAccumulate);
+                        if (s & kAccumulate) {
+                            if (o.emit[row]) *dst = *dst + w * o.pd[row][k];
+                        } else {
+                            *dst = o.emit[row] ? 0.0 + w * o.pd[row][k] : 0.0;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if (a.degen) a.degen[c] = (uint8_t)((o.res_degen ? 1 : 0) | ((JAC && o.jac_degen) ? 2 : 0));
+}
+
+__global__ void permute_kernel(const double* __restrict__ src, const uint32_t* __restrict__ perm, double* __restrict__ dst,
+                               uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[perm[i]] = src[i];
+}
+
+int32_t upload_tables(ezpz_error_detail_t* detail) {
+    uint8_t rows[EZPZ_K_COUNT], emit_len[EZPZ_K_COUNT][2];
+    for (int k = 0; k < EZPZ_K_COUNT; ++k) {
+        rows[k] = ezk::kKinds[k].rows;
+        emit_len[k][0] = ezk::kKinds[k].emit_len[0];
+        emit_len[k][1] = ezk::kKinds[k].emit_len[1];
+    }
+    EZ_CUDA(cudaMemcpyToSymbol(c_rows, rows, sizeof rows), "cudaMemcpyToSymbol(c_rows)");
+    EZ_CUDA(cudaMemcpyToSymbol(c_emit_len, emit_len, sizeof emit_len), "cudaMemcpyToSymbol(c_emit_len)");
+    return EZPZ_OK;
+}
+
+}  // namespace
+
+namespace ezs {
+
+int32_t cuda_fail(cudaError_t e, ezpz_error_detail_t* detail, const char* what) {
+    if (detail) {
+        detail->a = (uint64_t)e;
+        std::snprintf(detail->message, sizeof detail->message, "%s: %s", what, cudaGetErrorString(e));
+    }
+    if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver || e == cudaErrorInvalidDevice) return EZPZ_ERR_NO_DEVICE;
+    return EZPZ_ERR_CUDA;
+}
+
+int32_t get_device_copy(ezpz_context* ctx, const ezpz_structure* cs, DeviceCopy** out, ezpz_error_detail_t* detail) {
+    ezpz_structure* s = const_cast<ezpz_structure*>(cs);
+    std::lock_guard<std::mutex> lock(s->dev_mutex);
+    for (DeviceCopy* d : s->dev)
+        if (d->device == ctx->device) {
+            *out = d;
+            return EZPZ_OK;
+        }
+    DeviceCopy* d = new (std::nothrow) DeviceCopy();
+    if (!d) return EZPZ_ERR_INVALID_ARGUMENT;
+    d->device = ctx->device;
+    EZ_CUDA(cudaSetDevice(ctx->device), "cudaSetDevice");
+    if (s->n_cons) {
+        EZ_CUDA(cudaMalloc(&d->cons, sizeof(DevCons) * s->n_cons), "cudaMalloc(cons)");
+        EZ_CUDA(cudaMemcpy(d->cons, s->dev_cons.data(), sizeof(DevCons) * s->n_cons, cudaMemcpyHostToDevice), "cudaMemcpy(cons)");
+    }
+    if (s->small.valid && !s->small.tape.empty()) {
+        EZ_CUDA(cudaMalloc(&d->tape, sizeof(uint32_t) * s->small.tape.size()), "cudaMalloc(tape)");
+        EZ_CUDA(cudaMemcpy(d->tape, s->small.tape.data(), sizeof(uint32_t) * s->small.tape.size(), cudaMemcpyHostToDevice),
+                "cudaMemcpy(tape)");
+    }
+    if (!s->csc_to_csr.empty()) {
+        EZ_CUDA(cudaMalloc(&d->csc_to_csr, sizeof(uint32_t) * s->csc_to_csr.size()), "cudaMalloc(perm)");
+        EZ_CUDA(cudaMemcpy(d->csc_to_csr, s->csc_to_csr.data(), sizeof(uint32_t) * s->csc_to_csr.size(), cudaMemcpyHostToDevice),
+                "cudaMemcpy(perm)");
+    }
+    s->dev.push_back(d);
+    *out = d;
+    return EZPZ_OK;
+}
+
+int32_t ensure_ws(ezpz_context* ctx, size_t bytes, ezpz_error_detail_t* detail) {
+    if (bytes <= ctx->ws_bytes) return EZPZ_OK;
+    if (ctx->ws) cudaFree(ctx->ws);
+    ctx->ws = nullptr;
+    ctx->ws_bytes = 0;
+    size_t want = std::max(bytes, (size_t)1 << 20);
+    EZ_CUDA(cudaMalloc(&ctx->ws, want), "cudaMalloc(workspace)");
+    ctx->ws_bytes = want;
+    return EZPZ_OK;
+}
+
+void release_device_copies(ezpz_structure* s) {
+    std::lock_guard<std::mutex> lock(s->dev_mutex);
+    for (DeviceCopy* d : s->dev) {
+        if (cudaSetDevice(d->device) == cudaSuccess) {
+            if (d->cons) cudaFree(d->cons);
+            if (d->tape) cudaFree(d->tape);
+            if (d->csc_to_csr) cudaFree(d->csc_to_csr);
+            if (d->large) release_large(d);
+        }
+        delete d;
+    }
+    s->dev.clear();
+}
+}  // namespace ezs
+
+extern "C" {
+
+int32_t ezpz_b200_context_create(int32_t device, ezpz_context_t** out, ezpz_error_detail_t* detail) {
+    if (!out) return EZPZ_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    if (detail) std::memset(detail, 0, sizeof *detail);
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess) return cuda_fail(e, detail, "cudaGetDeviceCount");
+    if (count == 0 || device < 0 || device >= count) {
+        if (detail) std::snprintf(detail->message, sizeof detail->message, "no CUDA device %d (found %d)", device, count);
+        return EZPZ_ERR_NO_DEVICE;
+    }
+    EZ_CUDA(cudaSetDevice(device), "cudaSetDevice");
+    ezpz_context* ctx = new (std::nothrow) ezpz_context();
+    if (!ctx) return EZPZ_ERR_INVALID_ARGUMENT;
+    ctx->device = device;
+    int v = 0;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device);
+    ctx->sm_count = v;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    ctx->smem_optin = (size_t)v;
+    e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        delete ctx;
+        return cuda_fail(e, detail, "cudaStreamCreate");
+    }
+    int32_t rc = upload_tables(detail);
+    if (rc != EZPZ_OK) {
+        cudaStreamDestroy(ctx->stream);
+        delete ctx;
+        return rc;
+    }
+    e = cudaFuncSetAttribute(lm_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
+    if (e != cudaSuccess) {
+        cudaStreamDestroy(ctx->stream);
+        delete ctx;
+        return cuda_fail(e, detail, "cudaFuncSetAttribute(lm_small_kernel)");
+    }
+    *out = ctx;
+    return EZPZ_OK;
+}
+
+void ezpz_b200_context_destroy(ezpz_context_t* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaStreamDestroy(ctx->stream);
+    }
+    if (ctx->ws) cudaFree(ctx->ws);
+    delete ctx;
+}
+
+uint64_t ezpz_b200_context_launches(const ezpz_context_t* ctx) { return ctx ? ctx->launches : 0; }
+
+int32_t ezpz_b200_context_synchronize(ezpz_context_t* ctx) {
+    if (!ctx) return EZPZ_ERR_INVALID_ARGUMENT;
+    ezpz_error_detail_t* detail = nullptr;
+    EZ_CUDA(cudaStreamSynchronize(ctx->stream), "cudaStreamSynchronize");
+    return EZPZ_OK;
+}
+
+int32_t ezpz_b200_solve_batch_device(ezpz_context_t* ctx, const ezpz_structure_t* s, const ezpz_config_t* config,
+                                     uint64_t batch, const ezpz_batch_io_t* io, void* cuda_stream,
+                                     ezpz_error_detail_t* detail) {
+    if (!ctx || !s || !config || !io) return EZPZ_ERR_INVALID_ARGUMENT;
+    if (detail) std::memset(detail, 0, sizeof *detail);
+    if (batch == 0) return EZPZ_OK;
+    if (!io->guesses || !io->final_values || !io->iterations || !io->status) return EZPZ_ERR_INVALID_ARGUMENT;
+    if (s->n_cons == 0 || s->m == 0) return EZPZ_ERR_EMPTY_SYSTEM;
+    if (!s->small.valid) {
+        if (detail)
+            std::snprintf(detail->message, sizeof detail->message,
+                          "system too large for the batched thread-per-problem kernel (needs %llu doubles per problem)",
+                          (unsigned long long)((uint64_t)s->n + 2ull * s->m + s->csc_row_idx.size() + s->l_row_idx.size() + s->n));
+        return EZPZ_ERR_TOO_LARGE;
+    }
+    EZ_CUDA(cudaSetDevice(ctx->device), "cudaSetDevice");
+    DeviceCopy* dc = nullptr;
+    int32_t rc = get_device_copy(ctx, s, &dc, detail);
+    if (rc != EZPZ_OK) return rc;
+    const SmallProgram& P = s->small;
+    SmallArgs a;
+    a.cons = dc->cons;
+    a.tape = dc->tape;
+    a.guesses = io->guesses;
+    a.params = io->params;
+    a.finals = io->final_values;
+    a.iterations = io->iterations;
+    a.status = io->status;
+    a.unsat = io->unsat_mask;
+    a.degen = io->degen_count;
+    a.jac = io->jacobian;
+    a.nnz = (uint32_t)s->csc_row_idx.size();
+    a.batch = batch;
+    a.residual_tolerance = config->residual_tolerance;
+    a.step_tolerance = config->step_tolerance;
+    a.initial_lambda = config->initial_lambda;
+    a.max_iterations = (uint32_t)std::min<uint64_t>(config->max_iterations, 0x7fffffffu);
+    a.n_cons = s->n_cons;
+    a.n = s->n;
+    a.m = s->m;
+    a.W = P.W;
+    a.X0 = P.X0;
+    a.R0 = P.R0;
+    a.RN0 = P.RN0;
+    a.J0 = P.J0;
+    a.L0 = P.L0;
+    a.D0 = P.D0;
+    a.S0 = P.S0;
+    a.n_ops = P.n_ops;
+    a.unsat_words = (s->n_cons + 31) / 32;
+    // threads per block: as many problems as fit the shared memory of one SM, in whole warps, at most 256
+    const size_t per_thread = (size_t)P.W * sizeof(double);
+    uint32_t T = (uint32_t)std::min<size_t>(256, ctx->smem_optin / per_thread);
+    T = T / 32 * 32;
+    if (T < 32) return EZPZ_ERR_TOO_LARGE;
+    if (batch < T) T = (uint32_t)((batch + 31) / 32 * 32);
+    const size_t smem = per_thread * T;
+    const uint64_t grid = (batch + T - 1) / T;
+    if (grid > 0x7fffffffull) return EZPZ_ERR_TOO_LARGE;
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+    lm_small_kernel<<<(unsigned)grid, T, smem, st>>>(a);
+    ctx->launches += 1;
+    EZ_CUDA(cudaGetLastError(), "lm_small_kernel launch");
+    return EZPZ_OK;
+}
+
+int32_t ezpz_b200_solve_batch(ezpz_context_t* ctx, const ezpz_structure_t* s, const ezpz_config_t* config,
+                              uint64_t batch, const ezpz_batch_io_t* io, ezpz_error_detail_t* detail) {
+    if (!ctx || !s || !config || !io) return EZPZ_ERR_INVALID_ARGUMENT;
+    if (detail) std::memset(detail, 0, sizeof *detail);
+    if (batch == 0) return EZPZ_OK;
+    if (!io->guesses || !io->final_values || !io->iterations || !io->status) return EZPZ_ERR_INVALID_ARGUMENT;
+    EZ_CUDA(cudaSetDevice(ctx->device), "cudaSetDevice");
+    const size_t n = s->n, nc = s->n_cons, uw = (s->n_cons + 31) / 32;
+    const size_t b_x = align_up(batch * n * sizeof(double), 256);
+    const size_t b_p = io->params ? align_up(batch * nc * sizeof(double), 256) : 0;
+    const size_t b_it = align_up(batch * sizeof(uint32_t), 256);
+    const size_t b_st = align_up(batch, 256);
+    const size_t b_un = io->unsat_mask ? align_up(batch * uw * sizeof(uint32_t), 256) : 0;
+    const size_t b_dg = io->degen_count ? align_up(batch * nc * sizeof(uint32_t), 256) : 0;
+    const size_t nnz = s->csc_row_idx.size();
+    const size_t b_jc = io->jacobian ? align_up(batch * nnz * sizeof(double), 256) : 0;
+    int32_t rc = ensure_ws(ctx, 2 * b_x + b_p + b_it + b_st + b_un + b_dg + b_jc, detail);
+    if (rc != EZPZ_OK) return rc;
+    char* w = (char*)ctx->ws;
+    double* d_g = (double*)w; w += b_x;
+    double* d_f = (double*)w; w += b_x;
+    double* d_p = io->params ? (double*)w : nullptr; w += b_p;
+    uint32_t* d_it = (uint32_t*)w; w += b_it;
+    uint8_t* d_st = (uint8_t*)w; w += b_st;
+    uint32_t* d_un = io->unsat_mask ? (uint32_t*)w : nullptr; w += b_un;
+    uint32_t* d_dg = io->degen_count ? (uint32_t*)w : nullptr; w += b_dg;
+    double* d_jc = io->jacobian ? (double*)w : nullptr; w += b_jc;
+    cudaStream_t st = ctx->stream;
+    EZ_CUDA(cudaMemcpyAsync(d_g, io->guesses, batch * n * sizeof(double), cudaMemcpyHostToDevice, st), "H2D guesses");
+    if (d_p) EZ_CUDA(cudaMemcpyAsync(d_p, io->params, batch * nc * sizeof(double), cudaMemcpyHostToDevice, st), "H2D params");
+    ezpz_batch_io_t dio;
+    dio.guesses = d_g;
+    dio.params = d_p;
+    dio.final_values = d_f;
+    dio.iterations = d_it;
+    dio.status = d_st;
+    dio.unsat_mask = d_un;
+    dio.degen_count = d_dg;
+    dio.jacobian = d_jc;
+    rc = ezpz_b200_solve_batch_device(ctx, s, config, batch, &dio, st, detail);
+    if (rc != EZPZ_OK) return rc;
+    EZ_CUDA(cudaMemcpyAsync(io->final_values, d_f, batch * n * sizeof(double), cudaMemcpyDeviceToHost, st), "D2H finals");
+    EZ_CUDA(cudaMemcpyAsync(io->iterations, d_it, batch * sizeof(uint32_t), cudaMemcpyDeviceToHost, st), "D2H iterations");
+    EZ_CUDA(cudaMemcpyAsync(io->status, d_st, batch, cudaMemcpyDeviceToHost, st), "D2H status");
+    if (d_un) EZ_CUDA(cudaMemcpyAsync(io->unsat_mask, d_un, batch * uw * sizeof(uint32_t), cudaMemcpyDeviceToHost, st), "D2H unsat");
+    if (d_dg) EZ_CUDA(cudaMemcpyAsync(io->degen_count, d_dg, batch * nc * sizeof(uint32_t), cudaMemcpyDeviceToHost, st), "D2H degen");
+    if (d_jc) EZ_CUDA(cudaMemcpyAsync(io->jacobian, d_jc, batch * nnz * sizeof(double), cudaMemcpyDeviceToHost, st), "D2H jacobian");
+    EZ_CUDA(cudaStreamSynchronize(st), "cudaStreamSynchronize");
+    return EZPZ_OK;
+}
+
+int32_t ezpz_b200_solve_one(ezpz_context_t* ctx, const ezpz_structure_t* s, const ezpz_config_t* config,
+                            const ezpz_one_io_t* io, ezpz_error_detail_t* detail) {
+    if (!ctx || !s || !config || !io) return EZPZ_ERR_INVALID_ARGUMENT;
+    if (detail) std::memset(detail, 0, sizeof *detail);
+    if (!io->guesses || !io->final_values || !io->iterations || !io->status) return EZPZ_ERR_INVALID_ARGUMENT;
+    if (io->lin_iters) *io->lin_iters = 0;
+    if (s->small.valid) {
+        ezpz_batch_io_t b;
+        b.guesses = io->guesses;
+        b.params = nullptr;
+        b.final_values = io->final_values;
+        b.iterations = io->iterations;
+        b.status = io->status;
+        b.unsat_mask = io->unsat_mask;
+        b.degen_count = io->degen_count;
+        b.jacobian = io->jacobian;
+        if (io->path_used) *io->path_used = 0;
+        return ezpz_b200_solve_batch(ctx, s, config, 1, &b, detail);
+    }
+    return ezs::solve_large(ctx, s, config, io, detail);
+}
+
+int32_t ezpz_b200_eval(ezpz_context_t* ctx, const ezpz_structure_t* s, const double* x, double* r, double* jac_csc,
+                       double* jac_csr, uint8_t* degen, ezpz_error_detail_t* detail) {
+    if (!ctx || !s || !x) return EZPZ_ERR_INVALID_ARGUMENT;
+    if (detail) std::memset(detail, 0, sizeof *detail);
+    if (s->n_cons == 0) return EZPZ_OK;
+    EZ_CUDA(cudaSetDevice(ctx->device), "cudaSetDevice");
+    DeviceCopy* dc = nullptr;
+    int32_t rc = get_device_copy(ctx, s, &dc, detail);
+    if (rc != EZPZ_OK) return rc;
+    const size_t n = s->n, m = s->m, nnz = s->csc_row_idx.size(), nc = s->n_cons;
+    const size_t b_x = align_up(n * 8, 256), b_r = align_up(m * 8, 256), b_j = align_up(nnz * 8, 256), b_d = align_up(nc, 256);
+    rc = ensure_ws(ctx, b_x + b_r + 2 * b_j + b_d, detail);
+    if (rc != EZPZ_OK) return rc;
+    char* w = (char*)ctx->ws;
+    double* d_x = (double*)w; w += b_x;
+    double* d_r = (double*)w; w += b_r;
+    double* d_j = (double*)w; w += b_j;
+    double* d_j2 = (double*)w; w += b_j;
+    uint8_t* d_d = (uint8_t*)w;
+    cudaStream_t st = ctx->stream;
+    EZ_CUDA(cudaMemcpyAsync(d_x, x, n * 8, cudaMemcpyHostToDevice, st), "H2D x");
+    AsmArgs a;
+    a.cons = dc->cons;
+    a.x = d_x;
+    a.r = d_r;
+    a.jvals = d_j;
+    a.degen = d_d;
+    a.n_cons = s->n_cons;
+    const unsigned T = 128, grid = (unsigned)((nc + T - 1) / T);
+    assemble_kernel<true><<<grid, T, 0, st>>>(a);
+    ctx->launches += 1;
+    EZ_CUDA(cudaGetLastError(), "assemble_kernel launch");
+    if (r) EZ_CUDA(cudaMemcpyAsync(r, d_r, m * 8, cudaMemcpyDeviceToHost, st), "D2H r");
+    if (jac_csc) EZ_CUDA(cudaMemcpyAsync(jac_csc, d_j, nnz * 8, cudaMemcpyDeviceToHost, st), "D2H jac");
+    if (jac_csr && nnz) {
+        permute_kernel<<<(unsigned)((nnz + 255) / 256), 256, 0, st>>>(d_j, dc->csc_to_csr, d_j2, (uint32_t)nnz);
+        ctx->launches += 1;
+        EZ_CUDA(cudaGetLastError(), "permute_kernel launch");
+        EZ_CUDA(cudaMemcpyAsync(jac_csr, d_j2, nnz * 8, cudaMemcpyDeviceToHost, st), "D2H jac csr");
+    }
+    if (degen) EZ_CUDA(cudaMemcpyAsync(degen, d_d, nc, cudaMemcpyDeviceToHost, st), "D2H degen");
+    EZ_CUDA(cudaStreamSynchronize(st), "cudaStreamSynchronize");
+    return EZPZ_OK;
+}
+
+void ezpz_b200_angle_sincos(double radians, double* sin_out, double* cos_out) {
+    double s, c;
+    ezm::ez_sincos(radians, s, c);
+    if (sin_out) *sin_out = s;
+    if (cos_out) *cos_out = c;
+}
+
+double ezpz_b200_hypot(double x, double y) { return ezm::ez_hypot(x, y); }
+
+}  // extern "C"

@@ -1,0 +1,47 @@
+// device.h — declarations shared by the CUDA translation units of libezpz_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+
+#include "structure.h"
+
+namespace ezs {
+
+// Device-resident copy of an analysed structure (one per CUDA device, created lazily).
+struct DeviceCopy {
+    int device = -1;
+    DevCons* cons = nullptr;         // [n_cons]
+    uint32_t* tape = nullptr;        // small-system op tape
+    uint32_t* csc_to_csr = nullptr;  // [nnz] position in CSR order of each CSC entry
+    void* large = nullptr;           // LargeDevice (large.cu), created on first use
+};
+
+int32_t cuda_fail(cudaError_t e, ezpz_error_detail_t* detail, const char* what);
+int32_t get_device_copy(ezpz_context* ctx, const ezpz_structure* s, DeviceCopy** out, ezpz_error_detail_t* detail);
+int32_t ensure_ws(ezpz_context* ctx, size_t bytes, ezpz_error_detail_t* detail);
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+void release_large(DeviceCopy* d);  // large.cu
+// Single system that does not fit the thread-per-problem kernel (large.cu).
+int32_t solve_large(ezpz_context* ctx, const ezpz_structure* s, const ezpz_config_t* config, const ezpz_one_io_t* io,
+                    ezpz_error_detail_t* detail);
+
+}  // namespace ezs
+
+struct ezpz_context {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int sm_count = 0;
+    size_t smem_optin = 0;
+    uint64_t launches = 0;
+    // grow-only device workspace for the host-buffer entry points
+    void* ws = nullptr;
+    size_t ws_bytes = 0;
+};
+
+#define EZ_CUDA(call, what)                                                \
+    do {                                                                   \
+        cudaError_t e__ = (call);                                          \
+        if (e__ != cudaSuccess) return ezs::cuda_fail(e__, detail, what);  \
+    } while (0)

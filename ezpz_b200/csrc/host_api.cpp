@@ -1,0 +1,216 @@
+// host_api.cpp — ezpz::solve / ezpz::solve_analysis behind the C ABI (ezpz_b200_solve).
+//
+// Host control that surrounds the hot path in the reference and stays host-side here:
+//   * the empty-request short circuit               ezpz/src/lib.rs:155-170
+//   * the priority loop over ascending levels       lib.rs:199-246 (always restarting from the ORIGINAL guesses)
+//   * the static lint                               ezpz/src/warnings.rs:34-59
+//   * result packing (unsatisfied in original request indices, priority_solved, warnings)  lib.rs:333-355
+// Everything numeric — side inference, the LM loop, the unsatisfied check, the freedom analysis — runs on
+// the device through ezpz_b200_structure_create + ezpz_b200_solve_one + ezpz_b200_freedom_analysis.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "../../include/ezpz_b200.h"
+#include "kinds.h"
+
+namespace {
+
+constexpr double kEpsilon = 1e-4;  // lib.rs:43
+bool nearly_eq(double a, double b) { return std::fabs(a - b) < kEpsilon; }  // warnings.rs:85-87
+
+struct Warn {
+    int64_t about;
+    uint32_t kind;
+    uint32_t count;
+    double angle;
+};
+
+struct Level {
+    std::vector<double> finals;
+    std::vector<uint64_t> unsat;
+    std::vector<uint32_t> under;
+    std::vector<Warn> warnings;
+    uint64_t iterations = 0;
+    bool converged = false;
+    uint32_t priority = 0;
+    uint32_t num_vars = 0, num_eqs = 0;
+    int32_t path = 0;
+};
+
+void export_level(const Level& L, ezpz_outcome_t* out) {
+    if (out->final_values && !L.finals.empty()) std::memcpy(out->final_values, L.finals.data(), L.finals.size() * sizeof(double));
+    out->n_unsatisfied = (uint32_t)L.unsat.size();
+    if (out->unsatisfied) std::copy(L.unsat.begin(), L.unsat.end(), out->unsatisfied);
+    out->n_underconstrained = (uint32_t)L.under.size();
+    if (out->underconstrained) std::copy(L.under.begin(), L.under.end(), out->underconstrained);
+    out->n_warnings = (uint32_t)L.warnings.size();
+    if (out->warnings)
+        for (uint32_t k = 0; k < std::min<uint32_t>(out->warnings_cap, out->n_warnings); ++k) {
+            out->warnings[k].about_constraint = L.warnings[k].about;
+            out->warnings[k].kind = L.warnings[k].kind;
+            out->warnings[k].count = L.warnings[k].count;
+            out->warnings[k].angle_deg = L.warnings[k].angle;
+        }
+    out->iterations = L.iterations;
+    out->converged = L.converged ? 1 : 0;
+    out->priority_solved = L.priority;
+    out->num_vars = L.num_vars;
+    out->num_eqs = L.num_eqs;
+    out->path_used = L.path;
+}
+
+// solve_inner (lib.rs:265-356) for one subset.  `ids[k]` = original request index of subset entry k.
+int32_t solve_level(ezpz_context_t* ctx, const std::vector<ezpz_constraint_t>& cons, const std::vector<uint64_t>& ids,
+                    const std::vector<double>& angles, uint32_t level_priority, const uint32_t* var_ids,
+                    const double* guesses, uint32_t n_vars, const ezpz_config_t* config, bool analysis, Level& L,
+                    ezpz_error_detail_t* detail) {
+    const uint32_t nc = (uint32_t)cons.size();
+    L = Level();
+    L.num_vars = n_vars;
+    for (const auto& c : cons) L.num_eqs += ezk::kKinds[c.kind].rows;
+    L.priority = level_priority;
+    // warnings::lint — about_constraint is the ORIGINAL request index (constraint.id)
+    for (uint32_t k = 0; k < nc; ++k) {
+        if (cons[k].kind != EZPZ_K_LINES_AT_ANGLE || cons[k].flags != EZPZ_ANGLE_OTHER) continue;
+        const double deg = angles.empty() ? NAN : angles[k];
+        if (std::isnan(deg)) continue;
+        if (nearly_eq(deg, 0.0) || nearly_eq(deg, 360.0) || nearly_eq(deg, 180.0)) L.warnings.push_back({(int64_t)ids[k], 1u, 1u, deg});
+        else if (nearly_eq(deg, 90.0) || nearly_eq(deg, -90.0)) L.warnings.push_back({(int64_t)ids[k], 2u, 1u, deg});
+    }
+    ezpz_structure_t* S = nullptr;
+    int32_t rc = ezpz_b200_structure_create(cons.data(), nc, var_ids, n_vars, &S, detail);
+    if (rc != EZPZ_OK) {
+        if (rc == EZPZ_ERR_MISSING_GUESS && detail) detail->constraint_id = ids[detail->constraint_id];
+        return rc;
+    }
+    uint64_t nnz = 0;
+    ezpz_b200_structure_dims(S, nullptr, nullptr, &nnz, nullptr, nullptr, nullptr);
+    L.finals.assign(n_vars, 0.0);
+    std::vector<uint32_t> unsat((nc + 31) / 32, 0), degen(nc, 0);
+    std::vector<double> jac(analysis ? nnz : 0);
+    uint32_t iterations = 0;
+    uint8_t status = 0;
+    ezpz_one_io_t io;
+    std::memset(&io, 0, sizeof io);
+    io.guesses = guesses;
+    io.final_values = L.finals.data();
+    io.iterations = &iterations;
+    io.status = &status;
+    io.unsat_mask = unsat.data();
+    io.degen_count = degen.data();
+    io.jacobian = analysis ? jac.data() : nullptr;
+    io.path_used = &L.path;
+    rc = ezpz_b200_solve_one(ctx, S, config, &io, detail);
+    if (rc == EZPZ_OK) {
+        L.iterations = iterations;
+        L.converged = (status & EZPZ_ST_CONVERGED) != 0;
+        // Degenerate warnings: about_constraint is the index inside the current subset (solver.rs:327,343)
+        for (uint32_t k = 0; k < nc; ++k)
+            if (degen[k]) L.warnings.push_back({(int64_t)k, 0u, degen[k], NAN});
+        for (uint32_t k = 0; k < nc; ++k)
+            if (unsat[k >> 5] & (1u << (k & 31u))) L.unsat.push_back(ids[k]);
+        if (status & EZPZ_ST_SOLVE_ERROR) rc = EZPZ_ERR_SOLVE;
+    }
+    if (rc == EZPZ_OK && analysis) {
+        std::vector<uint32_t> mask((n_vars + 31) / 32, 0);
+        rc = ezpz_b200_freedom_analysis(ctx, S, 1, jac.data(), mask.data(), detail);
+        if (rc == EZPZ_OK)
+            for (uint32_t j = 0; j < n_vars; ++j)
+                if (mask[j >> 5] & (1u << (j & 31u))) L.under.push_back(j);
+    }
+    ezpz_b200_structure_destroy(S);
+    return rc;
+}
+
+}  // namespace
+
+extern "C" int32_t ezpz_b200_solve(ezpz_context_t* ctx, const ezpz_constraint_t* cons, const uint32_t* priorities,
+                                   const double* angles_deg, uint32_t n_cons, const uint32_t* var_ids,
+                                   const double* guesses, uint32_t n_vars, const ezpz_config_t* config,
+                                   int32_t analysis, ezpz_outcome_t* outcome, ezpz_error_detail_t* detail) {
+    if (!outcome || !config || (n_vars && !guesses) || (n_cons && !cons)) return EZPZ_ERR_INVALID_ARGUMENT;
+    if (detail) std::memset(detail, 0, sizeof *detail);
+    outcome->n_unsatisfied = outcome->n_underconstrained = outcome->n_warnings = 0;
+    outcome->iterations = 0;
+    outcome->converged = 0;
+    outcome->priority_solved = 0;
+    outcome->num_vars = n_vars;
+    outcome->num_eqs = 0;
+    outcome->path_used = -1;
+    for (uint32_t k = 0; k < n_cons; ++k)
+        if (cons[k].kind >= EZPZ_K_COUNT) return EZPZ_ERR_INVALID_ARGUMENT;
+    if (n_cons == 0) {  // lib.rs:155-170
+        if (outcome->final_values && n_vars) std::memcpy(outcome->final_values, guesses, n_vars * sizeof(double));
+        outcome->converged = 1;
+        return EZPZ_OK;
+    }
+    if (!ctx) return EZPZ_ERR_NO_DEVICE;
+    std::vector<uint32_t> levels;
+    for (uint32_t k = 0; k < n_cons; ++k) levels.push_back(priorities ? priorities[k] : 0u);
+    std::sort(levels.begin(), levels.end());
+    levels.erase(std::unique(levels.begin(), levels.end()), levels.end());
+    // Constraint::set_from_initial_values reads guesses BY ID (lib.rs:172-186).  With ids 0..n-1 the device
+    // resolves Undefined sides itself; with an explicit id list that is not the identity, resolve here so
+    // that the by-id semantics is kept.
+    std::vector<ezpz_constraint_t> all(cons, cons + n_cons);
+    bool identity = true;
+    if (var_ids)
+        for (uint32_t k = 0; k < n_vars; ++k) identity = identity && var_ids[k] == k;
+    if (!identity) {
+        uint32_t max_id = 0;
+        for (uint32_t k = 0; k < n_vars; ++k) max_id = std::max(max_id, var_ids[k]);
+        std::vector<double> by_id((size_t)max_id + 1, 0.0);
+        for (uint32_t k = 0; k < n_vars; ++k) by_id[var_ids[k]] = guesses[k];
+        auto val = [&](uint32_t id) { return id < by_id.size() ? by_id[id] : 0.0; };
+        for (auto& c : all) {
+            if (c.flags != EZPZ_SIDE_UNDEFINED) continue;
+            if (c.kind == EZPZ_K_LINE_TANGENT_TO_CIRCLE) {
+                const double ux = val(c.ids[2]) - val(c.ids[0]), uy = val(c.ids[3]) - val(c.ids[1]);
+                const double vx = val(c.ids[4]) - val(c.ids[0]), vy = val(c.ids[5]) - val(c.ids[1]);
+                c.flags = (ux * vy - uy * vx >= 0.0) ? EZPZ_LINE_SIDE_LEFT : EZPZ_LINE_SIDE_RIGHT;
+            } else if (c.kind == EZPZ_K_CIRCLE_TANGENT_TO_CIRCLE) {
+                const double dist = ezpz_b200_hypot(val(c.ids[0]) - val(c.ids[3]), val(c.ids[1]) - val(c.ids[4]));
+                const double ar = val(c.ids[2]), br = val(c.ids[5]);
+                const double r_int = std::fabs(std::fabs(ar - br) - dist), r_ext = std::fabs(ar + br - dist);
+                c.flags = (r_int < r_ext) ? EZPZ_CIRCLE_SIDE_INTERIOR : EZPZ_CIRCLE_SIDE_EXTERIOR;
+            }
+        }
+    }
+    bool have = false;
+    Level best;
+    for (uint32_t level : levels) {
+        std::vector<ezpz_constraint_t> subset;
+        std::vector<uint64_t> ids;
+        std::vector<double> angles;
+        uint32_t lowest = 0;
+        for (uint32_t k = 0; k < n_cons; ++k) {
+            const uint32_t p = priorities ? priorities[k] : 0u;
+            if (p <= level) {
+                subset.push_back(all[k]);
+                ids.push_back(k);
+                if (angles_deg) angles.push_back(angles_deg[k]);
+                lowest = std::max(lowest, p);
+            }
+        }
+        Level cur;
+        const int32_t rc = solve_level(ctx, subset, ids, angles, lowest, var_ids, guesses, n_vars, config, analysis != 0, cur, detail);
+        if (rc != EZPZ_OK) {  // lib.rs:239-244: fall back to the previous level, else report the error
+            if (have) {
+                export_level(best, outcome);
+                return EZPZ_OK;
+            }
+            export_level(cur, outcome);
+            return rc;
+        }
+        if (!cur.unsat.empty()) {  // lib.rs:228-234
+            export_level(have ? best : cur, outcome);
+            return EZPZ_OK;
+        }
+        best = std::move(cur);
+        have = true;
+    }
+    export_level(best, outcome);
+    return EZPZ_OK;
+}

@@ -1,0 +1,467 @@
+// structure.cpp — host analysis behind ezpz_b200_structure_create (see structure.h).
+//
+// Steps and the reference code each one replaces:
+//   1. validation              validate_variables, ezpz/src/solver.rs:142-189
+//   2. rows + J pattern        Model::new, solver.rs:217-265 (pairs -> sort + dedup -> CSC); CSR = transpose
+//   3. scatter slots           replaces the per-nonzero linear search of refresh_jacobian, solver.rs:412-418
+//   4. pattern of A = JtJ + D  precompute_symbolic_cholesky, solver.rs:289-300 (ones-valued J, JtJ + lambda*I)
+//   5. symbolic Cholesky       SymbolicLlt::try_new (faer, not in tree) -> natural-order elimination-tree
+//                              column merge here (DESIGN.md §3 states the arithmetic-order spec)
+//   6. connected components    of the graph of A (used to choose the large-system path)
+//   7. op tapes                straight-line programme of the batched small-system kernel
+#include "structure.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+
+#include "kinds.h"
+
+using namespace ezs;
+
+namespace {
+
+void set_detail(ezpz_error_detail_t* d, const char* msg) {
+    if (!d) return;
+    std::snprintf(d->message, sizeof d->message, "%s", msg);
+}
+
+// lower(A) by columns from the CSR rows of J: (i, j), i >= j, whenever some row holds both columns.
+void build_a_pattern(ezpz_structure& S) {
+    const uint32_t n = S.n;
+    std::vector<std::vector<uint32_t>> cols(n);
+    for (uint32_t j = 0; j < n; ++j) cols[j].push_back(j);  // lambda*I puts every diagonal in
+    for (uint32_t r = 0; r < S.m; ++r) {
+        const uint32_t b = S.csr_row_ptr[r], e = S.csr_row_ptr[r + 1];
+        for (uint32_t p = b; p < e; ++p)
+            for (uint32_t q = p; q < e; ++q) cols[S.csr_col_idx[p]].push_back(S.csr_col_idx[q]);  // col p <= col q
+    }
+    S.a_col_ptr.assign(n + 1, 0);
+    S.a_row_idx.clear();
+    for (uint32_t j = 0; j < n; ++j) {
+        auto& c = cols[j];
+        std::sort(c.begin(), c.end());
+        c.erase(std::unique(c.begin(), c.end()), c.end());
+        S.a_row_idx.insert(S.a_row_idx.end(), c.begin(), c.end());
+        S.a_col_ptr[j + 1] = (uint32_t)S.a_row_idx.size();
+    }
+}
+
+// Natural-order symbolic Cholesky: struct(L_j) = struct(A_j) U (struct(L_c) \ {c}) over the children c of
+// j in the elimination tree, parent(j) = min(struct(L_j) \ {j}).
+void build_l_pattern(ezpz_structure& S) {
+    const uint32_t n = S.n;
+    std::vector<std::vector<uint32_t>> lcol(n);
+    std::vector<std::vector<uint32_t>> children(n);
+    std::vector<uint32_t> tmp;
+    for (uint32_t j = 0; j < n; ++j) {
+        std::vector<uint32_t>& cur = lcol[j];
+        cur.assign(S.a_row_idx.begin() + S.a_col_ptr[j], S.a_row_idx.begin() + S.a_col_ptr[j + 1]);
+        for (uint32_t c : children[j]) {
+            tmp.clear();
+            // merge cur with lcol[c] minus entries <= j... lcol[c] = {c, parent=j, ...}; skip c itself
+            const std::vector<uint32_t>& lc = lcol[c];
+            std::set_union(cur.begin(), cur.end(), lc.begin() + 1, lc.end(), std::back_inserter(tmp));
+            cur.swap(tmp);
+        }
+        // cur[0] == j always (diagonal present)
+        if (cur.size() > 1) children[cur[1]].push_back(j);
+    }
+    S.l_col_ptr.assign(n + 1, 0);
+    S.l_row_idx.clear();
+    for (uint32_t j = 0; j < n; ++j) {
+        S.l_row_idx.insert(S.l_row_idx.end(), lcol[j].begin(), lcol[j].end());
+        S.l_col_ptr[j + 1] = (uint32_t)S.l_row_idx.size();
+    }
+}
+
+void build_components(ezpz_structure& S) {
+    const uint32_t n = S.n;
+    std::vector<uint32_t> parent(n);
+    std::iota(parent.begin(), parent.end(), 0u);
+    auto find = [&](uint32_t v) {
+        while (parent[v] != v) {
+            parent[v] = parent[parent[v]];
+            v = parent[v];
+        }
+        return v;
+    };
+    for (uint32_t r = 0; r < S.m; ++r) {
+        const uint32_t b = S.csr_row_ptr[r], e = S.csr_row_ptr[r + 1];
+        for (uint32_t p = b + 1; p < e; ++p) {
+            uint32_t x = find(S.csr_col_idx[b]), y = find(S.csr_col_idx[p]);
+            if (x != y) parent[std::max(x, y)] = std::min(x, y);
+        }
+    }
+    S.comp_of.assign(n, 0);
+    std::vector<uint32_t> label(n, UINT32_MAX), size;
+    uint32_t nc = 0;
+    for (uint32_t v = 0; v < n; ++v) {
+        uint32_t root = find(v);
+        if (label[root] == UINT32_MAX) {
+            label[root] = nc++;
+            size.push_back(0);
+        }
+        S.comp_of[v] = label[root];
+        size[label[root]]++;
+    }
+    S.n_components = nc;
+    S.max_component = size.empty() ? 0 : *std::max_element(size.begin(), size.end());
+}
+
+// ---- op tape -------------------------------------------------------------------------------------
+struct TapeBuilder {
+    std::vector<uint32_t>& t;
+    uint32_t n_ops = 0;
+    uint64_t n_pairs = 0;
+    size_t head = 0;
+    explicit TapeBuilder(std::vector<uint32_t>& tape) : t(tape) {}
+    void begin(uint32_t dst, uint32_t code, uint32_t fin_kind, uint32_t fin_slot) {
+        head = t.size();
+        t.push_back(dst & 0xffffu);
+        t.push_back((fin_slot & 0xffffu) | ((code | (fin_kind << OP_FIN_SHIFT)) << 16));
+        ++n_ops;
+    }
+    void pair(uint32_t a, uint32_t b) {
+        t.push_back((a & 0xffffu) | (b << 16));
+        t[head] += 1u << 16;
+        ++n_pairs;
+    }
+};
+
+// Shared-memory budget of the thread-per-problem kernel: at least one warp must fit in 227 KB.
+constexpr uint32_t kMaxSmallW = (227u * 1024u) / (8u * 33u);  // 880 doubles per problem (stride 33 for 32 threads)
+
+void build_small_program(ezpz_structure& S) {
+    SmallProgram& P = S.small;
+    P = SmallProgram();
+    const uint32_t n = S.n, m = S.m;
+    const uint32_t nnz_j = (uint32_t)S.csc_row_idx.size();
+    const uint32_t nnz_l = (uint32_t)S.l_row_idx.size();
+    const uint64_t W = (uint64_t)n + 2ull * m + nnz_j + nnz_l + n + S.n_side;
+    if (W > kMaxSmallW || n == 0) return;
+    P.X0 = 0;
+    P.R0 = n;
+    P.RN0 = P.R0 + m;
+    P.J0 = P.RN0 + m;
+    P.L0 = P.J0 + nnz_j;
+    P.D0 = P.L0 + nnz_l;
+    P.S0 = P.D0 + n;
+    P.n_side = S.n_side;
+    P.W = (uint32_t)W;
+    TapeBuilder tb(P.tape);
+
+    // position of every L entry: column-major, diagonal first; row lists for intersections
+    struct RowEnt {
+        uint32_t col, slot;
+    };
+    std::vector<std::vector<RowEnt>> lrow(n);  // strictly lower entries of row i, columns ascending
+    std::vector<uint32_t> diag_slot(n);
+    for (uint32_t j = 0; j < n; ++j) {
+        diag_slot[j] = P.L0 + S.l_col_ptr[j];
+        for (uint32_t p = S.l_col_ptr[j] + 1; p < S.l_col_ptr[j + 1]; ++p) lrow[S.l_row_idx[p]].push_back({j, P.L0 + p});
+    }
+
+    // (1) A = JtJ + lambda*I into the L slots; structural fill entries become +0.0.
+    for (uint32_t j = 0; j < n; ++j) {
+        uint32_t ap = S.a_col_ptr[j];
+        const uint32_t ae = S.a_col_ptr[j + 1];
+        for (uint32_t p = S.l_col_ptr[j]; p < S.l_col_ptr[j + 1]; ++p) {
+            const uint32_t i = S.l_row_idx[p];
+            tb.begin(P.L0 + p, 0u, i == j ? OP_FIN_LAMBDA : OP_FIN_NONE, 0u);
+            while (ap < ae && S.a_row_idx[ap] < i) ++ap;
+            if (ap < ae && S.a_row_idx[ap] == i) {
+                // rows shared by columns i and j of J, ascending
+                uint32_t pi = S.csc_col_ptr[i], pie = S.csc_col_ptr[i + 1];
+                uint32_t pj = S.csc_col_ptr[j], pje = S.csc_col_ptr[j + 1];
+                while (pi < pie && pj < pje) {
+                    const uint32_t ri = S.csc_row_idx[pi], rj = S.csc_row_idx[pj];
+                    if (ri == rj) {
+                        tb.pair(P.J0 + pi, P.J0 + pj);
+                        ++pi;
+                        ++pj;
+                    } else if (ri < rj) ++pi;
+                    else ++pj;
+                }
+            }
+        }
+    }
+    // (2) b = Jt * (-r) into d
+    for (uint32_t j = 0; j < n; ++j) {
+        tb.begin(P.D0 + j, OP_NEGATE, OP_FIN_NONE, 0u);
+        for (uint32_t p = S.csc_col_ptr[j]; p < S.csc_col_ptr[j + 1]; ++p) tb.pair(P.J0 + p, P.R0 + S.csc_row_idx[p]);
+    }
+    // (3) left-looking Cholesky, column by column: pivot, then the sub-diagonal entries
+    for (uint32_t j = 0; j < n; ++j) {
+        tb.begin(diag_slot[j], OP_INIT_DST | OP_NEGATE, OP_FIN_PIVOT, 0u);
+        for (const RowEnt& e : lrow[j]) tb.pair(e.slot, e.slot);
+        for (uint32_t p = S.l_col_ptr[j] + 1; p < S.l_col_ptr[j + 1]; ++p) {
+            const uint32_t i = S.l_row_idx[p];
+            tb.begin(P.L0 + p, OP_INIT_DST | OP_NEGATE, OP_FIN_MUL, diag_slot[j]);
+            // k < j present in both row i and row j, ascending
+            const auto& ri = lrow[i];
+            const auto& rj = lrow[j];
+            size_t a = 0, b = 0;
+            while (a < ri.size() && b < rj.size() && ri[a].col < j && rj[b].col < j) {
+                if (ri[a].col == rj[b].col) {
+                    tb.pair(ri[a].slot, rj[b].slot);
+                    ++a;
+                    ++b;
+                } else if (ri[a].col < rj[b].col) ++a;
+                else ++b;
+            }
+        }
+    }
+    // (4) forward substitution L y = b (in place in d)
+    for (uint32_t i = 0; i < n; ++i) {
+        tb.begin(P.D0 + i, OP_INIT_DST | OP_NEGATE, OP_FIN_MUL, diag_slot[i]);
+        for (const RowEnt& e : lrow[i]) tb.pair(e.slot, P.D0 + e.col);
+    }
+    // (5) backward substitution Lt d = y
+    for (uint32_t ii = n; ii-- > 0;) {
+        tb.begin(P.D0 + ii, OP_INIT_DST | OP_NEGATE, OP_FIN_MUL, diag_slot[ii]);
+        for (uint32_t p = S.l_col_ptr[ii] + 1; p < S.l_col_ptr[ii + 1]; ++p) tb.pair(P.L0 + p, P.D0 + S.l_row_idx[p]);
+    }
+    P.n_ops = tb.n_ops;
+    P.n_pairs = tb.n_pairs;
+    // a single op may not hold more than 65535 pairs (16-bit count); cannot happen below kMaxSmallW
+    P.valid = true;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t ezpz_b200_structure_create(const ezpz_constraint_t* cons, uint32_t n_cons, const uint32_t* var_ids,
+                                   uint32_t n_vars, ezpz_structure_t** out, ezpz_error_detail_t* detail) {
+    if (!out) return EZPZ_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    if (detail) std::memset(detail, 0, sizeof *detail);
+    if (n_cons > 0 && !cons) return EZPZ_ERR_INVALID_ARGUMENT;
+    for (uint32_t c = 0; c < n_cons; ++c) {
+        if (cons[c].kind >= EZPZ_K_COUNT) {
+            set_detail(detail, "constraint kind out of range");
+            if (detail) detail->constraint_id = c;
+            return EZPZ_ERR_INVALID_ARGUMENT;
+        }
+    }
+    // 1. validate_variables: every id named by a row list must be among the guess ids.
+    {
+        std::vector<uint8_t> present;
+        if (var_ids) {
+            uint32_t mx = 0;
+            for (uint32_t k = 0; k < n_vars; ++k) mx = std::max(mx, var_ids[k]);
+            present.assign((size_t)mx + 1, 0);
+            for (uint32_t k = 0; k < n_vars; ++k) present[var_ids[k]] = 1;
+        }
+        for (uint32_t c = 0; c < n_cons; ++c) {
+            const ezk::KindInfo& ki = ezk::kKinds[cons[c].kind];
+            for (int row = 0; row < 2; ++row) {
+                for (int k = 0; k < ki.nz_len[row]; ++k) {
+                    const uint32_t v = cons[c].ids[ki.nz[row][k]];
+                    const bool found = var_ids ? (v < present.size() && present[v]) : (v < n_vars);
+                    if (!found) {
+                        if (detail) {
+                            detail->constraint_id = c;
+                            detail->variable = v;
+                            std::snprintf(detail->message, sizeof detail->message,
+                                          "Constraint %u references variable %u but no such variable appears in "
+                                          "your initial guesses.",
+                                          c, v);
+                        }
+                        return EZPZ_ERR_MISSING_GUESS;
+                    }
+                }
+            }
+        }
+    }
+    ezpz_structure* S = new (std::nothrow) ezpz_structure();
+    if (!S) return EZPZ_ERR_INVALID_ARGUMENT;
+    S->n_cons = n_cons;
+    S->n = n_vars;
+    S->cons.assign(cons, cons + n_cons);
+    // 2. rows and pairs
+    S->cons_row0.assign(n_cons + 1, 0);
+    std::vector<uint64_t> pairs;  // (col << 32) | row: sorting gives CSC order
+    uint32_t row_num = 0;
+    for (uint32_t c = 0; c < n_cons; ++c) {
+        const ezk::KindInfo& ki = ezk::kKinds[cons[c].kind];
+        S->cons_row0[c] = row_num;
+        for (int row = 0; row < ki.rows; ++row) {
+            for (int k = 0; k < ki.nz_len[row]; ++k) {
+                const uint32_t v = cons[c].ids[ki.nz[row][k]];
+                if (v >= n_vars) {  // column index outside the matrix: faer's CreationError (solver.rs:256-260)
+                    set_detail(detail, "Could not create matrix: index out of bounds");
+                    delete S;
+                    return EZPZ_ERR_MATRIX;
+                }
+                pairs.push_back(((uint64_t)v << 32) | row_num);
+            }
+            ++row_num;
+        }
+    }
+    S->cons_row0[n_cons] = row_num;
+    S->m = row_num;
+    std::sort(pairs.begin(), pairs.end());
+    pairs.erase(std::unique(pairs.begin(), pairs.end()), pairs.end());
+    const size_t nnz = pairs.size();
+    S->csc_col_ptr.assign((size_t)n_vars + 1, 0);
+    S->csc_row_idx.resize(nnz);
+    S->csr_row_ptr.assign((size_t)S->m + 1, 0);
+    for (size_t k = 0; k < nnz; ++k) {
+        const uint32_t col = (uint32_t)(pairs[k] >> 32), row = (uint32_t)pairs[k];
+        S->csc_col_ptr[col + 1]++;
+        S->csr_row_ptr[row + 1]++;
+        S->csc_row_idx[k] = row;
+    }
+    for (uint32_t j = 0; j < n_vars; ++j) S->csc_col_ptr[j + 1] += S->csc_col_ptr[j];
+    for (uint32_t r = 0; r < S->m; ++r) S->csr_row_ptr[r + 1] += S->csr_row_ptr[r];
+    S->csr_col_idx.resize(nnz);
+    S->csr_to_csc.resize(nnz);
+    S->csc_to_csr.resize(nnz);
+    {
+        std::vector<uint32_t> cursor(S->csr_row_ptr.begin(), S->csr_row_ptr.end() - 1);
+        for (size_t k = 0; k < nnz; ++k) {
+            const uint32_t col = (uint32_t)(pairs[k] >> 32), row = (uint32_t)pairs[k];
+            const uint32_t pos = cursor[row]++;
+            S->csr_col_idx[pos] = col;
+            S->csr_to_csc[pos] = (uint32_t)k;
+            S->csc_to_csr[k] = pos;
+        }
+    }
+    // 3. analysed constraints with scatter slots
+    S->dev_cons.resize(n_cons);
+    S->n_side = 0;
+    for (uint32_t c = 0; c < n_cons; ++c) {
+        const ezpz_constraint_t& src = cons[c];
+        const ezk::KindInfo& ki = ezk::kKinds[src.kind];
+        DevCons& dc = S->dev_cons[c];
+        std::memset(&dc, 0, sizeof dc);
+        dc.p0 = src.p0;
+        dc.p1 = src.p1;
+        dc.weight = src.weight;
+        dc.kind = src.kind;
+        dc.flags = src.flags;
+        dc.row0 = S->cons_row0[c];
+        dc.side_slot = UINT32_MAX;
+        if ((src.kind == EZPZ_K_LINE_TANGENT_TO_CIRCLE || src.kind == EZPZ_K_CIRCLE_TANGENT_TO_CIRCLE) &&
+            src.flags == EZPZ_SIDE_UNDEFINED)
+            dc.side_slot = S->n_side++;
+        std::memcpy(dc.ids, src.ids, sizeof dc.ids);
+        for (int row = 0; row < ki.rows; ++row) {
+            const uint32_t r = dc.row0 + row;
+            for (int k = 0; k < ki.emit_len[row]; ++k) {
+                const uint32_t col = src.ids[ki.emit[row][k]];
+                const uint32_t* b = S->csc_row_idx.data() + S->csc_col_ptr[col];
+                const uint32_t* e = S->csc_row_idx.data() + S->csc_col_ptr[col + 1];
+                const uint32_t* it = std::lower_bound(b, e, r);
+                uint32_t slot = (uint32_t)(it - S->csc_row_idx.data());
+                for (int q = 0; q < k; ++q)
+                    if ((dc.slot[row][q] & ~kAccumulate) == slot) {
+                        slot |= kAccumulate;
+                        break;
+                    }
+                dc.slot[row][k] = slot;
+            }
+        }
+    }
+    build_a_pattern(*S);
+    build_l_pattern(*S);
+    build_components(*S);
+    build_small_program(*S);
+    *out = S;
+    return EZPZ_OK;
+}
+
+void ezpz_b200_structure_destroy(ezpz_structure_t* s) {
+    if (!s) return;
+    release_device_copies(s);
+    delete s;
+}
+
+int32_t ezpz_b200_structure_dims(const ezpz_structure_t* s, uint32_t* m, uint32_t* n, uint64_t* nnz_j,
+                                 uint64_t* nnz_a, uint64_t* nnz_l, uint32_t* n_components) {
+    if (!s) return EZPZ_ERR_INVALID_ARGUMENT;
+    if (m) *m = s->m;
+    if (n) *n = s->n;
+    if (nnz_j) *nnz_j = s->csc_row_idx.size();
+    if (nnz_a) *nnz_a = s->a_row_idx.size();
+    if (nnz_l) *nnz_l = s->l_row_idx.size();
+    if (n_components) *n_components = s->n_components;
+    return EZPZ_OK;
+}
+
+int32_t ezpz_b200_structure_pattern(const ezpz_structure_t* s, const uint32_t** csc_col_ptr,
+                                    const uint32_t** csc_row_idx, const uint32_t** csr_row_ptr,
+                                    const uint32_t** csr_col_idx) {
+    if (!s) return EZPZ_ERR_INVALID_ARGUMENT;
+    if (csc_col_ptr) *csc_col_ptr = s->csc_col_ptr.data();
+    if (csc_row_idx) *csc_row_idx = s->csc_row_idx.data();
+    if (csr_row_ptr) *csr_row_ptr = s->csr_row_ptr.data();
+    if (csr_col_idx) *csr_col_idx = s->csr_col_idx.data();
+    return EZPZ_OK;
+}
+
+int32_t ezpz_b200_structure_pattern_a(const ezpz_structure_t* s, const uint32_t** a_col_ptr,
+                                      const uint32_t** a_row_idx, const uint32_t** l_col_ptr,
+                                      const uint32_t** l_row_idx) {
+    if (!s) return EZPZ_ERR_INVALID_ARGUMENT;
+    if (a_col_ptr) *a_col_ptr = s->a_col_ptr.data();
+    if (a_row_idx) *a_row_idx = s->a_row_idx.data();
+    if (l_col_ptr) *l_col_ptr = s->l_col_ptr.data();
+    if (l_row_idx) *l_row_idx = s->l_row_idx.data();
+    return EZPZ_OK;
+}
+
+int32_t ezpz_b200_structure_rows(const ezpz_structure_t* s, const uint32_t** cons_row0) {
+    if (!s || !cons_row0) return EZPZ_ERR_INVALID_ARGUMENT;
+    *cons_row0 = s->cons_row0.data();
+    return EZPZ_OK;
+}
+
+void ezpz_b200_shard_range(uint64_t batch, uint32_t rank, uint32_t world, uint64_t* begin, uint64_t* end) {
+    if (world == 0) world = 1;
+    if (rank >= world) rank = world - 1;
+    const uint64_t base = batch / world, extra = batch % world;
+    const uint64_t b = (uint64_t)rank * base + std::min<uint64_t>(rank, extra);
+    const uint64_t len = base + (rank < extra ? 1 : 0);
+    if (begin) *begin = b;
+    if (end) *end = b + len;
+}
+
+void ezpz_b200_config_default(ezpz_config_t* cfg) {
+    if (!cfg) return;
+    cfg->max_iterations = 35;       // solver.rs:73-80
+    cfg->residual_tolerance = 1e-8;
+    cfg->step_tolerance = 1e-12;
+    cfg->initial_lambda = 1e-9;
+}
+
+uint32_t ezpz_b200_abi_version(void) { return EZPZ_B200_ABI_VERSION; }
+
+const char* ezpz_b200_status_name(int32_t status) {
+    switch (status) {
+        case EZPZ_OK: return "OK";
+        case EZPZ_ERR_NOT_FOUND: return "NotFound";
+        case EZPZ_ERR_WRONG_NUMBER_GUESSES: return "WrongNumberGuesses";
+        case EZPZ_ERR_MISSING_GUESS: return "MissingGuess";
+        case EZPZ_ERR_MATRIX: return "FaerMatrix";
+        case EZPZ_ERR_FAER: return "Faer";
+        case EZPZ_ERR_SOLVE: return "FaerSolve";
+        case EZPZ_ERR_SVD: return "FaerSvd";
+        case EZPZ_ERR_EMPTY_SYSTEM: return "EmptySystemNotAllowed";
+        case EZPZ_ERR_INVALID_ARGUMENT: return "InvalidArgument";
+        case EZPZ_ERR_NO_DEVICE: return "NoDevice";
+        case EZPZ_ERR_CUDA: return "Cuda";
+        case EZPZ_ERR_UNSUPPORTED: return "Unsupported";
+        case EZPZ_ERR_TOO_LARGE: return "TooLarge";
+        case EZPZ_ERR_PARSE: return "Parse";
+        case EZPZ_ERR_TEXT_MISSING_GUESS: return "TextMissingGuess";
+        case EZPZ_ERR_TEXT_UNUSED_GUESSES: return "TextUnusedGuesses";
+        case EZPZ_ERR_TEXT_UNDEFINED_POINT: return "TextUndefinedPoint";
+        default: return "Unknown";
+    }
+}
+
+}  // extern "C"

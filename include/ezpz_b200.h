@@ -224,6 +224,9 @@ int32_t ezpz_b200_context_synchronize(ezpz_context_t* ctx);
  *                                    unsatisfied (lib.rs:305-327)
  *   degen_count    [batch * n_cons]  optional: how many Warning::Degenerate were raised per
  *                                    constraint (solver.rs:340-346,385-391)
+ *   jacobian       [batch * nnz]     optional: the cached Jacobian values (CSC order) at the last
+ *                                    accepted point, i.e. what freedom_analysis reads
+ *                                    (find_dof.rs:16-18)
  */
 typedef struct ezpz_batch_io {
     const double* guesses;
@@ -233,6 +236,7 @@ typedef struct ezpz_batch_io {
     uint8_t* status;
     uint32_t* unsat_mask;
     uint32_t* degen_count;
+    double* jacobian;
 } ezpz_batch_io_t;
 
 int32_t ezpz_b200_solve_batch(ezpz_context_t* ctx, const ezpz_structure_t* s,
@@ -264,6 +268,7 @@ typedef struct ezpz_one_io {
     uint8_t* status;
     uint32_t* unsat_mask;  /* optional [ceil(n_cons/32)] */
     uint32_t* degen_count; /* optional [n_cons] */
+    double* jacobian;      /* optional [nnz], CSC order, values at the last accepted point */
     int32_t* path_used;    /* optional */
     uint32_t* lin_iters;   /* optional: total inner (PCG) iterations, 0 for direct paths */
 } ezpz_one_io_t;
@@ -285,12 +290,58 @@ int32_t ezpz_b200_eval(ezpz_context_t* ctx, const ezpz_structure_t* s, const dou
                        double* jac_csc, double* jac_csr, uint8_t* degen,
                        ezpz_error_detail_t* detail);
 
-/* Freedom analysis (find_dof.rs:15-104) for `batch` problems at their final values: var j is
- * flagged in under_mask (bit j of [batch * ceil(n/32)] words) when its nullspace participation
- * exceeds the reference's threshold.  Runs on the device. */
+/* Freedom analysis (find_dof.rs:15-104) for `batch` problems of one structure: dense column-pivoted
+ * QR of each problem's Jacobian (`jacobian`: [batch * nnz] values in CSC order, as exported by the
+ * solve calls), rank by |R_ii| > 1e-8 * max|R_ii|, nullspace participation per variable; variable j is
+ * underconstrained iff its participation exceeds (1e-3 * max participation)^2.  Bit j of
+ * under_mask[problem * ceil(n/32) + j/32] is set for underconstrained variables.  Host pointers; runs on
+ * the device (one thread per problem); EZPZ_ERR_TOO_LARGE beyond 256 variables (the reference's dense
+ * O(m n^2) analysis is itself unusable there, tests.rs:140-145). */
 int32_t ezpz_b200_freedom_analysis(ezpz_context_t* ctx, const ezpz_structure_t* s, uint64_t batch,
-                                   const double* final_values, const double* params,
-                                   uint32_t* under_mask, ezpz_error_detail_t* detail);
+                                   const double* jacobian, uint32_t* under_mask,
+                                   ezpz_error_detail_t* detail);
+
+/* ---------------------------------------------------------------------------------------------
+ * ezpz::solve / ezpz::solve_analysis (lib.rs:80-144) with flat arguments: the priority loop
+ * (lib.rs:148-263), the lint (warnings.rs:34-59), one structure analysis + one device solve per
+ * priority level, the unsatisfied list in ORIGINAL request indices, and (analysis != 0) the
+ * underconstrained variable list.  This is what the Rust shim's `solve` calls.
+ *   priorities  [n_cons] or NULL (all 0)
+ *   angles_deg  [n_cons] or NULL: for LinesAtAngle(Other(a)) the angle in degrees, NaN otherwise
+ *               (only used by the lint)
+ *   var_ids     [n_vars] or NULL (ids 0..n_vars-1)
+ * On error the status is returned and `outcome` carries what FailureOutcome does: warnings, num_vars,
+ * num_eqs (solve_outcome.rs:136-181).
+ */
+typedef struct ezpz_warning {
+    int64_t about_constraint; /* -1 = None */
+    uint32_t kind;            /* 0 Degenerate, 1 ShouldBeParallel, 2 ShouldBePerpendicular */
+    uint32_t count;           /* Degenerate: how many times it was raised */
+    double angle_deg;
+} ezpz_warning_t;
+
+typedef struct ezpz_outcome {
+    double* final_values;       /* [n_vars] */
+    uint64_t* unsatisfied;      /* [n_cons] */
+    uint32_t* underconstrained; /* [n_vars], may be NULL when analysis == 0 */
+    ezpz_warning_t* warnings;   /* [warnings_cap], may be NULL */
+    uint32_t warnings_cap;
+    uint32_t n_warnings;        /* produced (may exceed warnings_cap; only the first cap are stored) */
+    uint32_t n_unsatisfied;
+    uint32_t n_underconstrained;
+    uint64_t iterations;
+    uint32_t converged;
+    uint32_t priority_solved;
+    uint32_t num_vars;
+    uint32_t num_eqs;
+    int32_t path_used;
+    uint32_t reserved;
+} ezpz_outcome_t;
+
+int32_t ezpz_b200_solve(ezpz_context_t* ctx, const ezpz_constraint_t* cons, const uint32_t* priorities,
+                        const double* angles_deg, uint32_t n_cons, const uint32_t* var_ids,
+                        const double* guesses, uint32_t n_vars, const ezpz_config_t* config,
+                        int32_t analysis, ezpz_outcome_t* outcome, ezpz_error_detail_t* detail);
 
 /* ---------------------------------------------------------------------------------------------
  * Scalar helpers with the bits of libm 0.2.16 (see ezpz_b200/csrc/dmath.cuh). */

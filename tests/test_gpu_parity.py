@@ -1,0 +1,320 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the CPU oracle on the same inputs.
+
+Bars (BASELINE.json north_star): sparsity pattern bit-exact; iteration count and converged /
+unsatisfied / underconstrained verdicts identical; final coordinates within 1e-9 absolute (or relative for
+large coordinates).  Residuals and Jacobian values of a single evaluation are compared BIT FOR BIT.
+"""
+import math
+
+import numpy as np
+import pytest
+
+import ezpz_b200 as ez
+import orc
+import workloads as wl
+
+pytestmark = pytest.mark.gpu
+
+FIXTURES = sorted(wl.fixtures())
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float64).view(np.uint64)
+
+
+def assert_bitwise(a, b, what):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    same = (bits(a) == bits(b)) | (np.isnan(a) & np.isnan(b))
+    assert same.all(), f"{what}: {np.count_nonzero(~same)} of {a.size} values differ, first at {np.argmin(same)}: {a.flat[np.argmin(same)]!r} vs {b.flat[np.argmin(same)]!r}"
+
+
+def resolved(recs, guesses):
+    """Records with Undefined sides resolved from `guesses` the way the oracle's orc_eval expects."""
+    out = recs.copy()
+    for r in out:
+        if r["flags"] != 0:
+            continue
+        ids = r["ids"]
+        if r["kind"] == 0:
+            ux, uy = guesses[ids[2]] - guesses[ids[0]], guesses[ids[3]] - guesses[ids[1]]
+            vx, vy = guesses[ids[4]] - guesses[ids[0]], guesses[ids[5]] - guesses[ids[1]]
+            r["flags"] = 1 if ux * vy - uy * vx >= 0.0 else 2
+        elif r["kind"] == 1:
+            dist = orc.lib().orc_fn_hypot(guesses[ids[0]] - guesses[ids[3]], guesses[ids[1]] - guesses[ids[4]])
+            ar, br = guesses[ids[2]], guesses[ids[5]]
+            r["flags"] = 2 if abs(abs(ar - br) - dist) < abs(ar + br - dist) else 1
+    return out
+
+
+@pytest.mark.parametrize("name", FIXTURES)
+def test_eval_bitwise_on_fixtures(ctx, name):
+    """Kernel family (1)+(2): residuals and scattered Jacobian values at the fixture's initial guess."""
+    recs, n, g, _ = wl.system_from_text(wl.fixture_text(name))
+    st = ez.Structure(recs, n)
+    r, jc, jr, dg = ctx.evaluate(st, g)
+    ro, jo, dgo, pat = orc.evaluate(resolved(recs, g), n, g)
+    assert_bitwise(r, ro, "residual")
+    assert_bitwise(jc, jo, "jacobian (CSC)")
+    # CSR order is the same values permuted
+    rc, p = orc.pattern(recs, n)
+    dense = {}
+    for j in range(n):
+        for e in range(p["csc_col_ptr"][j], p["csc_col_ptr"][j + 1]):
+            dense[(p["csc_row_idx"][e], j)] = jo[e]
+    k = 0
+    for i in range(p["m"]):
+        for e in range(p["csr_row_ptr"][i], p["csr_row_ptr"][i + 1]):
+            assert bits(np.array([jr[k]]))[0] == bits(np.array([dense[(i, p["csr_col_idx"][e])]]))[0]
+            k += 1
+    assert np.array_equal(dg, dgo)
+
+
+@pytest.mark.parametrize("name", FIXTURES)
+def test_solve_fixture_matches_oracle(ctx, name):
+    recs, n, g, _ = wl.system_from_text(wl.fixture_text(name))
+    st = ez.Structure(recs, n)
+    out = ctx.solve_one(st, g, want_jacobian=True)
+    o = orc.solve_inner(recs, g, analysis=True)
+    assert o.rc == 0
+    assert out.iterations == o.iterations, "iteration count"
+    assert out.converged == o.converged
+    assert out.unsatisfied == o.unsatisfied, "inconsistent verdict"
+    scale = np.maximum(1.0, np.abs(o.final_values))
+    assert (np.abs(out.final_values - o.final_values) <= 1e-9 * scale).all()
+    assert_bitwise(out.final_values, o.final_values, "final values")
+    assert np.array_equal(out.degen_count, o.degen_count)
+    mask = ctx.freedom_analysis(st, out.jacobian)[0]
+    under = [j for j in range(n) if mask[j >> 5] >> (j & 31) & 1]
+    assert under == o.underconstrained, "underconstrained verdict"
+
+
+def test_batch_two_rectangles_matches_oracle(ctx):
+    recs, n, g = wl.two_rectangles_batch(4096)
+    st = ez.Structure(recs, n)
+    out = ctx.solve_batch(st, g, want_degen=True)
+    fin, it, status = orc.solve_batch(recs, n, g, hoist=True)
+    assert np.array_equal(out.iterations, it)
+    assert np.array_equal(out.status, status)
+    assert_bitwise(out.final_values, fin, "final values")
+    # problem 0 is the unperturbed fixture: its solution is the reference's (tests.rs:569-577)
+    expect = [1, 1, 5, 1, 5, 4, 1, 4, 2, 2, 6, 2, 6, 6, 2, 6]
+    assert np.abs(out.final_values[0] - expect).max() < 1e-4
+
+
+def test_batch_full_size_properties(ctx):
+    """Config 2 at full size (65,536): size-independent properties instead of the oracle."""
+    recs, n, g = wl.two_rectangles_batch(65536)
+    st = ez.Structure(recs, n)
+    out = ctx.solve_batch(st, g)
+    assert (out.status & 1).all(), "all converge"
+    assert not (out.status & 2).any(), "all satisfied"
+    expect = np.array([1, 1, 5, 1, 5, 4, 1, 4, 2, 2, 6, 2, 6, 6, 2, 6], dtype=np.float64)
+    assert np.abs(out.final_values - expect[None, :]).max() < 1e-6
+    # idempotence: solving from the solution takes 0 iterations and does not move
+    again = ctx.solve_batch(st, out.final_values)
+    assert (again.iterations == 0).all()
+    assert np.array_equal(again.final_values, out.final_values)
+    # a 1,024-problem sample against the oracle
+    idx = np.arange(0, 65536, 64)
+    fin, it, status = orc.solve_batch(recs, n, g[idx], hoist=True)
+    assert np.array_equal(out.iterations[idx], it)
+    assert_bitwise(out.final_values[idx], fin, "sampled final values")
+
+
+@pytest.mark.parametrize("name", ["square", "circle_tangent", "arc_length", "parc_coincident", "inconsistent",
+                                  "underconstrained", "perpendicular", "symmetric", "perpdist", "chamfer_square"])
+def test_batch_mixed_structures(ctx, name):
+    """Config 5 ingredients: perturbed batches incl. inconsistent and underconstrained systems."""
+    recs, n, g = wl.perturbed_batch(name, 512, 0xE2B200D5EED00000 + 7, 0.25)
+    st = ez.Structure(recs, n)
+    out = ctx.solve_batch(st, g, want_degen=True, want_jacobian=True)
+    fin, it, status = orc.solve_batch(recs, n, g, hoist=True)
+    mism = np.flatnonzero(out.iterations != it)
+    assert mism.size == 0, f"{mism.size} iteration-count mismatches, first {mism[:5]}"
+    assert np.array_equal(out.status, status)
+    assert_bitwise(out.final_values, fin, "final values")
+    masks = ctx.freedom_analysis(st, out.jacobian)
+    for b in range(0, 512, 37):
+        o = orc.solve_inner(recs, g[b], analysis=True)
+        under = [j for j in range(n) if masks[b, j >> 5] >> (j & 31) & 1]
+        assert under == o.underconstrained
+
+
+def test_params_override(ctx):
+    """Per-problem targets: distance(p0,p1,d) with d varying per problem."""
+    recs, n, g0, _ = wl.system_from_text(wl.fixture_text("two_rectangles"))
+    B = 64
+    g = np.repeat(g0[None, :], B, 0)
+    params = np.repeat(recs["p0"][None, :], B, 0).copy()
+    dist_rows = np.flatnonzero(recs["kind"] == ez.K_DISTANCE)
+    params[:, dist_rows[0]] = np.linspace(3.0, 5.0, B)
+    st = ez.Structure(recs, n)
+    out = ctx.solve_batch(st, g, params=params)
+    fin, it, status = orc.solve_batch(recs, n, g, params=params, hoist=True)
+    assert np.array_equal(out.iterations, it)
+    assert_bitwise(out.final_values, fin, "final values")
+    assert np.abs((out.final_values[:, 2] - out.final_values[:, 0]) - params[:, dist_rows[0]]).max() < 1e-6
+
+
+def _random_values(rng, n, scale=8.0):
+    return rng.uniform(-scale, scale, n)
+
+
+def test_eval_random_all_kinds_bitwise(ctx):
+    """Every kind on random points (the input distribution of proptests.rs:188-234), bit for bit, plus
+    degenerate inputs (coincident points) to exercise the zero-row branches."""
+    rng = np.random.default_rng(20261017)
+    for trial in range(40):
+        cons = random_constraints(rng, 60, 24)
+        recs = ez.records(cons, rng.choice([1.0, 0.5, 3.0], len(cons)))
+        x = _random_values(rng, 24)
+        if trial % 4 == 0:  # collapse some points onto each other
+            x[2:4] = x[0:2]
+            x[8:10] = x[6:8]
+        st = ez.Structure(recs, 24)
+        r, jc, jr, dg = ctx.evaluate(st, x)
+        ro, jo, dgo, _ = orc.evaluate(resolved(recs, x), 24, x)
+        assert_bitwise(r, ro, f"trial {trial} residual")
+        assert_bitwise(jc, jo, f"trial {trial} jacobian")
+        assert np.array_equal(dg, dgo)
+
+
+def random_constraints(rng, count, n_vars):
+    pts = [ez.DatumPoint.new_xy(2 * i, 2 * i + 1) for i in range(n_vars // 2)]
+
+    def P():
+        return pts[rng.integers(len(pts))]
+
+    def Ln():
+        return ez.DatumLineSegment(P(), P())
+
+    def Ci():
+        return ez.DatumCircle(P(), ez.DatumDistance(int(rng.integers(n_vars))))
+
+    def Ar():
+        return ez.DatumCircularArc(P(), P(), P())
+
+    def AK():
+        k = rng.integers(3)
+        if k == 0:
+            return ez.AngleKind.Parallel()
+        if k == 1:
+            return ez.AngleKind.Perpendicular()
+        return ez.AngleKind.Other(ez.Angle.from_radians(rng.uniform(-4, 4)))
+
+    C = ez.Constraint
+    makers = [
+        lambda: C.LineTangentToCircle(Ln(), Ci(), int(rng.integers(1, 3))),
+        lambda: C.CircleTangentToCircle(Ci(), Ci(), int(rng.integers(1, 3))),
+        lambda: C.Distance(P(), P(), rng.uniform(0, 5)),
+        lambda: C.DistanceVar(P(), P(), ez.DatumDistance(int(rng.integers(n_vars)))),
+        lambda: C.VerticalDistance(P(), P(), rng.uniform(-5, 5)),
+        lambda: C.HorizontalDistance(P(), P(), rng.uniform(-5, 5)),
+        lambda: C.Vertical(Ln()),
+        lambda: C.Horizontal(Ln()),
+        lambda: C.LinesAtAngle(Ln(), Ln(), AK()),
+        lambda: C.Fixed(int(rng.integers(n_vars)), rng.uniform(-5, 5)),
+        lambda: C.ScalarEqual(int(rng.integers(n_vars)), int(rng.integers(n_vars))),
+        lambda: C.PointsCoincident(P(), P()),
+        lambda: C.CircleRadius(Ci(), rng.uniform(0, 5)),
+        lambda: C.LinesEqualLength(Ln(), Ln()),
+        lambda: C.ArcRadius(Ar(), rng.uniform(0, 5)),
+        lambda: C.Arc(Ar()),
+        lambda: C.Midpoint(Ln(), P()),
+        lambda: C.PointLineDistance(P(), Ln(), rng.uniform(-5, 5)),
+        lambda: C.VerticalPointLineDistance(P(), Ln(), rng.uniform(-5, 5)),
+        lambda: C.HorizontalPointLineDistance(P(), Ln(), rng.uniform(-5, 5)),
+        lambda: C.Symmetric(Ln(), P(), P()),
+        lambda: C.PointArcCoincident(Ar(), P()),
+        lambda: C.ArcLength(Ar(), rng.uniform(0, 9)),
+        lambda: C.ArcAngle(Ar(), ez.Angle.from_degrees(rng.uniform(-200, 200))),
+        lambda: C.PointsAtAngle(P(), P(), P(), AK()),
+    ]
+    out = [m() for m in makers]  # every kind at least once
+    while len(out) < count:
+        out.append(makers[rng.integers(len(makers))]())
+    return out
+
+
+def test_device_math_bitwise(ctx):
+    """hypot / sin / cos on the device (through ArcLength, Distance evaluations) were covered above; here the
+    host copies of the same functions against the oracle's."""
+    rng = np.random.default_rng(7)
+    L = orc.lib()
+    import ctypes as C
+    for _ in range(2000):
+        a, b = rng.uniform(-1e3, 1e3, 2) * 10.0 ** rng.integers(-8, 8)
+        assert ez.native.lib().ezpz_b200_hypot(a, b) == L.orc_fn_hypot(a, b)
+        s, c = ez.angle_sincos(a)
+        assert s == L.orc_fn_sin(a) and c == L.orc_fn_cos(a)
+
+
+def test_api_solve_mirrors_reference_tests(ctx):
+    """ezpz::solve semantics through ezpz_b200_solve (tests.rs:39-128, 256-284, 1090-1127)."""
+    C, R = ez.Constraint, ez.ConstraintRequest
+    # it_returns_best_satisfied_solution (tests.rs:49-68)
+    reqs = [R.new(C.Fixed(0, 0.0), 0), R.new(C.Fixed(0, 1.0), 1), R.new(C.Fixed(0, 2.0), 1)]
+    s = ez.solve_analysis(reqs, [(0, 0.5)])
+    assert s.is_satisfied() and s.priority_solved() == 0
+    # priority_solver_reports_original_indices (tests.rs:87-106)
+    reqs = [R.new(C.Fixed(0, 0.0), 1), R.new(C.Fixed(0, 1.0), 0), R.new(C.Fixed(0, 2.0), 0)]
+    s = ez.solve_analysis(reqs, [(0, 0.5)])
+    assert s.unsatisfied() == [1, 2] and s.priority_solved() == 0
+    # initials_become_finals_if_no_constraints (tests.rs:70-85)
+    s = ez.solve_analysis([], [(0, 0.5)])
+    assert s.is_satisfied() and list(s.final_values()) == [0.5]
+    # too_many_variables / empty (tests.rs:39-47, 108-128)
+    with pytest.raises(ez.FailureOutcome) as e:
+        ez.solve_analysis([R.highest_priority(C.Fixed(0, 0.0))], [])
+    assert e.value.name == "MissingGuess" and e.value.constraint_id == 0 and e.value.variable == 0
+    # weight_biases_inconsistent_solution (tests.rs:256-284)
+    reqs = [R.highest_priority(C.Fixed(0, 0.0)), R.highest_priority(C.Fixed(0, 100.0)).with_weight(100.0)]
+    assert ez.solve(reqs, [(0, 50.0)]).final_values()[0] > 99.0
+    reqs = [R.highest_priority(C.Fixed(0, 0.0)), R.highest_priority(C.Fixed(0, 100.0))]
+    assert abs(ez.solve(reqs, [(0, 50.0)]).final_values()[0] - 50.0) < 1e-4
+    # strange_nonconvergence: iterations == 2 (tests.rs:1090-1127)
+    p, q, r, s_, t = [ez.DatumPoint.new_xy(2 * i, 2 * i + 1) for i in range(5)]
+    reqs = [R.highest_priority(c) for c in (
+        C.Fixed(0, 0.0), C.Fixed(1, 0.0), C.PointsCoincident(r, s_), C.PointsCoincident(q, p),
+        C.LinesEqualLength(ez.DatumLineSegment(q, r), ez.DatumLineSegment(s_, t)))]
+    g = [0.0, -0.02, -3.39, -0.38, -2.76, 4.83, -1.54, 5.21, -1.15, 2.75]
+    out = ez.solve(reqs, list(enumerate(g)), ez.Config().with_max_iterations(31))
+    assert out.iterations() == 2
+    # warnings (tests.rs:1129-1159): lines_at_angle(..., 0rad) -> ShouldBeParallel about constraint 7
+    txt = ("# constraints\npoint p\npoint q\np.x = 0\np.y = 0\nq.y = 0\nvertical(p, q)\npoint r\npoint s\nr.x = 0\n"
+           "s.x = 0\ns.y = 0\nlines_at_angle(p, q, r, s, 0rad)\n\n# guesses\np roughly (3, 4)\nq roughly (5, 6)\n"
+           "r roughly (3, 4)\ns roughly (5, 6)\n")
+    o = ez.textual.Problem(txt).to_constraint_system().solve()
+    assert any(w.about_constraint == 7 and w.content == ez.Warning.ShouldBeParallel for w in o.warnings)
+
+
+def test_iteration_count_pins_on_gpu(ctx):
+    """lines_at_angle_isolated / lines_angle_sign_check / points_at_angle_already_satisfied
+    (tests.rs:1506-1766) through the GPU path."""
+    C, R = ez.Constraint, ez.ConstraintRequest
+    P = [ez.DatumPoint.new_xy(2 * i, 2 * i + 1) for i in range(4)]
+    l0, l1 = ez.DatumLineSegment(P[0], P[1]), ez.DatumLineSegment(P[2], P[3])
+    pi = math.pi
+    cases = [([[0, 0], [1, 0], [0, 0], [0, 2]], 0.5 * pi, 0), ([[0, 0], [1, 0], [0, 0], [0, 2]], -0.5 * pi, 0),
+             ([[0, 0], [1, 0], [0, 0], [2, 0]], 0.0, 0), ([[0, 0], [1, 0], [0, 0], [2, 0]], pi, 0),
+             ([[0, 0], [-1, 0], [0, 0], [2, 0]], 0.0, 0), ([[0, 0], [-1, 0], [0, 0], [2, 0]], pi, 0),
+             ([[0, 0], [1, 0], [0, 0], [0, 2]], 0.0, 4), ([[0, 0], [1, 0], [0, 0], [0, 2]], pi, 4),
+             ([[0, 0], [0, 1], [0, 0], [0, 2]], 0.5 * pi, 4), ([[0, 0], [0, 1], [0, 0], [0, 2]], -0.5 * pi, 4)]
+    cfg = ez.Config().with_max_iterations(100)
+    for pts, ang, expect in cases:
+        reqs = [R.highest_priority(C.LinesAtAngle(l0, l1, ez.AngleKind.Other(ez.Angle.from_radians(ang))))]
+        g = [v for p in pts for v in p]
+        out = ez.solve(reqs, list(enumerate(map(float, g))), cfg)
+        assert out.is_satisfied() and out.iterations() == expect, (ang, out.iterations())
+    l1b = ez.DatumLineSegment(P[1], P[2])
+    for ang, expect in [(0.1 * pi, 3), (-0.1 * pi, 4)]:
+        reqs = [R.highest_priority(c) for c in (
+            C.Fixed(0, 0.0), C.Fixed(1, 0.0), C.Fixed(2, 1.0), C.Fixed(3, 0.0),
+            C.LinesAtAngle(l0, l1b, ez.AngleKind.Other(ez.Angle.from_radians(ang))))]
+        out = ez.solve(reqs, list(enumerate([0.0, 0.0, 1.0, 0.0, 2.0, 1.0])), cfg)
+        assert out.is_satisfied() and out.iterations() == expect
+    for p1, p2, ang in [([1, 0], [0, 2], 0.5 * pi), ([1, 0], [0, -2], -0.5 * pi), ([1, 0], [3, 0], 0.0),
+                        ([1, 0], [-2, 0], pi), ([2, 0], [1, 1], 0.25 * pi)]:
+        reqs = [R.highest_priority(C.PointsAtAngle(P[0], P[1], P[2], ez.AngleKind.Other(ez.Angle.from_radians(ang))))]
+        out = ez.solve(reqs, list(enumerate(map(float, [0, 0, *p1, *p2]))), cfg)
+        assert out.is_satisfied() and out.iterations() == 0
