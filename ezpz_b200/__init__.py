@@ -534,18 +534,24 @@ class Context:
     def synchronize(self):
         native.lib().ezpz_b200_context_synchronize(self.handle)
 
-    def solve_batch(self, st, guesses, params=None, config=None, want_unsat=True, want_degen=False, want_jacobian=False):
+    def solve_batch(self, st, guesses, params=None, config=None, want_unsat=True, want_degen=False, want_jacobian=False,
+                    out=None):
+        """ezpz_b200_solve_batch: host buffers in, host buffers out.  `out`: an earlier BatchResult (e.g. with
+        pinned arrays) to reuse instead of allocating."""
         g = np.ascontiguousarray(guesses, dtype=np.float64).reshape(-1, st.n_vars)
         B = g.shape[0]
         cfg = (config or Config())._native()
-        res = BatchResult()
-        res.final_values = np.empty_like(g)
-        res.iterations = np.empty(B, np.uint32)
-        res.status = np.empty(B, np.uint8)
-        uw = (st.n_cons + 31) // 32
-        res.unsat_mask = np.zeros((B, uw), np.uint32) if want_unsat else None
-        res.degen_count = np.zeros((B, st.n_cons), np.uint32) if want_degen else None
-        res.jacobian = np.zeros((B, st.nnz), np.float64) if want_jacobian else None
+        if out is None:
+            res = BatchResult()
+            res.final_values = np.empty_like(g)
+            res.iterations = np.empty(B, np.uint32)
+            res.status = np.empty(B, np.uint8)
+            uw = (st.n_cons + 31) // 32
+            res.unsat_mask = np.zeros((B, uw), np.uint32) if want_unsat else None
+            res.degen_count = np.zeros((B, st.n_cons), np.uint32) if want_degen else None
+            res.jacobian = np.zeros((B, st.nnz), np.float64) if want_jacobian else None
+        else:
+            res = out
         p = None if params is None else np.ascontiguousarray(params, dtype=np.float64)
         io = native.BatchIO(native.ptr(g), native.ptr(p), native.ptr(res.final_values), native.ptr(res.iterations),
                             native.ptr(res.status), native.ptr(res.unsat_mask), native.ptr(res.degen_count),

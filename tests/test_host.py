@@ -1,0 +1,197 @@
+"""Host logic, CPU only: the C ABI loads and exports every declared symbol, the text pipeline, the
+structure analysis (pattern parity with the oracle, bit-exact), sharding."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import ezpz_b200 as ez
+import orc
+import workloads as wl
+from ezpz_b200 import native
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    with open(os.path.join(ROOT, "include", "ezpz_b200.h")) as f:
+        header = f.read()
+    declared = sorted(set(re.findall(r"\b(ezpz_b200_[a-z0-9_]+)\s*\(", header)))
+    assert len(declared) >= 25
+    lib = C.CDLL(native.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} is declared in include/ezpz_b200.h but not exported"
+    assert sorted(native.SYMBOL_NAMES) == declared, "native.py must bind exactly the header's functions"
+    assert native.lib().ezpz_b200_abi_version() == 1
+    assert C.sizeof(native.Constraint) == 64
+
+
+def test_config_default():
+    cfg = native.Config()
+    native.lib().ezpz_b200_config_default(C.byref(cfg))
+    assert (cfg.max_iterations, cfg.residual_tolerance, cfg.step_tolerance, cfg.initial_lambda) == (35, 1e-8, 1e-12, 1e-9)
+
+
+def test_tiny_worked_pattern():
+    """SURVEY.md §8c worked example (test_cases/tiny)."""
+    recs, n, g, _ = wl.system_from_text(wl.fixture_text("tiny"))
+    pat = ez.Structure(recs, n).pattern()
+    assert list(pat["csc_col_ptr"]) == [0, 2, 3, 4, 5] and list(pat["csc_row_idx"]) == [0, 3, 1, 3, 2]
+    assert list(pat["csr_row_ptr"]) == [0, 1, 2, 3, 5] and list(pat["csr_col_idx"]) == [0, 1, 3, 0, 2]
+
+
+@pytest.mark.parametrize("name", sorted(wl.fixtures()))
+def test_patterns_match_oracle_bit_exactly(name):
+    recs, n, g, _ = wl.system_from_text(wl.fixture_text(name))
+    st = ez.Structure(recs, n)
+    pat = st.pattern()
+    rc, op = orc.pattern(recs, n)
+    assert rc == 0
+    for k in ("csc_col_ptr", "csc_row_idx", "csr_row_ptr", "csr_col_idx", "cons_row0"):
+        assert np.array_equal(pat[k], op[k]), k
+    assert (pat["m"], pat["nnz"]) == (op["m"], op["nnz"])
+    # pattern of A and of the Cholesky factor: product is CSC with the diagonal first, oracle is by rows
+    pa, oc = st.pattern_a(), orc.pattern_chol(recs, n)
+    def cols_to_rows(col_ptr, row_idx, strict):
+        rows = [[] for _ in range(n)]
+        for j in range(n):
+            for p in range(col_ptr[j], col_ptr[j + 1]):
+                if not (strict and row_idx[p] == j):
+                    rows[row_idx[p]].append(j)
+        return rows
+    a_rows = cols_to_rows(pa["a_col_ptr"], pa["a_row_idx"], False)
+    l_rows = cols_to_rows(pa["l_col_ptr"], pa["l_row_idx"], True)
+    for i in range(n):
+        assert a_rows[i] == list(oc["a_col"][oc["a_row_ptr"][i]:oc["a_row_ptr"][i + 1]])
+        assert l_rows[i] == list(oc["l_col"][oc["l_row_ptr"][i]:oc["l_row_ptr"][i + 1]])
+
+
+def test_patterns_random_and_massive():
+    from test_gpu_parity import random_constraints
+    rng = np.random.default_rng(3)
+    for _ in range(10):
+        recs = ez.records(random_constraints(rng, 80, 40))
+        pat = ez.Structure(recs, 40).pattern()
+        rc, op = orc.pattern(recs, 40)
+        for k in ("csc_col_ptr", "csc_row_idx", "csr_row_ptr", "csr_col_idx"):
+            assert np.array_equal(pat[k], op[k])
+    recs, n, g, _ = wl.system_from_text(wl.massive_problem_text(500))
+    st = ez.Structure(recs, n)
+    assert (st.m, st.n, st.nnz, st.n_components) == (2000, 2000, 2500, 1500)
+    rc, op = orc.pattern(recs, n)
+    assert np.array_equal(st.pattern()["csr_col_idx"], op["csr_col_idx"])
+    recs, n, g, _ = wl.system_from_text(wl.massive_problem_text(600))
+    st = ez.Structure(recs, n)
+    assert (st.m, st.n, st.nnz) == (2400, 2400, 3000)  # the checked-in problem.md
+
+
+def test_structure_errors():
+    Cn = ez.Constraint
+    with pytest.raises(ez.EzpzError) as e:
+        ez.Structure(ez.records([Cn.Fixed(0, 0.0), Cn.Fixed(7, 1.0)]), 4)
+    assert e.value.name == "MissingGuess" and e.value.constraint_id == 1 and e.value.variable == 7
+    with pytest.raises(ez.EzpzError) as e:  # id is among the guesses but beyond the matrix (FaerMatrix)
+        ez.Structure(ez.records([Cn.Fixed(9, 0.0)]), 2, var_ids=[3, 9])
+    assert e.value.name == "FaerMatrix"
+    recs = ez.records([Cn.Fixed(0, 0.0)])
+    recs[0]["kind"] = 99
+    with pytest.raises(ez.EzpzError) as e:
+        ez.Structure(recs, 1)
+    assert e.value.name == "InvalidArgument"
+    # PointsCoincident with only x ids guessed: first missing id comes from row 1 (solver.rs:448-478)
+    with pytest.raises(ez.EzpzError) as e:
+        ez.Structure(ez.records([Cn.PointsCoincident(ez.DatumPoint.new_xy(0, 1), ez.DatumPoint.new_xy(2, 3))]), 2,
+                     var_ids=[0, 2])
+    assert e.value.name == "MissingGuess" and e.value.variable == 1
+
+
+def test_text_errors_and_quirks():
+    T = ez.textual
+    with pytest.raises(T.TextualError) as e:
+        T.Problem("# constraints\npoint p\n\n# guesses\nq roughly (0, 0)\n").to_constraint_system()
+    assert e.value.name == "TextMissingGuess"
+    with pytest.raises(T.TextualError) as e:
+        T.Problem("# constraints\npoint p\n\n# guesses\np roughly (0, 0)\nghost roughly (1, 1)\n").to_constraint_system()
+    assert e.value.name == "TextUnusedGuesses" and "ghost" in e.value.message
+    with pytest.raises(T.TextualError) as e:
+        T.Problem("# constraints\npoint p\nmissing.x = 2.5\n\n# guesses\np roughly (0, 0)\n").to_constraint_system()
+    assert e.value.name == "TextUndefinedPoint"
+    for bad in ["", "# constraints\n", "# constraints\npoint p\n# guesses\np roughly (0,0)\n",
+                "# constraints\npoint p\n\n# guesses\np roughly (0,0)\n\n\nextra"]:
+        with pytest.raises(T.TextualError) as e:
+            T.Problem(bad)
+        assert e.value.name == "Parse"
+    # sqrt(...) number expressions, deg/rad angles, no spaces around '='
+    cs = T.Problem("# constraints\npoint a\npoint b\npoint c\npoint d\ndistance(a, b, sqrt(sqrt(16)))\n"
+                   "lines_at_angle(a, b, c, d, 90deg)\na.x=1e0\n\n# guesses\na roughly (0,0)\nb roughly (1, 0)\n"
+                   "c roughly (-.5,+2.)\nd roughly (3,3)").to_constraint_system()
+    assert cs.constraints["p0"][0] == 2.0 and cs.angles_deg[1] == 90.0 and cs.constraints["p0"][2] == 1.0
+    assert list(cs.initial_guesses[4:6]) == [-0.5, 2.0]
+    s, c = ez.angle_sincos(90.0 * (np.pi / 180.0))
+    assert (cs.constraints["p0"][1], cs.constraints["p1"][1]) == (c, s)
+    # `A.center = (x, y)` on an ARC is silently dropped (executor.rs:273-283); circles keep it
+    cs = T.Problem("# constraints\narc a\na.center = (1, 2)\nis_arc(a)\n\n# guesses\na.center roughly (0,0)\n"
+                   "a.a roughly (1,0)\na.b roughly (0,1)\n").to_constraint_system()
+    assert len(cs.constraints) == 1 and cs.constraints["kind"][0] == ez.K_ARC
+    assert list(cs.constraints["ids"][0][:6]) == [0, 1, 2, 3, 4, 5]
+    cs = T.Problem("# constraints\ncircle c\nc.center = (1, 2)\nradius(c, 3)\n\n# guesses\nc.center roughly (0,0)\n"
+                   "c.radius roughly 1\n").to_constraint_system()
+    assert list(cs.constraints["kind"]) == [ez.K_FIXED, ez.K_FIXED, ez.K_CIRCLE_RADIUS]
+    assert [int(r["ids"][0]) for r in cs.constraints[:2]] == [0, 1] and int(cs.constraints["ids"][2][2]) == 2
+
+
+def test_variable_numbering_points_circles_arcs():
+    """executor.rs:41-108: points first, then circles (cx,cy,r), then arcs (a,b,center)."""
+    cs = ez.textual.Problem(wl.fixture_text("circle_tangent")).to_constraint_system()
+    assert cs.num_vars == 7 and cs.inner_points == ["p", "q"] and cs.inner_circles == ["a"]
+    tan = cs.constraints[cs.constraints["kind"] == ez.K_LINE_TANGENT_TO_CIRCLE][0]
+    assert list(tan["ids"][:7]) == [0, 1, 2, 3, 4, 5, 6] and tan["flags"] == 0
+    cs = ez.textual.Problem(wl.fixture_text("parc_coincident")).to_constraint_system()
+    pac = cs.constraints[cs.constraints["kind"] == ez.K_POINT_ARC_COINCIDENT][0]
+    assert list(pac["ids"]) == [2, 3, 4, 5, 6, 7, 0, 1]
+    assert list(cs.initial_guesses) == [4, 3, 0, 4, 4, 0, 0.1, 0.2]
+
+
+def test_shard_range():
+    L = native.lib()
+    for batch, world in [(65536, 8), (10, 3), (5, 8), (0, 4), (1000003, 7)]:
+        covered = []
+        for rank in range(world):
+            b, e = C.c_uint64(), C.c_uint64()
+            L.ezpz_b200_shard_range(batch, rank, world, C.byref(b), C.byref(e))
+            covered.append((b.value, e.value))
+        assert covered[0][0] == 0 and covered[-1][1] == batch
+        assert all(covered[k][1] == covered[k + 1][0] for k in range(world - 1))
+        sizes = [e - b for b, e in covered]
+        assert max(sizes) - min(sizes) <= 1
+
+
+def test_host_math_matches_oracle_bitwise():
+    """The product's own libm restatement (dmath.cuh, host side) against the oracle's, bit for bit."""
+    rng = np.random.default_rng(2)
+    L, O = native.lib(), orc.lib()
+    for k in range(20000):
+        a, b = rng.uniform(-1, 1, 2) * 10.0 ** rng.integers(-12, 12)
+        assert L.ezpz_b200_hypot(a, b) == O.orc_fn_hypot(a, b)
+        s, c = ez.angle_sincos(a)
+        assert s == O.orc_fn_sin(a) and c == O.orc_fn_cos(a)
+    for a in [0.0, -0.0, np.pi, np.pi / 2, -np.pi / 4, 1e-30, 0.7853981633974483, 0.7853981633974484, 1e5, -3e5]:
+        s, c = ez.angle_sincos(a)
+        assert s == O.orc_fn_sin(a) and c == O.orc_fn_cos(a)
+
+
+def test_no_gpu_fails_loudly():
+    """Without a CUDA device the product path must fail, not fall back."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(ez.EzpzError) as e:
+        ez.Context(0)
+    assert e.value.name in ("NoDevice", "Cuda")
+    with pytest.raises(Exception):
+        ez.solve([ez.ConstraintRequest.highest_priority(ez.Constraint.Fixed(0, 0.0))], [(0, 1.0)])
+    # the one case that needs no device: an empty request list returns the guesses (lib.rs:155-170)
+    out = ez.solve([], [(0, 0.5)])
+    assert list(out.final_values()) == [0.5] and out.iterations() == 0 and out.converged()
