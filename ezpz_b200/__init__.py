@@ -608,6 +608,18 @@ class Context:
             raise EzpzError(rc, det)
         return r, jc, jr, dg
 
+    def large_bench(self, st, x, which, reps=20):
+        """(mean microseconds per launch, algorithmic bytes) of a stand-alone large-path kernel:
+        which 0 = assembly, 1 = SpMV J p, 2 = SpMV Jt q."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        us, by = C.c_double(), C.c_double()
+        det = native.ErrorDetail()
+        rc = native.lib().ezpz_b200_large_bench(self.handle, st.handle, native.ptr(x), int(which), int(reps),
+                                                C.byref(us), C.byref(by), C.byref(det))
+        if rc != 0:
+            raise EzpzError(rc, det)
+        return us.value, by.value
+
     def freedom_analysis(self, st, jacobian):
         j = np.ascontiguousarray(jacobian, dtype=np.float64).reshape(-1, st.nnz)
         B = j.shape[0]

@@ -1,15 +1,646 @@
-// large.cu — single large systems (placeholder until the sparse path lands in this round).
+// large.cu — one large system on the device: the whole Levenberg–Marquardt loop of
+// ezpz/src/solver/newton.rs:29-145 for systems that do not fit the thread-per-problem kernel (configs 3 and
+// 4 of BASELINE.json: massive_parallel_system at 2,000 x 2,000 and the synthetic 1M-variable sketch).
+//
+// One persistent cooperative kernel (lm_large_kernel) runs assembly, the damped step solve, the tentative
+// step, accept/reject, lambda adaptation and both convergence tests; the host launches it once and reads the
+// result.  Phases are separated by grid-wide barriers (a single __syncthreads when the system is small
+// enough for one CTA, which keeps a 2,000-variable solve at a few tens of microseconds).
+//   * assembly      one thread per constraint, kind-sorted order so that warps are mostly kind-uniform;
+//                   residuals to r, partials through precomputed slots into J (CSC order) and a CSR-ordered
+//                   copy for the row-wise SpMV (Model::residual / refresh_jacobian, solver.rs:318-440);
+//   * step solve    (a) level-scheduled sparse Cholesky when the dependency depth of the natural-order
+//                   factorisation is small (block-diagonal systems such as massive_parallel_system): same
+//                   arithmetic-order spec as the small path, so results match the oracle bit for bit;
+//                   (b) otherwise Jacobi-preconditioned conjugate gradients on (JtJ + lambda I) d = -Jt r,
+//                   applied matrix-free as Jt (J p) + lambda p with two SpMVs per iteration;
+//   * sum r^2       a strictly sequential left fold, as Rust's `.map(|x| x * x).sum()` is (newton.rs:45,116):
+//                   the accept test `S' < S` is a floating-point tie-breaker, so the summation order is part
+//                   of the reference semantics.  One thread adds from shared-memory chunks that the whole CTA
+//                   stages; max|r| and max|d| are order-independent and are reduced in parallel.
+// spmv_csr_kernel / assemble_large_kernel are also exported as stand-alone launches (ezpz_b200_large_bench)
+// so that their HBM throughput can be timed with CUDA events and profiled with ncu.
+#include <cooperative_groups.h>
+
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
 #include "device.h"
+#include "eval.cuh"
+
+namespace cg = cooperative_groups;
+using namespace ezs;
+
+namespace {
+
+__constant__ uint8_t cl_rows[EZPZ_K_COUNT];
+__constant__ uint8_t cl_emit_len[EZPZ_K_COUNT][2];
+
+struct LargeCtrl {
+    double lambda, S, S2, largest, step;
+    double rz, bb;
+    uint32_t iterations, converged, fail, done;
+    uint32_t any_unsat, any_degen, lin_iters, pad;
+};
+
+struct LargeArgs {
+    const DevCons* cons;
+    const uint32_t* cons_order;
+    const uint32_t *csr_row_ptr, *csr_col_idx, *csc_col_ptr, *csc_row_idx, *csc_to_csr;
+    // direct path
+    const uint32_t *level_ptr, *op_dst, *op_fin, *op_code, *op_ptr, *pair_a, *pair_b;
+    double* vg;          // [x | r | rn | J csc | L | d]
+    double* jr;          // J values in CSR order (PCG path)
+    double* cgv;         // PCG vectors: p, res, ap, dinv (n each), q (m)
+    double* partials;    // 3 * gridDim.x
+    uint8_t* side;       // resolved side per constraint
+    uint32_t* degen;     // per-constraint Warning::Degenerate counters
+    uint32_t* unsat;     // bit mask
+    LargeCtrl* ctrl;
+    double residual_tolerance, step_tolerance, initial_lambda, cg_rtol;
+    uint32_t max_iterations, cg_max_iters;
+    uint32_t n_cons, n, m, nnz, n_levels;
+    uint32_t X0, R0, RN0, J0, L0, D0;
+    uint32_t direct;
+};
+
+struct GX {
+    const double* p;
+    __device__ __forceinline__ double operator()(uint32_t id) const { return p[id]; }
+};
+
+// Assembly of all constraints by the calling thread set (grid-stride).  mode bit0: residuals into
+// vg[rdst + row]; bit1: Jacobian values; weighted unless `unweighted_check` (post-solve verdict).
+template <bool RES, bool JAC>
+__device__ void assemble_phase(const LargeArgs& a, uint32_t rdst, uint32_t tid, uint32_t nth, bool write_jr) {
+    const GX X{a.vg + a.X0};
+    for (uint32_t k = tid; k < a.n_cons; k += nth) {
+        const uint32_t c = a.cons_order[k];
+        const DevCons& dc = a.cons[c];
+        ezd::EvalOut o;
+        ezd::eval_constraint<JAC>(dc.kind, a.side[c], dc.ids, dc.p0, dc.p1, X, o);
+        const double w = dc.weight;
+        const uint32_t rows = cl_rows[dc.kind];
+        uint32_t ndeg = 0;
+        if (RES) {
+            a.vg[rdst + dc.row0] = w * o.res[0];
+            if (rows == 2) a.vg[rdst + dc.row0 + 1] = w * o.res[1];
+            if (o.res_degen) ++ndeg;
+        }
+        if (JAC) {
+            if (o.jac_degen) ++ndeg;
+#pragma unroll
+            for (int row = 0; row < 2; ++row) {
+                if (row < (int)rows) {
+                    const uint32_t len = cl_emit_len[dc.kind][row];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        if (q < (int)len) {
+                            const uint32_t s = dc.slot[row][q];
+                            const uint32_t slot = s & ~kAccumulate;
+                            double* dst = a.vg + a.J0 + slot;
+                            double v;
+                            if (s & kAccumulate) v = o.emit[row] ? *dst + w * o.pd[row][q] : *dst;
+                            else v = o.emit[row] ? 0.0 + w * o.pd[row][q] : 0.0;
+                            *dst = v;
+                            if (write_jr) a.jr[a.csc_to_csr[slot]] = v;
+                        }
+                    }
+                }
+            }
+        }
+        if (ndeg) {
+            a.degen[c] += ndeg;
+            a.ctrl->any_degen = 1;
+        }
+    }
+}
+
+// NaN-ignoring max |v[i]| over the grid: per-block partial to partials[blockIdx.x]; caller syncs, then every
+// thread folds the partials (same order everywhere).
+__device__ void max_abs_partial(const double* v, uint32_t count, uint32_t tid, uint32_t nth, double* partial_out,
+                                double* sm) {
+    double mx = __longlong_as_double(0x7ff8000000000000LL);  // NaN: identity of the NaN-ignoring max
+    for (uint32_t i = tid; i < count; i += nth) mx = ezm::ez_fmax(mx, ezm::ez_abs(v[i]));
+    sm[threadIdx.x] = mx;
+    __syncthreads();
+    for (uint32_t s = blockDim.x / 2; s > 0; s >>= 1) {
+        if (threadIdx.x < s) sm[threadIdx.x] = ezm::ez_fmax(sm[threadIdx.x], sm[threadIdx.x + s]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *partial_out = sm[0];
+    __syncthreads();
+}
+__device__ double fold_max(const double* partials, uint32_t count) {
+    double mx = partials[0];
+    for (uint32_t i = 1; i < count; ++i) mx = ezm::ez_fmax(mx, partials[i]);
+    return mx;
+}
+// Deterministic block sum (fixed tree) of one value per thread -> partial_out.
+__device__ void block_sum(double v, double* partial_out, double* sm) {
+    sm[threadIdx.x] = v;
+    __syncthreads();
+    for (uint32_t s = blockDim.x / 2; s > 0; s >>= 1) {
+        if (threadIdx.x < s) sm[threadIdx.x] = sm[threadIdx.x] + sm[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *partial_out = sm[0];
+    __syncthreads();
+}
+__device__ double fold_sum(const double* partials, uint32_t count) {
+    double s = 0.0;
+    for (uint32_t i = 0; i < count; ++i) s = s + partials[i];
+    return s;
+}
+
+// Sequential left fold of v[i]^2 (block 0 only): the CTA stages squares in shared memory chunk by chunk, one
+// thread adds them in index order.
+__device__ void sequential_sum_squares(const double* v, uint32_t count, double* out, double* sm, uint32_t sm_len) {
+    double acc = 0.0;
+    for (uint32_t base = 0; base < count; base += sm_len) {
+        const uint32_t len = min(sm_len, count - base);
+        for (uint32_t i = threadIdx.x; i < len; i += blockDim.x) {
+            const double r = v[base + i];
+            sm[i] = r * r;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t i = 0;
+            for (; i + 8 <= len; i += 8) {
+                const double s0 = sm[i], s1 = sm[i + 1], s2 = sm[i + 2], s3 = sm[i + 3];
+                const double s4 = sm[i + 4], s5 = sm[i + 5], s6 = sm[i + 6], s7 = sm[i + 7];
+                acc = acc + s0; acc = acc + s1; acc = acc + s2; acc = acc + s3;
+                acc = acc + s4; acc = acc + s5; acc = acc + s6; acc = acc + s7;
+            }
+            for (; i < len; ++i) acc = acc + sm[i];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out = acc;
+}
+
+constexpr uint32_t kBlock = 512;
+constexpr uint32_t kSmDoubles = 4096;  // 32 KB staging
+
+__global__ void __launch_bounds__(kBlock) lm_large_kernel(const LargeArgs a) {
+    __shared__ double sm[kSmDoubles];
+    cg::grid_group grid = cg::this_grid();
+    const bool single = gridDim.x == 1;
+    auto sync = [&]() {
+        if (single) __syncthreads();
+        else grid.sync();
+    };
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    const uint32_t G = gridDim.x;
+    LargeCtrl* ctrl = a.ctrl;
+    double* vg = a.vg;
+    double* pm = a.partials;           // max / pAp
+    double* ps1 = a.partials + G;      // rz
+    double* ps2 = a.partials + 2 * G;  // rr
+    const bool use_cg = !a.direct;
+
+    // sides from the initial guesses (lib.rs:183-186), counters
+    {
+        const GX X{vg + a.X0};
+        for (uint32_t c = tid; c < a.n_cons; c += nth) {
+            const DevCons& dc = a.cons[c];
+            a.side[c] = (uint8_t)ezd::resolve_side(dc.kind, dc.flags, dc.ids, X);
+            a.degen[c] = 0;
+        }
+        for (uint32_t w = tid; w < (a.n_cons + 31) / 32; w += nth) a.unsat[w] = 0;
+        if (tid == 0) {
+            ctrl->lambda = a.initial_lambda;
+            ctrl->iterations = a.max_iterations;
+            ctrl->converged = 0;
+            ctrl->fail = 0;
+            ctrl->any_unsat = 0;
+            ctrl->any_degen = 0;
+            ctrl->lin_iters = 0;
+        }
+    }
+    sync();
+    assemble_phase<true, true>(a, a.R0, tid, nth, use_cg);
+    sync();
+    if (blockIdx.x == 0) sequential_sum_squares(vg + a.R0, a.m, &ctrl->S, sm, kSmDoubles);
+    sync();
+
+    double lambda = a.initial_lambda, S = ctrl->S;
+    uint32_t iterations = a.max_iterations;
+    bool converged = false;
+    uint32_t lin_iters = 0;
+    for (uint32_t it = 0; it < a.max_iterations; ++it) {
+        max_abs_partial(vg + a.R0, a.m, tid, nth, &pm[blockIdx.x], sm);
+        sync();
+        const double largest = fold_max(pm, G);
+        if (largest <= a.residual_tolerance) {
+            iterations = it;
+            converged = true;
+            break;
+        }
+        bool fail = false;
+        if (!use_cg) {
+            // level-scheduled direct solve (same op semantics as run_tape in device.cu)
+            for (uint32_t lv = 0; lv < a.n_levels; ++lv) {
+                const uint32_t ob = a.level_ptr[lv], oe = a.level_ptr[lv + 1];
+                for (uint32_t o = ob + tid; o < oe; o += nth) {
+                    const uint32_t dst = a.op_dst[o], code = a.op_code[o];
+                    double acc = (code & OP_INIT_DST) ? vg[dst] : 0.0;
+                    const uint32_t pb = a.op_ptr[o], pe = a.op_ptr[o + 1];
+                    if (code & OP_NEGATE)
+                        for (uint32_t q = pb; q < pe; ++q) acc = __fma_rn(-vg[a.pair_a[q]], vg[a.pair_b[q]], acc);
+                    else
+                        for (uint32_t q = pb; q < pe; ++q) acc = __fma_rn(vg[a.pair_a[q]], vg[a.pair_b[q]], acc);
+                    const uint32_t fk = (code >> OP_FIN_SHIFT) & 3u;
+                    if (fk == OP_FIN_LAMBDA) acc = __dadd_rn(acc, lambda);
+                    else if (fk == OP_FIN_MUL) acc = __dmul_rn(acc, vg[a.op_fin[o]]);
+                    else if (fk == OP_FIN_PIVOT) {
+                        if (!(acc > 0.0) || !ezm::ez_isfinite(acc)) ctrl->fail = 1;
+                        acc = __ddiv_rn(1.0, __dsqrt_rn(acc));
+                    }
+                    vg[dst] = acc;
+                }
+                sync();
+            }
+            fail = ctrl->fail != 0;
+        } else {
+            // Jacobi-preconditioned CG on (JtJ + lambda I) d = -Jt r
+            double* p = a.cgv;
+            double* res = p + a.n;
+            double* ap = res + a.n;
+            double* dinv = ap + a.n;
+            double* q = dinv + a.n;
+            double* d = vg + a.D0;
+            const double* jv = vg + a.J0;
+            const double* r = vg + a.R0;
+            double lrz = 0.0, lbb = 0.0;
+            for (uint32_t j = tid; j < a.n; j += nth) {
+                double b = 0.0, dg = 0.0;
+                for (uint32_t e = a.csc_col_ptr[j]; e < a.csc_col_ptr[j + 1]; ++e) {
+                    const double v = jv[e];
+                    b = __fma_rn(v, -r[a.csc_row_idx[e]], b);
+                    dg = __fma_rn(v, v, dg);
+                }
+                const double di = 1.0 / (dg + lambda);
+                dinv[j] = di;
+                d[j] = 0.0;
+                res[j] = b;
+                const double z = di * b;
+                p[j] = z;
+                lrz += b * z;
+                lbb += b * b;
+            }
+            block_sum(lrz, &ps1[blockIdx.x], sm);
+            block_sum(lbb, &ps2[blockIdx.x], sm);
+            sync();
+            double rz = fold_sum(ps1, G);
+            const double bb = fold_sum(ps2, G);
+            const double stop = a.cg_rtol * a.cg_rtol * bb;
+            if (bb > 0.0) {
+                for (uint32_t k = 0; k < a.cg_max_iters; ++k) {
+                    for (uint32_t i = tid; i < a.m; i += nth) {  // q = J p
+                        double s = 0.0;
+                        for (uint32_t e = a.csr_row_ptr[i]; e < a.csr_row_ptr[i + 1]; ++e) s = __fma_rn(a.jr[e], p[a.csr_col_idx[e]], s);
+                        q[i] = s;
+                    }
+                    sync();
+                    double lpap = 0.0;
+                    for (uint32_t j = tid; j < a.n; j += nth) {  // ap = Jt q + lambda p
+                        double s = lambda * p[j];
+                        for (uint32_t e = a.csc_col_ptr[j]; e < a.csc_col_ptr[j + 1]; ++e) s = __fma_rn(jv[e], q[a.csc_row_idx[e]], s);
+                        ap[j] = s;
+                        lpap += p[j] * s;
+                    }
+                    block_sum(lpap, &pm[blockIdx.x], sm);
+                    sync();
+                    const double pap = fold_sum(pm, G);
+                    ++lin_iters;
+                    if (!(pap > 0.0) || !ezm::ez_isfinite(pap)) {
+                        fail = true;
+                        break;
+                    }
+                    const double alpha = rz / pap;
+                    double lrz2 = 0.0, lrr = 0.0;
+                    for (uint32_t j = tid; j < a.n; j += nth) {
+                        d[j] = d[j] + alpha * p[j];
+                        const double rj = res[j] - alpha * ap[j];
+                        res[j] = rj;
+                        lrz2 += rj * (dinv[j] * rj);
+                        lrr += rj * rj;
+                    }
+                    block_sum(lrz2, &ps1[blockIdx.x], sm);
+                    block_sum(lrr, &ps2[blockIdx.x], sm);
+                    sync();
+                    const double rz2 = fold_sum(ps1, G);
+                    const double rr = fold_sum(ps2, G);
+                    if (rr <= stop) break;
+                    const double beta = rz2 / rz;
+                    rz = rz2;
+                    for (uint32_t j = tid; j < a.n; j += nth) p[j] = dinv[j] * res[j] + beta * p[j];
+                    sync();
+                }
+            }
+            sync();
+        }
+        if (fail) {
+            sync();
+            if (tid == 0) ctrl->fail = 0;
+            lambda *= 10.0;
+            sync();
+            continue;
+        }
+        max_abs_partial(vg + a.D0, a.n, tid, nth, &pm[blockIdx.x], sm);
+        sync();
+        const double step = fold_max(pm, G);
+        for (uint32_t j = tid; j < a.n; j += nth) vg[a.X0 + j] += vg[a.D0 + j];
+        sync();
+        assemble_phase<true, false>(a, a.RN0, tid, nth, false);
+        sync();
+        if (blockIdx.x == 0) sequential_sum_squares(vg + a.RN0, a.m, &ctrl->S2, sm, kSmDoubles);
+        sync();
+        const double S2 = ctrl->S2;
+        if (S2 < S) {
+            for (uint32_t i = tid; i < a.m; i += nth) vg[a.R0 + i] = vg[a.RN0 + i];
+            assemble_phase<false, true>(a, a.R0, tid, nth, use_cg);
+            S = S2;
+            lambda *= 0.1;
+        } else {
+            for (uint32_t j = tid; j < a.n; j += nth) vg[a.X0 + j] -= vg[a.D0 + j];
+            lambda *= 10.0;
+        }
+        sync();
+        if (step <= a.step_tolerance) {
+            iterations = it;
+            converged = true;
+            break;
+        }
+    }
+    // post-solve verdict (lib.rs:305-327): unweighted residuals, |r| < 1e-4 per component
+    {
+        const GX X{vg + a.X0};
+        for (uint32_t c = tid; c < a.n_cons; c += nth) {
+            const DevCons& dc = a.cons[c];
+            ezd::EvalOut o;
+            ezd::eval_constraint<false>(dc.kind, a.side[c], dc.ids, dc.p0, dc.p1, X, o);
+            bool sat = ezm::ez_abs(o.res[0]) < ezd::kEps;
+            if (cl_rows[dc.kind] == 2) sat = sat && (ezm::ez_abs(o.res[1]) < ezd::kEps);
+            if (!sat) {
+                atomicOr(&a.unsat[c >> 5], 1u << (c & 31u));
+                ctrl->any_unsat = 1;
+            }
+        }
+    }
+    if (tid == 0) {
+        ctrl->iterations = iterations;
+        ctrl->converged = converged ? 1u : 0u;
+        ctrl->lambda = lambda;
+        ctrl->S = S;
+        ctrl->lin_iters = lin_iters;
+    }
+}
+
+// ---- stand-alone kernels for throughput measurement (same device code as the phases above) ------------
+__global__ void __launch_bounds__(256) assemble_large_kernel(const LargeArgs a) {
+    assemble_phase<true, true>(a, a.R0, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x, true);
+}
+__global__ void __launch_bounds__(256) spmv_csr_kernel(const uint32_t* __restrict__ row_ptr, const uint32_t* __restrict__ col_idx,
+                                                       const double* __restrict__ vals, const double* __restrict__ x,
+                                                       double* __restrict__ y, uint32_t rows) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < rows; i += gridDim.x * blockDim.x) {
+        double s = 0.0;
+        for (uint32_t e = row_ptr[i]; e < row_ptr[i + 1]; ++e) s = __fma_rn(vals[e], x[col_idx[e]], s);
+        y[i] = s;
+    }
+}
+
+struct LargeDevice {
+    uint32_t *cons_order = nullptr, *csr_row_ptr = nullptr, *csr_col_idx = nullptr, *csc_col_ptr = nullptr, *csc_row_idx = nullptr;
+    uint32_t *level_ptr = nullptr, *op_dst = nullptr, *op_fin = nullptr, *op_code = nullptr, *op_ptr = nullptr, *pair_a = nullptr, *pair_b = nullptr;
+    double *vg = nullptr, *jr = nullptr, *cgv = nullptr, *partials = nullptr;
+    uint8_t* side = nullptr;
+    uint32_t *degen = nullptr, *unsat = nullptr;
+    LargeCtrl* ctrl = nullptr;
+    int grid = 0;
+    bool tables = false;
+};
+
+template <class T>
+int32_t upload(T** dst, const std::vector<T>& src, ezpz_error_detail_t* detail) {
+    if (src.empty()) {
+        EZ_CUDA(cudaMalloc(dst, sizeof(T)), "cudaMalloc");
+        return EZPZ_OK;
+    }
+    EZ_CUDA(cudaMalloc(dst, sizeof(T) * src.size()), "cudaMalloc");
+    EZ_CUDA(cudaMemcpy(*dst, src.data(), sizeof(T) * src.size(), cudaMemcpyHostToDevice), "cudaMemcpy");
+    return EZPZ_OK;
+}
+#define EZ_TRY(x)                    \
+    do {                             \
+        int32_t rc__ = (x);          \
+        if (rc__ != EZPZ_OK) return rc__; \
+    } while (0)
+
+int32_t get_large(ezpz_context* ctx, const ezpz_structure* s, DeviceCopy* dc, LargeDevice** out, ezpz_error_detail_t* detail) {
+    if (dc->large) {
+        *out = (LargeDevice*)dc->large;
+        return EZPZ_OK;
+    }
+    const LargeProgram& P = s->large;
+    LargeDevice* L = new (std::nothrow) LargeDevice();
+    if (!L) return EZPZ_ERR_INVALID_ARGUMENT;
+    dc->large = L;  // owned by the device copy from here on (released with it)
+    EZ_TRY(upload(&L->cons_order, P.cons_order, detail));
+    EZ_TRY(upload(&L->csr_row_ptr, s->csr_row_ptr, detail));
+    EZ_TRY(upload(&L->csr_col_idx, s->csr_col_idx, detail));
+    EZ_TRY(upload(&L->csc_col_ptr, s->csc_col_ptr, detail));
+    EZ_TRY(upload(&L->csc_row_idx, s->csc_row_idx, detail));
+    EZ_TRY(upload(&L->level_ptr, P.level_ptr, detail));
+    EZ_TRY(upload(&L->op_dst, P.op_dst, detail));
+    EZ_TRY(upload(&L->op_fin, P.op_fin, detail));
+    EZ_TRY(upload(&L->op_code, P.op_code, detail));
+    EZ_TRY(upload(&L->op_ptr, P.op_ptr, detail));
+    EZ_TRY(upload(&L->pair_a, P.pair_a, detail));
+    EZ_TRY(upload(&L->pair_b, P.pair_b, detail));
+    const size_t nnz = s->csc_row_idx.size();
+    EZ_CUDA(cudaMalloc(&L->vg, sizeof(double) * std::max<size_t>(1, P.VG)), "cudaMalloc(vg)");
+    EZ_CUDA(cudaMemset(L->vg, 0, sizeof(double) * std::max<size_t>(1, P.VG)), "cudaMemset(vg)");
+    EZ_CUDA(cudaMalloc(&L->jr, sizeof(double) * std::max<size_t>(1, nnz)), "cudaMalloc(jr)");
+    EZ_CUDA(cudaMalloc(&L->cgv, sizeof(double) * (4 * (size_t)s->n + s->m + 1)), "cudaMalloc(cgv)");
+    EZ_CUDA(cudaMalloc(&L->side, std::max<size_t>(1, s->n_cons)), "cudaMalloc(side)");
+    EZ_CUDA(cudaMalloc(&L->degen, sizeof(uint32_t) * std::max<size_t>(1, s->n_cons)), "cudaMalloc(degen)");
+    EZ_CUDA(cudaMalloc(&L->unsat, sizeof(uint32_t) * ((s->n_cons + 31) / 32 + 1)), "cudaMalloc(unsat)");
+    EZ_CUDA(cudaMalloc(&L->ctrl, sizeof(LargeCtrl)), "cudaMalloc(ctrl)");
+    // grid: one CTA for small systems (barriers are __syncthreads), else every SM, co-resident
+    const size_t work = (size_t)s->n + s->m + nnz;
+    int per_sm = 0;
+    EZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lm_large_kernel, kBlock, 0), "occupancy");
+    if (per_sm < 1) per_sm = 1;
+    L->grid = work <= 65536 ? 1 : ctx->sm_count * std::min(per_sm, 2);
+    EZ_CUDA(cudaMalloc(&L->partials, sizeof(double) * 3 * (size_t)L->grid), "cudaMalloc(partials)");
+    uint8_t rows[EZPZ_K_COUNT], emit_len[EZPZ_K_COUNT][2];
+    for (int k = 0; k < EZPZ_K_COUNT; ++k) {
+        rows[k] = ezk::kKinds[k].rows;
+        emit_len[k][0] = ezk::kKinds[k].emit_len[0];
+        emit_len[k][1] = ezk::kKinds[k].emit_len[1];
+    }
+    EZ_CUDA(cudaMemcpyToSymbol(cl_rows, rows, sizeof rows), "cudaMemcpyToSymbol");
+    EZ_CUDA(cudaMemcpyToSymbol(cl_emit_len, emit_len, sizeof emit_len), "cudaMemcpyToSymbol");
+    *out = L;
+    return EZPZ_OK;
+}
+
+void fill_args(LargeArgs& a, const ezpz_structure* s, const DeviceCopy* dc, const LargeDevice* L, const ezpz_config_t* config) {
+    const LargeProgram& P = s->large;
+    std::memset(&a, 0, sizeof a);
+    a.cons = dc->cons;
+    a.cons_order = L->cons_order;
+    a.csr_row_ptr = L->csr_row_ptr;
+    a.csr_col_idx = L->csr_col_idx;
+    a.csc_col_ptr = L->csc_col_ptr;
+    a.csc_row_idx = L->csc_row_idx;
+    a.csc_to_csr = dc->csc_to_csr;
+    a.level_ptr = L->level_ptr;
+    a.op_dst = L->op_dst;
+    a.op_fin = L->op_fin;
+    a.op_code = L->op_code;
+    a.op_ptr = L->op_ptr;
+    a.pair_a = L->pair_a;
+    a.pair_b = L->pair_b;
+    a.vg = L->vg;
+    a.jr = L->jr;
+    a.cgv = L->cgv;
+    a.partials = L->partials;
+    a.side = L->side;
+    a.degen = L->degen;
+    a.unsat = L->unsat;
+    a.ctrl = L->ctrl;
+    a.residual_tolerance = config->residual_tolerance;
+    a.step_tolerance = config->step_tolerance;
+    a.initial_lambda = config->initial_lambda;
+    a.cg_rtol = 1e-13;
+    a.max_iterations = (uint32_t)std::min<uint64_t>(config->max_iterations, 0x7fffffffu);
+    a.cg_max_iters = 20000;
+    a.n_cons = s->n_cons;
+    a.n = s->n;
+    a.m = s->m;
+    a.nnz = (uint32_t)s->csc_row_idx.size();
+    a.n_levels = P.n_levels;
+    a.X0 = P.X0;
+    a.R0 = P.R0;
+    a.RN0 = P.RN0;
+    a.J0 = P.J0;
+    a.L0 = P.L0;
+    a.D0 = P.D0;
+    a.direct = P.direct ? 1u : 0u;
+}
+
+}  // namespace
 
 namespace ezs {
 
-void release_large(DeviceCopy* d) { (void)d; }
+void release_large(DeviceCopy* d) {
+    LargeDevice* L = (LargeDevice*)d->large;
+    if (!L) return;
+    void* ptrs[] = {L->cons_order, L->csr_row_ptr, L->csr_col_idx, L->csc_col_ptr, L->csc_row_idx, L->level_ptr, L->op_dst,
+                    L->op_fin, L->op_code, L->op_ptr, L->pair_a, L->pair_b, L->vg, L->jr, L->cgv, L->partials, L->side,
+                    L->degen, L->unsat, L->ctrl};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    delete L;
+    d->large = nullptr;
+}
 
 int32_t solve_large(ezpz_context* ctx, const ezpz_structure* s, const ezpz_config_t* config, const ezpz_one_io_t* io,
                     ezpz_error_detail_t* detail) {
-    (void)ctx; (void)s; (void)config; (void)io;
-    if (detail) std::snprintf(detail->message, sizeof detail->message, "large-system path not built yet");
-    return EZPZ_ERR_TOO_LARGE;
+    if (!s->large.built) return EZPZ_ERR_TOO_LARGE;
+    if (s->n_cons == 0 || s->m == 0) return EZPZ_ERR_EMPTY_SYSTEM;
+    EZ_CUDA(cudaSetDevice(ctx->device), "cudaSetDevice");
+    DeviceCopy* dc = nullptr;
+    EZ_TRY(get_device_copy(ctx, s, &dc, detail));
+    LargeDevice* L = nullptr;
+    EZ_TRY(get_large(ctx, s, dc, &L, detail));
+    LargeArgs a;
+    fill_args(a, s, dc, L, config);
+    cudaStream_t st = ctx->stream;
+    EZ_CUDA(cudaMemcpyAsync(L->vg + a.X0, io->guesses, sizeof(double) * s->n, cudaMemcpyHostToDevice, st), "H2D guesses");
+    void* params[] = {(void*)&a};
+    if (L->grid == 1) {
+        lm_large_kernel<<<1, kBlock, 0, st>>>(a);
+    } else {
+        EZ_CUDA(cudaLaunchCooperativeKernel((void*)lm_large_kernel, dim3(L->grid), dim3(kBlock), params, 0, st),
+                "cudaLaunchCooperativeKernel(lm_large_kernel)");
+    }
+    ctx->launches += 1;
+    EZ_CUDA(cudaGetLastError(), "lm_large_kernel launch");
+    LargeCtrl h;
+    EZ_CUDA(cudaMemcpyAsync(&h, L->ctrl, sizeof h, cudaMemcpyDeviceToHost, st), "D2H ctrl");
+    EZ_CUDA(cudaMemcpyAsync(io->final_values, L->vg + a.X0, sizeof(double) * s->n, cudaMemcpyDeviceToHost, st), "D2H finals");
+    if (io->unsat_mask)
+        EZ_CUDA(cudaMemcpyAsync(io->unsat_mask, L->unsat, sizeof(uint32_t) * ((s->n_cons + 31) / 32), cudaMemcpyDeviceToHost, st), "D2H unsat");
+    if (io->degen_count)
+        EZ_CUDA(cudaMemcpyAsync(io->degen_count, L->degen, sizeof(uint32_t) * s->n_cons, cudaMemcpyDeviceToHost, st), "D2H degen");
+    if (io->jacobian)
+        EZ_CUDA(cudaMemcpyAsync(io->jacobian, L->vg + a.J0, sizeof(double) * a.nnz, cudaMemcpyDeviceToHost, st), "D2H jacobian");
+    EZ_CUDA(cudaStreamSynchronize(st), "cudaStreamSynchronize");
+    *io->iterations = h.iterations;
+    *io->status = (uint8_t)((h.converged ? EZPZ_ST_CONVERGED : 0u) | (h.any_unsat ? EZPZ_ST_UNSATISFIED : 0u) |
+                            (h.any_degen ? EZPZ_ST_DEGENERATE : 0u));
+    if (io->path_used) *io->path_used = s->large.direct ? 1 : 2;
+    if (io->lin_iters) *io->lin_iters = h.lin_iters;
+    return EZPZ_OK;
 }
 
 }  // namespace ezs
+
+// Stand-alone launches of the assembly and SpMV kernels on a structure's large-system buffers, timed with
+// CUDA events: reps launches each, returns mean microseconds per launch and the algorithmic bytes moved
+// (SURVEY.md §8d formulas).  x must hold n doubles.  which: 0 assembly, 1 SpMV y = J p (CSR), 2 SpMV z = Jt q (CSC).
+extern "C" int32_t ezpz_b200_large_bench(ezpz_context_t* ctx, const ezpz_structure_t* s, const double* x, int32_t which,
+                                         int32_t reps, double* mean_us, double* algorithmic_bytes,
+                                         ezpz_error_detail_t* detail) {
+    if (!ctx || !s || !x || !mean_us || reps < 1) return EZPZ_ERR_INVALID_ARGUMENT;
+    if (detail) std::memset(detail, 0, sizeof *detail);
+    if (!s->large.built) return EZPZ_ERR_UNSUPPORTED;
+    EZ_CUDA(cudaSetDevice(ctx->device), "cudaSetDevice");
+    DeviceCopy* dc = nullptr;
+    EZ_TRY(get_device_copy(ctx, s, &dc, detail));
+    LargeDevice* L = nullptr;
+    EZ_TRY(get_large(ctx, s, dc, &L, detail));
+    ezpz_config_t cfg;
+    ezpz_b200_config_default(&cfg);
+    LargeArgs a;
+    fill_args(a, s, dc, L, &cfg);
+    cudaStream_t st = ctx->stream;
+    EZ_CUDA(cudaMemcpyAsync(L->vg + a.X0, x, sizeof(double) * s->n, cudaMemcpyHostToDevice, st), "H2D x");
+    EZ_CUDA(cudaMemsetAsync(L->side, 1, s->n_cons, st), "memset side");
+    EZ_CUDA(cudaMemsetAsync(L->degen, 0, sizeof(uint32_t) * s->n_cons, st), "memset degen");
+    const unsigned grid = (unsigned)ctx->sm_count * 8;
+    const double n = s->n, m = s->m, nnz = (double)s->csc_row_idx.size(), C = s->n_cons;
+    cudaEvent_t e0, e1;
+    EZ_CUDA(cudaEventCreate(&e0), "cudaEventCreate");
+    EZ_CUDA(cudaEventCreate(&e1), "cudaEventCreate");
+    // one untimed launch first (also fills jr for the SpMVs)
+    assemble_large_kernel<<<grid, 256, 0, st>>>(a);
+    ctx->launches += 1;
+    EZ_CUDA(cudaEventRecord(e0, st), "cudaEventRecord");
+    for (int k = 0; k < reps; ++k) {
+        if (which == 0) assemble_large_kernel<<<grid, 256, 0, st>>>(a);
+        else if (which == 1) spmv_csr_kernel<<<grid, 256, 0, st>>>(L->csr_row_ptr, L->csr_col_idx, L->jr, L->vg + a.X0, L->cgv + 4 * (size_t)s->n, s->m);
+        else spmv_csr_kernel<<<grid, 256, 0, st>>>(L->csc_col_ptr, L->csc_row_idx, L->vg + a.J0, L->vg + a.R0, L->cgv, s->n);
+        ctx->launches += 1;
+    }
+    EZ_CUDA(cudaEventRecord(e1, st), "cudaEventRecord");
+    EZ_CUDA(cudaEventSynchronize(e1), "cudaEventSynchronize");
+    EZ_CUDA(cudaGetLastError(), "bench kernels");
+    float ms = 0.f;
+    EZ_CUDA(cudaEventElapsedTime(&ms, e0, e1), "cudaEventElapsedTime");
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *mean_us = (double)ms * 1e3 / reps;
+    if (algorithmic_bytes) {
+        if (which == 0) *algorithmic_bytes = 136.0 * C + 8 * n + 8 * m + 2 * 8 * nnz + 4 * nnz;  // records + x + r + J (two orders) + csr slot map
+        else if (which == 1) *algorithmic_bytes = 12 * nnz + 4 * (m + 1) + 8 * n + 8 * m;
+        else *algorithmic_bytes = 12 * nnz + 4 * (n + 1) + 8 * m + 8 * n;
+    }
+    return EZPZ_OK;
+}

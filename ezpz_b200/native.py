@@ -71,6 +71,8 @@ _SYMBOLS = [
     ("ezpz_b200_solve_batch_device", C.c_int32, [_P, _P, C.POINTER(Config), C.c_uint64, C.POINTER(BatchIO), _P, C.POINTER(ErrorDetail)]),
     ("ezpz_b200_shard_range", None, [C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     ("ezpz_b200_solve_one", C.c_int32, [_P, _P, C.POINTER(Config), C.POINTER(OneIO), C.POINTER(ErrorDetail)]),
+    ("ezpz_b200_large_bench", C.c_int32, [_P, _P, _P, C.c_int32, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                          C.POINTER(ErrorDetail)]),
     ("ezpz_b200_eval", C.c_int32, [_P, _P, _P, _P, _P, _P, _P, C.POINTER(ErrorDetail)]),
     ("ezpz_b200_freedom_analysis", C.c_int32, [_P, _P, C.c_uint64, _P, _P, C.POINTER(ErrorDetail)]),
     ("ezpz_b200_solve", C.c_int32, [_P, _P, _P, _P, C.c_uint32, _P, _P, C.c_uint32, C.POINTER(Config), C.c_int32,

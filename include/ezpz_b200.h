@@ -277,6 +277,14 @@ int32_t ezpz_b200_solve_one(ezpz_context_t* ctx, const ezpz_structure_t* s,
                             const ezpz_config_t* config, const ezpz_one_io_t* io,
                             ezpz_error_detail_t* detail);
 
+/* Stand-alone timing of the large-system kernels on a structure's device buffers (CUDA events, `reps`
+ * launches): which = 0 fused assembly (residual + Jacobian + scatter), 1 SpMV y = J p (CSR), 2 SpMV
+ * z = Jt q (CSC).  Returns mean microseconds per launch and the algorithmic bytes one launch moves
+ * (SURVEY.md §8d).  Only for structures that take the large path. */
+int32_t ezpz_b200_large_bench(ezpz_context_t* ctx, const ezpz_structure_t* s, const double* x,
+                              int32_t which, int32_t reps, double* mean_us, double* algorithmic_bytes,
+                              ezpz_error_detail_t* detail);
+
 /* ---------------------------------------------------------------------------------------------
  * Parity / debugging entry (the reference's `dbg-jac` feature, solver.rs:370-439): one evaluation
  * of the residual vector and the Jacobian values at `x` through the device assembly kernel.

@@ -1,0 +1,69 @@
+"""GPU parity for single large systems (configs 3 and 4 of BASELINE.json) through ezpz_b200_solve_one."""
+import os
+
+import numpy as np
+import pytest
+
+import ezpz_b200 as ez
+import orc
+import workloads as wl
+from test_gpu_parity import assert_bitwise
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("lines,over", [(500, False), (600, False), (500, True)])
+def test_massive_parallel_system_direct_path(ctx, lines, over):
+    """Config 3: 2,000 x 2,000 (README size), the checked-in 2,400 x 2,400 and the overconstrained variant.
+    Level-scheduled direct solve: bit-exact against the oracle."""
+    recs, n, g, _ = wl.system_from_text(wl.massive_problem_text(lines, over))
+    st = ez.Structure(recs, n)
+    out = ctx.solve_one(st, g)
+    assert out.path_used == 1
+    o = orc.solve_inner(recs, g)
+    assert out.iterations == o.iterations and out.converged and out.unsatisfied == []
+    if not over:
+        assert out.iterations == 2  # README.md:38 "Iterations needed: 2"
+    assert_bitwise(out.final_values, o.final_values, "final values")
+    for k in range(lines):  # every line ends up vertical at x = k, from y = 0 to y = 4
+        assert np.abs(out.final_values[4 * k:4 * k + 4] - [k, 0, k, 4]).max() < 1e-6
+
+
+def test_chain_sketch_direct_path_bitwise(ctx):
+    recs, n, g, exact = wl.chain_sketch(64)
+    st = ez.Structure(recs, n)
+    out = ctx.solve_one(st, g, want_jacobian=True)
+    assert out.path_used == 1
+    o = orc.solve_inner(recs, g)
+    assert out.iterations == o.iterations and out.converged == o.converged and out.unsatisfied == o.unsatisfied
+    assert_bitwise(out.final_values, o.final_values, "final values")
+    assert np.abs(out.final_values - exact).max() < 1e-6
+
+
+def test_chain_sketch_pcg_path(ctx):
+    """PCG path forced on a 13,312-variable sketch: the step is solved iteratively to 1e-13 relative residual,
+    so results agree with the oracle's direct solve to 1e-9 and the LM trajectory has the same length."""
+    os.environ["EZPZ_B200_FORCE_PCG"] = "1"
+    try:
+        recs, n, g, exact = wl.chain_sketch(1024)
+        st = ez.Structure(recs, n)
+    finally:
+        del os.environ["EZPZ_B200_FORCE_PCG"]
+    out = ctx.solve_one(st, g)
+    assert out.path_used == 2 and out.lin_iters > 0
+    o = orc.solve_inner(recs, g)
+    assert out.converged and out.unsatisfied == []
+    assert out.iterations == o.iterations
+    scale = np.maximum(1.0, np.abs(o.final_values))
+    assert (np.abs(out.final_values - o.final_values) <= 1e-9 * scale).all()
+
+
+def test_large_eval_matches_oracle_bitwise(ctx):
+    """Assembly kernel on a 13k-variable system: residuals and Jacobian values bit for bit."""
+    from test_gpu_parity import resolved
+    recs, n, g, exact = wl.chain_sketch(1024)
+    st = ez.Structure(recs, n)
+    r, jc, jr, dg = ctx.evaluate(st, g)
+    ro, jo, dgo, _ = orc.evaluate(resolved(recs, g), n, g)
+    assert_bitwise(r, ro, "residual")
+    assert_bitwise(jc, jo, "jacobian")

@@ -89,3 +89,93 @@ def mixed_batches(total, half_width=0.25):
         recs, n_vars, g = perturbed_batch(name, b, 0xE2B200D5EED00000 + (idx << 40), half_width)
         out.append((name, recs, n_vars, g))
     return out
+
+
+def chain_sketch(cells, seed=0xE2B20004, noise=0.05):
+    """Config 4 of BASELINE.json: a synthetic connected sketch of `cells` cells x 13 variables
+    mixing distances, angles, circle tangents and arcs, built through the API (not text), deterministic from
+    the seed.  Cell i owns a segment A_i B_i (4 vars), a circle C_i (3) and an arc R_i (6):
+      A_i is chained to A_{i-1} by Horizontal/VerticalDistance and anchored by Fixed every 8th cell;
+      B_i by Distance(A_i, B_i) and LinesAtAngle(line_{i-1}, line_i, theta_i) (anchor cells: Fixed B_i.y);
+      C_i by CircleRadius + LineTangentToCircle(line_i, C_i) + Fixed(cx); every cell with i % 8 == 4 instead
+          fixes its centre and gets its radius from CircleTangentToCircle(C_i, C_{i+1}, Exterior);
+      R_i by PointsCoincident(R_i.start, B_i), ArcRadius, ArcLength, Arc and Fixed(centre.x).
+    15-16 rows per 13 variables (consistent redundancy), one connected component.  `cells` must be a
+    multiple of 8.  Returns (records, n_vars, guesses, exact_solution)."""
+    from ezpz_b200 import native
+    assert cells % 8 == 0 and cells >= 8
+    K = cells
+    i = np.arange(K)
+    u = lambda k, lo, hi: lo + (uniform_pm(seed + (k << 40), K, 0.5) + 0.5) * (hi - lo)
+    Ls = u(1, 2.0, 5.0)
+    phi = np.deg2rad(u(2, 20.0, 70.0))
+    rho = u(3, 0.5, 1.5)
+    tpar = u(4, 0.2, 0.8)
+    rarc = u(5, 1.0, 3.0)
+    psi = np.deg2rad(u(6, 40.0, 140.0))
+    alpha = u(7, 0.2, 0.8) * np.pi
+    Ax, Ay = 6.0 * i, np.zeros(K)
+    Bx, By = Ax + Ls * np.cos(phi), Ay + Ls * np.sin(phi)
+    nx, ny = -np.sin(phi), np.cos(phi)  # left normal
+    cx = Ax + tpar * (Bx - Ax) + rho * nx
+    cy = Ay + tpar * (By - Ay) + rho * ny
+    cr = rho.copy()
+    special = (i % 8) == 4
+    cx[special], cy[special] = 6.0 * i[special] + 3.0, 12.0
+    nxt = (i + 1) % K
+    cr[special] = np.hypot(cx[special] - cx[nxt[special]], cy[special] - cy[nxt[special]]) - cr[nxt[special]]
+    sx, sy = Bx, By
+    ccx, ccy = sx - rarc * np.cos(psi), sy - rarc * np.sin(psi)
+    ex = ccx + np.cos(alpha) * (sx - ccx) - np.sin(alpha) * (sy - ccy)
+    ey = ccy + np.sin(alpha) * (sx - ccx) + np.cos(alpha) * (sy - ccy)
+    exact = np.stack([Ax, Ay, Bx, By, cx, cy, cr, sx, sy, ex, ey, ccx, ccy], axis=1).reshape(-1)
+    n_vars = 13 * K
+    b = 13 * i
+    anchor = (i % 8) == 0
+    theta = phi - np.roll(phi, 1)
+
+    def rec(kind, ids, p0=0.0, p1=0.0, flags=0):
+        count = len(ids[0]) if hasattr(ids[0], "__len__") else 1
+        r = np.zeros(count, dtype=native.REC_DTYPE)
+        r["kind"], r["flags"], r["p0"], r["p1"], r["weight"] = kind, flags, p0, p1, 1.0
+        for k, col in enumerate(ids):
+            r["ids"][:, k] = col
+        return r
+
+    per_cell = []  # list of (cell index array, records) to be merged in cell order, stable
+    sel = anchor
+    per_cell.append((i[sel], 0, rec(9, [b[sel]], Ax[sel])))
+    per_cell.append((i[sel], 1, rec(9, [b[sel] + 1], Ay[sel])))
+    sel = i > 0
+    prev = b[sel] - 13
+    per_cell.append((i[sel], 2, rec(5, [prev, prev + 1, b[sel], b[sel] + 1], -6.0)))
+    per_cell.append((i[sel], 3, rec(4, [prev, prev + 1, b[sel], b[sel] + 1], 0.0)))
+    per_cell.append((i, 4, rec(2, [b, b + 1, b + 2, b + 3], Ls)))
+    sel = anchor
+    per_cell.append((i[sel], 5, rec(9, [b[sel] + 3], By[sel])))
+    sel = ~anchor
+    prev = b[sel] - 13
+    per_cell.append((i[sel], 5, rec(8, [prev, prev + 1, prev + 2, prev + 3, b[sel], b[sel] + 1, b[sel] + 2, b[sel] + 3],
+                                    np.cos(theta[sel]), np.sin(theta[sel]), 2)))
+    sel = ~special
+    per_cell.append((i[sel], 6, rec(12, [b[sel] + 4, b[sel] + 5, b[sel] + 6], rho[sel])))
+    per_cell.append((i[sel], 7, rec(0, [b[sel], b[sel] + 1, b[sel] + 2, b[sel] + 3, b[sel] + 4, b[sel] + 5, b[sel] + 6])))
+    per_cell.append((i[sel], 8, rec(9, [b[sel] + 4], cx[sel])))
+    sel = special
+    nb = 13 * nxt[sel]
+    per_cell.append((i[sel], 6, rec(9, [b[sel] + 4], cx[sel])))
+    per_cell.append((i[sel], 7, rec(9, [b[sel] + 5], cy[sel])))
+    per_cell.append((i[sel], 8, rec(1, [b[sel] + 4, b[sel] + 5, b[sel] + 6, nb + 4, nb + 5, nb + 6], flags=1)))
+    arc = [b + 7, b + 8, b + 9, b + 10, b + 11, b + 12]
+    per_cell.append((i, 9, rec(11, [b + 7, b + 8, b + 2, b + 3])))
+    per_cell.append((i, 10, rec(14, arc, rarc)))
+    per_cell.append((i, 11, rec(22, arc, alpha * rarc)))
+    per_cell.append((i, 12, rec(15, arc)))
+    per_cell.append((i, 13, rec(9, [b + 11], ccx)))
+    cell_idx = np.concatenate([c for c, _, _ in per_cell])
+    order_in_cell = np.concatenate([np.full(len(c), o) for c, o, _ in per_cell])
+    recs = np.concatenate([r for _, _, r in per_cell])
+    perm = np.lexsort((order_in_cell, cell_idx))
+    recs = np.ascontiguousarray(recs[perm])
+    guesses = exact + uniform_pm(seed + (99 << 40), n_vars, noise)
+    return recs, n_vars, guesses, exact
