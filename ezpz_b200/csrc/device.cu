@@ -21,6 +21,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -52,44 +53,62 @@ struct SmallArgs {
     double residual_tolerance, step_tolerance, initial_lambda;
     uint32_t max_iterations;
     uint32_t n_cons, n, m, W, X0, R0, RN0, J0, L0, D0, S0, n_ops, unsat_words, nnz;
+    uint32_t tape_words;     // length of the tape in 32-bit words
+    uint32_t stage_in_smem;  // 1: constraint records and tape are copied to shared memory by each CTA
+    uint32_t weights_one;    // 1: every weight is exactly 1.0 (r == unweighted residuals)
 };
 
-struct SmemX {
-    const double* p;
-    uint32_t stride;
-    __device__ __forceinline__ double operator()(uint32_t id) const { return p[id * stride]; }
-};
 struct GlobalX {
     const double* p;
     __device__ __forceinline__ double operator()(uint32_t id) const { return __ldg(p + id); }
 };
 
+// Per-thread view of the shared-memory state: column `threadIdx.x` of V[slot][thread].  Slots are addressed
+// by BYTE offsets that are uniform across the warp (slot * stride * 8), so an access is base + uniform.
+struct VView {
+    char* base;   // &V[0][threadIdx.x]
+    uint32_t sb;  // stride in bytes between consecutive slots (= blockDim.x * 8)
+    __device__ __forceinline__ double ld(uint32_t off) const { return *reinterpret_cast<const double*>(base + off); }
+    __device__ __forceinline__ void st(uint32_t off, double v) const { *reinterpret_cast<double*>(base + off) = v; }
+    __device__ __forceinline__ double lds(uint32_t slot) const { return ld(slot * sb); }
+    __device__ __forceinline__ void sts(uint32_t slot, double v) const { st(slot * sb, v); }
+};
+struct SmemX {
+    VView v;
+    uint32_t x0;  // byte offset of x[0]
+    __device__ __forceinline__ double operator()(uint32_t id) const { return v.ld(x0 + id * v.sb); }
+};
+
 // One pass over all constraints of this thread's problem.
 //   RES: write weight*residual to V[rdst + row] and count Warning::Degenerate of Model::residual
-//   JAC: write the Jacobian values and count Warning::Degenerate of Model::refresh_jacobian
+//   JAC: write the Jacobian values to V[jdst + slot]; degenerate rows are reported through jac_degen_any and
+//        counted by the caller only if the point is accepted (Model::refresh_jacobian runs only then)
 template <bool RES, bool JAC>
-__device__ __forceinline__ void eval_all(const SmallArgs& a, double* V, uint32_t stride, uint32_t rdst,
-                                         const double* __restrict__ prow, uint32_t* __restrict__ degen_row,
-                                         bool& any_degen) {
-    const SmemX X{V + a.X0 * stride, stride};
+__device__ __forceinline__ void eval_all(const SmallArgs& a, const DevCons* __restrict__ cons, const VView& V,
+                                         uint32_t rdst, uint32_t jdst, const double* __restrict__ prow,
+                                         uint32_t* __restrict__ degen_row, bool& res_degen_any, bool& jac_degen_any) {
+    const SmemX X{V, a.X0 * V.sb};
+#pragma unroll 1
     for (uint32_t c = 0; c < a.n_cons; ++c) {
-        const DevCons& dc = a.cons[c];
+        const DevCons& dc = cons[c];
         const uint32_t kind = dc.kind;
         uint32_t side = dc.flags;
-        if (dc.side_slot != 0xffffffffu) side = (uint32_t)V[(a.S0 + dc.side_slot) * stride];
+        if (dc.side_slot != 0xffffffffu) side = (uint32_t)V.lds(a.S0 + dc.side_slot);
         const double p0 = prow ? prow[c] : dc.p0;
         ezd::EvalOut o;
         ezd::eval_constraint<JAC>(kind, side, dc.ids, p0, dc.p1, X, o);
         const double w = dc.weight;
         const uint32_t rows = c_rows[kind];
-        uint32_t ndeg = 0;
         if (RES) {
-            V[(rdst + dc.row0) * stride] = w * o.res[0];
-            if (rows == 2) V[(rdst + dc.row0 + 1) * stride] = w * o.res[1];
-            if (o.res_degen) ++ndeg;
+            V.sts(rdst + dc.row0, w * o.res[0]);
+            if (rows == 2) V.sts(rdst + dc.row0 + 1, w * o.res[1]);
+            if (o.res_degen) {
+                res_degen_any = true;
+                if (degen_row) degen_row[c] += 1;
+            }
         }
         if (JAC) {
-            if (o.jac_degen) ++ndeg;
+            if (o.jac_degen) jac_degen_any = true;
 #pragma unroll
             for (int row = 0; row < 2; ++row) {
                 if (row < (int)rows) {
@@ -98,126 +117,159 @@ __device__ __forceinline__ void eval_all(const SmallArgs& a, double* V, uint32_t
                     for (int k = 0; k < 8; ++k) {
                         if (k < (int)len) {
                             const uint32_t s = dc.slot[row][k];
-                            double* dst = V + (a.J0 + (s & ~kAccumulate)) * stride;
+                            const uint32_t off = (jdst + (s & ~kAccumulate)) * V.sb;
                             if (s & kAccumulate) {
-                                if (o.emit[row]) *dst = *dst + w * o.pd[row][k];
+                                if (o.emit[row]) V.st(off, V.ld(off) + w * o.pd[row][k]);
                             } else {
-                                *dst = o.emit[row] ? 0.0 + w * o.pd[row][k] : 0.0;
+                                V.st(off, o.emit[row] ? 0.0 + w * o.pd[row][k] : 0.0);
                             }
                         }
                     }
                 }
             }
         }
-        if (ndeg) {
-            any_degen = true;
-            if (degen_row) degen_row[c] += ndeg;
-        }
+    }
+}
+
+// Warning::Degenerate bookkeeping of Model::refresh_jacobian (solver.rs:385-391) for an accepted point: only
+// run when some constraint was degenerate there and the caller asked for per-constraint counts.
+__device__ __noinline__ void count_jacobian_degenerates(const SmallArgs& a, const DevCons* __restrict__ cons, VView V,
+                                                        const double* __restrict__ prow, uint32_t* __restrict__ degen_row) {
+    const SmemX X{V, a.X0 * V.sb};
+    for (uint32_t c = 0; c < a.n_cons; ++c) {
+        const DevCons& dc = cons[c];
+        uint32_t side = dc.flags;
+        if (dc.side_slot != 0xffffffffu) side = (uint32_t)V.lds(a.S0 + dc.side_slot);
+        ezd::EvalOut o;
+        ezd::eval_constraint<true>(dc.kind, side, dc.ids, prow ? prow[c] : dc.p0, dc.p1, X, o);
+        if (o.jac_degen) degen_row[c] += 1;
     }
 }
 
 // The linear-algebra tape of one LM iteration: A = JtJ + lambda*I, b = -Jt r, A = L Lt, L y = b, Lt d = y.
+// Device format (32-bit words): per op a 4-word header {dst byte offset, pair count, code, fin byte offset}
+// followed by one {a, b} byte-offset pair per multiply-add.  Offsets are uniform across the warp; when the
+// tape sits in the constant bank (kernel parameter) the decode runs on the uniform datapath and an operand
+// access is a single LDS [thread base + uniform offset].
 // Returns true when a pivot was not positive and finite ("LltError::Numeric", newton.rs:96-99).
-__device__ __forceinline__ bool run_tape(const uint32_t* __restrict__ tape, uint32_t n_ops, double* V,
-                                         uint32_t stride, double lambda) {
+__device__ __forceinline__ bool run_tape(const uint32_t* __restrict__ tape, uint32_t n_ops, const VView& V, double lambda) {
     bool fail = false;
-    const uint32_t* p = tape;
+    uint32_t w = 0;  // 32-bit word index: keeps the loop control out of 64-bit pointer arithmetic
+#pragma unroll 1
     for (uint32_t op = 0; op < n_ops; ++op) {
-        const uint32_t h0 = __ldg(p), h1 = __ldg(p + 1);
-        p += 2;
-        const uint32_t dst = h0 & 0xffffu, np = h0 >> 16;
-        const uint32_t fin = h1 & 0xffffu, code = h1 >> 16;
-        double acc = (code & OP_INIT_DST) ? V[dst * stride] : 0.0;
+        const uint32_t dst = tape[w], np = tape[w + 1], code = tape[w + 2], fin = tape[w + 3];
+        w += 4;
+        double acc = (code & OP_INIT_DST) ? V.ld(dst) : 0.0;
+        const uint32_t we = w + 2 * np;
         if (code & OP_NEGATE) {
-            for (uint32_t i = 0; i < np; ++i) {
-                const uint32_t w = __ldg(p + i);
-                acc = __fma_rn(-V[(w & 0xffffu) * stride], V[(w >> 16) * stride], acc);
-            }
+#pragma unroll 1
+            for (; w < we; w += 2) acc = __fma_rn(-V.ld(tape[w]), V.ld(tape[w + 1]), acc);
         } else {
-            for (uint32_t i = 0; i < np; ++i) {
-                const uint32_t w = __ldg(p + i);
-                acc = __fma_rn(V[(w & 0xffffu) * stride], V[(w >> 16) * stride], acc);
-            }
+#pragma unroll 1
+            for (; w < we; w += 2) acc = __fma_rn(V.ld(tape[w]), V.ld(tape[w + 1]), acc);
         }
-        p += np;
         const uint32_t fk = (code >> OP_FIN_SHIFT) & 3u;
-        if (fk == OP_FIN_LAMBDA) {
+        if (fk == OP_FIN_MUL) {
+            acc = __dmul_rn(acc, V.ld(fin));
+        } else if (fk == OP_FIN_LAMBDA) {
             acc = __dadd_rn(acc, lambda);
-        } else if (fk == OP_FIN_MUL) {
-            acc = __dmul_rn(acc, V[fin * stride]);
         } else if (fk == OP_FIN_PIVOT) {
             if (!(acc > 0.0) || !ezm::ez_isfinite(acc)) fail = true;
             acc = __ddiv_rn(1.0, __dsqrt_rn(acc));
         }
-        V[dst * stride] = acc;
+        V.st(dst, acc);
     }
     return fail;
 }
 
-__global__ void __launch_bounds__(256) lm_small_kernel(const SmallArgs a) {
-    extern __shared__ double smem[];
-    const uint32_t stride = blockDim.x;
-    const uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= a.batch) return;  // no block-wide barrier below: every thread owns its shared-memory column
-    double* V = smem + threadIdx.x;
+// The whole solve of one problem by one thread: newton.rs:29-145 + lib.rs:305-327.
+__device__ __forceinline__ void lm_small_body(const SmallArgs& a, const DevCons* __restrict__ cons,
+                                              const uint32_t* __restrict__ tape, const VView V, uint64_t b) {
     const double* __restrict__ prow = a.params ? a.params + b * a.n_cons : nullptr;
     uint32_t* __restrict__ degen_row = a.degen ? a.degen + b * a.n_cons : nullptr;
     bool any_degen = false;
+    const uint32_t sb = V.sb;
+    const uint32_t oX = a.X0 * sb, oR = a.R0 * sb, oRN = a.RN0 * sb, oJ = a.J0 * sb, oL = a.L0 * sb, oD = a.D0 * sb;
 
     {  // initial guesses (lib.rs:275: values are positional == by id)
         const double* __restrict__ g = a.guesses + b * a.n;
-        for (uint32_t j = 0; j < a.n; ++j) V[(a.X0 + j) * stride] = g[j];
+        for (uint32_t j = 0; j < a.n; ++j) V.st(oX + j * sb, g[j]);
     }
     if (degen_row)
         for (uint32_t c = 0; c < a.n_cons; ++c) degen_row[c] = 0;
     {  // Constraint::set_from_initial_values (lib.rs:183-186)
-        const SmemX X{V + a.X0 * stride, stride};
+        const SmemX X{V, oX};
         for (uint32_t c = 0; c < a.n_cons; ++c) {
-            const DevCons& dc = a.cons[c];
+            const DevCons& dc = cons[c];
             if (dc.side_slot != 0xffffffffu)
-                V[(a.S0 + dc.side_slot) * stride] = (double)ezd::resolve_side(dc.kind, dc.flags, dc.ids, X);
+                V.sts(a.S0 + dc.side_slot, (double)ezd::resolve_side(dc.kind, dc.flags, dc.ids, X));
         }
     }
 
-    // newton.rs:29-145
     double lambda = a.initial_lambda;
-    eval_all<true, true>(a, V, stride, a.R0, prow, degen_row, any_degen);
+    {
+        bool rd = false, jd = false;
+        eval_all<true, true>(a, cons, V, a.R0, a.J0, prow, degen_row, rd, jd);
+        if (jd && degen_row) count_jacobian_degenerates(a, cons, V, prow, degen_row);
+        any_degen = rd || jd;
+    }
     double S = 0.0;
     for (uint32_t i = 0; i < a.m; ++i) {
-        const double r = V[(a.R0 + i) * stride];
+        const double r = V.ld(oR + i * sb);
         S = S + r * r;
     }
     uint32_t iterations = a.max_iterations;
     bool converged = false;
+    bool x_dirty = false;  // x was last modified by a rejected step: r no longer belongs to the bits of x
+#pragma unroll 1
     for (uint32_t it = 0; it < a.max_iterations; ++it) {
-        double largest = ezm::ez_abs(V[a.R0 * stride]);
-        for (uint32_t i = 1; i < a.m; ++i) largest = ezm::ez_fmax(largest, ezm::ez_abs(V[(a.R0 + i) * stride]));
+        // max |r_i| with libm::fmax semantics (NaN-ignoring): NaN < x is false, so a NaN candidate never wins
+        // and a NaN incumbent is replaced by any number.
+        double largest = ezm::ez_abs(V.ld(oR));
+        for (uint32_t i = 1; i < a.m; ++i) {
+            const double v = ezm::ez_abs(V.ld(oR + i * sb));
+            largest = (largest < v || largest != largest) ? v : largest;
+        }
         if (largest <= a.residual_tolerance) {
             iterations = it;
             converged = true;
             break;
         }
-        if (run_tape(a.tape, a.n_ops, V, stride, lambda)) {
+        if (run_tape(tape, a.n_ops, V, lambda)) {
             lambda *= 10.0;
             continue;
         }
-        double step = ezm::ez_abs(V[a.D0 * stride]);
-        for (uint32_t j = 1; j < a.n; ++j) step = ezm::ez_fmax(step, ezm::ez_abs(V[(a.D0 + j) * stride]));
-        for (uint32_t j = 0; j < a.n; ++j) V[(a.X0 + j) * stride] += V[(a.D0 + j) * stride];
-        eval_all<true, false>(a, V, stride, a.RN0, prow, degen_row, any_degen);
+        double step = ezm::ez_abs(V.ld(oD));
+        for (uint32_t j = 1; j < a.n; ++j) {
+            const double v = ezm::ez_abs(V.ld(oD + j * sb));
+            step = (step < v || step != step) ? v : step;
+        }
+        for (uint32_t j = 0; j < a.n; ++j) V.st(oX + j * sb, V.ld(oX + j * sb) + V.ld(oD + j * sb));
+        // One fused pass at the trial point: residuals into r_next and, speculatively, the Jacobian into the
+        // (now dead) A/L region; an accepted step copies both over, a rejected one leaves r and J untouched,
+        // exactly as Model::residual + refresh_jacobian do (newton.rs:115-131).
+        bool rd = false, jd = false;
+        eval_all<true, true>(a, cons, V, a.RN0, a.L0, prow, degen_row, rd, jd);
+        any_degen = any_degen || rd;
         double S2 = 0.0;
         for (uint32_t i = 0; i < a.m; ++i) {
-            const double r = V[(a.RN0 + i) * stride];
+            const double r = V.ld(oRN + i * sb);
             S2 = S2 + r * r;
         }
         if (S2 < S) {
-            for (uint32_t i = 0; i < a.m; ++i) V[(a.R0 + i) * stride] = V[(a.RN0 + i) * stride];
-            eval_all<false, true>(a, V, stride, a.R0, prow, degen_row, any_degen);
+            for (uint32_t i = 0; i < a.m; ++i) V.st(oR + i * sb, V.ld(oRN + i * sb));
+            for (uint32_t k = 0; k < a.nnz; ++k) V.st(oJ + k * sb, V.ld(oL + k * sb));
+            if (jd) {
+                any_degen = true;
+                if (degen_row) count_jacobian_degenerates(a, cons, V, prow, degen_row);
+            }
             S = S2;
             lambda *= 0.1;
+            x_dirty = false;
         } else {
-            for (uint32_t j = 0; j < a.n; ++j) V[(a.X0 + j) * stride] -= V[(a.D0 + j) * stride];
+            for (uint32_t j = 0; j < a.n; ++j) V.st(oX + j * sb, V.ld(oX + j * sb) - V.ld(oD + j * sb));
             lambda *= 10.0;
+            x_dirty = true;
         }
         if (step <= a.step_tolerance) {
             iterations = it;
@@ -226,21 +278,30 @@ __global__ void __launch_bounds__(256) lm_small_kernel(const SmallArgs a) {
         }
     }
 
-    // lib.rs:305-327: unweighted residuals at the final point, |r| < 1e-4 per component
+    // lib.rs:305-327: unweighted residuals at the final point, |r| < 1e-4 per component.  When every weight
+    // is 1.0 and x still holds the bits r was evaluated at, r IS that residual vector and is reused.
     bool any_unsat = false;
     {
-        const SmemX X{V + a.X0 * stride, stride};
+        const bool reuse = a.weights_one && !x_dirty;
+        const SmemX X{V, oX};
         uint32_t* __restrict__ urow = a.unsat ? a.unsat + b * a.unsat_words : nullptr;
         uint32_t word = 0;
         for (uint32_t c = 0; c < a.n_cons; ++c) {
-            const DevCons& dc = a.cons[c];
-            uint32_t side = dc.flags;
-            if (dc.side_slot != 0xffffffffu) side = (uint32_t)V[(a.S0 + dc.side_slot) * stride];
-            const double p0 = prow ? prow[c] : dc.p0;
-            ezd::EvalOut o;
-            ezd::eval_constraint<false>(dc.kind, side, dc.ids, p0, dc.p1, X, o);
-            bool sat = ezm::ez_abs(o.res[0]) < ezd::kEps;
-            if (c_rows[dc.kind] == 2) sat = sat && (ezm::ez_abs(o.res[1]) < ezd::kEps);
+            const DevCons& dc = cons[c];
+            double r0, r1;
+            if (reuse) {
+                r0 = V.ld(oR + dc.row0 * sb);
+                r1 = (c_rows[dc.kind] == 2) ? V.ld(oR + (dc.row0 + 1) * sb) : 0.0;
+            } else {
+                uint32_t side = dc.flags;
+                if (dc.side_slot != 0xffffffffu) side = (uint32_t)V.lds(a.S0 + dc.side_slot);
+                const double p0 = prow ? prow[c] : dc.p0;
+                ezd::EvalOut o;
+                ezd::eval_constraint<false>(dc.kind, side, dc.ids, p0, dc.p1, X, o);
+                r0 = o.res[0];
+                r1 = (c_rows[dc.kind] == 2) ? o.res[1] : 0.0;
+            }
+            const bool sat = (ezm::ez_abs(r0) < ezd::kEps) && (ezm::ez_abs(r1) < ezd::kEps);
             if (!sat) {
                 any_unsat = true;
                 word |= 1u << (c & 31u);
@@ -253,15 +314,58 @@ __global__ void __launch_bounds__(256) lm_small_kernel(const SmallArgs a) {
     }
     {
         double* __restrict__ f = a.finals + b * a.n;
-        for (uint32_t j = 0; j < a.n; ++j) f[j] = V[(a.X0 + j) * stride];
+        for (uint32_t j = 0; j < a.n; ++j) f[j] = V.ld(oX + j * sb);
     }
     if (a.jac) {  // Jacobian cached at the last accepted point (what freedom_analysis reads)
         double* __restrict__ jo = a.jac + b * a.nnz;
-        for (uint32_t k = 0; k < a.nnz; ++k) jo[k] = V[(a.J0 + k) * stride];
+        for (uint32_t k = 0; k < a.nnz; ++k) jo[k] = V.ld(oJ + k * sb);
     }
     a.iterations[b] = iterations;
     a.status[b] = (uint8_t)((converged ? EZPZ_ST_CONVERGED : 0u) | (any_unsat ? EZPZ_ST_UNSATISFIED : 0u) |
                             (any_degen ? EZPZ_ST_DEGENERATE : 0u));
+}
+
+// Variant 1: constraint records and tape travel in the kernel parameter (constant bank).  NW 32-bit words.
+template <int NW>
+struct ConstBlob {
+    alignas(8) uint32_t w[NW];
+};
+template <int NW>
+__global__ void __launch_bounds__(256) lm_small_kernel_const(const __grid_constant__ SmallArgs a,
+                                                             const __grid_constant__ ConstBlob<NW> blob) {
+    extern __shared__ double smem[];
+    const uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= a.batch) return;  // no block-wide barrier: every thread owns its shared-memory column
+    const DevCons* cons = reinterpret_cast<const DevCons*>(blob.w);
+    const uint32_t* tape = blob.w + a.n_cons * (uint32_t)(sizeof(DevCons) / 4);
+    const VView V{reinterpret_cast<char*>(smem + threadIdx.x), blockDim.x * 8u};
+    lm_small_body(a, cons, tape, V, b);
+}
+
+// Variant 2 (tables too large for the parameter space): staged in shared memory behind the per-problem
+// state when they fit (STAGED), else read from global memory through L1.
+template <bool STAGED>
+__global__ void __launch_bounds__(256) lm_small_kernel(const SmallArgs a) {
+    extern __shared__ double smem[];
+    const uint32_t stride = blockDim.x;
+    const DevCons* cons = a.cons;
+    const uint32_t* tape = a.tape;
+    if (STAGED) {
+        double* tail = smem + (size_t)a.W * stride;
+        uint32_t* s_cons = reinterpret_cast<uint32_t*>(tail);
+        const uint32_t cons_words = a.n_cons * (uint32_t)(sizeof(DevCons) / 4);
+        uint32_t* s_tape = s_cons + cons_words;
+        const uint32_t* g_cons = reinterpret_cast<const uint32_t*>(a.cons);
+        for (uint32_t i = threadIdx.x; i < cons_words; i += blockDim.x) s_cons[i] = g_cons[i];
+        for (uint32_t i = threadIdx.x; i < a.tape_words; i += blockDim.x) s_tape[i] = a.tape[i];
+        __syncthreads();
+        cons = reinterpret_cast<const DevCons*>(s_cons);
+        tape = s_tape;
+    }
+    const uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= a.batch) return;
+    const VView V{reinterpret_cast<char*>(smem + threadIdx.x), stride * 8u};
+    lm_small_body(a, cons, tape, V, b);
 }
 
 // ---- assembly over one system in global memory ----------------------------------------------------
@@ -359,11 +463,6 @@ int32_t get_device_copy(ezpz_context* ctx, const ezpz_structure* cs, DeviceCopy*
         EZ_CUDA(cudaMalloc(&d->cons, sizeof(DevCons) * s->n_cons), "cudaMalloc(cons)");
         EZ_CUDA(cudaMemcpy(d->cons, s->dev_cons.data(), sizeof(DevCons) * s->n_cons, cudaMemcpyHostToDevice), "cudaMemcpy(cons)");
     }
-    if (s->small.valid && !s->small.tape.empty()) {
-        EZ_CUDA(cudaMalloc(&d->tape, sizeof(uint32_t) * s->small.tape.size()), "cudaMalloc(tape)");
-        EZ_CUDA(cudaMemcpy(d->tape, s->small.tape.data(), sizeof(uint32_t) * s->small.tape.size(), cudaMemcpyHostToDevice),
-                "cudaMemcpy(tape)");
-    }
     if (!s->csc_to_csr.empty()) {
         EZ_CUDA(cudaMalloc(&d->csc_to_csr, sizeof(uint32_t) * s->csc_to_csr.size()), "cudaMalloc(perm)");
         EZ_CUDA(cudaMemcpy(d->csc_to_csr, s->csc_to_csr.data(), sizeof(uint32_t) * s->csc_to_csr.size(), cudaMemcpyHostToDevice),
@@ -385,12 +484,54 @@ int32_t ensure_ws(ezpz_context* ctx, size_t bytes, ezpz_error_detail_t* detail) 
     return EZPZ_OK;
 }
 
+// The small-system tape in device format (see run_tape) for a given shared-memory stride: byte offsets
+// slot * stride * 8.  Built once per stride; kept on the host (for the kernel-parameter path) and on the device.
+int32_t get_scaled_tape(ezpz_context* ctx, const ezpz_structure* cs, DeviceCopy* d, uint32_t stride, ScaledTape** out,
+                        ezpz_error_detail_t* detail) {
+    ezpz_structure* s = const_cast<ezpz_structure*>(cs);
+    std::lock_guard<std::mutex> lock(s->dev_mutex);
+    for (ScaledTape* t : d->tapes)
+        if (t->stride == stride) {
+            *out = t;
+            return EZPZ_OK;
+        }
+    const std::vector<uint32_t>& src = s->small.tape;
+    ScaledTape* t = new (std::nothrow) ScaledTape();
+    if (!t) return EZPZ_ERR_INVALID_ARGUMENT;
+    t->stride = stride;
+    const uint32_t sb = stride * 8u;
+    size_t i = 0;
+    while (i < src.size()) {
+        const uint32_t h0 = src[i], h1 = src[i + 1];
+        const uint32_t np = h0 >> 16;
+        t->words.push_back((h0 & 0xffffu) * sb);
+        t->words.push_back(np);
+        t->words.push_back(h1 >> 16);
+        t->words.push_back((h1 & 0xffffu) * sb);
+        for (uint32_t k = 0; k < np; ++k) {
+            const uint32_t w = src[i + 2 + k];
+            t->words.push_back((w & 0xffffu) * sb);
+            t->words.push_back((w >> 16) * sb);
+        }
+        i += 2 + np;
+    }
+    EZ_CUDA(cudaSetDevice(ctx->device), "cudaSetDevice");
+    EZ_CUDA(cudaMalloc(&t->dev, sizeof(uint32_t) * std::max<size_t>(1, t->words.size())), "cudaMalloc(tape)");
+    EZ_CUDA(cudaMemcpy(t->dev, t->words.data(), sizeof(uint32_t) * t->words.size(), cudaMemcpyHostToDevice), "cudaMemcpy(tape)");
+    d->tapes.push_back(t);
+    *out = t;
+    return EZPZ_OK;
+}
+
 void release_device_copies(ezpz_structure* s) {
     std::lock_guard<std::mutex> lock(s->dev_mutex);
     for (DeviceCopy* d : s->dev) {
         if (cudaSetDevice(d->device) == cudaSuccess) {
             if (d->cons) cudaFree(d->cons);
-            if (d->tape) cudaFree(d->tape);
+            for (ScaledTape* t : d->tapes) {
+                if (t->dev) cudaFree(t->dev);
+                delete t;
+            }
             if (d->csc_to_csr) cudaFree(d->csc_to_csr);
             if (d->large) release_large(d);
         }
@@ -427,13 +568,27 @@ int32_t ezpz_b200_context_create(int32_t device, ezpz_context_t** out, ezpz_erro
         delete ctx;
         return cuda_fail(e, detail, "cudaStreamCreate");
     }
+    for (int k = 0; k < 3 && e == cudaSuccess; ++k) {
+        e = cudaStreamCreateWithFlags(&ctx->pipe[k], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->pipe_done[k], cudaEventDisableTiming);
+    }
+    if (e != cudaSuccess) {
+        delete ctx;
+        return cuda_fail(e, detail, "cudaStreamCreate(pipeline)");
+    }
     int32_t rc = upload_tables(detail);
     if (rc != EZPZ_OK) {
         cudaStreamDestroy(ctx->stream);
         delete ctx;
         return rc;
     }
-    e = cudaFuncSetAttribute(lm_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
+    e = cudaFuncSetAttribute(lm_small_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(lm_small_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(lm_small_kernel_const<2040>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(lm_small_kernel_const<7680>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
     if (e != cudaSuccess) {
         cudaStreamDestroy(ctx->stream);
         delete ctx;
@@ -449,6 +604,10 @@ void ezpz_b200_context_destroy(ezpz_context_t* ctx) {
     if (ctx->stream) {
         cudaStreamSynchronize(ctx->stream);
         cudaStreamDestroy(ctx->stream);
+    }
+    for (int k = 0; k < 3; ++k) {
+        if (ctx->pipe[k]) cudaStreamDestroy(ctx->pipe[k]);
+        if (ctx->pipe_done[k]) cudaEventDestroy(ctx->pipe_done[k]);
     }
     if (ctx->ws) cudaFree(ctx->ws);
     delete ctx;
@@ -485,7 +644,7 @@ int32_t ezpz_b200_solve_batch_device(ezpz_context_t* ctx, const ezpz_structure_t
     const SmallProgram& P = s->small;
     SmallArgs a;
     a.cons = dc->cons;
-    a.tape = dc->tape;
+    a.tape = nullptr;
     a.guesses = io->guesses;
     a.params = io->params;
     a.finals = io->final_values;
@@ -513,17 +672,59 @@ int32_t ezpz_b200_solve_batch_device(ezpz_context_t* ctx, const ezpz_structure_t
     a.S0 = P.S0;
     a.n_ops = P.n_ops;
     a.unsat_words = (s->n_cons + 31) / 32;
-    // threads per block: as many problems as fit the shared memory of one SM, in whole warps, at most 256
+    // Threads per block: as many problems as fit the shared memory of one SM, in whole warps, at most 256.
+    // The constraint records and the tape go, in order of preference, into the kernel parameter (constant
+    // bank), into shared memory behind the per-problem state, or stay in global memory.
     const size_t per_thread = (size_t)P.W * sizeof(double);
-    uint32_t T = (uint32_t)std::min<size_t>(256, ctx->smem_optin / per_thread);
+    const size_t cons_bytes = (size_t)s->n_cons * sizeof(DevCons);
+    size_t tape_words_v3 = 0;
+    {
+        const std::vector<uint32_t>& src = P.tape;
+        for (size_t i = 0; i < src.size(); i += 2 + (src[i] >> 16)) tape_words_v3 += 4 + 2 * (size_t)(src[i] >> 16);
+    }
+    const size_t tables = cons_bytes + tape_words_v3 * sizeof(uint32_t);
+    constexpr int kBlobSmall = 2040, kBlobLarge = 7680;  // words: 8,160 B and 30,720 B of the 32,764 B parameter space
+    // Measured on B200 (profiles/r01d): the shared-memory copy is faster than the constant bank here (indexed
+    // LDC has a longer dependent latency than a broadcast LDS and the per-thread loop exits keep the decode off
+    // the uniform datapath), so shared memory is preferred and the parameter path is the fallback.
+    const bool stage = tables <= 64 * 1024 && per_thread * 32 + tables <= ctx->smem_optin &&
+                       (ctx->smem_optin - tables) / per_thread >= 64;
+    const bool in_param = !stage && tables <= (size_t)kBlobLarge * 4;
+    const size_t avail = ctx->smem_optin - (stage ? tables : 0);
+    uint32_t T = (uint32_t)std::min<size_t>(256, avail / per_thread);
     T = T / 32 * 32;
     if (T < 32) return EZPZ_ERR_TOO_LARGE;
     if (batch < T) T = (uint32_t)((batch + 31) / 32 * 32);
-    const size_t smem = per_thread * T;
+    const size_t smem = per_thread * T + (stage ? tables : 0);
     const uint64_t grid = (batch + T - 1) / T;
     if (grid > 0x7fffffffull) return EZPZ_ERR_TOO_LARGE;
+    ScaledTape* tape = nullptr;
+    rc = get_scaled_tape(ctx, s, dc, T, &tape, detail);
+    if (rc != EZPZ_OK) return rc;
+    a.tape = tape->dev;
+    a.tape_words = (uint32_t)tape->words.size();
+    a.stage_in_smem = stage ? 1u : 0u;
+    a.weights_one = s->all_weights_one ? 1u : 0u;
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
-    lm_small_kernel<<<(unsigned)grid, T, smem, st>>>(a);
+    if (in_param) {
+        auto fill = [&](uint32_t* w) {
+            std::memcpy(w, s->dev_cons.data(), cons_bytes);
+            std::memcpy(w + cons_bytes / 4, tape->words.data(), tape->words.size() * 4);
+        };
+        if (tables <= (size_t)kBlobSmall * 4) {
+            static thread_local ConstBlob<kBlobSmall> blob;
+            fill(blob.w);
+            lm_small_kernel_const<kBlobSmall><<<(unsigned)grid, T, smem, st>>>(a, blob);
+        } else {
+            static thread_local ConstBlob<kBlobLarge> blob;
+            fill(blob.w);
+            lm_small_kernel_const<kBlobLarge><<<(unsigned)grid, T, smem, st>>>(a, blob);
+        }
+    } else if (stage) {
+        lm_small_kernel<true><<<(unsigned)grid, T, smem, st>>>(a);
+    } else {
+        lm_small_kernel<false><<<(unsigned)grid, T, smem, st>>>(a);
+    }
     ctx->launches += 1;
     EZ_CUDA(cudaGetLastError(), "lm_small_kernel launch");
     return EZPZ_OK;
@@ -556,27 +757,39 @@ int32_t ezpz_b200_solve_batch(ezpz_context_t* ctx, const ezpz_structure_t* s, co
     uint32_t* d_un = io->unsat_mask ? (uint32_t*)w : nullptr; w += b_un;
     uint32_t* d_dg = io->degen_count ? (uint32_t*)w : nullptr; w += b_dg;
     double* d_jc = io->jacobian ? (double*)w : nullptr; w += b_jc;
-    cudaStream_t st = ctx->stream;
-    EZ_CUDA(cudaMemcpyAsync(d_g, io->guesses, batch * n * sizeof(double), cudaMemcpyHostToDevice, st), "H2D guesses");
-    if (d_p) EZ_CUDA(cudaMemcpyAsync(d_p, io->params, batch * nc * sizeof(double), cudaMemcpyHostToDevice, st), "H2D params");
-    ezpz_batch_io_t dio;
-    dio.guesses = d_g;
-    dio.params = d_p;
-    dio.final_values = d_f;
-    dio.iterations = d_it;
-    dio.status = d_st;
-    dio.unsat_mask = d_un;
-    dio.degen_count = d_dg;
-    dio.jacobian = d_jc;
-    rc = ezpz_b200_solve_batch_device(ctx, s, config, batch, &dio, st, detail);
-    if (rc != EZPZ_OK) return rc;
-    EZ_CUDA(cudaMemcpyAsync(io->final_values, d_f, batch * n * sizeof(double), cudaMemcpyDeviceToHost, st), "D2H finals");
-    EZ_CUDA(cudaMemcpyAsync(io->iterations, d_it, batch * sizeof(uint32_t), cudaMemcpyDeviceToHost, st), "D2H iterations");
-    EZ_CUDA(cudaMemcpyAsync(io->status, d_st, batch, cudaMemcpyDeviceToHost, st), "D2H status");
-    if (d_un) EZ_CUDA(cudaMemcpyAsync(io->unsat_mask, d_un, batch * uw * sizeof(uint32_t), cudaMemcpyDeviceToHost, st), "D2H unsat");
-    if (d_dg) EZ_CUDA(cudaMemcpyAsync(io->degen_count, d_dg, batch * nc * sizeof(uint32_t), cudaMemcpyDeviceToHost, st), "D2H degen");
-    if (d_jc) EZ_CUDA(cudaMemcpyAsync(io->jacobian, d_jc, batch * nnz * sizeof(double), cudaMemcpyDeviceToHost, st), "D2H jacobian");
-    EZ_CUDA(cudaStreamSynchronize(st), "cudaStreamSynchronize");
+    // Copy/compute pipeline: the batch is cut into chunks that rotate over three streams, so the H2D copy of
+    // chunk k+1, the kernel of chunk k and the D2H copy of chunk k-1 overlap (with pinned host buffers the
+    // copies are true DMA on the two copy engines; pageable buffers still work, just without the overlap).
+    uint64_t n_chunks = std::min<uint64_t>(16, std::max<uint64_t>(1, batch / 16384));
+    if (const char* env = std::getenv("EZPZ_B200_CHUNKS")) n_chunks = std::max<uint64_t>(1, std::strtoull(env, nullptr, 10));
+    const uint64_t chunk = (batch + n_chunks - 1) / n_chunks;
+    EZ_CUDA(cudaStreamSynchronize(ctx->stream), "cudaStreamSynchronize");
+    for (uint64_t c = 0; c < n_chunks; ++c) {
+        const uint64_t b0 = c * chunk;
+        if (b0 >= batch) break;
+        const uint64_t cnt = std::min(chunk, batch - b0);
+        cudaStream_t st = ctx->pipe[c % 3];
+        EZ_CUDA(cudaMemcpyAsync(d_g + b0 * n, io->guesses + b0 * n, cnt * n * sizeof(double), cudaMemcpyHostToDevice, st), "H2D guesses");
+        if (d_p) EZ_CUDA(cudaMemcpyAsync(d_p + b0 * nc, io->params + b0 * nc, cnt * nc * sizeof(double), cudaMemcpyHostToDevice, st), "H2D params");
+        ezpz_batch_io_t dio;
+        dio.guesses = d_g + b0 * n;
+        dio.params = d_p ? d_p + b0 * nc : nullptr;
+        dio.final_values = d_f + b0 * n;
+        dio.iterations = d_it + b0;
+        dio.status = d_st + b0;
+        dio.unsat_mask = d_un ? d_un + b0 * uw : nullptr;
+        dio.degen_count = d_dg ? d_dg + b0 * nc : nullptr;
+        dio.jacobian = d_jc ? d_jc + b0 * nnz : nullptr;
+        rc = ezpz_b200_solve_batch_device(ctx, s, config, cnt, &dio, st, detail);
+        if (rc != EZPZ_OK) return rc;
+        EZ_CUDA(cudaMemcpyAsync(io->final_values + b0 * n, d_f + b0 * n, cnt * n * sizeof(double), cudaMemcpyDeviceToHost, st), "D2H finals");
+        EZ_CUDA(cudaMemcpyAsync(io->iterations + b0, d_it + b0, cnt * sizeof(uint32_t), cudaMemcpyDeviceToHost, st), "D2H iterations");
+        EZ_CUDA(cudaMemcpyAsync(io->status + b0, d_st + b0, cnt, cudaMemcpyDeviceToHost, st), "D2H status");
+        if (d_un) EZ_CUDA(cudaMemcpyAsync(io->unsat_mask + b0 * uw, d_un + b0 * uw, cnt * uw * sizeof(uint32_t), cudaMemcpyDeviceToHost, st), "D2H unsat");
+        if (d_dg) EZ_CUDA(cudaMemcpyAsync(io->degen_count + b0 * nc, d_dg + b0 * nc, cnt * nc * sizeof(uint32_t), cudaMemcpyDeviceToHost, st), "D2H degen");
+        if (d_jc) EZ_CUDA(cudaMemcpyAsync(io->jacobian + b0 * nnz, d_jc + b0 * nnz, cnt * nnz * sizeof(double), cudaMemcpyDeviceToHost, st), "D2H jacobian");
+    }
+    for (int k = 0; k < 3; ++k) EZ_CUDA(cudaStreamSynchronize(ctx->pipe[k]), "cudaStreamSynchronize");
     return EZPZ_OK;
 }
 

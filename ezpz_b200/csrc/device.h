@@ -4,16 +4,25 @@
 
 #include <cstdint>
 #include <cstdio>
+#include <utility>
+#include <vector>
 
 #include "structure.h"
 
 namespace ezs {
 
+// The small-system op tape in device format for one shared-memory stride (threads per CTA).
+struct ScaledTape {
+    uint32_t stride = 0;
+    std::vector<uint32_t> words;  // host copy (kernel-parameter path)
+    uint32_t* dev = nullptr;      // device copy (shared-memory / global paths)
+};
+
 // Device-resident copy of an analysed structure (one per CUDA device, created lazily).
 struct DeviceCopy {
     int device = -1;
     DevCons* cons = nullptr;         // [n_cons]
-    uint32_t* tape = nullptr;        // small-system op tape
+    std::vector<ScaledTape*> tapes;  // one per stride used so far
     uint32_t* csc_to_csr = nullptr;  // [nnz] position in CSR order of each CSC entry
     void* large = nullptr;           // LargeDevice (large.cu), created on first use
 };
@@ -32,6 +41,8 @@ int32_t solve_large(ezpz_context* ctx, const ezpz_structure* s, const ezpz_confi
 struct ezpz_context {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t pipe[3] = {nullptr, nullptr, nullptr};  // copy/compute pipeline of the host-buffer batch call
+    cudaEvent_t pipe_done[3] = {nullptr, nullptr, nullptr};
     int sm_count = 0;
     size_t smem_optin = 0;
     uint64_t launches = 0;

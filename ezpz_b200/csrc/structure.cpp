@@ -142,14 +142,17 @@ void build_small_program(ezpz_structure& S) {
     const uint32_t n = S.n, m = S.m;
     const uint32_t nnz_j = (uint32_t)S.csc_row_idx.size();
     const uint32_t nnz_l = (uint32_t)S.l_row_idx.size();
-    const uint64_t W = (uint64_t)n + 2ull * m + nnz_j + nnz_l + n + S.n_side;
+    // The A/L region doubles as the buffer of the trial point's Jacobian (the factor is dead by the time the
+    // tentative step is evaluated), so it is sized for whichever is larger.
+    const uint32_t lt = std::max(nnz_l, nnz_j);
+    const uint64_t W = (uint64_t)n + 2ull * m + nnz_j + lt + n + S.n_side;
     if (W > kMaxSmallW || n == 0) return;
     P.X0 = 0;
     P.R0 = n;
     P.RN0 = P.R0 + m;
     P.J0 = P.RN0 + m;
     P.L0 = P.J0 + nnz_j;
-    P.D0 = P.L0 + nnz_l;
+    P.D0 = P.L0 + lt;
     P.S0 = P.D0 + n;
     P.n_side = S.n_side;
     P.W = (uint32_t)W;
@@ -506,6 +509,8 @@ int32_t ezpz_b200_structure_create(const ezpz_constraint_t* cons, uint32_t n_con
     // 3. analysed constraints with scatter slots
     S->dev_cons.resize(n_cons);
     S->n_side = 0;
+    S->all_weights_one = true;
+    for (uint32_t c = 0; c < n_cons; ++c) S->all_weights_one = S->all_weights_one && cons[c].weight == 1.0;
     for (uint32_t c = 0; c < n_cons; ++c) {
         const ezpz_constraint_t& src = cons[c];
         const ezk::KindInfo& ki = ezk::kKinds[src.kind];

@@ -81,6 +81,7 @@ struct ezpz_structure {
     uint32_t max_component = 0;  // vars in the largest component
     std::vector<ezs::DevCons> dev_cons;
     uint32_t n_side = 0;
+    bool all_weights_one = true;
     ezs::SmallProgram small;
     ezs::LargeProgram large;
     bool have_l_pattern = false;  // false when the symbolic factorisation was skipped (very large systems)
