@@ -36,6 +36,7 @@ namespace {
 
 __constant__ uint8_t cl_rows[EZPZ_K_COUNT];
 __constant__ uint8_t cl_emit_len[EZPZ_K_COUNT][2];
+__constant__ uint8_t cl_nids[EZPZ_K_COUNT];
 
 struct LargeCtrl {
     double lambda, S, S2, largest, step;
@@ -45,8 +46,8 @@ struct LargeCtrl {
 };
 
 struct LargeArgs {
-    const DevCons* cons;
-    const uint32_t* cons_order;
+    const uint32_t* recs;    // analysed constraints in PROCESSING order (see LargeRec below), word-transposed in
+                             // tiles of 32: word w of slot k at recs[(k / 32) * kRecWords * 32 + w * 32 + k % 32]
     const uint32_t *csr_row_ptr, *csr_col_idx, *csc_col_ptr, *csc_row_idx, *csc_to_csr;
     // direct path
     const uint32_t *level_ptr, *op_dst, *op_fin, *op_code, *op_ptr, *pair_a, *pair_b;
@@ -54,13 +55,14 @@ struct LargeArgs {
     double* jr;          // J values in CSR order (PCG path)
     double* cgv;         // PCG vectors: p, res, ap, dinv (n each), q (m)
     double* partials;    // 3 * gridDim.x
-    uint8_t* side;       // resolved side per constraint
+    uint8_t* side;       // resolved side per processing slot
     uint32_t* degen;     // per-constraint Warning::Degenerate counters
     uint32_t* unsat;     // bit mask
     LargeCtrl* ctrl;
     double residual_tolerance, step_tolerance, initial_lambda, cg_rtol;
     uint32_t max_iterations, cg_max_iters;
-    uint32_t n_cons, n, m, nnz, n_levels;
+    uint32_t n_cons, n_slots, n, m, nnz, n_levels;
+    uint32_t unit_weights;
     uint32_t X0, R0, RN0, J0, L0, D0;
     uint32_t direct;
 };
@@ -69,49 +71,100 @@ struct GX {
     const double* p;
     __device__ __forceinline__ double operator()(uint32_t id) const { return p[id]; }
 };
+// Variables already gathered into registers; "ids" are then the positions 0..7.
+struct RegX {
+    const double* v;
+    __device__ __forceinline__ double operator()(uint32_t pos) const { return v[pos]; }
+};
 
-// Assembly of all constraints by the calling thread set (grid-stride).  mode bit0: residuals into
-// vg[rdst + row]; bit1: Jacobian values; weighted unless `unweighted_check` (post-solve verdict).
+// LargeRec — one analysed constraint of the large path, 36 words.  Slots are laid out in PROCESSING order:
+// tiles of kTile consecutive input constraints, stably sorted by kind inside the tile, every kind group
+// padded to a multiple of 32 slots (kind 0xff = padding).  A warp therefore runs one kind (no divergence in
+// the per-kind switch) while the rows, Jacobian slots and variables a tile touches stay within a few hundred
+// KB, so partial-sector writes of neighbouring kinds merge in L2 before they reach HBM.  Only the words a
+// kind needs are fetched: word w of 32 consecutive slots is one 128-byte line.
+enum : uint32_t {
+    RW_KIND = 0,    // kind | flags << 8
+    RW_ROW0 = 1,    // first residual row
+    RW_ORIG = 2,    // index of the constraint in the caller's list (rare paths: degenerate counters, verdict bits)
+    RW_JR0 = 3,     // position of row0's first entry in the CSR-ordered copy of J
+    RW_JRC0 = 4,    // CSR position of each emitted partial of row 0, 4 bits each, relative to RW_JR0
+    RW_JRC1 = 5,    // ... of row 1
+    RW_IDS = 6,     // 8 variable ids
+    RW_P0 = 14, RW_P1 = 16, RW_WEIGHT = 18,  // doubles (lo, hi)
+    RW_SLOT = 20,   // 2 x 8 CSC scatter slots (bit 31: accumulate)
+    kRecWords = 36
+};
+constexpr uint32_t kPadKind = 0xffu;
+
+struct RecPtr {
+    const uint32_t* base;
+    __device__ __forceinline__ uint32_t w(uint32_t k) const { return __ldg(base + k * 32u); }
+    __device__ __forceinline__ double d(uint32_t k) const { return __hiloint2double((int)w(k + 1), (int)w(k)); }
+};
+__device__ __forceinline__ RecPtr rec_at(const uint32_t* __restrict__ recs, uint32_t k) {
+    return RecPtr{recs + (size_t)(k >> 5) * (kRecWords * 32u) + (k & 31u)};
+}
+__device__ __forceinline__ bool kind_has_p1(uint32_t kind) {
+    return kind == EZPZ_K_LINES_AT_ANGLE || kind == EZPZ_K_ARC_ANGLE || kind == EZPZ_K_POINTS_AT_ANGLE;
+}
+
+// Assembly of all constraints by the calling thread set (grid-stride), one thread per processing slot.
+//   RES: weighted residuals into vg[rdst + row];  JAC: Jacobian values into J (CSC order, through the
+//   precomputed scatter slots) and, when write_jr, into the CSR-ordered copy used by the row-wise SpMV (the
+//   entries of a constraint's rows are contiguous there, so that copy needs one base and 4-bit offsets).
 template <bool RES, bool JAC>
 __device__ void assemble_phase(const LargeArgs& a, uint32_t rdst, uint32_t tid, uint32_t nth, bool write_jr) {
-    const GX X{a.vg + a.X0};
-    for (uint32_t k = tid; k < a.n_cons; k += nth) {
-        const uint32_t c = a.cons_order[k];
-        const DevCons& dc = a.cons[c];
+    const double* __restrict__ x = a.vg + a.X0;
+    for (uint32_t k = tid; k < a.n_slots; k += nth) {
+        const RecPtr rec = rec_at(a.recs, k);
+        const uint32_t kind = rec.w(RW_KIND) & 0xffu;
+        if (kind == kPadKind) continue;
+        const uint32_t nids = cl_nids[kind];
+        // Gather the variables BEFORE the per-kind switch: the warp issues its gathers together.
+        double xv[8];
+#pragma unroll
+        for (uint32_t q = 0; q < 8; ++q) xv[q] = q < nids ? x[rec.w(RW_IDS + q)] : 0.0;
+        const double p0 = rec.d(RW_P0);
+        const double p1 = kind_has_p1(kind) ? rec.d(RW_P1) : 0.0;
+        const double w = a.unit_weights ? 1.0 : rec.d(RW_WEIGHT);
+        const uint32_t row0 = rec.w(RW_ROW0);
+        const uint32_t ident[8] = {0, 1, 2, 3, 4, 5, 6, 7};
+        const RegX XR{xv};
         ezd::EvalOut o;
-        ezd::eval_constraint<JAC>(dc.kind, a.side[c], dc.ids, dc.p0, dc.p1, X, o);
-        const double w = dc.weight;
-        const uint32_t rows = cl_rows[dc.kind];
+        ezd::eval_constraint<JAC>(kind, a.side[k], ident, p0, p1, XR, o);
+        const uint32_t rows = cl_rows[kind];
         uint32_t ndeg = 0;
         if (RES) {
-            a.vg[rdst + dc.row0] = w * o.res[0];
-            if (rows == 2) a.vg[rdst + dc.row0 + 1] = w * o.res[1];
+            a.vg[rdst + row0] = w * o.res[0];
+            if (rows == 2) a.vg[rdst + row0 + 1] = w * o.res[1];
             if (o.res_degen) ++ndeg;
         }
         if (JAC) {
             if (o.jac_degen) ++ndeg;
+            const uint32_t jr0 = write_jr ? rec.w(RW_JR0) : 0u;
 #pragma unroll
             for (int row = 0; row < 2; ++row) {
                 if (row < (int)rows) {
-                    const uint32_t len = cl_emit_len[dc.kind][row];
+                    const uint32_t len = cl_emit_len[kind][row];
+                    const uint32_t jrc = write_jr ? rec.w(RW_JRC0 + row) : 0u;
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
                         if (q < (int)len) {
-                            const uint32_t s = dc.slot[row][q];
-                            const uint32_t slot = s & ~kAccumulate;
-                            double* dst = a.vg + a.J0 + slot;
+                            const uint32_t s = rec.w(RW_SLOT + row * 8 + q);
+                            double* dst = a.vg + a.J0 + (s & ~kAccumulate);
                             double v;
                             if (s & kAccumulate) v = o.emit[row] ? *dst + w * o.pd[row][q] : *dst;
                             else v = o.emit[row] ? 0.0 + w * o.pd[row][q] : 0.0;
                             *dst = v;
-                            if (write_jr) a.jr[a.csc_to_csr[slot]] = v;
+                            if (write_jr) a.jr[jr0 + ((jrc >> (4 * q)) & 15u)] = v;
                         }
                     }
                 }
             }
         }
         if (ndeg) {
-            a.degen[c] += ndeg;
+            a.degen[rec.w(RW_ORIG)] += ndeg;
             a.ctrl->any_degen = 1;
         }
     }
@@ -203,11 +256,19 @@ __global__ void __launch_bounds__(kBlock) lm_large_kernel(const LargeArgs a) {
     // sides from the initial guesses (lib.rs:183-186), counters
     {
         const GX X{vg + a.X0};
-        for (uint32_t c = tid; c < a.n_cons; c += nth) {
-            const DevCons& dc = a.cons[c];
-            a.side[c] = (uint8_t)ezd::resolve_side(dc.kind, dc.flags, dc.ids, X);
-            a.degen[c] = 0;
+        for (uint32_t k = tid; k < a.n_slots; k += nth) {
+            const RecPtr rec = rec_at(a.recs, k);
+            const uint32_t kf = rec.w(RW_KIND), kind = kf & 0xffu;
+            uint32_t side = (kf >> 8) & 0xffu;
+            if (side == EZPZ_SIDE_UNDEFINED && (kind == EZPZ_K_LINE_TANGENT_TO_CIRCLE || kind == EZPZ_K_CIRCLE_TANGENT_TO_CIRCLE)) {
+                uint32_t ids[8];
+#pragma unroll
+                for (uint32_t q = 0; q < 8; ++q) ids[q] = rec.w(RW_IDS + q);
+                side = ezd::resolve_side(kind, side, ids, X);
+            }
+            a.side[k] = (uint8_t)side;
         }
+        for (uint32_t c = tid; c < a.n_cons; c += nth) a.degen[c] = 0;
         for (uint32_t w = tid; w < (a.n_cons + 31) / 32; w += nth) a.unsat[w] = 0;
         if (tid == 0) {
             ctrl->lambda = a.initial_lambda;
@@ -377,14 +438,23 @@ __global__ void __launch_bounds__(kBlock) lm_large_kernel(const LargeArgs a) {
     }
     // post-solve verdict (lib.rs:305-327): unweighted residuals, |r| < 1e-4 per component
     {
-        const GX X{vg + a.X0};
-        for (uint32_t c = tid; c < a.n_cons; c += nth) {
-            const DevCons& dc = a.cons[c];
+        const double* __restrict__ x = vg + a.X0;
+        for (uint32_t k = tid; k < a.n_slots; k += nth) {
+            const RecPtr rec = rec_at(a.recs, k);
+            const uint32_t kind = rec.w(RW_KIND) & 0xffu;
+            if (kind == kPadKind) continue;
+            const uint32_t nids = cl_nids[kind];
+            double xv[8];
+#pragma unroll
+            for (uint32_t q = 0; q < 8; ++q) xv[q] = q < nids ? x[rec.w(RW_IDS + q)] : 0.0;
+            const uint32_t ident[8] = {0, 1, 2, 3, 4, 5, 6, 7};
+            const RegX XR{xv};
             ezd::EvalOut o;
-            ezd::eval_constraint<false>(dc.kind, a.side[c], dc.ids, dc.p0, dc.p1, X, o);
+            ezd::eval_constraint<false>(kind, a.side[k], ident, rec.d(RW_P0), kind_has_p1(kind) ? rec.d(RW_P1) : 0.0, XR, o);
             bool sat = ezm::ez_abs(o.res[0]) < ezd::kEps;
-            if (cl_rows[dc.kind] == 2) sat = sat && (ezm::ez_abs(o.res[1]) < ezd::kEps);
+            if (cl_rows[kind] == 2) sat = sat && (ezm::ez_abs(o.res[1]) < ezd::kEps);
             if (!sat) {
+                const uint32_t c = rec.w(RW_ORIG);
                 atomicOr(&a.unsat[c >> 5], 1u << (c & 31u));
                 ctrl->any_unsat = 1;
             }
@@ -400,8 +470,8 @@ __global__ void __launch_bounds__(kBlock) lm_large_kernel(const LargeArgs a) {
 }
 
 // ---- stand-alone kernels for throughput measurement (same device code as the phases above) ------------
-__global__ void __launch_bounds__(256) assemble_large_kernel(const LargeArgs a) {
-    assemble_phase<true, true>(a, a.R0, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x, true);
+__global__ void __launch_bounds__(128, 5) assemble_large_kernel(const LargeArgs a, const bool write_jr) {
+    assemble_phase<true, true>(a, a.R0, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x, write_jr);
 }
 __global__ void __launch_bounds__(256) spmv_csr_kernel(const uint32_t* __restrict__ row_ptr, const uint32_t* __restrict__ col_idx,
                                                        const double* __restrict__ vals, const double* __restrict__ x,
@@ -414,7 +484,9 @@ __global__ void __launch_bounds__(256) spmv_csr_kernel(const uint32_t* __restric
 }
 
 struct LargeDevice {
-    uint32_t *cons_order = nullptr, *csr_row_ptr = nullptr, *csr_col_idx = nullptr, *csc_col_ptr = nullptr, *csc_row_idx = nullptr;
+    uint32_t* recs = nullptr;
+    uint32_t n_slots = 0;
+    uint32_t *csr_row_ptr = nullptr, *csr_col_idx = nullptr, *csc_col_ptr = nullptr, *csc_row_idx = nullptr;
     uint32_t *level_ptr = nullptr, *op_dst = nullptr, *op_fin = nullptr, *op_code = nullptr, *op_ptr = nullptr, *pair_a = nullptr, *pair_b = nullptr;
     double *vg = nullptr, *jr = nullptr, *cgv = nullptr, *partials = nullptr;
     uint8_t* side = nullptr;
@@ -449,7 +521,43 @@ int32_t get_large(ezpz_context* ctx, const ezpz_structure* s, DeviceCopy* dc, La
     LargeDevice* L = new (std::nothrow) LargeDevice();
     if (!L) return EZPZ_ERR_INVALID_ARGUMENT;
     dc->large = L;  // owned by the device copy from here on (released with it)
-    EZ_TRY(upload(&L->cons_order, P.cons_order, detail));
+    {
+        // LargeRec words, transposed in tiles of 32 processing slots
+        const uint32_t n_slots = (uint32_t)P.cons_order.size();
+        std::vector<uint32_t> t((size_t)((n_slots + 31) / 32) * kRecWords * 32, 0u);
+        for (uint32_t k = 0; k < n_slots; ++k) {
+            uint32_t* w = t.data() + (size_t)(k >> 5) * (kRecWords * 32) + (k & 31u);
+            auto put = [&](uint32_t word, uint32_t v) { w[word * 32] = v; };
+            const uint32_t c = P.cons_order[k];
+            if (c == UINT32_MAX) {
+                put(RW_KIND, kPadKind);
+                continue;
+            }
+            const DevCons& dc = s->dev_cons[c];
+            const ezk::KindInfo& ki = ezk::kKinds[dc.kind];
+            put(RW_KIND, dc.kind | ((dc.flags & 0xffu) << 8));
+            put(RW_ROW0, dc.row0);
+            put(RW_ORIG, c);
+            const uint32_t jr0 = s->csr_row_ptr[dc.row0];
+            put(RW_JR0, jr0);
+            for (int row = 0; row < ki.rows; ++row) {
+                uint32_t code = 0;
+                for (int q = 0; q < ki.emit_len[row]; ++q) {
+                    const uint32_t off = s->csc_to_csr[dc.slot[row][q] & ~kAccumulate] - jr0;  // < 16: two rows of <= 8
+                    code |= (off & 15u) << (4 * q);
+                    put(RW_SLOT + row * 8 + q, dc.slot[row][q]);
+                }
+                put(RW_JRC0 + row, code);
+            }
+            for (int q = 0; q < 8; ++q) put(RW_IDS + q, dc.ids[q]);
+            uint32_t dw[2];
+            std::memcpy(dw, &dc.p0, 8); put(RW_P0, dw[0]); put(RW_P0 + 1, dw[1]);
+            std::memcpy(dw, &dc.p1, 8); put(RW_P1, dw[0]); put(RW_P1 + 1, dw[1]);
+            std::memcpy(dw, &dc.weight, 8); put(RW_WEIGHT, dw[0]); put(RW_WEIGHT + 1, dw[1]);
+        }
+        EZ_TRY(upload(&L->recs, t, detail));
+        L->n_slots = n_slots;
+    }
     EZ_TRY(upload(&L->csr_row_ptr, s->csr_row_ptr, detail));
     EZ_TRY(upload(&L->csr_col_idx, s->csr_col_idx, detail));
     EZ_TRY(upload(&L->csc_col_ptr, s->csc_col_ptr, detail));
@@ -466,7 +574,7 @@ int32_t get_large(ezpz_context* ctx, const ezpz_structure* s, DeviceCopy* dc, La
     EZ_CUDA(cudaMemset(L->vg, 0, sizeof(double) * std::max<size_t>(1, P.VG)), "cudaMemset(vg)");
     EZ_CUDA(cudaMalloc(&L->jr, sizeof(double) * std::max<size_t>(1, nnz)), "cudaMalloc(jr)");
     EZ_CUDA(cudaMalloc(&L->cgv, sizeof(double) * (4 * (size_t)s->n + s->m + 1)), "cudaMalloc(cgv)");
-    EZ_CUDA(cudaMalloc(&L->side, std::max<size_t>(1, s->n_cons)), "cudaMalloc(side)");
+    EZ_CUDA(cudaMalloc(&L->side, std::max<size_t>(1, L->n_slots)), "cudaMalloc(side)");
     EZ_CUDA(cudaMalloc(&L->degen, sizeof(uint32_t) * std::max<size_t>(1, s->n_cons)), "cudaMalloc(degen)");
     EZ_CUDA(cudaMalloc(&L->unsat, sizeof(uint32_t) * ((s->n_cons + 31) / 32 + 1)), "cudaMalloc(unsat)");
     EZ_CUDA(cudaMalloc(&L->ctrl, sizeof(LargeCtrl)), "cudaMalloc(ctrl)");
@@ -477,14 +585,16 @@ int32_t get_large(ezpz_context* ctx, const ezpz_structure* s, DeviceCopy* dc, La
     if (per_sm < 1) per_sm = 1;
     L->grid = work <= 65536 ? 1 : ctx->sm_count * std::min(per_sm, 2);
     EZ_CUDA(cudaMalloc(&L->partials, sizeof(double) * 3 * (size_t)L->grid), "cudaMalloc(partials)");
-    uint8_t rows[EZPZ_K_COUNT], emit_len[EZPZ_K_COUNT][2];
+    uint8_t rows[EZPZ_K_COUNT], emit_len[EZPZ_K_COUNT][2], nids[EZPZ_K_COUNT];
     for (int k = 0; k < EZPZ_K_COUNT; ++k) {
+        nids[k] = ezk::kKinds[k].n_ids;
         rows[k] = ezk::kKinds[k].rows;
         emit_len[k][0] = ezk::kKinds[k].emit_len[0];
         emit_len[k][1] = ezk::kKinds[k].emit_len[1];
     }
     EZ_CUDA(cudaMemcpyToSymbol(cl_rows, rows, sizeof rows), "cudaMemcpyToSymbol");
     EZ_CUDA(cudaMemcpyToSymbol(cl_emit_len, emit_len, sizeof emit_len), "cudaMemcpyToSymbol");
+    EZ_CUDA(cudaMemcpyToSymbol(cl_nids, nids, sizeof nids), "cudaMemcpyToSymbol");
     *out = L;
     return EZPZ_OK;
 }
@@ -492,8 +602,9 @@ int32_t get_large(ezpz_context* ctx, const ezpz_structure* s, DeviceCopy* dc, La
 void fill_args(LargeArgs& a, const ezpz_structure* s, const DeviceCopy* dc, const LargeDevice* L, const ezpz_config_t* config) {
     const LargeProgram& P = s->large;
     std::memset(&a, 0, sizeof a);
-    a.cons = dc->cons;
-    a.cons_order = L->cons_order;
+    a.recs = L->recs;
+    a.n_slots = L->n_slots;
+    a.unit_weights = s->all_weights_one ? 1u : 0u;
     a.csr_row_ptr = L->csr_row_ptr;
     a.csr_col_idx = L->csr_col_idx;
     a.csc_col_ptr = L->csc_col_ptr;
@@ -541,7 +652,7 @@ namespace ezs {
 void release_large(DeviceCopy* d) {
     LargeDevice* L = (LargeDevice*)d->large;
     if (!L) return;
-    void* ptrs[] = {L->cons_order, L->csr_row_ptr, L->csr_col_idx, L->csc_col_ptr, L->csc_row_idx, L->level_ptr, L->op_dst,
+    void* ptrs[] = {L->recs, L->csr_row_ptr, L->csr_col_idx, L->csc_col_ptr, L->csc_row_idx, L->level_ptr, L->op_dst,
                     L->op_fin, L->op_code, L->op_ptr, L->pair_a, L->pair_b, L->vg, L->jr, L->cgv, L->partials, L->side,
                     L->degen, L->unsat, L->ctrl};
     for (void* p : ptrs)
@@ -594,7 +705,8 @@ int32_t solve_large(ezpz_context* ctx, const ezpz_structure* s, const ezpz_confi
 
 // Stand-alone launches of the assembly and SpMV kernels on a structure's large-system buffers, timed with
 // CUDA events: reps launches each, returns mean microseconds per launch and the algorithmic bytes moved
-// (SURVEY.md §8d formulas).  x must hold n doubles.  which: 0 assembly, 1 SpMV y = J p (CSR), 2 SpMV z = Jt q (CSC).
+// (SURVEY.md §8d formulas).  x must hold n doubles.  which: 0 assembly (J in CSC order, the direct path's), 1 SpMV
+// y = J p (CSR), 2 SpMV z = Jt q (CSC), 3 assembly writing both the CSC and the CSR-ordered copy (PCG path's).
 extern "C" int32_t ezpz_b200_large_bench(ezpz_context_t* ctx, const ezpz_structure_t* s, const double* x, int32_t which,
                                          int32_t reps, double* mean_us, double* algorithmic_bytes,
                                          ezpz_error_detail_t* detail) {
@@ -612,19 +724,20 @@ extern "C" int32_t ezpz_b200_large_bench(ezpz_context_t* ctx, const ezpz_structu
     fill_args(a, s, dc, L, &cfg);
     cudaStream_t st = ctx->stream;
     EZ_CUDA(cudaMemcpyAsync(L->vg + a.X0, x, sizeof(double) * s->n, cudaMemcpyHostToDevice, st), "H2D x");
-    EZ_CUDA(cudaMemsetAsync(L->side, 1, s->n_cons, st), "memset side");
+    EZ_CUDA(cudaMemsetAsync(L->side, 1, L->n_slots, st), "memset side");
     EZ_CUDA(cudaMemsetAsync(L->degen, 0, sizeof(uint32_t) * s->n_cons, st), "memset degen");
     const unsigned grid = (unsigned)ctx->sm_count * 8;
+    const unsigned grid_asm = (unsigned)std::min<size_t>(((size_t)L->n_slots + 127) / 128, (size_t)ctx->sm_count * 64);
     const double n = s->n, m = s->m, nnz = (double)s->csc_row_idx.size(), C = s->n_cons;
     cudaEvent_t e0, e1;
     EZ_CUDA(cudaEventCreate(&e0), "cudaEventCreate");
     EZ_CUDA(cudaEventCreate(&e1), "cudaEventCreate");
     // one untimed launch first (also fills jr for the SpMVs)
-    assemble_large_kernel<<<grid, 256, 0, st>>>(a);
+    assemble_large_kernel<<<grid_asm, 128, 0, st>>>(a, true);
     ctx->launches += 1;
     EZ_CUDA(cudaEventRecord(e0, st), "cudaEventRecord");
     for (int k = 0; k < reps; ++k) {
-        if (which == 0) assemble_large_kernel<<<grid, 256, 0, st>>>(a);
+        if (which == 0 || which == 3) assemble_large_kernel<<<grid_asm, 128, 0, st>>>(a, which == 3);
         else if (which == 1) spmv_csr_kernel<<<grid, 256, 0, st>>>(L->csr_row_ptr, L->csr_col_idx, L->jr, L->vg + a.X0, L->cgv + 4 * (size_t)s->n, s->m);
         else spmv_csr_kernel<<<grid, 256, 0, st>>>(L->csc_col_ptr, L->csc_row_idx, L->vg + a.J0, L->vg + a.R0, L->cgv, s->n);
         ctx->launches += 1;
@@ -638,7 +751,9 @@ extern "C" int32_t ezpz_b200_large_bench(ezpz_context_t* ctx, const ezpz_structu
     cudaEventDestroy(e1);
     *mean_us = (double)ms * 1e3 / reps;
     if (algorithmic_bytes) {
-        if (which == 0) *algorithmic_bytes = 136.0 * C + 8 * n + 8 * m + 2 * 8 * nnz + 4 * nnz;  // records + x + r + J (two orders) + csr slot map
+        // 64-byte records + x + r + J values + scatter slots (+ the CSR-ordered copy, which == 3)
+        if (which == 0) *algorithmic_bytes = 64.0 * C + 8 * n + 8 * m + 8 * nnz + 4 * nnz;
+        else if (which == 3) *algorithmic_bytes = 64.0 * C + 8 * n + 8 * m + 2 * 8 * nnz + 4 * nnz;
         else if (which == 1) *algorithmic_bytes = 12 * nnz + 4 * (m + 1) + 8 * n + 8 * m;
         else *algorithmic_bytes = 12 * nnz + 4 * (n + 1) + 8 * m + 8 * n;
     }

@@ -247,10 +247,29 @@ void build_large_program(ezpz_structure& S) {
     P = LargeProgram();
     const uint32_t n = S.n, m = S.m;
     const uint32_t nnz_j = (uint32_t)S.csc_row_idx.size();
-    P.cons_order.resize(S.n_cons);
-    std::iota(P.cons_order.begin(), P.cons_order.end(), 0u);
-    std::stable_sort(P.cons_order.begin(), P.cons_order.end(),
-                     [&](uint32_t a, uint32_t b) { return S.cons[a].kind < S.cons[b].kind; });
+    // Processing order of the assembly phase: tiles of kAssemblyTile consecutive input constraints, stably
+    // sorted by kind inside the tile, each kind group padded to whole warps (UINT32_MAX = idle slot).  Sorting
+    // the whole list by kind makes warps kind-uniform but scatters the row and slot writes (ncu on the
+    // 1M-variable sketch: 595 MB of DRAM traffic for 231 MB algorithmic); plain input order keeps locality
+    // but runs 6 of 32 lanes per instruction (every warp holds a dozen kinds).  Tiles give both.
+    {
+        constexpr uint32_t kAssemblyTile = 4096;
+        P.cons_order.clear();
+        P.cons_order.reserve((size_t)S.n_cons + S.n_cons / 8 + 32 * EZPZ_K_COUNT);
+        std::vector<uint32_t> tile;
+        for (uint32_t t0 = 0; t0 < S.n_cons; t0 += kAssemblyTile) {
+            const uint32_t t1 = std::min(S.n_cons, t0 + kAssemblyTile);
+            tile.resize(t1 - t0);
+            std::iota(tile.begin(), tile.end(), t0);
+            std::stable_sort(tile.begin(), tile.end(), [&](uint32_t a, uint32_t b) { return S.cons[a].kind < S.cons[b].kind; });
+            for (size_t q = 0; q < tile.size(); ++q) {
+                if (q > 0 && S.cons[tile[q]].kind != S.cons[tile[q - 1]].kind)
+                    while (P.cons_order.size() % 32) P.cons_order.push_back(UINT32_MAX);
+                P.cons_order.push_back(tile[q]);
+            }
+            while (P.cons_order.size() % 32) P.cons_order.push_back(UINT32_MAX);
+        }
+    }
     const uint32_t nnz_l = S.have_l_pattern ? (uint32_t)S.l_row_idx.size() : 0;
     P.X0 = 0;
     P.R0 = n;

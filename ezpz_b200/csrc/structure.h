@@ -47,7 +47,7 @@ struct SmallProgram {
     std::vector<uint32_t> tape;
 };
 
-// The single-large-system programme (large.cu): a kind-sorted constraint order for the assembly phase and,
+// The single-large-system programme (large.cu): the processing order of the assembly phase and,
 // when the dependency depth of the natural-order sparse Cholesky is small (e.g. block-diagonal systems),
 // the level-scheduled op list of the direct solve.  Slots index one global value array
 // VG = [x | r | r_next | J (CSC order) | A/L | d].
@@ -57,7 +57,8 @@ struct LargeProgram {
     uint32_t X0 = 0, R0 = 0, RN0 = 0, J0 = 0, L0 = 0, D0 = 0, VG = 0;
     uint32_t n_levels = 0, n_ops = 0;
     uint64_t n_pairs = 0;
-    std::vector<uint32_t> cons_order;                      // constraint indices sorted by kind
+    std::vector<uint32_t> cons_order;                      // processing slots of the assembly phase -> constraint
+                                                           // index (tile-local kind sort, UINT32_MAX = padding)
     std::vector<uint32_t> level_ptr;                       // n_levels + 1, ranges into the op arrays
     std::vector<uint32_t> op_dst, op_fin, op_code, op_ptr; // op_ptr: n_ops + 1, ranges into the pair arrays
     std::vector<uint32_t> pair_a, pair_b;
