@@ -503,6 +503,16 @@ class Structure:
                     l_col_ptr=self._arr(c, self.n + 1), l_row_idx=self._arr(d, self.nnz_l))
 
 
+    def ordering(self):
+        """How the large path solves the damped step: dict(path, elim_order, nested, n_levels, nnz_l, sum_chunk)."""
+        path, nested, nl, nnz, ch, po = C.c_int32(), C.c_int32(), C.c_uint32(), C.c_uint64(), C.c_uint32(), C.c_void_p()
+        native.lib().ezpz_b200_structure_ordering(self.handle, C.byref(path), C.byref(po), C.byref(nested), C.byref(nl),
+                                                  C.byref(nnz), C.byref(ch))
+        order = self._arr(po, self.n) if po.value else None
+        return dict(path=path.value, elim_order=order, nested=bool(nested.value), n_levels=nl.value, nnz_l=nnz.value,
+                    sum_chunk=ch.value)
+
+
 class BatchResult:
     pass
 
@@ -593,7 +603,8 @@ class Context:
             raise EzpzError(rc, det)
         res.iterations, res.status, res.path_used, res.lin_iters = int(it[0]), int(status[0]), int(path[0]), int(lin[0])
         res.converged = bool(res.status & 1)
-        res.unsatisfied = [c for c in range(st.n_cons) if res.unsat_mask[c >> 5] >> (c & 31) & 1]
+        bits = np.unpackbits(res.unsat_mask.view(np.uint8), bitorder="little")[:st.n_cons]
+        res.unsatisfied = np.flatnonzero(bits).tolist()
         return res
 
     def evaluate(self, st, x):

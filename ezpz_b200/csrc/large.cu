@@ -9,20 +9,27 @@
 //   * assembly      one thread per constraint, kind-sorted order so that warps are mostly kind-uniform;
 //                   residuals to r, partials through precomputed slots into J (CSC order) and a CSR-ordered
 //                   copy for the row-wise SpMV (Model::residual / refresh_jacobian, solver.rs:318-440);
-//   * step solve    (a) level-scheduled sparse Cholesky when the dependency depth of the natural-order
-//                   factorisation is small (block-diagonal systems such as massive_parallel_system): same
-//                   arithmetic-order spec as the small path, so results match the oracle bit for bit;
-//                   (b) otherwise Jacobi-preconditioned conjugate gradients on (JtJ + lambda I) d = -Jt r,
-//                   applied matrix-free as Jt (J p) + lambda p with two SpMVs per iteration;
-//   * sum r^2       a strictly sequential left fold, as Rust's `.map(|x| x * x).sum()` is (newton.rs:45,116):
-//                   the accept test `S' < S` is a floating-point tie-breaker, so the summation order is part
-//                   of the reference semantics.  One thread adds from shared-memory chunks that the whole CTA
-//                   stages; max|r| and max|d| are order-independent and are reduced in parallel.
+//   * step solve    (a) sparse Cholesky scheduled by elimination-tree level (sparse_direct.cpp: natural order
+//                   for shallow trees such as the block-diagonal massive_parallel_system, nested dissection
+//                   otherwise): one grid-wide phase per level for factor + forward substitution, one per level
+//                   for the backward substitution; the top of the tree (a few columns per level) is run by a
+//                   single CTA with __syncthreads instead of grid barriers.  Same arithmetic-order spec as the
+//                   small path applied to P A Pt, so results match the oracle (given the same order) bit for bit;
+//                   (b) when the factor would be too large, Jacobi-preconditioned conjugate gradients on
+//                   (JtJ + lambda I) d = -Jt r, applied matrix-free as Jt (J p) + lambda p (two SpMVs/iteration);
+//   * sum r^2       single-CTA systems: a strictly sequential left fold, as Rust's `.map(|x| x * x).sum()` is
+//                   (newton.rs:45,116) — the accept test `S' < S` is a floating-point tie-breaker, so the
+//                   summation order is part of the reference semantics.  Multi-CTA systems (more than 65,536
+//                   values): the same fold inside chunks of 1,024 rows, then a sequential fold of the chunk
+//                   sums (a 1M-row sequential chain would cost 5 ms per evaluation); the oracle reproduces
+//                   this with sum_chunk = 1024.  max|r| and max|d| are order-independent.
 // spmv_csr_kernel / assemble_large_kernel are also exported as stand-alone launches (ezpz_b200_large_bench)
 // so that their HBM throughput can be timed with CUDA events and profiled with ncu.
 #include <cooperative_groups.h>
 
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -43,27 +50,34 @@ struct LargeCtrl {
     double rz, bb;
     uint32_t iterations, converged, fail, done;
     uint32_t any_unsat, any_degen, lin_iters, pad;
+    // nanoseconds per phase, accumulated by thread 0 (printed by solve_large when EZPZ_B200_DEBUG=1):
+    // 0 assembly + residual sweeps, 1 sums and maxima, 2 A/rhs assembly, 3 factor levels (grid), 4 top of the tree
+    // (one CTA: factor + backward), 5 backward levels (grid), 6 PCG, 7 everything
+    unsigned long long t[8];
 };
 
 struct LargeArgs {
     const uint32_t* recs;    // analysed constraints in PROCESSING order (see LargeRec below), word-transposed in
                              // tiles of 32: word w of slot k at recs[(k / 32) * kRecWords * 32 + w * 32 + k % 32]
     const uint32_t *csr_row_ptr, *csr_col_idx, *csc_col_ptr, *csc_row_idx, *csc_to_csr;
-    // direct path
-    const uint32_t *level_ptr, *op_dst, *op_fin, *op_code, *op_ptr, *pair_a, *pair_b;
-    double* vg;          // [x | r | rn | J csc | L | d]
+    // sparse direct path (structure.h: LargeProgram)
+    const uint32_t *perm, *lr_ptr, *lr_col, *lvl_ptr, *lvl_cols, *ent_ptr, *ent_row, *ent_col, *ent_slot;
+    const uint32_t *ent_mask_ptr, *ent_mask, *aent, *aprod_ptr, *aprod_a, *aprod_b, *lvl_maxrow;
+    double* vg;          // [x | r | rn | J csc | L by rows | diag(A) | 1/pivot | y | d]
     double* jr;          // J values in CSR order (PCG path)
     double* cgv;         // PCG vectors: p, res, ap, dinv (n each), q (m)
     double* partials;    // 3 * gridDim.x
+    double* sumsq;       // chunk sums of r^2 (multi-CTA grids)
+    unsigned long long* lvl_ns;  // debug (EZPZ_B200_DEBUG=1): per level, ns spent in factor / backward phases, else NULL
     uint8_t* side;       // resolved side per processing slot
     uint32_t* degen;     // per-constraint Warning::Degenerate counters
     uint32_t* unsat;     // bit mask
     LargeCtrl* ctrl;
     double residual_tolerance, step_tolerance, initial_lambda, cg_rtol;
     uint32_t max_iterations, cg_max_iters;
-    uint32_t n_cons, n_slots, n, m, nnz, n_levels;
+    uint32_t n_cons, n_slots, n, m, nnz, n_levels, solo_level, nnz_l, n_aent;
     uint32_t unit_weights;
-    uint32_t X0, R0, RN0, J0, L0, D0;
+    uint32_t X0, R0, RN0, J0, L0, DG0, RV0, Y0, D0;
     uint32_t direct;
 };
 
@@ -114,7 +128,7 @@ __device__ __forceinline__ bool kind_has_p1(uint32_t kind) {
 //   precomputed scatter slots) and, when write_jr, into the CSR-ordered copy used by the row-wise SpMV (the
 //   entries of a constraint's rows are contiguous there, so that copy needs one base and 4-bit offsets).
 template <bool RES, bool JAC>
-__device__ void assemble_phase(const LargeArgs& a, uint32_t rdst, uint32_t tid, uint32_t nth, bool write_jr) {
+__device__ __forceinline__ void assemble_phase_inl(const LargeArgs& a, uint32_t rdst, uint32_t tid, uint32_t nth, bool write_jr) {
     const double* __restrict__ x = a.vg + a.X0;
     for (uint32_t k = tid; k < a.n_slots; k += nth) {
         const RecPtr rec = rec_at(a.recs, k);
@@ -170,6 +184,12 @@ __device__ void assemble_phase(const LargeArgs& a, uint32_t rdst, uint32_t tid, 
     }
 }
 
+// Out-of-line copy for the persistent kernel (keeps its register allocation apart from the solver phases).
+template <bool RES, bool JAC>
+__device__ __noinline__ void assemble_phase(const LargeArgs& a, uint32_t rdst, uint32_t tid, uint32_t nth, bool write_jr) {
+    assemble_phase_inl<RES, JAC>(a, rdst, tid, nth, write_jr);
+}
+
 // NaN-ignoring max |v[i]| over the grid: per-block partial to partials[blockIdx.x]; caller syncs, then every
 // thread folds the partials (same order everywhere).
 __device__ void max_abs_partial(const double* v, uint32_t count, uint32_t tid, uint32_t nth, double* partial_out,
@@ -185,10 +205,19 @@ __device__ void max_abs_partial(const double* v, uint32_t count, uint32_t tid, u
     if (threadIdx.x == 0) *partial_out = sm[0];
     __syncthreads();
 }
-__device__ double fold_max(const double* partials, uint32_t count) {
-    double mx = partials[0];
-    for (uint32_t i = 1; i < count; ++i) mx = ezm::ez_fmax(mx, partials[i]);
-    return mx;
+// Fold of the per-CTA partials, done once per CTA (thread 0, same order in every CTA) and broadcast through
+// shared memory.  Must be called by every thread of the CTA.
+__device__ double fold_max(const double* partials, uint32_t count, double* sm) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double mx = partials[0];
+        for (uint32_t i = 1; i < count; ++i) mx = ezm::ez_fmax(mx, partials[i]);
+        sm[0] = mx;
+    }
+    __syncthreads();
+    const double v = sm[0];
+    __syncthreads();
+    return v;
 }
 // Deterministic block sum (fixed tree) of one value per thread -> partial_out.
 __device__ void block_sum(double v, double* partial_out, double* sm) {
@@ -201,10 +230,25 @@ __device__ void block_sum(double v, double* partial_out, double* sm) {
     if (threadIdx.x == 0) *partial_out = sm[0];
     __syncthreads();
 }
-__device__ double fold_sum(const double* partials, uint32_t count) {
-    double s = 0.0;
-    for (uint32_t i = 0; i < count; ++i) s = s + partials[i];
-    return s;
+__device__ double fold_sum(const double* partials, uint32_t count, double* sm) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        uint32_t i = 0;
+        for (; i + 8 <= count; i += 8) {
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = partials[i + u];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) s = s + v[u];
+        }
+        for (; i < count; ++i) s = s + partials[i];
+        sm[0] = s;
+    }
+    __syncthreads();
+    const double v = sm[0];
+    __syncthreads();
+    return v;
 }
 
 // Sequential left fold of v[i]^2 (block 0 only): the CTA stages squares in shared memory chunk by chunk, one
@@ -233,11 +277,367 @@ __device__ void sequential_sum_squares(const double* v, uint32_t count, double* 
     if (threadIdx.x == 0) *out = acc;
 }
 
+// Chunked sum of squares for multi-CTA grids: chunk c = rows [c * kSumChunk, ...) folded sequentially from +0.0
+// into out[c]; the caller synchronises and folds the chunk sums sequentially (fold_sum).
+constexpr uint32_t kSumChunk = 1024;
+__device__ void chunk_sum_squares(const double* v, uint32_t count, double* out, uint32_t tid, uint32_t nth, double* warp_stage) {
+    // One warp per chunk: the lanes stage the chunk in shared memory with coalesced loads (kWarpStageDoubles = 512
+    // values per round), lane 0 runs the dependent chain of adds from there.
+    const uint32_t chunks = (count + kSumChunk - 1) / kSumChunk;
+    const uint32_t lane = threadIdx.x & 31u, n_warps = nth >> 5;
+    for (uint32_t c = tid >> 5; c < chunks; c += n_warps) {
+        const uint32_t b = c * kSumChunk, e = min(count, b + kSumChunk);
+        double acc = 0.0;
+        for (uint32_t h = b; h < e; h += 512) {
+            const uint32_t len = min(512u, e - h);
+            for (uint32_t t = lane; t < len; t += 32) {
+                const double r = v[h + t];
+                warp_stage[t] = r * r;
+            }
+            __syncwarp();
+            if (lane == 0) {
+                uint32_t i = 0;
+                for (; i + 8 <= len; i += 8) {
+                    double q[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) q[u] = warp_stage[i + u];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) acc = acc + q[u];
+                }
+                for (; i < len; ++i) acc = acc + warp_stage[i];
+            }
+            __syncwarp();
+        }
+        if (lane == 0) out[c] = acc;
+    }
+}
+
+// ---- sparse direct step solve (schedule: sparse_direct.cpp) ---------------------------------------------
+// Loads are issued in batches that do not depend on the running sums, so that a dependent chain of fused
+// multiply-adds (the arithmetic-order spec is sequential in k) costs one memory round trip per kBatch terms
+// instead of one per term.
+constexpr int kBatch = 8;
+
+// A = JtJ + lambda*I in elimination numbering into the L value slots (pure fill entries start from +0.0),
+// the diagonal into diag[], b = -Jt r into y[].
+__device__ void direct_assemble(const LargeArgs& a, double lambda, uint32_t tid, uint32_t nth) {
+    const double* jv = a.vg + a.J0;
+    const double* r = a.vg + a.R0;
+    double* lv = a.vg + a.L0;
+    for (uint32_t e = tid; e < a.nnz_l; e += nth) {  // pure fill
+        const uint32_t s = __ldg(a.ent_slot + e);
+        if (!(s & kEntryInA)) lv[s] = 0.0;
+    }
+    for (uint32_t k = tid; k < a.n_aent; k += nth) {
+        const uint32_t s = __ldg(a.ent_slot + __ldg(a.aent + k)) & ~kEntryInA;
+        const uint32_t qb = __ldg(a.aprod_ptr + k), qe = __ldg(a.aprod_ptr + k + 1);
+        double acc = 0.0;
+        for (uint32_t q = qb; q < qe; ++q) acc = __fma_rn(jv[__ldg(a.aprod_a + q)], jv[__ldg(a.aprod_b + q)], acc);
+        lv[s] = acc;
+    }
+    for (uint32_t j = tid; j < a.n; j += nth) {
+        const uint32_t c = __ldg(a.perm + j);
+        double dg = 0.0, b = 0.0;
+        for (uint32_t e = __ldg(a.csc_col_ptr + c); e < __ldg(a.csc_col_ptr + c + 1); ++e) {
+            const double v = jv[e];
+            dg = __fma_rn(v, v, dg);
+            b = __fma_rn(v, -r[__ldg(a.csc_row_idx + e)], b);
+        }
+        a.vg[a.DG0 + j] = __dadd_rn(dg, lambda);
+        a.vg[a.Y0 + j] = b;
+    }
+}
+
+// Iterator over the set bits of a mask stored as consecutive 32-bit words (ascending positions).
+struct BitWalk {
+    const uint32_t* w;
+    uint32_t word, base;
+    __device__ __forceinline__ void init(const uint32_t* words) {
+        w = words;
+        word = __ldg(w);
+        base = 0;
+    }
+    __device__ __forceinline__ uint32_t next() {  // caller guarantees another set bit exists
+        while (word == 0) {
+            ++w;
+            base += 32;
+            word = __ldg(w);
+        }
+        const uint32_t b = __ffs(word) - 1;
+        word &= word - 1;
+        return base + b;
+    }
+};
+
+// ---- one work item of a factorisation level -----------------------------------------------------------------
+// Entry item (i, j): L[i][j] = (A[i][j] - sum_k L[i][k] L[j][k]) / L[j][j], k ascending over the columns present
+// in both rows (static masks), with column j's pivot recomputed from row j (same operations, same order as the
+// column item) so that entries and pivots of a level need no barrier between them.
+__device__ __noinline__ void factor_entry_thread(const LargeArgs& a, uint32_t e) {
+    double* lv = a.vg + a.L0;
+    const uint32_t i = __ldg(a.ent_row + e), j = __ldg(a.ent_col + e), s = __ldg(a.ent_slot + e) & ~kEntryInA;
+    const uint32_t mp = __ldg(a.ent_mask_ptr + e);
+    const uint32_t ri0 = __ldg(a.lr_ptr + i), rj0 = __ldg(a.lr_ptr + j), len_j = __ldg(a.lr_ptr + j + 1) - rj0;
+    const uint32_t wj = (len_j + 31) >> 5;
+    double acc = lv[s], piv = a.vg[a.DG0 + j];
+    const double* rowj = lv + rj0;
+    const double* rowi = lv + ri0;
+    uint32_t n_match = 0;
+    for (uint32_t q = 0; q < wj; ++q) n_match += __popc(__ldg(a.ent_mask + mp + q));
+    BitWalk bj, bi;
+    if (n_match) {
+        bj.init(a.ent_mask + mp);
+        bi.init(a.ent_mask + mp + wj);
+    }
+    // the two chains advance together, one batch of independent loads per step
+    uint32_t t = 0, q = 0;
+    while (t + kBatch <= len_j || q + kBatch <= n_match) {
+        const bool do_p = t + kBatch <= len_j, do_m = q + kBatch <= n_match;
+        double v[kBatch], vi[kBatch], vj[kBatch];
+        if (do_p) {
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u) v[u] = rowj[t + u];
+        }
+        if (do_m) {
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u) {
+                vi[u] = rowi[bi.next()];
+                vj[u] = rowj[bj.next()];
+            }
+        }
+        if (do_p) {
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u) piv = __fma_rn(-v[u], v[u], piv);
+            t += kBatch;
+        }
+        if (do_m) {
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u) acc = __fma_rn(-vi[u], vj[u], acc);
+            q += kBatch;
+        }
+    }
+    for (; t < len_j; ++t) {
+        const double v = rowj[t];
+        piv = __fma_rn(-v, v, piv);
+    }
+    for (; q < n_match; ++q) {
+        const double vi = rowi[bi.next()], vj = rowj[bj.next()];
+        acc = __fma_rn(-vi, vj, acc);
+    }
+    const double rinv = __ddiv_rn(1.0, __dsqrt_rn(piv));
+    lv[s] = __dmul_rn(acc, rinv);
+}
+
+// Column item j: pivot -> 1/pivot, and the forward substitution y[j] = (b[j] - sum_k L[j][k] y[k]) / L[j][j].
+__device__ __noinline__ void factor_column_thread(const LargeArgs& a, uint32_t j) {
+    const double* lv = a.vg + a.L0;
+    double* y = a.vg + a.Y0;
+    const uint32_t rj0 = __ldg(a.lr_ptr + j), len_j = __ldg(a.lr_ptr + j + 1) - rj0;
+    double piv = a.vg[a.DG0 + j], ay = y[j];
+    uint32_t t = 0;
+    for (; t + kBatch <= len_j; t += kBatch) {
+        double v[kBatch], yv[kBatch];
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) {
+            v[u] = lv[rj0 + t + u];
+            yv[u] = y[__ldg(a.lr_col + rj0 + t + u)];
+        }
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) {
+            piv = __fma_rn(-v[u], v[u], piv);
+            ay = __fma_rn(-v[u], yv[u], ay);
+        }
+    }
+    for (; t < len_j; ++t) {
+        const double l = lv[rj0 + t];
+        piv = __fma_rn(-l, l, piv);
+        ay = __fma_rn(-l, y[__ldg(a.lr_col + rj0 + t)], ay);
+    }
+    if (!(piv > 0.0) || !ezm::ez_isfinite(piv)) a.ctrl->fail = 1;
+    const double rinv = __ddiv_rn(1.0, __dsqrt_rn(piv));
+    a.vg[a.RV0 + j] = rinv;
+    y[j] = __dmul_rn(ay, rinv);
+}
+
+// Backward item: column at position p of the level list, d[j] = (y[j] - sum_{k > j} L[k][j] d[k]) / L[j][j].
+__device__ __noinline__ void backward_column_thread(const LargeArgs& a, uint32_t p) {
+    const double* lv = a.vg + a.L0;
+    double* y = a.vg + a.Y0;
+    const uint32_t j = __ldg(a.lvl_cols + p);
+    double acc = y[j];
+    uint32_t q = __ldg(a.ent_ptr + p);
+    const uint32_t qe = __ldg(a.ent_ptr + p + 1);
+    for (; q + kBatch <= qe; q += kBatch) {
+        double l[kBatch], yv[kBatch];
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) {
+            l[u] = lv[__ldg(a.ent_slot + q + u) & ~kEntryInA];
+            yv[u] = y[__ldg(a.ent_row + q + u)];
+        }
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) acc = __fma_rn(-l[u], yv[u], acc);
+    }
+    for (; q < qe; ++q) acc = __fma_rn(-lv[__ldg(a.ent_slot + q) & ~kEntryInA], y[__ldg(a.ent_row + q)], acc);
+    const double v = __dmul_rn(acc, a.vg[a.RV0 + j]);
+    y[j] = v;
+    a.vg[a.D0 + __ldg(a.perm + j)] = v;
+}
+
+// ---- warp-cooperative variants for the upper part of the tree (few items, long rows) ------------------------
+// The 32 lanes stage the rows in shared memory with coalesced loads (one memory round trip instead of one per
+// batch), then lane 0 / lane 1 run the two sequential chains from shared memory.  Rows longer than kRowCap fall
+// back to the thread variant on lane 0.
+constexpr uint32_t kRowCap = 256;
+constexpr uint32_t kWarpStageDoubles = 2 * kRowCap;
+
+__device__ __noinline__ void factor_entry_warp(const LargeArgs& a, uint32_t e, uint32_t lane, double* st) {
+    double* lv = a.vg + a.L0;
+    const uint32_t i = __ldg(a.ent_row + e), j = __ldg(a.ent_col + e), s = __ldg(a.ent_slot + e) & ~kEntryInA;
+    const uint32_t ri0 = __ldg(a.lr_ptr + i), rj0 = __ldg(a.lr_ptr + j), len_j = __ldg(a.lr_ptr + j + 1) - rj0;
+    const uint32_t pre_i = s - ri0;
+    if (len_j > kRowCap || pre_i > kRowCap) {
+        if (lane == 0) factor_entry_thread(a, e);
+        return;
+    }
+    double* sj = st;
+    double* si = st + kRowCap;
+    for (uint32_t t = lane; t < len_j; t += 32) sj[t] = lv[rj0 + t];
+    for (uint32_t t = lane; t < pre_i; t += 32) si[t] = lv[ri0 + t];
+    __syncwarp();
+    double res = 0.0;
+    if (lane == 0) {
+        const uint32_t mp = __ldg(a.ent_mask_ptr + e), wj = (len_j + 31) >> 5;
+        uint32_t n_match = 0;
+        for (uint32_t q = 0; q < wj; ++q) n_match += __popc(__ldg(a.ent_mask + mp + q));
+        double acc = lv[s];
+        if (n_match) {
+            BitWalk bj, bi;
+            bj.init(a.ent_mask + mp);
+            bi.init(a.ent_mask + mp + wj);
+            for (uint32_t q = 0; q < n_match; ++q) {
+                const double vi = si[bi.next()], vj = sj[bj.next()];
+                acc = __fma_rn(-vi, vj, acc);
+            }
+        }
+        res = acc;
+    } else if (lane == 1) {
+        double piv = a.vg[a.DG0 + j];
+        for (uint32_t t = 0; t < len_j; ++t) piv = __fma_rn(-sj[t], sj[t], piv);
+        res = __ddiv_rn(1.0, __dsqrt_rn(piv));
+    }
+    const double rinv = __shfl_sync(0xffffffffu, res, 1);
+    if (lane == 0) lv[s] = __dmul_rn(res, rinv);
+    __syncwarp();
+}
+
+__device__ __noinline__ void factor_column_warp(const LargeArgs& a, uint32_t j, uint32_t lane, double* st) {
+    const double* lv = a.vg + a.L0;
+    double* y = a.vg + a.Y0;
+    const uint32_t rj0 = __ldg(a.lr_ptr + j), len_j = __ldg(a.lr_ptr + j + 1) - rj0;
+    if (len_j > kRowCap) {
+        if (lane == 0) factor_column_thread(a, j);
+        return;
+    }
+    double* sj = st;
+    double* sy = st + kRowCap;
+    for (uint32_t t = lane; t < len_j; t += 32) {
+        sj[t] = lv[rj0 + t];
+        sy[t] = y[__ldg(a.lr_col + rj0 + t)];
+    }
+    __syncwarp();
+    double res = 0.0;
+    if (lane == 0) {
+        double piv = a.vg[a.DG0 + j];
+        for (uint32_t t = 0; t < len_j; ++t) piv = __fma_rn(-sj[t], sj[t], piv);
+        if (!(piv > 0.0) || !ezm::ez_isfinite(piv)) a.ctrl->fail = 1;
+        res = __ddiv_rn(1.0, __dsqrt_rn(piv));
+    } else if (lane == 1) {
+        double ay = y[j];
+        for (uint32_t t = 0; t < len_j; ++t) ay = __fma_rn(-sj[t], sy[t], ay);
+        res = ay;
+    }
+    const double rinv = __shfl_sync(0xffffffffu, res, 0);
+    if (lane == 0) a.vg[a.RV0 + j] = rinv;
+    if (lane == 1) y[j] = __dmul_rn(res, rinv);
+    __syncwarp();
+}
+
+__device__ __noinline__ void backward_column_warp(const LargeArgs& a, uint32_t p, uint32_t lane, double* st) {
+    const double* lv = a.vg + a.L0;
+    double* y = a.vg + a.Y0;
+    const uint32_t q0 = __ldg(a.ent_ptr + p), len = __ldg(a.ent_ptr + p + 1) - q0;
+    if (len > kRowCap) {
+        if (lane == 0) backward_column_thread(a, p);
+        return;
+    }
+    double* sl = st;
+    double* sy = st + kRowCap;
+    for (uint32_t t = lane; t < len; t += 32) {
+        sl[t] = lv[__ldg(a.ent_slot + q0 + t) & ~kEntryInA];
+        sy[t] = y[__ldg(a.ent_row + q0 + t)];
+    }
+    __syncwarp();
+    if (lane == 0) {
+        const uint32_t j = __ldg(a.lvl_cols + p);
+        double acc = y[j];
+        for (uint32_t t = 0; t < len; ++t) acc = __fma_rn(-sl[t], sy[t], acc);
+        const double v = __dmul_rn(acc, a.vg[a.RV0 + j]);
+        y[j] = v;
+        a.vg[a.D0 + __ldg(a.perm + j)] = v;
+    }
+    __syncwarp();
+}
+
+// One elimination-tree level of the factorisation fused with the forward substitution, run by the thread set
+// (tid, nth) — the whole grid or one CTA.  Work items: the level's sub-diagonal entries and its columns.  Levels
+// with long rows and few items (the upper part of the tree) are run one item per warp.
+__device__ void direct_factor_level(const LargeArgs& a, uint32_t lvl, uint32_t tid, uint32_t nth, double* warp_stage) {
+    const uint32_t pb = __ldg(a.lvl_ptr + lvl), pe = __ldg(a.lvl_ptr + lvl + 1);
+    const uint32_t eb = __ldg(a.ent_ptr + pb), ee = __ldg(a.ent_ptr + pe);
+    const uint32_t n_ent = ee - eb, n_items = n_ent + (pe - pb);
+    const uint32_t n_warps = nth >> 5;
+    if (__ldg(a.lvl_maxrow + lvl) > 24 && n_items <= 2 * n_warps) {
+        const uint32_t lane = threadIdx.x & 31u;
+        for (uint32_t w = tid >> 5; w < n_items; w += n_warps) {
+            if (w < n_ent) factor_entry_warp(a, eb + w, lane, warp_stage);
+            else factor_column_warp(a, __ldg(a.lvl_cols + pb + (w - n_ent)), lane, warp_stage);
+        }
+        return;
+    }
+    for (uint32_t w = tid; w < n_items; w += nth) {
+        if (w < n_ent) factor_entry_thread(a, eb + w);
+        else factor_column_thread(a, __ldg(a.lvl_cols + pb + (w - n_ent)));
+    }
+}
+
+// One level of the backward substitution Lt d = y (levels descending); the final value is also scattered to d
+// in variable numbering.
+__device__ void direct_backward_level(const LargeArgs& a, uint32_t lvl, uint32_t tid, uint32_t nth, double* warp_stage) {
+    const uint32_t pb = __ldg(a.lvl_ptr + lvl), pe = __ldg(a.lvl_ptr + lvl + 1);
+    const uint32_t n_warps = nth >> 5;
+    if (pe - pb <= 2 * n_warps) {
+        const uint32_t lane = threadIdx.x & 31u;
+        for (uint32_t p = pb + (tid >> 5); p < pe; p += n_warps) backward_column_warp(a, p, lane, warp_stage);
+        return;
+    }
+    for (uint32_t p = pb + tid; p < pe; p += nth) backward_column_thread(a, p);
+}
+
 constexpr uint32_t kBlock = 512;
 constexpr uint32_t kSmDoubles = 4096;  // 32 KB staging
 
+__device__ __forceinline__ unsigned long long now_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+constexpr size_t kLmDynamicSmem = (kBlock / 32) * kWarpStageDoubles * sizeof(double);  // 64 KB
+
 __global__ void __launch_bounds__(kBlock) lm_large_kernel(const LargeArgs a) {
     __shared__ double sm[kSmDoubles];
+    extern __shared__ double warp_stage_all[];  // (kBlock / 32) * kWarpStageDoubles, see kLmDynamicSmem
+    double* warp_stage = warp_stage_all + (threadIdx.x >> 5) * kWarpStageDoubles;
     cg::grid_group grid = cg::this_grid();
     const bool single = gridDim.x == 1;
     auto sync = [&]() {
@@ -252,6 +652,13 @@ __global__ void __launch_bounds__(kBlock) lm_large_kernel(const LargeArgs a) {
     double* ps1 = a.partials + G;      // rz
     double* ps2 = a.partials + 2 * G;  // rr
     const bool use_cg = !a.direct;
+    unsigned long long t_mark = now_ns(), t_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const unsigned long long t_begin = t_mark;
+    auto lap = [&](int k) {  // charge the time since the previous mark to phase k (thread 0's view)
+        const unsigned long long t = now_ns();
+        t_acc[k] += t - t_mark;
+        t_mark = t;
+    };
 
     // sides from the initial guesses (lib.rs:183-186), counters
     {
@@ -283,17 +690,29 @@ __global__ void __launch_bounds__(kBlock) lm_large_kernel(const LargeArgs a) {
     sync();
     assemble_phase<true, true>(a, a.R0, tid, nth, use_cg);
     sync();
-    if (blockIdx.x == 0) sequential_sum_squares(vg + a.R0, a.m, &ctrl->S, sm, kSmDoubles);
-    sync();
+    lap(0);
+    // S = sum r^2 (see the header comment for the two summation orders)
+    const uint32_t n_chunks = (a.m + kSumChunk - 1) / kSumChunk;
+    auto sum_squares = [&](const double* v, double* ctrl_slot) -> double {
+        if (single) {
+            sequential_sum_squares(v, a.m, ctrl_slot, sm, kSmDoubles);
+            __syncthreads();
+            return *ctrl_slot;
+        }
+        chunk_sum_squares(v, a.m, a.sumsq, tid, nth, warp_stage);
+        grid.sync();
+        return fold_sum(a.sumsq, n_chunks, sm);
+    };
 
-    double lambda = a.initial_lambda, S = ctrl->S;
+    double lambda = a.initial_lambda, S = sum_squares(vg + a.R0, &ctrl->S);
     uint32_t iterations = a.max_iterations;
     bool converged = false;
     uint32_t lin_iters = 0;
     for (uint32_t it = 0; it < a.max_iterations; ++it) {
         max_abs_partial(vg + a.R0, a.m, tid, nth, &pm[blockIdx.x], sm);
         sync();
-        const double largest = fold_max(pm, G);
+        const double largest = fold_max(pm, G, sm);
+        lap(1);
         if (largest <= a.residual_tolerance) {
             iterations = it;
             converged = true;
@@ -301,28 +720,35 @@ __global__ void __launch_bounds__(kBlock) lm_large_kernel(const LargeArgs a) {
         }
         bool fail = false;
         if (!use_cg) {
-            // level-scheduled direct solve (same op semantics as run_tape in device.cu)
-            for (uint32_t lv = 0; lv < a.n_levels; ++lv) {
-                const uint32_t ob = a.level_ptr[lv], oe = a.level_ptr[lv + 1];
-                for (uint32_t o = ob + tid; o < oe; o += nth) {
-                    const uint32_t dst = a.op_dst[o], code = a.op_code[o];
-                    double acc = (code & OP_INIT_DST) ? vg[dst] : 0.0;
-                    const uint32_t pb = a.op_ptr[o], pe = a.op_ptr[o + 1];
-                    if (code & OP_NEGATE)
-                        for (uint32_t q = pb; q < pe; ++q) acc = __fma_rn(-vg[a.pair_a[q]], vg[a.pair_b[q]], acc);
-                    else
-                        for (uint32_t q = pb; q < pe; ++q) acc = __fma_rn(vg[a.pair_a[q]], vg[a.pair_b[q]], acc);
-                    const uint32_t fk = (code >> OP_FIN_SHIFT) & 3u;
-                    if (fk == OP_FIN_LAMBDA) acc = __dadd_rn(acc, lambda);
-                    else if (fk == OP_FIN_MUL) acc = __dmul_rn(acc, vg[a.op_fin[o]]);
-                    else if (fk == OP_FIN_PIVOT) {
-                        if (!(acc > 0.0) || !ezm::ez_isfinite(acc)) ctrl->fail = 1;
-                        acc = __ddiv_rn(1.0, __dsqrt_rn(acc));
-                    }
-                    vg[dst] = acc;
-                }
+            direct_assemble(a, lambda, tid, nth);
+            sync();
+            lap(2);
+            for (uint32_t lv = 0; lv < a.solo_level; ++lv) {
+                const unsigned long long t0 = a.lvl_ns ? now_ns() : 0ull;
+                direct_factor_level(a, lv, tid, nth, warp_stage);
                 sync();
+                if (a.lvl_ns && tid == 0) a.lvl_ns[2 * lv] += now_ns() - t0;
             }
+            lap(3);
+            if (a.solo_level < a.n_levels && blockIdx.x == 0) {  // top of the tree: one CTA, CTA-level barriers
+                for (uint32_t lv = a.solo_level; lv < a.n_levels; ++lv) {
+                    direct_factor_level(a, lv, threadIdx.x, blockDim.x, warp_stage);
+                    __syncthreads();
+                }
+                for (uint32_t lv = a.n_levels; lv-- > a.solo_level;) {
+                    direct_backward_level(a, lv, threadIdx.x, blockDim.x, warp_stage);
+                    __syncthreads();
+                }
+            }
+            if (a.solo_level < a.n_levels) sync();
+            lap(4);
+            for (uint32_t lv = a.solo_level; lv-- > 0;) {
+                const unsigned long long t0 = a.lvl_ns ? now_ns() : 0ull;
+                direct_backward_level(a, lv, tid, nth, warp_stage);
+                sync();
+                if (a.lvl_ns && tid == 0) a.lvl_ns[2 * lv + 1] += now_ns() - t0;
+            }
+            lap(5);
             fail = ctrl->fail != 0;
         } else {
             // Jacobi-preconditioned CG on (JtJ + lambda I) d = -Jt r
@@ -354,8 +780,8 @@ __global__ void __launch_bounds__(kBlock) lm_large_kernel(const LargeArgs a) {
             block_sum(lrz, &ps1[blockIdx.x], sm);
             block_sum(lbb, &ps2[blockIdx.x], sm);
             sync();
-            double rz = fold_sum(ps1, G);
-            const double bb = fold_sum(ps2, G);
+            double rz = fold_sum(ps1, G, sm);
+            const double bb = fold_sum(ps2, G, sm);
             const double stop = a.cg_rtol * a.cg_rtol * bb;
             if (bb > 0.0) {
                 for (uint32_t k = 0; k < a.cg_max_iters; ++k) {
@@ -374,7 +800,7 @@ __global__ void __launch_bounds__(kBlock) lm_large_kernel(const LargeArgs a) {
                     }
                     block_sum(lpap, &pm[blockIdx.x], sm);
                     sync();
-                    const double pap = fold_sum(pm, G);
+                    const double pap = fold_sum(pm, G, sm);
                     ++lin_iters;
                     if (!(pap > 0.0) || !ezm::ez_isfinite(pap)) {
                         fail = true;
@@ -392,8 +818,8 @@ __global__ void __launch_bounds__(kBlock) lm_large_kernel(const LargeArgs a) {
                     block_sum(lrz2, &ps1[blockIdx.x], sm);
                     block_sum(lrr, &ps2[blockIdx.x], sm);
                     sync();
-                    const double rz2 = fold_sum(ps1, G);
-                    const double rr = fold_sum(ps2, G);
+                    const double rz2 = fold_sum(ps1, G, sm);
+                    const double rr = fold_sum(ps2, G, sm);
                     if (rr <= stop) break;
                     const double beta = rz2 / rz;
                     rz = rz2;
@@ -402,6 +828,7 @@ __global__ void __launch_bounds__(kBlock) lm_large_kernel(const LargeArgs a) {
                 }
             }
             sync();
+            lap(6);
         }
         if (fail) {
             sync();
@@ -412,14 +839,15 @@ __global__ void __launch_bounds__(kBlock) lm_large_kernel(const LargeArgs a) {
         }
         max_abs_partial(vg + a.D0, a.n, tid, nth, &pm[blockIdx.x], sm);
         sync();
-        const double step = fold_max(pm, G);
+        const double step = fold_max(pm, G, sm);
         for (uint32_t j = tid; j < a.n; j += nth) vg[a.X0 + j] += vg[a.D0 + j];
         sync();
+        lap(1);
         assemble_phase<true, false>(a, a.RN0, tid, nth, false);
         sync();
-        if (blockIdx.x == 0) sequential_sum_squares(vg + a.RN0, a.m, &ctrl->S2, sm, kSmDoubles);
-        sync();
-        const double S2 = ctrl->S2;
+        lap(0);
+        const double S2 = sum_squares(vg + a.RN0, &ctrl->S2);
+        lap(1);
         if (S2 < S) {
             for (uint32_t i = tid; i < a.m; i += nth) vg[a.R0 + i] = vg[a.RN0 + i];
             assemble_phase<false, true>(a, a.R0, tid, nth, use_cg);
@@ -430,6 +858,7 @@ __global__ void __launch_bounds__(kBlock) lm_large_kernel(const LargeArgs a) {
             lambda *= 10.0;
         }
         sync();
+        lap(0);
         if (step <= a.step_tolerance) {
             iterations = it;
             converged = true;
@@ -461,6 +890,9 @@ __global__ void __launch_bounds__(kBlock) lm_large_kernel(const LargeArgs a) {
         }
     }
     if (tid == 0) {
+        lap(0);
+        t_acc[7] = now_ns() - t_begin;
+        for (int k = 0; k < 8; ++k) ctrl->t[k] = t_acc[k];
         ctrl->iterations = iterations;
         ctrl->converged = converged ? 1u : 0u;
         ctrl->lambda = lambda;
@@ -471,7 +903,7 @@ __global__ void __launch_bounds__(kBlock) lm_large_kernel(const LargeArgs a) {
 
 // ---- stand-alone kernels for throughput measurement (same device code as the phases above) ------------
 __global__ void __launch_bounds__(128, 5) assemble_large_kernel(const LargeArgs a, const bool write_jr) {
-    assemble_phase<true, true>(a, a.R0, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x, write_jr);
+    assemble_phase_inl<true, true>(a, a.R0, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x, write_jr);
 }
 __global__ void __launch_bounds__(256) spmv_csr_kernel(const uint32_t* __restrict__ row_ptr, const uint32_t* __restrict__ col_idx,
                                                        const double* __restrict__ vals, const double* __restrict__ x,
@@ -487,8 +919,11 @@ struct LargeDevice {
     uint32_t* recs = nullptr;
     uint32_t n_slots = 0;
     uint32_t *csr_row_ptr = nullptr, *csr_col_idx = nullptr, *csc_col_ptr = nullptr, *csc_row_idx = nullptr;
-    uint32_t *level_ptr = nullptr, *op_dst = nullptr, *op_fin = nullptr, *op_code = nullptr, *op_ptr = nullptr, *pair_a = nullptr, *pair_b = nullptr;
-    double *vg = nullptr, *jr = nullptr, *cgv = nullptr, *partials = nullptr;
+    uint32_t *perm = nullptr, *lr_ptr = nullptr, *lr_col = nullptr, *lvl_ptr = nullptr, *lvl_cols = nullptr, *ent_ptr = nullptr,
+             *ent_row = nullptr, *ent_col = nullptr, *ent_slot = nullptr, *ent_mask_ptr = nullptr, *ent_mask = nullptr,
+             *aent = nullptr, *aprod_ptr = nullptr, *aprod_a = nullptr, *aprod_b = nullptr, *lvl_maxrow = nullptr;
+    double *vg = nullptr, *jr = nullptr, *cgv = nullptr, *partials = nullptr, *sumsq = nullptr;
+    unsigned long long* lvl_ns = nullptr;
     uint8_t* side = nullptr;
     uint32_t *degen = nullptr, *unsat = nullptr;
     LargeCtrl* ctrl = nullptr;
@@ -562,18 +997,34 @@ int32_t get_large(ezpz_context* ctx, const ezpz_structure* s, DeviceCopy* dc, La
     EZ_TRY(upload(&L->csr_col_idx, s->csr_col_idx, detail));
     EZ_TRY(upload(&L->csc_col_ptr, s->csc_col_ptr, detail));
     EZ_TRY(upload(&L->csc_row_idx, s->csc_row_idx, detail));
-    EZ_TRY(upload(&L->level_ptr, P.level_ptr, detail));
-    EZ_TRY(upload(&L->op_dst, P.op_dst, detail));
-    EZ_TRY(upload(&L->op_fin, P.op_fin, detail));
-    EZ_TRY(upload(&L->op_code, P.op_code, detail));
-    EZ_TRY(upload(&L->op_ptr, P.op_ptr, detail));
-    EZ_TRY(upload(&L->pair_a, P.pair_a, detail));
-    EZ_TRY(upload(&L->pair_b, P.pair_b, detail));
+    if (P.direct) {
+        EZ_TRY(upload(&L->perm, P.perm, detail));
+        EZ_TRY(upload(&L->lr_ptr, P.lr_ptr, detail));
+        EZ_TRY(upload(&L->lr_col, P.lr_col, detail));
+        EZ_TRY(upload(&L->lvl_ptr, P.lvl_ptr, detail));
+        EZ_TRY(upload(&L->lvl_cols, P.lvl_cols, detail));
+        EZ_TRY(upload(&L->ent_ptr, P.ent_ptr, detail));
+        EZ_TRY(upload(&L->ent_row, P.ent_row, detail));
+        EZ_TRY(upload(&L->ent_col, P.ent_col, detail));
+        EZ_TRY(upload(&L->ent_slot, P.ent_slot, detail));
+        EZ_TRY(upload(&L->ent_mask_ptr, P.ent_mask_ptr, detail));
+        EZ_TRY(upload(&L->ent_mask, P.ent_mask, detail));
+        EZ_TRY(upload(&L->aent, P.aent, detail));
+        EZ_TRY(upload(&L->aprod_ptr, P.aprod_ptr, detail));
+        EZ_TRY(upload(&L->aprod_a, P.aprod_a, detail));
+        EZ_TRY(upload(&L->aprod_b, P.aprod_b, detail));
+        EZ_TRY(upload(&L->lvl_maxrow, P.lvl_maxrow, detail));
+    }
     const size_t nnz = s->csc_row_idx.size();
     EZ_CUDA(cudaMalloc(&L->vg, sizeof(double) * std::max<size_t>(1, P.VG)), "cudaMalloc(vg)");
     EZ_CUDA(cudaMemset(L->vg, 0, sizeof(double) * std::max<size_t>(1, P.VG)), "cudaMemset(vg)");
     EZ_CUDA(cudaMalloc(&L->jr, sizeof(double) * std::max<size_t>(1, nnz)), "cudaMalloc(jr)");
     EZ_CUDA(cudaMalloc(&L->cgv, sizeof(double) * (4 * (size_t)s->n + s->m + 1)), "cudaMalloc(cgv)");
+    if (const char* dbg = std::getenv("EZPZ_B200_DEBUG"); dbg && dbg[0] == '1' && dbg[1] == '2' && P.direct) {
+        EZ_CUDA(cudaMalloc(&L->lvl_ns, sizeof(unsigned long long) * 2 * std::max<size_t>(1, P.n_levels)), "cudaMalloc(lvl_ns)");
+        EZ_CUDA(cudaMemset(L->lvl_ns, 0, sizeof(unsigned long long) * 2 * std::max<size_t>(1, P.n_levels)), "cudaMemset(lvl_ns)");
+    }
+    EZ_CUDA(cudaMalloc(&L->sumsq, sizeof(double) * ((size_t)s->m / kSumChunk + 2)), "cudaMalloc(sumsq)");
     EZ_CUDA(cudaMalloc(&L->side, std::max<size_t>(1, L->n_slots)), "cudaMalloc(side)");
     EZ_CUDA(cudaMalloc(&L->degen, sizeof(uint32_t) * std::max<size_t>(1, s->n_cons)), "cudaMalloc(degen)");
     EZ_CUDA(cudaMalloc(&L->unsat, sizeof(uint32_t) * ((s->n_cons + 31) / 32 + 1)), "cudaMalloc(unsat)");
@@ -581,7 +1032,9 @@ int32_t get_large(ezpz_context* ctx, const ezpz_structure* s, DeviceCopy* dc, La
     // grid: one CTA for small systems (barriers are __syncthreads), else every SM, co-resident
     const size_t work = (size_t)s->n + s->m + nnz;
     int per_sm = 0;
-    EZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lm_large_kernel, kBlock, 0), "occupancy");
+    EZ_CUDA(cudaFuncSetAttribute(lm_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLmDynamicSmem),
+            "cudaFuncSetAttribute(lm_large_kernel)");
+    EZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lm_large_kernel, kBlock, kLmDynamicSmem), "occupancy");
     if (per_sm < 1) per_sm = 1;
     L->grid = work <= 65536 ? 1 : ctx->sm_count * std::min(per_sm, 2);
     EZ_CUDA(cudaMalloc(&L->partials, sizeof(double) * 3 * (size_t)L->grid), "cudaMalloc(partials)");
@@ -610,13 +1063,25 @@ void fill_args(LargeArgs& a, const ezpz_structure* s, const DeviceCopy* dc, cons
     a.csc_col_ptr = L->csc_col_ptr;
     a.csc_row_idx = L->csc_row_idx;
     a.csc_to_csr = dc->csc_to_csr;
-    a.level_ptr = L->level_ptr;
-    a.op_dst = L->op_dst;
-    a.op_fin = L->op_fin;
-    a.op_code = L->op_code;
-    a.op_ptr = L->op_ptr;
-    a.pair_a = L->pair_a;
-    a.pair_b = L->pair_b;
+    a.perm = L->perm;
+    a.lr_ptr = L->lr_ptr;
+    a.lr_col = L->lr_col;
+    a.lvl_ptr = L->lvl_ptr;
+    a.lvl_cols = L->lvl_cols;
+    a.ent_ptr = L->ent_ptr;
+    a.ent_row = L->ent_row;
+    a.ent_col = L->ent_col;
+    a.ent_slot = L->ent_slot;
+    a.ent_mask_ptr = L->ent_mask_ptr;
+    a.ent_mask = L->ent_mask;
+    a.aent = L->aent;
+    a.aprod_ptr = L->aprod_ptr;
+    a.aprod_a = L->aprod_a;
+    a.aprod_b = L->aprod_b;
+    a.lvl_maxrow = L->lvl_maxrow;
+    a.n_aent = (uint32_t)P.aent.size();
+    a.sumsq = L->sumsq;
+    a.lvl_ns = L->lvl_ns;
     a.vg = L->vg;
     a.jr = L->jr;
     a.cgv = L->cgv;
@@ -636,11 +1101,16 @@ void fill_args(LargeArgs& a, const ezpz_structure* s, const DeviceCopy* dc, cons
     a.m = s->m;
     a.nnz = (uint32_t)s->csc_row_idx.size();
     a.n_levels = P.n_levels;
+    a.solo_level = P.solo_level;
+    a.nnz_l = P.nnz_l;
     a.X0 = P.X0;
     a.R0 = P.R0;
     a.RN0 = P.RN0;
     a.J0 = P.J0;
     a.L0 = P.L0;
+    a.DG0 = P.DG0;
+    a.RV0 = P.RV0;
+    a.Y0 = P.Y0;
     a.D0 = P.D0;
     a.direct = P.direct ? 1u : 0u;
 }
@@ -652,9 +1122,10 @@ namespace ezs {
 void release_large(DeviceCopy* d) {
     LargeDevice* L = (LargeDevice*)d->large;
     if (!L) return;
-    void* ptrs[] = {L->recs, L->csr_row_ptr, L->csr_col_idx, L->csc_col_ptr, L->csc_row_idx, L->level_ptr, L->op_dst,
-                    L->op_fin, L->op_code, L->op_ptr, L->pair_a, L->pair_b, L->vg, L->jr, L->cgv, L->partials, L->side,
-                    L->degen, L->unsat, L->ctrl};
+    void* ptrs[] = {L->recs, L->csr_row_ptr, L->csr_col_idx, L->csc_col_ptr, L->csc_row_idx, L->perm, L->lr_ptr, L->lr_col,
+                    L->lvl_ptr, L->lvl_cols, L->ent_ptr, L->ent_row, L->ent_col, L->ent_slot, L->ent_mask_ptr, L->ent_mask, L->aent,
+                    L->aprod_ptr, L->aprod_a, L->aprod_b, L->lvl_maxrow, L->vg, L->jr, L->cgv,
+                    L->partials, L->sumsq, L->lvl_ns, L->side, L->degen, L->unsat, L->ctrl};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     delete L;
@@ -676,9 +1147,9 @@ int32_t solve_large(ezpz_context* ctx, const ezpz_structure* s, const ezpz_confi
     EZ_CUDA(cudaMemcpyAsync(L->vg + a.X0, io->guesses, sizeof(double) * s->n, cudaMemcpyHostToDevice, st), "H2D guesses");
     void* params[] = {(void*)&a};
     if (L->grid == 1) {
-        lm_large_kernel<<<1, kBlock, 0, st>>>(a);
+        lm_large_kernel<<<1, kBlock, kLmDynamicSmem, st>>>(a);
     } else {
-        EZ_CUDA(cudaLaunchCooperativeKernel((void*)lm_large_kernel, dim3(L->grid), dim3(kBlock), params, 0, st),
+        EZ_CUDA(cudaLaunchCooperativeKernel((void*)lm_large_kernel, dim3(L->grid), dim3(kBlock), params, kLmDynamicSmem, st),
                 "cudaLaunchCooperativeKernel(lm_large_kernel)");
     }
     ctx->launches += 1;
@@ -693,6 +1164,23 @@ int32_t solve_large(ezpz_context* ctx, const ezpz_structure* s, const ezpz_confi
     if (io->jacobian)
         EZ_CUDA(cudaMemcpyAsync(io->jacobian, L->vg + a.J0, sizeof(double) * a.nnz, cudaMemcpyDeviceToHost, st), "D2H jacobian");
     EZ_CUDA(cudaStreamSynchronize(st), "cudaStreamSynchronize");
+    const char* dbg = std::getenv("EZPZ_B200_DEBUG");
+    if (dbg && dbg[0] == '1' && dbg[1] == '2' && a.lvl_ns) {
+        std::vector<unsigned long long> t(2 * (size_t)a.n_levels);
+        cudaMemcpy(t.data(), a.lvl_ns, sizeof(unsigned long long) * t.size(), cudaMemcpyDeviceToHost);
+        const LargeProgram& P = s->large;
+        for (uint32_t l = 0; l < a.solo_level; ++l)
+            std::fprintf(stderr, "  level %3u cols %7u entries %8u maxrow %4u  factor %8.1f us  backward %8.1f us (all iterations)\n", l,
+                         P.lvl_ptr[l + 1] - P.lvl_ptr[l], P.ent_ptr[P.lvl_ptr[l + 1]] - P.ent_ptr[P.lvl_ptr[l]], P.lvl_maxrow[l],
+                         t[2 * l] * 1e-3, t[2 * l + 1] * 1e-3);
+        cudaMemset(a.lvl_ns, 0, sizeof(unsigned long long) * t.size());
+    }
+    if (dbg && dbg[0] == '1')
+        std::fprintf(stderr,
+                     "[lm_large_kernel] grid %d x %u  it %u  us: eval %.1f  sums/max %.1f  A+rhs %.1f  factor(grid) %.1f  "
+                     "top-of-tree(1 CTA) %.1f  backward(grid) %.1f  pcg %.1f  total %.1f\n",
+                     L->grid, kBlock, h.iterations, h.t[0] * 1e-3, h.t[1] * 1e-3, h.t[2] * 1e-3, h.t[3] * 1e-3, h.t[4] * 1e-3,
+                     h.t[5] * 1e-3, h.t[6] * 1e-3, h.t[7] * 1e-3);
     *io->iterations = h.iterations;
     *io->status = (uint8_t)((h.converged ? EZPZ_ST_CONVERGED : 0u) | (h.any_unsat ? EZPZ_ST_UNSATISFIED : 0u) |
                             (h.any_degen ? EZPZ_ST_DEGENERATE : 0u));

@@ -236,12 +236,8 @@ void build_small_program(ezpz_structure& S) {
 }
 
 
-// Level-scheduled direct programme for single large systems.  Same op sequence as the small tape, 32-bit
-// slots, and a level per op: an op runs one level after the last writer of anything it reads and after the
-// last reader of what it overwrites.
-constexpr uint32_t kMaxDirectLevels = 4096;   // beyond this dependency depth the PCG path is used
-constexpr uint64_t kMaxDirectPairs = 1ull << 28;
-
+// Programme of the single-large-system path: assembly processing order, value-array layout, and the sparse
+// direct schedule (sparse_direct.cpp).
 void build_large_program(ezpz_structure& S) {
     LargeProgram& P = S.large;
     P = LargeProgram();
@@ -270,158 +266,24 @@ void build_large_program(ezpz_structure& S) {
             while (P.cons_order.size() % 32) P.cons_order.push_back(UINT32_MAX);
         }
     }
-    const uint32_t nnz_l = S.have_l_pattern ? (uint32_t)S.l_row_idx.size() : 0;
+    build_sparse_direct(S);
+    const uint64_t nnz_l = P.direct ? P.nnz_l : 0;
+    const uint64_t total = (uint64_t)n + 2ull * m + nnz_j + nnz_l + 4ull * n;
+    if (total >= 0xfffffff0ull) {  // 32-bit slots: fall back to the PCG path
+        P.direct = false;
+        P.nnz_l = 0;
+    }
     P.X0 = 0;
     P.R0 = n;
     P.RN0 = P.R0 + m;
     P.J0 = P.RN0 + m;
     P.L0 = P.J0 + nnz_j;
-    P.D0 = P.L0 + nnz_l;
-    P.VG = P.D0 + n;
+    P.DG0 = P.L0 + (P.direct ? P.nnz_l : 0);
+    P.RV0 = P.DG0 + n;
+    P.Y0 = P.RV0 + n;
+    P.D0 = P.Y0 + n;
+    P.VG = (uint64_t)P.D0 + n;
     P.built = true;
-    if (!S.have_l_pattern) return;
-    struct RowEnt {
-        uint32_t col, slot;
-    };
-    std::vector<std::vector<RowEnt>> lrow(n);
-    std::vector<uint32_t> diag_slot(n);
-    for (uint32_t j = 0; j < n; ++j) {
-        diag_slot[j] = P.L0 + S.l_col_ptr[j];
-        for (uint32_t p = S.l_col_ptr[j] + 1; p < S.l_col_ptr[j + 1]; ++p) lrow[S.l_row_idx[p]].push_back({j, P.L0 + p});
-    }
-    std::vector<uint32_t> dst, fin, code, ptr{0}, pa, pb;
-    auto begin = [&](uint32_t d, uint32_t c, uint32_t fk, uint32_t f) {
-        dst.push_back(d);
-        fin.push_back(f);
-        code.push_back(c | (fk << OP_FIN_SHIFT));
-        ptr.push_back((uint32_t)pa.size());
-    };
-    auto pair = [&](uint32_t a, uint32_t b) {
-        pa.push_back(a);
-        pb.push_back(b);
-        ptr.back() = (uint32_t)pa.size();
-    };
-    for (uint32_t j = 0; j < n; ++j) {  // (1) A = JtJ + lambda I
-        uint32_t ap = S.a_col_ptr[j];
-        const uint32_t ae = S.a_col_ptr[j + 1];
-        for (uint32_t p = S.l_col_ptr[j]; p < S.l_col_ptr[j + 1]; ++p) {
-            const uint32_t i = S.l_row_idx[p];
-            begin(P.L0 + p, 0u, i == j ? OP_FIN_LAMBDA : OP_FIN_NONE, 0u);
-            while (ap < ae && S.a_row_idx[ap] < i) ++ap;
-            if (ap < ae && S.a_row_idx[ap] == i) {
-                uint32_t pi = S.csc_col_ptr[i], pie = S.csc_col_ptr[i + 1];
-                uint32_t pj = S.csc_col_ptr[j], pje = S.csc_col_ptr[j + 1];
-                while (pi < pie && pj < pje) {
-                    const uint32_t ri = S.csc_row_idx[pi], rj = S.csc_row_idx[pj];
-                    if (ri == rj) {
-                        pair(P.J0 + pi, P.J0 + pj);
-                        ++pi;
-                        ++pj;
-                    } else if (ri < rj) ++pi;
-                    else ++pj;
-                }
-            }
-        }
-    }
-    for (uint32_t j = 0; j < n; ++j) {  // (2) b = -Jt r
-        begin(P.D0 + j, OP_NEGATE, OP_FIN_NONE, 0u);
-        for (uint32_t p = S.csc_col_ptr[j]; p < S.csc_col_ptr[j + 1]; ++p) pair(P.J0 + p, P.R0 + S.csc_row_idx[p]);
-    }
-    for (uint32_t j = 0; j < n; ++j) {  // (3) Cholesky
-        begin(diag_slot[j], OP_INIT_DST | OP_NEGATE, OP_FIN_PIVOT, 0u);
-        for (const RowEnt& e : lrow[j]) pair(e.slot, e.slot);
-        for (uint32_t p = S.l_col_ptr[j] + 1; p < S.l_col_ptr[j + 1]; ++p) {
-            const uint32_t i = S.l_row_idx[p];
-            begin(P.L0 + p, OP_INIT_DST | OP_NEGATE, OP_FIN_MUL, diag_slot[j]);
-            const auto& ri = lrow[i];
-            const auto& rj = lrow[j];
-            size_t a = 0, b = 0;
-            while (a < ri.size() && b < rj.size() && ri[a].col < j && rj[b].col < j) {
-                if (ri[a].col == rj[b].col) {
-                    pair(ri[a].slot, rj[b].slot);
-                    ++a;
-                    ++b;
-                } else if (ri[a].col < rj[b].col) ++a;
-                else ++b;
-            }
-            if (pa.size() > kMaxDirectPairs) return;
-        }
-    }
-    for (uint32_t i = 0; i < n; ++i) {  // (4) forward
-        begin(P.D0 + i, OP_INIT_DST | OP_NEGATE, OP_FIN_MUL, diag_slot[i]);
-        for (const RowEnt& e : lrow[i]) pair(e.slot, P.D0 + e.col);
-    }
-    for (uint32_t ii = n; ii-- > 0;) {  // (5) backward
-        begin(P.D0 + ii, OP_INIT_DST | OP_NEGATE, OP_FIN_MUL, diag_slot[ii]);
-        for (uint32_t p = S.l_col_ptr[ii] + 1; p < S.l_col_ptr[ii + 1]; ++p) pair(P.L0 + p, P.D0 + S.l_row_idx[p]);
-    }
-    // levels
-    const uint32_t n_ops = (uint32_t)dst.size();
-    std::vector<uint32_t> wlev(P.VG, 0), rlev(P.VG, 0), lev(n_ops);
-    uint32_t max_level = 0;
-    for (uint32_t o = 0; o < n_ops; ++o) {
-        uint32_t l = std::max(wlev[dst[o]], rlev[dst[o]]);
-        const uint32_t fk = (code[o] >> OP_FIN_SHIFT) & 3u;
-        if (fk == OP_FIN_MUL) l = std::max(l, wlev[fin[o]]);
-        for (uint32_t q = ptr[o]; q < ptr[o + 1]; ++q) l = std::max(l, std::max(wlev[pa[q]], wlev[pb[q]]));
-        l += 1;
-        lev[o] = l;
-        max_level = std::max(max_level, l);
-        if (fk == OP_FIN_MUL) rlev[fin[o]] = std::max(rlev[fin[o]], l);
-        for (uint32_t q = ptr[o]; q < ptr[o + 1]; ++q) {
-            rlev[pa[q]] = std::max(rlev[pa[q]], l);
-            rlev[pb[q]] = std::max(rlev[pb[q]], l);
-        }
-        wlev[dst[o]] = l;
-    }
-    // EZPZ_B200_FORCE_PCG=1 sends every large system down the PCG path (tests and benchmarks use it to
-    // exercise that path on systems small enough for the oracle to check quickly).
-    const char* force = std::getenv("EZPZ_B200_FORCE_PCG");
-    if (max_level > kMaxDirectLevels || (force && force[0] == '1')) return;
-    // counting sort of ops by level (stable: keeps tape order inside a level)
-    P.level_ptr.assign(max_level + 1, 0);
-    for (uint32_t o = 0; o < n_ops; ++o) P.level_ptr[lev[o]]++;  // level l in [1, max_level] -> bucket l
-    {
-        uint32_t run = 0;
-        for (uint32_t l = 0; l <= max_level; ++l) {
-            const uint32_t c = P.level_ptr[l];
-            P.level_ptr[l] = run;
-            run += c;
-        }
-    }
-    // level_ptr[l] = start of level l (1-based); shift so that level index is 0-based with n_levels+1 entries
-    std::vector<uint32_t> start(P.level_ptr.begin() + 1, P.level_ptr.end());
-    start.push_back(n_ops);
-    std::vector<uint32_t> cursor(start.begin(), start.end() - 1);
-    P.op_dst.resize(n_ops);
-    P.op_fin.resize(n_ops);
-    P.op_code.resize(n_ops);
-    P.op_ptr.assign(n_ops + 1, 0);
-    P.pair_a.resize(pa.size());
-    P.pair_b.resize(pb.size());
-    std::vector<uint32_t> where(n_ops);
-    for (uint32_t o = 0; o < n_ops; ++o) where[o] = cursor[lev[o] - 1]++;
-    std::vector<uint32_t> inv(n_ops);
-    for (uint32_t o = 0; o < n_ops; ++o) inv[where[o]] = o;
-    uint32_t run = 0;
-    for (uint32_t k = 0; k < n_ops; ++k) {
-        const uint32_t o = inv[k];
-        P.op_dst[k] = dst[o];
-        P.op_fin[k] = fin[o];
-        P.op_code[k] = code[o];
-        P.op_ptr[k] = run;
-        for (uint32_t q = ptr[o]; q < ptr[o + 1]; ++q) {
-            P.pair_a[run] = pa[q];
-            P.pair_b[run] = pb[q];
-            ++run;
-        }
-    }
-    P.op_ptr[n_ops] = run;
-    P.level_ptr = start;
-    P.n_levels = max_level;
-    P.n_ops = n_ops;
-    P.n_pairs = run;
-    P.direct = true;
 }
 
 }  // namespace
@@ -615,6 +477,21 @@ int32_t ezpz_b200_structure_pattern_a(const ezpz_structure_t* s, const uint32_t*
     if (a_row_idx) *a_row_idx = s->a_row_idx.data();
     if (l_col_ptr) *l_col_ptr = s->l_col_ptr.data();
     if (l_row_idx) *l_row_idx = s->l_row_idx.data();
+    return EZPZ_OK;
+}
+
+int32_t ezpz_b200_structure_ordering(const ezpz_structure_t* s, int32_t* path, const uint32_t** elim_order,
+                                     int32_t* nested, uint32_t* n_levels, uint64_t* nnz_l, uint32_t* sum_chunk) {
+    if (!s) return EZPZ_ERR_INVALID_ARGUMENT;
+    const LargeProgram& P = s->large;
+    const bool direct = P.built && P.direct;
+    if (path) *path = !P.built ? 0 : (P.direct ? 1 : 2);
+    if (elim_order) *elim_order = direct ? P.perm.data() : nullptr;
+    if (nested) *nested = direct && P.nested ? 1 : 0;
+    if (n_levels) *n_levels = direct ? P.n_levels : 0;
+    if (nnz_l) *nnz_l = direct ? P.nnz_l : 0;
+    // large.cu: single-CTA systems (n + m + nnz <= 65,536) fold sequentially, larger ones in chunks of 1,024
+    if (sum_chunk) *sum_chunk = (P.built && (size_t)s->n + s->m + s->csc_row_idx.size() > 65536) ? 1024u : 0u;
     return EZPZ_OK;
 }
 

@@ -47,21 +47,40 @@ struct SmallProgram {
     std::vector<uint32_t> tape;
 };
 
-// The single-large-system programme (large.cu): the processing order of the assembly phase and,
-// when the dependency depth of the natural-order sparse Cholesky is small (e.g. block-diagonal systems),
-// the level-scheduled op list of the direct solve.  Slots index one global value array
-// VG = [x | r | r_next | J (CSC order) | A/L | d].
+// The single-large-system programme (large.cu): the processing order of the assembly phase and, unless the
+// factor would be too large, the level-scheduled sparse direct solve built by sparse_direct.cpp.  Slots index
+// one global value array  VG = [x | r | r_next | J (CSC order) | L (by rows) | diag(A) | 1/pivot | y | d].
+constexpr uint32_t kEntryInA = 0x80000000u;  // ent_slot flag: A = JtJ itself has this entry (else pure fill)
+
 struct LargeProgram {
     bool built = false;
-    bool direct = false;          // level-scheduled direct solve available
-    uint32_t X0 = 0, R0 = 0, RN0 = 0, J0 = 0, L0 = 0, D0 = 0, VG = 0;
-    uint32_t n_levels = 0, n_ops = 0;
-    uint64_t n_pairs = 0;
+    bool direct = false;          // sparse direct solve available (otherwise the PCG path runs)
+    bool nested = false;          // perm is a nested-dissection order (false: natural order 0..n-1)
+    uint32_t X0 = 0, R0 = 0, RN0 = 0, J0 = 0, L0 = 0, DG0 = 0, RV0 = 0, Y0 = 0, D0 = 0;
+    uint64_t VG = 0;
+    uint32_t n_levels = 0, solo_level = 0, nnz_l = 0;
     std::vector<uint32_t> cons_order;                      // processing slots of the assembly phase -> constraint
                                                            // index (tile-local kind sort, UINT32_MAX = padding)
-    std::vector<uint32_t> level_ptr;                       // n_levels + 1, ranges into the op arrays
-    std::vector<uint32_t> op_dst, op_fin, op_code, op_ptr; // op_ptr: n_ops + 1, ranges into the pair arrays
-    std::vector<uint32_t> pair_a, pair_b;
+    std::vector<uint32_t> perm;                            // elimination position -> variable
+    std::vector<uint32_t> lr_ptr, lr_col;                  // strictly-lower L by rows, columns ascending; the value
+                                                           // of entry e lives at VG[L0 + e]
+    std::vector<uint32_t> lvl_ptr;                         // n_levels + 1: ranges of lvl_cols (etree height levels)
+    std::vector<uint32_t> lvl_cols;                        // columns ordered by (level, index)
+    std::vector<uint32_t> lvl_maxrow;                      // longest row of L among each level's columns
+    std::vector<uint32_t> ent_ptr;                         // n + 1, by POSITION in lvl_cols: ranges of ent_*
+    std::vector<uint32_t> ent_row, ent_col, ent_slot;      // sub-diagonal entries of each column, rows ascending;
+                                                           // ent_slot = position in row order | kEntryInA
+    // Static row intersections: for entry e = (i, j), bit t of the first ceil(len_j / 32) words at
+    // ent_mask[ent_mask_ptr[e]] says that column lr_col[lr_ptr[j] + t] of row j is also in row i; the following
+    // ceil(pre_i / 32) words mark the matching positions of row i's prefix (pre_i = entries of row i left of j).
+    // The q-th set bits of the two masks pair up, so the factorisation never compares column indices.
+    std::vector<uint32_t> ent_mask_ptr;                    // nnz_l + 1
+    std::vector<uint32_t> ent_mask;
+    // A = JtJ: for every L entry flagged kEntryInA (in ent_* order), the products J[r][i] * J[r][j] over shared rows
+    // r ascending, as pairs of positions in the CSC value array of J.
+    std::vector<uint32_t> aent;                            // indices into ent_* of the entries A has
+    std::vector<uint32_t> aprod_ptr;                       // aent.size() + 1
+    std::vector<uint32_t> aprod_a, aprod_b;
 };
 
 struct DeviceCopy;  // defined in device.h
@@ -94,4 +113,6 @@ struct ezpz_structure {
 namespace ezs {
 // Implemented in device.cu; called by ezpz_b200_structure_destroy.
 void release_device_copies(ezpz_structure* s);
+// sparse_direct.cpp: ordering, symbolic factorisation and level schedule of the large-system direct solve.
+void build_sparse_direct(ezpz_structure& S);
 }  // namespace ezs

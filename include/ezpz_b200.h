@@ -277,9 +277,22 @@ int32_t ezpz_b200_solve_one(ezpz_context_t* ctx, const ezpz_structure_t* s,
                             const ezpz_config_t* config, const ezpz_one_io_t* io,
                             ezpz_error_detail_t* detail);
 
+/* How a structure that takes the large path solves its damped step (replaces what faer's
+ * SymbolicLlt::try_new decides inside precompute_symbolic_cholesky, solver.rs:289-300):
+ *   *path        0 = batched-small kernel (no large programme), 1 = sparse direct, 2 = PCG
+ *   *elim_order  [n] elimination position -> variable (NULL unless path 1); natural order 0..n-1 or
+ *                nested dissection (*nested != 0)
+ *   *n_levels    height of the elimination tree = number of parallel factorisation phases
+ *   *nnz_l       strictly-lower entries of the factor
+ *   *sum_chunk   rows per chunk of the sum-of-squares fold on this structure (0 = one sequential fold)
+ * The arithmetic is the oracle's applied to P A Pt; parity tests hand `elim_order` and `sum_chunk` to the oracle. */
+int32_t ezpz_b200_structure_ordering(const ezpz_structure_t* s, int32_t* path, const uint32_t** elim_order,
+                                     int32_t* nested, uint32_t* n_levels, uint64_t* nnz_l,
+                                     uint32_t* sum_chunk);
+
 /* Stand-alone timing of the large-system kernels on a structure's device buffers (CUDA events, `reps`
- * launches): which = 0 fused assembly (residual + Jacobian + scatter), 1 SpMV y = J p (CSR), 2 SpMV
- * z = Jt q (CSC).  Returns mean microseconds per launch and the algorithmic bytes one launch moves
+ * launches): which = 0 fused assembly (residual + Jacobian + scatter into CSC order), 1 SpMV y = J p (CSR),
+ * 2 SpMV z = Jt q (CSC), 3 the assembly that also writes the CSR-ordered copy (PCG path).  Returns mean microseconds per launch and the algorithmic bytes one launch moves
  * (SURVEY.md §8d).  Only for structures that take the large path. */
 int32_t ezpz_b200_large_bench(ezpz_context_t* ctx, const ezpz_structure_t* s, const double* x,
                               int32_t which, int32_t reps, double* mean_us, double* algorithmic_bytes,

@@ -29,6 +29,12 @@
 //   y, d    = forward / backward substitution with the same fma(-l, v, acc) pattern, k ascending,
 //             finished by acc * rinv[i];
 //   S       = sum r_i^2 as acc = acc + r_i*r_i (two roundings each, as Rust's .map(|x| x*x).sum()).
+// Two OPTIONAL knobs exist only so that the large-system CUDA path can be checked bit for bit (the defaults are
+// the reference-faithful natural order and sequential sum; tests compare both ways):
+//   elim_order  an elimination order for the Cholesky (faer picks its own fill-reducing order, which is
+//               unknowable here): the formulas above are applied to P A Pt, d is scattered back;
+//   sum_chunk   S folded sequentially inside chunks of that many rows, then the chunk sums folded
+//               sequentially (the GPU cannot afford a 1M-long dependent chain per evaluation).
 // Constraint residuals and partials are evaluated without any contraction (Rust semantics).
 #include <algorithm>
 #include <atomic>
@@ -142,6 +148,39 @@ static int32_t build_pattern(const Rec* cons, uint32_t n_cons, uint32_t n_vars, 
         fill[r]++;
     }
     return OK;
+}
+
+// Pattern of J*P (column j of the result = column perm[j] of J) and, for each of its CSC value positions, the
+// position of the same entry in J's CSC value array.
+static void permute_pattern(const Pattern& P, const std::vector<uint32_t>& perm, Pattern& Q, std::vector<uint32_t>& jmap) {
+    const uint32_t n = P.n;
+    Q.m = P.m;
+    Q.n = n;
+    Q.cons_row0 = P.cons_row0;
+    Q.csc_col_ptr.assign(n + 1, 0);
+    Q.csc_row_idx.clear();
+    jmap.clear();
+    for (uint32_t j = 0; j < n; ++j) {
+        for (uint32_t e = P.csc_col_ptr[perm[j]]; e < P.csc_col_ptr[perm[j] + 1]; ++e) {
+            Q.csc_row_idx.push_back(P.csc_row_idx[e]);
+            jmap.push_back(e);
+        }
+        Q.csc_col_ptr[j + 1] = (uint32_t)Q.csc_row_idx.size();
+    }
+    const size_t nnz = Q.csc_row_idx.size();
+    Q.csr_row_ptr.assign(Q.m + 1, 0);
+    for (size_t k = 0; k < nnz; ++k) Q.csr_row_ptr[Q.csc_row_idx[k] + 1]++;
+    for (uint32_t r = 0; r < Q.m; ++r) Q.csr_row_ptr[r + 1] += Q.csr_row_ptr[r];
+    Q.csr_col_idx.resize(nnz);
+    Q.csr_to_csc.resize(nnz);
+    std::vector<uint32_t> fill(Q.csr_row_ptr.begin(), Q.csr_row_ptr.end() - 1);
+    for (uint32_t j = 0; j < n; ++j)
+        for (uint32_t k = Q.csc_col_ptr[j]; k < Q.csc_col_ptr[j + 1]; ++k) {
+            const uint32_t r = Q.csc_row_idx[k];
+            Q.csr_col_idx[fill[r]] = j;
+            Q.csr_to_csc[fill[r]] = k;
+            fill[r]++;
+        }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -332,6 +371,39 @@ struct Model {
     std::vector<double> jvals;          // CSC order
     std::vector<uint32_t> degen_count;  // per constraint: number of Warning::Degenerate pushed
     JRow row0, row1;
+    // optional knobs (see the header): elimination order and chunked sum of squares
+    std::vector<uint32_t> perm;
+    uint32_t sum_chunk = 0;
+    Pattern Pp;
+    std::vector<uint32_t> jmap;
+    std::vector<double> jp, dp;
+
+    void analyse() {
+        if (perm.empty()) {
+            chol.analyse(P);
+            return;
+        }
+        permute_pattern(P, perm, Pp, jmap);
+        chol.analyse(Pp);
+        jp.assign(jmap.size(), 0.0);
+        dp.assign(P.n, 0.0);
+    }
+
+    double sum_squares(const std::vector<double>& r) const {
+        const uint32_t m = (uint32_t)r.size();
+        if (sum_chunk == 0) {
+            double acc = 0.0;
+            for (uint32_t i = 0; i < m; ++i) acc = acc + r[i] * r[i];
+            return acc;
+        }
+        double total = 0.0;
+        for (uint32_t b = 0; b < m; b += sum_chunk) {
+            double acc = 0.0;
+            for (uint32_t i = b; i < std::min(m, b + sum_chunk); ++i) acc = acc + r[i] * r[i];
+            total = total + acc;
+        }
+        return total;
+    }
 
     Rec effective(uint32_t ci) const {
         Rec c = cons[ci];
@@ -387,8 +459,7 @@ struct Model {
         double lambda = cfg.initial_lambda;
         residual(x, r.data());
         refresh_jacobian(x);
-        double residual_sq = 0.0;
-        for (uint32_t i = 0; i < m; ++i) residual_sq = residual_sq + r[i] * r[i];
+        double residual_sq = sum_squares(r);
         for (uint64_t it = 0; it < cfg.max_iterations; ++it) {
             if (m == 0) return E_EMPTY;
             double largest = std::fabs(r[0]);
@@ -398,7 +469,11 @@ struct Model {
                 *converged = true;
                 return OK;
             }
-            chol.assemble(jvals, lambda);
+            if (perm.empty()) chol.assemble(jvals, lambda);
+            else {
+                for (size_t k = 0; k < jmap.size(); ++k) jp[k] = jvals[jmap[k]];
+                chol.assemble(jp, lambda);
+            }
             for (uint32_t j = 0; j < n; ++j) {  // b = Jt * (-r)
                 double acc = 0.0;
                 for (uint32_t e = P.csc_col_ptr[j]; e < P.csc_col_ptr[j + 1]; ++e)
@@ -410,7 +485,12 @@ struct Model {
                 lambda *= 10.0;
                 continue;
             }
-            chol.solve(d);
+            if (perm.empty()) chol.solve(d);
+            else {
+                for (uint32_t j = 0; j < n; ++j) dp[j] = d[perm[j]];
+                chol.solve(dp);
+                for (uint32_t j = 0; j < n; ++j) d[perm[j]] = dp[j];
+            }
             double step = 0.0;  // unwrap_or(0.0) for n == 0
             if (n > 0) {
                 step = std::fabs(d[0]);
@@ -418,8 +498,7 @@ struct Model {
             }
             for (uint32_t j = 0; j < n; ++j) x[j] += d[j];
             residual(x, rn.data());
-            double next_sq = 0.0;
-            for (uint32_t i = 0; i < m; ++i) next_sq = next_sq + rn[i] * rn[i];
+            double next_sq = sum_squares(rn);
             if (trace) { trace->push_back(lambda); trace->push_back(residual_sq); trace->push_back(next_sq); trace->push_back(step); }
             if (next_sq < residual_sq) {
                 r.swap(rn);
@@ -560,7 +639,8 @@ struct Outcome {
 static int32_t solve_inner(const Rec* cons, const uint64_t* cons_ids, const uint32_t* prios, uint32_t n_cons,
                            const uint32_t* var_ids, const double* guesses, uint32_t n_vars,
                            const double* param_override, const Cfg& cfg, bool analysis, Outcome& out,
-                           ErrDetail* det, std::vector<double>* trace) {
+                           ErrDetail* det, std::vector<double>* trace, const uint32_t* elim_order = nullptr,
+                           uint32_t sum_chunk = 0) {
     out.num_vars = n_vars;
     out.num_eqs = 0;
     for (uint32_t ci = 0; ci < n_cons; ++ci) out.num_eqs += residual_dim(cons[ci]);
@@ -574,7 +654,9 @@ static int32_t solve_inner(const Rec* cons, const uint64_t* cons_ids, const uint
     if (rc != OK) return rc;
     M.jvals.assign(M.P.csc_row_idx.size(), 0.0);
     M.degen_count.assign(n_cons, 0);
-    M.chol.analyse(M.P);
+    if (elim_order) M.perm.assign(elim_order, elim_order + n_vars);
+    M.sum_chunk = sum_chunk;
+    M.analyse();
     out.final_values.assign(guesses, guesses + n_vars);
     rc = M.solve_lm(out.final_values.data(), cfg, &out.iterations, &out.converged, trace);
     if (rc != OK) return rc;
@@ -742,6 +824,35 @@ int32_t orc_solve_inner(const orc::Rec* cons, uint32_t n_cons, const double* gue
         std::memcpy(trace, tr.data(), k * sizeof(double));
         *trace_len = k;
     }
+    return rc;
+}
+
+// orc_solve_inner with the two optional large-system knobs (see the header comment): an elimination order
+// (a permutation of 0..n_vars-1, or NULL = natural) and the chunk length of the sum-of-squares fold (0 = one
+// sequential fold).
+int32_t orc_solve_inner_ordered(const orc::Rec* cons, uint32_t n_cons, const double* guesses, uint32_t n_vars,
+                                const orc::Cfg* cfg, int32_t resolve_sides, const uint32_t* elim_order,
+                                uint32_t sum_chunk, orc_outcome_t* out) {
+    std::vector<orc::Rec> c(cons, cons + n_cons);
+    if (resolve_sides) {
+        for (orc::Rec& r : c) {
+            bool ok = true;
+            for (int k = 0; k < 8; ++k) ok = ok && r.ids[k] < n_vars;
+            if (ok) orc::set_from_initial_values(r, guesses);
+        }
+    }
+    if (elim_order) {
+        std::vector<uint8_t> seen(n_vars, 0);
+        for (uint32_t j = 0; j < n_vars; ++j) {
+            if (elim_order[j] >= n_vars || seen[elim_order[j]]) return orc::E_INVALID;
+            seen[elim_order[j]] = 1;
+        }
+    }
+    orc::Outcome o;
+    orc::ErrDetail det;
+    int32_t rc = orc::solve_inner(c.data(), nullptr, nullptr, n_cons, nullptr, guesses, n_vars, nullptr, *cfg, false, o,
+                                  &det, nullptr, elim_order, sum_chunk);
+    export_outcome(o, det, n_cons, out);
     return rc;
 }
 

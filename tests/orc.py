@@ -162,6 +162,23 @@ def solve_inner(recs, guesses, params=None, cfg=None, analysis=False, resolve_si
     return r
 
 
+def solve_inner_ordered(recs, guesses, elim_order=None, sum_chunk=0, cfg=None, resolve_sides=True):
+    """solve_inner with the two large-system knobs of the oracle: an elimination order for the Cholesky and the
+    chunk length of the sum-of-squares fold (what Structure.ordering() reports for the CUDA large path)."""
+    L = lib()
+    recs = as_recs(recs)
+    n_cons = len(recs)
+    g = np.ascontiguousarray(guesses, dtype=np.float64)
+    n_vars = len(g)
+    cfg = cfg or default_cfg()
+    eo = None if elim_order is None else np.ascontiguousarray(elim_order, dtype=np.uint32)
+    o, fv, un, dg, uc = _mk_outcome(n_cons, n_vars)
+    rc = L.orc_solve_inner_ordered(recs.ctypes.data_as(C.c_void_p), C.c_uint32(n_cons), _p(g, C.c_double),
+                                   C.c_uint32(n_vars), C.byref(cfg), C.c_int32(1 if resolve_sides else 0),
+                                   _p(eo, C.c_uint32), C.c_uint32(int(sum_chunk)), C.byref(o))
+    return _result(rc, o, fv, un, dg, uc, n_cons, n_vars)
+
+
 def pattern(recs, n_vars):
     L = lib()
     recs = as_recs(recs)

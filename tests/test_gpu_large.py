@@ -29,15 +29,42 @@ def test_massive_parallel_system_direct_path(ctx, lines, over):
         assert np.abs(out.final_values[4 * k:4 * k + 4] - [k, 0, k, 4]).max() < 1e-6
 
 
-def test_chain_sketch_direct_path_bitwise(ctx):
-    recs, n, g, exact = wl.chain_sketch(64)
+def _check_direct(ctx, cells):
+    """Sparse direct path: bit-exact against the oracle run with the same elimination order and sum-of-squares
+    chunking (Structure.ordering()), and within the north-star tolerance (identical iteration count and verdict,
+    1e-9 on coordinates) of the reference-faithful oracle (natural order, sequential sum)."""
+    recs, n, g, exact = wl.chain_sketch(cells)
     st = ez.Structure(recs, n)
-    out = ctx.solve_one(st, g, want_jacobian=True)
+    od = st.ordering()
+    assert od["path"] == 1 and sorted(od["elim_order"].tolist()) == list(range(n))
+    out = ctx.solve_one(st, g)
     assert out.path_used == 1
-    o = orc.solve_inner(recs, g)
+    o = orc.solve_inner_ordered(recs, g, od["elim_order"], od["sum_chunk"])
     assert out.iterations == o.iterations and out.converged == o.converged and out.unsatisfied == o.unsatisfied
     assert_bitwise(out.final_values, o.final_values, "final values")
+    ref = orc.solve_inner(recs, g)
+    assert out.iterations == ref.iterations and out.converged == ref.converged and out.unsatisfied == ref.unsatisfied
+    scale = np.maximum(1.0, np.abs(ref.final_values))
+    assert (np.abs(out.final_values - ref.final_values) <= 1e-9 * scale).all()
     assert np.abs(out.final_values - exact).max() < 1e-6
+    return od
+
+
+def test_chain_sketch_direct_single_cta(ctx):
+    od = _check_direct(ctx, 64)  # 832 variables: one CTA, nested-dissection order, sequential sum of squares
+    assert od["nested"] and od["sum_chunk"] == 0
+
+
+@pytest.mark.parametrize("cells", [1024, 8192])
+def test_chain_sketch_direct_grid(ctx, cells):
+    od = _check_direct(ctx, cells)  # cooperative grid, levels run grid-wide then by one CTA
+    assert od["nested"] and od["sum_chunk"] == 1024
+
+
+def test_chain_sketch_1m_variables(ctx):
+    """BASELINE.json config 4: the synthetic 1,001,000-variable sketch (arcs, circle tangents, distances, angles)."""
+    od = _check_direct(ctx, 77000)
+    assert od["n_levels"] < 1024
 
 
 def test_chain_sketch_pcg_path(ctx):
