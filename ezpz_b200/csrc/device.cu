@@ -836,6 +836,15 @@ int32_t ezpz_b200_eval(ezpz_context_t* ctx, const ezpz_structure_t* s, const dou
     uint8_t* d_d = (uint8_t*)w;
     cudaStream_t st = ctx->stream;
     EZ_CUDA(cudaMemcpyAsync(d_x, x, n * 8, cudaMemcpyHostToDevice, st), "H2D x");
+    // Structures that take the large path are evaluated by that path's own assembly kernel; the generic kernel
+    // below then only supplies what that kernel does not keep (the CSR permutation, the two degenerate bits).
+    bool large_done = false, large_csr = false;
+    if (s->large.built) {
+        rc = ezs::eval_large(ctx, s, x, r, jac_csc, jac_csr, &large_csr, detail);
+        if (rc != EZPZ_OK) return rc;
+        large_done = true;
+        if (!degen && (!jac_csr || large_csr)) return EZPZ_OK;
+    }
     AsmArgs a;
     a.cons = dc->cons;
     a.x = d_x;
@@ -847,9 +856,9 @@ int32_t ezpz_b200_eval(ezpz_context_t* ctx, const ezpz_structure_t* s, const dou
     assemble_kernel<true><<<grid, T, 0, st>>>(a);
     ctx->launches += 1;
     EZ_CUDA(cudaGetLastError(), "assemble_kernel launch");
-    if (r) EZ_CUDA(cudaMemcpyAsync(r, d_r, m * 8, cudaMemcpyDeviceToHost, st), "D2H r");
-    if (jac_csc) EZ_CUDA(cudaMemcpyAsync(jac_csc, d_j, nnz * 8, cudaMemcpyDeviceToHost, st), "D2H jac");
-    if (jac_csr && nnz) {
+    if (r && !large_done) EZ_CUDA(cudaMemcpyAsync(r, d_r, m * 8, cudaMemcpyDeviceToHost, st), "D2H r");
+    if (jac_csc && !large_done) EZ_CUDA(cudaMemcpyAsync(jac_csc, d_j, nnz * 8, cudaMemcpyDeviceToHost, st), "D2H jac");
+    if (jac_csr && nnz && !(large_done && large_csr)) {
         permute_kernel<<<(unsigned)((nnz + 255) / 256), 256, 0, st>>>(d_j, dc->csc_to_csr, d_j2, (uint32_t)nnz);
         ctx->launches += 1;
         EZ_CUDA(cudaGetLastError(), "permute_kernel launch");

@@ -56,9 +56,21 @@ struct LargeCtrl {
     unsigned long long t[8];
 };
 
+// (record tiles: see the comment above assemble_slot)
+struct KindLayout {  // word offsets inside a record; 0xff = absent
+    uint8_t n_words, ids, p0, p1, weight, slot0, slot1, jr;
+};
+struct TileDesc {
+    uint32_t off16;  // tile start in the record array, in 16-byte units
+    uint32_t meta;   // kind | n_valid << 8
+};
+constexpr uint32_t kMaxRecWords = 1 + 8 + 2 + 2 + 2 + 16 + 3;  // row0, ids, p0, p1, weight, slots, CSR base + 2 offset words
+
 struct LargeArgs {
-    const uint32_t* recs;    // analysed constraints in PROCESSING order (see LargeRec below), word-transposed in
-                             // tiles of 32: word w of slot k at recs[(k / 32) * kRecWords * 32 + w * 32 + k % 32]
+    const uint32_t* recs;      // record tiles, back to back
+    const TileDesc* tiles;     // [n_tiles]
+    const uint32_t* slot_orig; // processing slot -> index in the caller's constraint list (rare paths)
+    KindLayout layout[EZPZ_K_COUNT];
     const uint32_t *csr_row_ptr, *csr_col_idx, *csc_col_ptr, *csc_row_idx, *csc_to_csr;
     // sparse direct path (structure.h: LargeProgram)
     const uint32_t *perm, *lr_ptr, *lr_col, *lvl_ptr, *lvl_cols, *ent_ptr, *ent_row, *ent_col, *ent_slot;
@@ -69,13 +81,14 @@ struct LargeArgs {
     double* partials;    // 3 * gridDim.x
     double* sumsq;       // chunk sums of r^2 (multi-CTA grids)
     unsigned long long* lvl_ns;  // debug (EZPZ_B200_DEBUG=1): per level, ns spent in factor / backward phases, else NULL
-    uint8_t* side;       // resolved side per processing slot
+    uint8_t* side;       // resolved side per processing slot (tangent kinds only)
+    const uint8_t* side_flags;  // the caller's side per processing slot (0 = Undefined: resolved from the guesses)
     uint32_t* degen;     // per-constraint Warning::Degenerate counters
     uint32_t* unsat;     // bit mask
     LargeCtrl* ctrl;
     double residual_tolerance, step_tolerance, initial_lambda, cg_rtol;
     uint32_t max_iterations, cg_max_iters;
-    uint32_t n_cons, n_slots, n, m, nnz, n_levels, solo_level, nnz_l, n_aent;
+    uint32_t n_cons, n_slots, n_tiles, n, m, nnz, n_levels, solo_level, nnz_l, n_aent;
     uint32_t unit_weights;
     uint32_t X0, R0, RN0, J0, L0, DG0, RV0, Y0, D0;
     uint32_t direct;
@@ -91,104 +104,153 @@ struct RegX {
     __device__ __forceinline__ double operator()(uint32_t pos) const { return v[pos]; }
 };
 
-// LargeRec — one analysed constraint of the large path, 36 words.  Slots are laid out in PROCESSING order:
-// tiles of kTile consecutive input constraints, stably sorted by kind inside the tile, every kind group
-// padded to a multiple of 32 slots (kind 0xff = padding).  A warp therefore runs one kind (no divergence in
-// the per-kind switch) while the rows, Jacobian slots and variables a tile touches stay within a few hundred
-// KB, so partial-sector writes of neighbouring kinds merge in L2 before they reach HBM.  Only the words a
-// kind needs are fetched: word w of 32 consecutive slots is one 128-byte line.
-enum : uint32_t {
-    RW_KIND = 0,    // kind | flags << 8
-    RW_ROW0 = 1,    // first residual row
-    RW_ORIG = 2,    // index of the constraint in the caller's list (rare paths: degenerate counters, verdict bits)
-    RW_JR0 = 3,     // position of row0's first entry in the CSR-ordered copy of J
-    RW_JRC0 = 4,    // CSR position of each emitted partial of row 0, 4 bits each, relative to RW_JR0
-    RW_JRC1 = 5,    // ... of row 1
-    RW_IDS = 6,     // 8 variable ids
-    RW_P0 = 14, RW_P1 = 16, RW_WEIGHT = 18,  // doubles (lo, hi)
-    RW_SLOT = 20,   // 2 x 8 CSC scatter slots (bit 31: accumulate)
-    kRecWords = 36
-};
-constexpr uint32_t kPadKind = 0xffu;
-
-struct RecPtr {
-    const uint32_t* base;
-    __device__ __forceinline__ uint32_t w(uint32_t k) const { return __ldg(base + k * 32u); }
-    __device__ __forceinline__ double d(uint32_t k) const { return __hiloint2double((int)w(k + 1), (int)w(k)); }
-};
-__device__ __forceinline__ RecPtr rec_at(const uint32_t* __restrict__ recs, uint32_t k) {
-    return RecPtr{recs + (size_t)(k >> 5) * (kRecWords * 32u) + (k & 31u)};
-}
-__device__ __forceinline__ bool kind_has_p1(uint32_t kind) {
-    return kind == EZPZ_K_LINES_AT_ANGLE || kind == EZPZ_K_ARC_ANGLE || kind == EZPZ_K_POINTS_AT_ANGLE;
+// Record tiles — the analysed constraints as the large path reads them.  Processing order (structure.cpp): tiles
+// of kAssemblyTile consecutive input constraints, stably sorted by kind inside the tile, every kind group padded
+// to whole warps.  One RECORD TILE = 32 consecutive processing slots = ONE kind; it stores only the words that
+// kind needs (KindLayout), word-transposed: word w of slot l at tile[w * 32 + l], so a tile is n_words * 128
+// contiguous bytes.  A warp therefore runs one kind (no divergence in the per-kind switch), reads its tile as one
+// contiguous block — the stand-alone assembly kernel pulls it into shared memory with ONE bulk async copy
+// (cp.async.bulk + mbarrier, three tiles in flight per warp) — and the rows, Jacobian slots and variables a group
+// of neighbouring tiles touches stay within a few hundred KB, so partial-sector writes merge in L2.
+__device__ __forceinline__ double rec_double(const uint32_t* rec, uint32_t word) {
+    return __hiloint2double((int)rec[(word + 1) * 32], (int)rec[word * 32]);
 }
 
-// Assembly of all constraints by the calling thread set (grid-stride), one thread per processing slot.
-//   RES: weighted residuals into vg[rdst + row];  JAC: Jacobian values into J (CSC order, through the
-//   precomputed scatter slots) and, when write_jr, into the CSR-ordered copy used by the row-wise SpMV (the
-//   entries of a constraint's rows are contiguous there, so that copy needs one base and 4-bit offsets).
-template <bool RES, bool JAC>
-__device__ __forceinline__ void assemble_phase_inl(const LargeArgs& a, uint32_t rdst, uint32_t tid, uint32_t nth, bool write_jr) {
-    const double* __restrict__ x = a.vg + a.X0;
-    for (uint32_t k = tid; k < a.n_slots; k += nth) {
-        const RecPtr rec = rec_at(a.recs, k);
-        const uint32_t kind = rec.w(RW_KIND) & 0xffu;
-        if (kind == kPadKind) continue;
-        const uint32_t nids = cl_nids[kind];
-        // Gather the variables BEFORE the per-kind switch: the warp issues its gathers together.
-        double xv[8];
+// One constraint: `rec` points at this lane's column of the tile (global or shared memory), k = processing slot.
+//   RES: weighted residuals into vg[rdst + row];  JAC: Jacobian values into J (CSC order, through the precomputed
+//   scatter slots) and, when write_jr, into the CSR-ordered copy used by the row-wise SpMV (the entries of a
+//   constraint's rows are contiguous there: one base + 4-bit offsets).
+// The (at most 8) variables of one constraint, gathered BEFORE the per-kind switch so that the warp issues its
+// gathers together.  Ids mostly come as the (x, y) pair of a point at (2i, 2i + 1): such a pair is one aligned
+// 16-byte load, which halves the sectors the L1 has to look up.
+__device__ __forceinline__ void gather_x(const LargeArgs& a, const KindLayout ly, uint32_t kind, const uint32_t* rec, double (&xv)[8]) {
+    const double* __restrict__ x = a.vg + a.X0;  // X0 == 0: 16-byte aligned
+    const uint32_t nids = cl_nids[kind];
 #pragma unroll
-        for (uint32_t q = 0; q < 8; ++q) xv[q] = q < nids ? x[rec.w(RW_IDS + q)] : 0.0;
-        const double p0 = rec.d(RW_P0);
-        const double p1 = kind_has_p1(kind) ? rec.d(RW_P1) : 0.0;
-        const double w = a.unit_weights ? 1.0 : rec.d(RW_WEIGHT);
-        const uint32_t row0 = rec.w(RW_ROW0);
-        const uint32_t ident[8] = {0, 1, 2, 3, 4, 5, 6, 7};
-        const RegX XR{xv};
-        ezd::EvalOut o;
-        ezd::eval_constraint<JAC>(kind, a.side[k], ident, p0, p1, XR, o);
-        const uint32_t rows = cl_rows[kind];
-        uint32_t ndeg = 0;
-        if (RES) {
-            a.vg[rdst + row0] = w * o.res[0];
-            if (rows == 2) a.vg[rdst + row0 + 1] = w * o.res[1];
-            if (o.res_degen) ++ndeg;
-        }
-        if (JAC) {
-            if (o.jac_degen) ++ndeg;
-            const uint32_t jr0 = write_jr ? rec.w(RW_JR0) : 0u;
-#pragma unroll
-            for (int row = 0; row < 2; ++row) {
-                if (row < (int)rows) {
-                    const uint32_t len = cl_emit_len[kind][row];
-                    const uint32_t jrc = write_jr ? rec.w(RW_JRC0 + row) : 0u;
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        if (q < (int)len) {
-                            const uint32_t s = rec.w(RW_SLOT + row * 8 + q);
-                            double* dst = a.vg + a.J0 + (s & ~kAccumulate);
-                            double v;
-                            if (s & kAccumulate) v = o.emit[row] ? *dst + w * o.pd[row][q] : *dst;
-                            else v = o.emit[row] ? 0.0 + w * o.pd[row][q] : 0.0;
-                            *dst = v;
-                            if (write_jr) a.jr[jr0 + ((jrc >> (4 * q)) & 15u)] = v;
-                        }
-                    }
+    for (uint32_t q = 0; q < 8; q += 2) {
+        xv[q] = 0.0;
+        xv[q + 1] = 0.0;
+        if (q < nids) {
+            const uint32_t i0 = rec[(ly.ids + q) * 32];
+            if (q + 1 < nids) {
+                const uint32_t i1 = rec[(ly.ids + q + 1) * 32];
+                if (i1 == i0 + 1 && !(i0 & 1u)) {
+                    const double2 v = *reinterpret_cast<const double2*>(x + i0);
+                    xv[q] = v.x;
+                    xv[q + 1] = v.y;
+                } else {
+                    xv[q] = x[i0];
+                    xv[q + 1] = x[i1];
                 }
+            } else {
+                xv[q] = x[i0];
             }
-        }
-        if (ndeg) {
-            a.degen[rec.w(RW_ORIG)] += ndeg;
-            a.ctrl->any_degen = 1;
         }
     }
 }
 
+template <bool RES, bool JAC>
+__device__ __forceinline__ void assemble_slot(const LargeArgs& a, const KindLayout ly, uint32_t kind, const uint32_t* rec, uint32_t k,
+                                              uint32_t rdst, bool write_jr, const double (&xv)[8]) {
+    const double p0 = ly.p0 != 0xff ? rec_double(rec, ly.p0) : 0.0;
+    const double p1 = ly.p1 != 0xff ? rec_double(rec, ly.p1) : 0.0;
+    const double w = ly.weight != 0xff ? rec_double(rec, ly.weight) : 1.0;
+    const uint32_t row0 = rec[0];
+    const uint32_t side = (kind == EZPZ_K_LINE_TANGENT_TO_CIRCLE || kind == EZPZ_K_CIRCLE_TANGENT_TO_CIRCLE) ? a.side[k] : 0u;
+    const uint32_t ident[8] = {0, 1, 2, 3, 4, 5, 6, 7};
+    const RegX XR{xv};
+    ezd::EvalOut o;
+    ezd::eval_constraint<JAC>(kind, side, ident, p0, p1, XR, o);
+    const uint32_t rows = cl_rows[kind];
+    uint32_t ndeg = 0;
+    if (RES) {
+        a.vg[rdst + row0] = w * o.res[0];
+        if (rows == 2) a.vg[rdst + row0 + 1] = w * o.res[1];
+        if (o.res_degen) ++ndeg;
+    }
+    if (JAC) {
+        if (o.jac_degen) ++ndeg;
+        const bool jr_on = write_jr && ly.jr != 0xff;
+        const uint32_t jr0 = jr_on ? rec[ly.jr * 32] : 0u;
+#pragma unroll
+        for (int row = 0; row < 2; ++row) {
+            if (row < (int)rows) {
+                const uint32_t len = cl_emit_len[kind][row];
+                const uint32_t jrc = jr_on ? rec[(ly.jr + 1 + row) * 32] : 0u;
+                const uint32_t sb = row == 0 ? ly.slot0 : ly.slot1;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    if (q < (int)len) {
+                        const uint32_t s = rec[(sb + q) * 32];
+                        double* dst = a.vg + a.J0 + (s & ~kAccumulate);
+                        double v;
+                        if (s & kAccumulate) v = o.emit[row] ? *dst + w * o.pd[row][q] : *dst;
+                        else v = o.emit[row] ? 0.0 + w * o.pd[row][q] : 0.0;
+                        *dst = v;
+                        if (jr_on) a.jr[jr0 + ((jrc >> (4 * q)) & 15u)] = v;
+                    }
+                }
+            }
+        }
+    }
+    if (ndeg) {
+        a.degen[a.slot_orig[k]] += ndeg;
+        a.ctrl->any_degen = 1;
+    }
+}
+
+// All tiles by the calling warps (gw = global warp index of nw), records read straight from global memory.
+template <bool RES, bool JAC>
+__device__ __forceinline__ void assemble_phase_inl(const LargeArgs& a, uint32_t rdst, uint32_t tid, uint32_t nth, bool write_jr) {
+    const uint32_t lane = threadIdx.x & 31u, nw = nth >> 5;
+    for (uint32_t t = tid >> 5; t < a.n_tiles; t += nw) {
+        const TileDesc td = a.tiles[t];
+        const uint32_t kind = td.meta & 0xffu, n_valid = td.meta >> 8;
+        if (lane < n_valid) {
+            const uint32_t* rec = a.recs + (size_t)td.off16 * 4 + lane;
+            double xv[8];
+            gather_x(a, a.layout[kind], kind, rec, xv);
+            assemble_slot<RES, JAC>(a, a.layout[kind], kind, rec, t * 32 + lane, rdst, write_jr, xv);
+        }
+    }
+}
 // Out-of-line copy for the persistent kernel (keeps its register allocation apart from the solver phases).
 template <bool RES, bool JAC>
 __device__ __noinline__ void assemble_phase(const LargeArgs& a, uint32_t rdst, uint32_t tid, uint32_t nth, bool write_jr) {
     assemble_phase_inl<RES, JAC>(a, rdst, tid, nth, write_jr);
 }
+
+// ---- bulk-copy staging (stand-alone assembly kernel) -------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+constexpr uint32_t kAsmStages = 3;
+constexpr uint32_t kAsmWarps = 8;                         // warps per CTA of the stand-alone assembly kernel
+constexpr uint32_t kTileBytesMax = kMaxRecWords * 128;    // 4352
+constexpr size_t kAsmSmem = (size_t)kAsmWarps * kAsmStages * kTileBytesMax + kAsmWarps * kAsmStages * sizeof(uint64_t);
 
 // NaN-ignoring max |v[i]| over the grid: per-block partial to partials[blockIdx.x]; caller syncs, then every
 // thread folds the partials (same order everywhere).
@@ -626,6 +688,31 @@ __device__ void direct_backward_level(const LargeArgs& a, uint32_t lvl, uint32_t
 constexpr uint32_t kBlock = 512;
 constexpr uint32_t kSmDoubles = 4096;  // 32 KB staging
 
+// Constraint::set_from_initial_values (constraints.rs:146-193, called at lib.rs:183-186): only the two tangent
+// kinds carry a side; Undefined ones are resolved from the current x (the initial guesses).
+__device__ void resolve_sides(const LargeArgs& a, uint32_t tid, uint32_t nth) {
+    const GX X{a.vg + a.X0};
+    for (uint32_t t = tid >> 5; t < a.n_tiles; t += nth >> 5) {
+        const TileDesc td = a.tiles[t];
+        const uint32_t kind = td.meta & 0xffu, lane = threadIdx.x & 31u;
+        if ((kind == EZPZ_K_LINE_TANGENT_TO_CIRCLE || kind == EZPZ_K_CIRCLE_TANGENT_TO_CIRCLE) && lane < (td.meta >> 8)) {
+            const uint32_t* rec = a.recs + (size_t)td.off16 * 4 + lane;
+            const KindLayout ly = a.layout[kind];
+            uint32_t side = a.side_flags[t * 32 + lane];  // as given by the caller
+            if (side == EZPZ_SIDE_UNDEFINED) {
+                uint32_t ids[8];
+#pragma unroll
+                for (uint32_t q = 0; q < 8; ++q) ids[q] = q < cl_nids[kind] ? rec[(ly.ids + q) * 32] : 0u;
+                side = ezd::resolve_side(kind, side, ids, X);
+            }
+            a.side[t * 32 + lane] = (uint8_t)side;
+        }
+    }
+}
+__global__ void __launch_bounds__(256) resolve_sides_kernel(const LargeArgs a) {
+    resolve_sides(a, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
+}
+
 __device__ __forceinline__ unsigned long long now_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -662,19 +749,7 @@ __global__ void __launch_bounds__(kBlock) lm_large_kernel(const LargeArgs a) {
 
     // sides from the initial guesses (lib.rs:183-186), counters
     {
-        const GX X{vg + a.X0};
-        for (uint32_t k = tid; k < a.n_slots; k += nth) {
-            const RecPtr rec = rec_at(a.recs, k);
-            const uint32_t kf = rec.w(RW_KIND), kind = kf & 0xffu;
-            uint32_t side = (kf >> 8) & 0xffu;
-            if (side == EZPZ_SIDE_UNDEFINED && (kind == EZPZ_K_LINE_TANGENT_TO_CIRCLE || kind == EZPZ_K_CIRCLE_TANGENT_TO_CIRCLE)) {
-                uint32_t ids[8];
-#pragma unroll
-                for (uint32_t q = 0; q < 8; ++q) ids[q] = rec.w(RW_IDS + q);
-                side = ezd::resolve_side(kind, side, ids, X);
-            }
-            a.side[k] = (uint8_t)side;
-        }
+        resolve_sides(a, tid, nth);
         for (uint32_t c = tid; c < a.n_cons; c += nth) a.degen[c] = 0;
         for (uint32_t w = tid; w < (a.n_cons + 31) / 32; w += nth) a.unsat[w] = 0;
         if (tid == 0) {
@@ -867,23 +942,25 @@ __global__ void __launch_bounds__(kBlock) lm_large_kernel(const LargeArgs a) {
     }
     // post-solve verdict (lib.rs:305-327): unweighted residuals, |r| < 1e-4 per component
     {
-        const double* __restrict__ x = vg + a.X0;
-        for (uint32_t k = tid; k < a.n_slots; k += nth) {
-            const RecPtr rec = rec_at(a.recs, k);
-            const uint32_t kind = rec.w(RW_KIND) & 0xffu;
-            if (kind == kPadKind) continue;
-            const uint32_t nids = cl_nids[kind];
+        for (uint32_t t = tid >> 5; t < a.n_tiles; t += nth >> 5) {
+            const TileDesc td = a.tiles[t];
+            const uint32_t kind = td.meta & 0xffu, lane = threadIdx.x & 31u;
+            if (lane >= (td.meta >> 8)) continue;
+            const uint32_t k = t * 32 + lane;
+            const uint32_t* rec = a.recs + (size_t)td.off16 * 4 + lane;
+            const KindLayout ly = a.layout[kind];
             double xv[8];
-#pragma unroll
-            for (uint32_t q = 0; q < 8; ++q) xv[q] = q < nids ? x[rec.w(RW_IDS + q)] : 0.0;
+            gather_x(a, ly, kind, rec, xv);
             const uint32_t ident[8] = {0, 1, 2, 3, 4, 5, 6, 7};
             const RegX XR{xv};
+            const uint32_t side = (kind == EZPZ_K_LINE_TANGENT_TO_CIRCLE || kind == EZPZ_K_CIRCLE_TANGENT_TO_CIRCLE) ? a.side[k] : 0u;
             ezd::EvalOut o;
-            ezd::eval_constraint<false>(kind, a.side[k], ident, rec.d(RW_P0), kind_has_p1(kind) ? rec.d(RW_P1) : 0.0, XR, o);
+            ezd::eval_constraint<false>(kind, side, ident, ly.p0 != 0xff ? rec_double(rec, ly.p0) : 0.0,
+                                        ly.p1 != 0xff ? rec_double(rec, ly.p1) : 0.0, XR, o);
             bool sat = ezm::ez_abs(o.res[0]) < ezd::kEps;
             if (cl_rows[kind] == 2) sat = sat && (ezm::ez_abs(o.res[1]) < ezd::kEps);
             if (!sat) {
-                const uint32_t c = rec.w(RW_ORIG);
+                const uint32_t c = a.slot_orig[k];
                 atomicOr(&a.unsat[c >> 5], 1u << (c & 31u));
                 ctrl->any_unsat = 1;
             }
@@ -902,8 +979,63 @@ __global__ void __launch_bounds__(kBlock) lm_large_kernel(const LargeArgs a) {
 }
 
 // ---- stand-alone kernels for throughput measurement (same device code as the phases above) ------------
-__global__ void __launch_bounds__(128, 5) assemble_large_kernel(const LargeArgs a, const bool write_jr) {
-    assemble_phase_inl<true, true>(a, a.R0, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x, write_jr);
+// Persistent warps; every warp owns tiles gw, gw + nw, ... and keeps kAsmStages of them in flight: lane 0 arms the
+// stage's mbarrier with the tile's byte count and issues one cp.async.bulk for the whole tile; the warp waits on
+// the barrier's phase, evaluates its 32 constraints out of shared memory, and refills the stage.
+__global__ void __launch_bounds__(kAsmWarps * 32, 2) assemble_large_kernel(const LargeArgs a, const bool write_jr) {
+    extern __shared__ __align__(128) unsigned char asm_smem[];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    unsigned char* stage_base = asm_smem + (size_t)warp * kAsmStages * kTileBytesMax;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(asm_smem + (size_t)kAsmWarps * kAsmStages * kTileBytesMax) + warp * kAsmStages;
+    const uint32_t gw = blockIdx.x * kAsmWarps + warp, nw = gridDim.x * kAsmWarps;
+    if (lane == 0) {
+        for (uint32_t st = 0; st < kAsmStages; ++st) mbar_init(&bars[st], 1);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncwarp();
+    const uint32_t count = gw < a.n_tiles ? (a.n_tiles - gw + nw - 1) / nw : 0u;
+    auto issue = [&](uint32_t k) {  // lane 0: start the copy of this warp's k-th tile into stage k % kAsmStages
+        const TileDesc td = a.tiles[gw + k * nw];
+        const uint32_t bytes = (uint32_t)a.layout[td.meta & 0xffu].n_words * 128u;
+        const uint32_t st = k % kAsmStages;
+        mbar_expect_tx(&bars[st], bytes);
+        bulk_copy_g2s(stage_base + (size_t)st * kTileBytesMax, a.recs + (size_t)td.off16 * 4, bytes, &bars[st]);
+    };
+    if (lane == 0)
+        for (uint32_t k = 0; k < kAsmStages && k < count; ++k) issue(k);
+    // The gathers of tile k + 1 are issued before tile k is evaluated (its record is already in shared memory, two
+    // more are in flight), so their latency hides behind the arithmetic.
+    double xv[8], xn[8];
+    TileDesc td = count ? a.tiles[gw] : TileDesc{0, 0};
+    if (count) {
+        mbar_wait(&bars[0], 0);
+        if (lane < (td.meta >> 8))
+            gather_x(a, a.layout[td.meta & 0xffu], td.meta & 0xffu, reinterpret_cast<const uint32_t*>(stage_base) + lane, xv);
+    }
+    for (uint32_t k = 0; k < count; ++k) {
+        const uint32_t t = gw + k * nw, st = k % kAsmStages;
+        const uint32_t kind = td.meta & 0xffu, n_valid = td.meta >> 8;
+        TileDesc tn{0, 0};
+        if (k + 1 < count) {
+            tn = a.tiles[t + nw];
+            const uint32_t sn = (k + 1) % kAsmStages;
+            mbar_wait(&bars[sn], ((k + 1) / kAsmStages) & 1u);
+            if (lane < (tn.meta >> 8))
+                gather_x(a, a.layout[tn.meta & 0xffu], tn.meta & 0xffu,
+                         reinterpret_cast<const uint32_t*>(stage_base + (size_t)sn * kTileBytesMax) + lane, xn);
+        }
+        if (lane < n_valid)
+            assemble_slot<true, true>(a, a.layout[kind], kind, reinterpret_cast<const uint32_t*>(stage_base + (size_t)st * kTileBytesMax) + lane,
+                                      t * 32 + lane, a.R0, write_jr, xv);
+        __syncwarp();
+        if (lane == 0 && k + kAsmStages < count) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            issue(k + kAsmStages);
+        }
+        td = tn;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) xv[q] = xn[q];
+    }
 }
 __global__ void __launch_bounds__(256) spmv_csr_kernel(const uint32_t* __restrict__ row_ptr, const uint32_t* __restrict__ col_idx,
                                                        const double* __restrict__ vals, const double* __restrict__ x,
@@ -916,8 +1048,11 @@ __global__ void __launch_bounds__(256) spmv_csr_kernel(const uint32_t* __restric
 }
 
 struct LargeDevice {
-    uint32_t* recs = nullptr;
-    uint32_t n_slots = 0;
+    uint32_t *recs = nullptr, *slot_orig = nullptr;
+    TileDesc* tiles = nullptr;
+    uint8_t* side_flags = nullptr;
+    KindLayout layout[EZPZ_K_COUNT];
+    uint32_t n_slots = 0, n_tiles = 0;
     uint32_t *csr_row_ptr = nullptr, *csr_col_idx = nullptr, *csc_col_ptr = nullptr, *csc_row_idx = nullptr;
     uint32_t *perm = nullptr, *lr_ptr = nullptr, *lr_col = nullptr, *lvl_ptr = nullptr, *lvl_cols = nullptr, *ent_ptr = nullptr,
              *ent_row = nullptr, *ent_col = nullptr, *ent_slot = nullptr, *ent_mask_ptr = nullptr, *ent_mask = nullptr,
@@ -957,41 +1092,77 @@ int32_t get_large(ezpz_context* ctx, const ezpz_structure* s, DeviceCopy* dc, La
     if (!L) return EZPZ_ERR_INVALID_ARGUMENT;
     dc->large = L;  // owned by the device copy from here on (released with it)
     {
-        // LargeRec words, transposed in tiles of 32 processing slots
-        const uint32_t n_slots = (uint32_t)P.cons_order.size();
-        std::vector<uint32_t> t((size_t)((n_slots + 31) / 32) * kRecWords * 32, 0u);
-        for (uint32_t k = 0; k < n_slots; ++k) {
-            uint32_t* w = t.data() + (size_t)(k >> 5) * (kRecWords * 32) + (k & 31u);
-            auto put = [&](uint32_t word, uint32_t v) { w[word * 32] = v; };
-            const uint32_t c = P.cons_order[k];
-            if (c == UINT32_MAX) {
-                put(RW_KIND, kPadKind);
-                continue;
-            }
-            const DevCons& dc = s->dev_cons[c];
-            const ezk::KindInfo& ki = ezk::kKinds[dc.kind];
-            put(RW_KIND, dc.kind | ((dc.flags & 0xffu) << 8));
-            put(RW_ROW0, dc.row0);
-            put(RW_ORIG, c);
-            const uint32_t jr0 = s->csr_row_ptr[dc.row0];
-            put(RW_JR0, jr0);
-            for (int row = 0; row < ki.rows; ++row) {
-                uint32_t code = 0;
-                for (int q = 0; q < ki.emit_len[row]; ++q) {
-                    const uint32_t off = s->csc_to_csr[dc.slot[row][q] & ~kAccumulate] - jr0;  // < 16: two rows of <= 8
-                    code |= (off & 15u) << (4 * q);
-                    put(RW_SLOT + row * 8 + q, dc.slot[row][q]);
-                }
-                put(RW_JRC0 + row, code);
-            }
-            for (int q = 0; q < 8; ++q) put(RW_IDS + q, dc.ids[q]);
-            uint32_t dw[2];
-            std::memcpy(dw, &dc.p0, 8); put(RW_P0, dw[0]); put(RW_P0 + 1, dw[1]);
-            std::memcpy(dw, &dc.p1, 8); put(RW_P1, dw[0]); put(RW_P1 + 1, dw[1]);
-            std::memcpy(dw, &dc.weight, 8); put(RW_WEIGHT, dw[0]); put(RW_WEIGHT + 1, dw[1]);
+        // record tiles (see the comment above assemble_slot)
+        static const uint8_t kHasP0[EZPZ_K_COUNT] = {0, 0, 1, 0, 1, 1, 0, 0, 1, 1, 0, 0, 1, 0, 1, 0, 0, 1, 1, 1, 0, 0, 1, 1, 1};
+        const bool with_jr = !P.direct;  // only the PCG path keeps the CSR-ordered copy of J
+        for (int k = 0; k < EZPZ_K_COUNT; ++k) {
+            const ezk::KindInfo& ki = ezk::kKinds[k];
+            KindLayout& ly = L->layout[k];
+            uint8_t w = 1;  // word 0: first residual row
+            ly.ids = w; w += ki.n_ids;
+            ly.p0 = kHasP0[k] ? w : 0xff; w += kHasP0[k] ? 2 : 0;
+            const bool has_p1 = k == EZPZ_K_LINES_AT_ANGLE || k == EZPZ_K_ARC_ANGLE || k == EZPZ_K_POINTS_AT_ANGLE;
+            ly.p1 = has_p1 ? w : 0xff; w += has_p1 ? 2 : 0;
+            ly.weight = s->all_weights_one ? 0xff : w; w += s->all_weights_one ? 0 : 2;
+            ly.slot0 = w; w += ki.emit_len[0];
+            ly.slot1 = w; w += ki.emit_len[1];
+            ly.jr = with_jr ? w : 0xff; w += with_jr ? 1 + ki.rows : 0;
+            ly.n_words = w;
         }
-        EZ_TRY(upload(&L->recs, t, detail));
+        const uint32_t n_slots = (uint32_t)P.cons_order.size(), n_tiles = n_slots / 32;  // cons_order is padded to whole warps
+        std::vector<TileDesc> tiles(n_tiles);
+        std::vector<uint32_t> recs, orig(n_slots, 0u);
+        std::vector<uint8_t> flags(std::max<uint32_t>(1, n_slots), 0);
+        recs.reserve((size_t)n_slots * 16);
+        for (uint32_t t = 0; t < n_tiles; ++t) {
+            const uint32_t c0 = P.cons_order[(size_t)t * 32];  // first slot of a tile is never padding
+            const uint32_t kind = s->dev_cons[c0].kind;
+            const KindLayout& ly = L->layout[kind];
+            const ezk::KindInfo& ki = ezk::kKinds[kind];
+            const size_t base = recs.size();  // multiple of 32 words = 128 bytes
+            recs.resize(base + (size_t)ly.n_words * 32, 0u);
+            uint32_t n_valid = 0;
+            for (uint32_t l = 0; l < 32; ++l) {
+                const uint32_t c = P.cons_order[(size_t)t * 32 + l];
+                if (c == UINT32_MAX) continue;  // padding sits at the end of the kind group
+                n_valid = l + 1;
+                const DevCons& dc = s->dev_cons[c];
+                auto put = [&](uint32_t word, uint32_t v) { recs[base + (size_t)word * 32 + l] = v; };
+                auto put_d = [&](uint32_t word, double v) {
+                    uint32_t dw[2];
+                    std::memcpy(dw, &v, 8);
+                    put(word, dw[0]);
+                    put(word + 1, dw[1]);
+                };
+                orig[(size_t)t * 32 + l] = c;
+                flags[(size_t)t * 32 + l] = (uint8_t)(dc.flags & 0xffu);
+                put(0, dc.row0);
+                for (int q = 0; q < ki.n_ids; ++q) put(ly.ids + q, dc.ids[q]);
+                if (ly.p0 != 0xff) put_d(ly.p0, dc.p0);
+                if (ly.p1 != 0xff) put_d(ly.p1, dc.p1);
+                if (ly.weight != 0xff) put_d(ly.weight, dc.weight);
+                const uint32_t jr0 = s->csr_row_ptr[dc.row0];
+                if (ly.jr != 0xff) put(ly.jr, jr0);
+                for (int row = 0; row < ki.rows; ++row) {
+                    uint32_t code = 0;
+                    for (int q = 0; q < ki.emit_len[row]; ++q) {
+                        const uint32_t off = s->csc_to_csr[dc.slot[row][q] & ~kAccumulate] - jr0;  // < 16: two rows of <= 8
+                        code |= (off & 15u) << (4 * q);
+                        put((row == 0 ? ly.slot0 : ly.slot1) + q, dc.slot[row][q]);
+                    }
+                    if (ly.jr != 0xff) put(ly.jr + 1 + row, code);
+                }
+            }
+            tiles[t].off16 = (uint32_t)(base / 4);
+            tiles[t].meta = kind | (n_valid << 8);
+            if (base / 4 > 0xfffffff0ull) return EZPZ_ERR_TOO_LARGE;
+        }
+        EZ_TRY(upload(&L->recs, recs, detail));
+        EZ_TRY(upload(&L->tiles, tiles, detail));
+        EZ_TRY(upload(&L->slot_orig, orig, detail));
+        EZ_TRY(upload(&L->side_flags, flags, detail));
         L->n_slots = n_slots;
+        L->n_tiles = n_tiles;
     }
     EZ_TRY(upload(&L->csr_row_ptr, s->csr_row_ptr, detail));
     EZ_TRY(upload(&L->csr_col_idx, s->csr_col_idx, detail));
@@ -1056,7 +1227,12 @@ void fill_args(LargeArgs& a, const ezpz_structure* s, const DeviceCopy* dc, cons
     const LargeProgram& P = s->large;
     std::memset(&a, 0, sizeof a);
     a.recs = L->recs;
+    a.tiles = L->tiles;
+    a.slot_orig = L->slot_orig;
+    a.side_flags = L->side_flags;
+    std::memcpy(a.layout, L->layout, sizeof a.layout);
     a.n_slots = L->n_slots;
+    a.n_tiles = L->n_tiles;
     a.unit_weights = s->all_weights_one ? 1u : 0u;
     a.csr_row_ptr = L->csr_row_ptr;
     a.csr_col_idx = L->csr_col_idx;
@@ -1122,7 +1298,7 @@ namespace ezs {
 void release_large(DeviceCopy* d) {
     LargeDevice* L = (LargeDevice*)d->large;
     if (!L) return;
-    void* ptrs[] = {L->recs, L->csr_row_ptr, L->csr_col_idx, L->csc_col_ptr, L->csc_row_idx, L->perm, L->lr_ptr, L->lr_col,
+    void* ptrs[] = {L->recs, L->tiles, L->slot_orig, L->side_flags, L->csr_row_ptr, L->csr_col_idx, L->csc_col_ptr, L->csc_row_idx, L->perm, L->lr_ptr, L->lr_col,
                     L->lvl_ptr, L->lvl_cols, L->ent_ptr, L->ent_row, L->ent_col, L->ent_slot, L->ent_mask_ptr, L->ent_mask, L->aent,
                     L->aprod_ptr, L->aprod_a, L->aprod_b, L->lvl_maxrow, L->vg, L->jr, L->cgv,
                     L->partials, L->sumsq, L->lvl_ns, L->side, L->degen, L->unsat, L->ctrl};
@@ -1130,6 +1306,39 @@ void release_large(DeviceCopy* d) {
         if (p) cudaFree(p);
     delete L;
     d->large = nullptr;
+}
+
+// One residual + Jacobian evaluation at x through the large path's own assembly kernel (ezpz_b200_eval).
+int32_t eval_large(ezpz_context* ctx, const ezpz_structure* s, const double* x, double* r, double* jac_csc, double* jac_csr,
+                   bool* have_csr, ezpz_error_detail_t* detail) {
+    if (!s->large.built) return EZPZ_ERR_UNSUPPORTED;
+    EZ_CUDA(cudaSetDevice(ctx->device), "cudaSetDevice");
+    DeviceCopy* dc = nullptr;
+    EZ_TRY(get_device_copy(ctx, s, &dc, detail));
+    LargeDevice* L = nullptr;
+    EZ_TRY(get_large(ctx, s, dc, &L, detail));
+    ezpz_config_t cfg;
+    ezpz_b200_config_default(&cfg);
+    LargeArgs a;
+    fill_args(a, s, dc, L, &cfg);
+    cudaStream_t st = ctx->stream;
+    const size_t nnz = s->csc_row_idx.size();
+    EZ_CUDA(cudaMemcpyAsync(L->vg + a.X0, x, sizeof(double) * s->n, cudaMemcpyHostToDevice, st), "H2D x");
+    EZ_CUDA(cudaMemsetAsync(L->degen, 0, sizeof(uint32_t) * s->n_cons, st), "memset degen");
+    resolve_sides_kernel<<<(unsigned)std::max<size_t>(1, std::min<size_t>((L->n_tiles + 7) / 8, 4096)), 256, 0, st>>>(a);
+    EZ_CUDA(cudaFuncSetAttribute(assemble_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAsmSmem),
+            "cudaFuncSetAttribute(assemble_large_kernel)");
+    const unsigned grid = (unsigned)std::max<size_t>(1, std::min<size_t>((L->n_tiles + kAsmWarps - 1) / kAsmWarps, (size_t)ctx->sm_count * 2));
+    const bool with_jr = !s->large.direct;
+    assemble_large_kernel<<<grid, kAsmWarps * 32, kAsmSmem, st>>>(a, with_jr);
+    ctx->launches += 2;
+    EZ_CUDA(cudaGetLastError(), "assemble_large_kernel launch");
+    if (r) EZ_CUDA(cudaMemcpyAsync(r, L->vg + a.R0, sizeof(double) * s->m, cudaMemcpyDeviceToHost, st), "D2H r");
+    if (jac_csc) EZ_CUDA(cudaMemcpyAsync(jac_csc, L->vg + a.J0, sizeof(double) * nnz, cudaMemcpyDeviceToHost, st), "D2H jac");
+    if (jac_csr && with_jr) EZ_CUDA(cudaMemcpyAsync(jac_csr, L->jr, sizeof(double) * nnz, cudaMemcpyDeviceToHost, st), "D2H jac csr");
+    if (have_csr) *have_csr = with_jr;
+    EZ_CUDA(cudaStreamSynchronize(st), "cudaStreamSynchronize");
+    return EZPZ_OK;
 }
 
 int32_t solve_large(ezpz_context* ctx, const ezpz_structure* s, const ezpz_config_t* config, const ezpz_one_io_t* io,
@@ -1215,26 +1424,52 @@ extern "C" int32_t ezpz_b200_large_bench(ezpz_context_t* ctx, const ezpz_structu
     EZ_CUDA(cudaMemsetAsync(L->side, 1, L->n_slots, st), "memset side");
     EZ_CUDA(cudaMemsetAsync(L->degen, 0, sizeof(uint32_t) * s->n_cons, st), "memset degen");
     const unsigned grid = (unsigned)ctx->sm_count * 8;
-    const unsigned grid_asm = (unsigned)std::min<size_t>(((size_t)L->n_slots + 127) / 128, (size_t)ctx->sm_count * 64);
+    const unsigned grid_asm = (unsigned)std::max<size_t>(1, std::min<size_t>((L->n_tiles + kAsmWarps - 1) / kAsmWarps, (size_t)ctx->sm_count * 2));
+    EZ_CUDA(cudaFuncSetAttribute(assemble_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAsmSmem),
+            "cudaFuncSetAttribute(assemble_large_kernel)");
     const double n = s->n, m = s->m, nnz = (double)s->csc_row_idx.size(), C = s->n_cons;
     cudaEvent_t e0, e1;
     EZ_CUDA(cudaEventCreate(&e0), "cudaEventCreate");
     EZ_CUDA(cudaEventCreate(&e1), "cudaEventCreate");
     // one untimed launch first (also fills jr for the SpMVs)
-    assemble_large_kernel<<<grid_asm, 128, 0, st>>>(a, true);
+    assemble_large_kernel<<<grid_asm, kAsmWarps * 32, kAsmSmem, st>>>(a, true);
     ctx->launches += 1;
-    EZ_CUDA(cudaEventRecord(e0, st), "cudaEventRecord");
-    for (int k = 0; k < reps; ++k) {
-        if (which == 0 || which == 3) assemble_large_kernel<<<grid_asm, 128, 0, st>>>(a, which == 3);
+    // Launches run back to back inside ONE event pair (a per-launch pair adds ~5 us of launch latency to kernels that
+    // take 15-50 us).  For an HBM figure the caller passes a system whose working set exceeds the 126 MB L2
+    // (profiles/large_bench.py: 2.08M variables, ~270 MB), so every launch streams from HBM; EZPZ_B200_BENCH_FLUSH_L2=1
+    // instead times each launch on its own after a 256 MiB fill.
+    const char* fl = std::getenv("EZPZ_B200_BENCH_FLUSH_L2");
+    const bool flush = fl && fl[0] == '1';
+    void* flush_buf = nullptr;
+    const size_t flush_bytes = 256u << 20;
+    if (flush) EZ_CUDA(cudaMalloc(&flush_buf, flush_bytes), "cudaMalloc(flush)");
+    float ms = 0.f;
+    auto launch = [&]() {
+        if (which == 0 || which == 3) assemble_large_kernel<<<grid_asm, kAsmWarps * 32, kAsmSmem, st>>>(a, which == 3);
         else if (which == 1) spmv_csr_kernel<<<grid, 256, 0, st>>>(L->csr_row_ptr, L->csr_col_idx, L->jr, L->vg + a.X0, L->cgv + 4 * (size_t)s->n, s->m);
         else spmv_csr_kernel<<<grid, 256, 0, st>>>(L->csc_col_ptr, L->csc_row_idx, L->vg + a.J0, L->vg + a.R0, L->cgv, s->n);
         ctx->launches += 1;
+    };
+    if (flush) {
+        for (int k = 0; k < reps; ++k) {
+            EZ_CUDA(cudaMemsetAsync(flush_buf, k & 0xff, flush_bytes, st), "memset flush");
+            EZ_CUDA(cudaEventRecord(e0, st), "cudaEventRecord");
+            launch();
+            EZ_CUDA(cudaEventRecord(e1, st), "cudaEventRecord");
+            EZ_CUDA(cudaEventSynchronize(e1), "cudaEventSynchronize");
+            float one = 0.f;
+            EZ_CUDA(cudaEventElapsedTime(&one, e0, e1), "cudaEventElapsedTime");
+            ms += one;
+        }
+    } else {
+        EZ_CUDA(cudaEventRecord(e0, st), "cudaEventRecord");
+        for (int k = 0; k < reps; ++k) launch();
+        EZ_CUDA(cudaEventRecord(e1, st), "cudaEventRecord");
+        EZ_CUDA(cudaEventSynchronize(e1), "cudaEventSynchronize");
+        EZ_CUDA(cudaEventElapsedTime(&ms, e0, e1), "cudaEventElapsedTime");
     }
-    EZ_CUDA(cudaEventRecord(e1, st), "cudaEventRecord");
-    EZ_CUDA(cudaEventSynchronize(e1), "cudaEventSynchronize");
     EZ_CUDA(cudaGetLastError(), "bench kernels");
-    float ms = 0.f;
-    EZ_CUDA(cudaEventElapsedTime(&ms, e0, e1), "cudaEventElapsedTime");
+    if (flush_buf) cudaFree(flush_buf);
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     *mean_us = (double)ms * 1e3 / reps;

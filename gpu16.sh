@@ -1,0 +1,3 @@
+python -m pytest tests/test_gpu_large.py -m gpu -x -q 2>&1 | tail -25
+python profiles/large_bench.py 77000 20 --solve
+EZPZ_B200_FORCE_PCG=1 python profiles/large_bench.py 77000 20
