@@ -551,6 +551,7 @@ __device__ __noinline__ void backward_column_thread(const LargeArgs& a, uint32_t
 // back to the thread variant on lane 0.
 constexpr uint32_t kRowCap = 256;
 constexpr uint32_t kWarpStageDoubles = 2 * kRowCap;
+static_assert(kWarpStageDoubles == 512, "one 4 KB stage per warp serves the factor levels and the sum of squares");
 
 __device__ __noinline__ void factor_entry_warp(const LargeArgs& a, uint32_t e, uint32_t lane, double* st) {
     double* lv = a.vg + a.L0;
@@ -1037,6 +1038,8 @@ __global__ void __launch_bounds__(kAsmWarps * 32, 2) assemble_large_kernel(const
         for (int q = 0; q < 8; ++q) xv[q] = xn[q];
     }
 }
+// Thread per row, entries ascending, one fma chain (measured faster than staging the warp's entry range through
+// shared memory: both are bound by the L1's sector lookups for the x gathers, and shared memory shares that pipe).
 __global__ void __launch_bounds__(256) spmv_csr_kernel(const uint32_t* __restrict__ row_ptr, const uint32_t* __restrict__ col_idx,
                                                        const double* __restrict__ vals, const double* __restrict__ x,
                                                        double* __restrict__ y, uint32_t rows) {
