@@ -21,6 +21,9 @@ topology), then per step the whole Levenberg-Marquardt solve of all 65,536 probl
   cpu_baseline  the CPU oracle (a port of the reference algorithm; the Rust reference cannot be built
             here) on all host cores, per-solve structure analysis included as the reference does.
 
+  large_system  (N = 1) BASELINE.json configs 3 and 4: one large system per solve, GPU time through the C ABI next
+            to the CPU port, plus the HBM figures of the assembly and SpMV kernels on a system larger than L2.
+
 `--impl reference` times that CPU port alone on the same config and prints the same JSON shape.
 """
 import argparse
@@ -115,6 +118,67 @@ def cpu_arm(steps, warmup, sample_batch):
                       f"structure analysis repeated per solve as the reference does; with the analysis hoisted "
                       f"once per thread: {sample_batch / t_hoist:.0f} solves/s",
             "ms_per_step": best * 1e3}
+
+
+def large_system_report(ctx, peaks):
+    """Configs 3 and 4 of BASELINE.json (one large system per solve; rank 0, N = 1 only): solve time through the
+    C ABI with host buffers next to the CPU port on the same inputs, and the HBM figures of the assembly and SpMV
+    kernels on a system whose working set exceeds L2."""
+    import numpy as np
+    import torch
+
+    import ezpz_b200 as ez
+    import orc
+    import workloads as wl
+
+    out = {}
+    # config 3: massive_parallel_system, 500 lines = 2,000 rows x 2,000 vars (README.md:36-40)
+    recs, n, g, _ = wl.system_from_text(wl.massive_problem_text(500, False))
+    st = ez.Structure(recs, n)
+    times, it, status, path = ctx.time_solve_one(st, g, reps=30)
+    gpu_us = statistics.median(times[5:]) * 1e6
+    cpu = []
+    for _ in range(7):
+        t0 = time.perf_counter()
+        o = orc.solve_inner(recs, g)
+        cpu.append(time.perf_counter() - t0)
+    out["massive_parallel_system_2000x2000"] = {
+        "gpu_solve_us": gpu_us, "cpu_port_solve_us": statistics.median(cpu) * 1e6, "cpu_cores": 1,
+        "readme_reference_us": 2943, "lm_iterations": it, "cpu_lm_iterations": int(o.iterations),
+        "converged": bool(status & 1), "path": {0: "batched-small", 1: "sparse direct", 2: "PCG"}[path],
+        "note": "ezpz_b200_solve_one, host buffers, H2D + one persistent kernel + D2H per call; CPU = oracle port incl. its "
+                "per-solve analysis, as ezpz-cli times it; README figure is the reference's own (hardware not stated)"}
+    # config 4: synthetic 1,001,000-variable sketch
+    recs, n, g, exact = wl.chain_sketch(77000)
+    t0 = time.perf_counter()
+    st = ez.Structure(recs, n)
+    analysis_s = time.perf_counter() - t0
+    od = st.ordering()
+    hg = torch.from_numpy(g).pin_memory().numpy()
+    hf = torch.empty(n, dtype=torch.float64).pin_memory().numpy()
+    times, it, status, path = ctx.time_solve_one(st, hg, reps=6, final_values=hf)
+    gpu_ms = statistics.median(times[1:]) * 1e3
+    t0 = time.perf_counter()
+    o = orc.solve_inner(recs, g)
+    cpu_ms = (time.perf_counter() - t0) * 1e3
+    scale = np.maximum(1.0, np.abs(o.final_values))
+    out["synthetic_1M_variable_sketch"] = {
+        "n": n, "m": st.m, "nnz": st.nnz, "gpu_solve_ms": gpu_ms, "cpu_port_solve_ms": cpu_ms, "cpu_cores": 1,
+        "lm_iterations": it, "cpu_lm_iterations": int(o.iterations), "converged": bool(status & 1),
+        "max_rel_diff_vs_cpu_port": float((np.abs(hf - o.final_values) / scale).max()),
+        "path": {0: "batched-small", 1: "sparse direct", 2: "PCG"}[path], "elimination_tree_levels": od["n_levels"],
+        "nnz_l": od["nnz_l"], "host_analysis_s_once_per_topology": analysis_s}
+    del st
+    # kernels on 2.08M variables (~270 MB working set > 126 MB L2), launches back to back
+    recs, n, g, _ = wl.chain_sketch(160000)
+    st = ez.Structure(recs, n)
+    ks = {}
+    for which, name in ((0, "assemble_large_kernel"), (2, "spmv_csr_kernel (z = Jt q)"), (1, "spmv_csr_kernel (y = J p)")):
+        us, by = ctx.large_bench(st, g, which, 20)
+        ks[name] = {"us_per_launch": us, "algorithmic_MB": by / 1e6, "GB_s": by / us / 1e3,
+                    "frac_of_hbm_peak": by / us / 1e3 / peaks["hbm_gbs"]}
+    out["kernels_on_2M_variable_sketch"] = ks
+    return out
 
 
 def run_reference(args):
@@ -283,6 +347,8 @@ def run_gpu(args):
         if world == 1:
             sample = BATCH_PER_GPU
             line["cpu_baseline"] = {k: v for k, v in cpu_arm(3, 1, sample).items() if k != "ms_per_step"}
+            if not args.no_large:
+                line["large_system"] = large_system_report(ctx, peaks)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -321,6 +387,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-large", action="store_true", help="skip the single-large-system report (configs 3 and 4)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -607,6 +607,30 @@ class Context:
         res.unsatisfied = np.flatnonzero(bits).tolist()
         return res
 
+    def time_solve_one(self, st, guesses, reps=10, final_values=None):
+        """Wall-clock seconds of `reps` ezpz_b200_solve_one calls on caller-provided host buffers (pass pinned arrays
+        for large systems); buffers and the ctypes structs are built once, so the time is the C call's.  Returns
+        (list of seconds, iterations, status, path_used)."""
+        import time
+        g = np.ascontiguousarray(guesses, dtype=np.float64)
+        cfg = Config()._native()
+        fv = final_values if final_values is not None else np.empty_like(g)
+        it, status, path, lin = np.zeros(1, np.uint32), np.zeros(1, np.uint8), np.zeros(1, np.int32), np.zeros(1, np.uint32)
+        unsat = np.zeros((st.n_cons + 31) // 32, np.uint32)
+        io = native.OneIO(native.ptr(g), native.ptr(fv), native.ptr(it), native.ptr(status), native.ptr(unsat), None, None,
+                          native.ptr(path), native.ptr(lin))
+        det = native.ErrorDetail()
+        fn = native.lib().ezpz_b200_solve_one
+        args = (self.handle, st.handle, C.byref(cfg), C.byref(io), C.byref(det))
+        times = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            rc = fn(*args)
+            times.append(time.perf_counter() - t0)
+            if rc != 0:
+                raise EzpzError(rc, det)
+        return times, int(it[0]), int(status[0]), int(path[0])
+
     def evaluate(self, st, x):
         """One residual + Jacobian evaluation through the device assembly kernel (parity/debug entry)."""
         x = np.ascontiguousarray(x, dtype=np.float64)
