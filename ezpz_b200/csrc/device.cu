@@ -730,6 +730,24 @@ int32_t ezpz_b200_solve_batch_device(ezpz_context_t* ctx, const ezpz_structure_t
     return EZPZ_OK;
 }
 
+// Problems per full wave of the batched kernel on this device: one CTA per SM (the per-problem state fills the
+// SM's shared memory), T problems per CTA — the same T ezpz_b200_solve_batch_device picks for a large batch.
+static uint64_t small_wave_problems(const ezpz_context* ctx, const ezpz_structure* s) {
+    const SmallProgram& P = s->small;
+    if (!P.valid) return 0;
+    const size_t per_thread = (size_t)P.W * sizeof(double);
+    size_t tape_words_v3 = 0;
+    for (size_t i = 0; i < P.tape.size(); i += 2 + (P.tape[i] >> 16)) tape_words_v3 += 4 + 2 * (size_t)(P.tape[i] >> 16);
+    const size_t tables = (size_t)s->n_cons * sizeof(DevCons) + tape_words_v3 * sizeof(uint32_t);
+    const bool stage = tables <= 64 * 1024 && per_thread * 32 + tables <= ctx->smem_optin &&
+                       (ctx->smem_optin - tables) / per_thread >= 64;
+    const size_t avail = ctx->smem_optin - (stage ? tables : 0);
+    const uint32_t T = (uint32_t)std::min<size_t>(256, avail / per_thread) / 32 * 32;
+    if (T < 32) return 0;
+    const size_t ctas_per_sm = std::max<size_t>(1, ctx->smem_optin / (per_thread * T + (stage ? tables : 0)));
+    return (uint64_t)ctx->sm_count * T * ctas_per_sm;
+}
+
 int32_t ezpz_b200_solve_batch(ezpz_context_t* ctx, const ezpz_structure_t* s, const ezpz_config_t* config,
                               uint64_t batch, const ezpz_batch_io_t* io, ezpz_error_detail_t* detail) {
     if (!ctx || !s || !config || !io) return EZPZ_ERR_INVALID_ARGUMENT;
@@ -760,9 +778,18 @@ int32_t ezpz_b200_solve_batch(ezpz_context_t* ctx, const ezpz_structure_t* s, co
     // Copy/compute pipeline: the batch is cut into chunks that rotate over three streams, so the H2D copy of
     // chunk k+1, the kernel of chunk k and the D2H copy of chunk k-1 overlap (with pinned host buffers the
     // copies are true DMA on the two copy engines; pageable buffers still work, just without the overlap).
-    uint64_t n_chunks = std::min<uint64_t>(16, std::max<uint64_t>(1, batch / 16384));
-    if (const char* env = std::getenv("EZPZ_B200_CHUNKS")) n_chunks = std::max<uint64_t>(1, std::strtoull(env, nullptr, 10));
-    const uint64_t chunk = (batch + n_chunks - 1) / n_chunks;
+    // A chunk is a whole number of kernel waves (a partial wave costs as much kernel time as a full one), at most
+    // eight chunks per call.
+    uint64_t chunk = batch;
+    if (const uint64_t wave = small_wave_problems(ctx, s); wave > 0 && batch > wave) {
+        const uint64_t waves = (batch + wave - 1) / wave;
+        chunk = wave * ((waves + 7) / 8);
+    }
+    if (const char* env = std::getenv("EZPZ_B200_CHUNKS")) {
+        const uint64_t k = std::max<uint64_t>(1, std::strtoull(env, nullptr, 10));
+        chunk = (batch + k - 1) / k;
+    }
+    const uint64_t n_chunks = (batch + chunk - 1) / chunk;
     EZ_CUDA(cudaStreamSynchronize(ctx->stream), "cudaStreamSynchronize");
     for (uint64_t c = 0; c < n_chunks; ++c) {
         const uint64_t b0 = c * chunk;
