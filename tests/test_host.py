@@ -195,3 +195,35 @@ def test_no_gpu_fails_loudly():
     # the one case that needs no device: an empty request list returns the guesses (lib.rs:155-170)
     out = ez.solve([], [(0, 0.5)])
     assert list(out.final_values()) == [0.5] and out.iterations() == 0 and out.converged()
+
+
+def test_large_system_ordering_host_analysis():
+    """sparse_direct.cpp on the CPU: the elimination order is a permutation, natural for the block-diagonal
+    massive_parallel_system (shallow tree), nested dissection with a logarithmic tree for the chain sketch; the oracle
+    solves to the same answer (identical iteration count, 1e-9) whichever order it is given."""
+    import orc
+    recs, n, g, _ = wl.system_from_text(wl.massive_problem_text(500, False))
+    od = ez.Structure(recs, n).ordering()
+    assert od["path"] == 1 and not od["nested"] and od["n_levels"] <= 4 and od["sum_chunk"] == 0
+    assert np.array_equal(od["elim_order"], np.arange(n))
+    heights = {}
+    for cells in (64, 1024, 4096):
+        recs, n, g, exact = wl.chain_sketch(cells)
+        st = ez.Structure(recs, n)
+        od = st.ordering()
+        assert od["path"] == 1 and od["nested"]
+        assert sorted(od["elim_order"].tolist()) == list(range(n))
+        assert od["nnz_l"] < 16 * n  # fill stays linear in n
+        heights[cells] = od["n_levels"]
+        if cells <= 1024:
+            a = orc.solve_inner(recs, g)
+            b = orc.solve_inner_ordered(recs, g, od["elim_order"], od["sum_chunk"])
+            assert a.iterations == b.iterations and a.converged and b.converged
+            assert np.abs(a.final_values - b.final_values).max() < 1e-9
+            c = orc.solve_inner_ordered(recs, g, None, 0)
+            assert np.array_equal(a.final_values, c.final_values)
+    # 64x more cells add a few separators to the height, they do not multiply it
+    assert heights[4096] < heights[64] + 100
+    # a small system takes the batched kernel: no large programme
+    recs, n, g, _ = wl.system_from_text(wl.fixture_text("square"))
+    assert ez.Structure(recs, n).ordering()["path"] == 0
