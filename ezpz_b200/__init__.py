@@ -667,6 +667,13 @@ class Context:
         return mask
 
 
+def shard_range(batch, rank, world):
+    """Contiguous shard [begin, end) of a batch for rank `rank` of `world` (ezpz_b200_shard_range)."""
+    b, e = C.c_uint64(), C.c_uint64()
+    native.lib().ezpz_b200_shard_range(int(batch), int(rank), int(world), C.byref(b), C.byref(e))
+    return b.value, e.value
+
+
 _default_ctx = None
 
 
