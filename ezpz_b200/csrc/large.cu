@@ -73,9 +73,8 @@ struct LargeArgs {
     KindLayout layout[EZPZ_K_COUNT];
     const uint32_t *csr_row_ptr, *csr_col_idx, *csc_col_ptr, *csc_row_idx, *csc_to_csr;
     // sparse direct path (structure.h: LargeProgram)
-    const uint32_t *perm, *lr_ptr, *lr_col, *lvl_ptr, *lvl_cols, *ent_ptr, *ent_row, *ent_col, *ent_slot;
-    const uint32_t *ent_mask_ptr, *ent_mask, *aent, *aprod_ptr, *aprod_a, *aprod_b, *lvl_maxrow;
-    double* vg;          // [x | r | rn | J csc | L by rows | diag(A) | 1/pivot | y | d]
+    const uint32_t *perm, *sn_rows, *upd_rel, *upd_rec, *stage_ptr, *stage_rec, *aent_slot, *aprod_ptr, *aprod_a, *aprod_b, *diag_slot;
+    double* vg;          // [x | r | rn | J csc | L panels | 1/pivot | y | d]
     double* jr;          // J values in CSR order (PCG path)
     double* cgv;         // PCG vectors: p, res, ap, dinv (n each), q (m)
     double* partials;    // 3 * gridDim.x
@@ -88,9 +87,9 @@ struct LargeArgs {
     LargeCtrl* ctrl;
     double residual_tolerance, step_tolerance, initial_lambda, cg_rtol;
     uint32_t max_iterations, cg_max_iters;
-    uint32_t n_cons, n_slots, n_tiles, n, m, nnz, n_levels, solo_level, nnz_l, n_aent;
+    uint32_t n_cons, n_slots, n_tiles, n, m, nnz, n_levels, nnz_l, n_aent;
     uint32_t unit_weights;
-    uint32_t X0, R0, RN0, J0, L0, DG0, RV0, Y0, D0;
+    uint32_t X0, R0, RN0, J0, L0, RV0, Y0, D0;
     uint32_t direct;
 };
 
@@ -374,28 +373,22 @@ __device__ void chunk_sum_squares(const double* v, uint32_t count, double* out, 
     }
 }
 
-// ---- sparse direct step solve (schedule: sparse_direct.cpp) ---------------------------------------------
-// Loads are issued in batches that do not depend on the running sums, so that a dependent chain of fused
-// multiply-adds (the arithmetic-order spec is sequential in k) costs one memory round trip per kBatch terms
-// instead of one per term.
-constexpr int kBatch = 8;
-
-// A = JtJ + lambda*I in elimination numbering into the L value slots (pure fill entries start from +0.0),
-// the diagonal into diag[], b = -Jt r into y[].
+// ---- supernodal sparse direct step solve (schedule: sparse_direct.cpp) --------------------------------------
+// A = JtJ + lambda*I in elimination numbering into the panels (entries of the panels A does not have start from
+// +0.0), b = -Jt r into y[].  Two phases separated by a barrier: zero fill, then the products.
+__device__ void direct_zero(const LargeArgs& a, uint32_t tid, uint32_t nth) {
+    double* lv = a.vg + a.L0;
+    for (uint32_t e = tid; e < a.nnz_l; e += nth) lv[e] = 0.0;
+}
 __device__ void direct_assemble(const LargeArgs& a, double lambda, uint32_t tid, uint32_t nth) {
     const double* jv = a.vg + a.J0;
     const double* r = a.vg + a.R0;
     double* lv = a.vg + a.L0;
-    for (uint32_t e = tid; e < a.nnz_l; e += nth) {  // pure fill
-        const uint32_t s = __ldg(a.ent_slot + e);
-        if (!(s & kEntryInA)) lv[s] = 0.0;
-    }
     for (uint32_t k = tid; k < a.n_aent; k += nth) {
-        const uint32_t s = __ldg(a.ent_slot + __ldg(a.aent + k)) & ~kEntryInA;
         const uint32_t qb = __ldg(a.aprod_ptr + k), qe = __ldg(a.aprod_ptr + k + 1);
         double acc = 0.0;
         for (uint32_t q = qb; q < qe; ++q) acc = __fma_rn(jv[__ldg(a.aprod_a + q)], jv[__ldg(a.aprod_b + q)], acc);
-        lv[s] = acc;
+        lv[__ldg(a.aent_slot + k)] = acc;
     }
     for (uint32_t j = tid; j < a.n; j += nth) {
         const uint32_t c = __ldg(a.perm + j);
@@ -405,287 +398,273 @@ __device__ void direct_assemble(const LargeArgs& a, double lambda, uint32_t tid,
             dg = __fma_rn(v, v, dg);
             b = __fma_rn(v, -r[__ldg(a.csc_row_idx + e)], b);
         }
-        a.vg[a.DG0 + j] = __dadd_rn(dg, lambda);
+        lv[__ldg(a.diag_slot + j)] = __dadd_rn(dg, lambda);
         a.vg[a.Y0 + j] = b;
     }
 }
 
-// Iterator over the set bits of a mask stored as consecutive 32-bit words (ascending positions).
-struct BitWalk {
-    const uint32_t* w;
-    uint32_t word, base;
-    __device__ __forceinline__ void init(const uint32_t* words) {
-        w = words;
-        word = __ldg(w);
-        base = 0;
-    }
-    __device__ __forceinline__ uint32_t next() {  // caller guarantees another set bit exists
-        while (word == 0) {
-            ++w;
-            base += 32;
-            word = __ldg(w);
-        }
-        const uint32_t b = __ffs(word) - 1;
-        word &= word - 1;
-        return base + b;
-    }
+// Teams.  A supernode is factorised by a TEAM of 1 thread (panels of a few doubles, in global memory), 32 lanes
+// (a warp: stages with many panels) or 512 threads (a whole CTA: the upper stages of the tree, where a handful of
+// panels each receive dozens of updates).  Warps and CTAs stage the panel, the update blocks of the descendant
+// panels (each followed by y of that panel's columns), the update records, the relative row positions and their
+// inverse maps in shared memory (sizes in doubles / 32-bit words / 16-bit words):
+template <int TEAM>
+struct TeamCaps;
+template <>
+struct TeamCaps<1> {
+    static constexpr uint32_t panel = 0, block = 0, rel = 0, inv = 0, recs = 0;
 };
+template <>
+struct TeamCaps<32> {
+    static constexpr uint32_t panel = 576, block = 448, rel = 256, inv = 512, recs = 32;
+};
+template <>
+struct TeamCaps<512> {
+    static constexpr uint32_t panel = 15360, block = 4096, rel = 2048, inv = 8192, recs = 32;
+};
+constexpr uint32_t kYCap = 16;  // y of the panel's columns (a panel has at most 16)
+template <int TEAM>
+constexpr uint32_t team_stage_doubles() {  // recs = update records fetched per batch, 8 words each
+    return TeamCaps<TEAM>::panel + TeamCaps<TEAM>::block + kYCap + TeamCaps<TEAM>::recs * 8 / 2 + TeamCaps<TEAM>::rel / 2 +
+           TeamCaps<TEAM>::inv / 4;
+}
+constexpr uint32_t kWarpStageDoubles = team_stage_doubles<32>();  // 1,440 doubles = 11,520 bytes per warp
+template <int TEAM>
+__device__ __forceinline__ void team_sync() {
+    if (TEAM == 32) __syncwarp();
+    else if (TEAM > 32) __syncthreads();
+}
 
-// ---- one work item of a factorisation level -----------------------------------------------------------------
-// Entry item (i, j): L[i][j] = (A[i][j] - sum_k L[i][k] L[j][k]) / L[j][j], k ascending over the columns present
-// in both rows (static masks), with column j's pivot recomputed from row j (same operations, same order as the
-// column item) so that entries and pivots of a level need no barrier between them.
-__device__ __noinline__ void factor_entry_thread(const LargeArgs& a, uint32_t e) {
-    double* lv = a.vg + a.L0;
-    const uint32_t i = __ldg(a.ent_row + e), j = __ldg(a.ent_col + e), s = __ldg(a.ent_slot + e) & ~kEntryInA;
-    const uint32_t mp = __ldg(a.ent_mask_ptr + e);
-    const uint32_t ri0 = __ldg(a.lr_ptr + i), rj0 = __ldg(a.lr_ptr + j), len_j = __ldg(a.lr_ptr + j + 1) - rj0;
-    const uint32_t wj = (len_j + 31) >> 5;
-    double acc = lv[s], piv = a.vg[a.DG0 + j];
-    const double* rowj = lv + rj0;
-    const double* rowi = lv + ri0;
-    uint32_t n_match = 0;
-    for (uint32_t q = 0; q < wj; ++q) n_match += __popc(__ldg(a.ent_mask + mp + q));
-    BitWalk bj, bi;
-    if (n_match) {
-        bj.init(a.ent_mask + mp);
-        bi.init(a.ent_mask + mp + wj);
+
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t* smem_dst, const uint32_t* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// One update of panel P (w columns) by a block B of a descendant panel (T rows x wK columns; its first nc rows are
+// columns of P's supernode, rel[] = where each row lands in P): P[i][j] = fma(-B[i][k], B[j][k], P[i][j]) for the row
+// pairs i >= j with j among the first nc, k ascending; and the forward substitution of those nc rows against yK = y of
+// the descendant's columns.
+template <int TEAM>
+__device__ __forceinline__ void sn_apply_update(double* P, uint32_t w, double* ys, const double* yK, const double* B, const uint32_t* rel,
+                                                uint32_t T, uint32_t wK, uint32_t nc, uint32_t lane) {
+    for (uint32_t p = lane; p < nc * T; p += TEAM) {
+        const uint32_t tj = p / T, ti = p - tj * T;
+        if (ti < tj) continue;
+        double* dst = P + rel[ti] * w + rel[tj];
+        double acc = *dst;
+        for (uint32_t k = 0; k < wK; ++k) acc = __fma_rn(-B[ti * wK + k], B[tj * wK + k], acc);
+        *dst = acc;
     }
-    // the two chains advance together, one batch of independent loads per step
-    uint32_t t = 0, q = 0;
-    while (t + kBatch <= len_j || q + kBatch <= n_match) {
-        const bool do_p = t + kBatch <= len_j, do_m = q + kBatch <= n_match;
-        double v[kBatch], vi[kBatch], vj[kBatch];
-        if (do_p) {
-#pragma unroll
-            for (int u = 0; u < kBatch; ++u) v[u] = rowj[t + u];
+    for (uint32_t tj = lane; tj < nc; tj += TEAM) {
+        const uint32_t c = rel[tj];
+        double acc = ys[c];
+        for (uint32_t k = 0; k < wK; ++k) acc = __fma_rn(-B[tj * wK + k], yK[k], acc);
+        ys[c] = acc;
+    }
+}
+
+// Factorisation of one supernode J fused with the forward substitution of its columns, by a team of TEAM threads
+// (`lane` = index in the team, `stage` = the team's shared memory).  Left-looking, k ascending everywhere — the
+// arithmetic of the column algorithm:
+//   1. external updates, descendants K ascending: P[i][j] = fma(-L[i][k], L[j][k], P[i][j]) over K's columns k,
+//      for every pair of K's rows (i >= j) with j a column of J;  y[j] = fma(-L[j][k], y[k], y[j]);
+//   2. the panel's own columns c ascending: the same fma chains over the columns k < c of the panel, pivot
+//      (fails unless > 0 and finite), 1/pivot, scaling, and y[c].
+template <int TEAM>
+__device__ __noinline__ void sn_factor(const LargeArgs& a, uint32_t pos, uint32_t lane, double* stage) {
+    using Caps = TeamCaps<TEAM>;
+    double* lv = a.vg + a.L0;
+    double* y = a.vg + a.Y0;
+    const uint4 hdr = __ldg(reinterpret_cast<const uint4*>(a.stage_rec) + 2 * (size_t)pos);        // j0, w, h, rows
+    const uint4 hdr2 = __ldg(reinterpret_cast<const uint4*>(a.stage_rec) + 2 * (size_t)pos + 1);   // panel, first update, updates
+    const uint32_t j0 = hdr.x, w = hdr.y, h = hdr.z;
+    double* G = lv + hdr2.x;
+    const bool staged = TEAM > 1 && h * w <= Caps::panel;
+    double* P = staged ? stage : G;
+    double* kb = TEAM > 1 ? stage + Caps::panel : nullptr;
+    double* ys = TEAM > 1 ? stage + Caps::panel + Caps::block : y + j0;  // w <= 16 values
+    uint32_t* srec = TEAM > 1 ? reinterpret_cast<uint32_t*>(stage + Caps::panel + Caps::block + kYCap) : nullptr;
+    uint32_t* srel = TEAM > 1 ? srec + Caps::recs * 8 : nullptr;
+    uint16_t* inv = TEAM > 1 ? reinterpret_cast<uint16_t*>(srel + Caps::rel) : nullptr;
+    if (TEAM > 1) {
+        if (staged)
+            for (uint32_t t = lane; t < h * w; t += TEAM) P[t] = G[t];
+        for (uint32_t c = lane; c < w; c += TEAM) ys[c] = y[j0 + c];
+        team_sync<TEAM>();
+    }
+    // ---- 1. external updates
+    const uint32_t ub = hdr2.y, ue = hdr2.y + hdr2.z;
+    if (TEAM > 1) {
+        for (uint32_t u0 = ub; u0 < ue;) {
+            // The records of the next (up to 32) updates go to shared memory; then a chunk of consecutive updates
+            // whose blocks and relative positions fit the stage is fetched with asynchronous copies that are all in
+            // flight together (one memory round trip per chunk instead of several per update).
+            const uint32_t avail = min(Caps::recs, ue - u0);
+            for (uint32_t q = lane; q < avail * 8; q += TEAM) srec[q] = __ldg(a.upd_rec + 8 * (size_t)u0 + q);
+            team_sync<TEAM>();
+            uint32_t cnt = 0, tot_b = 0, tot_r = 0;
+            while (cnt < avail) {
+                const uint32_t* r = srec + 8 * cnt;
+                const uint32_t T = r[1], wK = r[2] & 0xffu, len = T * wK;
+                if (tot_b + len + wK > Caps::block || tot_r + T > Caps::rel || (cnt + 1) * h > Caps::inv || T >= 0xffffu) break;
+                for (uint32_t q = lane; q < len; q += TEAM) cp_async8(kb + tot_b + q, lv + r[0] + q);
+                for (uint32_t q = lane; q < wK; q += TEAM) cp_async8(kb + tot_b + len + q, y + r[4] + q);  // y of K's columns
+                for (uint32_t q = lane; q < T; q += TEAM) cp_async4(srel + tot_r + q, a.upd_rel + r[3] + q);
+                tot_b += len + wK;
+                tot_r += T;
+                ++cnt;
+            }
+            if (cnt == 0) {
+                // an update too large for the stage: pair by pair, straight from global memory
+                const uint32_t* r = srec;
+                const uint32_t T = r[1], wK = r[2] & 0xffu, nc = r[2] >> 8;
+                sn_apply_update<TEAM>(P, w, ys, y + r[4], lv + r[0], a.upd_rel + r[3], T, wK, nc, lane);
+                team_sync<TEAM>();
+                u0 += 1;
+                continue;
+            }
+            // inverse maps: inv[i * h + (panel row)] = position of that row in update i's block, 0xffff when absent
+            for (uint32_t q = lane; q < cnt * h; q += TEAM) inv[q] = 0xffffu;
+            cp_async_wait_all();
+            team_sync<TEAM>();
+            for (uint32_t i = 0, roff = 0; i < cnt; ++i) {
+                const uint32_t T = srec[8 * i + 1];
+                for (uint32_t t = lane; t < T; t += TEAM) inv[i * h + srel[roff + t]] = (uint16_t)t;
+                roff += T;
+            }
+            team_sync<TEAM>();
+            // Every panel entry is owned by one thread, which applies the chunk's updates to it in order: no barrier
+            // between updates, no index comparisons (r >= c implies the block positions satisfy ti >= tj).
+            for (uint32_t e = lane; e < h * w; e += TEAM) {
+                const uint32_t r = e / w, c = e - r * w;
+                if (c > r) continue;
+                double acc = P[e];
+                for (uint32_t i = 0, boff = 0; i < cnt; ++i) {
+                    const uint32_t T = srec[8 * i + 1], z = srec[8 * i + 2], wK = z & 0xffu;
+                    const uint32_t ti = inv[i * h + r], tj = inv[i * h + c];
+                    if (ti != 0xffffu && tj < (z >> 8)) {
+                        const double* bi = kb + boff + ti * wK;
+                        const double* bj = kb + boff + tj * wK;
+                        for (uint32_t k = 0; k < wK; ++k) acc = __fma_rn(-bi[k], bj[k], acc);
+                    }
+                    boff += T * wK + wK;
+                }
+                P[e] = acc;
+            }
+            for (uint32_t c = lane; c < w; c += TEAM) {  // forward substitution of the panel's columns against y of the descendants'
+                double acc = ys[c];
+                for (uint32_t i = 0, boff = 0; i < cnt; ++i) {
+                    const uint32_t T = srec[8 * i + 1], z = srec[8 * i + 2], wK = z & 0xffu;
+                    const uint32_t tj = inv[i * h + c];
+                    if (tj < (z >> 8)) {
+                        const double* bj = kb + boff + tj * wK;
+                        const double* yK = kb + boff + T * wK;
+                        for (uint32_t k = 0; k < wK; ++k) acc = __fma_rn(-bj[k], yK[k], acc);
+                    }
+                    boff += T * wK + wK;
+                }
+                ys[c] = acc;
+            }
+            team_sync<TEAM>();
+            u0 += cnt;
         }
-        if (do_m) {
-#pragma unroll
-            for (int u = 0; u < kBatch; ++u) {
-                vi[u] = rowi[bi.next()];
-                vj[u] = rowj[bj.next()];
+    } else {
+        for (uint32_t u = ub; u < ue; ++u) {
+            const uint32_t* r = a.upd_rec + 8 * (size_t)u;
+            const uint32_t T = __ldg(r + 1), z = __ldg(r + 2);
+            sn_apply_update<1>(P, w, ys, y + __ldg(r + 4), lv + __ldg(r), a.upd_rel + __ldg(r + 3), T, z & 0xffu, z >> 8, 0);
+        }
+    }
+    // ---- 2. the panel's own columns
+    for (uint32_t c = 0; c < w; ++c) {
+        for (uint32_t r = c + lane; r < h; r += TEAM) {
+            double acc = P[r * w + c], piv = P[c * w + c];
+            for (uint32_t k = 0; k < c; ++k) {
+                const double lck = P[c * w + k];
+                piv = __fma_rn(-lck, lck, piv);
+                acc = __fma_rn(-P[r * w + k], lck, acc);
+            }
+            const double rinv = __ddiv_rn(1.0, __dsqrt_rn(piv));
+            if (r == c) {
+                if (!(piv > 0.0) || !ezm::ez_isfinite(piv)) a.ctrl->fail = 1;
+                a.vg[a.RV0 + j0 + c] = rinv;
+                double ay = ys[c];
+                for (uint32_t k = 0; k < c; ++k) ay = __fma_rn(-P[c * w + k], ys[k], ay);
+                ys[c] = __dmul_rn(ay, rinv);
+            } else {
+                P[r * w + c] = __dmul_rn(acc, rinv);
             }
         }
-        if (do_p) {
-#pragma unroll
-            for (int u = 0; u < kBatch; ++u) piv = __fma_rn(-v[u], v[u], piv);
-            t += kBatch;
-        }
-        if (do_m) {
-#pragma unroll
-            for (int u = 0; u < kBatch; ++u) acc = __fma_rn(-vi[u], vj[u], acc);
-            q += kBatch;
-        }
+        team_sync<TEAM>();
     }
-    for (; t < len_j; ++t) {
-        const double v = rowj[t];
-        piv = __fma_rn(-v, v, piv);
+    if (TEAM > 1) {
+        if (staged)
+            for (uint32_t t = lane; t < h * w; t += TEAM) G[t] = P[t];
+        for (uint32_t c = lane; c < w; c += TEAM) y[j0 + c] = ys[c];
+        team_sync<TEAM>();
     }
-    for (; q < n_match; ++q) {
-        const double vi = rowi[bi.next()], vj = rowj[bj.next()];
-        acc = __fma_rn(-vi, vj, acc);
-    }
-    const double rinv = __ddiv_rn(1.0, __dsqrt_rn(piv));
-    lv[s] = __dmul_rn(acc, rinv);
 }
 
-// Column item j: pivot -> 1/pivot, and the forward substitution y[j] = (b[j] - sum_k L[j][k] y[k]) / L[j][j].
-__device__ __noinline__ void factor_column_thread(const LargeArgs& a, uint32_t j) {
+// Backward substitution of one supernode (stages descending): for its columns j descending,
+// d[j] = (y[j] - sum_{i > j} L[i][j] d[i]) / L[j][j], rows i ascending (first the panel's own rows, then the rows
+// below); the final value is also scattered to d in variable numbering.  One sequential chain per supernode.
+template <int TEAM>
+__device__ __noinline__ void sn_backward(const LargeArgs& a, uint32_t pos, uint32_t lane, double* stage) {
+    using Caps = TeamCaps<TEAM>;
     const double* lv = a.vg + a.L0;
     double* y = a.vg + a.Y0;
-    const uint32_t rj0 = __ldg(a.lr_ptr + j), len_j = __ldg(a.lr_ptr + j + 1) - rj0;
-    double piv = a.vg[a.DG0 + j], ay = y[j];
-    uint32_t t = 0;
-    for (; t + kBatch <= len_j; t += kBatch) {
-        double v[kBatch], yv[kBatch];
-#pragma unroll
-        for (int u = 0; u < kBatch; ++u) {
-            v[u] = lv[rj0 + t + u];
-            yv[u] = y[__ldg(a.lr_col + rj0 + t + u)];
-        }
-#pragma unroll
-        for (int u = 0; u < kBatch; ++u) {
-            piv = __fma_rn(-v[u], v[u], piv);
-            ay = __fma_rn(-v[u], yv[u], ay);
-        }
+    const uint4 hdr = __ldg(reinterpret_cast<const uint4*>(a.stage_rec) + 2 * (size_t)pos);
+    const uint32_t j0 = hdr.x, w = hdr.y, h = hdr.z, rb = hdr.w;
+    const double* G = lv + __ldg(a.stage_rec + 8 * (size_t)pos + 4);
+    const bool staged = TEAM > 1 && h * w <= Caps::panel && h <= Caps::block;
+    const double* P = G;
+    double* dv = nullptr;  // d of the panel's rows (own columns: being computed; below: final), staged variant only
+    if (staged) {
+        double* Ps = stage;
+        dv = stage + Caps::panel;
+        for (uint32_t t = lane; t < h * w; t += TEAM) Ps[t] = G[t];
+        for (uint32_t t = lane; t < h; t += TEAM) dv[t] = y[__ldg(a.sn_rows + rb + t)];
+        P = Ps;
+        team_sync<TEAM>();
     }
-    for (; t < len_j; ++t) {
-        const double l = lv[rj0 + t];
-        piv = __fma_rn(-l, l, piv);
-        ay = __fma_rn(-l, y[__ldg(a.lr_col + rj0 + t)], ay);
-    }
-    if (!(piv > 0.0) || !ezm::ez_isfinite(piv)) a.ctrl->fail = 1;
-    const double rinv = __ddiv_rn(1.0, __dsqrt_rn(piv));
-    a.vg[a.RV0 + j] = rinv;
-    y[j] = __dmul_rn(ay, rinv);
-}
-
-// Backward item: column at position p of the level list, d[j] = (y[j] - sum_{k > j} L[k][j] d[k]) / L[j][j].
-__device__ __noinline__ void backward_column_thread(const LargeArgs& a, uint32_t p) {
-    const double* lv = a.vg + a.L0;
-    double* y = a.vg + a.Y0;
-    const uint32_t j = __ldg(a.lvl_cols + p);
-    double acc = y[j];
-    uint32_t q = __ldg(a.ent_ptr + p);
-    const uint32_t qe = __ldg(a.ent_ptr + p + 1);
-    for (; q + kBatch <= qe; q += kBatch) {
-        double l[kBatch], yv[kBatch];
-#pragma unroll
-        for (int u = 0; u < kBatch; ++u) {
-            l[u] = lv[__ldg(a.ent_slot + q + u) & ~kEntryInA];
-            yv[u] = y[__ldg(a.ent_row + q + u)];
-        }
-#pragma unroll
-        for (int u = 0; u < kBatch; ++u) acc = __fma_rn(-l[u], yv[u], acc);
-    }
-    for (; q < qe; ++q) acc = __fma_rn(-lv[__ldg(a.ent_slot + q) & ~kEntryInA], y[__ldg(a.ent_row + q)], acc);
-    const double v = __dmul_rn(acc, a.vg[a.RV0 + j]);
-    y[j] = v;
-    a.vg[a.D0 + __ldg(a.perm + j)] = v;
-}
-
-// ---- warp-cooperative variants for the upper part of the tree (few items, long rows) ------------------------
-// The 32 lanes stage the rows in shared memory with coalesced loads (one memory round trip instead of one per
-// batch), then lane 0 / lane 1 run the two sequential chains from shared memory.  Rows longer than kRowCap fall
-// back to the thread variant on lane 0.
-constexpr uint32_t kRowCap = 256;
-constexpr uint32_t kWarpStageDoubles = 2 * kRowCap;
-static_assert(kWarpStageDoubles == 512, "one 4 KB stage per warp serves the factor levels and the sum of squares");
-
-__device__ __noinline__ void factor_entry_warp(const LargeArgs& a, uint32_t e, uint32_t lane, double* st) {
-    double* lv = a.vg + a.L0;
-    const uint32_t i = __ldg(a.ent_row + e), j = __ldg(a.ent_col + e), s = __ldg(a.ent_slot + e) & ~kEntryInA;
-    const uint32_t ri0 = __ldg(a.lr_ptr + i), rj0 = __ldg(a.lr_ptr + j), len_j = __ldg(a.lr_ptr + j + 1) - rj0;
-    const uint32_t pre_i = s - ri0;
-    if (len_j > kRowCap || pre_i > kRowCap) {
-        if (lane == 0) factor_entry_thread(a, e);
-        return;
-    }
-    double* sj = st;
-    double* si = st + kRowCap;
-    for (uint32_t t = lane; t < len_j; t += 32) sj[t] = lv[rj0 + t];
-    for (uint32_t t = lane; t < pre_i; t += 32) si[t] = lv[ri0 + t];
-    __syncwarp();
-    double res = 0.0;
     if (lane == 0) {
-        const uint32_t mp = __ldg(a.ent_mask_ptr + e), wj = (len_j + 31) >> 5;
-        uint32_t n_match = 0;
-        for (uint32_t q = 0; q < wj; ++q) n_match += __popc(__ldg(a.ent_mask + mp + q));
-        double acc = lv[s];
-        if (n_match) {
-            BitWalk bj, bi;
-            bj.init(a.ent_mask + mp);
-            bi.init(a.ent_mask + mp + wj);
-            for (uint32_t q = 0; q < n_match; ++q) {
-                const double vi = si[bi.next()], vj = sj[bj.next()];
-                acc = __fma_rn(-vi, vj, acc);
-            }
+        for (uint32_t c = w; c-- > 0;) {
+            double acc = staged ? dv[c] : y[j0 + c];
+            for (uint32_t r = c + 1; r < h; ++r)
+                acc = __fma_rn(-P[r * w + c], staged ? dv[r] : y[__ldg(a.sn_rows + rb + r)], acc);
+            const double v = __dmul_rn(acc, a.vg[a.RV0 + j0 + c]);
+            if (staged) dv[c] = v;
+            y[j0 + c] = v;
+            a.vg[a.D0 + __ldg(a.perm + j0 + c)] = v;
         }
-        res = acc;
-    } else if (lane == 1) {
-        double piv = a.vg[a.DG0 + j];
-        for (uint32_t t = 0; t < len_j; ++t) piv = __fma_rn(-sj[t], sj[t], piv);
-        res = __ddiv_rn(1.0, __dsqrt_rn(piv));
     }
-    const double rinv = __shfl_sync(0xffffffffu, res, 1);
-    if (lane == 0) lv[s] = __dmul_rn(res, rinv);
-    __syncwarp();
+    team_sync<TEAM>();
 }
 
-__device__ __noinline__ void factor_column_warp(const LargeArgs& a, uint32_t j, uint32_t lane, double* st) {
-    const double* lv = a.vg + a.L0;
-    double* y = a.vg + a.Y0;
-    const uint32_t rj0 = __ldg(a.lr_ptr + j), len_j = __ldg(a.lr_ptr + j + 1) - rj0;
-    if (len_j > kRowCap) {
-        if (lane == 0) factor_column_thread(a, j);
-        return;
-    }
-    double* sj = st;
-    double* sy = st + kRowCap;
-    for (uint32_t t = lane; t < len_j; t += 32) {
-        sj[t] = lv[rj0 + t];
-        sy[t] = y[__ldg(a.lr_col + rj0 + t)];
-    }
-    __syncwarp();
-    double res = 0.0;
-    if (lane == 0) {
-        double piv = a.vg[a.DG0 + j];
-        for (uint32_t t = 0; t < len_j; ++t) piv = __fma_rn(-sj[t], sj[t], piv);
-        if (!(piv > 0.0) || !ezm::ez_isfinite(piv)) a.ctrl->fail = 1;
-        res = __ddiv_rn(1.0, __dsqrt_rn(piv));
-    } else if (lane == 1) {
-        double ay = y[j];
-        for (uint32_t t = 0; t < len_j; ++t) ay = __fma_rn(-sj[t], sy[t], ay);
-        res = ay;
-    }
-    const double rinv = __shfl_sync(0xffffffffu, res, 0);
-    if (lane == 0) a.vg[a.RV0 + j] = rinv;
-    if (lane == 1) y[j] = __dmul_rn(res, rinv);
-    __syncwarp();
-}
-
-__device__ __noinline__ void backward_column_warp(const LargeArgs& a, uint32_t p, uint32_t lane, double* st) {
-    const double* lv = a.vg + a.L0;
-    double* y = a.vg + a.Y0;
-    const uint32_t q0 = __ldg(a.ent_ptr + p), len = __ldg(a.ent_ptr + p + 1) - q0;
-    if (len > kRowCap) {
-        if (lane == 0) backward_column_thread(a, p);
-        return;
-    }
-    double* sl = st;
-    double* sy = st + kRowCap;
-    for (uint32_t t = lane; t < len; t += 32) {
-        sl[t] = lv[__ldg(a.ent_slot + q0 + t) & ~kEntryInA];
-        sy[t] = y[__ldg(a.ent_row + q0 + t)];
-    }
-    __syncwarp();
-    if (lane == 0) {
-        const uint32_t j = __ldg(a.lvl_cols + p);
-        double acc = y[j];
-        for (uint32_t t = 0; t < len; ++t) acc = __fma_rn(-sl[t], sy[t], acc);
-        const double v = __dmul_rn(acc, a.vg[a.RV0 + j]);
-        y[j] = v;
-        a.vg[a.D0 + __ldg(a.perm + j)] = v;
-    }
-    __syncwarp();
-}
-
-// One elimination-tree level of the factorisation fused with the forward substitution, run by the thread set
-// (tid, nth) — the whole grid or one CTA.  Work items: the level's sub-diagonal entries and its columns.  Levels
-// with long rows and few items (the upper part of the tree) are run one item per warp.
-__device__ void direct_factor_level(const LargeArgs& a, uint32_t lvl, uint32_t tid, uint32_t nth, double* warp_stage) {
-    const uint32_t pb = __ldg(a.lvl_ptr + lvl), pe = __ldg(a.lvl_ptr + lvl + 1);
-    const uint32_t eb = __ldg(a.ent_ptr + pb), ee = __ldg(a.ent_ptr + pe);
-    const uint32_t n_ent = ee - eb, n_items = n_ent + (pe - pb);
-    const uint32_t n_warps = nth >> 5;
-    if (__ldg(a.lvl_maxrow + lvl) > 24 && n_items <= 2 * n_warps) {
-        const uint32_t lane = threadIdx.x & 31u;
-        for (uint32_t w = tid >> 5; w < n_items; w += n_warps) {
-            if (w < n_ent) factor_entry_warp(a, eb + w, lane, warp_stage);
-            else factor_column_warp(a, __ldg(a.lvl_cols + pb + (w - n_ent)), lane, warp_stage);
-        }
-        return;
-    }
-    for (uint32_t w = tid; w < n_items; w += nth) {
-        if (w < n_ent) factor_entry_thread(a, eb + w);
-        else factor_column_thread(a, __ldg(a.lvl_cols + pb + (w - n_ent)));
+// One stage of the supernode tree, run by the whole grid (or its only CTA).  Tiny panels: one per thread.  The others:
+// one per warp while the stage has more of them than the grid has CTAs, else one per CTA (cta_stage = the CTA's whole
+// dynamic shared memory; warp_stage = this warp's slice of it).  (Four 8-lane teams per warp were measured slower on
+// the bottom stages: diverged teams of one warp execute one after the other.)
+__device__ void direct_factor_stage(const LargeArgs& a, uint32_t st, uint32_t tid, uint32_t nth, double* warp_stage, double* cta_stage) {
+    const uint32_t b0 = __ldg(a.stage_ptr + 2 * st), b1 = __ldg(a.stage_ptr + 2 * st + 1), b2 = __ldg(a.stage_ptr + 2 * st + 2);
+    for (uint32_t k = b0 + tid; k < b1; k += nth) sn_factor<1>(a, k, 0, nullptr);
+    if (b2 - b1 > gridDim.x) {
+        for (uint32_t k = b1 + (tid >> 5); k < b2; k += nth >> 5) sn_factor<32>(a, k, threadIdx.x & 31u, warp_stage);
+    } else {
+        for (uint32_t k = b1 + blockIdx.x; k < b2; k += gridDim.x) sn_factor<512>(a, k, threadIdx.x, cta_stage);
     }
 }
-
-// One level of the backward substitution Lt d = y (levels descending); the final value is also scattered to d
-// in variable numbering.
-__device__ void direct_backward_level(const LargeArgs& a, uint32_t lvl, uint32_t tid, uint32_t nth, double* warp_stage) {
-    const uint32_t pb = __ldg(a.lvl_ptr + lvl), pe = __ldg(a.lvl_ptr + lvl + 1);
-    const uint32_t n_warps = nth >> 5;
-    if (pe - pb <= 2 * n_warps) {
-        const uint32_t lane = threadIdx.x & 31u;
-        for (uint32_t p = pb + (tid >> 5); p < pe; p += n_warps) backward_column_warp(a, p, lane, warp_stage);
-        return;
-    }
-    for (uint32_t p = pb + tid; p < pe; p += nth) backward_column_thread(a, p);
+__device__ void direct_backward_stage(const LargeArgs& a, uint32_t st, uint32_t tid, uint32_t nth, double* warp_stage) {
+    const uint32_t b0 = __ldg(a.stage_ptr + 2 * st), b1 = __ldg(a.stage_ptr + 2 * st + 1), b2 = __ldg(a.stage_ptr + 2 * st + 2);
+    for (uint32_t k = b0 + tid; k < b1; k += nth) sn_backward<1>(a, k, 0, nullptr);
+    for (uint32_t k = b1 + (tid >> 5); k < b2; k += nth >> 5) sn_backward<32>(a, k, threadIdx.x & 31u, warp_stage);
 }
 
+static_assert(team_stage_doubles<512>() <= (512 / 32) * kWarpStageDoubles, "the CTA team's stage must fit the CTA's dynamic shared memory");
 constexpr uint32_t kBlock = 512;
 constexpr uint32_t kSmDoubles = 4096;  // 32 KB staging
 
@@ -720,9 +699,9 @@ __device__ __forceinline__ unsigned long long now_ns() {
     return t;
 }
 
-constexpr size_t kLmDynamicSmem = (kBlock / 32) * kWarpStageDoubles * sizeof(double);  // 64 KB
+constexpr size_t kLmDynamicSmem = (kBlock / 32) * kWarpStageDoubles * sizeof(double);  // 164 KB
 
-__global__ void __launch_bounds__(kBlock) lm_large_kernel(const LargeArgs a) {
+__global__ void __launch_bounds__(kBlock, 1) lm_large_kernel(const LargeArgs a) {
     __shared__ double sm[kSmDoubles];
     extern __shared__ double warp_stage_all[];  // (kBlock / 32) * kWarpStageDoubles, see kLmDynamicSmem
     double* warp_stage = warp_stage_all + (threadIdx.x >> 5) * kWarpStageDoubles;
@@ -796,33 +775,23 @@ __global__ void __launch_bounds__(kBlock) lm_large_kernel(const LargeArgs a) {
         }
         bool fail = false;
         if (!use_cg) {
+            direct_zero(a, tid, nth);
+            sync();
             direct_assemble(a, lambda, tid, nth);
             sync();
             lap(2);
-            for (uint32_t lv = 0; lv < a.solo_level; ++lv) {
+            for (uint32_t st = 0; st < a.n_levels; ++st) {
                 const unsigned long long t0 = a.lvl_ns ? now_ns() : 0ull;
-                direct_factor_level(a, lv, tid, nth, warp_stage);
+                direct_factor_stage(a, st, tid, nth, warp_stage, warp_stage_all);
                 sync();
-                if (a.lvl_ns && tid == 0) a.lvl_ns[2 * lv] += now_ns() - t0;
+                if (a.lvl_ns && tid == 0) a.lvl_ns[2 * st] += now_ns() - t0;
             }
             lap(3);
-            if (a.solo_level < a.n_levels && blockIdx.x == 0) {  // top of the tree: one CTA, CTA-level barriers
-                for (uint32_t lv = a.solo_level; lv < a.n_levels; ++lv) {
-                    direct_factor_level(a, lv, threadIdx.x, blockDim.x, warp_stage);
-                    __syncthreads();
-                }
-                for (uint32_t lv = a.n_levels; lv-- > a.solo_level;) {
-                    direct_backward_level(a, lv, threadIdx.x, blockDim.x, warp_stage);
-                    __syncthreads();
-                }
-            }
-            if (a.solo_level < a.n_levels) sync();
-            lap(4);
-            for (uint32_t lv = a.solo_level; lv-- > 0;) {
+            for (uint32_t st = a.n_levels; st-- > 0;) {
                 const unsigned long long t0 = a.lvl_ns ? now_ns() : 0ull;
-                direct_backward_level(a, lv, tid, nth, warp_stage);
+                direct_backward_stage(a, st, tid, nth, warp_stage);
                 sync();
-                if (a.lvl_ns && tid == 0) a.lvl_ns[2 * lv + 1] += now_ns() - t0;
+                if (a.lvl_ns && tid == 0) a.lvl_ns[2 * st + 1] += now_ns() - t0;
             }
             lap(5);
             fail = ctrl->fail != 0;
@@ -1057,9 +1026,7 @@ struct LargeDevice {
     KindLayout layout[EZPZ_K_COUNT];
     uint32_t n_slots = 0, n_tiles = 0;
     uint32_t *csr_row_ptr = nullptr, *csr_col_idx = nullptr, *csc_col_ptr = nullptr, *csc_row_idx = nullptr;
-    uint32_t *perm = nullptr, *lr_ptr = nullptr, *lr_col = nullptr, *lvl_ptr = nullptr, *lvl_cols = nullptr, *ent_ptr = nullptr,
-             *ent_row = nullptr, *ent_col = nullptr, *ent_slot = nullptr, *ent_mask_ptr = nullptr, *ent_mask = nullptr,
-             *aent = nullptr, *aprod_ptr = nullptr, *aprod_a = nullptr, *aprod_b = nullptr, *lvl_maxrow = nullptr;
+    uint32_t* direct_tables[11] = {};  // device copies of the LargeProgram arrays of the sparse direct solve
     double *vg = nullptr, *jr = nullptr, *cgv = nullptr, *partials = nullptr, *sumsq = nullptr;
     unsigned long long* lvl_ns = nullptr;
     uint8_t* side = nullptr;
@@ -1172,22 +1139,9 @@ int32_t get_large(ezpz_context* ctx, const ezpz_structure* s, DeviceCopy* dc, La
     EZ_TRY(upload(&L->csc_col_ptr, s->csc_col_ptr, detail));
     EZ_TRY(upload(&L->csc_row_idx, s->csc_row_idx, detail));
     if (P.direct) {
-        EZ_TRY(upload(&L->perm, P.perm, detail));
-        EZ_TRY(upload(&L->lr_ptr, P.lr_ptr, detail));
-        EZ_TRY(upload(&L->lr_col, P.lr_col, detail));
-        EZ_TRY(upload(&L->lvl_ptr, P.lvl_ptr, detail));
-        EZ_TRY(upload(&L->lvl_cols, P.lvl_cols, detail));
-        EZ_TRY(upload(&L->ent_ptr, P.ent_ptr, detail));
-        EZ_TRY(upload(&L->ent_row, P.ent_row, detail));
-        EZ_TRY(upload(&L->ent_col, P.ent_col, detail));
-        EZ_TRY(upload(&L->ent_slot, P.ent_slot, detail));
-        EZ_TRY(upload(&L->ent_mask_ptr, P.ent_mask_ptr, detail));
-        EZ_TRY(upload(&L->ent_mask, P.ent_mask, detail));
-        EZ_TRY(upload(&L->aent, P.aent, detail));
-        EZ_TRY(upload(&L->aprod_ptr, P.aprod_ptr, detail));
-        EZ_TRY(upload(&L->aprod_a, P.aprod_a, detail));
-        EZ_TRY(upload(&L->aprod_b, P.aprod_b, detail));
-        EZ_TRY(upload(&L->lvl_maxrow, P.lvl_maxrow, detail));
+        const std::vector<uint32_t>* src[11] = {&P.perm, &P.sn_rows, &P.upd_rel, &P.upd_rec, &P.stage_ptr, &P.stage_rec, &P.aent_slot,
+                                                &P.aprod_ptr, &P.aprod_a, &P.aprod_b, &P.diag_slot};
+        for (int k = 0; k < 11; ++k) EZ_TRY(upload(&L->direct_tables[k], *src[k], detail));
     }
     const size_t nnz = s->csc_row_idx.size();
     EZ_CUDA(cudaMalloc(&L->vg, sizeof(double) * std::max<size_t>(1, P.VG)), "cudaMalloc(vg)");
@@ -1242,23 +1196,11 @@ void fill_args(LargeArgs& a, const ezpz_structure* s, const DeviceCopy* dc, cons
     a.csc_col_ptr = L->csc_col_ptr;
     a.csc_row_idx = L->csc_row_idx;
     a.csc_to_csr = dc->csc_to_csr;
-    a.perm = L->perm;
-    a.lr_ptr = L->lr_ptr;
-    a.lr_col = L->lr_col;
-    a.lvl_ptr = L->lvl_ptr;
-    a.lvl_cols = L->lvl_cols;
-    a.ent_ptr = L->ent_ptr;
-    a.ent_row = L->ent_row;
-    a.ent_col = L->ent_col;
-    a.ent_slot = L->ent_slot;
-    a.ent_mask_ptr = L->ent_mask_ptr;
-    a.ent_mask = L->ent_mask;
-    a.aent = L->aent;
-    a.aprod_ptr = L->aprod_ptr;
-    a.aprod_a = L->aprod_a;
-    a.aprod_b = L->aprod_b;
-    a.lvl_maxrow = L->lvl_maxrow;
-    a.n_aent = (uint32_t)P.aent.size();
+    {
+        const uint32_t** dst[11] = {&a.perm, &a.sn_rows, &a.upd_rel, &a.upd_rec, &a.stage_ptr, &a.stage_rec, &a.aent_slot, &a.aprod_ptr,
+                                    &a.aprod_a, &a.aprod_b, &a.diag_slot};
+        for (int k = 0; k < 11; ++k) *dst[k] = L->direct_tables[k];
+    }
     a.sumsq = L->sumsq;
     a.lvl_ns = L->lvl_ns;
     a.vg = L->vg;
@@ -1280,14 +1222,13 @@ void fill_args(LargeArgs& a, const ezpz_structure* s, const DeviceCopy* dc, cons
     a.m = s->m;
     a.nnz = (uint32_t)s->csc_row_idx.size();
     a.n_levels = P.n_levels;
-    a.solo_level = P.solo_level;
     a.nnz_l = P.nnz_l;
+    a.n_aent = (uint32_t)P.aent_slot.size();
     a.X0 = P.X0;
     a.R0 = P.R0;
     a.RN0 = P.RN0;
     a.J0 = P.J0;
     a.L0 = P.L0;
-    a.DG0 = P.DG0;
     a.RV0 = P.RV0;
     a.Y0 = P.Y0;
     a.D0 = P.D0;
@@ -1301,10 +1242,10 @@ namespace ezs {
 void release_large(DeviceCopy* d) {
     LargeDevice* L = (LargeDevice*)d->large;
     if (!L) return;
-    void* ptrs[] = {L->recs, L->tiles, L->slot_orig, L->side_flags, L->csr_row_ptr, L->csr_col_idx, L->csc_col_ptr, L->csc_row_idx, L->perm, L->lr_ptr, L->lr_col,
-                    L->lvl_ptr, L->lvl_cols, L->ent_ptr, L->ent_row, L->ent_col, L->ent_slot, L->ent_mask_ptr, L->ent_mask, L->aent,
-                    L->aprod_ptr, L->aprod_a, L->aprod_b, L->lvl_maxrow, L->vg, L->jr, L->cgv,
-                    L->partials, L->sumsq, L->lvl_ns, L->side, L->degen, L->unsat, L->ctrl};
+    void* ptrs[] = {L->recs, L->tiles, L->slot_orig, L->side_flags, L->csr_row_ptr, L->csr_col_idx, L->csc_col_ptr, L->csc_row_idx,
+                    L->vg, L->jr, L->cgv, L->partials, L->sumsq, L->lvl_ns, L->side, L->degen, L->unsat, L->ctrl};
+    for (uint32_t* p : L->direct_tables)
+        if (p) cudaFree(p);
     for (void* p : ptrs)
         if (p) cudaFree(p);
     delete L;
@@ -1381,16 +1322,15 @@ int32_t solve_large(ezpz_context* ctx, const ezpz_structure* s, const ezpz_confi
         std::vector<unsigned long long> t(2 * (size_t)a.n_levels);
         cudaMemcpy(t.data(), a.lvl_ns, sizeof(unsigned long long) * t.size(), cudaMemcpyDeviceToHost);
         const LargeProgram& P = s->large;
-        for (uint32_t l = 0; l < a.solo_level; ++l)
-            std::fprintf(stderr, "  level %3u cols %7u entries %8u maxrow %4u  factor %8.1f us  backward %8.1f us (all iterations)\n", l,
-                         P.lvl_ptr[l + 1] - P.lvl_ptr[l], P.ent_ptr[P.lvl_ptr[l + 1]] - P.ent_ptr[P.lvl_ptr[l]], P.lvl_maxrow[l],
-                         t[2 * l] * 1e-3, t[2 * l + 1] * 1e-3);
+        for (uint32_t l = 0; l < a.n_levels; ++l)
+            std::fprintf(stderr, "  stage %3u panels %7u  factor %8.1f us  backward %8.1f us (all iterations)\n", l,
+                         P.stage_ptr[2 * l + 2] - P.stage_ptr[2 * l], t[2 * l] * 1e-3, t[2 * l + 1] * 1e-3);
         cudaMemset(a.lvl_ns, 0, sizeof(unsigned long long) * t.size());
     }
     if (dbg && dbg[0] == '1')
         std::fprintf(stderr,
-                     "[lm_large_kernel] grid %d x %u  it %u  us: eval %.1f  sums/max %.1f  A+rhs %.1f  factor(grid) %.1f  "
-                     "top-of-tree(1 CTA) %.1f  backward(grid) %.1f  pcg %.1f  total %.1f\n",
+                     "[lm_large_kernel] grid %d x %u  it %u  us: eval %.1f  sums/max %.1f  A+rhs %.1f  factor stages %.1f  "
+                     "(unused) %.1f  backward stages %.1f  pcg %.1f  total %.1f\n",
                      L->grid, kBlock, h.iterations, h.t[0] * 1e-3, h.t[1] * 1e-3, h.t[2] * 1e-3, h.t[3] * 1e-3, h.t[4] * 1e-3,
                      h.t[5] * 1e-3, h.t[6] * 1e-3, h.t[7] * 1e-3);
     *io->iterations = h.iterations;

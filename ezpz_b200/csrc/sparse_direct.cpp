@@ -26,7 +26,6 @@
 #include <cstdio>
 #include <cstdlib>
 #include <numeric>
-#include <thread>
 #include <vector>
 
 #include "structure.h"
@@ -39,8 +38,8 @@ constexpr uint32_t kNone = UINT32_MAX;
 constexpr uint32_t kNaturalMaxHeight = 192;     // natural order is kept when its elimination tree is this shallow
 constexpr uint32_t kLeafVars = 48;              // dissection stops at parts of this many variables
 constexpr uint64_t kMaxFactorEntries = 1ull << 29;  // beyond this nnz(L) the PCG path is used
-constexpr uint32_t kSoloEntries = 32;           // a level with at most this many work items is run by one CTA (its
-                                                // 16 warps take one or two items each), sparing a grid barrier
+constexpr uint32_t kMaxPanelWidth = 16;         // columns per supernode panel
+constexpr uint32_t kLanePanel = 8;              // panels of at most this many doubles are factorised by a single thread
 
 struct Graph {
     std::vector<uint32_t> ptr, adj;  // symmetric adjacency without self loops
@@ -283,134 +282,216 @@ void build_sparse_direct(ezpz_structure& S) {
             }
         }
     }
-    const uint32_t nnz_l = (uint32_t)lc_row.size();
+    const size_t nnz_l_true = lc_row.size();
 
-    // ---- 4. L by rows (value order), level-ordered column work lists --------------------------------
-    P.lr_ptr.assign((size_t)n + 1, 0);
-    for (uint32_t q = 0; q < nnz_l; ++q) P.lr_ptr[lc_row[q] + 1]++;
-    for (uint32_t i = 0; i < n; ++i) P.lr_ptr[i + 1] += P.lr_ptr[i];
-    P.lr_col.resize(nnz_l);
-    std::vector<uint32_t> slot_of(nnz_l);  // CSC entry -> position in row order
-    {
-        std::vector<uint32_t> cur(P.lr_ptr.begin(), P.lr_ptr.end() - 1);
-        for (uint32_t j = 0; j < n; ++j)  // columns ascending => every row fills with ascending columns
-            for (uint32_t q = lc_ptr[j]; q < lc_ptr[j + 1]; ++q) {
-                const uint32_t pos = cur[lc_row[q]]++;
-                P.lr_col[pos] = j;
-                slot_of[q] = pos;
-            }
+    // ---- 4. supernodes: maximal chains of the elimination tree, at most kMaxPanelWidth columns -------
+    // Column j + 1 continues column j's supernode when j's parent is j + 1 and j + 1 has no other child: along such
+    // a chain struct(L_{j+1}) contains struct(L_j) \ {j + 1}, so the columns share (almost) one row structure and
+    // are factorised as ONE dense panel: rows = the supernode's own columns followed by the union of the
+    // sub-diagonal structures (entries the true factor does not have are explicit zeros; they stay exactly zero
+    // and contribute fma(-0, x, acc) = acc, so the values of the true entries do not change).
+    std::vector<uint32_t> n_child(n, 0);
+    for (uint32_t j = 0; j < n; ++j)
+        if (parent[j] != kNone) n_child[parent[j]]++;
+    // Relaxed: column j also continues the supernode of its child j - 1 when it has further children in other
+    // subtrees (their rows become explicit zeros in the earlier columns of the panel): fewer, wider panels and a
+    // lower supernode tree.  EZPZ_B200_STRICT_SUPERNODES=1 keeps the strict chains.
+    const char* strict = std::getenv("EZPZ_B200_STRICT_SUPERNODES");
+    const bool relax = !(strict && strict[0] == '1');
+    P.sn_ptr.assign(1, 0u);
+    for (uint32_t j = 1; j < n; ++j) {
+        const bool chain = parent[j - 1] == j && (n_child[j] == 1 || relax) && j - P.sn_ptr.back() < kMaxPanelWidth;
+        if (!chain) P.sn_ptr.push_back(j);
     }
-    P.lvl_ptr.assign((size_t)n_levels + 1, 0);
-    for (uint32_t j = 0; j < n; ++j) P.lvl_ptr[level[j] + 1]++;
-    for (uint32_t l = 0; l < n_levels; ++l) P.lvl_ptr[l + 1] += P.lvl_ptr[l];
-    P.lvl_cols.resize(n);
+    P.sn_ptr.push_back(n);
+    const uint32_t n_sn = (uint32_t)P.sn_ptr.size() - 1;
+    std::vector<uint32_t> sn_of(n);
+    for (uint32_t s = 0; s < n_sn; ++s)
+        for (uint32_t j = P.sn_ptr[s]; j < P.sn_ptr[s + 1]; ++j) sn_of[j] = s;
+    // panel rows: own columns, then the sorted union of the columns' sub-diagonal rows outside the supernode
+    P.sn_row_ptr.assign((size_t)n_sn + 1, 0);
+    P.sn_rows.clear();
+    P.panel_off.assign((size_t)n_sn + 1, 0);
     {
-        std::vector<uint32_t> cur(P.lvl_ptr.begin(), P.lvl_ptr.end() - 1);
-        for (uint32_t j = 0; j < n; ++j) P.lvl_cols[cur[level[j]]++] = j;
+        std::vector<uint32_t> mark(n, kNone), below;
+        uint64_t off = 0;
+        for (uint32_t s = 0; s < n_sn; ++s) {
+            const uint32_t j0 = P.sn_ptr[s], j1 = P.sn_ptr[s + 1];
+            below.clear();
+            for (uint32_t j = j0; j < j1; ++j)
+                for (uint32_t q = lc_ptr[j]; q < lc_ptr[j + 1]; ++q) {
+                    const uint32_t i = lc_row[q];
+                    if (i >= j1 && mark[i] != s) {
+                        mark[i] = s;
+                        below.push_back(i);
+                    }
+                }
+            std::sort(below.begin(), below.end());
+            for (uint32_t j = j0; j < j1; ++j) P.sn_rows.push_back(j);
+            P.sn_rows.insert(P.sn_rows.end(), below.begin(), below.end());
+            P.sn_row_ptr[s + 1] = (uint32_t)P.sn_rows.size();
+            P.panel_off[s] = (uint32_t)off;
+            off += (uint64_t)(j1 - j0) * (j1 - j0 + below.size());
+            if (off > kMaxFactorEntries) return;  // leave P.direct false: PCG path
+        }
+        P.panel_off[n_sn] = (uint32_t)off;
     }
-    P.ent_ptr.assign((size_t)n + 1, 0);
-    P.ent_row.resize(nnz_l);
-    P.ent_col.resize(nnz_l);
-    P.ent_slot.resize(nnz_l);
+    const uint32_t nnz_l = P.panel_off[n_sn];  // doubles of panel storage (explicit zeros included)
+    auto panel_h = [&](uint32_t s) { return P.sn_row_ptr[s + 1] - P.sn_row_ptr[s]; };
+    auto panel_w = [&](uint32_t s) { return P.sn_ptr[s + 1] - P.sn_ptr[s]; };
+    bool inconsistent = false;  // a row that should be in a panel is not: never expected; falls back to the PCG path
+    auto pos_in = [&](uint32_t s, uint32_t row) {  // position of a global row in supernode s's row list
+        const uint32_t* b = P.sn_rows.data() + P.sn_row_ptr[s];
+        const uint32_t* e = P.sn_rows.data() + P.sn_row_ptr[s + 1];
+        const uint32_t* it = std::lower_bound(b + panel_w(s), e, row);  // only used for rows below the diagonal block
+        if (it == e || *it != row) {
+            inconsistent = true;
+            return 0u;
+        }
+        return (uint32_t)(it - b);
+    };
+    // ---- 5. update lists: which descendant supernodes K update supernode J, and where K's rows land in J ----
+    // K's rows below its own columns, grouped by the supernode that owns them: every group is one (J <- K) update;
+    // the rows of K from the group's start to the end of K's list all lie inside J's panel (elimination tree).
     {
-        uint32_t run = 0;
-        for (uint32_t p = 0; p < n; ++p) {
-            const uint32_t j = P.lvl_cols[p];
-            P.ent_ptr[p] = run;
-            for (uint32_t q = lc_ptr[j]; q < lc_ptr[j + 1]; ++q, ++run) {
-                P.ent_row[run] = lc_row[q];
-                P.ent_col[run] = j;
-                P.ent_slot[run] = slot_of[q] | (lc_in_a[q] ? kEntryInA : 0u);
+        std::vector<std::vector<uint32_t>> upd(n_sn);  // per J: indices into the flat update arrays
+        std::vector<uint32_t> uK, uB, uC;
+        for (uint32_t K = 0; K < n_sn; ++K) {
+            const uint32_t rb = P.sn_row_ptr[K], w = panel_w(K), h = panel_h(K);
+            uint32_t t = w;
+            while (t < h) {
+                const uint32_t J = sn_of[P.sn_rows[rb + t]];
+                uint32_t t2 = t;
+                while (t2 < h && sn_of[P.sn_rows[rb + t2]] == J) ++t2;
+                upd[J].push_back((uint32_t)uK.size());
+                uK.push_back(K);
+                uB.push_back(t);
+                uC.push_back(t2 - t);
+                t = t2;
             }
         }
-        P.ent_ptr[n] = run;
-    }
-    P.lvl_maxrow.assign(n_levels, 0);
-    for (uint32_t l = 0; l < n_levels; ++l)
-        for (uint32_t p = P.lvl_ptr[l]; p < P.lvl_ptr[l + 1]; ++p)
-            P.lvl_maxrow[l] = std::max(P.lvl_maxrow[l], P.lr_ptr[P.lvl_cols[p] + 1] - P.lr_ptr[P.lvl_cols[p]]);
-    // first level from which every remaining level is small enough for one CTA
-    P.solo_level = n_levels;
-    while (P.solo_level > 0) {
-        const uint32_t l = P.solo_level - 1;
-        const uint64_t items = (uint64_t)(P.lvl_ptr[l + 1] - P.lvl_ptr[l]) + (P.ent_ptr[P.lvl_ptr[l + 1]] - P.ent_ptr[P.lvl_ptr[l]]);
-        if (items > kSoloEntries) break;
-        --P.solo_level;
-    }
-    // static row intersections (see structure.h), built in parallel over entries
-    {
-        P.ent_mask_ptr.assign((size_t)nnz_l + 1, 0);
-        uint64_t words = 0;
-        for (uint32_t e = 0; e < nnz_l; ++e) {
-            const uint32_t i = P.ent_row[e], j = P.ent_col[e], s = P.ent_slot[e] & ~kEntryInA;
-            P.ent_mask_ptr[e] = (uint32_t)words;
-            words += (P.lr_ptr[j + 1] - P.lr_ptr[j] + 31) / 32 + (s - P.lr_ptr[i] + 31) / 32;
-            if (words >= 0xffffffffull) return;  // 32-bit offsets: leave P.direct false (PCG path)
-        }
-        P.ent_mask_ptr[nnz_l] = (uint32_t)words;
-        P.ent_mask.assign(words, 0u);
-        auto fill = [&](uint32_t e0, uint32_t e1) {
-            for (uint32_t e = e0; e < e1; ++e) {
-                const uint32_t i = P.ent_row[e], j = P.ent_col[e], s = P.ent_slot[e] & ~kEntryInA;
-                const uint32_t rj0 = P.lr_ptr[j], len_j = P.lr_ptr[j + 1] - rj0, ri0 = P.lr_ptr[i], pre_i = s - ri0;
-                uint32_t* mj = P.ent_mask.data() + P.ent_mask_ptr[e];
-                uint32_t* mi = mj + (len_j + 31) / 32;
-                uint32_t a = 0, b = 0;
-                while (a < pre_i && b < len_j) {
-                    const uint32_t ca = P.lr_col[ri0 + a], cb = P.lr_col[rj0 + b];
-                    if (ca == cb) {
-                        mi[a >> 5] |= 1u << (a & 31);
-                        mj[b >> 5] |= 1u << (b & 31);
-                        ++a;
-                        ++b;
-                    } else if (ca < cb) ++a;
-                    else ++b;
+        P.upd_ptr.assign((size_t)n_sn + 1, 0);
+        P.upd_sn.clear();
+        P.upd_rbegin.clear();
+        P.upd_ncols.clear();
+        P.upd_rel_ptr.clear();
+        P.upd_rel.clear();
+        for (uint32_t J = 0; J < n_sn; ++J) {
+            const uint32_t j0 = P.sn_ptr[J];
+            for (uint32_t u : upd[J]) {  // ascending K by construction
+                const uint32_t K = uK[u], rb = P.sn_row_ptr[K], h = panel_h(K);
+                P.upd_sn.push_back(K);
+                P.upd_rbegin.push_back(uB[u]);
+                P.upd_ncols.push_back(uC[u]);
+                P.upd_rel_ptr.push_back((uint32_t)P.upd_rel.size());
+                for (uint32_t t = uB[u]; t < h; ++t) {
+                    const uint32_t row = P.sn_rows[rb + t];
+                    P.upd_rel.push_back(t < uB[u] + uC[u] ? row - j0 : pos_in(J, row));
                 }
             }
-        };
-        const uint32_t nt = nnz_l < (1u << 16) ? 1u : std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
-        if (nt == 1) fill(0, nnz_l);
-        else {
-            std::vector<std::thread> pool;
-            for (uint32_t t = 0; t < nt; ++t)
-                pool.emplace_back(fill, (uint32_t)((uint64_t)nnz_l * t / nt), (uint32_t)((uint64_t)nnz_l * (t + 1) / nt));
-            for (auto& th : pool) th.join();
+            P.upd_ptr[J + 1] = (uint32_t)P.upd_sn.size();
+        }
+        P.upd_rel_ptr.push_back((uint32_t)P.upd_rel.size());
+        // where each update's block of K's panel lives: rows upd_rbegin.. to the end, all w_K columns, contiguous
+        // one 32-byte record per update, what the device reads: {block start slot, T = rows in the block, w_K | ncols << 8,
+        // offset of the relative positions, first column of K, 0, 0, 0}
+        P.upd_rec.assign(P.upd_sn.size() * 8, 0u);
+        for (size_t u = 0; u < P.upd_sn.size(); ++u) {
+            const uint32_t K = P.upd_sn[u];
+            uint32_t* r = P.upd_rec.data() + u * 8;
+            r[0] = P.panel_off[K] + P.upd_rbegin[u] * panel_w(K);
+            r[1] = panel_h(K) - P.upd_rbegin[u];
+            r[2] = panel_w(K) | (P.upd_ncols[u] << 8);
+            r[3] = P.upd_rel_ptr[u];
+            r[4] = P.sn_ptr[K];
         }
     }
-    // products of A = JtJ for the entries A itself has
+    // ---- 6. stages: height of every supernode in the supernode tree; small panels and large panels apart ----
+    std::vector<uint32_t> sn_level(n_sn, 0);
+    uint32_t n_stages = 0;
+    for (uint32_t s = 0; s < n_sn; ++s) {
+        n_stages = std::max(n_stages, sn_level[s] + 1);
+        const uint32_t last = P.sn_ptr[s + 1] - 1;
+        if (parent[last] != kNone) {
+            const uint32_t ps = sn_of[parent[last]];
+            sn_level[ps] = std::max(sn_level[ps], sn_level[s] + 1);
+        }
+    }
+    P.stage_ptr.assign((size_t)2 * n_stages + 1, 0);  // per stage: [lane-sized panels | warp-sized panels]
+    auto bucket = [&](uint32_t s) {  // a single thread takes panels of a few doubles that receive at most two updates
+        const bool tiny = panel_h(s) * panel_w(s) <= kLanePanel && P.upd_ptr[s + 1] - P.upd_ptr[s] <= 2;
+        return 2 * sn_level[s] + (tiny ? 0u : 1u);
+    };
+    for (uint32_t s = 0; s < n_sn; ++s) P.stage_ptr[bucket(s) + 1]++;
+    for (uint32_t k = 0; k < 2 * n_stages; ++k) P.stage_ptr[k + 1] += P.stage_ptr[k];
+    P.stage_sn.resize(n_sn);
     {
-        P.aent.clear();
+        std::vector<uint32_t> cur(P.stage_ptr.begin(), P.stage_ptr.end() - 1);
+        for (uint32_t s = 0; s < n_sn; ++s) P.stage_sn[cur[bucket(s)]++] = s;
+    }
+    // one 32-byte record per supernode IN STAGE ORDER (what a team reads first, one memory round trip):
+    // {first column, width, height, offset of its row list, panel offset, first update, number of updates, 0}
+    P.stage_rec.assign((size_t)n_sn * 8, 0u);
+    for (uint32_t k = 0; k < n_sn; ++k) {
+        const uint32_t sn = P.stage_sn[k];
+        uint32_t* r = P.stage_rec.data() + (size_t)k * 8;
+        r[0] = P.sn_ptr[sn];
+        r[1] = panel_w(sn);
+        r[2] = panel_h(sn);
+        r[3] = P.sn_row_ptr[sn];
+        r[4] = P.panel_off[sn];
+        r[5] = P.upd_ptr[sn];
+        r[6] = P.upd_ptr[sn + 1] - P.upd_ptr[sn];
+    }
+    // ---- 7. A = JtJ: products of every entry A has, addressed to its panel slot; diagonal slots ---------------
+    {
+        P.aent_slot.clear();
         P.aprod_ptr.assign(1, 0u);
         P.aprod_a.clear();
         P.aprod_b.clear();
-        for (uint32_t e = 0; e < nnz_l; ++e) {
-            if (!(P.ent_slot[e] & kEntryInA)) continue;
-            const uint32_t ci = perm[P.ent_row[e]], cj = perm[P.ent_col[e]];
-            uint32_t pi = S.csc_col_ptr[ci], pj = S.csc_col_ptr[cj];
-            const uint32_t pie = S.csc_col_ptr[ci + 1], pje = S.csc_col_ptr[cj + 1];
-            while (pi < pie && pj < pje) {
-                const uint32_t ri = S.csc_row_idx[pi], rj = S.csc_row_idx[pj];
-                if (ri == rj) {
-                    P.aprod_a.push_back(pi);
-                    P.aprod_b.push_back(pj);
-                    ++pi;
-                    ++pj;
-                } else if (ri < rj) ++pi;
-                else ++pj;
+        P.diag_slot.resize(n);
+        for (uint32_t j = 0; j < n; ++j) {
+            const uint32_t J = sn_of[j], j0 = P.sn_ptr[J], w = panel_w(J);
+            P.diag_slot[j] = P.panel_off[J] + (j - j0) * w + (j - j0);
+            const uint32_t cj = perm[j];
+            for (uint32_t q = lc_ptr[j]; q < lc_ptr[j + 1]; ++q) {
+                if (!lc_in_a[q]) continue;
+                const uint32_t i = lc_row[q], ci = perm[i];
+                const uint32_t pos = i < P.sn_ptr[J + 1] ? i - j0 : pos_in(J, i);
+                uint32_t pi = S.csc_col_ptr[ci], pj = S.csc_col_ptr[cj];
+                const uint32_t pie = S.csc_col_ptr[ci + 1], pje = S.csc_col_ptr[cj + 1];
+                while (pi < pie && pj < pje) {
+                    const uint32_t ri = S.csc_row_idx[pi], rj = S.csc_row_idx[pj];
+                    if (ri == rj) {
+                        P.aprod_a.push_back(pi);
+                        P.aprod_b.push_back(pj);
+                        ++pi;
+                        ++pj;
+                    } else if (ri < rj) ++pi;
+                    else ++pj;
+                }
+                P.aent_slot.push_back(P.panel_off[J] + pos * w + (j - j0));
+                P.aprod_ptr.push_back((uint32_t)P.aprod_a.size());
             }
-            P.aent.push_back(e);
-            P.aprod_ptr.push_back((uint32_t)P.aprod_a.size());
         }
     }
+    if (inconsistent) {
+        std::fprintf(stderr, "[ezpz_b200] sparse_direct: inconsistent panel structure, using the PCG path\n");
+        return;
+    }
+    n_levels = n_stages;
     if (const char* dbg = std::getenv("EZPZ_B200_DEBUG"); dbg && dbg[0] == '1') {
-        std::fprintf(stderr, "[sparse_direct] n %u nnz_l %u levels %u solo_level %u nested %d\n", n, nnz_l, n_levels,
-                     P.solo_level, (int)P.nested);
-        for (uint32_t l = 0; l < n_levels; ++l) {
-            uint32_t maxrow = 0;
-            for (uint32_t p = P.lvl_ptr[l]; p < P.lvl_ptr[l + 1]; ++p)
-                maxrow = std::max(maxrow, P.lr_ptr[P.lvl_cols[p] + 1] - P.lr_ptr[P.lvl_cols[p]]);
-            std::fprintf(stderr, "  level %u: cols %u entries %u max row length %u\n", l, P.lvl_ptr[l + 1] - P.lvl_ptr[l],
-                         P.ent_ptr[P.lvl_ptr[l + 1]] - P.ent_ptr[P.lvl_ptr[l]], maxrow);
+        std::fprintf(stderr, "[sparse_direct] n %u nested %d supernodes %u stages %u panel doubles %u true nnz(L) %zu updates %zu\n", n,
+                     (int)P.nested, n_sn, n_stages, nnz_l, nnz_l_true, P.upd_sn.size());
+        for (uint32_t st = 0; st < n_stages; ++st) {
+            uint32_t max_h = 0, max_u = 0;
+            for (uint32_t k = P.stage_ptr[2 * st]; k < P.stage_ptr[2 * st + 2]; ++k) {
+                const uint32_t sn = P.stage_sn[k];
+                max_h = std::max(max_h, panel_h(sn));
+                max_u = std::max(max_u, P.upd_ptr[sn + 1] - P.upd_ptr[sn]);
+            }
+            std::fprintf(stderr, "  stage %u: %u lane-sized + %u warp-sized panels, tallest %u rows, most updates %u\n", st,
+                         P.stage_ptr[2 * st + 1] - P.stage_ptr[2 * st], P.stage_ptr[2 * st + 2] - P.stage_ptr[2 * st + 1], max_h, max_u);
         }
     }
     P.perm = perm;

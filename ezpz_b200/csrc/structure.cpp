@@ -268,7 +268,7 @@ void build_large_program(ezpz_structure& S) {
     }
     build_sparse_direct(S);
     const uint64_t nnz_l = P.direct ? P.nnz_l : 0;
-    const uint64_t total = (uint64_t)n + 2ull * m + nnz_j + nnz_l + 4ull * n;
+    const uint64_t total = (uint64_t)n + 2ull * m + nnz_j + nnz_l + 3ull * n;
     if (total >= 0xfffffff0ull) {  // 32-bit slots: fall back to the PCG path
         P.direct = false;
         P.nnz_l = 0;
@@ -278,8 +278,7 @@ void build_large_program(ezpz_structure& S) {
     P.RN0 = P.R0 + m;
     P.J0 = P.RN0 + m;
     P.L0 = P.J0 + nnz_j;
-    P.DG0 = P.L0 + (P.direct ? P.nnz_l : 0);
-    P.RV0 = P.DG0 + n;
+    P.RV0 = P.L0 + (P.direct ? P.nnz_l : 0);
     P.Y0 = P.RV0 + n;
     P.D0 = P.Y0 + n;
     P.VG = (uint64_t)P.D0 + n;

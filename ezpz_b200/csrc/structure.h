@@ -48,39 +48,36 @@ struct SmallProgram {
 };
 
 // The single-large-system programme (large.cu): the processing order of the assembly phase and, unless the
-// factor would be too large, the level-scheduled sparse direct solve built by sparse_direct.cpp.  Slots index
-// one global value array  VG = [x | r | r_next | J (CSC order) | L (by rows) | diag(A) | 1/pivot | y | d].
-constexpr uint32_t kEntryInA = 0x80000000u;  // ent_slot flag: A = JtJ itself has this entry (else pure fill)
-
+// factor would be too large, the supernodal sparse direct solve built by sparse_direct.cpp.  Slots index one
+// global value array  VG = [x | r | r_next | J (CSC order) | L panels | 1/pivot | y | d].
 struct LargeProgram {
     bool built = false;
     bool direct = false;          // sparse direct solve available (otherwise the PCG path runs)
     bool nested = false;          // perm is a nested-dissection order (false: natural order 0..n-1)
-    uint32_t X0 = 0, R0 = 0, RN0 = 0, J0 = 0, L0 = 0, DG0 = 0, RV0 = 0, Y0 = 0, D0 = 0;
+    uint32_t X0 = 0, R0 = 0, RN0 = 0, J0 = 0, L0 = 0, RV0 = 0, Y0 = 0, D0 = 0;
     uint64_t VG = 0;
-    uint32_t n_levels = 0, solo_level = 0, nnz_l = 0;
+    uint32_t n_levels = 0;        // stages = height of the supernode tree
+    uint32_t nnz_l = 0;           // doubles of panel storage
     std::vector<uint32_t> cons_order;                      // processing slots of the assembly phase -> constraint
                                                            // index (tile-local kind sort, UINT32_MAX = padding)
     std::vector<uint32_t> perm;                            // elimination position -> variable
-    std::vector<uint32_t> lr_ptr, lr_col;                  // strictly-lower L by rows, columns ascending; the value
-                                                           // of entry e lives at VG[L0 + e]
-    std::vector<uint32_t> lvl_ptr;                         // n_levels + 1: ranges of lvl_cols (etree height levels)
-    std::vector<uint32_t> lvl_cols;                        // columns ordered by (level, index)
-    std::vector<uint32_t> lvl_maxrow;                      // longest row of L among each level's columns
-    std::vector<uint32_t> ent_ptr;                         // n + 1, by POSITION in lvl_cols: ranges of ent_*
-    std::vector<uint32_t> ent_row, ent_col, ent_slot;      // sub-diagonal entries of each column, rows ascending;
-                                                           // ent_slot = position in row order | kEntryInA
-    // Static row intersections: for entry e = (i, j), bit t of the first ceil(len_j / 32) words at
-    // ent_mask[ent_mask_ptr[e]] says that column lr_col[lr_ptr[j] + t] of row j is also in row i; the following
-    // ceil(pre_i / 32) words mark the matching positions of row i's prefix (pre_i = entries of row i left of j).
-    // The q-th set bits of the two masks pair up, so the factorisation never compares column indices.
-    std::vector<uint32_t> ent_mask_ptr;                    // nnz_l + 1
-    std::vector<uint32_t> ent_mask;
-    // A = JtJ: for every L entry flagged kEntryInA (in ent_* order), the products J[r][i] * J[r][j] over shared rows
-    // r ascending, as pairs of positions in the CSC value array of J.
-    std::vector<uint32_t> aent;                            // indices into ent_* of the entries A has
-    std::vector<uint32_t> aprod_ptr;                       // aent.size() + 1
-    std::vector<uint32_t> aprod_a, aprod_b;
+    // Supernode s = columns [sn_ptr[s], sn_ptr[s+1]) (a chain of the elimination tree, <= 16 columns).  Its panel is
+    // dense, row-major, h x w doubles at VG[L0 + panel_off[s]]: rows sn_rows[sn_row_ptr[s] ...) = the w own columns
+    // (the diagonal block) followed by the sorted union of the columns' sub-diagonal rows.
+    std::vector<uint32_t> sn_ptr, sn_row_ptr, sn_rows, panel_off;
+    // Updates of supernode J by its descendants, ascending: upd_sn[u] = K, whose panel rows upd_rbegin[u].. (to the end
+    // of K's row list) all lie in J's panel; the first upd_ncols[u] of them are columns of J.  upd_rel[upd_rel_ptr[u] + t]
+    // = position in J's row list of K's row upd_rbegin[u] + t.
+    // The block of K's panel an update reads (rows upd_rbegin[u] to the end, all of K's columns) is contiguous.
+    // upd_rec = the 8-word record per update the device reads (sparse_direct.cpp).
+    std::vector<uint32_t> upd_ptr, upd_sn, upd_rbegin, upd_ncols, upd_rel_ptr, upd_rel, upd_rec;
+    // Stage k (height in the supernode tree): supernodes stage_sn[stage_ptr[2k] .. stage_ptr[2k+1]) have lane-sized
+    // panels (one thread each), stage_sn[stage_ptr[2k+1] .. stage_ptr[2k+2]) warp-sized ones.
+    // stage_rec = the 8-word record per supernode in stage order that the device reads (sparse_direct.cpp).
+    std::vector<uint32_t> stage_ptr, stage_sn, stage_rec;
+    // A = JtJ: for every entry A has (strictly lower), its panel slot and the products J[r][i] * J[r][j] over shared
+    // rows r ascending as pairs of positions in the CSC value array of J; diag_slot[j] = panel slot of A[j][j].
+    std::vector<uint32_t> aent_slot, aprod_ptr, aprod_a, aprod_b, diag_slot;
 };
 
 struct DeviceCopy;  // defined in device.h
