@@ -487,8 +487,8 @@ __device__ __noinline__ void sn_factor(const LargeArgs& a, uint32_t pos, uint32_
     double* P = staged ? stage : G;
     double* kb = TEAM > 1 ? stage + Caps::panel : nullptr;
     double* ys = TEAM > 1 ? stage + Caps::panel + Caps::block : y + j0;  // w <= 16 values
-    uint32_t* srec = TEAM > 1 ? reinterpret_cast<uint32_t*>(stage + Caps::panel + Caps::block + kYCap) : nullptr;
-    uint32_t* srel = TEAM > 1 ? srec + Caps::recs * 8 : nullptr;
+    uint32_t* srec_base = TEAM > 1 ? reinterpret_cast<uint32_t*>(stage + Caps::panel + Caps::block + kYCap) : nullptr;
+    uint32_t* srel = TEAM > 1 ? srec_base + Caps::recs * 8 : nullptr;
     uint16_t* inv = TEAM > 1 ? reinterpret_cast<uint16_t*>(srel + Caps::rel) : nullptr;
     if (TEAM > 1) {
         if (staged)
@@ -499,78 +499,115 @@ __device__ __noinline__ void sn_factor(const LargeArgs& a, uint32_t pos, uint32_
     // ---- 1. external updates
     const uint32_t ub = hdr2.y, ue = hdr2.y + hdr2.z;
     if (TEAM > 1) {
+        uint32_t win = ub, win_n = 0;  // window of update records held in shared memory: [win, win + win_n)
         for (uint32_t u0 = ub; u0 < ue;) {
             // The records of the next (up to 32) updates go to shared memory; then a chunk of consecutive updates
             // whose blocks and relative positions fit the stage is fetched with asynchronous copies that are all in
             // flight together (one memory round trip per chunk instead of several per update).
-            const uint32_t avail = min(Caps::recs, ue - u0);
-            for (uint32_t q = lane; q < avail * 8; q += TEAM) srec[q] = __ldg(a.upd_rec + 8 * (size_t)u0 + q);
-            team_sync<TEAM>();
+            if (u0 >= win + win_n) {
+                team_sync<TEAM>();  // everybody is done with the previous window
+                win = u0;
+                win_n = min(Caps::recs, ue - u0);
+                for (uint32_t q = lane; q < win_n * 8; q += TEAM) srec_base[q] = __ldg(a.upd_rec + 8 * (size_t)win + q);
+                team_sync<TEAM>();
+            }
+            uint32_t* srec = srec_base + 8 * (u0 - win);
+            const uint32_t avail = win + win_n - u0;
+            // Staged layout of update i of a chunk: srec[8 i + 5] = staged columns ws (all of K's columns, or a slice of
+            // them), block = T rows x ws columns, row-major, followed by ws values of y.
+            // Every panel entry is owned by one thread, which applies the chunk's updates to it in order: no barrier
+            // between updates, no index comparisons (r >= c implies the block positions satisfy ti >= tj).
+            auto apply = [&](uint32_t cnt) {
+                for (uint32_t e = lane; e < h * w; e += TEAM) {
+                    const uint32_t r = e / w, c = e - r * w;
+                    if (c > r) continue;
+                    double acc = P[e];
+                    for (uint32_t i = 0, boff = 0; i < cnt; ++i) {
+                        const uint32_t T = srec[8 * i + 1], nc = srec[8 * i + 2] >> 8, ws = srec[8 * i + 5];
+                        const uint32_t ti = inv[i * h + r], tj = inv[i * h + c];
+                        if (ti != 0xffffu && tj < nc) {
+                            const double* bi = kb + boff + ti * ws;
+                            const double* bj = kb + boff + tj * ws;
+                            for (uint32_t k = 0; k < ws; ++k) acc = __fma_rn(-bi[k], bj[k], acc);
+                        }
+                        boff += T * ws + ws;
+                    }
+                    P[e] = acc;
+                }
+                for (uint32_t c = lane; c < w; c += TEAM) {  // forward substitution against y of the descendants' columns
+                    double acc = ys[c];
+                    for (uint32_t i = 0, boff = 0; i < cnt; ++i) {
+                        const uint32_t T = srec[8 * i + 1], nc = srec[8 * i + 2] >> 8, ws = srec[8 * i + 5];
+                        const uint32_t tj = inv[i * h + c];
+                        if (tj < nc) {
+                            const double* bj = kb + boff + tj * ws;
+                            const double* yK = kb + boff + T * ws;
+                            for (uint32_t k = 0; k < ws; ++k) acc = __fma_rn(-bj[k], yK[k], acc);
+                        }
+                        boff += T * ws + ws;
+                    }
+                    ys[c] = acc;
+                }
+                team_sync<TEAM>();
+            };
+            // inverse maps: inv[i * h + (panel row)] = position of that row in update i's block, 0xffff when absent
+            auto build_inverse = [&](uint32_t cnt) {
+                for (uint32_t i = 0, roff = 0; i < cnt; ++i) {
+                    const uint32_t T = srec[8 * i + 1];
+                    for (uint32_t t = lane; t < T; t += TEAM) inv[i * h + srel[roff + t]] = (uint16_t)t;
+                    roff += T;
+                }
+                team_sync<TEAM>();
+            };
             uint32_t cnt = 0, tot_b = 0, tot_r = 0;
             while (cnt < avail) {
-                const uint32_t* r = srec + 8 * cnt;
+                uint32_t* r = srec + 8 * cnt;
                 const uint32_t T = r[1], wK = r[2] & 0xffu, len = T * wK;
                 if (tot_b + len + wK > Caps::block || tot_r + T > Caps::rel || (cnt + 1) * h > Caps::inv || T >= 0xffffu) break;
                 for (uint32_t q = lane; q < len; q += TEAM) cp_async8(kb + tot_b + q, lv + r[0] + q);
                 for (uint32_t q = lane; q < wK; q += TEAM) cp_async8(kb + tot_b + len + q, y + r[4] + q);  // y of K's columns
                 for (uint32_t q = lane; q < T; q += TEAM) cp_async4(srel + tot_r + q, a.upd_rel + r[3] + q);
+                if (lane == 0) r[5] = wK;
                 tot_b += len + wK;
                 tot_r += T;
                 ++cnt;
             }
-            if (cnt == 0) {
-                // an update too large for the stage: pair by pair, straight from global memory
-                const uint32_t* r = srec;
-                const uint32_t T = r[1], wK = r[2] & 0xffu, nc = r[2] >> 8;
-                sn_apply_update<TEAM>(P, w, ys, y + r[4], lv + r[0], a.upd_rel + r[3], T, wK, nc, lane);
+            if (cnt > 0) {
+                for (uint32_t q = lane; q < cnt * h; q += TEAM) inv[q] = 0xffffu;
+                cp_async_wait_all();
                 team_sync<TEAM>();
-                u0 += 1;
+                build_inverse(cnt);
+                apply(cnt);
+                u0 += cnt;
                 continue;
             }
-            // inverse maps: inv[i * h + (panel row)] = position of that row in update i's block, 0xffff when absent
-            for (uint32_t q = lane; q < cnt * h; q += TEAM) inv[q] = 0xffffu;
-            cp_async_wait_all();
-            team_sync<TEAM>();
-            for (uint32_t i = 0, roff = 0; i < cnt; ++i) {
-                const uint32_t T = srec[8 * i + 1];
-                for (uint32_t t = lane; t < T; t += TEAM) inv[i * h + srel[roff + t]] = (uint16_t)t;
-                roff += T;
-            }
-            team_sync<TEAM>();
-            // Every panel entry is owned by one thread, which applies the chunk's updates to it in order: no barrier
-            // between updates, no index comparisons (r >= c implies the block positions satisfy ti >= tj).
-            for (uint32_t e = lane; e < h * w; e += TEAM) {
-                const uint32_t r = e / w, c = e - r * w;
-                if (c > r) continue;
-                double acc = P[e];
-                for (uint32_t i = 0, boff = 0; i < cnt; ++i) {
-                    const uint32_t T = srec[8 * i + 1], z = srec[8 * i + 2], wK = z & 0xffu;
-                    const uint32_t ti = inv[i * h + r], tj = inv[i * h + c];
-                    if (ti != 0xffffu && tj < (z >> 8)) {
-                        const double* bi = kb + boff + ti * wK;
-                        const double* bj = kb + boff + tj * wK;
-                        for (uint32_t k = 0; k < wK; ++k) acc = __fma_rn(-bi[k], bj[k], acc);
+            // One update whose block is larger than the stage.
+            const uint32_t T = srec[1], wK = srec[2] & 0xffu, nc = srec[2] >> 8;
+            if (T + 1 <= Caps::block && T <= Caps::rel && h <= Caps::inv && T < 0xffffu) {
+                // Column slices of the descendant's panel, as many columns at a time as fit: every entry's fma chain
+                // simply continues from slice to slice (k stays ascending).
+                const uint32_t ws_max = Caps::block / (T + 1);
+                for (uint32_t q = lane; q < h; q += TEAM) inv[q] = 0xffffu;
+                for (uint32_t q = lane; q < T; q += TEAM) cp_async4(srel + q, a.upd_rel + srec[3] + q);
+                for (uint32_t ks = 0; ks < wK; ks += ws_max) {
+                    const uint32_t ws = min(ws_max, wK - ks);
+                    for (uint32_t q = lane; q < T * ws; q += TEAM) {
+                        const uint32_t t = q / ws, k = q - t * ws;
+                        cp_async8(kb + q, lv + srec[0] + t * wK + ks + k);
                     }
-                    boff += T * wK + wK;
+                    for (uint32_t q = lane; q < ws; q += TEAM) cp_async8(kb + T * ws + q, y + srec[4] + ks + q);
+                    if (lane == 0) srec[5] = ws;
+                    cp_async_wait_all();
+                    team_sync<TEAM>();
+                    if (ks == 0) build_inverse(1);
+                    apply(1);
                 }
-                P[e] = acc;
+            } else {
+                // pair by pair, straight from global memory
+                sn_apply_update<TEAM>(P, w, ys, y + srec[4], lv + srec[0], a.upd_rel + srec[3], T, wK, nc, lane);
+                team_sync<TEAM>();
             }
-            for (uint32_t c = lane; c < w; c += TEAM) {  // forward substitution of the panel's columns against y of the descendants'
-                double acc = ys[c];
-                for (uint32_t i = 0, boff = 0; i < cnt; ++i) {
-                    const uint32_t T = srec[8 * i + 1], z = srec[8 * i + 2], wK = z & 0xffu;
-                    const uint32_t tj = inv[i * h + c];
-                    if (tj < (z >> 8)) {
-                        const double* bj = kb + boff + tj * wK;
-                        const double* yK = kb + boff + T * wK;
-                        for (uint32_t k = 0; k < wK; ++k) acc = __fma_rn(-bj[k], yK[k], acc);
-                    }
-                    boff += T * wK + wK;
-                }
-                ys[c] = acc;
-            }
-            team_sync<TEAM>();
-            u0 += cnt;
+            u0 += 1;
         }
     } else {
         for (uint32_t u = ub; u < ue; ++u) {

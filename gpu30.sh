@@ -4,7 +4,7 @@ import sys, time
 sys.path.insert(0,'tests')
 import ezpz_b200 as ez, workloads as wl
 ctx = ez.Context(0)
-for build in (lambda: wl.chain_sketch(1024), lambda: wl.chain_sketch(77000)):
+for build in (lambda: wl.chain_sketch(77000),):
     recs, n, g, _ = build()
     st = ez.Structure(recs, n)
     out = ctx.solve_one(st, g)

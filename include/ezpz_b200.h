@@ -282,8 +282,8 @@ int32_t ezpz_b200_solve_one(ezpz_context_t* ctx, const ezpz_structure_t* s,
  *   *path        0 = batched-small kernel (no large programme), 1 = sparse direct, 2 = PCG
  *   *elim_order  [n] elimination position -> variable (NULL unless path 1); natural order 0..n-1 or
  *                nested dissection (*nested != 0)
- *   *n_levels    height of the elimination tree = number of parallel factorisation phases
- *   *nnz_l       strictly-lower entries of the factor
+ *   *n_levels    height of the supernode tree = number of parallel factorisation stages
+ *   *nnz_l       doubles of panel storage of the factor (dense supernode panels, explicit zeros included)
  *   *sum_chunk   rows per chunk of the sum-of-squares fold on this structure (0 = one sequential fold)
  * The arithmetic is the oracle's applied to P A Pt; parity tests hand `elim_order` and `sum_chunk` to the oracle. */
 int32_t ezpz_b200_structure_ordering(const ezpz_structure_t* s, int32_t* path, const uint32_t** elim_order,

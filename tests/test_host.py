@@ -213,7 +213,7 @@ def test_large_system_ordering_host_analysis():
         od = st.ordering()
         assert od["path"] == 1 and od["nested"]
         assert sorted(od["elim_order"].tolist()) == list(range(n))
-        assert od["nnz_l"] < 16 * n  # fill stays linear in n
+        assert od["nnz_l"] < 32 * n  # panel storage (explicit zeros of the relaxed supernodes included) stays linear in n
         heights[cells] = od["n_levels"]
         if cells <= 1024:
             a = orc.solve_inner(recs, g)
@@ -222,8 +222,8 @@ def test_large_system_ordering_host_analysis():
             assert np.abs(a.final_values - b.final_values).max() < 1e-9
             c = orc.solve_inner_ordered(recs, g, None, 0)
             assert np.array_equal(a.final_values, c.final_values)
-    # 64x more cells add a few separators to the height, they do not multiply it
-    assert heights[4096] < heights[64] + 100
+    # 64x more cells add a few stages to the supernode tree, they do not multiply it
+    assert heights[4096] <= heights[64] + 12 and heights[4096] < 40
     # a small system takes the batched kernel: no large programme
     recs, n, g, _ = wl.system_from_text(wl.fixture_text("square"))
     assert ez.Structure(recs, n).ordering()["path"] == 0
