@@ -29,11 +29,11 @@ def test_massive_parallel_system_direct_path(ctx, lines, over):
         assert np.abs(out.final_values[4 * k:4 * k + 4] - [k, 0, k, 4]).max() < 1e-6
 
 
-def _check_direct(ctx, cells):
+def _check_direct(ctx, cells, system=None, exact_tol=1e-6):
     """Sparse direct path: bit-exact against the oracle run with the same elimination order and sum-of-squares
     chunking (Structure.ordering()), and within the north-star tolerance (identical iteration count and verdict,
     1e-9 on coordinates) of the reference-faithful oracle (natural order, sequential sum)."""
-    recs, n, g, exact = wl.chain_sketch(cells)
+    recs, n, g, exact = system if system is not None else wl.chain_sketch(cells)
     st = ez.Structure(recs, n)
     od = st.ordering()
     assert od["path"] == 1 and sorted(od["elim_order"].tolist()) == list(range(n))
@@ -46,7 +46,7 @@ def _check_direct(ctx, cells):
     assert out.iterations == ref.iterations and out.converged == ref.converged and out.unsatisfied == ref.unsatisfied
     scale = np.maximum(1.0, np.abs(ref.final_values))
     assert (np.abs(out.final_values - ref.final_values) <= 1e-9 * scale).all()
-    assert np.abs(out.final_values - exact).max() < 1e-6
+    assert np.abs(out.final_values - exact).max() < exact_tol  # the constructed solution (LM stops at max|r| <= 1e-8)
     return od
 
 
@@ -65,6 +65,14 @@ def test_chain_sketch_1m_variables(ctx):
     """BASELINE.json config 4: the synthetic 1,001,000-variable sketch (arcs, circle tangents, distances, angles)."""
     od = _check_direct(ctx, 77000)
     assert od["n_levels"] < 1024
+
+
+@pytest.mark.parametrize("N,weights", [(12, False), (40, False), (40, True), (100, False)])
+def test_grid_truss_direct(ctx, N, weights):
+    """A 2D lattice (separators of ~N points, panels hundreds of rows tall, dozens of updates per panel): the regime
+    opposite to the chain sketch — panels that do not fit a warp's stage, CTA teams, column-sliced update blocks."""
+    od = _check_direct(ctx, 0, wl.grid_truss(N, weights=weights), exact_tol=1e-4)
+    assert od["nested"]
 
 
 def test_chain_sketch_pcg_path(ctx):

@@ -179,3 +179,41 @@ def chain_sketch(cells, seed=0xE2B20004, noise=0.05):
     recs = np.ascontiguousarray(recs[perm])
     guesses = exact + uniform_pm(seed + (99 << 40), n_vars, noise)
     return recs, n_vars, guesses, exact
+
+
+def grid_truss(N, seed=0xE2B20006, noise=0.03, weights=False):
+    """A 2D lattice sketch (not a chain): N x N points, Distance constraints to the right, down and one diagonal
+    neighbour (a rigid triangulated truss), the first point Fixed in x and y and the second in y.  Its graph has
+    separators of ~N points, so the large path's panels are hundreds of rows tall — the opposite regime of
+    chain_sketch.  Returns (records, n_vars, guesses, exact_solution)."""
+    from ezpz_b200 import native
+    gx, gy = np.meshgrid(np.arange(N, dtype=np.float64) * 2.0, np.arange(N, dtype=np.float64) * 1.5, indexing="xy")
+    jitter = uniform_pm(seed, 2 * N * N, 0.3).reshape(N, N, 2)
+    px, py = gx + jitter[:, :, 0], gy + jitter[:, :, 1]
+    exact = np.stack([px, py], axis=2).reshape(-1)
+    pid = lambda r, c: 2 * (r * N + c)
+    recs = []
+
+    def rec(kind, ids, p0=0.0, w=1.0):
+        r = np.zeros(1, dtype=native.REC_DTYPE)
+        r["kind"], r["p0"], r["weight"] = kind, p0, w
+        r["ids"][0, :len(ids)] = ids
+        return r
+
+    recs.append(rec(9, [pid(0, 0)], px[0, 0]))
+    recs.append(rec(9, [pid(0, 0) + 1], py[0, 0]))
+    recs.append(rec(9, [pid(0, 1) + 1], py[0, 1]))
+    k = 0
+    for r in range(N):
+        for c in range(N):
+            for dr, dc in ((0, 1), (1, 0), (1, 1)):
+                r2, c2 = r + dr, c + dc
+                if r2 < N and c2 < N:
+                    a, b = pid(r, c), pid(r2, c2)
+                    d = float(np.hypot(px[r, c] - px[r2, c2], py[r, c] - py[r2, c2]))
+                    k += 1
+                    recs.append(rec(2, [a, a + 1, b, b + 1], d, (0.5 if k % 3 == 0 else 2.0 if k % 3 == 1 else 1.0) if weights else 1.0))
+    recs = np.ascontiguousarray(np.concatenate(recs))
+    n_vars = 2 * N * N
+    guesses = exact + uniform_pm(seed + (7 << 40), n_vars, noise)
+    return recs, n_vars, guesses, exact
