@@ -134,3 +134,22 @@ def test_large_eval_all_kinds_bitwise(ctx):
         order = np.lexsort((np.repeat(np.arange(n_vars), np.diff(pat["csc_col_ptr"])), pat["csc_row_idx"]))
         assert_bitwise(jr, jo[order], f"trial {trial} jacobian (CSR order)")
         assert np.array_equal(dg, dgo)
+
+
+@pytest.mark.parametrize("cells", [64, 1024])
+def test_large_path_failed_factorisations(ctx, cells):
+    """Non-finite pivots (a guess at 1e308 overflows the distances): every factorisation fails, lambda is bumped and the
+    iteration is burnt (newton.rs:96-99) until max_iterations — same trajectory length and verdict as the oracle, on the
+    single-CTA and on the cooperative-grid variant."""
+    recs, n, g, exact = wl.chain_sketch(cells)
+    g = g.copy()
+    g[2] = 1e308
+    st = ez.Structure(recs, n)
+    od = st.ordering()
+    out = ctx.solve_one(st, g)
+    o = orc.solve_inner_ordered(recs, g, od["elim_order"], od["sum_chunk"])
+    assert out.iterations == o.iterations == 35 and not out.converged and not o.converged
+    assert out.unsatisfied == o.unsatisfied
+    finite = np.isfinite(o.final_values)
+    assert np.array_equal(np.isfinite(out.final_values), finite)
+    assert_bitwise(out.final_values[finite], o.final_values[finite], "finite final values")
