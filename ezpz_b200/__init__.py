@@ -607,6 +607,34 @@ class Context:
         res.unsatisfied = np.flatnonzero(bits).tolist()
         return res
 
+    def solve_batch_priorities(self, recs, priorities, n_vars, guesses, params=None, config=None):
+        """The priority loop of ezpz::solve (lib.rs:199-246) for a batch of problems of one topology
+        (ezpz_b200_solve_batch_priorities).  Returns a BatchResult with final_values, iterations, status,
+        priority_solved and unsat_mask (ORIGINAL request indices)."""
+        if not isinstance(recs, np.ndarray):
+            recs = records(recs)
+        recs = np.ascontiguousarray(recs)
+        n_cons = len(recs)
+        g = np.ascontiguousarray(guesses, dtype=np.float64).reshape(-1, n_vars)
+        B = g.shape[0]
+        pr = None if priorities is None else np.ascontiguousarray(priorities, dtype=np.uint32)
+        pa = None if params is None else np.ascontiguousarray(params, dtype=np.float64).reshape(B, n_cons)
+        cfg = (config or Config())._native()
+        res = BatchResult()
+        res.final_values = np.empty_like(g)
+        res.iterations = np.zeros(B, np.uint32)
+        res.status = np.zeros(B, np.uint8)
+        res.priority_solved = np.zeros(B, np.uint32)
+        res.unsat_mask = np.zeros((B, (n_cons + 31) // 32), np.uint32)
+        det = native.ErrorDetail()
+        rc = native.lib().ezpz_b200_solve_batch_priorities(
+            self.handle, native.ptr(recs), native.ptr(pr), n_cons, int(n_vars), C.byref(cfg), B, native.ptr(g), native.ptr(pa),
+            native.ptr(res.final_values), native.ptr(res.iterations), native.ptr(res.status), native.ptr(res.priority_solved),
+            native.ptr(res.unsat_mask), C.byref(det))
+        if rc != 0:
+            raise EzpzError(rc, det)
+        return res
+
     def time_solve_one(self, st, guesses, reps=10, final_values=None):
         """Wall-clock seconds of `reps` ezpz_b200_solve_one calls on caller-provided host buffers (pass pinned arrays
         for large systems); buffers and the ctypes structs are built once, so the time is the C call's.  Returns

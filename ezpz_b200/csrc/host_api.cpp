@@ -214,3 +214,111 @@ extern "C" int32_t ezpz_b200_solve(ezpz_context_t* ctx, const ezpz_constraint_t*
     export_level(best, outcome);
     return EZPZ_OK;
 }
+
+
+// The same priority loop for a batch of problems of one topology: one structure and one batched solve per level.
+extern "C" int32_t ezpz_b200_solve_batch_priorities(ezpz_context_t* ctx, const ezpz_constraint_t* cons, const uint32_t* priorities,
+                                                    uint32_t n_cons, uint32_t n_vars, const ezpz_config_t* config, uint64_t batch,
+                                                    const double* guesses, const double* params, double* final_values,
+                                                    uint32_t* iterations, uint8_t* status, uint32_t* priority_solved,
+                                                    uint32_t* unsat_mask, ezpz_error_detail_t* detail) {
+    if (!config || (n_cons && !cons) || !final_values || !iterations || !status || (batch && n_vars && !guesses))
+        return EZPZ_ERR_INVALID_ARGUMENT;
+    if (detail) std::memset(detail, 0, sizeof *detail);
+    for (uint32_t k = 0; k < n_cons; ++k)
+        if (cons[k].kind >= EZPZ_K_COUNT) return EZPZ_ERR_INVALID_ARGUMENT;
+    const size_t uw = (n_cons + 31) / 32;
+    if (n_cons == 0) {  // lib.rs:155-170
+        if (batch && n_vars) std::memcpy(final_values, guesses, (size_t)batch * n_vars * sizeof(double));
+        for (uint64_t b = 0; b < batch; ++b) {
+            iterations[b] = 0;
+            status[b] = EZPZ_ST_CONVERGED;
+            if (priority_solved) priority_solved[b] = 0;
+        }
+        return EZPZ_OK;
+    }
+    if (!ctx) return EZPZ_ERR_NO_DEVICE;
+    if (batch == 0) return EZPZ_OK;
+    std::vector<uint32_t> levels;
+    for (uint32_t k = 0; k < n_cons; ++k) levels.push_back(priorities ? priorities[k] : 0u);
+    std::sort(levels.begin(), levels.end());
+    levels.erase(std::unique(levels.begin(), levels.end()), levels.end());
+    // per problem: 0 = no level kept yet, 1 = a satisfied level is kept, 2 = stopped
+    std::vector<uint8_t> state(batch, 0);
+    std::vector<uint64_t> active(batch);
+    for (uint64_t b = 0; b < batch; ++b) active[b] = b;
+    std::vector<double> g_sub, p_sub, f_sub;
+    std::vector<uint32_t> it_sub, un_sub;
+    std::vector<uint8_t> st_sub;
+    for (size_t li = 0; li < levels.size() && !active.empty(); ++li) {
+        const uint32_t level = levels[li];
+        std::vector<ezpz_constraint_t> subset;
+        std::vector<uint32_t> ids;
+        uint32_t lowest = 0;
+        for (uint32_t k = 0; k < n_cons; ++k) {
+            const uint32_t p = priorities ? priorities[k] : 0u;
+            if (p <= level) {
+                subset.push_back(cons[k]);
+                ids.push_back(k);
+                lowest = std::max(lowest, p);
+            }
+        }
+        const uint32_t nc = (uint32_t)subset.size();
+        const size_t uws = (nc + 31) / 32;
+        ezpz_structure_t* S = nullptr;
+        int32_t rc = ezpz_b200_structure_create(subset.data(), nc, nullptr, n_vars, &S, detail);
+        if (rc != EZPZ_OK) {  // lib.rs:239-244: problems that already keep a level keep it; otherwise the error is the answer
+            if (rc == EZPZ_ERR_MISSING_GUESS && detail) detail->constraint_id = ids[detail->constraint_id];
+            return li == 0 ? rc : EZPZ_OK;
+        }
+        // the still-undecided problems, compacted
+        const uint64_t nb = active.size();
+        g_sub.resize((size_t)nb * n_vars);
+        f_sub.resize((size_t)nb * n_vars);
+        it_sub.resize(nb);
+        st_sub.resize(nb);
+        un_sub.assign((size_t)nb * uws, 0u);
+        if (params) p_sub.resize((size_t)nb * nc);
+        for (uint64_t q = 0; q < nb; ++q) {
+            std::memcpy(g_sub.data() + q * n_vars, guesses + active[q] * n_vars, n_vars * sizeof(double));
+            if (params)
+                for (uint32_t k = 0; k < nc; ++k) p_sub[q * nc + k] = params[active[q] * n_cons + ids[k]];
+        }
+        ezpz_batch_io_t io;
+        std::memset(&io, 0, sizeof io);
+        io.guesses = g_sub.data();
+        io.params = params ? p_sub.data() : nullptr;
+        io.final_values = f_sub.data();
+        io.iterations = it_sub.data();
+        io.status = st_sub.data();
+        io.unsat_mask = un_sub.data();
+        rc = ezpz_b200_solve_batch(ctx, S, config, nb, &io, detail);
+        ezpz_b200_structure_destroy(S);
+        if (rc != EZPZ_OK) return li == 0 ? rc : EZPZ_OK;
+        std::vector<uint64_t> next;
+        for (uint64_t q = 0; q < nb; ++q) {
+            const uint64_t b = active[q];
+            const bool unsat = (st_sub[q] & EZPZ_ST_UNSATISFIED) != 0;
+            const bool keep = !unsat || state[b] == 0;  // an unsatisfied level is kept only when nothing else is (lib.rs:232-234)
+            if (keep) {
+                std::memcpy(final_values + b * n_vars, f_sub.data() + q * n_vars, n_vars * sizeof(double));
+                iterations[b] = it_sub[q];
+                status[b] = st_sub[q];
+                if (priority_solved) priority_solved[b] = lowest;
+                if (unsat_mask) {
+                    uint32_t* dst = unsat_mask + b * uw;
+                    std::fill(dst, dst + uw, 0u);
+                    for (uint32_t k = 0; k < nc; ++k)
+                        if (un_sub[q * uws + (k >> 5)] & (1u << (k & 31u))) dst[ids[k] >> 5] |= 1u << (ids[k] & 31u);
+                }
+            }
+            if (unsat) state[b] = 2;
+            else {
+                state[b] = 1;
+                next.push_back(b);
+            }
+        }
+        active.swap(next);
+    }
+    return EZPZ_OK;
+}

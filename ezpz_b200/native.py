@@ -79,6 +79,8 @@ _SYMBOLS = [
     ("ezpz_b200_freedom_analysis", C.c_int32, [_P, _P, C.c_uint64, _P, _P, C.POINTER(ErrorDetail)]),
     ("ezpz_b200_solve", C.c_int32, [_P, _P, _P, _P, C.c_uint32, _P, _P, C.c_uint32, C.POINTER(Config), C.c_int32,
                                     C.POINTER(OutcomeRec), C.POINTER(ErrorDetail)]),
+    ("ezpz_b200_solve_batch_priorities", C.c_int32, [_P, _P, _P, C.c_uint32, C.c_uint32, C.POINTER(Config), C.c_uint64, _P, _P, _P, _P,
+                                                     _P, _P, _P, C.POINTER(ErrorDetail)]),
     ("ezpz_b200_angle_sincos", None, [C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     ("ezpz_b200_hypot", C.c_double, [C.c_double, C.c_double]),
     ("ezpz_b200_config_default", None, [C.POINTER(Config)]),

@@ -365,6 +365,30 @@ int32_t ezpz_b200_solve(ezpz_context_t* ctx, const ezpz_constraint_t* cons, cons
                         int32_t analysis, ezpz_outcome_t* outcome, ezpz_error_detail_t* detail);
 
 /* ---------------------------------------------------------------------------------------------
+ * The priority loop of ezpz::solve (lib.rs:199-246) for a BATCH of problems of one topology: the
+ * constraints, their priorities and weights are shared, guesses (and optionally the p0 targets) differ
+ * per problem.  For every distinct priority level, ascending: ONE structure analysis of the constraints
+ * with priority <= level and ONE batched solve of all still-undecided problems from their ORIGINAL
+ * guesses.  A problem keeps the result of the last level that left no constraint unsatisfied; the first
+ * level with unsatisfied constraints stops it (its own result is kept only if it is the first level) —
+ * exactly what the per-problem loop does.
+ *   priorities       [n_cons] (NULL = all 0)
+ *   guesses          [batch * n_vars]
+ *   params           [batch * n_cons] per-problem p0 overrides in ORIGINAL request order, or NULL
+ *   final_values     [batch * n_vars]
+ *   iterations       [batch]   LM iterations of the level whose result is kept
+ *   status           [batch]   EZPZ_ST_* of that level
+ *   priority_solved  [batch]   highest priority among the constraints of that level
+ *   unsat_mask       [batch * ceil(n_cons / 32)] bit c = ORIGINAL request c unsatisfied (optional)
+ */
+int32_t ezpz_b200_solve_batch_priorities(ezpz_context_t* ctx, const ezpz_constraint_t* cons,
+                                         const uint32_t* priorities, uint32_t n_cons, uint32_t n_vars,
+                                         const ezpz_config_t* config, uint64_t batch, const double* guesses,
+                                         const double* params, double* final_values, uint32_t* iterations,
+                                         uint8_t* status, uint32_t* priority_solved, uint32_t* unsat_mask,
+                                         ezpz_error_detail_t* detail);
+
+/* ---------------------------------------------------------------------------------------------
  * Scalar helpers with the bits of libm 0.2.16 (see ezpz_b200/csrc/dmath.cuh). */
 void ezpz_b200_angle_sincos(double radians, double* sin_out, double* cos_out);
 double ezpz_b200_hypot(double x, double y);

@@ -318,3 +318,43 @@ def test_iteration_count_pins_on_gpu(ctx):
         reqs = [R.highest_priority(C.PointsAtAngle(P[0], P[1], P[2], ez.AngleKind.Other(ez.Angle.from_radians(ang))))]
         out = ez.solve(reqs, list(enumerate(map(float, [0, 0, *p1, *p2]))), cfg)
         assert out.is_satisfied() and out.iterations() == 0
+
+
+def test_batch_priority_tiers_match_oracle(ctx):
+    """The priority loop of ezpz::solve (lib.rs:199-246) for a batch (ezpz_b200_solve_batch_priorities): three tiers on the
+    square fixture's topology, the tier-1 target varied per problem so that some problems stop at tier 0, some at tier 1 and
+    some reach tier 2; per problem identical to the CPU oracle's priority loop (values bit for bit, iterations, tier,
+    unsatisfied ORIGINAL indices)."""
+    recs0, n, g0, _ = wl.system_from_text(wl.fixture_text("two_rectangles"))
+    recs0 = ez.records(recs0) if not isinstance(recs0, np.ndarray) else recs0
+    extra = np.zeros(3, dtype=recs0.dtype)
+    extra["weight"] = 1.0
+    # tier 1: distance between the first rectangle's opposite corners (points 0 and 2); tier 2: two Fixed on point 4
+    extra[0]["kind"], extra[0]["ids"][:4] = 2, [0, 1, 4, 5]
+    extra[1]["kind"], extra[1]["ids"][0], extra[1]["p0"] = 9, 8, 2.0
+    extra[2]["kind"], extra[2]["ids"][0], extra[2]["p0"] = 9, 8, 2.5   # contradicts the previous one: tier 2 never satisfied
+    recs = np.concatenate([recs0, extra])
+    nc = len(recs)
+    prio = np.zeros(nc, np.uint32)
+    prio[len(recs0)] = 1
+    prio[len(recs0) + 1:] = 2
+    B = 96
+    rng = np.random.default_rng(7)
+    g = g0[None, :] + rng.uniform(-0.2, 0.2, (B, n))
+    params = np.tile(recs["p0"], (B, 1))
+    base = orc.solve(recs0, g0)  # the rectangle at tier 0
+    diag = float(np.hypot(base.final_values[4] - base.final_values[0], base.final_values[5] - base.final_values[1]))
+    params[:, len(recs0)] = np.where(np.arange(B) % 3 == 0, diag, diag + 0.5 + 0.01 * np.arange(B))  # consistent for every third problem
+    params[:, len(recs0) + 2] = np.where(np.arange(B) % 6 == 0, 2.0, 2.5)  # tier 2 consistent for every sixth
+    out = ctx.solve_batch_priorities(recs, prio, n, g, params=params)
+    tiers = set()
+    for b in range(B):
+        rb = recs.copy()
+        rb["p0"] = params[b]
+        o = orc.solve(rb, g[b], priorities=prio)
+        got_unsat = [c for c in range(nc) if out.unsat_mask[b, c >> 5] >> (c & 31) & 1]
+        assert out.iterations[b] == o.iterations and bool(out.status[b] & 1) == o.converged, b
+        assert out.priority_solved[b] == o.priority_solved and got_unsat == list(o.unsatisfied), b
+        assert_bitwise(out.final_values[b], o.final_values, f"problem {b}")
+        tiers.add(int(out.priority_solved[b]))
+    assert tiers == {0, 1, 2}
