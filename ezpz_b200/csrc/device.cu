@@ -610,6 +610,7 @@ void ezpz_b200_context_destroy(ezpz_context_t* ctx) {
         if (ctx->pipe_done[k]) cudaEventDestroy(ctx->pipe_done[k]);
     }
     if (ctx->ws) cudaFree(ctx->ws);
+    ezs::release_structure_cache(ctx);
     delete ctx;
 }
 

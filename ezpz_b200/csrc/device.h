@@ -53,7 +53,13 @@ struct ezpz_context {
     // grow-only device workspace for the host-buffer entry points
     void* ws = nullptr;
     size_t ws_bytes = 0;
+    // topology cache of ezpz_b200_solve (host_api.cpp): analysed structures keyed by their constraint list
+    void* structure_cache = nullptr;
 };
+
+namespace ezs {
+void release_structure_cache(ezpz_context* ctx);  // host_api.cpp
+}
 
 #define EZ_CUDA(call, what)                                                \
     do {                                                                   \

@@ -9,13 +9,90 @@
 // the device through ezpz_b200_structure_create + ezpz_b200_solve_one + ezpz_b200_freedom_analysis.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
 #include "../../include/ezpz_b200.h"
+#include "device.h"
 #include "kinds.h"
 
 namespace {
+
+// ---- topology cache -------------------------------------------------------------------------------------------
+// The reference analyses the system inside every solve call (Model::new, lib.rs:279).  Interactive callers solve the
+// same sketch topology again and again (dragging a point changes guesses, not constraints), so ezpz_b200_solve keeps
+// the analysed structures of the last few distinct constraint lists per context: a repeated call skips the pattern
+// build, the symbolic factorisation, the tape / supernode schedule and the upload of the device tables.
+struct CachedStructure {
+    uint64_t hash = 0;
+    std::vector<ezpz_constraint_t> cons;
+    std::vector<uint32_t> var_ids;
+    bool has_var_ids = false;
+    uint32_t n_vars = 0;
+    ezpz_structure_t* S = nullptr;
+    uint64_t last_use = 0;
+};
+struct StructureCache {
+    std::vector<CachedStructure> entries;
+    uint64_t clock = 0, hits = 0, misses = 0;
+};
+constexpr size_t kCacheEntries = 8;
+constexpr uint32_t kCacheMaxVars = 1u << 18;  // larger systems hold GBs of device tables: not cached
+
+uint64_t fnv1a(const void* data, size_t bytes, uint64_t h) {
+    const unsigned char* p = static_cast<const unsigned char*>(data);
+    for (size_t i = 0; i < bytes; ++i) h = (h ^ p[i]) * 0x100000001b3ull;
+    return h;
+}
+
+// Returns a structure for this constraint list (created on a miss); *owned = true when the caller must destroy it.
+int32_t cached_structure(ezpz_context_t* ctx, const std::vector<ezpz_constraint_t>& cons, const uint32_t* var_ids, uint32_t n_vars,
+                         ezpz_structure_t** out, bool* owned, ezpz_error_detail_t* detail) {
+    *owned = true;
+    const bool disabled = [] {
+        const char* e = std::getenv("EZPZ_B200_NO_STRUCTURE_CACHE");
+        return e && e[0] == '1';
+    }();
+    if (!ctx || n_vars > kCacheMaxVars || disabled)
+        return ezpz_b200_structure_create(cons.data(), (uint32_t)cons.size(), var_ids, n_vars, out, detail);
+    if (!ctx->structure_cache) ctx->structure_cache = new StructureCache();
+    StructureCache& C = *static_cast<StructureCache*>(ctx->structure_cache);
+    uint64_t h = fnv1a(cons.data(), cons.size() * sizeof(ezpz_constraint_t), 0xcbf29ce484222325ull);
+    h = fnv1a(&n_vars, sizeof n_vars, h);
+    if (var_ids) h = fnv1a(var_ids, n_vars * sizeof(uint32_t), h);
+    for (CachedStructure& e : C.entries) {
+        if (e.hash != h || e.n_vars != n_vars || e.cons.size() != cons.size() || e.has_var_ids != (var_ids != nullptr)) continue;
+        if (std::memcmp(e.cons.data(), cons.data(), cons.size() * sizeof(ezpz_constraint_t)) != 0) continue;
+        if (var_ids && std::memcmp(e.var_ids.data(), var_ids, n_vars * sizeof(uint32_t)) != 0) continue;
+        e.last_use = ++C.clock;
+        ++C.hits;
+        *out = e.S;
+        *owned = false;
+        return EZPZ_OK;
+    }
+    ++C.misses;
+    const int32_t rc = ezpz_b200_structure_create(cons.data(), (uint32_t)cons.size(), var_ids, n_vars, out, detail);
+    if (rc != EZPZ_OK) return rc;
+    if (C.entries.size() >= kCacheEntries) {
+        size_t oldest = 0;
+        for (size_t k = 1; k < C.entries.size(); ++k)
+            if (C.entries[k].last_use < C.entries[oldest].last_use) oldest = k;
+        ezpz_b200_structure_destroy(C.entries[oldest].S);
+        C.entries.erase(C.entries.begin() + oldest);
+    }
+    CachedStructure e;
+    e.hash = h;
+    e.cons = cons;
+    if (var_ids) e.var_ids.assign(var_ids, var_ids + n_vars);
+    e.has_var_ids = var_ids != nullptr;
+    e.n_vars = n_vars;
+    e.S = *out;
+    e.last_use = ++C.clock;
+    C.entries.push_back(std::move(e));
+    *owned = false;
+    return EZPZ_OK;
+}
 
 constexpr double kEpsilon = 1e-4;  // lib.rs:43
 bool nearly_eq(double a, double b) { return std::fabs(a - b) < kEpsilon; }  // warnings.rs:85-87
@@ -80,7 +157,8 @@ int32_t solve_level(ezpz_context_t* ctx, const std::vector<ezpz_constraint_t>& c
         else if (nearly_eq(deg, 90.0) || nearly_eq(deg, -90.0)) L.warnings.push_back({(int64_t)ids[k], 2u, 1u, deg});
     }
     ezpz_structure_t* S = nullptr;
-    int32_t rc = ezpz_b200_structure_create(cons.data(), nc, var_ids, n_vars, &S, detail);
+    bool owned = true;
+    int32_t rc = cached_structure(ctx, cons, var_ids, n_vars, &S, &owned, detail);
     if (rc != EZPZ_OK) {
         if (rc == EZPZ_ERR_MISSING_GUESS && detail) detail->constraint_id = ids[detail->constraint_id];
         return rc;
@@ -120,11 +198,21 @@ int32_t solve_level(ezpz_context_t* ctx, const std::vector<ezpz_constraint_t>& c
             for (uint32_t j = 0; j < n_vars; ++j)
                 if (mask[j >> 5] & (1u << (j & 31u))) L.under.push_back(j);
     }
-    ezpz_b200_structure_destroy(S);
+    if (owned) ezpz_b200_structure_destroy(S);
     return rc;
 }
 
 }  // namespace
+
+namespace ezs {
+void release_structure_cache(ezpz_context* ctx) {
+    if (!ctx || !ctx->structure_cache) return;
+    StructureCache* C = static_cast<StructureCache*>(ctx->structure_cache);
+    for (CachedStructure& e : C->entries) ezpz_b200_structure_destroy(e.S);
+    delete C;
+    ctx->structure_cache = nullptr;
+}
+}  // namespace ezs
 
 extern "C" int32_t ezpz_b200_solve(ezpz_context_t* ctx, const ezpz_constraint_t* cons, const uint32_t* priorities,
                                    const double* angles_deg, uint32_t n_cons, const uint32_t* var_ids,

@@ -358,3 +358,27 @@ def test_batch_priority_tiers_match_oracle(ctx):
         assert_bitwise(out.final_values[b], o.final_values, f"problem {b}")
         tiers.add(int(out.priority_solved[b]))
     assert tiers == {0, 1, 2}
+
+
+def test_solve_topology_cache(ctx):
+    """ezpz_b200_solve keeps the analysed structures of the last few constraint lists (host_api.cpp): alternating
+    topologies, repeated with new guesses and with a changed target (a different list -> a miss), always the oracle's answer."""
+    C, R = ez.Constraint, ez.ConstraintRequest
+    p, q = ez.DatumPoint.new_xy(0, 1), ez.DatumPoint.new_xy(2, 3)
+
+    def sys_a(d):
+        return [R.highest_priority(c) for c in (C.Fixed(0, 0.0), C.Fixed(1, 0.0), C.Horizontal(ez.DatumLineSegment(p, q)),
+                                                C.Distance(p, q, d))]
+
+    def sys_b():
+        return [R.highest_priority(c) for c in (C.Fixed(0, 1.0), C.Fixed(1, 2.0), C.Vertical(ez.DatumLineSegment(p, q)),
+                                                C.Distance(p, q, 3.0))]
+
+    rng = np.random.default_rng(3)
+    for k in range(12):
+        reqs = sys_a(2.0 + (k // 6)) if k % 2 == 0 else sys_b()
+        g = rng.uniform(-1.0, 4.0, 4)
+        out = ez.solve(reqs, list(enumerate(g)), ctx=ctx)
+        o = orc.solve(ez.records([r.constraint for r in reqs]), g)
+        assert out.iterations() == o.iterations and out.is_satisfied() == (len(o.unsatisfied) == 0)
+        assert_bitwise(np.array(out.final_values()), o.final_values, f"call {k}")
