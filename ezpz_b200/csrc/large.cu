@@ -87,7 +87,7 @@ struct LargeArgs {
     LargeCtrl* ctrl;
     double residual_tolerance, step_tolerance, initial_lambda, cg_rtol;
     uint32_t max_iterations, cg_max_iters;
-    uint32_t n_cons, n_slots, n_tiles, n, m, nnz, n_levels, nnz_l, n_aent;
+    uint32_t n_cons, n_slots, n_tiles, tile_bytes_max, n, m, nnz, n_levels, nnz_l, n_aent;
     uint32_t unit_weights;
     uint32_t X0, R0, RN0, J0, L0, RV0, Y0, D0;
     uint32_t direct;
@@ -109,7 +109,7 @@ struct RegX {
 // kind needs (KindLayout), word-transposed: word w of slot l at tile[w * 32 + l], so a tile is n_words * 128
 // contiguous bytes.  A warp therefore runs one kind (no divergence in the per-kind switch), reads its tile as one
 // contiguous block — the stand-alone assembly kernel pulls it into shared memory with ONE bulk async copy
-// (cp.async.bulk + mbarrier, three tiles in flight per warp) — and the rows, Jacobian slots and variables a group
+// (cp.async.bulk + mbarrier, three to eight tiles in flight per warp) — and the rows, Jacobian slots and variables a group
 // of neighbouring tiles touches stay within a few hundred KB, so partial-sector writes merge in L2.
 __device__ __forceinline__ double rec_double(const uint32_t* rec, uint32_t word) {
     return __hiloint2double((int)rec[(word + 1) * 32], (int)rec[word * 32]);
@@ -246,10 +246,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
 }
 
-constexpr uint32_t kAsmStages = 3;
+constexpr uint32_t kAsmStagesMax = 8;   // tiles in flight per warp: as many as fit its 13 KB of shared memory (3 for the
+                                        // widest record layout, 4-8 for structures whose kinds need fewer words)
 constexpr uint32_t kAsmWarps = 8;                         // warps per CTA of the stand-alone assembly kernel
 constexpr uint32_t kTileBytesMax = kMaxRecWords * 128;    // 4352
-constexpr size_t kAsmSmem = (size_t)kAsmWarps * kAsmStages * kTileBytesMax + kAsmWarps * kAsmStages * sizeof(uint64_t);
+constexpr size_t kAsmWarpBytes = 3 * (size_t)kTileBytesMax;  // 13,056 bytes of tile stages per warp
+constexpr size_t kAsmSmem = (size_t)kAsmWarps * kAsmWarpBytes + kAsmWarps * kAsmStagesMax * sizeof(uint64_t);
 
 // NaN-ignoring max |v[i]| over the grid: per-block partial to partials[blockIdx.x]; caller syncs, then every
 // thread folds the partials (same order everywhere).
@@ -992,9 +994,10 @@ __global__ void __launch_bounds__(kBlock, 1) lm_large_kernel(const LargeArgs a) 
 __global__ void __launch_bounds__(kAsmWarps * 32, 2) assemble_large_kernel(const LargeArgs a, const bool write_jr) {
     extern __shared__ __align__(128) unsigned char asm_smem[];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-    unsigned char* stage_base = asm_smem + (size_t)warp * kAsmStages * kTileBytesMax;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(asm_smem + (size_t)kAsmWarps * kAsmStages * kTileBytesMax) + warp * kAsmStages;
+    unsigned char* stage_base = asm_smem + (size_t)warp * kAsmWarpBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(asm_smem + (size_t)kAsmWarps * kAsmWarpBytes) + warp * kAsmStagesMax;
     const uint32_t gw = blockIdx.x * kAsmWarps + warp, nw = gridDim.x * kAsmWarps;
+    const uint32_t kStageBytes = a.tile_bytes_max, kAsmStages = min(kAsmStagesMax, (uint32_t)(kAsmWarpBytes / kStageBytes));
     if (lane == 0) {
         for (uint32_t st = 0; st < kAsmStages; ++st) mbar_init(&bars[st], 1);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -1006,7 +1009,7 @@ __global__ void __launch_bounds__(kAsmWarps * 32, 2) assemble_large_kernel(const
         const uint32_t bytes = (uint32_t)a.layout[td.meta & 0xffu].n_words * 128u;
         const uint32_t st = k % kAsmStages;
         mbar_expect_tx(&bars[st], bytes);
-        bulk_copy_g2s(stage_base + (size_t)st * kTileBytesMax, a.recs + (size_t)td.off16 * 4, bytes, &bars[st]);
+        bulk_copy_g2s(stage_base + (size_t)st * kStageBytes, a.recs + (size_t)td.off16 * 4, bytes, &bars[st]);
     };
     if (lane == 0)
         for (uint32_t k = 0; k < kAsmStages && k < count; ++k) issue(k);
@@ -1029,10 +1032,10 @@ __global__ void __launch_bounds__(kAsmWarps * 32, 2) assemble_large_kernel(const
             mbar_wait(&bars[sn], ((k + 1) / kAsmStages) & 1u);
             if (lane < (tn.meta >> 8))
                 gather_x(a, a.layout[tn.meta & 0xffu], tn.meta & 0xffu,
-                         reinterpret_cast<const uint32_t*>(stage_base + (size_t)sn * kTileBytesMax) + lane, xn);
+                         reinterpret_cast<const uint32_t*>(stage_base + (size_t)sn * kStageBytes) + lane, xn);
         }
         if (lane < n_valid)
-            assemble_slot<true, true>(a, a.layout[kind], kind, reinterpret_cast<const uint32_t*>(stage_base + (size_t)st * kTileBytesMax) + lane,
+            assemble_slot<true, true>(a, a.layout[kind], kind, reinterpret_cast<const uint32_t*>(stage_base + (size_t)st * kStageBytes) + lane,
                                       t * 32 + lane, a.R0, write_jr, xv);
         __syncwarp();
         if (lane == 0 && k + kAsmStages < count) {
@@ -1061,7 +1064,7 @@ struct LargeDevice {
     TileDesc* tiles = nullptr;
     uint8_t* side_flags = nullptr;
     KindLayout layout[EZPZ_K_COUNT];
-    uint32_t n_slots = 0, n_tiles = 0;
+    uint32_t n_slots = 0, n_tiles = 0, tile_bytes_max = 128;
     uint32_t *csr_row_ptr = nullptr, *csr_col_idx = nullptr, *csc_col_ptr = nullptr, *csc_row_idx = nullptr;
     uint32_t* direct_tables[11] = {};  // device copies of the LargeProgram arrays of the sparse direct solve
     double *vg = nullptr, *jr = nullptr, *cgv = nullptr, *partials = nullptr, *sumsq = nullptr;
@@ -1170,6 +1173,8 @@ int32_t get_large(ezpz_context* ctx, const ezpz_structure* s, DeviceCopy* dc, La
         EZ_TRY(upload(&L->side_flags, flags, detail));
         L->n_slots = n_slots;
         L->n_tiles = n_tiles;
+        for (uint32_t t = 0; t < n_tiles; ++t)
+            L->tile_bytes_max = std::max<uint32_t>(L->tile_bytes_max, (uint32_t)L->layout[tiles[t].meta & 0xffu].n_words * 128u);
     }
     EZ_TRY(upload(&L->csr_row_ptr, s->csr_row_ptr, detail));
     EZ_TRY(upload(&L->csr_col_idx, s->csr_col_idx, detail));
@@ -1227,6 +1232,7 @@ void fill_args(LargeArgs& a, const ezpz_structure* s, const DeviceCopy* dc, cons
     std::memcpy(a.layout, L->layout, sizeof a.layout);
     a.n_slots = L->n_slots;
     a.n_tiles = L->n_tiles;
+    a.tile_bytes_max = L->tile_bytes_max;
     a.unit_weights = s->all_weights_one ? 1u : 0u;
     a.csr_row_ptr = L->csr_row_ptr;
     a.csr_col_idx = L->csr_col_idx;
