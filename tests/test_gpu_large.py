@@ -153,3 +153,28 @@ def test_large_path_failed_factorisations(ctx, cells):
     finite = np.isfinite(o.final_values)
     assert np.array_equal(np.isfinite(out.final_values), finite)
     assert_bitwise(out.final_values[finite], o.final_values[finite], "finite final values")
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4])
+def test_random_systems_all_kinds_large_path(ctx, seed):
+    """Random constraint soups (all 25 kinds, weights, given and undefined tangent sides; inconsistent, rank deficient,
+    sometimes degenerate) on 400 variables through the large path: whatever the LM trajectory does — failed
+    factorisations, rejected steps, no convergence — it is the oracle's trajectory (same order and sum chunking):
+    iteration count, verdict bits and every finite coordinate bit for bit."""
+    from test_gpu_parity import random_constraints
+    rng = np.random.default_rng(1000 + seed)
+    n_vars = 400
+    cons = random_constraints(rng, 420 + 40 * seed, n_vars)
+    weights = rng.choice([1.0, 0.5, 3.0], len(cons)) if seed % 2 else np.ones(len(cons))
+    recs = ez.records(cons, weights)
+    g = rng.uniform(-8.0, 8.0, n_vars)
+    st = ez.Structure(recs, n_vars)
+    od = st.ordering()
+    assert od["path"] == 1
+    out = ctx.solve_one(st, g)
+    o = orc.solve_inner_ordered(recs, g, od["elim_order"], od["sum_chunk"])
+    assert out.iterations == o.iterations and out.converged == o.converged
+    assert out.unsatisfied == o.unsatisfied
+    finite = np.isfinite(o.final_values)
+    assert np.array_equal(np.isfinite(out.final_values), finite)
+    assert_bitwise(out.final_values[finite], o.final_values[finite], "finite final values")
