@@ -22,10 +22,12 @@
 // Arithmetic-order spec in elimination numbering j <-> variable perm[j]: identical formulas to
 // the natural-order oracle applied to P A Pt; tests pass `perm` to the oracle to check bit-exactness.
 #include <algorithm>
+#include <chrono>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <numeric>
+#include <thread>
 #include <vector>
 
 #include "structure.h"
@@ -216,7 +218,16 @@ void build_sparse_direct(ezpz_structure& S) {
     if (n == 0) return;
     const char* force = std::getenv("EZPZ_B200_FORCE_PCG");
     if (force && force[0] == '1') return;
+    const auto t_start = std::chrono::steady_clock::now();
+    auto lap = [&, last = t_start](const char* what) mutable {
+        const char* dbg = std::getenv("EZPZ_B200_DEBUG");
+        if (!(dbg && dbg[0] == '1')) return;
+        const auto now = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[sparse_direct] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(now - last).count());
+        last = now;
+    };
     const Graph g = build_graph(S);
+    lap("adjacency");
 
     // ---- 2. elimination order ---------------------------------------------------------------------
     std::vector<uint32_t> perm(n), iperm(n), parent, level;
@@ -240,6 +251,7 @@ void build_sparse_direct(ezpz_structure& S) {
         }
     }
 
+    lap("ordering");
     // ---- 3. symbolic factorisation, by columns -----------------------------------------------------
     // struct(L_j) = {i > j : A_perm(i, j) != 0}  U  (struct(L_c) \ {j}) over the etree children c of j.
     std::vector<uint32_t> lc_ptr((size_t)n + 1, 0), lc_row;
@@ -284,6 +296,7 @@ void build_sparse_direct(ezpz_structure& S) {
     }
     const size_t nnz_l_true = lc_row.size();
 
+    lap("symbolic factorisation");
     // ---- 4. supernodes: maximal chains of the elimination tree, at most kMaxPanelWidth columns -------
     // Column j + 1 continues column j's supernode when j's parent is j + 1 and j + 1 has no other child: along such
     // a chain struct(L_{j+1}) contains struct(L_j) \ {j + 1}, so the columns share (almost) one row structure and
@@ -350,6 +363,7 @@ void build_sparse_direct(ezpz_structure& S) {
         }
         return (uint32_t)(it - b);
     };
+    lap("supernodes and panels");
     // ---- 5. update lists: which descendant supernodes K update supernode J, and where K's rows land in J ----
     // K's rows below its own columns, grouped by the supernode that owns them: every group is one (J <- K) update;
     // the rows of K from the group's start to the end of K's list all lie inside J's panel (elimination tree).
@@ -406,6 +420,7 @@ void build_sparse_direct(ezpz_structure& S) {
             r[4] = P.sn_ptr[K];
         }
     }
+    lap("update lists");
     // ---- 6. stages: height of every supernode in the supernode tree; small panels and large panels apart ----
     std::vector<uint32_t> sn_level(n_sn, 0);
     uint32_t n_stages = 0;
@@ -443,38 +458,89 @@ void build_sparse_direct(ezpz_structure& S) {
         r[5] = P.upd_ptr[sn];
         r[6] = P.upd_ptr[sn + 1] - P.upd_ptr[sn];
     }
+    lap("stages and records");
     // ---- 7. A = JtJ: products of every entry A has, addressed to its panel slot; diagonal slots ---------------
+    // Independent per column: column ranges are processed by a few threads into private lists that are then
+    // concatenated in column order.
     {
-        P.aent_slot.clear();
-        P.aprod_ptr.assign(1, 0u);
-        P.aprod_a.clear();
-        P.aprod_b.clear();
         P.diag_slot.resize(n);
-        for (uint32_t j = 0; j < n; ++j) {
-            const uint32_t J = sn_of[j], j0 = P.sn_ptr[J], w = panel_w(J);
-            P.diag_slot[j] = P.panel_off[J] + (j - j0) * w + (j - j0);
-            const uint32_t cj = perm[j];
-            for (uint32_t q = lc_ptr[j]; q < lc_ptr[j + 1]; ++q) {
-                if (!lc_in_a[q]) continue;
-                const uint32_t i = lc_row[q], ci = perm[i];
-                const uint32_t pos = i < P.sn_ptr[J + 1] ? i - j0 : pos_in(J, i);
-                uint32_t pi = S.csc_col_ptr[ci], pj = S.csc_col_ptr[cj];
-                const uint32_t pie = S.csc_col_ptr[ci + 1], pje = S.csc_col_ptr[cj + 1];
-                while (pi < pie && pj < pje) {
-                    const uint32_t ri = S.csc_row_idx[pi], rj = S.csc_row_idx[pj];
-                    if (ri == rj) {
-                        P.aprod_a.push_back(pi);
-                        P.aprod_b.push_back(pj);
-                        ++pi;
-                        ++pj;
-                    } else if (ri < rj) ++pi;
-                    else ++pj;
+        struct Part {
+            std::vector<uint32_t> slot, cnt, pa, pb;
+            bool bad = false;
+        };
+        const uint32_t nt = n < (1u << 16) ? 1u : std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+        std::vector<Part> parts(nt);
+        auto work = [&](uint32_t t) {
+            Part& part = parts[t];
+            const uint32_t c0 = (uint32_t)((uint64_t)n * t / nt), c1 = (uint32_t)((uint64_t)n * (t + 1) / nt);
+            for (uint32_t j = c0; j < c1; ++j) {
+                const uint32_t J = sn_of[j], j0 = P.sn_ptr[J], j1 = P.sn_ptr[J + 1], w = j1 - j0;
+                P.diag_slot[j] = P.panel_off[J] + (j - j0) * w + (j - j0);
+                const uint32_t cj = perm[j];
+                // rows of the panel below the diagonal block, walked together with the column's (ascending) rows
+                const uint32_t* prow = P.sn_rows.data() + P.sn_row_ptr[J];
+                const uint32_t ph = P.sn_row_ptr[J + 1] - P.sn_row_ptr[J];
+                uint32_t pp = w;
+                for (uint32_t q = lc_ptr[j]; q < lc_ptr[j + 1]; ++q) {
+                    if (!lc_in_a[q]) continue;
+                    const uint32_t i = lc_row[q], ci = perm[i];
+                    uint32_t pos;
+                    if (i < j1) pos = i - j0;
+                    else {
+                        while (pp < ph && prow[pp] < i) ++pp;
+                        if (pp >= ph || prow[pp] != i) {
+                            part.bad = true;
+                            continue;
+                        }
+                        pos = pp;
+                    }
+                    uint32_t pi = S.csc_col_ptr[ci], pj = S.csc_col_ptr[cj], found = 0;
+                    const uint32_t pie = S.csc_col_ptr[ci + 1], pje = S.csc_col_ptr[cj + 1];
+                    while (pi < pie && pj < pje) {
+                        const uint32_t ri = S.csc_row_idx[pi], rj = S.csc_row_idx[pj];
+                        if (ri == rj) {
+                            part.pa.push_back(pi);
+                            part.pb.push_back(pj);
+                            ++found;
+                            ++pi;
+                            ++pj;
+                        } else if (ri < rj) ++pi;
+                        else ++pj;
+                    }
+                    part.slot.push_back(P.panel_off[J] + pos * w + (j - j0));
+                    part.cnt.push_back(found);
                 }
-                P.aent_slot.push_back(P.panel_off[J] + pos * w + (j - j0));
-                P.aprod_ptr.push_back((uint32_t)P.aprod_a.size());
             }
+        };
+        if (nt == 1) work(0);
+        else {
+            std::vector<std::thread> pool;
+            for (uint32_t t = 0; t < nt; ++t) pool.emplace_back(work, t);
+            for (auto& th : pool) th.join();
+        }
+        size_t n_ent = 0, n_prod = 0;
+        for (const Part& part : parts) {
+            n_ent += part.slot.size();
+            n_prod += part.pa.size();
+            inconsistent = inconsistent || part.bad;
+        }
+        P.aent_slot.clear();
+        P.aent_slot.reserve(n_ent);
+        P.aprod_ptr.assign(1, 0u);
+        P.aprod_ptr.reserve(n_ent + 1);
+        P.aprod_a.clear();
+        P.aprod_a.reserve(n_prod);
+        P.aprod_b.clear();
+        P.aprod_b.reserve(n_prod);
+        for (const Part& part : parts) {
+            P.aent_slot.insert(P.aent_slot.end(), part.slot.begin(), part.slot.end());
+            P.aprod_a.insert(P.aprod_a.end(), part.pa.begin(), part.pa.end());
+            P.aprod_b.insert(P.aprod_b.end(), part.pb.begin(), part.pb.end());
+            uint32_t run = P.aprod_ptr.back();
+            for (uint32_t c : part.cnt) P.aprod_ptr.push_back(run += c);
         }
     }
+    lap("products of A");
     if (inconsistent) {
         std::fprintf(stderr, "[ezpz_b200] sparse_direct: inconsistent panel structure, using the PCG path\n");
         return;

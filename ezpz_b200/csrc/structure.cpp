@@ -12,6 +12,7 @@
 #include "structure.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -28,23 +29,32 @@ void set_detail(ezpz_error_detail_t* d, const char* msg) {
     std::snprintf(d->message, sizeof d->message, "%s", msg);
 }
 
-// lower(A) by columns from the CSR rows of J: (i, j), i >= j, whenever some row holds both columns.
+// lower(A) by columns from the patterns of J: column j holds every i >= j that shares a row with j (and j itself:
+// lambda*I puts every diagonal in).  For each column its rows are walked in CSC order and their CSR entries >= j
+// collected with a marker array; the short list is then sorted.
 void build_a_pattern(ezpz_structure& S) {
     const uint32_t n = S.n;
-    std::vector<std::vector<uint32_t>> cols(n);
-    for (uint32_t j = 0; j < n; ++j) cols[j].push_back(j);  // lambda*I puts every diagonal in
-    for (uint32_t r = 0; r < S.m; ++r) {
-        const uint32_t b = S.csr_row_ptr[r], e = S.csr_row_ptr[r + 1];
-        for (uint32_t p = b; p < e; ++p)
-            for (uint32_t q = p; q < e; ++q) cols[S.csr_col_idx[p]].push_back(S.csr_col_idx[q]);  // col p <= col q
-    }
-    S.a_col_ptr.assign(n + 1, 0);
+    S.a_col_ptr.assign((size_t)n + 1, 0);
     S.a_row_idx.clear();
+    S.a_row_idx.reserve(S.csc_row_idx.size() * 3 + n);
+    std::vector<uint32_t> mark(n, UINT32_MAX), col;
     for (uint32_t j = 0; j < n; ++j) {
-        auto& c = cols[j];
-        std::sort(c.begin(), c.end());
-        c.erase(std::unique(c.begin(), c.end()), c.end());
-        S.a_row_idx.insert(S.a_row_idx.end(), c.begin(), c.end());
+        col.clear();
+        col.push_back(j);
+        mark[j] = j;
+        for (uint32_t p = S.csc_col_ptr[j]; p < S.csc_col_ptr[j + 1]; ++p) {
+            const uint32_t r = S.csc_row_idx[p];
+            for (uint32_t q = S.csr_row_ptr[r + 1]; q-- > S.csr_row_ptr[r];) {  // columns descending: stop below j
+                const uint32_t i = S.csr_col_idx[q];
+                if (i <= j) break;
+                if (mark[i] != j) {
+                    mark[i] = j;
+                    col.push_back(i);
+                }
+            }
+        }
+        std::sort(col.begin(), col.end());
+        S.a_row_idx.insert(S.a_row_idx.end(), col.begin(), col.end());
         S.a_col_ptr[j + 1] = (uint32_t)S.a_row_idx.size();
     }
 }
@@ -334,12 +344,22 @@ int32_t ezpz_b200_structure_create(const ezpz_constraint_t* cons, uint32_t n_con
     }
     ezpz_structure* S = new (std::nothrow) ezpz_structure();
     if (!S) return EZPZ_ERR_INVALID_ARGUMENT;
+    auto lap = [last = std::chrono::steady_clock::now()](const char* what) mutable {
+        const char* dbg = std::getenv("EZPZ_B200_DEBUG");
+        if (!(dbg && dbg[0] == '1')) return;
+        const auto now = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[structure]     %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(now - last).count());
+        last = now;
+    };
     S->n_cons = n_cons;
     S->n = n_vars;
     S->cons.assign(cons, cons + n_cons);
     // 2. rows and pairs
     S->cons_row0.assign(n_cons + 1, 0);
-    std::vector<uint64_t> pairs;  // (col << 32) | row: sorting gives CSC order
+    // Pairs (row, col) are generated row by row, so a STABLE counting sort by column leaves every column's rows
+    // ascending and duplicates (a variable named twice by one row) adjacent: sort + dedup in O(nnz), which is what
+    // faer's try_new_from_indices does with a comparison sort (solver.rs:255-256).
+    std::vector<uint32_t> pr, pc;  // row, col of every named (row, variable)
     uint32_t row_num = 0;
     for (uint32_t c = 0; c < n_cons; ++c) {
         const ezk::KindInfo& ki = ezk::kKinds[cons[c].kind];
@@ -352,14 +372,21 @@ int32_t ezpz_b200_structure_create(const ezpz_constraint_t* cons, uint32_t n_con
                     delete S;
                     return EZPZ_ERR_MATRIX;
                 }
-                pairs.push_back(((uint64_t)v << 32) | row_num);
+                pr.push_back(row_num);
+                pc.push_back(v);
             }
             ++row_num;
         }
     }
     S->cons_row0[n_cons] = row_num;
     S->m = row_num;
-    std::sort(pairs.begin(), pairs.end());
+    std::vector<uint64_t> pairs(pr.size());  // (col << 32) | row in CSC order
+    {
+        std::vector<uint32_t> start((size_t)n_vars + 1, 0);
+        for (uint32_t v : pc) start[v + 1]++;
+        for (uint32_t j = 0; j < n_vars; ++j) start[j + 1] += start[j];
+        for (size_t k = 0; k < pr.size(); ++k) pairs[start[pc[k]]++] = ((uint64_t)pc[k] << 32) | pr[k];
+    }
     pairs.erase(std::unique(pairs.begin(), pairs.end()), pairs.end());
     const size_t nnz = pairs.size();
     S->csc_col_ptr.assign((size_t)n_vars + 1, 0);
@@ -386,6 +413,7 @@ int32_t ezpz_b200_structure_create(const ezpz_constraint_t* cons, uint32_t n_con
             S->csc_to_csr[k] = pos;
         }
     }
+    lap("pattern of J (sort, CSC, CSR)");
     // 3. analysed constraints with scatter slots
     S->dev_cons.resize(n_cons);
     S->n_side = 0;
@@ -424,7 +452,9 @@ int32_t ezpz_b200_structure_create(const ezpz_constraint_t* cons, uint32_t n_con
             }
         }
     }
+    lap("scatter slots");
     build_a_pattern(*S);
+    lap("pattern of A");
     // The symbolic factorisation is skipped for very large systems (they take the PCG path, large.cu).
     S->have_l_pattern = n_vars <= kMaxSymbolicVars;
     if (S->have_l_pattern) build_l_pattern(*S);
@@ -433,8 +463,10 @@ int32_t ezpz_b200_structure_create(const ezpz_constraint_t* cons, uint32_t n_con
         S->l_row_idx.clear();
     }
     build_components(*S);
+    lap("natural L pattern, components");
     if (S->have_l_pattern) build_small_program(*S);
     if (!S->small.valid) build_large_program(*S);
+    lap("programme");
     *out = S;
     return EZPZ_OK;
 }
