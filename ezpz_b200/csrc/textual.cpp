@@ -540,10 +540,21 @@ int32_t ezpz_b200_problem_system(ezpz_problem_t* P, const ezpz_constraint_t** co
                 if (gs.count(lab)) return text_err(EZPZ_ERR_TEXT_UNUSED_GUESSES, "You gave a guess for points which weren't defined: %s", lab);
         }
         const uint32_t np = (uint32_t)P->points.size(), ncirc = (uint32_t)P->circles.size();
-        auto index_of = [](const std::vector<std::string>& v, const std::string& s) -> int {
-            for (size_t q = 0; q < v.size(); ++q)
-                if (v[q] == s) return (int)q;
-            return -1;
+        // Label -> index tables (first declaration wins, as a linear scan would find it).  The reference resolves
+        // every label with a linear scan and a format! per candidate (executor.rs:121-174), quadratic in the number
+        // of points; here a lookup is one hash probe, so a 160,000-line file resolves in milliseconds.
+        auto make_index = [](const std::vector<std::string>& v) {
+            std::unordered_map<std::string, int> m;
+            m.reserve(v.size() * 2);
+            for (size_t q = 0; q < v.size(); ++q) m.emplace(v[q], (int)q);
+            return m;
+        };
+        const std::unordered_map<std::string, int> ix_points = make_index(P->points), ix_circles = make_index(P->circles),
+                                                   ix_arcs = make_index(P->arcs);
+        auto index_of = [&](const std::vector<std::string>& v, const std::string& s) -> int {
+            const auto& m = &v == &P->points ? ix_points : (&v == &P->circles ? ix_circles : ix_arcs);
+            const auto it = m.find(s);
+            return it == m.end() ? -1 : it->second;
         };
         auto strip = [](const std::string& s, const char* suffix, std::string& base) {
             size_t k = std::strlen(suffix);
