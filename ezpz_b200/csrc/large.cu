@@ -89,6 +89,7 @@ struct LargeArgs {
     uint32_t max_iterations, cg_max_iters;
     uint32_t n_cons, n_slots, n_tiles, tile_bytes_max, n, m, nnz, n_levels, nnz_l, n_aent;
     uint32_t unit_weights;
+    uint32_t cluster;  // launched as one thread-block cluster (mid-size systems)
     uint32_t X0, R0, RN0, J0, L0, RV0, Y0, D0;
     uint32_t direct;
 };
@@ -684,27 +685,38 @@ __device__ __noinline__ void sn_backward(const LargeArgs& a, uint32_t pos, uint3
     team_sync<TEAM>();
 }
 
-// One stage of the supernode tree, run by the whole grid (or its only CTA).  Tiny panels: one per thread.  The others:
-// one per warp while the stage has more of them than the grid has CTAs, else one per CTA (cta_stage = the CTA's whole
-// dynamic shared memory; warp_stage = this warp's slice of it).  (Four 8-lane teams per warp were measured slower on
+// One stage of the supernode tree, run by the whole grid (or cluster, or single CTA).  Tiny panels: one per thread.
+// Panels that fit a warp's stage: one per warp while the stage has more of them than the grid has CTAs, else one per
+// CTA.  Larger panels: always one per CTA (cta_stage = the CTA's whole dynamic shared memory; warp_stage = this warp's
+// slice of it).  (Four 8-lane teams per warp were measured slower on
 // the bottom stages: diverged teams of one warp execute one after the other.)
 __device__ void direct_factor_stage(const LargeArgs& a, uint32_t st, uint32_t tid, uint32_t nth, double* warp_stage, double* cta_stage) {
-    const uint32_t b0 = __ldg(a.stage_ptr + 2 * st), b1 = __ldg(a.stage_ptr + 2 * st + 1), b2 = __ldg(a.stage_ptr + 2 * st + 2);
+    const uint32_t b0 = __ldg(a.stage_ptr + 3 * st), b1 = __ldg(a.stage_ptr + 3 * st + 1), b2 = __ldg(a.stage_ptr + 3 * st + 2),
+                   b3 = __ldg(a.stage_ptr + 3 * st + 3);
     for (uint32_t k = b0 + tid; k < b1; k += nth) sn_factor<1>(a, k, 0, nullptr);
     if (b2 - b1 > gridDim.x) {
         for (uint32_t k = b1 + (tid >> 5); k < b2; k += nth >> 5) sn_factor<32>(a, k, threadIdx.x & 31u, warp_stage);
+        __syncthreads();  // the CTA panels below reuse the warps' shared memory
+        for (uint32_t k = b2 + blockIdx.x; k < b3; k += gridDim.x) sn_factor<512>(a, k, threadIdx.x, cta_stage);
     } else {
-        for (uint32_t k = b1 + blockIdx.x; k < b2; k += gridDim.x) sn_factor<512>(a, k, threadIdx.x, cta_stage);
+        for (uint32_t k = b1 + blockIdx.x; k < b3; k += gridDim.x) sn_factor<512>(a, k, threadIdx.x, cta_stage);
     }
 }
-__device__ void direct_backward_stage(const LargeArgs& a, uint32_t st, uint32_t tid, uint32_t nth, double* warp_stage) {
-    const uint32_t b0 = __ldg(a.stage_ptr + 2 * st), b1 = __ldg(a.stage_ptr + 2 * st + 1), b2 = __ldg(a.stage_ptr + 2 * st + 2);
+__device__ void direct_backward_stage(const LargeArgs& a, uint32_t st, uint32_t tid, uint32_t nth, double* warp_stage, double* cta_stage) {
+    const uint32_t b0 = __ldg(a.stage_ptr + 3 * st), b1 = __ldg(a.stage_ptr + 3 * st + 1), b2 = __ldg(a.stage_ptr + 3 * st + 2),
+                   b3 = __ldg(a.stage_ptr + 3 * st + 3);
     for (uint32_t k = b0 + tid; k < b1; k += nth) sn_backward<1>(a, k, 0, nullptr);
     for (uint32_t k = b1 + (tid >> 5); k < b2; k += nth >> 5) sn_backward<32>(a, k, threadIdx.x & 31u, warp_stage);
+    if (b3 > b2) {
+        __syncthreads();
+        for (uint32_t k = b2 + blockIdx.x; k < b3; k += gridDim.x) sn_backward<512>(a, k, threadIdx.x, cta_stage);
+    }
 }
 
 static_assert(team_stage_doubles<512>() <= (512 / 32) * kWarpStageDoubles, "the CTA team's stage must fit the CTA's dynamic shared memory");
 constexpr uint32_t kBlock = 512;
+constexpr uint32_t kClusterCtas = 8;        // portable maximum cluster size
+constexpr size_t kSingleCtaWork = 4096;     // n + m + nnz up to which one CTA runs the whole solve
 constexpr uint32_t kSmDoubles = 4096;  // 32 KB staging
 
 // Constraint::set_from_initial_values (constraints.rs:146-193, called at lib.rs:183-186): only the two tangent
@@ -745,10 +757,15 @@ __global__ void __launch_bounds__(kBlock, 1) lm_large_kernel(const LargeArgs a) 
     extern __shared__ double warp_stage_all[];  // (kBlock / 32) * kWarpStageDoubles, see kLmDynamicSmem
     double* warp_stage = warp_stage_all + (threadIdx.x >> 5) * kWarpStageDoubles;
     cg::grid_group grid = cg::this_grid();
-    const bool single = gridDim.x == 1;
+    // Three launch shapes: one CTA (barrier = __syncthreads), one thread-block cluster of kClusterCtas CTAs for mid-size
+    // systems (hardware cluster barrier, ~0.2 us, acquire/release at cluster scope), the whole GPU (cooperative grid barrier).
+    const bool single = gridDim.x == 1, clustered = a.cluster != 0;
     auto sync = [&]() {
         if (single) __syncthreads();
-        else grid.sync();
+        else if (clustered) {
+            asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+            asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+        } else grid.sync();
     };
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
     const uint32_t G = gridDim.x;
@@ -794,7 +811,7 @@ __global__ void __launch_bounds__(kBlock, 1) lm_large_kernel(const LargeArgs a) 
             return *ctrl_slot;
         }
         chunk_sum_squares(v, a.m, a.sumsq, tid, nth, warp_stage);
-        grid.sync();
+        sync();
         return fold_sum(a.sumsq, n_chunks, sm);
     };
 
@@ -828,7 +845,7 @@ __global__ void __launch_bounds__(kBlock, 1) lm_large_kernel(const LargeArgs a) 
             lap(3);
             for (uint32_t st = a.n_levels; st-- > 0;) {
                 const unsigned long long t0 = a.lvl_ns ? now_ns() : 0ull;
-                direct_backward_stage(a, st, tid, nth, warp_stage);
+                direct_backward_stage(a, st, tid, nth, warp_stage, warp_stage_all);
                 sync();
                 if (a.lvl_ns && tid == 0) a.lvl_ns[2 * st + 1] += now_ns() - t0;
             }
@@ -1073,6 +1090,7 @@ struct LargeDevice {
     uint32_t *degen = nullptr, *unsat = nullptr;
     LargeCtrl* ctrl = nullptr;
     int grid = 0;
+    bool cluster = false;
     bool tables = false;
 };
 
@@ -1206,7 +1224,9 @@ int32_t get_large(ezpz_context* ctx, const ezpz_structure* s, DeviceCopy* dc, La
             "cudaFuncSetAttribute(lm_large_kernel)");
     EZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lm_large_kernel, kBlock, kLmDynamicSmem), "occupancy");
     if (per_sm < 1) per_sm = 1;
-    L->grid = work <= 65536 ? 1 : ctx->sm_count * std::min(per_sm, 2);
+    // tiny systems: one CTA; up to 65,536 values: one cluster of 8 CTAs; beyond: every SM, co-resident
+    L->grid = work <= kSingleCtaWork ? 1 : (work <= 65536 ? (int)kClusterCtas : ctx->sm_count * std::min(per_sm, 2));
+    L->cluster = work > kSingleCtaWork && work <= 65536;
     EZ_CUDA(cudaMalloc(&L->partials, sizeof(double) * 3 * (size_t)L->grid), "cudaMalloc(partials)");
     uint8_t rows[EZPZ_K_COUNT], emit_len[EZPZ_K_COUNT][2], nids[EZPZ_K_COUNT];
     for (int k = 0; k < EZPZ_K_COUNT; ++k) {
@@ -1342,8 +1362,23 @@ int32_t solve_large(ezpz_context* ctx, const ezpz_structure* s, const ezpz_confi
     cudaStream_t st = ctx->stream;
     EZ_CUDA(cudaMemcpyAsync(L->vg + a.X0, io->guesses, sizeof(double) * s->n, cudaMemcpyHostToDevice, st), "H2D guesses");
     void* params[] = {(void*)&a};
+    a.cluster = L->cluster ? 1u : 0u;
     if (L->grid == 1) {
         lm_large_kernel<<<1, kBlock, kLmDynamicSmem, st>>>(a);
+    } else if (L->cluster) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(kClusterCtas);
+        cfg.blockDim = dim3(kBlock);
+        cfg.dynamicSmemBytes = kLmDynamicSmem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = kClusterCtas;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        EZ_CUDA(cudaLaunchKernelEx(&cfg, lm_large_kernel, a), "cudaLaunchKernelEx(lm_large_kernel, cluster)");
     } else {
         EZ_CUDA(cudaLaunchCooperativeKernel((void*)lm_large_kernel, dim3(L->grid), dim3(kBlock), params, kLmDynamicSmem, st),
                 "cudaLaunchCooperativeKernel(lm_large_kernel)");
@@ -1367,7 +1402,7 @@ int32_t solve_large(ezpz_context* ctx, const ezpz_structure* s, const ezpz_confi
         const LargeProgram& P = s->large;
         for (uint32_t l = 0; l < a.n_levels; ++l)
             std::fprintf(stderr, "  stage %3u panels %7u  factor %8.1f us  backward %8.1f us (all iterations)\n", l,
-                         P.stage_ptr[2 * l + 2] - P.stage_ptr[2 * l], t[2 * l] * 1e-3, t[2 * l + 1] * 1e-3);
+                         P.stage_ptr[3 * l + 3] - P.stage_ptr[3 * l], t[2 * l] * 1e-3, t[2 * l + 1] * 1e-3);
         cudaMemset(a.lvl_ns, 0, sizeof(unsigned long long) * t.size());
     }
     if (dbg && dbg[0] == '1')

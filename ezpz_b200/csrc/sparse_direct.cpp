@@ -41,6 +41,7 @@ constexpr uint32_t kNaturalMaxHeight = 192;     // natural order is kept when it
 constexpr uint32_t kLeafVars = 48;              // dissection stops at parts of this many variables
 constexpr uint64_t kMaxFactorEntries = 1ull << 29;  // beyond this nnz(L) the PCG path is used
 constexpr uint32_t kMaxPanelWidth = 16;         // columns per supernode panel
+constexpr uint32_t kWarpPanelCap = 576;         // doubles of panel a warp team can stage (large.cu: TeamCaps<32>::panel)
 constexpr uint32_t kLanePanel = 8;              // panels of at most this many doubles are factorised by a single thread
 
 struct Graph {
@@ -432,13 +433,16 @@ void build_sparse_direct(ezpz_structure& S) {
             sn_level[ps] = std::max(sn_level[ps], sn_level[s] + 1);
         }
     }
-    P.stage_ptr.assign((size_t)2 * n_stages + 1, 0);  // per stage: [lane-sized panels | warp-sized panels]
-    auto bucket = [&](uint32_t s) {  // a single thread takes panels of a few doubles that receive at most two updates
-        const bool tiny = panel_h(s) * panel_w(s) <= kLanePanel && P.upd_ptr[s + 1] - P.upd_ptr[s] <= 2;
-        return 2 * sn_level[s] + (tiny ? 0u : 1u);
+    P.stage_ptr.assign((size_t)3 * n_stages + 1, 0);  // per stage: [thread panels | warp panels | CTA panels]
+    auto bucket = [&](uint32_t s) {
+        // a single thread takes panels of a few doubles that receive at most two updates; panels that do not fit a warp's
+        // shared-memory stage go to whole CTAs (large.cu: TeamCaps<32>::panel); the rest to warps
+        const uint32_t sz = panel_h(s) * panel_w(s);
+        const bool tiny = sz <= kLanePanel && P.upd_ptr[s + 1] - P.upd_ptr[s] <= 2;
+        return 3 * sn_level[s] + (tiny ? 0u : (sz <= kWarpPanelCap ? 1u : 2u));
     };
     for (uint32_t s = 0; s < n_sn; ++s) P.stage_ptr[bucket(s) + 1]++;
-    for (uint32_t k = 0; k < 2 * n_stages; ++k) P.stage_ptr[k + 1] += P.stage_ptr[k];
+    for (uint32_t k = 0; k < 3 * n_stages; ++k) P.stage_ptr[k + 1] += P.stage_ptr[k];
     P.stage_sn.resize(n_sn);
     {
         std::vector<uint32_t> cur(P.stage_ptr.begin(), P.stage_ptr.end() - 1);
@@ -551,13 +555,14 @@ void build_sparse_direct(ezpz_structure& S) {
                      (int)P.nested, n_sn, n_stages, nnz_l, nnz_l_true, P.upd_sn.size());
         for (uint32_t st = 0; st < n_stages; ++st) {
             uint32_t max_h = 0, max_u = 0;
-            for (uint32_t k = P.stage_ptr[2 * st]; k < P.stage_ptr[2 * st + 2]; ++k) {
+            for (uint32_t k = P.stage_ptr[3 * st]; k < P.stage_ptr[3 * st + 3]; ++k) {
                 const uint32_t sn = P.stage_sn[k];
                 max_h = std::max(max_h, panel_h(sn));
                 max_u = std::max(max_u, P.upd_ptr[sn + 1] - P.upd_ptr[sn]);
             }
-            std::fprintf(stderr, "  stage %u: %u lane-sized + %u warp-sized panels, tallest %u rows, most updates %u\n", st,
-                         P.stage_ptr[2 * st + 1] - P.stage_ptr[2 * st], P.stage_ptr[2 * st + 2] - P.stage_ptr[2 * st + 1], max_h, max_u);
+            std::fprintf(stderr, "  stage %u: %u thread + %u warp + %u CTA panels, tallest %u rows, most updates %u\n", st,
+                         P.stage_ptr[3 * st + 1] - P.stage_ptr[3 * st], P.stage_ptr[3 * st + 2] - P.stage_ptr[3 * st + 1],
+                         P.stage_ptr[3 * st + 3] - P.stage_ptr[3 * st + 2], max_h, max_u);
         }
     }
     P.perm = perm;

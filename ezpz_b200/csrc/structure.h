@@ -71,8 +71,8 @@ struct LargeProgram {
     // The block of K's panel an update reads (rows upd_rbegin[u] to the end, all of K's columns) is contiguous.
     // upd_rec = the 8-word record per update the device reads (sparse_direct.cpp).
     std::vector<uint32_t> upd_ptr, upd_sn, upd_rbegin, upd_ncols, upd_rel_ptr, upd_rel, upd_rec;
-    // Stage k (height in the supernode tree): supernodes stage_sn[stage_ptr[2k] .. stage_ptr[2k+1]) have lane-sized
-    // panels (one thread each), stage_sn[stage_ptr[2k+1] .. stage_ptr[2k+2]) warp-sized ones.
+    // Stage k (height in the supernode tree): stage_sn[stage_ptr[3k] .. stage_ptr[3k+1]) = panels of a few doubles (one
+    // thread each), [3k+1 .. 3k+2) = panels that fit a warp's shared-memory stage, [3k+2 .. 3k+3) = larger ones (one CTA each).
     // stage_rec = the 8-word record per supernode in stage order that the device reads (sparse_direct.cpp).
     std::vector<uint32_t> stage_ptr, stage_sn, stage_rec;
     // A = JtJ: for every entry A has (strictly lower), its panel slot and the products J[r][i] * J[r][j] over shared

@@ -15,12 +15,16 @@ pytestmark = pytest.mark.gpu
 @pytest.mark.parametrize("lines,over", [(500, False), (600, False), (500, True)])
 def test_massive_parallel_system_direct_path(ctx, lines, over):
     """Config 3: 2,000 x 2,000 (README size), the checked-in 2,400 x 2,400 and the overconstrained variant.
-    Level-scheduled direct solve: bit-exact against the oracle."""
+    Sparse direct solve in natural order: bit-exact against the oracle (same sum-of-squares chunking)."""
     recs, n, g, _ = wl.system_from_text(wl.massive_problem_text(lines, over))
     st = ez.Structure(recs, n)
     out = ctx.solve_one(st, g)
     assert out.path_used == 1
-    o = orc.solve_inner(recs, g)
+    od = st.ordering()
+    assert not od["nested"] and od["sum_chunk"] == 1024  # natural order; one cluster of 8 CTAs, chunked sum of squares
+    o = orc.solve_inner_ordered(recs, g, None, od["sum_chunk"])
+    ref = orc.solve_inner(recs, g)  # the reference-faithful sequential sum: same trajectory, same solution to 1e-9
+    assert ref.iterations == o.iterations and np.abs(ref.final_values - o.final_values).max() <= 1e-9
     assert out.iterations == o.iterations and out.converged and out.unsatisfied == []
     if not over:
         assert out.iterations == 2  # README.md:38 "Iterations needed: 2"
@@ -50,9 +54,15 @@ def _check_direct(ctx, cells, system=None, exact_tol=1e-6):
     return od
 
 
-def test_chain_sketch_direct_single_cta(ctx):
-    od = _check_direct(ctx, 64)  # 832 variables: one CTA, nested-dissection order, sequential sum of squares
-    assert od["nested"] and od["sum_chunk"] == 0
+@pytest.mark.parametrize("cells", [8, 16])
+def test_chain_sketch_direct_single_cta(ctx, cells):
+    od = _check_direct(ctx, cells)  # 104 / 208 variables: one CTA, sequential sum of squares
+    assert od["path"] == 1 and od["sum_chunk"] == 0
+
+
+def test_chain_sketch_direct_cluster(ctx):
+    od = _check_direct(ctx, 64)  # 832 variables: one thread-block cluster of 8 CTAs, nested-dissection order
+    assert od["nested"] and od["sum_chunk"] == 1024
 
 
 @pytest.mark.parametrize("cells", [1024, 8192])
