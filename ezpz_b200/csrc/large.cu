@@ -4,22 +4,25 @@
 //
 // One persistent cooperative kernel (lm_large_kernel) runs assembly, the damped step solve, the tentative
 // step, accept/reject, lambda adaptation and both convergence tests; the host launches it once and reads the
-// result.  Phases are separated by grid-wide barriers (a single __syncthreads when the system is small
-// enough for one CTA, which keeps a 2,000-variable solve at a few tens of microseconds).
-//   * assembly      one thread per constraint, kind-sorted order so that warps are mostly kind-uniform;
-//                   residuals to r, partials through precomputed slots into J (CSC order) and a CSR-ordered
-//                   copy for the row-wise SpMV (Model::residual / refresh_jacobian, solver.rs:318-440);
-//   * step solve    (a) sparse Cholesky scheduled by elimination-tree level (sparse_direct.cpp: natural order
-//                   for shallow trees such as the block-diagonal massive_parallel_system, nested dissection
-//                   otherwise): one grid-wide phase per level for factor + forward substitution, one per level
-//                   for the backward substitution; the top of the tree (a few columns per level) is run by a
-//                   single CTA with __syncthreads instead of grid barriers.  Same arithmetic-order spec as the
-//                   small path applied to P A Pt, so results match the oracle (given the same order) bit for bit;
+// result.  Phases are separated by barriers whose kind follows the launch shape: __syncthreads for one CTA (tiny
+// systems), the hardware cluster barrier for one thread-block cluster of 8 CTAs (mid-size systems such as the
+// 2,000-variable massive_parallel_system), the cooperative grid barrier for the whole GPU.
+//   * assembly      one thread per constraint; record tiles of 32 constraints of one kind (tile-local kind sort), so
+//                   a warp runs one kind and neighbouring tiles touch neighbouring rows, slots and variables;
+//                   residuals to r, partials through precomputed slots into J (CSC order) and, on the PCG path, a
+//                   CSR-ordered copy for the row-wise SpMV (Model::residual / refresh_jacobian, solver.rs:318-440);
+//   * step solve    (a) supernodal sparse Cholesky (sparse_direct.cpp: natural order for shallow elimination trees
+//                   such as the block-diagonal massive_parallel_system, nested dissection otherwise; relaxed
+//                   etree-chain supernodes stored as dense panels): one phase per stage of the supernode tree for
+//                   factor + forward substitution, one per stage for the backward substitution; a panel is
+//                   factorised left-looking by one thread, one warp or one CTA depending on its size and on how
+//                   many panels the stage has.  Same arithmetic-order spec as the small path applied to P A Pt, so
+//                   results match the oracle (given the same order) bit for bit;
 //                   (b) when the factor would be too large, Jacobi-preconditioned conjugate gradients on
 //                   (JtJ + lambda I) d = -Jt r, applied matrix-free as Jt (J p) + lambda p (two SpMVs/iteration);
 //   * sum r^2       single-CTA systems: a strictly sequential left fold, as Rust's `.map(|x| x * x).sum()` is
 //                   (newton.rs:45,116) — the accept test `S' < S` is a floating-point tie-breaker, so the
-//                   summation order is part of the reference semantics.  Multi-CTA systems (more than 65,536
+//                   summation order is part of the reference semantics.  Multi-CTA systems (more than 4,096
 //                   values): the same fold inside chunks of 1,024 rows, then a sequential fold of the chunk
 //                   sums (a 1M-row sequential chain would cost 5 ms per evaluation); the oracle reproduces
 //                   this with sum_chunk = 1024.  max|r| and max|d| are order-independent.
@@ -1378,7 +1381,14 @@ int32_t solve_large(ezpz_context* ctx, const ezpz_structure* s, const ezpz_confi
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        EZ_CUDA(cudaLaunchKernelEx(&cfg, lm_large_kernel, a), "cudaLaunchKernelEx(lm_large_kernel, cluster)");
+        if (cudaLaunchKernelEx(&cfg, lm_large_kernel, a) != cudaSuccess) {
+            // no room for a cluster of this shape on this device/partition: the same 8 CTAs with the grid barrier
+            (void)cudaGetLastError();
+            L->cluster = false;
+            a.cluster = 0;
+            EZ_CUDA(cudaLaunchCooperativeKernel((void*)lm_large_kernel, dim3(L->grid), dim3(kBlock), params, kLmDynamicSmem, st),
+                    "cudaLaunchCooperativeKernel(lm_large_kernel)");
+        }
     } else {
         EZ_CUDA(cudaLaunchCooperativeKernel((void*)lm_large_kernel, dim3(L->grid), dim3(kBlock), params, kLmDynamicSmem, st),
                 "cudaLaunchCooperativeKernel(lm_large_kernel)");
