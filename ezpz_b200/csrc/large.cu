@@ -1220,6 +1220,7 @@ int32_t get_large(ezpz_context* ctx, const ezpz_structure* s, DeviceCopy* dc, La
     EZ_CUDA(cudaMalloc(&L->degen, sizeof(uint32_t) * std::max<size_t>(1, s->n_cons)), "cudaMalloc(degen)");
     EZ_CUDA(cudaMalloc(&L->unsat, sizeof(uint32_t) * ((s->n_cons + 31) / 32 + 1)), "cudaMalloc(unsat)");
     EZ_CUDA(cudaMalloc(&L->ctrl, sizeof(LargeCtrl)), "cudaMalloc(ctrl)");
+    EZ_CUDA(cudaMemset(L->ctrl, 0, sizeof(LargeCtrl)), "cudaMemset(ctrl)");  // not every field is written by every path
     // grid: one CTA for small systems (barriers are __syncthreads), else every SM, co-resident
     const size_t work = (size_t)s->n + s->m + nnz;
     int per_sm = 0;
