@@ -631,13 +631,8 @@ int32_t ezpz_b200_solve_batch_device(ezpz_context_t* ctx, const ezpz_structure_t
     if (batch == 0) return EZPZ_OK;
     if (!io->guesses || !io->final_values || !io->iterations || !io->status) return EZPZ_ERR_INVALID_ARGUMENT;
     if (s->n_cons == 0 || s->m == 0) return EZPZ_ERR_EMPTY_SYSTEM;
-    if (!s->small.valid) {
-        if (detail)
-            std::snprintf(detail->message, sizeof detail->message,
-                          "system too large for the batched thread-per-problem kernel (needs %llu doubles per problem)",
-                          (unsigned long long)((uint64_t)s->n + 2ull * s->m + s->csc_row_idx.size() + s->l_row_idx.size() + s->n));
-        return EZPZ_ERR_TOO_LARGE;
-    }
+    if (!s->small.valid)  // beyond the thread-per-problem kernel: the persistent LM kernel, one CTA per problem
+        return ezs::solve_large_batch(ctx, s, config, batch, io, cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream, detail);
     EZ_CUDA(cudaSetDevice(ctx->device), "cudaSetDevice");
     DeviceCopy* dc = nullptr;
     int32_t rc = get_device_copy(ctx, s, &dc, detail);

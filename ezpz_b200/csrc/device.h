@@ -36,6 +36,10 @@ void release_large(DeviceCopy* d);  // large.cu
 int32_t solve_large(ezpz_context* ctx, const ezpz_structure* s, const ezpz_config_t* config, const ezpz_one_io_t* io,
                     ezpz_error_detail_t* detail);
 
+// A batch of such systems, one CTA per problem; device pointers in io, enqueued on st (large.cu).
+int32_t solve_large_batch(ezpz_context* ctx, const ezpz_structure* s, const ezpz_config_t* config, uint64_t batch,
+                          const ezpz_batch_io_t* io, cudaStream_t st, ezpz_error_detail_t* detail);
+
 // ezpz_b200_eval for structures with a large programme: the large path's own assembly kernel (large.cu).
 int32_t eval_large(ezpz_context* ctx, const ezpz_structure* s, const double* x, double* r, double* jac_csc, double* jac_csr,
                    bool* have_csr, ezpz_error_detail_t* detail);

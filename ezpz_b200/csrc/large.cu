@@ -93,6 +93,14 @@ struct LargeArgs {
     uint32_t n_cons, n_slots, n_tiles, tile_bytes_max, n, m, nnz, n_levels, nnz_l, n_aent;
     uint32_t unit_weights;
     uint32_t cluster;  // launched as one thread-block cluster (mid-size systems)
+    uint32_t chunked_sums;  // sum of squares folded in chunks of kSumChunk rows (systems of more than kSingleCtaWork values)
+    // CTAs cooperating on ONE system and this CTA's rank among them (set by the kernel: the whole grid, or 1 / 0 in
+    // batch mode, where every CTA solves its own problem with CTA-level barriers)
+    uint32_t vgrid, vblock;
+    // batch mode (ezpz_b200_solve_batch on structures beyond the thread-per-problem kernel): problem b = blockIdx.x uses
+    // vg + b * vg_stride, jr + b * jr_stride, ... ; 0 = one system per launch
+    uint32_t batch;
+    size_t vg_stride, jr_stride, cgv_stride, sumsq_stride, side_stride, degen_stride, unsat_stride;
     uint32_t X0, R0, RN0, J0, L0, RV0, Y0, D0;
     uint32_t direct;
 };
@@ -252,10 +260,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 
 constexpr uint32_t kAsmStagesMax = 8;   // tiles in flight per warp: as many as fit its 13 KB of shared memory (3 for the
                                         // widest record layout, 4-8 for structures whose kinds need fewer words)
-constexpr uint32_t kAsmWarps = 8;                         // warps per CTA of the stand-alone assembly kernel
 constexpr uint32_t kTileBytesMax = kMaxRecWords * 128;    // 4352
-constexpr size_t kAsmWarpBytes = 3 * (size_t)kTileBytesMax;  // 13,056 bytes of tile stages per warp
-constexpr size_t kAsmSmem = (size_t)kAsmWarps * kAsmWarpBytes + kAsmWarps * kAsmStagesMax * sizeof(uint64_t);
 
 // NaN-ignoring max |v[i]| over the grid: per-block partial to partials[blockIdx.x]; caller syncs, then every
 // thread folds the partials (same order everywhere).
@@ -697,12 +702,12 @@ __device__ void direct_factor_stage(const LargeArgs& a, uint32_t st, uint32_t ti
     const uint32_t b0 = __ldg(a.stage_ptr + 3 * st), b1 = __ldg(a.stage_ptr + 3 * st + 1), b2 = __ldg(a.stage_ptr + 3 * st + 2),
                    b3 = __ldg(a.stage_ptr + 3 * st + 3);
     for (uint32_t k = b0 + tid; k < b1; k += nth) sn_factor<1>(a, k, 0, nullptr);
-    if (b2 - b1 > gridDim.x) {
+    if (b2 - b1 > a.vgrid) {
         for (uint32_t k = b1 + (tid >> 5); k < b2; k += nth >> 5) sn_factor<32>(a, k, threadIdx.x & 31u, warp_stage);
         __syncthreads();  // the CTA panels below reuse the warps' shared memory
-        for (uint32_t k = b2 + blockIdx.x; k < b3; k += gridDim.x) sn_factor<512>(a, k, threadIdx.x, cta_stage);
+        for (uint32_t k = b2 + a.vblock; k < b3; k += a.vgrid) sn_factor<512>(a, k, threadIdx.x, cta_stage);
     } else {
-        for (uint32_t k = b1 + blockIdx.x; k < b3; k += gridDim.x) sn_factor<512>(a, k, threadIdx.x, cta_stage);
+        for (uint32_t k = b1 + a.vblock; k < b3; k += a.vgrid) sn_factor<512>(a, k, threadIdx.x, cta_stage);
     }
 }
 __device__ void direct_backward_stage(const LargeArgs& a, uint32_t st, uint32_t tid, uint32_t nth, double* warp_stage, double* cta_stage) {
@@ -712,7 +717,7 @@ __device__ void direct_backward_stage(const LargeArgs& a, uint32_t st, uint32_t 
     for (uint32_t k = b1 + (tid >> 5); k < b2; k += nth >> 5) sn_backward<32>(a, k, threadIdx.x & 31u, warp_stage);
     if (b3 > b2) {
         __syncthreads();
-        for (uint32_t k = b2 + blockIdx.x; k < b3; k += gridDim.x) sn_backward<512>(a, k, threadIdx.x, cta_stage);
+        for (uint32_t k = b2 + a.vblock; k < b3; k += a.vgrid) sn_backward<512>(a, k, threadIdx.x, cta_stage);
     }
 }
 
@@ -755,14 +760,32 @@ __device__ __forceinline__ unsigned long long now_ns() {
 
 constexpr size_t kLmDynamicSmem = (kBlock / 32) * kWarpStageDoubles * sizeof(double);  // 164 KB
 
-__global__ void __launch_bounds__(kBlock, 1) lm_large_kernel(const LargeArgs a) {
+__global__ void __launch_bounds__(kBlock, 1) lm_large_kernel(const LargeArgs a_in) {
+    LargeArgs a = a_in;
+    if (a.batch) {  // one problem per CTA: this CTA's slices of the per-problem arrays
+        const size_t b = blockIdx.x;
+        a.vg += b * a.vg_stride;
+        a.jr += b * a.jr_stride;
+        a.cgv += b * a.cgv_stride;
+        a.sumsq += b * a.sumsq_stride;
+        a.side += b * a.side_stride;
+        a.degen += b * a.degen_stride;
+        a.unsat += b * a.unsat_stride;
+        a.partials += b * 3;
+        a.ctrl += b;
+        a.vgrid = 1;
+        a.vblock = 0;
+    } else {
+        a.vgrid = gridDim.x;
+        a.vblock = blockIdx.x;
+    }
     __shared__ double sm[kSmDoubles];
     extern __shared__ double warp_stage_all[];  // (kBlock / 32) * kWarpStageDoubles, see kLmDynamicSmem
     double* warp_stage = warp_stage_all + (threadIdx.x >> 5) * kWarpStageDoubles;
     cg::grid_group grid = cg::this_grid();
     // Three launch shapes: one CTA (barrier = __syncthreads), one thread-block cluster of kClusterCtas CTAs for mid-size
     // systems (hardware cluster barrier, ~0.2 us, acquire/release at cluster scope), the whole GPU (cooperative grid barrier).
-    const bool single = gridDim.x == 1, clustered = a.cluster != 0;
+    const bool single = a.vgrid == 1, clustered = a.cluster != 0;
     auto sync = [&]() {
         if (single) __syncthreads();
         else if (clustered) {
@@ -770,8 +793,8 @@ __global__ void __launch_bounds__(kBlock, 1) lm_large_kernel(const LargeArgs a) 
             asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
         } else grid.sync();
     };
-    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
-    const uint32_t G = gridDim.x;
+    const uint32_t tid = a.vblock * blockDim.x + threadIdx.x, nth = a.vgrid * blockDim.x;
+    const uint32_t G = a.vgrid;
     LargeCtrl* ctrl = a.ctrl;
     double* vg = a.vg;
     double* pm = a.partials;           // max / pAp
@@ -808,7 +831,7 @@ __global__ void __launch_bounds__(kBlock, 1) lm_large_kernel(const LargeArgs a) 
     // S = sum r^2 (see the header comment for the two summation orders)
     const uint32_t n_chunks = (a.m + kSumChunk - 1) / kSumChunk;
     auto sum_squares = [&](const double* v, double* ctrl_slot) -> double {
-        if (single) {
+        if (!a.chunked_sums) {
             sequential_sum_squares(v, a.m, ctrl_slot, sm, kSmDoubles);
             __syncthreads();
             return *ctrl_slot;
@@ -823,7 +846,7 @@ __global__ void __launch_bounds__(kBlock, 1) lm_large_kernel(const LargeArgs a) 
     bool converged = false;
     uint32_t lin_iters = 0;
     for (uint32_t it = 0; it < a.max_iterations; ++it) {
-        max_abs_partial(vg + a.R0, a.m, tid, nth, &pm[blockIdx.x], sm);
+        max_abs_partial(vg + a.R0, a.m, tid, nth, &pm[a.vblock], sm);
         sync();
         const double largest = fold_max(pm, G, sm);
         lap(1);
@@ -881,8 +904,8 @@ __global__ void __launch_bounds__(kBlock, 1) lm_large_kernel(const LargeArgs a) 
                 lrz += b * z;
                 lbb += b * b;
             }
-            block_sum(lrz, &ps1[blockIdx.x], sm);
-            block_sum(lbb, &ps2[blockIdx.x], sm);
+            block_sum(lrz, &ps1[a.vblock], sm);
+            block_sum(lbb, &ps2[a.vblock], sm);
             sync();
             double rz = fold_sum(ps1, G, sm);
             const double bb = fold_sum(ps2, G, sm);
@@ -902,7 +925,7 @@ __global__ void __launch_bounds__(kBlock, 1) lm_large_kernel(const LargeArgs a) 
                         ap[j] = s;
                         lpap += p[j] * s;
                     }
-                    block_sum(lpap, &pm[blockIdx.x], sm);
+                    block_sum(lpap, &pm[a.vblock], sm);
                     sync();
                     const double pap = fold_sum(pm, G, sm);
                     ++lin_iters;
@@ -919,8 +942,8 @@ __global__ void __launch_bounds__(kBlock, 1) lm_large_kernel(const LargeArgs a) 
                         lrz2 += rj * (dinv[j] * rj);
                         lrr += rj * rj;
                     }
-                    block_sum(lrz2, &ps1[blockIdx.x], sm);
-                    block_sum(lrr, &ps2[blockIdx.x], sm);
+                    block_sum(lrz2, &ps1[a.vblock], sm);
+                    block_sum(lrr, &ps2[a.vblock], sm);
                     sync();
                     const double rz2 = fold_sum(ps1, G, sm);
                     const double rr = fold_sum(ps2, G, sm);
@@ -941,7 +964,7 @@ __global__ void __launch_bounds__(kBlock, 1) lm_large_kernel(const LargeArgs a) 
             sync();
             continue;
         }
-        max_abs_partial(vg + a.D0, a.n, tid, nth, &pm[blockIdx.x], sm);
+        max_abs_partial(vg + a.D0, a.n, tid, nth, &pm[a.vblock], sm);
         sync();
         const double step = fold_max(pm, G, sm);
         for (uint32_t j = tid; j < a.n; j += nth) vg[a.X0 + j] += vg[a.D0 + j];
@@ -1011,7 +1034,9 @@ __global__ void __launch_bounds__(kBlock, 1) lm_large_kernel(const LargeArgs a) 
 // Persistent warps; every warp owns tiles gw, gw + nw, ... and keeps kAsmStages of them in flight: lane 0 arms the
 // stage's mbarrier with the tile's byte count and issues one cp.async.bulk for the whole tile; the warp waits on
 // the barrier's phase, evaluates its 32 constraints out of shared memory, and refills the stage.
-__global__ void __launch_bounds__(kAsmWarps * 32, 2) assemble_large_kernel(const LargeArgs a, const bool write_jr) {
+template <int kAsmWarps, int kCtasPerSm, int kStageTiles>
+__global__ void __launch_bounds__(kAsmWarps * 32, kCtasPerSm) assemble_large_kernel(const LargeArgs a, const bool write_jr) {
+    constexpr size_t kAsmWarpBytes = (size_t)kStageTiles * kTileBytesMax;
     extern __shared__ __align__(128) unsigned char asm_smem[];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     unsigned char* stage_base = asm_smem + (size_t)warp * kAsmWarpBytes;
@@ -1067,6 +1092,35 @@ __global__ void __launch_bounds__(kAsmWarps * 32, 2) assemble_large_kernel(const
         for (int q = 0; q < 8; ++q) xv[q] = xn[q];
     }
 }
+// Launch shapes of the assembly kernel: warps per CTA x CTAs per SM (the register budget follows) x widest tiles staged
+// per warp.  EZPZ_B200_ASM_VARIANT selects one for measurements; the default is the fastest measured on B200.
+template <int W, int C, int T>
+cudaError_t launch_assemble_as(const LargeArgs& a, bool write_jr, uint32_t n_tiles, int sm_count, cudaStream_t st) {
+    constexpr size_t smem = (size_t)W * T * kTileBytesMax + (size_t)W * kAsmStagesMax * sizeof(uint64_t);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(assemble_large_kernel<W, C, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    const unsigned grid = (unsigned)std::max<size_t>(1, std::min<size_t>((n_tiles + W - 1) / W, (size_t)sm_count * C));
+    assemble_large_kernel<W, C, T><<<grid, W * 32, smem, st>>>(a, write_jr);
+    return cudaGetLastError();
+}
+cudaError_t launch_assemble(const LargeArgs& a, bool write_jr, uint32_t n_tiles, int sm_count, cudaStream_t st) {
+    static const int variant = [] {
+        const char* e = std::getenv("EZPZ_B200_ASM_VARIANT");
+        return e ? std::atoi(e) : 0;
+    }();
+    switch (variant) {
+        case 1: return launch_assemble_as<5, 4, 2>(a, write_jr, n_tiles, sm_count, st);   // 20 warps/SM, <= 96 registers
+        case 2: return launch_assemble_as<6, 4, 2>(a, write_jr, n_tiles, sm_count, st);   // 24 warps/SM, <= 80 registers
+        case 3: return launch_assemble_as<4, 5, 2>(a, write_jr, n_tiles, sm_count, st);   // 20 warps/SM, <= 96 registers
+        case 4: return launch_assemble_as<4, 4, 3>(a, write_jr, n_tiles, sm_count, st);   // 16 warps/SM in 4 CTAs
+        default: return launch_assemble_as<8, 2, 3>(a, write_jr, n_tiles, sm_count, st);  // 16 warps/SM, 128 registers
+    }
+}
+
 // Thread per row, entries ascending, one fma chain (measured faster than staging the warp's entry range through
 // shared memory: both are bound by the L1's sector lookups for the x gathers, and shared memory shares that pipe).
 __global__ void __launch_bounds__(256) spmv_csr_kernel(const uint32_t* __restrict__ row_ptr, const uint32_t* __restrict__ col_idx,
@@ -1095,6 +1149,14 @@ struct LargeDevice {
     int grid = 0;
     bool cluster = false;
     bool tables = false;
+    // per-problem state of the one-CTA-per-problem batch mode (solve_large_batch), grown on demand
+    struct Batch {
+        double *vg = nullptr, *jr = nullptr, *cgv = nullptr, *sumsq = nullptr, *partials = nullptr;
+        uint8_t* side = nullptr;
+        uint32_t *degen = nullptr, *unsat = nullptr;
+        LargeCtrl* ctrl = nullptr;
+        uint64_t cap = 0;  // problems the buffers hold
+    } batch;
 };
 
 template <class T>
@@ -1300,6 +1362,42 @@ void fill_args(LargeArgs& a, const ezpz_structure* s, const DeviceCopy* dc, cons
     a.Y0 = P.Y0;
     a.D0 = P.D0;
     a.direct = P.direct ? 1u : 0u;
+    // the summation order belongs to the structure, not to the launch shape: a system solved alone (cluster / grid) and
+    // the same system solved as one CTA's problem in a batch fold S the same way
+    a.chunked_sums = ((size_t)s->n + s->m + s->csc_row_idx.size() > kSingleCtaWork) ? 1u : 0u;
+}
+
+// Batch mode epilogue: per problem, iterations / status out of its control block and x, masks, Jacobian out of its slices.
+struct BatchOut {
+    double* finals;
+    uint32_t* iterations;
+    uint8_t* status;
+    uint32_t* unsat;
+    uint32_t* degen;
+    double* jac;
+};
+__global__ void __launch_bounds__(256) large_batch_scatter_kernel(const LargeArgs a, const double* __restrict__ guesses) {
+    const size_t b = blockIdx.x;
+    double* x = a.vg + b * a.vg_stride + a.X0;
+    for (uint32_t j = threadIdx.x; j < a.n; j += blockDim.x) x[j] = guesses[b * a.n + j];
+}
+__global__ void __launch_bounds__(256) large_batch_gather_kernel(const LargeArgs a, const BatchOut o) {
+    const size_t b = blockIdx.x;
+    const double* vg = a.vg + b * a.vg_stride;
+    for (uint32_t j = threadIdx.x; j < a.n; j += blockDim.x) o.finals[b * a.n + j] = vg[a.X0 + j];
+    const uint32_t uw = (a.n_cons + 31) / 32;
+    if (o.unsat)
+        for (uint32_t w = threadIdx.x; w < uw; w += blockDim.x) o.unsat[b * uw + w] = a.unsat[b * a.unsat_stride + w];
+    if (o.degen)
+        for (uint32_t c = threadIdx.x; c < a.n_cons; c += blockDim.x) o.degen[b * a.n_cons + c] = a.degen[b * a.degen_stride + c];
+    if (o.jac)
+        for (uint32_t e = threadIdx.x; e < a.nnz; e += blockDim.x) o.jac[b * a.nnz + e] = vg[a.J0 + e];
+    if (threadIdx.x == 0) {
+        const LargeCtrl* c = a.ctrl + b;
+        o.iterations[b] = c->iterations;
+        o.status[b] = (uint8_t)((c->converged ? EZPZ_ST_CONVERGED : 0u) | (c->any_unsat ? EZPZ_ST_UNSATISFIED : 0u) |
+                                (c->any_degen ? EZPZ_ST_DEGENERATE : 0u));
+    }
 }
 
 }  // namespace
@@ -1314,6 +1412,10 @@ void release_large(DeviceCopy* d) {
     for (uint32_t* p : L->direct_tables)
         if (p) cudaFree(p);
     for (void* p : ptrs)
+        if (p) cudaFree(p);
+    void* bptrs[] = {L->batch.vg, L->batch.jr, L->batch.cgv, L->batch.sumsq, L->batch.partials, L->batch.side,
+                     L->batch.degen, L->batch.unsat, L->batch.ctrl};
+    for (void* p : bptrs)
         if (p) cudaFree(p);
     delete L;
     d->large = nullptr;
@@ -1337,13 +1439,9 @@ int32_t eval_large(ezpz_context* ctx, const ezpz_structure* s, const double* x, 
     EZ_CUDA(cudaMemcpyAsync(L->vg + a.X0, x, sizeof(double) * s->n, cudaMemcpyHostToDevice, st), "H2D x");
     EZ_CUDA(cudaMemsetAsync(L->degen, 0, sizeof(uint32_t) * s->n_cons, st), "memset degen");
     resolve_sides_kernel<<<(unsigned)std::max<size_t>(1, std::min<size_t>((L->n_tiles + 7) / 8, 4096)), 256, 0, st>>>(a);
-    EZ_CUDA(cudaFuncSetAttribute(assemble_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAsmSmem),
-            "cudaFuncSetAttribute(assemble_large_kernel)");
-    const unsigned grid = (unsigned)std::max<size_t>(1, std::min<size_t>((L->n_tiles + kAsmWarps - 1) / kAsmWarps, (size_t)ctx->sm_count * 2));
     const bool with_jr = !s->large.direct;
-    assemble_large_kernel<<<grid, kAsmWarps * 32, kAsmSmem, st>>>(a, with_jr);
+    EZ_CUDA(launch_assemble(a, with_jr, L->n_tiles, ctx->sm_count, st), "assemble_large_kernel launch");
     ctx->launches += 2;
-    EZ_CUDA(cudaGetLastError(), "assemble_large_kernel launch");
     if (r) EZ_CUDA(cudaMemcpyAsync(r, L->vg + a.R0, sizeof(double) * s->m, cudaMemcpyDeviceToHost, st), "D2H r");
     if (jac_csc) EZ_CUDA(cudaMemcpyAsync(jac_csc, L->vg + a.J0, sizeof(double) * nnz, cudaMemcpyDeviceToHost, st), "D2H jac");
     if (jac_csr && with_jr) EZ_CUDA(cudaMemcpyAsync(jac_csr, L->jr, sizeof(double) * nnz, cudaMemcpyDeviceToHost, st), "D2H jac csr");
@@ -1430,6 +1528,99 @@ int32_t solve_large(ezpz_context* ctx, const ezpz_structure* s, const ezpz_confi
     return EZPZ_OK;
 }
 
+// A batch of problems of one structure that does not fit the thread-per-problem kernel: the persistent LM kernel of the
+// single-system path with ONE CTA PER PROBLEM (barriers are __syncthreads, the structure's tables are shared, every
+// problem owns a slice of the state arrays).  Same arithmetic as solve_large on each problem, hence bit-identical to
+// solving them one by one.  All io pointers are device pointers; work is enqueued on `st`.
+int32_t solve_large_batch(ezpz_context* ctx, const ezpz_structure* s, const ezpz_config_t* config, uint64_t batch,
+                          const ezpz_batch_io_t* io, cudaStream_t st, ezpz_error_detail_t* detail) {
+    if (!s->large.built) return EZPZ_ERR_TOO_LARGE;
+    if (s->n_cons == 0 || s->m == 0) return EZPZ_ERR_EMPTY_SYSTEM;
+    if (io->params) {
+        if (detail)
+            std::snprintf(detail->message, sizeof detail->message,
+                          "per-problem parameter overrides are only available on the thread-per-problem kernel");
+        return EZPZ_ERR_UNSUPPORTED;
+    }
+    EZ_CUDA(cudaSetDevice(ctx->device), "cudaSetDevice");
+    DeviceCopy* dc = nullptr;
+    EZ_TRY(get_device_copy(ctx, s, &dc, detail));
+    LargeDevice* L = nullptr;
+    EZ_TRY(get_large(ctx, s, dc, &L, detail));
+    const LargeProgram& P = s->large;
+    const size_t nnz = s->csc_row_idx.size();
+    const bool use_cg = !P.direct;
+    const size_t vg_stride = align_up(std::max<size_t>(1, P.VG), 32), jr_stride = use_cg ? align_up(std::max<size_t>(1, nnz), 32) : 0,
+                 cgv_stride = use_cg ? align_up(4 * (size_t)s->n + s->m + 1, 32) : 0,
+                 sumsq_stride = align_up((size_t)s->m / kSumChunk + 2, 16), side_stride = align_up(std::max<size_t>(1, L->n_slots), 16),
+                 degen_stride = s->n_cons, unsat_stride = (s->n_cons + 31) / 32 + 1;
+    const size_t per_problem = 8 * (vg_stride + jr_stride + cgv_stride + sumsq_stride + 3) + side_stride +
+                               4 * (degen_stride + unsat_stride) + sizeof(LargeCtrl);
+    LargeDevice::Batch& B = L->batch;
+    if (B.cap < batch) {
+        // as many problems per launch as a quarter of the free memory holds (at least one wave of CTAs when it fits)
+        size_t free_b = 0, total_b = 0;
+        EZ_CUDA(cudaMemGetInfo(&free_b, &total_b), "cudaMemGetInfo");
+        void* old[] = {B.vg, B.jr, B.cgv, B.sumsq, B.partials, B.side, B.degen, B.unsat, B.ctrl};
+        size_t held = (size_t)B.cap * per_problem;
+        for (void* p : old)
+            if (p) cudaFree(p);
+        B = LargeDevice::Batch();
+        uint64_t cap = std::min<uint64_t>(batch, std::max<uint64_t>(1, (free_b + held) / 4 / per_problem));
+        if (const char* env = std::getenv("EZPZ_B200_LARGE_BATCH_CAP")) cap = std::max<uint64_t>(1, std::min<uint64_t>(cap, std::strtoull(env, nullptr, 10)));
+        EZ_CUDA(cudaMalloc(&B.vg, 8 * vg_stride * cap), "cudaMalloc(batch vg)");
+        EZ_CUDA(cudaMemsetAsync(B.vg, 0, 8 * vg_stride * cap, st), "cudaMemset(batch vg)");
+        EZ_CUDA(cudaMalloc(&B.jr, std::max<size_t>(8, 8 * jr_stride * cap)), "cudaMalloc(batch jr)");
+        EZ_CUDA(cudaMalloc(&B.cgv, std::max<size_t>(8, 8 * cgv_stride * cap)), "cudaMalloc(batch cgv)");
+        EZ_CUDA(cudaMalloc(&B.sumsq, 8 * sumsq_stride * cap), "cudaMalloc(batch sumsq)");
+        EZ_CUDA(cudaMalloc(&B.partials, 8 * 3 * cap), "cudaMalloc(batch partials)");
+        EZ_CUDA(cudaMalloc(&B.side, side_stride * cap), "cudaMalloc(batch side)");
+        EZ_CUDA(cudaMalloc(&B.degen, 4 * std::max<size_t>(1, degen_stride) * cap), "cudaMalloc(batch degen)");
+        EZ_CUDA(cudaMalloc(&B.unsat, 4 * unsat_stride * cap), "cudaMalloc(batch unsat)");
+        EZ_CUDA(cudaMalloc(&B.ctrl, sizeof(LargeCtrl) * cap), "cudaMalloc(batch ctrl)");
+        EZ_CUDA(cudaMemsetAsync(B.ctrl, 0, sizeof(LargeCtrl) * cap, st), "cudaMemset(batch ctrl)");
+        B.cap = cap;
+    }
+    LargeArgs a;
+    fill_args(a, s, dc, L, config);
+    a.vg = B.vg;
+    a.jr = B.jr;
+    a.cgv = B.cgv;
+    a.sumsq = B.sumsq;
+    a.partials = B.partials;
+    a.side = B.side;
+    a.degen = B.degen;
+    a.unsat = B.unsat;
+    a.ctrl = B.ctrl;
+    a.lvl_ns = nullptr;
+    a.cluster = 0;
+    a.batch = 1;
+    a.vg_stride = vg_stride;
+    a.jr_stride = jr_stride;
+    a.cgv_stride = cgv_stride;
+    a.sumsq_stride = sumsq_stride;
+    a.side_stride = side_stride;
+    a.degen_stride = degen_stride;
+    a.unsat_stride = unsat_stride;
+    const uint32_t uw = (s->n_cons + 31) / 32;
+    for (uint64_t b0 = 0; b0 < batch; b0 += B.cap) {
+        const unsigned cnt = (unsigned)std::min<uint64_t>(B.cap, batch - b0);
+        large_batch_scatter_kernel<<<cnt, 256, 0, st>>>(a, io->guesses + b0 * s->n);
+        lm_large_kernel<<<cnt, kBlock, kLmDynamicSmem, st>>>(a);
+        BatchOut o;
+        o.finals = io->final_values + b0 * s->n;
+        o.iterations = io->iterations + b0;
+        o.status = io->status + b0;
+        o.unsat = io->unsat_mask ? io->unsat_mask + b0 * uw : nullptr;
+        o.degen = io->degen_count ? io->degen_count + b0 * s->n_cons : nullptr;
+        o.jac = io->jacobian ? io->jacobian + b0 * nnz : nullptr;
+        large_batch_gather_kernel<<<cnt, 256, 0, st>>>(a, o);
+        ctx->launches += 3;
+        EZ_CUDA(cudaGetLastError(), "lm_large_kernel batch launch");
+    }
+    return EZPZ_OK;
+}
+
 }  // namespace ezs
 
 // Stand-alone launches of the assembly and SpMV kernels on a structure's large-system buffers, timed with
@@ -1456,15 +1647,12 @@ extern "C" int32_t ezpz_b200_large_bench(ezpz_context_t* ctx, const ezpz_structu
     EZ_CUDA(cudaMemsetAsync(L->side, 1, L->n_slots, st), "memset side");
     EZ_CUDA(cudaMemsetAsync(L->degen, 0, sizeof(uint32_t) * s->n_cons, st), "memset degen");
     const unsigned grid = (unsigned)ctx->sm_count * 8;
-    const unsigned grid_asm = (unsigned)std::max<size_t>(1, std::min<size_t>((L->n_tiles + kAsmWarps - 1) / kAsmWarps, (size_t)ctx->sm_count * 2));
-    EZ_CUDA(cudaFuncSetAttribute(assemble_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAsmSmem),
-            "cudaFuncSetAttribute(assemble_large_kernel)");
     const double n = s->n, m = s->m, nnz = (double)s->csc_row_idx.size(), C = s->n_cons;
     cudaEvent_t e0, e1;
     EZ_CUDA(cudaEventCreate(&e0), "cudaEventCreate");
     EZ_CUDA(cudaEventCreate(&e1), "cudaEventCreate");
     // one untimed launch first (also fills jr for the SpMVs)
-    assemble_large_kernel<<<grid_asm, kAsmWarps * 32, kAsmSmem, st>>>(a, true);
+    EZ_CUDA(launch_assemble(a, true, L->n_tiles, ctx->sm_count, st), "assemble_large_kernel launch");
     ctx->launches += 1;
     // Launches run back to back inside ONE event pair (a per-launch pair adds ~5 us of launch latency to kernels that
     // take 15-50 us).  For an HBM figure the caller passes a system whose working set exceeds the 126 MB L2
@@ -1477,7 +1665,7 @@ extern "C" int32_t ezpz_b200_large_bench(ezpz_context_t* ctx, const ezpz_structu
     if (flush) EZ_CUDA(cudaMalloc(&flush_buf, flush_bytes), "cudaMalloc(flush)");
     float ms = 0.f;
     auto launch = [&]() {
-        if (which == 0 || which == 3) assemble_large_kernel<<<grid_asm, kAsmWarps * 32, kAsmSmem, st>>>(a, which == 3);
+        if (which == 0 || which == 3) (void)launch_assemble(a, which == 3, L->n_tiles, ctx->sm_count, st);
         else if (which == 1) spmv_csr_kernel<<<grid, 256, 0, st>>>(L->csr_row_ptr, L->csr_col_idx, L->jr, L->vg + a.X0, L->cgv + 4 * (size_t)s->n, s->m);
         else spmv_csr_kernel<<<grid, 256, 0, st>>>(L->csc_col_ptr, L->csc_row_idx, L->vg + a.J0, L->vg + a.R0, L->cgv, s->n);
         ctx->launches += 1;

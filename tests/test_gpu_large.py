@@ -188,3 +188,35 @@ def test_random_systems_all_kinds_large_path(ctx, seed):
     finite = np.isfinite(o.final_values)
     assert np.array_equal(np.isfinite(out.final_values), finite)
     assert_bitwise(out.final_values[finite], o.final_values[finite], "finite final values")
+
+
+@pytest.mark.parametrize("cells,batch", [(16, 40), (64, 24)])
+def test_batch_of_mid_size_systems_one_cta_per_problem(ctx, cells, batch):
+    """ezpz_b200_solve_batch on a structure beyond the thread-per-problem kernel (208 / 832 variables): the persistent LM
+    kernel with one CTA per problem.  Every problem is bit-identical to solving it alone (ezpz_b200_solve_one: one CTA
+    resp. one cluster of 8 CTAs) and to the oracle with the structure's order and sum chunking; degenerate counts, the
+    unsatisfied mask and the exported Jacobian included.  One problem carries a 1e308 guess (failed factorisations)."""
+    recs, n, g, exact = wl.chain_sketch(cells)
+    st = ez.Structure(recs, n)
+    od = st.ordering()
+    rng = np.random.default_rng(77 + cells)
+    G = g[None, :] + rng.uniform(-0.02, 0.02, (batch, n))
+    G[0] = g
+    G[3, 2] = 1e308
+    os.environ["EZPZ_B200_LARGE_BATCH_CAP"] = "16"  # several launches per call
+    try:
+        out = ctx.solve_batch(st, G, want_unsat=True, want_degen=True, want_jacobian=True)
+    finally:
+        del os.environ["EZPZ_B200_LARGE_BATCH_CAP"]
+    for b in range(batch):
+        one = ctx.solve_one(st, G[b], want_jacobian=True)
+        o = orc.solve_inner_ordered(recs, G[b], od["elim_order"], od["sum_chunk"])
+        assert out.iterations[b] == one.iterations == o.iterations, b
+        assert (out.status[b] & 3) == (one.status & 3) and bool(out.status[b] & 1) == o.converged, b
+        finite = np.isfinite(o.final_values)
+        assert_bitwise(out.final_values[b][finite], o.final_values[finite], f"problem {b} final values vs oracle")
+        assert np.array_equal(out.final_values[b], one.final_values, equal_nan=True), b
+        assert np.array_equal(out.unsat_mask[b], one.unsat_mask), b
+        assert np.array_equal(out.degen_count[b], one.degen_count), b
+        assert np.array_equal(out.jacobian[b], one.jacobian, equal_nan=True), b
+    assert out.iterations[3] == 35 and not (out.status[3] & 1)
