@@ -93,6 +93,7 @@ struct LargeArgs {
     uint32_t n_cons, n_slots, n_tiles, tile_bytes_max, n, m, nnz, n_levels, nnz_l, n_aent;
     uint32_t unit_weights;
     uint32_t cluster;  // launched as one thread-block cluster (mid-size systems)
+    const uint32_t* jmap;   // direct path: position in the J region of each CSC entry (tile order); null = CSC order
     uint32_t chunked_sums;  // sum of squares folded in chunks of kSumChunk rows (systems of more than kSingleCtaWork values)
     // CTAs cooperating on ONE system and this CTA's rank among them (set by the kernel: the whole grid, or 1 / 0 in
     // batch mode, where every CTA solves its own problem with CTA-level barriers)
@@ -160,14 +161,13 @@ __device__ __forceinline__ void gather_x(const LargeArgs& a, const KindLayout ly
     }
 }
 
-template <bool RES, bool JAC>
+template <bool RES, bool JAC, bool NO_JR = false>
 __device__ __forceinline__ void assemble_slot(const LargeArgs& a, const KindLayout ly, uint32_t kind, const uint32_t* rec, uint32_t k,
-                                              uint32_t rdst, bool write_jr, const double (&xv)[8]) {
+                                              uint32_t rdst, bool write_jr, const double (&xv)[8], uint32_t side) {
     const double p0 = ly.p0 != 0xff ? rec_double(rec, ly.p0) : 0.0;
     const double p1 = ly.p1 != 0xff ? rec_double(rec, ly.p1) : 0.0;
     const double w = ly.weight != 0xff ? rec_double(rec, ly.weight) : 1.0;
     const uint32_t row0 = rec[0];
-    const uint32_t side = (kind == EZPZ_K_LINE_TANGENT_TO_CIRCLE || kind == EZPZ_K_CIRCLE_TANGENT_TO_CIRCLE) ? a.side[k] : 0u;
     const uint32_t ident[8] = {0, 1, 2, 3, 4, 5, 6, 7};
     const RegX XR{xv};
     ezd::EvalOut o;
@@ -181,7 +181,7 @@ __device__ __forceinline__ void assemble_slot(const LargeArgs& a, const KindLayo
     }
     if (JAC) {
         if (o.jac_degen) ++ndeg;
-        const bool jr_on = write_jr && ly.jr != 0xff;
+        const bool jr_on = !NO_JR && write_jr && ly.jr != 0xff;
         const uint32_t jr0 = jr_on ? rec[ly.jr * 32] : 0u;
 #pragma unroll
         for (int row = 0; row < 2; ++row) {
@@ -221,7 +221,8 @@ __device__ __forceinline__ void assemble_phase_inl(const LargeArgs& a, uint32_t 
             const uint32_t* rec = a.recs + (size_t)td.off16 * 4 + lane;
             double xv[8];
             gather_x(a, a.layout[kind], kind, rec, xv);
-            assemble_slot<RES, JAC>(a, a.layout[kind], kind, rec, t * 32 + lane, rdst, write_jr, xv);
+            const uint32_t side = (kind == EZPZ_K_LINE_TANGENT_TO_CIRCLE || kind == EZPZ_K_CIRCLE_TANGENT_TO_CIRCLE) ? a.side[t * 32 + lane] : 0u;
+            assemble_slot<RES, JAC>(a, a.layout[kind], kind, rec, t * 32 + lane, rdst, write_jr, xv, side);
         }
     }
 }
@@ -405,7 +406,7 @@ __device__ void direct_assemble(const LargeArgs& a, double lambda, uint32_t tid,
         const uint32_t c = __ldg(a.perm + j);
         double dg = 0.0, b = 0.0;
         for (uint32_t e = __ldg(a.csc_col_ptr + c); e < __ldg(a.csc_col_ptr + c + 1); ++e) {
-            const double v = jv[e];
+            const double v = jv[a.jmap ? __ldg(a.jmap + e) : e];
             dg = __fma_rn(v, v, dg);
             b = __fma_rn(v, -r[__ldg(a.csc_row_idx + e)], b);
         }
@@ -1034,13 +1035,14 @@ __global__ void __launch_bounds__(kBlock, 1) lm_large_kernel(const LargeArgs a_i
 // Persistent warps; every warp owns tiles gw, gw + nw, ... and keeps kAsmStages of them in flight: lane 0 arms the
 // stage's mbarrier with the tile's byte count and issues one cp.async.bulk for the whole tile; the warp waits on
 // the barrier's phase, evaluates its 32 constraints out of shared memory, and refills the stage.
-template <int kAsmWarps, int kCtasPerSm, int kStageTiles>
-__global__ void __launch_bounds__(kAsmWarps * 32, kCtasPerSm) assemble_large_kernel(const LargeArgs a, const bool write_jr) {
+template <int kAsmWarps, int kCtasPerSm, int kStageTiles, bool kWriteJr>
+__global__ void __launch_bounds__(kAsmWarps * 32, kCtasPerSm) assemble_large_kernel(const LargeArgs a) {
     constexpr size_t kAsmWarpBytes = (size_t)kStageTiles * kTileBytesMax;
     extern __shared__ __align__(128) unsigned char asm_smem[];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     unsigned char* stage_base = asm_smem + (size_t)warp * kAsmWarpBytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(asm_smem + (size_t)kAsmWarps * kAsmWarpBytes) + warp * kAsmStagesMax;
+    uint2* ring = reinterpret_cast<uint2*>(asm_smem + (size_t)kAsmWarps * (kAsmWarpBytes + kAsmStagesMax * sizeof(uint64_t))) + warp * 64;
     const uint32_t gw = blockIdx.x * kAsmWarps + warp, nw = gridDim.x * kAsmWarps;
     const uint32_t kStageBytes = a.tile_bytes_max, kAsmStages = min(kAsmStagesMax, (uint32_t)(kAsmWarpBytes / kStageBytes));
     if (lane == 0) {
@@ -1049,62 +1051,97 @@ __global__ void __launch_bounds__(kAsmWarps * 32, kCtasPerSm) assemble_large_ker
     }
     __syncwarp();
     const uint32_t count = gw < a.n_tiles ? (a.n_tiles - gw + nw - 1) / nw : 0u;
-    auto issue = [&](uint32_t k) {  // lane 0: start the copy of this warp's k-th tile into stage k % kAsmStages
-        const TileDesc td = a.tiles[gw + k * nw];
+    // Tile descriptors: this warp's descriptors go through a 64-entry ring in shared memory, filled 32 at a time (lane l
+    // fetches the descriptor of the warp's (32 b + l)-th tile) one block AHEAD of their use, so that neither the bulk copy
+    // of tile k + kAsmStages nor the gathers of tile k + 1 wait for a dependent global load.
+    auto load_block = [&](uint32_t b) {
+        const uint32_t k = b * 32 + lane;
+        return k < count ? *reinterpret_cast<const uint2*>(&a.tiles[gw + k * nw]) : make_uint2(0u, 0u);
+    };
+    auto desc = [&](uint32_t k) {
+        const uint2 v = ring[k & 63u];
+        return TileDesc{v.x, v.y};
+    };
+    ring[lane] = load_block(0);
+    ring[32 + lane] = load_block(1);
+    uint2 pf = load_block(2);
+    __syncwarp();
+    auto issue = [&](uint32_t st, const TileDesc td) {  // lane 0: start the copy of a tile into stage st
         const uint32_t bytes = (uint32_t)a.layout[td.meta & 0xffu].n_words * 128u;
-        const uint32_t st = k % kAsmStages;
         mbar_expect_tx(&bars[st], bytes);
         bulk_copy_g2s(stage_base + (size_t)st * kStageBytes, a.recs + (size_t)td.off16 * 4, bytes, &bars[st]);
     };
     if (lane == 0)
-        for (uint32_t k = 0; k < kAsmStages && k < count; ++k) issue(k);
-    // The gathers of tile k + 1 are issued before tile k is evaluated (its record is already in shared memory, two
-    // more are in flight), so their latency hides behind the arithmetic.
+        for (uint32_t k = 0; k < kAsmStages && k < count; ++k) issue(k, desc(k));
+    // The gathers of tile k + 1 (and its tangent-side byte) are issued before tile k is evaluated (its record is already in
+    // shared memory, more are in flight), so their latency hides behind the arithmetic.
+    auto is_tangent = [](uint32_t kind) { return kind == EZPZ_K_LINE_TANGENT_TO_CIRCLE || kind == EZPZ_K_CIRCLE_TANGENT_TO_CIRCLE; };
     double xv[8], xn[8];
-    TileDesc td = count ? a.tiles[gw] : TileDesc{0, 0};
+    uint32_t side = 0, side_n = 0;
+    TileDesc td = desc(0);
     if (count) {
         mbar_wait(&bars[0], 0);
-        if (lane < (td.meta >> 8))
+        if (lane < (td.meta >> 8)) {
             gather_x(a, a.layout[td.meta & 0xffu], td.meta & 0xffu, reinterpret_cast<const uint32_t*>(stage_base) + lane, xv);
+            if (is_tangent(td.meta & 0xffu)) side = a.side[gw * 32 + lane];
+        }
     }
-    for (uint32_t k = 0; k < count; ++k) {
-        const uint32_t t = gw + k * nw, st = k % kAsmStages;
+    // st = k % kAsmStages, sn = (k + 1) % kAsmStages, par_n = ((k + 1) / kAsmStages) & 1 — kept incrementally
+    uint32_t st = 0, sn = kAsmStages > 1 ? 1u : 0u, par_n = kAsmStages > 1 ? 0u : 1u;
+    for (uint32_t k = 0, t = gw; k < count; ++k, t += nw) {
+        if ((k & 31u) == 0 && k) {  // entering block b = k / 32: bring block b + 1 into the ring, start fetching block b + 2
+            const uint32_t b = k >> 5;
+            ring[((b + 1) & 1u) * 32 + lane] = pf;
+            pf = load_block(b + 2);
+            __syncwarp();
+        }
         const uint32_t kind = td.meta & 0xffu, n_valid = td.meta >> 8;
         TileDesc tn{0, 0};
         if (k + 1 < count) {
-            tn = a.tiles[t + nw];
-            const uint32_t sn = (k + 1) % kAsmStages;
-            mbar_wait(&bars[sn], ((k + 1) / kAsmStages) & 1u);
-            if (lane < (tn.meta >> 8))
+            tn = desc(k + 1);
+            mbar_wait(&bars[sn], par_n);
+            if (lane < (tn.meta >> 8)) {
                 gather_x(a, a.layout[tn.meta & 0xffu], tn.meta & 0xffu,
                          reinterpret_cast<const uint32_t*>(stage_base + (size_t)sn * kStageBytes) + lane, xn);
+                if (is_tangent(tn.meta & 0xffu)) side_n = a.side[(t + nw) * 32 + lane];
+            }
         }
         if (lane < n_valid)
-            assemble_slot<true, true>(a, a.layout[kind], kind, reinterpret_cast<const uint32_t*>(stage_base + (size_t)st * kStageBytes) + lane,
-                                      t * 32 + lane, a.R0, write_jr, xv);
+            assemble_slot<true, true, !kWriteJr>(a, a.layout[kind], kind,
+                                                 reinterpret_cast<const uint32_t*>(stage_base + (size_t)st * kStageBytes) + lane,
+                                                 t * 32 + lane, a.R0, kWriteJr, xv, side);
         __syncwarp();
         if (lane == 0 && k + kAsmStages < count) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            issue(k + kAsmStages);
+            issue(st, desc(k + kAsmStages));
         }
         td = tn;
+        side = side_n;
 #pragma unroll
         for (int q = 0; q < 8; ++q) xv[q] = xn[q];
+        st = sn;
+        if (++sn == kAsmStages) {
+            sn = 0;
+            par_n ^= 1u;
+        }
     }
 }
 // Launch shapes of the assembly kernel: warps per CTA x CTAs per SM (the register budget follows) x widest tiles staged
 // per warp.  EZPZ_B200_ASM_VARIANT selects one for measurements; the default is the fastest measured on B200.
 template <int W, int C, int T>
 cudaError_t launch_assemble_as(const LargeArgs& a, bool write_jr, uint32_t n_tiles, int sm_count, cudaStream_t st) {
-    constexpr size_t smem = (size_t)W * T * kTileBytesMax + (size_t)W * kAsmStagesMax * sizeof(uint64_t);
+    constexpr size_t smem = (size_t)W * T * kTileBytesMax + (size_t)W * kAsmStagesMax * sizeof(uint64_t) + (size_t)W * 64 * sizeof(uint2);
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(assemble_large_kernel<W, C, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(assemble_large_kernel<W, C, T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(assemble_large_kernel<W, C, T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
     const unsigned grid = (unsigned)std::max<size_t>(1, std::min<size_t>((n_tiles + W - 1) / W, (size_t)sm_count * C));
-    assemble_large_kernel<W, C, T><<<grid, W * 32, smem, st>>>(a, write_jr);
+    if (write_jr) assemble_large_kernel<W, C, T, true><<<grid, W * 32, smem, st>>>(a);
+    else assemble_large_kernel<W, C, T, false><<<grid, W * 32, smem, st>>>(a);
     return cudaGetLastError();
 }
 cudaError_t launch_assemble(const LargeArgs& a, bool write_jr, uint32_t n_tiles, int sm_count, cudaStream_t st) {
@@ -1140,6 +1177,7 @@ struct LargeDevice {
     KindLayout layout[EZPZ_K_COUNT];
     uint32_t n_slots = 0, n_tiles = 0, tile_bytes_max = 128;
     uint32_t *csr_row_ptr = nullptr, *csr_col_idx = nullptr, *csc_col_ptr = nullptr, *csc_row_idx = nullptr;
+    uint32_t* jmap = nullptr;          // device copy of LargeProgram::jt_of_csc (direct path)
     uint32_t* direct_tables[11] = {};  // device copies of the LargeProgram arrays of the sparse direct solve
     double *vg = nullptr, *jr = nullptr, *cgv = nullptr, *partials = nullptr, *sumsq = nullptr;
     unsigned long long* lvl_ns = nullptr;
@@ -1241,7 +1279,9 @@ int32_t get_large(ezpz_context* ctx, const ezpz_structure* s, DeviceCopy* dc, La
                     for (int q = 0; q < ki.emit_len[row]; ++q) {
                         const uint32_t off = s->csc_to_csr[dc.slot[row][q] & ~kAccumulate] - jr0;  // < 16: two rows of <= 8
                         code |= (off & 15u) << (4 * q);
-                        put((row == 0 ? ly.slot0 : ly.slot1) + q, dc.slot[row][q]);
+                        const uint32_t sl = dc.slot[row][q];  // direct path: J lives in tile order (structure.h)
+                        put((row == 0 ? ly.slot0 : ly.slot1) + q,
+                            P.jt_of_csc.empty() ? sl : (P.jt_of_csc[sl & ~kAccumulate] | (sl & kAccumulate)));
                     }
                     if (ly.jr != 0xff) put(ly.jr + 1 + row, code);
                 }
@@ -1267,6 +1307,7 @@ int32_t get_large(ezpz_context* ctx, const ezpz_structure* s, DeviceCopy* dc, La
         const std::vector<uint32_t>* src[11] = {&P.perm, &P.sn_rows, &P.upd_rel, &P.upd_rec, &P.stage_ptr, &P.stage_rec, &P.aent_slot,
                                                 &P.aprod_ptr, &P.aprod_a, &P.aprod_b, &P.diag_slot};
         for (int k = 0; k < 11; ++k) EZ_TRY(upload(&L->direct_tables[k], *src[k], detail));
+        if (!P.jt_of_csc.empty()) EZ_TRY(upload(&L->jmap, P.jt_of_csc, detail));
     }
     const size_t nnz = s->csc_row_idx.size();
     EZ_CUDA(cudaMalloc(&L->vg, sizeof(double) * std::max<size_t>(1, P.VG)), "cudaMalloc(vg)");
@@ -1325,6 +1366,7 @@ void fill_args(LargeArgs& a, const ezpz_structure* s, const DeviceCopy* dc, cons
     a.csc_col_ptr = L->csc_col_ptr;
     a.csc_row_idx = L->csc_row_idx;
     a.csc_to_csr = dc->csc_to_csr;
+    a.jmap = L->jmap;
     {
         const uint32_t** dst[11] = {&a.perm, &a.sn_rows, &a.upd_rel, &a.upd_rec, &a.stage_ptr, &a.stage_rec, &a.aent_slot, &a.aprod_ptr,
                                     &a.aprod_a, &a.aprod_b, &a.diag_slot};
@@ -1376,6 +1418,10 @@ struct BatchOut {
     uint32_t* degen;
     double* jac;
 };
+// J in CSC order for the callers that ask for it (ezpz_b200_eval, the Jacobian export of the solve calls).
+__global__ void __launch_bounds__(256) export_j_csc_kernel(const LargeArgs a, double* __restrict__ out) {
+    for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < a.nnz; e += gridDim.x * blockDim.x) out[e] = a.vg[a.J0 + a.jmap[e]];
+}
 __global__ void __launch_bounds__(256) large_batch_scatter_kernel(const LargeArgs a, const double* __restrict__ guesses) {
     const size_t b = blockIdx.x;
     double* x = a.vg + b * a.vg_stride + a.X0;
@@ -1391,7 +1437,7 @@ __global__ void __launch_bounds__(256) large_batch_gather_kernel(const LargeArgs
     if (o.degen)
         for (uint32_t c = threadIdx.x; c < a.n_cons; c += blockDim.x) o.degen[b * a.n_cons + c] = a.degen[b * a.degen_stride + c];
     if (o.jac)
-        for (uint32_t e = threadIdx.x; e < a.nnz; e += blockDim.x) o.jac[b * a.nnz + e] = vg[a.J0 + e];
+        for (uint32_t e = threadIdx.x; e < a.nnz; e += blockDim.x) o.jac[b * a.nnz + e] = vg[a.J0 + (a.jmap ? a.jmap[e] : e)];
     if (threadIdx.x == 0) {
         const LargeCtrl* c = a.ctrl + b;
         o.iterations[b] = c->iterations;
@@ -1407,7 +1453,7 @@ namespace ezs {
 void release_large(DeviceCopy* d) {
     LargeDevice* L = (LargeDevice*)d->large;
     if (!L) return;
-    void* ptrs[] = {L->recs, L->tiles, L->slot_orig, L->side_flags, L->csr_row_ptr, L->csr_col_idx, L->csc_col_ptr, L->csc_row_idx,
+    void* ptrs[] = {L->jmap, L->recs, L->tiles, L->slot_orig, L->side_flags, L->csr_row_ptr, L->csr_col_idx, L->csc_col_ptr, L->csc_row_idx,
                     L->vg, L->jr, L->cgv, L->partials, L->sumsq, L->lvl_ns, L->side, L->degen, L->unsat, L->ctrl};
     for (uint32_t* p : L->direct_tables)
         if (p) cudaFree(p);
@@ -1443,7 +1489,15 @@ int32_t eval_large(ezpz_context* ctx, const ezpz_structure* s, const double* x, 
     EZ_CUDA(launch_assemble(a, with_jr, L->n_tiles, ctx->sm_count, st), "assemble_large_kernel launch");
     ctx->launches += 2;
     if (r) EZ_CUDA(cudaMemcpyAsync(r, L->vg + a.R0, sizeof(double) * s->m, cudaMemcpyDeviceToHost, st), "D2H r");
-    if (jac_csc) EZ_CUDA(cudaMemcpyAsync(jac_csc, L->vg + a.J0, sizeof(double) * nnz, cudaMemcpyDeviceToHost, st), "D2H jac");
+    if (jac_csc) {
+        const double* src = L->vg + a.J0;
+        if (a.jmap && nnz) {  // tile order -> CSC order through the (otherwise unused on the direct path) CSR value buffer
+            export_j_csc_kernel<<<(unsigned)std::min<size_t>((nnz + 255) / 256, 4096), 256, 0, st>>>(a, L->jr);
+            ctx->launches += 1;
+            src = L->jr;
+        }
+        EZ_CUDA(cudaMemcpyAsync(jac_csc, src, sizeof(double) * nnz, cudaMemcpyDeviceToHost, st), "D2H jac");
+    }
     if (jac_csr && with_jr) EZ_CUDA(cudaMemcpyAsync(jac_csr, L->jr, sizeof(double) * nnz, cudaMemcpyDeviceToHost, st), "D2H jac csr");
     if (have_csr) *have_csr = with_jr;
     EZ_CUDA(cudaStreamSynchronize(st), "cudaStreamSynchronize");
@@ -1501,8 +1555,15 @@ int32_t solve_large(ezpz_context* ctx, const ezpz_structure* s, const ezpz_confi
         EZ_CUDA(cudaMemcpyAsync(io->unsat_mask, L->unsat, sizeof(uint32_t) * ((s->n_cons + 31) / 32), cudaMemcpyDeviceToHost, st), "D2H unsat");
     if (io->degen_count)
         EZ_CUDA(cudaMemcpyAsync(io->degen_count, L->degen, sizeof(uint32_t) * s->n_cons, cudaMemcpyDeviceToHost, st), "D2H degen");
-    if (io->jacobian)
-        EZ_CUDA(cudaMemcpyAsync(io->jacobian, L->vg + a.J0, sizeof(double) * a.nnz, cudaMemcpyDeviceToHost, st), "D2H jacobian");
+    if (io->jacobian) {
+        const double* src = L->vg + a.J0;
+        if (a.jmap && a.nnz) {
+            export_j_csc_kernel<<<(unsigned)std::min<size_t>(((size_t)a.nnz + 255) / 256, 4096), 256, 0, st>>>(a, L->jr);
+            ctx->launches += 1;
+            src = L->jr;
+        }
+        EZ_CUDA(cudaMemcpyAsync(io->jacobian, src, sizeof(double) * a.nnz, cudaMemcpyDeviceToHost, st), "D2H jacobian");
+    }
     EZ_CUDA(cudaStreamSynchronize(st), "cudaStreamSynchronize");
     const char* dbg = std::getenv("EZPZ_B200_DEBUG");
     if (dbg && dbg[0] == '1' && dbg[1] == '2' && a.lvl_ns) {

@@ -277,17 +277,53 @@ void build_large_program(ezpz_structure& S) {
         }
     }
     build_sparse_direct(S);
+    // Direct path: J in tile order.  Every record tile owns 32 x (partials the kind emits) consecutive doubles; partial q
+    // of the constraint in lane l sits at base + q * 32 + l.  A partial that accumulates into an entry the same constraint
+    // already wrote (bit 31 of its slot) shares that entry's position.  Consumers that think in CSC positions (the product
+    // lists of A = JtJ, the column walk of b = -Jt r, the exported Jacobian) go through jt_of_csc.
+    P.jt_of_csc.clear();
+    P.n_j = nnz_j;
+    if (P.direct) {
+        P.jt_of_csc.assign(nnz_j, UINT32_MAX);
+        uint64_t base = 0;
+        for (size_t t = 0; t * 32 < P.cons_order.size(); ++t) {
+            const ezk::KindInfo& ki = ezk::kKinds[S.cons[P.cons_order[t * 32]].kind];  // a tile's first slot is never padding
+            for (uint32_t l = 0; l < 32; ++l) {
+                const uint32_t c = P.cons_order[t * 32 + l];
+                if (c == UINT32_MAX) continue;
+                const DevCons& dc = S.dev_cons[c];
+                for (int row = 0; row < ki.rows; ++row)
+                    for (int q = 0; q < ki.emit_len[row]; ++q)
+                        if (!(dc.slot[row][q] & kAccumulate))
+                            P.jt_of_csc[dc.slot[row][q]] = (uint32_t)(base + (uint64_t)((row ? ki.emit_len[0] : 0) + q) * 32 + l);
+            }
+            base += 32ull * (ki.emit_len[0] + ki.emit_len[1]);
+        }
+        for (uint32_t e = 0; e < nnz_j; ++e)  // pattern entries no partial ever writes stay zero: park them behind the tiles
+            if (P.jt_of_csc[e] == UINT32_MAX) P.jt_of_csc[e] = (uint32_t)std::min<uint64_t>(base++, 0x7ffffffeull);
+        if (base < 0x7fffffffull) {
+            P.n_j = (uint32_t)base;
+            for (uint32_t& v : P.aprod_a) v = P.jt_of_csc[v];
+            for (uint32_t& v : P.aprod_b) v = P.jt_of_csc[v];
+        } else {
+            P.direct = false;  // positions must leave bit 31 free for the accumulate flag
+            P.nnz_l = 0;
+            P.jt_of_csc.clear();
+        }
+    }
     const uint64_t nnz_l = P.direct ? P.nnz_l : 0;
-    const uint64_t total = (uint64_t)n + 2ull * m + nnz_j + nnz_l + 3ull * n;
+    const uint64_t total = (uint64_t)n + 2ull * m + P.n_j + nnz_l + 3ull * n;
     if (total >= 0xfffffff0ull) {  // 32-bit slots: fall back to the PCG path
         P.direct = false;
         P.nnz_l = 0;
+        P.jt_of_csc.clear();
+        P.n_j = nnz_j;
     }
     P.X0 = 0;
     P.R0 = n;
     P.RN0 = P.R0 + m;
     P.J0 = P.RN0 + m;
-    P.L0 = P.J0 + nnz_j;
+    P.L0 = P.J0 + P.n_j;
     P.RV0 = P.L0 + (P.direct ? P.nnz_l : 0);
     P.Y0 = P.RV0 + n;
     P.D0 = P.Y0 + n;

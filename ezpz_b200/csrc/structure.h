@@ -49,7 +49,9 @@ struct SmallProgram {
 
 // The single-large-system programme (large.cu): the processing order of the assembly phase and, unless the
 // factor would be too large, the supernodal sparse direct solve built by sparse_direct.cpp.  Slots index one
-// global value array  VG = [x | r | r_next | J (CSC order) | L panels | 1/pivot | y | d].
+// global value array  VG = [x | r | r_next | J | L panels | 1/pivot | y | d].  J is stored in CSC order on the PCG path (its
+// SpMVs walk columns) and in TILE ORDER on the direct path (jt_of_csc): the partial q of lane l of record tile t lives at
+// jt_base(t) + q * 32 + l, so a warp's store of one partial is 256 contiguous bytes instead of 32 scattered sectors.
 struct LargeProgram {
     bool built = false;
     bool direct = false;          // sparse direct solve available (otherwise the PCG path runs)
@@ -61,6 +63,8 @@ struct LargeProgram {
     std::vector<uint32_t> cons_order;                      // processing slots of the assembly phase -> constraint
                                                            // index (tile-local kind sort, UINT32_MAX = padding)
     std::vector<uint32_t> perm;                            // elimination position -> variable
+    std::vector<uint32_t> jt_of_csc;                       // direct path: position in the J region of each CSC entry (empty = CSC order)
+    uint32_t n_j = 0;                                      // doubles of the J region (nnz in CSC order; more in tile order: idle lanes)
     // Supernode s = columns [sn_ptr[s], sn_ptr[s+1]) (a chain of the elimination tree, <= 16 columns).  Its panel is
     // dense, row-major, h x w doubles at VG[L0 + panel_off[s]]: rows sn_rows[sn_row_ptr[s] ...) = the w own columns
     // (the diagonal block) followed by the sorted union of the columns' sub-diagonal rows.
