@@ -781,7 +781,8 @@ int32_t ezpz_b200_solve_batch(ezpz_context_t* ctx, const ezpz_structure_t* s, co
         const uint64_t waves = (batch + wave - 1) / wave;
         chunk = wave * ((waves + 7) / 8);
     }
-    if (const char* env = std::getenv("EZPZ_B200_CHUNKS")) {
+    if (const char* env = std::getenv("EZPZ_B200_CHUNKS"); env && s->small.valid) {  // (the one-CTA-per-problem path keeps its
+                                                                                      // per-problem state in ONE buffer: one chunk)
         const uint64_t k = std::max<uint64_t>(1, std::strtoull(env, nullptr, 10));
         chunk = (batch + k - 1) / k;
     }

@@ -658,9 +658,11 @@ __device__ __noinline__ void sn_factor(const LargeArgs& a, uint32_t pos, uint32_
     }
 }
 
-// Backward substitution of one supernode (stages descending): for its columns j descending,
-// d[j] = (y[j] - sum_{i > j} L[i][j] d[i]) / L[j][j], rows i ascending (first the panel's own rows, then the rows
-// below); the final value is also scattered to d in variable numbering.  One sequential chain per supernode.
+// Backward substitution of one supernode (stages descending): d[j] = (y[j] - sum_{i > j} L[i][j] d[i]) / L[j][j] with the
+// rows i DESCENDING — first the rows below the supernode's diagonal block (their d is final), then the block's own rows.
+// The columns of the supernode advance together: lane c of the team's first warp owns column c; the rows below the block
+// are w independent chains; inside the block, step t (t = w-1 ... 0) finalises d[t] and every column c < t applies it —
+// one shuffle per step instead of one sequential chain per supernode.  The final values also go to d in variable numbering.
 template <int TEAM>
 __device__ __noinline__ void sn_backward(const LargeArgs& a, uint32_t pos, uint32_t lane, double* stage) {
     using Caps = TeamCaps<TEAM>;
@@ -669,9 +671,19 @@ __device__ __noinline__ void sn_backward(const LargeArgs& a, uint32_t pos, uint3
     const uint4 hdr = __ldg(reinterpret_cast<const uint4*>(a.stage_rec) + 2 * (size_t)pos);
     const uint32_t j0 = hdr.x, w = hdr.y, h = hdr.z, rb = hdr.w;
     const double* G = lv + __ldg(a.stage_rec + 8 * (size_t)pos + 4);
-    const bool staged = TEAM > 1 && h * w <= Caps::panel && h <= Caps::block;
+    if (TEAM == 1) {  // a panel of a few doubles: one thread, straight from global memory
+        for (uint32_t c = w; c-- > 0;) {
+            double acc = y[j0 + c];
+            for (uint32_t r = h; r-- > c + 1;) acc = __fma_rn(-G[r * w + c], y[__ldg(a.sn_rows + rb + r)], acc);
+            const double v = __dmul_rn(acc, a.vg[a.RV0 + j0 + c]);
+            y[j0 + c] = v;
+            a.vg[a.D0 + __ldg(a.perm + j0 + c)] = v;
+        }
+        return;
+    }
+    const bool staged = h * w <= Caps::panel && h <= Caps::block;
     const double* P = G;
-    double* dv = nullptr;  // d of the panel's rows (own columns: being computed; below: final), staged variant only
+    double* dv = nullptr;  // staged variant: y of the block's own rows, d of the rows below
     if (staged) {
         double* Ps = stage;
         dv = stage + Caps::panel;
@@ -680,13 +692,21 @@ __device__ __noinline__ void sn_backward(const LargeArgs& a, uint32_t pos, uint3
         P = Ps;
         team_sync<TEAM>();
     }
-    if (lane == 0) {
-        for (uint32_t c = w; c-- > 0;) {
-            double acc = staged ? dv[c] : y[j0 + c];
-            for (uint32_t r = c + 1; r < h; ++r)
-                acc = __fma_rn(-P[r * w + c], staged ? dv[r] : y[__ldg(a.sn_rows + rb + r)], acc);
-            const double v = __dmul_rn(acc, a.vg[a.RV0 + j0 + c]);
-            if (staged) dv[c] = v;
+    if (lane < 32) {
+        const uint32_t c = lane;
+        double acc = 0.0, rinv = 0.0;
+        if (c < w) {
+            acc = staged ? dv[c] : y[j0 + c];
+            rinv = a.vg[a.RV0 + j0 + c];
+            for (uint32_t r = h; r-- > w;) acc = __fma_rn(-P[r * w + c], staged ? dv[r] : y[__ldg(a.sn_rows + rb + r)], acc);
+        }
+        double v = 0.0;
+        for (uint32_t t = w; t-- > 0;) {
+            const double vt = __shfl_sync(0xffffffffu, __dmul_rn(acc, rinv), t);
+            if (c == t) v = vt;
+            else if (c < t) acc = __fma_rn(-P[t * w + c], vt, acc);
+        }
+        if (c < w) {
             y[j0 + c] = v;
             a.vg[a.D0 + __ldg(a.perm + j0 + c)] = v;
         }

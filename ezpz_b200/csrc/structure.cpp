@@ -234,10 +234,11 @@ void build_small_program(ezpz_structure& S) {
         tb.begin(P.D0 + i, OP_INIT_DST | OP_NEGATE, OP_FIN_MUL, diag_slot[i]);
         for (const RowEnt& e : lrow[i]) tb.pair(e.slot, P.D0 + e.col);
     }
-    // (5) backward substitution Lt d = y
+    // (5) backward substitution Lt d = y, rows of every column DESCENDING (on the large path this lets the
+    // columns of a supernode advance together, and one order serves both paths and the oracle)
     for (uint32_t ii = n; ii-- > 0;) {
         tb.begin(P.D0 + ii, OP_INIT_DST | OP_NEGATE, OP_FIN_MUL, diag_slot[ii]);
-        for (uint32_t p = S.l_col_ptr[ii] + 1; p < S.l_col_ptr[ii + 1]; ++p) tb.pair(P.L0 + p, P.D0 + S.l_row_idx[p]);
+        for (uint32_t p = S.l_col_ptr[ii + 1]; p-- > S.l_col_ptr[ii] + 1;) tb.pair(P.L0 + p, P.D0 + S.l_row_idx[p]);
     }
     P.n_ops = tb.n_ops;
     P.n_pairs = tb.n_pairs;

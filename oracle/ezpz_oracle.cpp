@@ -26,8 +26,10 @@
 //             the factorisation fails ("LltError::Numeric") iff !(acc > 0) or acc is not finite;
 //             rinv[i] = 1.0 / sqrt(acc) (IEEE sqrt, then IEEE divide) — one divide per column, every
 //             other "division by the pivot" is a multiplication by rinv;
-//   y, d    = forward / backward substitution with the same fma(-l, v, acc) pattern, k ascending,
-//             finished by acc * rinv[i];
+//   y, d    = forward / backward substitution with the same fma(-l, v, acc) pattern, finished by acc * rinv[i]:
+//             forward y[i] over the columns k < i ASCENDING; backward d[j] over the rows i > j DESCENDING (a written
+//             choice like the others — faer's own order is not observable; descending lets the columns of a supernode
+//             advance together on the device);
 //   S       = sum r_i^2 as acc = acc + r_i*r_i (two roundings each, as Rust's .map(|x| x*x).sum()).
 // Two OPTIONAL knobs exist only so that the large-system CUDA path can be checked bit for bit (the defaults are
 // the reference-faithful natural order and sequential sum; tests compare both ways):
@@ -354,7 +356,7 @@ struct Chol {
         }
         for (uint32_t ii = n; ii-- > 0;) {
             double acc = b[ii];
-            for (uint32_t q = l_colptr[ii]; q < l_colptr[ii + 1]; ++q)
+            for (uint32_t q = l_colptr[ii + 1]; q-- > l_colptr[ii];)  // rows i DESCENDING (see the header comment)
                 acc = std::fma(-l_val[l_colidx[q]], b[l_colrow[q]], acc);
             b[ii] = acc * l_diag[ii];
         }
