@@ -278,16 +278,19 @@ __device__ void max_abs_partial(const double* v, uint32_t count, uint32_t tid, u
     if (threadIdx.x == 0) *partial_out = sm[0];
     __syncthreads();
 }
-// Fold of the per-CTA partials, done once per CTA (thread 0, same order in every CTA) and broadcast through
-// shared memory.  Must be called by every thread of the CTA.
+// Fold of the per-CTA partials, once per CTA and broadcast through shared memory: the CTA loads the partials with one
+// coalesced pass (a single thread walking them in global memory pays an L2 round trip per handful of values), then a
+// fixed tree reduces them (the NaN-ignoring max does not depend on the order).  Must be called by every thread of the CTA.
 __device__ double fold_max(const double* partials, uint32_t count, double* sm) {
     __syncthreads();
-    if (threadIdx.x == 0) {
-        double mx = partials[0];
-        for (uint32_t i = 1; i < count; ++i) mx = ezm::ez_fmax(mx, partials[i]);
-        sm[0] = mx;
-    }
+    double mx = __longlong_as_double(0x7ff8000000000000LL);
+    for (uint32_t i = threadIdx.x; i < count; i += blockDim.x) mx = ezm::ez_fmax(mx, partials[i]);
+    sm[threadIdx.x] = mx;
     __syncthreads();
+    for (uint32_t s = blockDim.x / 2; s > 0; s >>= 1) {
+        if (threadIdx.x < s) sm[threadIdx.x] = ezm::ez_fmax(sm[threadIdx.x], sm[threadIdx.x + s]);
+        __syncthreads();
+    }
     const double v = sm[0];
     __syncthreads();
     return v;
@@ -303,23 +306,31 @@ __device__ void block_sum(double v, double* partial_out, double* sm) {
     if (threadIdx.x == 0) *partial_out = sm[0];
     __syncthreads();
 }
+// Sequential fold (index order, from +0.0) of `count` values in global memory, once per CTA: staged into shared memory
+// kSmDoubles at a time by the whole CTA, added in order by thread 0.
 __device__ double fold_sum(const double* partials, uint32_t count, double* sm) {
+    constexpr uint32_t kStage = 4096 - 1;  // sm[kStage] carries the running sum / the result
     __syncthreads();
-    if (threadIdx.x == 0) {
-        double s = 0.0;
-        uint32_t i = 0;
-        for (; i + 8 <= count; i += 8) {
-            double v[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) v[u] = partials[i + u];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) s = s + v[u];
+    double s = 0.0;
+    for (uint32_t base = 0; base < count; base += kStage) {
+        const uint32_t len = min(kStage, count - base);
+        for (uint32_t i = threadIdx.x; i < len; i += blockDim.x) sm[i] = partials[base + i];
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t i = 0;
+            for (; i + 8 <= len; i += 8) {
+                const double s0 = sm[i], s1 = sm[i + 1], s2 = sm[i + 2], s3 = sm[i + 3];
+                const double s4 = sm[i + 4], s5 = sm[i + 5], s6 = sm[i + 6], s7 = sm[i + 7];
+                s = s + s0; s = s + s1; s = s + s2; s = s + s3;
+                s = s + s4; s = s + s5; s = s + s6; s = s + s7;
+            }
+            for (; i < len; ++i) s = s + sm[i];
         }
-        for (; i < count; ++i) s = s + partials[i];
-        sm[0] = s;
+        __syncthreads();
     }
+    if (threadIdx.x == 0) sm[kStage] = s;
     __syncthreads();
-    const double v = sm[0];
+    const double v = sm[kStage];
     __syncthreads();
     return v;
 }
@@ -486,8 +497,13 @@ __device__ __forceinline__ void sn_apply_update(double* P, uint32_t w, double* y
 //      for every pair of K's rows (i >= j) with j a column of J;  y[j] = fma(-L[j][k], y[k], y[j]);
 //   2. the panel's own columns c ascending: the same fma chains over the columns k < c of the panel, pivot
 //      (fails unless > 0 and finite), 1/pivot, scaling, and y[c].
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// next_pos / next2_pos: the panels this team factorises after this one (UINT32_MAX = none): their records, panel and first
+// update records are pulled into L2 while this panel's own loads are in flight.
 template <int TEAM>
-__device__ __noinline__ void sn_factor(const LargeArgs& a, uint32_t pos, uint32_t lane, double* stage) {
+__device__ __noinline__ void sn_factor(const LargeArgs& a, uint32_t pos, uint32_t lane, double* stage, uint32_t next_pos = UINT32_MAX,
+                                       uint32_t next2_pos = UINT32_MAX) {
     using Caps = TeamCaps<TEAM>;
     double* lv = a.vg + a.L0;
     double* y = a.vg + a.Y0;
@@ -506,6 +522,15 @@ __device__ __noinline__ void sn_factor(const LargeArgs& a, uint32_t pos, uint32_
         if (staged)
             for (uint32_t t = lane; t < h * w; t += TEAM) P[t] = G[t];
         for (uint32_t c = lane; c < w; c += TEAM) ys[c] = y[j0 + c];
+        if (TEAM == 32 && next_pos != UINT32_MAX) {
+            const uint4 nh = __ldg(reinterpret_cast<const uint4*>(a.stage_rec) + 2 * (size_t)next_pos);
+            const uint4 nh2 = __ldg(reinterpret_cast<const uint4*>(a.stage_rec) + 2 * (size_t)next_pos + 1);
+            const uint32_t lines = (nh.y * nh.z * 8u + 127u) / 128u;
+            for (uint32_t q = lane; q < lines; q += 32) prefetch_l2(lv + nh2.x + 16u * q);
+            if (lane == 31) prefetch_l2(y + nh.x);
+            if (lane == 30 && nh2.z) prefetch_l2(a.upd_rec + 8 * (size_t)nh2.y);
+            if (lane == 29 && next2_pos != UINT32_MAX) prefetch_l2(a.stage_rec + 8 * (size_t)next2_pos);
+        }
         team_sync<TEAM>();
     }
     // ---- 1. external updates
@@ -724,7 +749,8 @@ __device__ void direct_factor_stage(const LargeArgs& a, uint32_t st, uint32_t ti
                    b3 = __ldg(a.stage_ptr + 3 * st + 3);
     for (uint32_t k = b0 + tid; k < b1; k += nth) sn_factor<1>(a, k, 0, nullptr);
     if (b2 - b1 > a.vgrid) {
-        for (uint32_t k = b1 + (tid >> 5); k < b2; k += nth >> 5) sn_factor<32>(a, k, threadIdx.x & 31u, warp_stage);
+        for (uint32_t k = b1 + (tid >> 5), nw = nth >> 5; k < b2; k += nw)
+            sn_factor<32>(a, k, threadIdx.x & 31u, warp_stage, k + nw < b2 ? k + nw : UINT32_MAX, k + 2 * nw < b2 ? k + 2 * nw : UINT32_MAX);
         __syncthreads();  // the CTA panels below reuse the warps' shared memory
         for (uint32_t k = b2 + a.vblock; k < b3; k += a.vgrid) sn_factor<512>(a, k, threadIdx.x, cta_stage);
     } else {

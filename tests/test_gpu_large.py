@@ -220,3 +220,48 @@ def test_batch_of_mid_size_systems_one_cta_per_problem(ctx, cells, batch):
         assert np.array_equal(out.degen_count[b], one.degen_count), b
         assert np.array_equal(out.jacobian[b], one.jacobian, equal_nan=True), b
     assert out.iterations[3] == 35 and not (out.status[3] & 1)
+
+
+def test_batch_of_mid_size_systems_pcg_path(ctx):
+    """The one-CTA-per-problem batch on the PCG path (forced): per-problem CSR copies and CG vectors; every problem equals the
+    same problem solved alone, bit for bit (same kernel code, same reduction shapes inside one CTA)."""
+    os.environ["EZPZ_B200_FORCE_PCG"] = "1"
+    try:
+        recs, n, g, exact = wl.chain_sketch(16)
+        st = ez.Structure(recs, n)
+    finally:
+        del os.environ["EZPZ_B200_FORCE_PCG"]
+    assert st.ordering()["path"] == 2
+    rng = np.random.default_rng(5)
+    G = g[None, :] + rng.uniform(-0.02, 0.02, (12, n))
+    out = ctx.solve_batch(st, G, want_unsat=True, want_degen=True, want_jacobian=True)
+    o = orc.solve_inner(recs, G[0])
+    for b in range(len(G)):
+        one = ctx.solve_one(st, G[b], want_jacobian=True)
+        assert one.path_used == 2
+        assert out.iterations[b] == one.iterations and (out.status[b] & 7) == (one.status & 7), b
+        assert np.array_equal(out.final_values[b], one.final_values), b
+        assert np.array_equal(out.unsat_mask[b], one.unsat_mask) and np.array_equal(out.degen_count[b], one.degen_count), b
+        assert np.array_equal(out.jacobian[b], one.jacobian), b
+    assert out.iterations[0] == o.iterations and np.abs(out.final_values[0] - o.final_values).max() <= 1e-9
+
+
+def test_batch_of_mid_size_systems_verdicts_and_errors(ctx):
+    """Inconsistent members of a batch (a contradicting Fixed row appended to the sketch) come back unsatisfied with the
+    oracle's constraint list; per-problem parameter overrides are refused on this path instead of being ignored."""
+    recs, n, g, exact = wl.chain_sketch(16)
+    extra = ez.records([ez.Constraint.Fixed(0, float(exact[0]) + 0.5)])
+    recs2 = np.concatenate([recs, extra])
+    st = ez.Structure(recs2, n)
+    assert st.ordering()["path"] == 1
+    od = st.ordering()
+    G = np.stack([g, g + 0.01])
+    out = ctx.solve_batch(st, G, want_unsat=True)
+    for b in range(2):
+        o = orc.solve_inner_ordered(recs2, G[b], od["elim_order"], od["sum_chunk"])
+        bits = np.unpackbits(out.unsat_mask[b].view(np.uint8), bitorder="little")[:st.n_cons]
+        assert np.flatnonzero(bits).tolist() == o.unsatisfied and len(o.unsatisfied) > 0
+        assert out.iterations[b] == o.iterations and bool(out.status[b] & 1) == o.converged and (out.status[b] & 2)
+        assert_bitwise(out.final_values[b], o.final_values, f"problem {b}")
+    with pytest.raises(ez.EzpzError):
+        ctx.solve_batch(st, G, params=np.zeros((2, st.n_cons)))
