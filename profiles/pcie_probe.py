@@ -1,5 +1,5 @@
 import os, subprocess, time, torch, ctypes
-print(subprocess.run("nvidia-smi topo -m; nproc; lscpu | grep -i 'numa\|socket\|model name'; cat /sys/bus/pci/devices/*/numa_node 2>/dev/null | sort | uniq -c", shell=True, capture_output=True, text=True).stdout)
+print(subprocess.run("nvidia-smi topo -m; nproc; lscpu | grep -i -E 'numa|socket|model name'; cat /sys/bus/pci/devices/*/numa_node 2>/dev/null | sort | uniq -c", shell=True, capture_output=True, text=True).stdout)
 print("affinity now:", len(os.sched_getaffinity(0)), sorted(os.sched_getaffinity(0))[:8], "...")
 def bw(tag, nbytes, wc=False):
     n = nbytes // 8
