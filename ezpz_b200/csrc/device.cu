@@ -484,6 +484,17 @@ int32_t ensure_ws(ezpz_context* ctx, size_t bytes, ezpz_error_detail_t* detail) 
     return EZPZ_OK;
 }
 
+int32_t ensure_pin(ezpz_context* ctx, size_t bytes, ezpz_error_detail_t* detail) {
+    if (bytes <= ctx->pin_bytes) return EZPZ_OK;
+    if (ctx->pin) cudaFreeHost(ctx->pin);
+    ctx->pin = nullptr;
+    ctx->pin_bytes = 0;
+    size_t want = std::max(bytes, (size_t)256 << 10);
+    EZ_CUDA(cudaHostAlloc(&ctx->pin, want, cudaHostAllocDefault), "cudaHostAlloc(staging)");
+    ctx->pin_bytes = want;
+    return EZPZ_OK;
+}
+
 // The small-system tape in device format (see run_tape) for a given shared-memory stride: byte offsets
 // slot * stride * 8.  Built once per stride; kept on the host (for the kernel-parameter path) and on the device.
 int32_t get_scaled_tape(ezpz_context* ctx, const ezpz_structure* cs, DeviceCopy* d, uint32_t stride, ScaledTape** out,
@@ -610,6 +621,7 @@ void ezpz_b200_context_destroy(ezpz_context_t* ctx) {
         if (ctx->pipe_done[k]) cudaEventDestroy(ctx->pipe_done[k]);
     }
     if (ctx->ws) cudaFree(ctx->ws);
+    if (ctx->pin) cudaFreeHost(ctx->pin);
     ezs::release_structure_cache(ctx);
     delete ctx;
 }

@@ -30,6 +30,7 @@ struct DeviceCopy {
 int32_t cuda_fail(cudaError_t e, ezpz_error_detail_t* detail, const char* what);
 int32_t get_device_copy(ezpz_context* ctx, const ezpz_structure* s, DeviceCopy** out, ezpz_error_detail_t* detail);
 int32_t ensure_ws(ezpz_context* ctx, size_t bytes, ezpz_error_detail_t* detail);
+int32_t ensure_pin(ezpz_context* ctx, size_t bytes, ezpz_error_detail_t* detail);
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 void release_large(DeviceCopy* d);  // large.cu
 // Single system that does not fit the thread-per-problem kernel (large.cu).
@@ -57,6 +58,9 @@ struct ezpz_context {
     // grow-only device workspace for the host-buffer entry points
     void* ws = nullptr;
     size_t ws_bytes = 0;
+    // grow-only pinned host staging buffer (small single-system solves: one DMA each way instead of pageable copies)
+    void* pin = nullptr;
+    size_t pin_bytes = 0;
     // topology cache of ezpz_b200_solve (host_api.cpp): analysed structures keyed by their constraint list
     void* structure_cache = nullptr;
 };

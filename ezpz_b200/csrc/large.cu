@@ -23,9 +23,10 @@
 //   * sum r^2       single-CTA systems: a strictly sequential left fold, as Rust's `.map(|x| x * x).sum()` is
 //                   (newton.rs:45,116) — the accept test `S' < S` is a floating-point tie-breaker, so the
 //                   summation order is part of the reference semantics.  Multi-CTA systems (more than 4,096
-//                   values): the same fold inside chunks of 1,024 rows, then a sequential fold of the chunk
-//                   sums (a 1M-row sequential chain would cost 5 ms per evaluation); the oracle reproduces
-//                   this with sum_chunk = 1024.  max|r| and max|d| are order-independent.
+//                   values): the same fold inside chunks of rows, then a sequential fold of the chunk sums (a 1M-row
+//                   sequential chain would cost 5 ms per evaluation); the chunk is the power of two next to sqrt(m) within
+//                   [64, 1024] (ezs::sum_chunk_for) and the oracle reproduces the fold with that sum_chunk.  max|r| and
+//                   max|d| are order-independent.
 // spmv_csr_kernel / assemble_large_kernel are also exported as stand-alone launches (ezpz_b200_large_bench)
 // so that their HBM throughput can be timed with CUDA events and profiled with ncu.
 #include <cooperative_groups.h>
@@ -94,7 +95,7 @@ struct LargeArgs {
     uint32_t unit_weights;
     uint32_t cluster;  // launched as one thread-block cluster (mid-size systems)
     const uint32_t* jmap;   // direct path: position in the J region of each CSC entry (tile order); null = CSC order
-    uint32_t chunked_sums;  // sum of squares folded in chunks of kSumChunk rows (systems of more than kSingleCtaWork values)
+    uint32_t sum_chunk;     // sum of squares folded in chunks of this many rows (ezs::sum_chunk_for); 0 = one sequential fold
     // CTAs cooperating on ONE system and this CTA's rank among them (set by the kernel: the whole grid, or 1 / 0 in
     // batch mode, where every CTA solves its own problem with CTA-level barriers)
     uint32_t vgrid, vblock;
@@ -361,10 +362,9 @@ __device__ void sequential_sum_squares(const double* v, uint32_t count, double* 
     if (threadIdx.x == 0) *out = acc;
 }
 
-// Chunked sum of squares for multi-CTA grids: chunk c = rows [c * kSumChunk, ...) folded sequentially from +0.0
+// Chunked sum of squares for multi-CTA grids: chunk c = rows [c * chunk, ...) folded sequentially from +0.0
 // into out[c]; the caller synchronises and folds the chunk sums sequentially (fold_sum).
-constexpr uint32_t kSumChunk = 1024;
-__device__ void chunk_sum_squares(const double* v, uint32_t count, double* out, uint32_t tid, uint32_t nth, double* warp_stage) {
+__device__ void chunk_sum_squares(const double* v, uint32_t count, uint32_t kSumChunk, double* out, uint32_t tid, uint32_t nth, double* warp_stage) {
     // One warp per chunk: the lanes stage the chunk in shared memory with coalesced loads (kWarpStageDoubles = 512
     // values per round), lane 0 runs the dependent chain of adds from there.
     const uint32_t chunks = (count + kSumChunk - 1) / kSumChunk;
@@ -876,14 +876,14 @@ __global__ void __launch_bounds__(kBlock, 1) lm_large_kernel(const LargeArgs a_i
     sync();
     lap(0);
     // S = sum r^2 (see the header comment for the two summation orders)
-    const uint32_t n_chunks = (a.m + kSumChunk - 1) / kSumChunk;
+    const uint32_t n_chunks = a.sum_chunk ? (a.m + a.sum_chunk - 1) / a.sum_chunk : 0u;
     auto sum_squares = [&](const double* v, double* ctrl_slot) -> double {
-        if (!a.chunked_sums) {
+        if (!a.sum_chunk) {
             sequential_sum_squares(v, a.m, ctrl_slot, sm, kSmDoubles);
             __syncthreads();
             return *ctrl_slot;
         }
-        chunk_sum_squares(v, a.m, a.sumsq, tid, nth, warp_stage);
+        chunk_sum_squares(v, a.m, a.sum_chunk, a.sumsq, tid, nth, warp_stage);
         sync();
         return fold_sum(a.sumsq, n_chunks, sm);
     };
@@ -1230,6 +1230,8 @@ struct LargeDevice {
     uint8_t* side = nullptr;
     uint32_t *degen = nullptr, *unsat = nullptr;
     LargeCtrl* ctrl = nullptr;
+    unsigned char* resblk = nullptr;  // [ctrl | unsat | degen], see get_large
+    size_t resblk_bytes = 0;
     int grid = 0;
     bool cluster = false;
     bool tables = false;
@@ -1364,12 +1366,19 @@ int32_t get_large(ezpz_context* ctx, const ezpz_structure* s, DeviceCopy* dc, La
         EZ_CUDA(cudaMalloc(&L->lvl_ns, sizeof(unsigned long long) * 2 * std::max<size_t>(1, P.n_levels)), "cudaMalloc(lvl_ns)");
         EZ_CUDA(cudaMemset(L->lvl_ns, 0, sizeof(unsigned long long) * 2 * std::max<size_t>(1, P.n_levels)), "cudaMemset(lvl_ns)");
     }
-    EZ_CUDA(cudaMalloc(&L->sumsq, sizeof(double) * ((size_t)s->m / kSumChunk + 2)), "cudaMalloc(sumsq)");
+    EZ_CUDA(cudaMalloc(&L->sumsq, sizeof(double) * ((size_t)s->m / 64 + 2)), "cudaMalloc(sumsq)");
     EZ_CUDA(cudaMalloc(&L->side, std::max<size_t>(1, L->n_slots)), "cudaMalloc(side)");
-    EZ_CUDA(cudaMalloc(&L->degen, sizeof(uint32_t) * std::max<size_t>(1, s->n_cons)), "cudaMalloc(degen)");
-    EZ_CUDA(cudaMalloc(&L->unsat, sizeof(uint32_t) * ((s->n_cons + 31) / 32 + 1)), "cudaMalloc(unsat)");
-    EZ_CUDA(cudaMalloc(&L->ctrl, sizeof(LargeCtrl)), "cudaMalloc(ctrl)");
-    EZ_CUDA(cudaMemset(L->ctrl, 0, sizeof(LargeCtrl)), "cudaMemset(ctrl)");  // not every field is written by every path
+    {
+        // control block, unsatisfied mask and degenerate counters in ONE allocation: a solve reads them back with one copy
+        const size_t b_ctrl = align_up(sizeof(LargeCtrl), 256), b_unsat = align_up(sizeof(uint32_t) * ((s->n_cons + 31) / 32 + 1), 256),
+                     b_degen = sizeof(uint32_t) * std::max<size_t>(1, s->n_cons);
+        L->resblk_bytes = b_ctrl + b_unsat + b_degen;
+        EZ_CUDA(cudaMalloc(&L->resblk, L->resblk_bytes), "cudaMalloc(result block)");
+        EZ_CUDA(cudaMemset(L->resblk, 0, L->resblk_bytes), "cudaMemset(result block)");  // not every field is written by every path
+        L->ctrl = reinterpret_cast<LargeCtrl*>(L->resblk);
+        L->unsat = reinterpret_cast<uint32_t*>(L->resblk + b_ctrl);
+        L->degen = reinterpret_cast<uint32_t*>(L->resblk + b_ctrl + b_unsat);
+    }
     // grid: one CTA for small systems (barriers are __syncthreads), else every SM, co-resident
     const size_t work = (size_t)s->n + s->m + nnz;
     int per_sm = 0;
@@ -1452,7 +1461,7 @@ void fill_args(LargeArgs& a, const ezpz_structure* s, const DeviceCopy* dc, cons
     a.direct = P.direct ? 1u : 0u;
     // the summation order belongs to the structure, not to the launch shape: a system solved alone (cluster / grid) and
     // the same system solved as one CTA's problem in a batch fold S the same way
-    a.chunked_sums = ((size_t)s->n + s->m + s->csc_row_idx.size() > kSingleCtaWork) ? 1u : 0u;
+    a.sum_chunk = ezs::sum_chunk_for(s->n, s->m, s->csc_row_idx.size());
 }
 
 // Batch mode epilogue: per problem, iterations / status out of its control block and x, masks, Jacobian out of its slices.
@@ -1500,7 +1509,7 @@ void release_large(DeviceCopy* d) {
     LargeDevice* L = (LargeDevice*)d->large;
     if (!L) return;
     void* ptrs[] = {L->jmap, L->recs, L->tiles, L->slot_orig, L->side_flags, L->csr_row_ptr, L->csr_col_idx, L->csc_col_ptr, L->csc_row_idx,
-                    L->vg, L->jr, L->cgv, L->partials, L->sumsq, L->lvl_ns, L->side, L->degen, L->unsat, L->ctrl};
+                    L->vg, L->jr, L->cgv, L->partials, L->sumsq, L->lvl_ns, L->side, L->resblk};
     for (uint32_t* p : L->direct_tables)
         if (p) cudaFree(p);
     for (void* p : ptrs)
@@ -1562,7 +1571,17 @@ int32_t solve_large(ezpz_context* ctx, const ezpz_structure* s, const ezpz_confi
     LargeArgs a;
     fill_args(a, s, dc, L, config);
     cudaStream_t st = ctx->stream;
-    EZ_CUDA(cudaMemcpyAsync(L->vg + a.X0, io->guesses, sizeof(double) * s->n, cudaMemcpyHostToDevice, st), "H2D guesses");
+    // Small systems go through the context's pinned staging buffer: one DMA in, two or three out and a single synchronisation,
+    // instead of five pageable copies that each stall the host (profiles/r01j_*).
+    const size_t b_x = sizeof(double) * s->n, b_j = io->jacobian ? sizeof(double) * a.nnz : 0;
+    const bool staged_io = 2 * b_x + L->resblk_bytes + b_j <= ((size_t)1 << 20);
+    unsigned char* pin = nullptr;
+    if (staged_io) {
+        EZ_TRY(ensure_pin(ctx, 2 * b_x + L->resblk_bytes + b_j, detail));
+        pin = static_cast<unsigned char*>(ctx->pin);
+        std::memcpy(pin, io->guesses, b_x);
+    }
+    EZ_CUDA(cudaMemcpyAsync(L->vg + a.X0, staged_io ? (const void*)pin : (const void*)io->guesses, b_x, cudaMemcpyHostToDevice, st), "H2D guesses");
     void* params[] = {(void*)&a};
     a.cluster = L->cluster ? 1u : 0u;
     if (L->grid == 1) {
@@ -1595,22 +1614,36 @@ int32_t solve_large(ezpz_context* ctx, const ezpz_structure* s, const ezpz_confi
     ctx->launches += 1;
     EZ_CUDA(cudaGetLastError(), "lm_large_kernel launch");
     LargeCtrl h;
-    EZ_CUDA(cudaMemcpyAsync(&h, L->ctrl, sizeof h, cudaMemcpyDeviceToHost, st), "D2H ctrl");
-    EZ_CUDA(cudaMemcpyAsync(io->final_values, L->vg + a.X0, sizeof(double) * s->n, cudaMemcpyDeviceToHost, st), "D2H finals");
-    if (io->unsat_mask)
-        EZ_CUDA(cudaMemcpyAsync(io->unsat_mask, L->unsat, sizeof(uint32_t) * ((s->n_cons + 31) / 32), cudaMemcpyDeviceToHost, st), "D2H unsat");
-    if (io->degen_count)
-        EZ_CUDA(cudaMemcpyAsync(io->degen_count, L->degen, sizeof(uint32_t) * s->n_cons, cudaMemcpyDeviceToHost, st), "D2H degen");
-    if (io->jacobian) {
-        const double* src = L->vg + a.J0;
-        if (a.jmap && a.nnz) {
-            export_j_csc_kernel<<<(unsigned)std::min<size_t>(((size_t)a.nnz + 255) / 256, 4096), 256, 0, st>>>(a, L->jr);
-            ctx->launches += 1;
-            src = L->jr;
-        }
-        EZ_CUDA(cudaMemcpyAsync(io->jacobian, src, sizeof(double) * a.nnz, cudaMemcpyDeviceToHost, st), "D2H jacobian");
+    const size_t uw = (s->n_cons + 31) / 32;
+    const double* jsrc = L->vg + a.J0;
+    if (io->jacobian && a.jmap && a.nnz) {
+        export_j_csc_kernel<<<(unsigned)std::min<size_t>(((size_t)a.nnz + 255) / 256, 4096), 256, 0, st>>>(a, L->jr);
+        ctx->launches += 1;
+        jsrc = L->jr;
     }
-    EZ_CUDA(cudaStreamSynchronize(st), "cudaStreamSynchronize");
+    if (staged_io) {
+        unsigned char* p_f = pin + b_x;
+        unsigned char* p_r = p_f + b_x;
+        unsigned char* p_j = p_r + L->resblk_bytes;
+        EZ_CUDA(cudaMemcpyAsync(p_r, L->resblk, L->resblk_bytes, cudaMemcpyDeviceToHost, st), "D2H results");
+        EZ_CUDA(cudaMemcpyAsync(p_f, L->vg + a.X0, b_x, cudaMemcpyDeviceToHost, st), "D2H finals");
+        if (io->jacobian) EZ_CUDA(cudaMemcpyAsync(p_j, jsrc, b_j, cudaMemcpyDeviceToHost, st), "D2H jacobian");
+        EZ_CUDA(cudaStreamSynchronize(st), "cudaStreamSynchronize");
+        std::memcpy(&h, p_r, sizeof h);
+        std::memcpy(io->final_values, p_f, b_x);
+        if (io->unsat_mask) std::memcpy(io->unsat_mask, p_r + (reinterpret_cast<unsigned char*>(L->unsat) - L->resblk), sizeof(uint32_t) * uw);
+        if (io->degen_count)
+            std::memcpy(io->degen_count, p_r + (reinterpret_cast<unsigned char*>(L->degen) - L->resblk), sizeof(uint32_t) * s->n_cons);
+        if (io->jacobian) std::memcpy(io->jacobian, p_j, b_j);
+    } else {
+        EZ_CUDA(cudaMemcpyAsync(&h, L->ctrl, sizeof h, cudaMemcpyDeviceToHost, st), "D2H ctrl");
+        EZ_CUDA(cudaMemcpyAsync(io->final_values, L->vg + a.X0, b_x, cudaMemcpyDeviceToHost, st), "D2H finals");
+        if (io->unsat_mask) EZ_CUDA(cudaMemcpyAsync(io->unsat_mask, L->unsat, sizeof(uint32_t) * uw, cudaMemcpyDeviceToHost, st), "D2H unsat");
+        if (io->degen_count)
+            EZ_CUDA(cudaMemcpyAsync(io->degen_count, L->degen, sizeof(uint32_t) * s->n_cons, cudaMemcpyDeviceToHost, st), "D2H degen");
+        if (io->jacobian) EZ_CUDA(cudaMemcpyAsync(io->jacobian, jsrc, b_j, cudaMemcpyDeviceToHost, st), "D2H jacobian");
+        EZ_CUDA(cudaStreamSynchronize(st), "cudaStreamSynchronize");
+    }
     const char* dbg = std::getenv("EZPZ_B200_DEBUG");
     if (dbg && dbg[0] == '1' && dbg[1] == '2' && a.lvl_ns) {
         std::vector<unsigned long long> t(2 * (size_t)a.n_levels);
@@ -1659,7 +1692,7 @@ int32_t solve_large_batch(ezpz_context* ctx, const ezpz_structure* s, const ezpz
     const bool use_cg = !P.direct;
     const size_t vg_stride = align_up(std::max<size_t>(1, P.VG), 32), jr_stride = use_cg ? align_up(std::max<size_t>(1, nnz), 32) : 0,
                  cgv_stride = use_cg ? align_up(4 * (size_t)s->n + s->m + 1, 32) : 0,
-                 sumsq_stride = align_up((size_t)s->m / kSumChunk + 2, 16), side_stride = align_up(std::max<size_t>(1, L->n_slots), 16),
+                 sumsq_stride = align_up((size_t)s->m / 64 + 2, 16), side_stride = align_up(std::max<size_t>(1, L->n_slots), 16),
                  degen_stride = s->n_cons, unsat_stride = (s->n_cons + 31) / 32 + 1;
     const size_t per_problem = 8 * (vg_stride + jr_stride + cgv_stride + sumsq_stride + 3) + side_stride +
                                4 * (degen_stride + unsat_stride) + sizeof(LargeCtrl);

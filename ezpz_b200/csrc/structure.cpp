@@ -559,7 +559,7 @@ int32_t ezpz_b200_structure_ordering(const ezpz_structure_t* s, int32_t* path, c
     if (n_levels) *n_levels = direct ? P.n_levels : 0;
     if (nnz_l) *nnz_l = direct ? P.nnz_l : 0;
     // large.cu: single-CTA systems (n + m + nnz <= 4,096) fold sequentially, larger ones (cluster or grid) in chunks of 1,024
-    if (sum_chunk) *sum_chunk = (P.built && (size_t)s->n + s->m + s->csc_row_idx.size() > 4096) ? 1024u : 0u;
+    if (sum_chunk) *sum_chunk = P.built ? ezs::sum_chunk_for(s->n, s->m, s->csc_row_idx.size()) : 0u;
     return EZPZ_OK;
 }
 

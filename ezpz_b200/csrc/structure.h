@@ -112,6 +112,15 @@ struct ezpz_structure {
 };
 
 namespace ezs {
+// Summation order of S = sum r^2 on the large path: 0 = one sequential fold (systems of at most 4,096
+// values, which one CTA solves), otherwise rows are folded sequentially inside chunks of this many rows and the chunk sums
+// are folded sequentially: the power of two next to sqrt(m), within [64, 1024], so that neither chain is long.
+inline uint32_t sum_chunk_for(uint32_t n, uint32_t m, size_t nnz) {
+    if ((size_t)n + m + nnz <= 4096) return 0;
+    uint32_t c = 64;
+    while (c < 1024 && (uint64_t)c * c < m) c *= 2;
+    return c;
+}
 // Implemented in device.cu; called by ezpz_b200_structure_destroy.
 void release_device_copies(ezpz_structure* s);
 // sparse_direct.cpp: ordering, symbolic factorisation and level schedule of the large-system direct solve.

@@ -21,7 +21,7 @@ def test_massive_parallel_system_direct_path(ctx, lines, over):
     out = ctx.solve_one(st, g)
     assert out.path_used == 1
     od = st.ordering()
-    assert not od["nested"] and od["sum_chunk"] == 1024  # natural order; one cluster of 8 CTAs, chunked sum of squares
+    assert not od["nested"] and od["sum_chunk"] == 64  # natural order; one cluster of 8 CTAs, chunked sum of squares
     o = orc.solve_inner_ordered(recs, g, None, od["sum_chunk"])
     ref = orc.solve_inner(recs, g)  # the reference-faithful sequential sum: same trajectory, same solution to 1e-9
     assert ref.iterations == o.iterations and np.abs(ref.final_values - o.final_values).max() <= 1e-9
@@ -62,13 +62,13 @@ def test_chain_sketch_direct_single_cta(ctx, cells):
 
 def test_chain_sketch_direct_cluster(ctx):
     od = _check_direct(ctx, 64)  # 832 variables: one thread-block cluster of 8 CTAs, nested-dissection order
-    assert od["nested"] and od["sum_chunk"] == 1024
+    assert od["nested"] and od["sum_chunk"] == 64
 
 
 @pytest.mark.parametrize("cells", [1024, 8192])
 def test_chain_sketch_direct_grid(ctx, cells):
     od = _check_direct(ctx, cells)  # cooperative grid, levels run grid-wide then by one CTA
-    assert od["nested"] and od["sum_chunk"] == 1024
+    assert od["nested"] and od["sum_chunk"] == (128 if cells == 1024 else 512)  # the power of two next to sqrt(m)
 
 
 def test_chain_sketch_1m_variables(ctx):

@@ -204,7 +204,7 @@ def test_large_system_ordering_host_analysis():
     import orc
     recs, n, g, _ = wl.system_from_text(wl.massive_problem_text(500, False))
     od = ez.Structure(recs, n).ordering()
-    assert od["path"] == 1 and not od["nested"] and od["n_levels"] <= 4 and od["sum_chunk"] == 1024
+    assert od["path"] == 1 and not od["nested"] and od["n_levels"] <= 4 and od["sum_chunk"] == 64
     assert np.array_equal(od["elim_order"], np.arange(n))
     heights = {}
     for cells in (64, 1024, 4096):
