@@ -404,25 +404,31 @@ __device__ void direct_zero(const LargeArgs& a, uint32_t tid, uint32_t nth) {
     for (uint32_t e = tid; e < a.nnz_l; e += nth) lv[e] = 0.0;
 }
 __device__ void direct_assemble(const LargeArgs& a, double lambda, uint32_t tid, uint32_t nth) {
-    const double* jv = a.vg + a.J0;
-    const double* r = a.vg + a.R0;
-    double* lv = a.vg + a.L0;
-    for (uint32_t k = tid; k < a.n_aent; k += nth) {
-        const uint32_t qb = __ldg(a.aprod_ptr + k), qe = __ldg(a.aprod_ptr + k + 1);
+    // (argument fields are read once: the block lives in local memory and stores force reloads, see sn_factor)
+    const double* const jv = a.vg + a.J0;
+    const double* const r = a.vg + a.R0;
+    double* const lv = a.vg + a.L0;
+    double* const yv = a.vg + a.Y0;
+    const uint32_t *const aprod_ptr = a.aprod_ptr, *const aprod_a = a.aprod_a, *const aprod_b = a.aprod_b, *const aent_slot = a.aent_slot;
+    const uint32_t *const perm = a.perm, *const col_ptr = a.csc_col_ptr, *const row_idx = a.csc_row_idx, *const jmap = a.jmap,
+                   *const diag_slot = a.diag_slot;
+    const uint32_t n_aent = a.n_aent, n = a.n;
+    for (uint32_t k = tid; k < n_aent; k += nth) {
+        const uint32_t qb = __ldg(aprod_ptr + k), qe = __ldg(aprod_ptr + k + 1);
         double acc = 0.0;
-        for (uint32_t q = qb; q < qe; ++q) acc = __fma_rn(jv[__ldg(a.aprod_a + q)], jv[__ldg(a.aprod_b + q)], acc);
-        lv[__ldg(a.aent_slot + k)] = acc;
+        for (uint32_t q = qb; q < qe; ++q) acc = __fma_rn(jv[__ldg(aprod_a + q)], jv[__ldg(aprod_b + q)], acc);
+        lv[__ldg(aent_slot + k)] = acc;
     }
-    for (uint32_t j = tid; j < a.n; j += nth) {
-        const uint32_t c = __ldg(a.perm + j);
+    for (uint32_t j = tid; j < n; j += nth) {
+        const uint32_t c = __ldg(perm + j);
         double dg = 0.0, b = 0.0;
-        for (uint32_t e = __ldg(a.csc_col_ptr + c); e < __ldg(a.csc_col_ptr + c + 1); ++e) {
-            const double v = jv[a.jmap ? __ldg(a.jmap + e) : e];
+        for (uint32_t e = __ldg(col_ptr + c), ee = __ldg(col_ptr + c + 1); e < ee; ++e) {
+            const double v = jv[jmap ? __ldg(jmap + e) : e];
             dg = __fma_rn(v, v, dg);
-            b = __fma_rn(v, -r[__ldg(a.csc_row_idx + e)], b);
+            b = __fma_rn(v, -r[__ldg(row_idx + e)], b);
         }
-        lv[__ldg(a.diag_slot + j)] = __dadd_rn(dg, lambda);
-        a.vg[a.Y0 + j] = b;
+        lv[__ldg(diag_slot + j)] = __dadd_rn(dg, lambda);
+        yv[j] = b;
     }
 }
 
@@ -505,11 +511,18 @@ template <int TEAM>
 __device__ __noinline__ void sn_factor(const LargeArgs& a, uint32_t pos, uint32_t lane, double* stage, uint32_t next_pos = UINT32_MAX,
                                        uint32_t next2_pos = UINT32_MAX) {
     using Caps = TeamCaps<TEAM>;
-    double* lv = a.vg + a.L0;
-    double* y = a.vg + a.Y0;
-    const uint4 hdr = __ldg(reinterpret_cast<const uint4*>(a.stage_rec) + 2 * (size_t)pos);        // j0, w, h, rows
-    const uint4 hdr2 = __ldg(reinterpret_cast<const uint4*>(a.stage_rec) + 2 * (size_t)pos + 1);   // panel, first update, updates
+    // The argument block lives in local memory inside the LM kernel and every store through a generic pointer makes the
+    // compiler reload its fields: everything the loops below need is read ONCE here.
+    double* const lv = a.vg + a.L0;
+    double* const y = a.vg + a.Y0;
+    const uint32_t* const upd_rec = a.upd_rec;
+    const uint32_t* const upd_rel = a.upd_rel;
+    const uint32_t* const stage_rec = a.stage_rec;
+    uint32_t* const fail_flag = &a.ctrl->fail;
+    const uint4 hdr = __ldg(reinterpret_cast<const uint4*>(stage_rec) + 2 * (size_t)pos);        // j0, w, h, rows
+    const uint4 hdr2 = __ldg(reinterpret_cast<const uint4*>(stage_rec) + 2 * (size_t)pos + 1);   // panel, first update, updates
     const uint32_t j0 = hdr.x, w = hdr.y, h = hdr.z;
+    double* const rinv_out = a.vg + a.RV0 + j0;
     double* G = lv + hdr2.x;
     const bool staged = TEAM > 1 && h * w <= Caps::panel;
     double* P = staged ? stage : G;
@@ -523,13 +536,13 @@ __device__ __noinline__ void sn_factor(const LargeArgs& a, uint32_t pos, uint32_
             for (uint32_t t = lane; t < h * w; t += TEAM) P[t] = G[t];
         for (uint32_t c = lane; c < w; c += TEAM) ys[c] = y[j0 + c];
         if (TEAM == 32 && next_pos != UINT32_MAX) {
-            const uint4 nh = __ldg(reinterpret_cast<const uint4*>(a.stage_rec) + 2 * (size_t)next_pos);
-            const uint4 nh2 = __ldg(reinterpret_cast<const uint4*>(a.stage_rec) + 2 * (size_t)next_pos + 1);
+            const uint4 nh = __ldg(reinterpret_cast<const uint4*>(stage_rec) + 2 * (size_t)next_pos);
+            const uint4 nh2 = __ldg(reinterpret_cast<const uint4*>(stage_rec) + 2 * (size_t)next_pos + 1);
             const uint32_t lines = (nh.y * nh.z * 8u + 127u) / 128u;
             for (uint32_t q = lane; q < lines; q += 32) prefetch_l2(lv + nh2.x + 16u * q);
             if (lane == 31) prefetch_l2(y + nh.x);
-            if (lane == 30 && nh2.z) prefetch_l2(a.upd_rec + 8 * (size_t)nh2.y);
-            if (lane == 29 && next2_pos != UINT32_MAX) prefetch_l2(a.stage_rec + 8 * (size_t)next2_pos);
+            if (lane == 30 && nh2.z) prefetch_l2(upd_rec + 8 * (size_t)nh2.y);
+            if (lane == 29 && next2_pos != UINT32_MAX) prefetch_l2(stage_rec + 8 * (size_t)next2_pos);
         }
         team_sync<TEAM>();
     }
@@ -545,7 +558,7 @@ __device__ __noinline__ void sn_factor(const LargeArgs& a, uint32_t pos, uint32_
                 team_sync<TEAM>();  // everybody is done with the previous window
                 win = u0;
                 win_n = min(Caps::recs, ue - u0);
-                for (uint32_t q = lane; q < win_n * 8; q += TEAM) srec_base[q] = __ldg(a.upd_rec + 8 * (size_t)win + q);
+                for (uint32_t q = lane; q < win_n * 8; q += TEAM) srec_base[q] = __ldg(upd_rec + 8 * (size_t)win + q);
                 team_sync<TEAM>();
             }
             uint32_t* srec = srec_base + 8 * (u0 - win);
@@ -603,7 +616,7 @@ __device__ __noinline__ void sn_factor(const LargeArgs& a, uint32_t pos, uint32_
                 if (tot_b + len + wK > Caps::block || tot_r + T > Caps::rel || (cnt + 1) * h > Caps::inv || T >= 0xffffu) break;
                 for (uint32_t q = lane; q < len; q += TEAM) cp_async8(kb + tot_b + q, lv + r[0] + q);
                 for (uint32_t q = lane; q < wK; q += TEAM) cp_async8(kb + tot_b + len + q, y + r[4] + q);  // y of K's columns
-                for (uint32_t q = lane; q < T; q += TEAM) cp_async4(srel + tot_r + q, a.upd_rel + r[3] + q);
+                for (uint32_t q = lane; q < T; q += TEAM) cp_async4(srel + tot_r + q, upd_rel + r[3] + q);
                 if (lane == 0) r[5] = wK;
                 tot_b += len + wK;
                 tot_r += T;
@@ -625,7 +638,7 @@ __device__ __noinline__ void sn_factor(const LargeArgs& a, uint32_t pos, uint32_
                 // simply continues from slice to slice (k stays ascending).
                 const uint32_t ws_max = Caps::block / (T + 1);
                 for (uint32_t q = lane; q < h; q += TEAM) inv[q] = 0xffffu;
-                for (uint32_t q = lane; q < T; q += TEAM) cp_async4(srel + q, a.upd_rel + srec[3] + q);
+                for (uint32_t q = lane; q < T; q += TEAM) cp_async4(srel + q, upd_rel + srec[3] + q);
                 for (uint32_t ks = 0; ks < wK; ks += ws_max) {
                     const uint32_t ws = min(ws_max, wK - ks);
                     for (uint32_t q = lane; q < T * ws; q += TEAM) {
@@ -641,19 +654,22 @@ __device__ __noinline__ void sn_factor(const LargeArgs& a, uint32_t pos, uint32_
                 }
             } else {
                 // pair by pair, straight from global memory
-                sn_apply_update<TEAM>(P, w, ys, y + srec[4], lv + srec[0], a.upd_rel + srec[3], T, wK, nc, lane);
+                sn_apply_update<TEAM>(P, w, ys, y + srec[4], lv + srec[0], upd_rel + srec[3], T, wK, nc, lane);
                 team_sync<TEAM>();
             }
             u0 += 1;
         }
     } else {
         for (uint32_t u = ub; u < ue; ++u) {
-            const uint32_t* r = a.upd_rec + 8 * (size_t)u;
+            const uint32_t* r = upd_rec + 8 * (size_t)u;
             const uint32_t T = __ldg(r + 1), z = __ldg(r + 2);
-            sn_apply_update<1>(P, w, ys, y + __ldg(r + 4), lv + __ldg(r), a.upd_rel + __ldg(r + 3), T, z & 0xffu, z >> 8, 0);
+            sn_apply_update<1>(P, w, ys, y + __ldg(r + 4), lv + __ldg(r), upd_rel + __ldg(r + 3), T, z & 0xffu, z >> 8, 0);
         }
     }
     // ---- 2. the panel's own columns
+    // (A variant that keeps row r of the panel in lane r's registers and moves L[c][k] by shuffle was measured slower:
+    // 9.0 ms against 8.7 ms of factor stages on the 1M-variable sketch — a warp waits on the panel's memory round trips,
+    // not on the column arithmetic; profiles/r01k_lm_kernel.md.)
     for (uint32_t c = 0; c < w; ++c) {
         for (uint32_t r = c + lane; r < h; r += TEAM) {
             double acc = P[r * w + c], piv = P[c * w + c];
@@ -664,8 +680,8 @@ __device__ __noinline__ void sn_factor(const LargeArgs& a, uint32_t pos, uint32_
             }
             const double rinv = __ddiv_rn(1.0, __dsqrt_rn(piv));
             if (r == c) {
-                if (!(piv > 0.0) || !ezm::ez_isfinite(piv)) a.ctrl->fail = 1;
-                a.vg[a.RV0 + j0 + c] = rinv;
+                if (!(piv > 0.0) || !ezm::ez_isfinite(piv)) *fail_flag = 1;
+                rinv_out[c] = rinv;
                 double ay = ys[c];
                 for (uint32_t k = 0; k < c; ++k) ay = __fma_rn(-P[c * w + k], ys[k], ay);
                 ys[c] = __dmul_rn(ay, rinv);
@@ -691,18 +707,22 @@ __device__ __noinline__ void sn_factor(const LargeArgs& a, uint32_t pos, uint32_
 template <int TEAM>
 __device__ __noinline__ void sn_backward(const LargeArgs& a, uint32_t pos, uint32_t lane, double* stage) {
     using Caps = TeamCaps<TEAM>;
-    const double* lv = a.vg + a.L0;
-    double* y = a.vg + a.Y0;
+    const double* const lv = a.vg + a.L0;  // (argument fields are read once: see sn_factor)
+    double* const y = a.vg + a.Y0;
     const uint4 hdr = __ldg(reinterpret_cast<const uint4*>(a.stage_rec) + 2 * (size_t)pos);
     const uint32_t j0 = hdr.x, w = hdr.y, h = hdr.z, rb = hdr.w;
     const double* G = lv + __ldg(a.stage_rec + 8 * (size_t)pos + 4);
+    const uint32_t* const rows = a.sn_rows + rb;
+    const double* const rinv_in = a.vg + a.RV0 + j0;
+    double* const d_out = a.vg + a.D0;
+    const uint32_t* const perm = a.perm + j0;
     if (TEAM == 1) {  // a panel of a few doubles: one thread, straight from global memory
         for (uint32_t c = w; c-- > 0;) {
             double acc = y[j0 + c];
-            for (uint32_t r = h; r-- > c + 1;) acc = __fma_rn(-G[r * w + c], y[__ldg(a.sn_rows + rb + r)], acc);
-            const double v = __dmul_rn(acc, a.vg[a.RV0 + j0 + c]);
+            for (uint32_t r = h; r-- > c + 1;) acc = __fma_rn(-G[r * w + c], y[__ldg(rows + r)], acc);
+            const double v = __dmul_rn(acc, rinv_in[c]);
             y[j0 + c] = v;
-            a.vg[a.D0 + __ldg(a.perm + j0 + c)] = v;
+            d_out[__ldg(perm + c)] = v;
         }
         return;
     }
@@ -713,7 +733,7 @@ __device__ __noinline__ void sn_backward(const LargeArgs& a, uint32_t pos, uint3
         double* Ps = stage;
         dv = stage + Caps::panel;
         for (uint32_t t = lane; t < h * w; t += TEAM) Ps[t] = G[t];
-        for (uint32_t t = lane; t < h; t += TEAM) dv[t] = y[__ldg(a.sn_rows + rb + t)];
+        for (uint32_t t = lane; t < h; t += TEAM) dv[t] = y[__ldg(rows + t)];
         P = Ps;
         team_sync<TEAM>();
     }
@@ -722,8 +742,8 @@ __device__ __noinline__ void sn_backward(const LargeArgs& a, uint32_t pos, uint3
         double acc = 0.0, rinv = 0.0;
         if (c < w) {
             acc = staged ? dv[c] : y[j0 + c];
-            rinv = a.vg[a.RV0 + j0 + c];
-            for (uint32_t r = h; r-- > w;) acc = __fma_rn(-P[r * w + c], staged ? dv[r] : y[__ldg(a.sn_rows + rb + r)], acc);
+            rinv = rinv_in[c];
+            for (uint32_t r = h; r-- > w;) acc = __fma_rn(-P[r * w + c], staged ? dv[r] : y[__ldg(rows + r)], acc);
         }
         double v = 0.0;
         for (uint32_t t = w; t-- > 0;) {
@@ -733,7 +753,7 @@ __device__ __noinline__ void sn_backward(const LargeArgs& a, uint32_t pos, uint3
         }
         if (c < w) {
             y[j0 + c] = v;
-            a.vg[a.D0 + __ldg(a.perm + j0 + c)] = v;
+            d_out[__ldg(perm + c)] = v;
         }
     }
     team_sync<TEAM>();
