@@ -125,6 +125,8 @@ struct RegX {
 // contiguous block — the stand-alone assembly kernel pulls it into shared memory with ONE bulk async copy
 // (cp.async.bulk + mbarrier, three to eight tiles in flight per warp) — and the rows, Jacobian slots and variables a group
 // of neighbouring tiles touches stay within a few hundred KB, so partial-sector writes merge in L2.
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 __device__ __forceinline__ double rec_double(const uint32_t* rec, uint32_t word) {
     return __hiloint2double((int)rec[(word + 1) * 32], (int)rec[word * 32]);
 }
@@ -169,6 +171,11 @@ __device__ __forceinline__ void assemble_slot(const LargeArgs& a, const KindLayo
     const double p1 = ly.p1 != 0xff ? rec_double(rec, ly.p1) : 0.0;
     const double w = ly.weight != 0xff ? rec_double(rec, ly.weight) : 1.0;
     const uint32_t row0 = rec[0];
+    // (argument fields are read once: inside the LM kernel the block lives in local memory and every store below would
+    // otherwise be followed by reloads of a.vg / a.J0 / a.jr)
+    double* const rout = a.vg + rdst + row0;
+    double* const jbase = a.vg + a.J0;
+    double* const jrbase = a.jr;
     const uint32_t ident[8] = {0, 1, 2, 3, 4, 5, 6, 7};
     const RegX XR{xv};
     ezd::EvalOut o;
@@ -176,8 +183,8 @@ __device__ __forceinline__ void assemble_slot(const LargeArgs& a, const KindLayo
     const uint32_t rows = cl_rows[kind];
     uint32_t ndeg = 0;
     if (RES) {
-        a.vg[rdst + row0] = w * o.res[0];
-        if (rows == 2) a.vg[rdst + row0 + 1] = w * o.res[1];
+        rout[0] = w * o.res[0];
+        if (rows == 2) rout[1] = w * o.res[1];
         if (o.res_degen) ++ndeg;
     }
     if (JAC) {
@@ -194,12 +201,12 @@ __device__ __forceinline__ void assemble_slot(const LargeArgs& a, const KindLayo
                 for (int q = 0; q < 8; ++q) {
                     if (q < (int)len) {
                         const uint32_t s = rec[(sb + q) * 32];
-                        double* dst = a.vg + a.J0 + (s & ~kAccumulate);
+                        double* dst = jbase + (s & ~kAccumulate);
                         double v;
                         if (s & kAccumulate) v = o.emit[row] ? *dst + w * o.pd[row][q] : *dst;
                         else v = o.emit[row] ? 0.0 + w * o.pd[row][q] : 0.0;
                         *dst = v;
-                        if (jr_on) a.jr[jr0 + ((jrc >> (4 * q)) & 15u)] = v;
+                        if (jr_on) jrbase[jr0 + ((jrc >> (4 * q)) & 15u)] = v;
                     }
                 }
             }
@@ -215,16 +222,30 @@ __device__ __forceinline__ void assemble_slot(const LargeArgs& a, const KindLayo
 template <bool RES, bool JAC>
 __device__ __forceinline__ void assemble_phase_inl(const LargeArgs& a, uint32_t rdst, uint32_t tid, uint32_t nth, bool write_jr) {
     const uint32_t lane = threadIdx.x & 31u, nw = nth >> 5;
-    for (uint32_t t = tid >> 5; t < a.n_tiles; t += nw) {
-        const TileDesc td = a.tiles[t];
+    // (argument fields read once, see assemble_slot)  The next tile's descriptor is fetched one iteration ahead and its
+    // record lines are pulled into L2 while the current tile is evaluated.
+    const TileDesc* const tiles = a.tiles;
+    const uint32_t* const recs = a.recs;
+    const uint8_t* const sides = a.side;
+    const uint32_t n_tiles = a.n_tiles;
+    uint32_t t = tid >> 5;
+    TileDesc td = t < n_tiles ? tiles[t] : TileDesc{0, 0};
+    for (; t < n_tiles; t += nw) {
+        const TileDesc tn = t + nw < n_tiles ? tiles[t + nw] : TileDesc{0, 0};
         const uint32_t kind = td.meta & 0xffu, n_valid = td.meta >> 8;
+        const KindLayout ly = a.layout[kind];
         if (lane < n_valid) {
-            const uint32_t* rec = a.recs + (size_t)td.off16 * 4 + lane;
+            const uint32_t* rec = recs + (size_t)td.off16 * 4 + lane;
             double xv[8];
-            gather_x(a, a.layout[kind], kind, rec, xv);
-            const uint32_t side = (kind == EZPZ_K_LINE_TANGENT_TO_CIRCLE || kind == EZPZ_K_CIRCLE_TANGENT_TO_CIRCLE) ? a.side[t * 32 + lane] : 0u;
-            assemble_slot<RES, JAC>(a, a.layout[kind], kind, rec, t * 32 + lane, rdst, write_jr, xv, side);
+            gather_x(a, ly, kind, rec, xv);
+            const uint32_t side = (kind == EZPZ_K_LINE_TANGENT_TO_CIRCLE || kind == EZPZ_K_CIRCLE_TANGENT_TO_CIRCLE) ? sides[t * 32 + lane] : 0u;
+            if (t + nw < n_tiles) {
+                const uint32_t lines = a.layout[tn.meta & 0xffu].n_words;  // one 128-byte line per record word
+                for (uint32_t q = lane; q < lines; q += 32) prefetch_l2(recs + (size_t)tn.off16 * 4 + 32 * q);
+            }
+            assemble_slot<RES, JAC>(a, ly, kind, rec, t * 32 + lane, rdst, write_jr, xv, side);
         }
+        td = tn;
     }
 }
 // Out-of-line copy for the persistent kernel (keeps its register allocation apart from the solver phases).
@@ -503,8 +524,6 @@ __device__ __forceinline__ void sn_apply_update(double* P, uint32_t w, double* y
 //      for every pair of K's rows (i >= j) with j a column of J;  y[j] = fma(-L[j][k], y[k], y[j]);
 //   2. the panel's own columns c ascending: the same fma chains over the columns k < c of the panel, pivot
 //      (fails unless > 0 and finite), 1/pivot, scaling, and y[c].
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-
 // next_pos / next2_pos: the panels this team factorises after this one (UINT32_MAX = none): their records, panel and first
 // update records are pulled into L2 while this panel's own loads are in flight.
 template <int TEAM>
