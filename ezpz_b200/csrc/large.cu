@@ -478,7 +478,11 @@ constexpr uint32_t team_stage_doubles() {  // recs = update records fetched per 
     return TeamCaps<TEAM>::panel + TeamCaps<TEAM>::block + kYCap + TeamCaps<TEAM>::recs * 8 / 2 + TeamCaps<TEAM>::rel / 2 +
            TeamCaps<TEAM>::inv / 4;
 }
-constexpr uint32_t kWarpStageDoubles = team_stage_doubles<32>();  // 1,440 doubles = 11,520 bytes per warp
+// A warp team's stage ends with a 16-double CARRY: the records of the panel the warp factorises next (tag = its position in
+// stage order), whose values and y are by then on their way into the block area (sn_factor<32>).
+constexpr uint32_t kCarryDoubles = 16;
+constexpr uint32_t kCarryOffset = team_stage_doubles<32>();  // in doubles from the start of the warp's stage
+constexpr uint32_t kWarpStageDoubles = kCarryOffset + kCarryDoubles;  // 1,440 doubles = 11,520 bytes per warp
 template <int TEAM>
 __device__ __forceinline__ void team_sync() {
     if (TEAM == 32) __syncwarp();
@@ -538,8 +542,13 @@ __device__ __noinline__ void sn_factor(const LargeArgs& a, uint32_t pos, uint32_
     const uint32_t* const upd_rel = a.upd_rel;
     const uint32_t* const stage_rec = a.stage_rec;
     uint32_t* const fail_flag = &a.ctrl->fail;
-    const uint4 hdr = __ldg(reinterpret_cast<const uint4*>(stage_rec) + 2 * (size_t)pos);        // j0, w, h, rows
-    const uint4 hdr2 = __ldg(reinterpret_cast<const uint4*>(stage_rec) + 2 * (size_t)pos + 1);   // panel, first update, updates
+    // Warp teams: has the previous call of this warp already started the copy of this panel (see the end of part 1)?
+    uint32_t* const carry = TEAM == 32 ? reinterpret_cast<uint32_t*>(stage + kCarryOffset) : nullptr;
+    const bool carried = TEAM == 32 && carry[0] == pos;
+    const uint4 hdr = carried ? *reinterpret_cast<const uint4*>(carry + 4)
+                              : __ldg(reinterpret_cast<const uint4*>(stage_rec) + 2 * (size_t)pos);  // j0, w, h, rows
+    const uint4 hdr2 = carried ? *reinterpret_cast<const uint4*>(carry + 8)
+                               : __ldg(reinterpret_cast<const uint4*>(stage_rec) + 2 * (size_t)pos + 1);  // panel, first update, updates
     const uint32_t j0 = hdr.x, w = hdr.y, h = hdr.z;
     double* const rinv_out = a.vg + a.RV0 + j0;
     double* G = lv + hdr2.x;
@@ -551,17 +560,15 @@ __device__ __noinline__ void sn_factor(const LargeArgs& a, uint32_t pos, uint32_
     uint32_t* srel = TEAM > 1 ? srec_base + Caps::recs * 8 : nullptr;
     uint16_t* inv = TEAM > 1 ? reinterpret_cast<uint16_t*>(srel + Caps::rel) : nullptr;
     if (TEAM > 1) {
-        if (staged)
-            for (uint32_t t = lane; t < h * w; t += TEAM) P[t] = G[t];
-        for (uint32_t c = lane; c < w; c += TEAM) ys[c] = y[j0 + c];
-        if (TEAM == 32 && next_pos != UINT32_MAX) {
-            const uint4 nh = __ldg(reinterpret_cast<const uint4*>(stage_rec) + 2 * (size_t)next_pos);
-            const uint4 nh2 = __ldg(reinterpret_cast<const uint4*>(stage_rec) + 2 * (size_t)next_pos + 1);
-            const uint32_t lines = (nh.y * nh.z * 8u + 127u) / 128u;
-            for (uint32_t q = lane; q < lines; q += 32) prefetch_l2(lv + nh2.x + 16u * q);
-            if (lane == 31) prefetch_l2(y + nh.x);
-            if (lane == 30 && nh2.z) prefetch_l2(upd_rec + 8 * (size_t)nh2.y);
-            if (lane == 29 && next2_pos != UINT32_MAX) prefetch_l2(stage_rec + 8 * (size_t)next2_pos);
+        if (carried) {  // values and y arrived in the block area: panel first, then y of its columns
+            cp_async_wait_all();
+            team_sync<TEAM>();
+            for (uint32_t t = lane; t < h * w; t += TEAM) P[t] = kb[t];
+            for (uint32_t c = lane; c < w; c += TEAM) ys[c] = kb[h * w + c];
+        } else {
+            if (staged)
+                for (uint32_t t = lane; t < h * w; t += TEAM) P[t] = G[t];
+            for (uint32_t c = lane; c < w; c += TEAM) ys[c] = y[j0 + c];
         }
         team_sync<TEAM>();
     }
@@ -685,6 +692,32 @@ __device__ __noinline__ void sn_factor(const LargeArgs& a, uint32_t pos, uint32_
             sn_apply_update<1>(P, w, ys, y + __ldg(r + 4), lv + __ldg(r), upd_rel + __ldg(r + 3), T, z & 0xffu, z >> 8, 0);
         }
     }
+    // ---- the next panel of this warp: records now, values and y into the (now idle) block area while part 2 runs
+    if (TEAM == 32) {
+        team_sync<TEAM>();  // every lane is done with the block area and with the carry of this panel
+        bool carry_next = false;
+        if (next_pos != UINT32_MAX) {
+            const uint4 nh = __ldg(reinterpret_cast<const uint4*>(stage_rec) + 2 * (size_t)next_pos);
+            const uint4 nh2 = __ldg(reinterpret_cast<const uint4*>(stage_rec) + 2 * (size_t)next_pos + 1);
+            const uint32_t nhw = nh.y * nh.z;
+            if (nhw + nh.y <= Caps::block && nhw <= Caps::panel) {
+                for (uint32_t q = lane; q < nhw; q += TEAM) cp_async8(kb + q, lv + nh2.x + q);
+                for (uint32_t q = lane; q < nh.y; q += TEAM) cp_async8(kb + nhw + q, y + nh.x + q);
+                if (lane == 0) {
+                    carry[0] = next_pos;
+                    *reinterpret_cast<uint4*>(carry + 4) = nh;
+                    *reinterpret_cast<uint4*>(carry + 8) = nh2;
+                }
+                carry_next = true;
+            } else {
+                const uint32_t lines = (nhw * 8u + 127u) / 128u;
+                for (uint32_t q = lane; q < lines; q += 32) prefetch_l2(lv + nh2.x + 16u * q);
+            }
+            if (lane == 30 && nh2.z) prefetch_l2(upd_rec + 8 * (size_t)nh2.y);
+            if (lane == 29 && next2_pos != UINT32_MAX) prefetch_l2(stage_rec + 8 * (size_t)next2_pos);
+        }
+        if (!carry_next && lane == 0) carry[0] = UINT32_MAX;
+    }
     // ---- 2. the panel's own columns
     // (A variant that keeps row r of the panel in lane r's registers and moves L[c][k] by shuffle was measured slower:
     // 9.0 ms against 8.7 ms of factor stages on the 1M-variable sketch — a warp waits on the panel's memory round trips,
@@ -788,6 +821,8 @@ __device__ void direct_factor_stage(const LargeArgs& a, uint32_t st, uint32_t ti
                    b3 = __ldg(a.stage_ptr + 3 * st + 3);
     for (uint32_t k = b0 + tid; k < b1; k += nth) sn_factor<1>(a, k, 0, nullptr);
     if (b2 - b1 > a.vgrid) {
+        if ((threadIdx.x & 31u) == 0) reinterpret_cast<uint32_t*>(warp_stage + kCarryOffset)[0] = UINT32_MAX;  // no carry
+        __syncwarp();
         for (uint32_t k = b1 + (tid >> 5), nw = nth >> 5; k < b2; k += nw)
             sn_factor<32>(a, k, threadIdx.x & 31u, warp_stage, k + nw < b2 ? k + nw : UINT32_MAX, k + 2 * nw < b2 ? k + 2 * nw : UINT32_MAX);
         __syncthreads();  // the CTA panels below reuse the warps' shared memory
