@@ -448,6 +448,24 @@ void build_sparse_direct(ezpz_structure& S) {
         std::vector<uint32_t> cur(P.stage_ptr.begin(), P.stage_ptr.end() - 1);
         for (uint32_t s = 0; s < n_sn; ++s) P.stage_sn[cur[bucket(s)]++] = s;
     }
+    // Inside a stage the warp (and CTA) panels are dealt round-robin to the teams: sorted by estimated cost, descending,
+    // every team receives one panel of each cost tier and the teams reach the stage's barrier together (ncu: half of the
+    // warp time of lm_large_kernel was spent waiting at barriers with the panels in elimination order).
+    if (const char* env = std::getenv("EZPZ_B200_STAGE_SORT"); !env || env[0] != '0') {
+        std::vector<uint32_t> cost(n_sn, 0);
+        for (uint32_t s = 0; s < n_sn; ++s) {
+            uint64_t c = 20 + 10ull * panel_w(s) + (uint64_t)panel_h(s) * panel_w(s) / 16;
+            for (uint32_t u = P.upd_ptr[s]; u < P.upd_ptr[s + 1]; ++u) {
+                const uint32_t K = P.upd_sn[u];
+                c += 35 + (uint64_t)(panel_h(K) - P.upd_rbegin[u]) * panel_w(K) / 16;
+            }
+            cost[s] = (uint32_t)std::min<uint64_t>(c, UINT32_MAX);
+        }
+        for (uint32_t st = 0; st < n_stages; ++st)
+            for (uint32_t cls = 1; cls <= 2; ++cls)
+                std::stable_sort(P.stage_sn.begin() + P.stage_ptr[3 * st + cls], P.stage_sn.begin() + P.stage_ptr[3 * st + cls + 1],
+                                 [&](uint32_t x, uint32_t y) { return cost[x] > cost[y]; });
+    }
     // one 32-byte record per supernode IN STAGE ORDER (what a team reads first, one memory round trip):
     // {first column, width, height, offset of its row list, panel offset, first update, number of updates, 0}
     P.stage_rec.assign((size_t)n_sn * 8, 0u);
