@@ -469,6 +469,10 @@ struct TeamCaps<32> {
     static constexpr uint32_t panel = 576, block = 448, rel = 256, inv = 512, recs = 32;
 };
 template <>
+struct TeamCaps<128> {  // four warps: the stages of four warp teams
+    static constexpr uint32_t panel = 1024, block = 3328, rel = 1024, inv = 2048, recs = 32;
+};
+template <>
 struct TeamCaps<512> {
     static constexpr uint32_t panel = 15360, block = 4096, rel = 2048, inv = 8192, recs = 32;
 };
@@ -486,6 +490,7 @@ constexpr uint32_t kWarpStageDoubles = kCarryOffset + kCarryDoubles;  // 1,440 d
 template <int TEAM>
 __device__ __forceinline__ void team_sync() {
     if (TEAM == 32) __syncwarp();
+    else if (TEAM == 128) asm volatile("bar.sync %0, 128;" ::"r"(1u + (threadIdx.x >> 7)) : "memory");  // named barrier of this quad
     else if (TEAM > 32) __syncthreads();
 }
 
@@ -554,7 +559,12 @@ __device__ __noinline__ void sn_factor(const LargeArgs& a, uint32_t pos, uint32_
     double* G = lv + hdr2.x;
     const bool staged = TEAM > 1 && h * w <= Caps::panel;
     double* P = staged ? stage : G;
-    double* kb = TEAM > 1 ? stage + Caps::panel : nullptr;
+    // The update blocks get whatever the panel leaves of the panel + block areas (a panel of 100 doubles in a warp's stage
+    // leaves 920 of the 1,024, twice the fixed split: more updates per memory round trip).
+    // (CTA teams keep the fixed split: their panels are large and 2D-lattice sketches measured slower with larger chunks.)
+    const uint32_t pan = TEAM >= 512 ? Caps::panel : (staged ? ((h * w + 1u) & ~1u) : 0u);
+    const uint32_t block_cap = TEAM > 1 ? Caps::panel + Caps::block - pan : 0u;
+    double* kb = TEAM > 1 ? stage + pan : nullptr;
     double* ys = TEAM > 1 ? stage + Caps::panel + Caps::block : y + j0;  // w <= 16 values
     uint32_t* srec_base = TEAM > 1 ? reinterpret_cast<uint32_t*>(stage + Caps::panel + Caps::block + kYCap) : nullptr;
     uint32_t* srel = TEAM > 1 ? srec_base + Caps::recs * 8 : nullptr;
@@ -563,8 +573,9 @@ __device__ __noinline__ void sn_factor(const LargeArgs& a, uint32_t pos, uint32_
         if (carried) {  // values and y arrived in the block area: panel first, then y of its columns
             cp_async_wait_all();
             team_sync<TEAM>();
-            for (uint32_t t = lane; t < h * w; t += TEAM) P[t] = kb[t];
-            for (uint32_t c = lane; c < w; c += TEAM) ys[c] = kb[h * w + c];
+            const double* cd = stage + (Caps::panel + Caps::block) - (h * w + w);  // where the previous call put them
+            for (uint32_t t = lane; t < h * w; t += TEAM) P[t] = cd[t];
+            for (uint32_t c = lane; c < w; c += TEAM) ys[c] = cd[h * w + c];
         } else {
             if (staged)
                 for (uint32_t t = lane; t < h * w; t += TEAM) P[t] = G[t];
@@ -639,7 +650,7 @@ __device__ __noinline__ void sn_factor(const LargeArgs& a, uint32_t pos, uint32_
             while (cnt < avail) {
                 uint32_t* r = srec + 8 * cnt;
                 const uint32_t T = r[1], wK = r[2] & 0xffu, len = T * wK;
-                if (tot_b + len + wK > Caps::block || tot_r + T > Caps::rel || (cnt + 1) * h > Caps::inv || T >= 0xffffu) break;
+                if (tot_b + len + wK > block_cap || tot_r + T > Caps::rel || (cnt + 1) * h > Caps::inv || T >= 0xffffu) break;
                 for (uint32_t q = lane; q < len; q += TEAM) cp_async8(kb + tot_b + q, lv + r[0] + q);
                 for (uint32_t q = lane; q < wK; q += TEAM) cp_async8(kb + tot_b + len + q, y + r[4] + q);  // y of K's columns
                 for (uint32_t q = lane; q < T; q += TEAM) cp_async4(srel + tot_r + q, upd_rel + r[3] + q);
@@ -659,10 +670,10 @@ __device__ __noinline__ void sn_factor(const LargeArgs& a, uint32_t pos, uint32_
             }
             // One update whose block is larger than the stage.
             const uint32_t T = srec[1], wK = srec[2] & 0xffu, nc = srec[2] >> 8;
-            if (T + 1 <= Caps::block && T <= Caps::rel && h <= Caps::inv && T < 0xffffu) {
+            if (T + 1 <= block_cap && T <= Caps::rel && h <= Caps::inv && T < 0xffffu) {
                 // Column slices of the descendant's panel, as many columns at a time as fit: every entry's fma chain
                 // simply continues from slice to slice (k stays ascending).
-                const uint32_t ws_max = Caps::block / (T + 1);
+                const uint32_t ws_max = block_cap / (T + 1);
                 for (uint32_t q = lane; q < h; q += TEAM) inv[q] = 0xffffu;
                 for (uint32_t q = lane; q < T; q += TEAM) cp_async4(srel + q, upd_rel + srec[3] + q);
                 for (uint32_t ks = 0; ks < wK; ks += ws_max) {
@@ -700,9 +711,12 @@ __device__ __noinline__ void sn_factor(const LargeArgs& a, uint32_t pos, uint32_
             const uint4 nh = __ldg(reinterpret_cast<const uint4*>(stage_rec) + 2 * (size_t)next_pos);
             const uint4 nh2 = __ldg(reinterpret_cast<const uint4*>(stage_rec) + 2 * (size_t)next_pos + 1);
             const uint32_t nhw = nh.y * nh.z;
-            if (nhw + nh.y <= Caps::block && nhw <= Caps::panel) {
-                for (uint32_t q = lane; q < nhw; q += TEAM) cp_async8(kb + q, lv + nh2.x + q);
-                for (uint32_t q = lane; q < nh.y; q += TEAM) cp_async8(kb + nhw + q, y + nh.x + q);
+            // destination: the END of the panel + block areas — clear of this panel (pan <= 576) and of the place the next
+            // call stages its panel (nhw doubles from the start)
+            if (2 * nhw + nh.y <= Caps::panel + Caps::block && pan + nhw + nh.y <= Caps::panel + Caps::block) {
+                double* cd = stage + (Caps::panel + Caps::block) - (nhw + nh.y);
+                for (uint32_t q = lane; q < nhw; q += TEAM) cp_async8(cd + q, lv + nh2.x + q);
+                for (uint32_t q = lane; q < nh.y; q += TEAM) cp_async8(cd + nhw + q, y + nh.x + q);
                 if (lane == 0) {
                     carry[0] = next_pos;
                     *reinterpret_cast<uint4*>(carry + 4) = nh;
@@ -820,10 +834,20 @@ __device__ void direct_factor_stage(const LargeArgs& a, uint32_t st, uint32_t ti
     const uint32_t b0 = __ldg(a.stage_ptr + 3 * st), b1 = __ldg(a.stage_ptr + 3 * st + 1), b2 = __ldg(a.stage_ptr + 3 * st + 2),
                    b3 = __ldg(a.stage_ptr + 3 * st + 3);
     for (uint32_t k = b0 + tid; k < b1; k += nth) sn_factor<1>(a, k, 0, nullptr);
-    if (b2 - b1 > a.vgrid) {
+    if (b2 - b1 > a.vgrid && b2 - b1 <= 8 * a.vgrid) {
+        // Between one and eight panels per CTA (the middle of the tree: every panel receives 10-20 updates): QUADS of four
+        // warps — a quad stages ~15 updates per round trip where a warp's stage holds two or three, and there are still
+        // enough quads for every panel of the stage.
+        for (uint32_t k = b1 + (threadIdx.x >> 7) * a.vgrid + a.vblock; k < b2; k += 4 * a.vgrid)
+            sn_factor<128>(a, k, threadIdx.x & 127u, cta_stage + (threadIdx.x >> 7) * 4 * kWarpStageDoubles);
+        __syncthreads();
+        for (uint32_t k = b2 + a.vblock; k < b3; k += a.vgrid) sn_factor<512>(a, k, threadIdx.x, cta_stage);
+    } else if (b2 - b1 > a.vgrid) {
         if ((threadIdx.x & 31u) == 0) reinterpret_cast<uint32_t*>(warp_stage + kCarryOffset)[0] = UINT32_MAX;  // no carry
         __syncwarp();
-        for (uint32_t k = b1 + (tid >> 5), nw = nth >> 5; k < b2; k += nw)
+        // Panels are dealt warp-major ACROSS the CTAs (panel k of the stage's cost-sorted list to CTA k mod G): the most
+        // expensive panels land on different SMs, and a stage with fewer panels than warps still uses every SM.
+        for (uint32_t k = b1 + (threadIdx.x >> 5) * a.vgrid + a.vblock, nw = nth >> 5; k < b2; k += nw)
             sn_factor<32>(a, k, threadIdx.x & 31u, warp_stage, k + nw < b2 ? k + nw : UINT32_MAX, k + 2 * nw < b2 ? k + 2 * nw : UINT32_MAX);
         __syncthreads();  // the CTA panels below reuse the warps' shared memory
         for (uint32_t k = b2 + a.vblock; k < b3; k += a.vgrid) sn_factor<512>(a, k, threadIdx.x, cta_stage);
@@ -835,7 +859,7 @@ __device__ void direct_backward_stage(const LargeArgs& a, uint32_t st, uint32_t 
     const uint32_t b0 = __ldg(a.stage_ptr + 3 * st), b1 = __ldg(a.stage_ptr + 3 * st + 1), b2 = __ldg(a.stage_ptr + 3 * st + 2),
                    b3 = __ldg(a.stage_ptr + 3 * st + 3);
     for (uint32_t k = b0 + tid; k < b1; k += nth) sn_backward<1>(a, k, 0, nullptr);
-    for (uint32_t k = b1 + (tid >> 5); k < b2; k += nth >> 5) sn_backward<32>(a, k, threadIdx.x & 31u, warp_stage);
+    for (uint32_t k = b1 + (threadIdx.x >> 5) * a.vgrid + a.vblock; k < b2; k += nth >> 5) sn_backward<32>(a, k, threadIdx.x & 31u, warp_stage);
     if (b3 > b2) {
         __syncthreads();
         for (uint32_t k = b2 + a.vblock; k < b3; k += a.vgrid) sn_backward<512>(a, k, threadIdx.x, cta_stage);
@@ -843,6 +867,7 @@ __device__ void direct_backward_stage(const LargeArgs& a, uint32_t st, uint32_t 
 }
 
 static_assert(team_stage_doubles<512>() <= (512 / 32) * kWarpStageDoubles, "the CTA team's stage must fit the CTA's dynamic shared memory");
+static_assert(team_stage_doubles<128>() <= 4 * kWarpStageDoubles, "a quad's stage must fit the stages of its four warps");
 constexpr uint32_t kBlock = 512;
 constexpr uint32_t kClusterCtas = 8;        // portable maximum cluster size
 constexpr size_t kSingleCtaWork = 4096;     // n + m + nnz up to which one CTA runs the whole solve

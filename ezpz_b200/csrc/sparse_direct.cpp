@@ -572,15 +572,23 @@ void build_sparse_direct(ezpz_structure& S) {
         std::fprintf(stderr, "[sparse_direct] n %u nested %d supernodes %u stages %u panel doubles %u true nnz(L) %zu updates %zu\n", n,
                      (int)P.nested, n_sn, n_stages, nnz_l, nnz_l_true, P.upd_sn.size());
         for (uint32_t st = 0; st < n_stages; ++st) {
-            uint32_t max_h = 0, max_u = 0;
+            uint32_t max_h = 0, max_u = 0, u4 = 0, u8 = 0, u16 = 0;
+            uint64_t sum_u = 0;
             for (uint32_t k = P.stage_ptr[3 * st]; k < P.stage_ptr[3 * st + 3]; ++k) {
-                const uint32_t sn = P.stage_sn[k];
+                const uint32_t sn = P.stage_sn[k], nu = P.upd_ptr[sn + 1] - P.upd_ptr[sn];
                 max_h = std::max(max_h, panel_h(sn));
-                max_u = std::max(max_u, P.upd_ptr[sn + 1] - P.upd_ptr[sn]);
+                max_u = std::max(max_u, nu);
+                sum_u += nu;
+                u4 += nu >= 4;
+                u8 += nu >= 8;
+                u16 += nu >= 16;
             }
-            std::fprintf(stderr, "  stage %u: %u thread + %u warp + %u CTA panels, tallest %u rows, most updates %u\n", st,
-                         P.stage_ptr[3 * st + 1] - P.stage_ptr[3 * st], P.stage_ptr[3 * st + 2] - P.stage_ptr[3 * st + 1],
-                         P.stage_ptr[3 * st + 3] - P.stage_ptr[3 * st + 2], max_h, max_u);
+            std::fprintf(stderr,
+                         "  stage %u: %u thread + %u warp + %u CTA panels, tallest %u rows, most updates %u (mean %.1f; panels with >= 4 / 8 / 16 "
+                         "updates: %u / %u / %u)\n",
+                         st, P.stage_ptr[3 * st + 1] - P.stage_ptr[3 * st], P.stage_ptr[3 * st + 2] - P.stage_ptr[3 * st + 1],
+                         P.stage_ptr[3 * st + 3] - P.stage_ptr[3 * st + 2], max_h, max_u,
+                         (double)sum_u / std::max<uint32_t>(1, P.stage_ptr[3 * st + 3] - P.stage_ptr[3 * st]), u4, u8, u16);
         }
     }
     P.perm = perm;
