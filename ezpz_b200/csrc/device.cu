@@ -819,11 +819,19 @@ int32_t ezpz_b200_solve_batch(ezpz_context_t* ctx, const ezpz_structure_t* s, co
         rc = ezpz_b200_solve_batch_device(ctx, s, config, cnt, &dio, st, detail);
         if (rc != EZPZ_OK) return rc;
         EZ_CUDA(cudaMemcpyAsync(io->final_values + b0 * n, d_f + b0 * n, cnt * n * sizeof(double), cudaMemcpyDeviceToHost, st), "D2H finals");
-        EZ_CUDA(cudaMemcpyAsync(io->iterations + b0, d_it + b0, cnt * sizeof(uint32_t), cudaMemcpyDeviceToHost, st), "D2H iterations");
-        EZ_CUDA(cudaMemcpyAsync(io->status + b0, d_st + b0, cnt, cudaMemcpyDeviceToHost, st), "D2H status");
-        if (d_un) EZ_CUDA(cudaMemcpyAsync(io->unsat_mask + b0 * uw, d_un + b0 * uw, cnt * uw * sizeof(uint32_t), cudaMemcpyDeviceToHost, st), "D2H unsat");
         if (d_dg) EZ_CUDA(cudaMemcpyAsync(io->degen_count + b0 * nc, d_dg + b0 * nc, cnt * nc * sizeof(uint32_t), cudaMemcpyDeviceToHost, st), "D2H degen");
         if (d_jc) EZ_CUDA(cudaMemcpyAsync(io->jacobian + b0 * nnz, d_jc + b0 * nnz, cnt * nnz * sizeof(double), cudaMemcpyDeviceToHost, st), "D2H jacobian");
+        EZ_CUDA(cudaEventRecord(ctx->pipe_done[c % 3], st), "cudaEventRecord");
+    }
+    // The small per-problem outputs (9 bytes a problem: iterations, status, unsatisfied mask) leave in ONE copy each for the
+    // whole batch once every chunk is done: per chunk they cost three more calls and copy-engine round trips than bytes.
+    {
+        cudaStream_t st = ctx->pipe[0];
+        for (int k = 1; k < 3; ++k)
+            if (n_chunks > (uint64_t)k) EZ_CUDA(cudaStreamWaitEvent(st, ctx->pipe_done[k], 0), "cudaStreamWaitEvent");
+        EZ_CUDA(cudaMemcpyAsync(io->iterations, d_it, batch * sizeof(uint32_t), cudaMemcpyDeviceToHost, st), "D2H iterations");
+        EZ_CUDA(cudaMemcpyAsync(io->status, d_st, batch, cudaMemcpyDeviceToHost, st), "D2H status");
+        if (d_un) EZ_CUDA(cudaMemcpyAsync(io->unsat_mask, d_un, batch * uw * sizeof(uint32_t), cudaMemcpyDeviceToHost, st), "D2H unsat");
     }
     for (int k = 0; k < 3; ++k) EZ_CUDA(cudaStreamSynchronize(ctx->pipe[k]), "cudaStreamSynchronize");
     return EZPZ_OK;
