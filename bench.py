@@ -214,6 +214,8 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # stdout carries the ONE JSON line: NCCL's version banner (NCCL_DEBUG=VERSION in this image) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     B = BATCH_PER_GPU
