@@ -213,6 +213,10 @@ int32_t ezpz_b200_context_synchronize(ezpz_context_t* ctx);
  * guesses (and optionally in the scalar target p0 of each constraint).  Replaces `batch` calls of
  * solve_inner (lib.rs:265-356) at one priority level.  The whole Levenberg–Marquardt loop
  * (newton.rs:29-145) runs on the device; there is no host round trip per iteration.
+ * Structures of up to 880 values per problem run one THREAD per problem (state in shared memory); larger
+ * ones run one CTA per problem through the persistent kernel of the single-system path — every problem
+ * then gets exactly what ezpz_b200_solve_one would give it.  `params` is only available on the
+ * thread-per-problem kernel (EZPZ_ERR_UNSUPPORTED otherwise).
  *
  * Host-buffer form: copies guesses in and results out inside the call (pinned staging).
  *   guesses        [batch * n]       row-major, one row per problem, in id order
