@@ -421,8 +421,15 @@ __device__ void chunk_sum_squares(const double* v, uint32_t count, uint32_t kSum
 // A = JtJ + lambda*I in elimination numbering into the panels (entries of the panels A does not have start from
 // +0.0), b = -Jt r into y[].  Two phases separated by a barrier: zero fill, then the products.
 __device__ void direct_zero(const LargeArgs& a, uint32_t tid, uint32_t nth) {
-    double* lv = a.vg + a.L0;
-    for (uint32_t e = tid; e < a.nnz_l; e += nth) lv[e] = 0.0;
+    double* const lv = a.vg + a.L0;  // (fields read once; 16-byte stores)
+    const uint32_t n = a.nnz_l;
+    const uint32_t head = (reinterpret_cast<uintptr_t>(lv) & 15u) ? 1u : 0u;
+    if (n == 0) return;
+    if (tid == 0 && head) lv[0] = 0.0;
+    double2* const v2 = reinterpret_cast<double2*>(lv + head);
+    const uint32_t n2 = (n - head) / 2;
+    for (uint32_t e = tid; e < n2; e += nth) v2[e] = make_double2(0.0, 0.0);
+    if (tid == 0 && ((n - head) & 1u)) lv[n - 1] = 0.0;
 }
 __device__ void direct_assemble(const LargeArgs& a, double lambda, uint32_t tid, uint32_t nth) {
     // (argument fields are read once: the block lives in local memory and stores force reloads, see sn_factor)
