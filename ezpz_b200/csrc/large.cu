@@ -763,21 +763,26 @@ __device__ __noinline__ void sn_factor(const LargeArgs& a, uint32_t pos, uint32_
     // (A variant that keeps row r of the panel in lane r's registers and moves L[c][k] by shuffle was measured slower:
     // 9.0 ms against 8.7 ms of factor stages on the 1M-variable sketch — a warp waits on the panel's memory round trips,
     // not on the column arithmetic; profiles/r01k_lm_kernel.md.)
+    // The forward substitution of column c, y[c] = (y[c] - sum_{k<c} L[c][k] y[k]) / L[c][c], rides along as one more "row"
+    // (r == h) of the column: the same fma chain with other operands, on a lane that would otherwise idle, instead of a second
+    // chain that the diagonal's lane ran after its pivot while the team waited at the barrier.
     for (uint32_t c = 0; c < w; ++c) {
-        for (uint32_t r = c + lane; r < h; r += TEAM) {
-            double acc = P[r * w + c], piv = P[c * w + c];
+        for (uint32_t r = c + lane; r <= h; r += TEAM) {
+            const bool yrow = r == h;
+            const double* pa = yrow ? P + c * w : P + r * w;
+            const double* pb = yrow ? ys : P + c * w;
+            double acc = yrow ? ys[c] : P[r * w + c], piv = P[c * w + c];
             for (uint32_t k = 0; k < c; ++k) {
                 const double lck = P[c * w + k];
                 piv = __fma_rn(-lck, lck, piv);
-                acc = __fma_rn(-P[r * w + k], lck, acc);
+                acc = __fma_rn(-pa[k], pb[k], acc);
             }
             const double rinv = __ddiv_rn(1.0, __dsqrt_rn(piv));
             if (r == c) {
                 if (!(piv > 0.0) || !ezm::ez_isfinite(piv)) *fail_flag = 1;
                 rinv_out[c] = rinv;
-                double ay = ys[c];
-                for (uint32_t k = 0; k < c; ++k) ay = __fma_rn(-P[c * w + k], ys[k], ay);
-                ys[c] = __dmul_rn(ay, rinv);
+            } else if (yrow) {
+                ys[c] = __dmul_rn(acc, rinv);
             } else {
                 P[r * w + c] = __dmul_rn(acc, rinv);
             }
