@@ -802,15 +802,26 @@ __device__ __noinline__ void sn_factor(const LargeArgs& a, uint32_t pos, uint32_
 // The columns of the supernode advance together: lane c of the team's first warp owns column c; the rows below the block
 // are w independent chains; inside the block, step t (t = w-1 ... 0) finalises d[t] and every column c < t applies it —
 // one shuffle per step instead of one sequential chain per supernode.  The final values also go to d in variable numbering.
+// Warp teams pipeline their panels through the carry at the end of the warp's stage (see sn_factor): while panel k is
+// substituted, the values and the row list of panel k + 1 travel into shared memory (cp.async, doubles 640.. of the stage)
+// and the record of panel k + 2 into registers; half of a warp's backward time used to be the dependent round trips record ->
+// values / row list -> d of the rows, of which only the last gather is left.
+//   carry words: [0] panel whose values + row list are staged, [4..8] its record; [1] panel whose record is in [12..16]
+constexpr uint32_t kBackCarryAt = 640, kBackCarryMaxH = 64, kBackCarryMaxHW = 384;
 template <int TEAM>
-__device__ __noinline__ void sn_backward(const LargeArgs& a, uint32_t pos, uint32_t lane, double* stage) {
+__device__ __noinline__ void sn_backward(const LargeArgs& a, uint32_t pos, uint32_t lane, double* stage, uint32_t next_pos = UINT32_MAX,
+                                         uint32_t next2_pos = UINT32_MAX) {
     using Caps = TeamCaps<TEAM>;
     const double* const lv = a.vg + a.L0;  // (argument fields are read once: see sn_factor)
     double* const y = a.vg + a.Y0;
-    const uint4 hdr = __ldg(reinterpret_cast<const uint4*>(a.stage_rec) + 2 * (size_t)pos);
+    const uint32_t* const stage_rec = a.stage_rec;
+    const uint32_t* const sn_rows = a.sn_rows;
+    uint32_t* const carry = TEAM == 32 ? reinterpret_cast<uint32_t*>(stage + kCarryOffset) : nullptr;
+    const bool carried = TEAM == 32 && carry[0] == pos;
+    const uint4 hdr = carried ? *reinterpret_cast<const uint4*>(carry + 4) : __ldg(reinterpret_cast<const uint4*>(stage_rec) + 2 * (size_t)pos);
     const uint32_t j0 = hdr.x, w = hdr.y, h = hdr.z, rb = hdr.w;
-    const double* G = lv + __ldg(a.stage_rec + 8 * (size_t)pos + 4);
-    const uint32_t* const rows = a.sn_rows + rb;
+    const double* G = lv + (carried ? carry[8] : __ldg(stage_rec + 8 * (size_t)pos + 4));
+    const uint32_t* const rows = sn_rows + rb;
     const double* const rinv_in = a.vg + a.RV0 + j0;
     double* const d_out = a.vg + a.D0;
     const uint32_t* const perm = a.perm + j0;
@@ -830,10 +841,52 @@ __device__ __noinline__ void sn_backward(const LargeArgs& a, uint32_t pos, uint3
     if (staged) {
         double* Ps = stage;
         dv = stage + Caps::panel;
-        for (uint32_t t = lane; t < h * w; t += TEAM) Ps[t] = G[t];
-        for (uint32_t t = lane; t < h; t += TEAM) dv[t] = y[__ldg(rows + t)];
+        if (carried) {  // values and row list are in the stage already: one gather is all that is left
+            cp_async_wait_all();
+            team_sync<TEAM>();
+            const double* cd = stage + kBackCarryAt;
+            const uint32_t* crows = reinterpret_cast<const uint32_t*>(cd + ((h * w + 1u) & ~1u));
+            for (uint32_t t = lane; t < h; t += TEAM) dv[t] = y[crows[t]];
+            for (uint32_t t = lane; t < h * w; t += TEAM) Ps[t] = cd[t];
+        } else {
+            for (uint32_t t = lane; t < h * w; t += TEAM) Ps[t] = G[t];
+            for (uint32_t t = lane; t < h; t += TEAM) dv[t] = y[__ldg(rows + t)];
+        }
         P = Ps;
         team_sync<TEAM>();
+    }
+    uint4 n2h = make_uint4(0, 0, 0, 0);
+    uint32_t n2off = 0;
+    if (TEAM == 32) {
+        // record of panel k + 1: carried by the previous call, else read now; record of panel k + 2: requested now, kept at the end
+        bool carry_next = false;
+        if (next_pos != UINT32_MAX && staged && h <= kBackCarryMaxH) {
+            const bool have = carry[1] == next_pos;
+            const uint4 nh = have ? *reinterpret_cast<const uint4*>(carry + 12) : __ldg(reinterpret_cast<const uint4*>(stage_rec) + 2 * (size_t)next_pos);
+            const uint32_t noff = have ? carry[16] : __ldg(stage_rec + 8 * (size_t)next_pos + 4);
+            const uint32_t nhw = nh.y * nh.z;
+            if (nh.z <= kBackCarryMaxH && nhw <= kBackCarryMaxHW) {
+                double* cd = stage + kBackCarryAt;
+                uint32_t* crows = reinterpret_cast<uint32_t*>(cd + ((nhw + 1u) & ~1u));
+                for (uint32_t q = lane; q < nhw; q += TEAM) cp_async8(cd + q, lv + noff + q);
+                for (uint32_t q = lane; q < nh.z; q += TEAM) cp_async4(crows + q, sn_rows + nh.w + q);
+                team_sync<TEAM>();  // every lane has read the carry of this panel
+                if (lane == 0) {
+                    carry[0] = next_pos;
+                    *reinterpret_cast<uint4*>(carry + 4) = nh;
+                    carry[8] = noff;
+                }
+                carry_next = true;
+            }
+        }
+        if (!carry_next) {
+            team_sync<TEAM>();
+            if (lane == 0) carry[0] = UINT32_MAX;
+        }
+        if (next2_pos != UINT32_MAX) {
+            n2h = __ldg(reinterpret_cast<const uint4*>(stage_rec) + 2 * (size_t)next2_pos);
+            n2off = __ldg(stage_rec + 8 * (size_t)next2_pos + 4);
+        }
     }
     if (lane < 32) {
         const uint32_t c = lane;
@@ -853,6 +906,11 @@ __device__ __noinline__ void sn_backward(const LargeArgs& a, uint32_t pos, uint3
             y[j0 + c] = v;
             d_out[__ldg(perm + c)] = v;
         }
+    }
+    if (TEAM == 32 && lane == 0) {
+        carry[1] = next2_pos;  // UINT32_MAX when there is none
+        *reinterpret_cast<uint4*>(carry + 12) = n2h;
+        carry[16] = n2off;
     }
     team_sync<TEAM>();
 }
@@ -891,7 +949,14 @@ __device__ void direct_backward_stage(const LargeArgs& a, uint32_t st, uint32_t 
     const uint32_t b0 = __ldg(a.stage_ptr + 3 * st), b1 = __ldg(a.stage_ptr + 3 * st + 1), b2 = __ldg(a.stage_ptr + 3 * st + 2),
                    b3 = __ldg(a.stage_ptr + 3 * st + 3);
     for (uint32_t k = b0 + tid; k < b1; k += nth) sn_backward<1>(a, k, 0, nullptr);
-    for (uint32_t k = b1 + (threadIdx.x >> 5) * a.vgrid + a.vblock; k < b2; k += nth >> 5) sn_backward<32>(a, k, threadIdx.x & 31u, warp_stage);
+    if ((threadIdx.x & 31u) == 0) {  // no carry from whatever used the stage before
+        uint32_t* carry = reinterpret_cast<uint32_t*>(warp_stage + kCarryOffset);
+        carry[0] = UINT32_MAX;
+        carry[1] = UINT32_MAX;
+    }
+    __syncwarp();
+    for (uint32_t k = b1 + (threadIdx.x >> 5) * a.vgrid + a.vblock, nw = nth >> 5; k < b2; k += nw)
+        sn_backward<32>(a, k, threadIdx.x & 31u, warp_stage, k + nw < b2 ? k + nw : UINT32_MAX, k + 2 * nw < b2 ? k + 2 * nw : UINT32_MAX);
     if (b3 > b2) {
         __syncthreads();
         for (uint32_t k = b2 + a.vblock; k < b3; k += a.vgrid) sn_backward<512>(a, k, threadIdx.x, cta_stage);
