@@ -475,8 +475,8 @@ struct TeamCaps<1> {
     static constexpr uint32_t panel = 0, block = 0, rel = 0, inv = 0, recs = 0;
 };
 template <>
-struct TeamCaps<32> {
-    static constexpr uint32_t panel = 576, block = 448, rel = 256, inv = 512, recs = 32;
+struct TeamCaps<32> {  // (no inverse maps: warp teams apply updates pair by pair; their space went to the block area)
+    static constexpr uint32_t panel = 576, block = 576, rel = 256, inv = 0, recs = 32;
 };
 template <>
 struct TeamCaps<128> {  // four warps: the stages of four warp teams
@@ -677,7 +677,7 @@ __device__ __noinline__ void sn_factor(const LargeArgs& a, uint32_t pos, uint32_
             while (cnt < avail) {
                 uint32_t* r = srec + 8 * cnt;
                 const uint32_t T = r[1], wK = r[2] & 0xffu, len = T * wK;
-                if (tot_b + len + wK > block_cap || tot_r + T > Caps::rel || (cnt + 1) * h > Caps::inv || T >= 0xffffu) break;
+                if (tot_b + len + wK > block_cap || tot_r + T > Caps::rel || (TEAM > kPairTeamMax && (cnt + 1) * h > Caps::inv) || T >= 0xffffu) break;
                 for (uint32_t q = lane; q < len; q += TEAM) cp_async8(kb + tot_b + q, lv + r[0] + q);
                 for (uint32_t q = lane; q < wK; q += TEAM) cp_async8(kb + tot_b + len + q, y + r[4] + q);  // y of K's columns
                 for (uint32_t q = lane; q < T; q += TEAM) cp_async4(srel + tot_r + q, upd_rel + r[3] + q);
@@ -687,7 +687,8 @@ __device__ __noinline__ void sn_factor(const LargeArgs& a, uint32_t pos, uint32_
                 ++cnt;
             }
             if (cnt > 0) {
-                for (uint32_t q = lane; q < cnt * h; q += TEAM) inv[q] = 0xffffu;
+                if constexpr (TEAM > kPairTeamMax)
+                    for (uint32_t q = lane; q < cnt * h; q += TEAM) inv[q] = 0xffffu;
                 cp_async_wait_all();
                 team_sync<TEAM>();
                 build_inverse(cnt);
@@ -697,11 +698,12 @@ __device__ __noinline__ void sn_factor(const LargeArgs& a, uint32_t pos, uint32_
             }
             // One update whose block is larger than the stage.
             const uint32_t T = srec[1], wK = srec[2] & 0xffu, nc = srec[2] >> 8;
-            if (T + 1 <= block_cap && T <= Caps::rel && h <= Caps::inv && T < 0xffffu) {
+            if (T + 1 <= block_cap && T <= Caps::rel && (TEAM <= kPairTeamMax || h <= Caps::inv) && T < 0xffffu) {
                 // Column slices of the descendant's panel, as many columns at a time as fit: every entry's fma chain
                 // simply continues from slice to slice (k stays ascending).
                 const uint32_t ws_max = block_cap / (T + 1);
-                for (uint32_t q = lane; q < h; q += TEAM) inv[q] = 0xffffu;
+                if constexpr (TEAM > kPairTeamMax)
+                    for (uint32_t q = lane; q < h; q += TEAM) inv[q] = 0xffffu;
                 for (uint32_t q = lane; q < T; q += TEAM) cp_async4(srel + q, upd_rel + srec[3] + q);
                 for (uint32_t ks = 0; ks < wK; ks += ws_max) {
                     const uint32_t ws = min(ws_max, wK - ks);
