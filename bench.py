@@ -213,9 +213,13 @@ def run_gpu(args):
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    saved_stdout = None
     if world > 1:
-        # stdout carries the ONE JSON line: NCCL's version banner (NCCL_DEBUG=VERSION in this image) goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # stdout carries the ONE JSON line: whatever native libraries print while the job runs (NCCL's version banner goes
+        # to file descriptor 1 whatever NCCL_DEBUG_FILE says) is sent to stderr; the descriptor comes back for the JSON line
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
 
     B = BATCH_PER_GPU
@@ -351,8 +355,14 @@ def run_gpu(args):
             line["cpu_baseline"] = {k: v for k, v in cpu_arm(3, 1, sample).items() if k != "ms_per_step"}
             if not args.no_large:
                 line["large_system"] = large_system_report(ctx, peaks)
+        if saved_stdout is not None:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
         print(json.dumps(line))
+        sys.stdout.flush()
     if world > 1:
+        if saved_stdout is not None and rank == 0:
+            os.dup2(2, 1)  # (teardown chatter, if any, off stdout again)
         dist.destroy_process_group()
 
 
