@@ -572,8 +572,9 @@ __device__ __noinline__ void sn_factor(const LargeArgs& a, uint32_t pos, uint32_
     double* P = staged ? stage : G;
     // The update blocks get whatever the panel leaves of the panel + block areas (a panel of 100 doubles in a warp's stage
     // leaves 920 of the 1,024, twice the fixed split: more updates per memory round trip).
-    // (CTA teams keep the fixed split: their panels are large and 2D-lattice sketches measured slower with larger chunks.)
-    const uint32_t pan = TEAM >= 512 ? Caps::panel : (staged ? ((h * w + 1u) & ~1u) : 0u);
+    // (CTA teams keep the fixed split for their large panels — 2D-lattice sketches measured slower with larger chunks — but
+    // the small panels of the upper tree, dozens of updates each, leave them nearly the whole stage for update blocks.)
+    const uint32_t pan = TEAM >= 512 ? (h * w <= 1024u ? 1024u : Caps::panel) : (staged ? ((h * w + 1u) & ~1u) : 0u);
     const uint32_t block_cap = TEAM > 1 ? Caps::panel + Caps::block - pan : 0u;
     double* kb = TEAM > 1 ? stage + pan : nullptr;
     double* ys = TEAM > 1 ? stage + Caps::panel + Caps::block : y + j0;  // w <= 16 values
