@@ -640,7 +640,28 @@ __device__ __noinline__ void sn_factor(const LargeArgs& a, uint32_t pos, uint32_
                         if (ti != 0xffffu && tj < nc) {
                             const double* bi = kb + boff + ti * ws;
                             const double* bj = kb + boff + tj * ws;
-                            for (uint32_t k = 0; k < ws; ++k) acc = __fma_rn(-bi[k], bj[k], acc);
+                            if (ws == 16 && !(boff & 1u)) {
+                                // full 16-column descendants (the upper tree): eight terms' operands per round of 16-byte
+                                // loads, so the shared-memory latency is paid twice per update instead of once per term
+                                const double2* bi2 = reinterpret_cast<const double2*>(bi);
+                                const double2* bj2 = reinterpret_cast<const double2*>(bj);
+#pragma unroll
+                                for (int half = 0; half < 2; ++half) {
+                                    double2 u[4], v[4];
+#pragma unroll
+                                    for (int q = 0; q < 4; ++q) {
+                                        u[q] = bi2[4 * half + q];
+                                        v[q] = bj2[4 * half + q];
+                                    }
+#pragma unroll
+                                    for (int q = 0; q < 4; ++q) {
+                                        acc = __fma_rn(-u[q].x, v[q].x, acc);
+                                        acc = __fma_rn(-u[q].y, v[q].y, acc);
+                                    }
+                                }
+                            } else {
+                                for (uint32_t k = 0; k < ws; ++k) acc = __fma_rn(-bi[k], bj[k], acc);
+                            }
                         }
                         boff += T * ws + ws;
                     }
