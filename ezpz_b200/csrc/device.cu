@@ -800,6 +800,20 @@ int32_t ezpz_b200_solve_batch(ezpz_context_t* ctx, const ezpz_structure_t* s, co
     }
     const uint64_t n_chunks = (batch + chunk - 1) / chunk;
     EZ_CUDA(cudaStreamSynchronize(ctx->stream), "cudaStreamSynchronize");
+    // EZPZ_B200_DEBUG=3: CUDA events after every copy and kernel of the pipeline, printed per call (where a slow call loses time)
+    static const bool trace = [] {
+        const char* e = std::getenv("EZPZ_B200_DEBUG");
+        return e && e[0] == '3';
+    }();
+    std::vector<cudaEvent_t> tev;
+    auto mark = [&](cudaStream_t st) {
+        if (!trace) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, st);
+        tev.push_back(e);
+    };
+    if (trace) mark(ctx->pipe[0]);
     for (uint64_t c = 0; c < n_chunks; ++c) {
         const uint64_t b0 = c * chunk;
         if (b0 >= batch) break;
@@ -807,6 +821,7 @@ int32_t ezpz_b200_solve_batch(ezpz_context_t* ctx, const ezpz_structure_t* s, co
         cudaStream_t st = ctx->pipe[c % 3];
         EZ_CUDA(cudaMemcpyAsync(d_g + b0 * n, io->guesses + b0 * n, cnt * n * sizeof(double), cudaMemcpyHostToDevice, st), "H2D guesses");
         if (d_p) EZ_CUDA(cudaMemcpyAsync(d_p + b0 * nc, io->params + b0 * nc, cnt * nc * sizeof(double), cudaMemcpyHostToDevice, st), "H2D params");
+        mark(st);
         ezpz_batch_io_t dio;
         dio.guesses = d_g + b0 * n;
         dio.params = d_p ? d_p + b0 * nc : nullptr;
@@ -818,22 +833,37 @@ int32_t ezpz_b200_solve_batch(ezpz_context_t* ctx, const ezpz_structure_t* s, co
         dio.jacobian = d_jc ? d_jc + b0 * nnz : nullptr;
         rc = ezpz_b200_solve_batch_device(ctx, s, config, cnt, &dio, st, detail);
         if (rc != EZPZ_OK) return rc;
+        mark(st);
+        EZ_CUDA(cudaEventRecord(ctx->pipe_done[c % 3], st), "cudaEventRecord");  // this stream's kernels so far are done
         EZ_CUDA(cudaMemcpyAsync(io->final_values + b0 * n, d_f + b0 * n, cnt * n * sizeof(double), cudaMemcpyDeviceToHost, st), "D2H finals");
         if (d_dg) EZ_CUDA(cudaMemcpyAsync(io->degen_count + b0 * nc, d_dg + b0 * nc, cnt * nc * sizeof(uint32_t), cudaMemcpyDeviceToHost, st), "D2H degen");
         if (d_jc) EZ_CUDA(cudaMemcpyAsync(io->jacobian + b0 * nnz, d_jc + b0 * nnz, cnt * nnz * sizeof(double), cudaMemcpyDeviceToHost, st), "D2H jacobian");
-        EZ_CUDA(cudaEventRecord(ctx->pipe_done[c % 3], st), "cudaEventRecord");
+        mark(st);
     }
     // The small per-problem outputs (9 bytes a problem: iterations, status, unsatisfied mask) leave in ONE copy each for the
     // whole batch once every chunk is done: per chunk they cost three more calls and copy-engine round trips than bytes.
+    // They only wait for the KERNELS of all chunks (not for the last chunk's finals) and go out on the three streams side by side.
     {
-        cudaStream_t st = ctx->pipe[0];
-        for (int k = 1; k < 3; ++k)
-            if (n_chunks > (uint64_t)k) EZ_CUDA(cudaStreamWaitEvent(st, ctx->pipe_done[k], 0), "cudaStreamWaitEvent");
-        EZ_CUDA(cudaMemcpyAsync(io->iterations, d_it, batch * sizeof(uint32_t), cudaMemcpyDeviceToHost, st), "D2H iterations");
-        EZ_CUDA(cudaMemcpyAsync(io->status, d_st, batch, cudaMemcpyDeviceToHost, st), "D2H status");
-        if (d_un) EZ_CUDA(cudaMemcpyAsync(io->unsat_mask, d_un, batch * uw * sizeof(uint32_t), cudaMemcpyDeviceToHost, st), "D2H unsat");
+        const int used = (int)std::min<uint64_t>(3, n_chunks);
+        for (int q = 0; q < 3; ++q)
+            for (int k = 0; k < used; ++k)
+                if (k != q) EZ_CUDA(cudaStreamWaitEvent(ctx->pipe[q], ctx->pipe_done[k], 0), "cudaStreamWaitEvent");
+        EZ_CUDA(cudaMemcpyAsync(io->iterations, d_it, batch * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->pipe[0]), "D2H iterations");
+        EZ_CUDA(cudaMemcpyAsync(io->status, d_st, batch, cudaMemcpyDeviceToHost, ctx->pipe[1]), "D2H status");
+        if (d_un) EZ_CUDA(cudaMemcpyAsync(io->unsat_mask, d_un, batch * uw * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->pipe[2]), "D2H unsat");
     }
+    if (trace) mark(ctx->pipe[0]);
     for (int k = 0; k < 3; ++k) EZ_CUDA(cudaStreamSynchronize(ctx->pipe[k]), "cudaStreamSynchronize");
+    if (trace && tev.size() >= 2) {
+        std::fprintf(stderr, "[solve_batch] us since call start, per chunk (H2D done, kernel done, D2H done):");
+        for (size_t k = 1; k < tev.size(); ++k) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, tev[0], tev[k]);
+            std::fprintf(stderr, "%s%.0f", (k - 1) % 3 == 0 ? " | " : " ", ms * 1e3);
+        }
+        std::fprintf(stderr, "\n");
+        for (cudaEvent_t e : tev) cudaEventDestroy(e);
+    }
     return EZPZ_OK;
 }
 
