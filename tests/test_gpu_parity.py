@@ -204,8 +204,8 @@ def random_constraints(rng, count, n_vars):
 
     C = ez.Constraint
     makers = [
-        lambda: C.LineTangentToCircle(Ln(), Ci(), int(rng.integers(1, 3))),
-        lambda: C.CircleTangentToCircle(Ci(), Ci(), int(rng.integers(1, 3))),
+        lambda: C.LineTangentToCircle(Ln(), Ci(), int(rng.integers(0, 3))),  # 0 = LineSide::Undefined
+        lambda: C.CircleTangentToCircle(Ci(), Ci(), int(rng.integers(0, 3))),  # 0 = CircleSide::Undefined
         lambda: C.Distance(P(), P(), rng.uniform(0, 5)),
         lambda: C.DistanceVar(P(), P(), ez.DatumDistance(int(rng.integers(n_vars)))),
         lambda: C.VerticalDistance(P(), P(), rng.uniform(-5, 5)),
@@ -382,3 +382,96 @@ def test_solve_topology_cache(ctx):
         o = orc.solve(ez.records([r.constraint for r in reqs]), g)
         assert out.iterations() == o.iterations and out.is_satisfied() == (len(o.unsatisfied) == 0)
         assert_bitwise(np.array(out.final_values()), o.final_values, f"call {k}")
+
+
+def _undefined_sides_system():
+    """Circles A (ids 0,1,2) and B (3,4,5), line p (6,7) - q (8,9).  A is pinned at the origin with radius 2, B has radius 1
+    and its centre on the x axis, the line is horizontal between x = -5 and x = 5.  Both tangencies are given with
+    Undefined sides, so each problem's guesses decide (constraints.rs:146-193): B ends up inside (|cx| = 1) or outside
+    (|cx| = 3) of A, the line above (y = 2) or below (y = -2) it."""
+    C = ez.Constraint
+    A = ez.DatumCircle(ez.DatumPoint.new_xy(0, 1), ez.DatumDistance(2))
+    B = ez.DatumCircle(ez.DatumPoint.new_xy(3, 4), ez.DatumDistance(5))
+    p, q = ez.DatumPoint.new_xy(6, 7), ez.DatumPoint.new_xy(8, 9)
+    ln = ez.DatumLineSegment(p, q)
+    cons = [C.Fixed(0, 0.0), C.Fixed(1, 0.0), C.CircleRadius(A, 2.0), C.Fixed(4, 0.0), C.CircleRadius(B, 1.0),
+            C.CircleTangentToCircle(A, B), C.Fixed(6, -5.0), C.Fixed(8, 5.0), C.Horizontal(ln), C.LineTangentToCircle(ln, A)]
+    assert cons[5].flags == 0 and cons[9].flags == 0
+    return ez.records(cons), 10
+
+
+def test_undefined_sides_resolved_per_problem_on_device(ctx):
+    """CircleSide::Undefined and LineSide::Undefined reach the device unresolved and are resolved there from each problem's
+    own guesses (set_from_initial_values, constraints.rs:146-193, both branches): the batched kernel, the single solve and
+    ezpz_b200_solve agree with the oracle bit for bit, and one batch holds problems of all four side combinations."""
+    recs, n = _undefined_sides_system()
+    st = ez.Structure(recs, n)
+    rng = np.random.default_rng(146193)
+    B = 512
+    G = np.zeros((B, n))
+    G[:, 2], G[:, 5] = 2.0 + rng.uniform(-0.2, 0.2, B), 1.0 + rng.uniform(-0.2, 0.2, B)
+    G[:, 3] = rng.uniform(0.3, 4.0, B)                       # centre of B: inside or outside of A
+    G[:, 6], G[:, 8] = -5.0, 5.0
+    y = rng.uniform(0.5, 3.0, B) * rng.choice([-1.0, 1.0], B)  # the line: above or below
+    G[:, 7], G[:, 9] = y, y + rng.uniform(-0.1, 0.1, B)
+    out = ctx.solve_batch(st, G, want_unsat=True)
+    fin, it, status = orc.solve_batch(recs, n, G, nthreads=2, hoist=True)
+    assert np.array_equal(out.iterations, it)
+    assert np.array_equal(out.status & 3, status & 3)
+    assert_bitwise(out.final_values, fin, "final values")
+    ok = (out.status & 3) == 1
+    assert ok.mean() > 0.9
+    inside = np.abs(np.abs(out.final_values[ok, 3]) - 1.0) < 1e-6
+    outside = np.abs(np.abs(out.final_values[ok, 3]) - 3.0) < 1e-6
+    above = np.abs(out.final_values[ok, 7] - 2.0) < 1e-6
+    below = np.abs(out.final_values[ok, 7] + 2.0) < 1e-6
+    assert (inside | outside).all() and (above | below).all()
+    for a in (inside, outside):
+        for b in (above, below):
+            assert (a & b).sum() > 10, "every side combination must occur in the batch"
+    # the side is decided by the sign tests of the reference, evaluated on the guesses
+    dist0 = np.abs(G[ok, 3])
+    want_inside = np.abs(np.abs(G[ok, 2] - G[ok, 5]) - dist0) < np.abs(G[ok, 2] + G[ok, 5] - dist0)
+    assert np.array_equal(inside, want_inside)
+    assert np.array_equal(below, G[ok, 7] >= 0.0) or np.array_equal(above, G[ok, 7] >= 0.0)
+    for b in (0, 1, 2, 3):
+        one = ctx.solve_one(st, G[b])
+        o = orc.solve_inner(recs, G[b])
+        assert one.iterations == o.iterations and one.converged == o.converged and one.unsatisfied == o.unsatisfied
+        assert_bitwise(one.final_values, o.final_values, f"solve_one {b}")
+
+
+def test_undefined_sides_mid_size_batch_and_large_path(ctx):
+    """The same Undefined-side resolution on the persistent large-path kernel: 40 disjoint copies of the system above in one
+    sketch (400 variables: one CTA per problem in a batch, one cluster when solved alone), every copy with its own side
+    combination."""
+    base, n1 = _undefined_sides_system()
+    copies = 40
+    recs = np.concatenate([base.copy() for _ in range(copies)])
+    for k in range(copies):
+        blk = recs[k * len(base):(k + 1) * len(base)]
+        for c, used in enumerate([1, 1, 3, 1, 3, 6, 1, 1, 4, 7]):  # ids each kind really names; unused ids stay 0
+            blk["ids"][c, :used] += n1 * k
+    n = n1 * copies
+    st = ez.Structure(recs, n)
+    od = st.ordering()
+    assert od["path"] == 1
+    rng = np.random.default_rng(7)
+    batch = 6
+    G = np.zeros((batch, copies, n1))
+    G[..., 2], G[..., 5] = 2.0, 1.0
+    G[..., 3] = rng.uniform(0.3, 4.0, (batch, copies))
+    G[..., 6], G[..., 8] = -5.0, 5.0
+    y = rng.uniform(0.5, 3.0, (batch, copies)) * rng.choice([-1.0, 1.0], (batch, copies))
+    G[..., 7], G[..., 9] = y, y
+    G = G.reshape(batch, n)
+    out = ctx.solve_batch(st, G, want_unsat=True)
+    for b in range(batch):
+        o = orc.solve_inner_ordered(recs, G[b], od["elim_order"], od["sum_chunk"])
+        one = ctx.solve_one(st, G[b])
+        assert out.iterations[b] == one.iterations == o.iterations
+        assert bool(out.status[b] & 1) == one.converged == o.converged
+        assert_bitwise(out.final_values[b], o.final_values, f"batch member {b}")
+        assert_bitwise(one.final_values, o.final_values, f"single solve {b}")
+    fv = out.final_values.reshape(batch, copies, n1)
+    assert ((np.abs(np.abs(fv[..., 3]) - 1.0) < 1e-6).any() and (np.abs(np.abs(fv[..., 3]) - 3.0) < 1e-6).any())
