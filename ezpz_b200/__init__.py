@@ -503,6 +503,46 @@ class Structure:
                     l_col_ptr=self._arr(c, self.n + 1), l_row_idx=self._arr(d, self.nnz_l))
 
 
+    def role_program(self, roles, stride=1):
+        """The tables of the batched kernel for `roles` cooperating warps (structure.h: RoleBlob), parsed: per role its
+        constraint list and its tape as a list of ops {"dst", "code", "fin", "pairs": [(a, b)...]} or {"barrier": True}
+        (slots, i.e. byte offsets divided by 8 * stride)."""
+        L = native.lib()
+        n_words, cons_word = C.c_uint64(0), C.c_uint32(0)
+        dims = (C.c_uint32 * 4)()
+        rc = L.ezpz_b200_structure_role_program(self.handle, roles, stride, None, 0, C.byref(n_words), C.byref(cons_word), dims)
+        if rc != 0:
+            raise EzpzError(rc)
+        words = np.zeros(n_words.value, dtype=np.uint32)
+        L.ezpz_b200_structure_role_program(self.handle, roles, stride, native.ptr(words), n_words.value, C.byref(n_words),
+                                           C.byref(cons_word), dims)
+        sb = 8 * stride
+        out = {"W": int(dims[0]), "n_cons": int(dims[1]), "barriers": int(dims[2]), "critical_cost": int(dims[3]), "words": words,
+               "roles": []}
+        for r in range(roles):
+            h = words[12 * r:12 * r + 12]
+            ops, w = [], int(h[2])
+            for _ in range(int(h[3])):
+                dst, npairs, code, fin = (int(v) for v in words[w:w + 4])
+                w += 4
+                if code & 16:
+                    ops.append({"barrier": True})
+                    continue
+                pairs = [(int(words[w + 2 * k]) // sb, int(words[w + 2 * k + 1]) // sb) for k in range(npairs)]
+                w += 2 * npairs + (2 if npairs % 2 else 0)  # headers sit on 16 bytes
+                ops.append({"dst": dst // sb, "code": code & 0x3f, "positive": (code >> 8) & 0x7f, "fin": fin // sb, "pairs": pairs})
+            out["roles"].append({"constraints": (words[int(h[0]):int(h[0]) + int(h[1])] & 0xffff).tolist(), "ops": ops,
+                                 "x": (int(h[4]), int(h[5])), "r": (int(h[6]), int(h[7])), "j": (int(h[8]), int(h[9]))})
+        return out
+
+    def batch_shape(self, batch, sm_count=148, smem_per_block=232448):
+        """(roles, problems per CTA) the batched kernel would use for `batch` problems on such a device."""
+        r, t = C.c_uint32(0), C.c_uint32(0)
+        rc = native.lib().ezpz_b200_structure_batch_shape(self.handle, batch, sm_count, smem_per_block, C.byref(r), C.byref(t))
+        if rc != 0:
+            raise EzpzError(rc)
+        return int(r.value), int(t.value)
+
     def ordering(self):
         """How the large path solves the damped step: dict(path, elim_order, nested, n_levels, nnz_l, sum_chunk)."""
         path, nested, nl, nnz, ch, po = C.c_int32(), C.c_int32(), C.c_uint32(), C.c_uint64(), C.c_uint32(), C.c_void_p()

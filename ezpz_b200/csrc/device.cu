@@ -39,8 +39,7 @@ __constant__ uint8_t c_rows[EZPZ_K_COUNT];
 __constant__ uint8_t c_emit_len[EZPZ_K_COUNT][2];
 
 struct SmallArgs {
-    const DevCons* cons;
-    const uint32_t* tape;
+    const uint32_t* tables;  // RoleBlob words (structure.h) on the device
     const double* guesses;
     const double* params;
     double* finals;
@@ -52,10 +51,11 @@ struct SmallArgs {
     uint64_t batch;
     double residual_tolerance, step_tolerance, initial_lambda;
     uint32_t max_iterations;
-    uint32_t n_cons, n, m, W, X0, R0, RN0, J0, L0, D0, S0, n_ops, unsat_words, nnz;
-    uint32_t tape_words;     // length of the tape in 32-bit words
-    uint32_t stage_in_smem;  // 1: constraint records and tape are copied to shared memory by each CTA
-    uint32_t weights_one;    // 1: every weight is exactly 1.0 (r == unweighted residuals)
+    uint32_t n_cons, n, m, W, X0, R0, RN0, J0, L0, D0, S0, F0, unsat_words, nnz;
+    uint32_t table_words;  // length of the blob in 32-bit words
+    uint32_t cons_word;    // word offset of the DevCons array inside the blob
+    uint32_t T, R;         // problems per CTA (a multiple of 32) and roles (warps per 32 problems)
+    uint32_t weights_one;  // 1: every weight is exactly 1.0 (r == unweighted residuals)
 };
 
 struct GlobalX {
@@ -63,15 +63,17 @@ struct GlobalX {
     __device__ __forceinline__ double operator()(uint32_t id) const { return __ldg(p + id); }
 };
 
-// Per-thread view of the shared-memory state: column `threadIdx.x` of V[slot][thread].  Slots are addressed
+// Per-thread view of the shared-memory state: column `problem` of V[slot][problem].  Slots are addressed
 // by BYTE offsets that are uniform across the warp (slot * stride * 8), so an access is base + uniform.
 struct VView {
-    char* base;   // &V[0][threadIdx.x]
-    uint32_t sb;  // stride in bytes between consecutive slots (= blockDim.x * 8)
+    char* base;   // &V[0][problem]
+    uint32_t sb;  // stride in bytes between consecutive slots (= problems per CTA * 8)
     __device__ __forceinline__ double ld(uint32_t off) const { return *reinterpret_cast<const double*>(base + off); }
     __device__ __forceinline__ void st(uint32_t off, double v) const { *reinterpret_cast<double*>(base + off) = v; }
+    __device__ __forceinline__ void stp(bool pred, uint32_t off, double v) const {
+        if (pred) *reinterpret_cast<double*>(base + off) = v;
+    }
     __device__ __forceinline__ double lds(uint32_t slot) const { return ld(slot * sb); }
-    __device__ __forceinline__ void sts(uint32_t slot, double v) const { st(slot * sb, v); }
 };
 struct SmemX {
     VView v;
@@ -79,17 +81,28 @@ struct SmemX {
     __device__ __forceinline__ double operator()(uint32_t id) const { return v.ld(x0 + id * v.sb); }
 };
 
-// One pass over all constraints of this thread's problem.
+// The R warps that share 32 problems meet at a named barrier (ids 1..15, one per problem group of the CTA).
+__device__ __forceinline__ void group_sync(uint32_t bar_id, uint32_t bar_threads) {
+    __syncwarp();
+    asm volatile("barrier.sync %0, %1;" ::"r"(bar_id), "r"(bar_threads) : "memory");
+}
+
+// One pass over the constraints of this role's list for this thread's problem.  Lanes with `act` false run along
+// (the warp is uniform) but store nothing.
 //   RES: write weight*residual to V[rdst + row] and count Warning::Degenerate of Model::residual
 //   JAC: write the Jacobian values to V[jdst + slot]; degenerate rows are reported through jac_degen_any and
 //        counted by the caller only if the point is accepted (Model::refresh_jacobian runs only then)
 template <bool RES, bool JAC>
-__device__ __forceinline__ void eval_all(const SmallArgs& a, const DevCons* __restrict__ cons, const VView& V,
-                                         uint32_t rdst, uint32_t jdst, const double* __restrict__ prow,
-                                         uint32_t* __restrict__ degen_row, bool& res_degen_any, bool& jac_degen_any) {
+__device__ __forceinline__ void eval_list(const SmallArgs& a, const DevCons* __restrict__ cons, const uint32_t* __restrict__ list,
+                                          uint32_t n_list, const VView& V, uint32_t rdst, uint32_t jdst,
+                                          const double* __restrict__ prow, uint32_t* __restrict__ degen_row, bool act,
+                                          bool& res_degen_any, bool& jac_degen_any) {
     const SmemX X{V, a.X0 * V.sb};
 #pragma unroll 1
-    for (uint32_t c = 0; c < a.n_cons; ++c) {
+    for (uint32_t q = 0; q < n_list; ++q) {
+        // list entry: constraint index | rows << 16 | partials of row 0 << 20 | partials of row 1 << 24 (structure.cpp)
+        const uint32_t entry = list[q];
+        const uint32_t c = entry & 0xffffu, rows = (entry >> 16) & 3u;
         const DevCons& dc = cons[c];
         const uint32_t kind = dc.kind;
         uint32_t side = dc.flags;
@@ -98,31 +111,30 @@ __device__ __forceinline__ void eval_all(const SmallArgs& a, const DevCons* __re
         ezd::EvalOut o;
         ezd::eval_constraint<JAC>(kind, side, dc.ids, p0, dc.p1, X, o);
         const double w = dc.weight;
-        const uint32_t rows = c_rows[kind];
         if (RES) {
-            V.sts(rdst + dc.row0, w * o.res[0]);
-            if (rows == 2) V.sts(rdst + dc.row0 + 1, w * o.res[1]);
-            if (o.res_degen) {
+            V.stp(act, (rdst + dc.row0) * V.sb, w * o.res[0]);
+            if (rows == 2) V.stp(act, (rdst + dc.row0 + 1) * V.sb, w * o.res[1]);
+            if (o.res_degen && act) {
                 res_degen_any = true;
                 if (degen_row) degen_row[c] += 1;
             }
         }
         if (JAC) {
-            if (o.jac_degen) jac_degen_any = true;
+            if (o.jac_degen && act) jac_degen_any = true;
 #pragma unroll
             for (int row = 0; row < 2; ++row) {
                 if (row < (int)rows) {
-                    const uint32_t len = c_emit_len[kind][row];
+                    const uint32_t len = (entry >> (20 + 4 * row)) & 15u;
+                    // (leaves at the row's last partial — a uniform branch — instead of predicating eight stores off)
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
-                        if (k < (int)len) {
-                            const uint32_t s = dc.slot[row][k];
-                            const uint32_t off = (jdst + (s & ~kAccumulate)) * V.sb;
-                            if (s & kAccumulate) {
-                                if (o.emit[row]) V.st(off, V.ld(off) + w * o.pd[row][k]);
-                            } else {
-                                V.st(off, o.emit[row] ? 0.0 + w * o.pd[row][k] : 0.0);
-                            }
+                        if (k >= (int)len) break;
+                        const uint32_t s = dc.slot[row][k];
+                        const uint32_t off = (jdst + (s & ~kAccumulate)) * V.sb;
+                        if (s & kAccumulate) {
+                            if (o.emit[row]) V.stp(act, off, V.ld(off) + w * o.pd[row][k]);
+                        } else {
+                            V.stp(act, off, o.emit[row] ? 0.0 + w * o.pd[row][k] : 0.0);
                         }
                     }
                 }
@@ -132,11 +144,13 @@ __device__ __forceinline__ void eval_all(const SmallArgs& a, const DevCons* __re
 }
 
 // Warning::Degenerate bookkeeping of Model::refresh_jacobian (solver.rs:385-391) for an accepted point: only
-// run when some constraint was degenerate there and the caller asked for per-constraint counts.
-__device__ __noinline__ void count_jacobian_degenerates(const SmallArgs& a, const DevCons* __restrict__ cons, VView V,
+// run when some constraint of this role's list was degenerate there and the caller asked for per-constraint counts.
+__device__ __noinline__ void count_jacobian_degenerates(const SmallArgs& a, const DevCons* __restrict__ cons,
+                                                        const uint32_t* __restrict__ list, uint32_t n_list, VView V,
                                                         const double* __restrict__ prow, uint32_t* __restrict__ degen_row) {
     const SmemX X{V, a.X0 * V.sb};
-    for (uint32_t c = 0; c < a.n_cons; ++c) {
+    for (uint32_t q = 0; q < n_list; ++q) {
+        const uint32_t c = list[q] & 0xffffu;
         const DevCons& dc = cons[c];
         uint32_t side = dc.flags;
         if (dc.side_slot != 0xffffffffu) side = (uint32_t)V.lds(a.S0 + dc.side_slot);
@@ -146,21 +160,35 @@ __device__ __noinline__ void count_jacobian_degenerates(const SmallArgs& a, cons
     }
 }
 
-// The linear-algebra tape of one LM iteration: A = JtJ + lambda*I, b = -Jt r, A = L Lt, L y = b, Lt d = y.
-// Device format (32-bit words): per op a 4-word header {dst byte offset, pair count, code, fin byte offset}
-// followed by one {a, b} byte-offset pair per multiply-add.  Offsets are uniform across the warp; when the
-// tape sits in the constant bank (kernel parameter) the decode runs on the uniform datapath and an operand
-// access is a single LDS [thread base + uniform offset].
-// Returns true when a pivot was not positive and finite ("LltError::Numeric", newton.rs:96-99).
-__device__ __forceinline__ bool run_tape(const uint32_t* __restrict__ tape, uint32_t n_ops, const VView& V, double lambda) {
+// This role's share of the linear-algebra tape of one LM iteration: A = JtJ + lambda*I, b = -Jt r, A = L Lt, L y = b,
+// Lt d = y.  Per op a 4-word header {dst byte offset, pair count, code, fin byte offset} followed by one {a, b}
+// byte-offset pair per multiply-add (padded to 16 bytes); a header with OP_BARRIER is the meeting point of the roles in
+// front of an op that depends on another role's work.  Offsets are uniform across the warp, so an operand access is
+// LDS [thread base + uniform].
+// Returns true when a pivot of this role was not positive and finite ("LltError::Numeric", newton.rs:96-99).
+__device__ __forceinline__ bool run_role_tape(const uint32_t* __restrict__ tape, uint32_t n_ops, const VView& V, double lambda,
+                                              bool act, uint32_t bar_id, uint32_t bar_threads) {
     bool fail = false;
     uint32_t w = 0;  // 32-bit word index: keeps the loop control out of 64-bit pointer arithmetic
 #pragma unroll 1
     for (uint32_t op = 0; op < n_ops; ++op) {
-        const uint32_t dst = tape[w], np = tape[w + 1], code = tape[w + 2], fin = tape[w + 3];
+        const uint4 h = *reinterpret_cast<const uint4*>(tape + w);
+        const uint32_t dst = h.x, np = h.y, code = h.z, fin = h.w;
         w += 4;
+        if (code & OP_BARRIER) {
+            group_sync(bar_id, bar_threads);
+            continue;
+        }
         double acc = (code & OP_INIT_DST) ? V.ld(dst) : 0.0;
+        // (Rolled on purpose: the ops are short — 1.7 pairs on average for two_rectangles — and a switch over fully
+        // unrolled bodies with all operands requested up front measured 9 % slower, profiles/r02a_lm_small_roles.md.)
         const uint32_t we = w + 2 * np;
+        if (const uint32_t npos = (code >> OP_POS_SHIFT) & OP_POS_MASK) {  // the assembly of A[i][j] fused in front (structure.cpp)
+            const uint32_t wp = w + 2 * npos;
+#pragma unroll 1
+            for (; w < wp; w += 2) acc = __fma_rn(V.ld(tape[w]), V.ld(tape[w + 1]), acc);
+        }
+        if (code & OP_MID_LAMBDA) acc = __dadd_rn(acc, lambda);
         if (code & OP_NEGATE) {
 #pragma unroll 1
             for (; w < we; w += 2) acc = __fma_rn(-V.ld(tape[w]), V.ld(tape[w + 1]), acc);
@@ -168,6 +196,7 @@ __device__ __forceinline__ bool run_tape(const uint32_t* __restrict__ tape, uint
 #pragma unroll 1
             for (; w < we; w += 2) acc = __fma_rn(V.ld(tape[w]), V.ld(tape[w + 1]), acc);
         }
+        w += (np & 1u) << 1;
         const uint32_t fk = (code >> OP_FIN_SHIFT) & 3u;
         if (fk == OP_FIN_MUL) {
             acc = __dmul_rn(acc, V.ld(fin));
@@ -177,42 +206,60 @@ __device__ __forceinline__ bool run_tape(const uint32_t* __restrict__ tape, uint
             if (!(acc > 0.0) || !ezm::ez_isfinite(acc)) fail = true;
             acc = __ddiv_rn(1.0, __dsqrt_rn(acc));
         }
-        V.st(dst, acc);
+        V.stp(act, dst, acc);
     }
     return fail;
 }
 
-// The whole solve of one problem by one thread: newton.rs:29-145 + lib.rs:305-327.
-__device__ __forceinline__ void lm_small_body(const SmallArgs& a, const DevCons* __restrict__ cons,
-                                              const uint32_t* __restrict__ tape, const VView V, uint64_t b) {
-    const double* __restrict__ prow = a.params ? a.params + b * a.n_cons : nullptr;
-    uint32_t* __restrict__ degen_row = a.degen ? a.degen + b * a.n_cons : nullptr;
-    bool any_degen = false;
+// The whole solve of one problem — newton.rs:29-145 + lib.rs:305-327 — by the R threads (one per role warp) that share
+// its shared-memory column.  Every role runs the same control flow on the same values (the sums of squares, maxima and
+// verdicts are recomputed by each role from shared memory, which is cheaper than broadcasting them), so the roles take
+// every branch together; the work that scales — constraint evaluation, the tape, the copies — is split.  A lane whose
+// problem has finished (or failed a factorisation: newton.rs:96-99 `continue`) keeps running with its stores switched
+// off until every lane of the warp is done, which is what SIMT divergence would cost anyway and keeps the named
+// barriers aligned.
+__device__ __forceinline__ void lm_roles_body(const SmallArgs& a, const uint32_t* __restrict__ tb, const VView V, uint64_t b,
+                                              bool valid, uint32_t role, uint32_t bar_id) {
+    const uint32_t R = a.R, bar_threads = 32u * R;
+    const uint32_t* __restrict__ hdr = tb + role * kRoleHdrWords;
+    const DevCons* __restrict__ cons = reinterpret_cast<const DevCons*>(tb + a.cons_word);
+    const uint32_t* __restrict__ list = tb + hdr[0];
+    const uint32_t n_list = hdr[1];
+    const uint32_t* __restrict__ tape = tb + hdr[2];
+    const uint32_t n_ops = hdr[3];
+    const uint32_t x_lo = hdr[4], x_hi = hdr[5], r_lo = hdr[6], r_hi = hdr[7], j_lo = hdr[8], j_hi = hdr[9];
+    const double* __restrict__ prow = (valid && a.params) ? a.params + b * a.n_cons : nullptr;
+    uint32_t* __restrict__ degen_row = (valid && a.degen) ? a.degen + b * a.n_cons : nullptr;
     const uint32_t sb = V.sb;
     const uint32_t oX = a.X0 * sb, oR = a.R0 * sb, oRN = a.RN0 * sb, oJ = a.J0 * sb, oL = a.L0 * sb, oD = a.D0 * sb;
+    uint32_t* const flag = reinterpret_cast<uint32_t*>(V.base + a.F0 * sb);  // bit 0 degenerate, bits 1-2 failed pivot (by parity)
+    bool any_degen = false;
 
-    {  // initial guesses (lib.rs:275: values are positional == by id)
+    if (valid) {  // initial guesses (lib.rs:275: values are positional == by id)
         const double* __restrict__ g = a.guesses + b * a.n;
-        for (uint32_t j = 0; j < a.n; ++j) V.st(oX + j * sb, g[j]);
+        for (uint32_t j = x_lo; j < x_hi; ++j) V.st(oX + j * sb, g[j]);
     }
     if (degen_row)
-        for (uint32_t c = 0; c < a.n_cons; ++c) degen_row[c] = 0;
+        for (uint32_t q = 0; q < n_list; ++q) degen_row[list[q] & 0xffffu] = 0;
+    if (role == 0) *flag = 0u;
+    if (R > 1) group_sync(bar_id, bar_threads);
     {  // Constraint::set_from_initial_values (lib.rs:183-186)
         const SmemX X{V, oX};
-        for (uint32_t c = 0; c < a.n_cons; ++c) {
-            const DevCons& dc = cons[c];
+        for (uint32_t q = 0; q < n_list; ++q) {
+            const DevCons& dc = cons[list[q] & 0xffffu];
             if (dc.side_slot != 0xffffffffu)
-                V.sts(a.S0 + dc.side_slot, (double)ezd::resolve_side(dc.kind, dc.flags, dc.ids, X));
+                V.stp(valid, (a.S0 + dc.side_slot) * sb, (double)ezd::resolve_side(dc.kind, dc.flags, dc.ids, X));
         }
     }
 
     double lambda = a.initial_lambda;
     {
         bool rd = false, jd = false;
-        eval_all<true, true>(a, cons, V, a.R0, a.J0, prow, degen_row, rd, jd);
-        if (jd && degen_row) count_jacobian_degenerates(a, cons, V, prow, degen_row);
+        eval_list<true, true>(a, cons, list, n_list, V, a.R0, a.J0, prow, degen_row, valid, rd, jd);
+        if (jd && degen_row) count_jacobian_degenerates(a, cons, list, n_list, V, prow, degen_row);
         any_degen = rd || jd;
     }
+    if (R > 1) group_sync(bar_id, bar_threads);
     double S = 0.0;
     for (uint32_t i = 0; i < a.m; ++i) {
         const double r = V.ld(oR + i * sb);
@@ -221,6 +268,7 @@ __device__ __forceinline__ void lm_small_body(const SmallArgs& a, const DevCons*
     uint32_t iterations = a.max_iterations;
     bool converged = false;
     bool x_dirty = false;  // x was last modified by a rejected step: r no longer belongs to the bits of x
+    bool alive = valid;
 #pragma unroll 1
     for (uint32_t it = 0; it < a.max_iterations; ++it) {
         // max |r_i| with libm::fmax semantics (NaN-ignoring): NaN < x is false, so a NaN candidate never wins
@@ -230,54 +278,82 @@ __device__ __forceinline__ void lm_small_body(const SmallArgs& a, const DevCons*
             const double v = ezm::ez_abs(V.ld(oR + i * sb));
             largest = (largest < v || largest != largest) ? v : largest;
         }
-        if (largest <= a.residual_tolerance) {
+        if (alive && largest <= a.residual_tolerance) {
             iterations = it;
             converged = true;
-            break;
+            alive = false;
         }
-        if (run_tape(tape, a.n_ops, V, lambda)) {
-            lambda *= 10.0;
-            continue;
+        if (!__any_sync(0xffffffffu, alive)) break;  // (the same lanes in every role's warp: the roles leave together)
+        bool failed = run_role_tape(tape, n_ops, V, lambda, alive, bar_id, bar_threads);
+        if (R > 1) {  // a failed pivot of any role fails the factorisation for all of them
+            const uint32_t fbit = 2u << (it & 1u);
+            if (failed && alive) atomicOr(flag, fbit);
+            group_sync(bar_id, bar_threads);
+            const uint32_t f = *reinterpret_cast<volatile uint32_t*>(flag);
+            failed = (f & fbit) != 0u;
+            if (role == 0 && (f & (fbit ^ 6u))) atomicAnd(flag, ~(fbit ^ 6u));  // the other parity's bit: read an iteration ago
         }
+        const bool stepping = alive && !failed;
+        if (alive && failed) lambda *= 10.0;  // newton.rs:96-99: the iteration is spent, no step test
         double step = ezm::ez_abs(V.ld(oD));
         for (uint32_t j = 1; j < a.n; ++j) {
             const double v = ezm::ez_abs(V.ld(oD + j * sb));
             step = (step < v || step != step) ? v : step;
         }
-        for (uint32_t j = 0; j < a.n; ++j) V.st(oX + j * sb, V.ld(oX + j * sb) + V.ld(oD + j * sb));
+        for (uint32_t j = x_lo; j < x_hi; ++j) V.stp(stepping, oX + j * sb, V.ld(oX + j * sb) + V.ld(oD + j * sb));
+        if (R > 1) group_sync(bar_id, bar_threads);
         // One fused pass at the trial point: residuals into r_next and, speculatively, the Jacobian into the
         // (now dead) A/L region; an accepted step copies both over, a rejected one leaves r and J untouched,
         // exactly as Model::residual + refresh_jacobian do (newton.rs:115-131).
         bool rd = false, jd = false;
-        eval_all<true, true>(a, cons, V, a.RN0, a.L0, prow, degen_row, rd, jd);
+        eval_list<true, true>(a, cons, list, n_list, V, a.RN0, a.L0, prow, degen_row, stepping, rd, jd);
         any_degen = any_degen || rd;
+        if (R > 1) group_sync(bar_id, bar_threads);
         double S2 = 0.0;
         for (uint32_t i = 0; i < a.m; ++i) {
             const double r = V.ld(oRN + i * sb);
             S2 = S2 + r * r;
         }
-        if (S2 < S) {
-            for (uint32_t i = 0; i < a.m; ++i) V.st(oR + i * sb, V.ld(oRN + i * sb));
-            for (uint32_t k = 0; k < a.nnz; ++k) V.st(oJ + k * sb, V.ld(oL + k * sb));
+        const bool accept = stepping && (S2 < S);
+        const bool reject = stepping && !accept;
+        for (uint32_t i = r_lo; i < r_hi; ++i) V.stp(accept, oR + i * sb, V.ld(oRN + i * sb));
+        for (uint32_t k = j_lo; k < j_hi; ++k) V.stp(accept, oJ + k * sb, V.ld(oL + k * sb));
+        for (uint32_t j = x_lo; j < x_hi; ++j) V.stp(reject, oX + j * sb, V.ld(oX + j * sb) - V.ld(oD + j * sb));
+        if (accept) {
             if (jd) {
                 any_degen = true;
-                if (degen_row) count_jacobian_degenerates(a, cons, V, prow, degen_row);
+                if (degen_row) count_jacobian_degenerates(a, cons, list, n_list, V, prow, degen_row);
             }
             S = S2;
             lambda *= 0.1;
             x_dirty = false;
-        } else {
-            for (uint32_t j = 0; j < a.n; ++j) V.st(oX + j * sb, V.ld(oX + j * sb) - V.ld(oD + j * sb));
+        } else if (reject) {
             lambda *= 10.0;
             x_dirty = true;
         }
-        if (step <= a.step_tolerance) {
+        if (R > 1) group_sync(bar_id, bar_threads);
+        if (stepping && step <= a.step_tolerance) {
             iterations = it;
             converged = true;
-            break;
+            alive = false;
         }
     }
 
+    if (valid) {
+        double* __restrict__ f = a.finals + b * a.n;
+        for (uint32_t j = x_lo; j < x_hi; ++j) f[j] = V.ld(oX + j * sb);
+        if (a.jac) {  // Jacobian cached at the last accepted point (what freedom_analysis reads)
+            double* __restrict__ jo = a.jac + b * a.nnz;
+            for (uint32_t k = j_lo; k < j_hi; ++k) jo[k] = V.ld(oJ + k * sb);
+        }
+    }
+    if (R > 1) {
+        if (any_degen && valid) atomicOr(flag, 1u);
+        group_sync(bar_id, bar_threads);
+        if (role != 0) return;
+        any_degen = (*reinterpret_cast<volatile uint32_t*>(flag) & 1u) != 0u;
+    }
+    if (!valid) return;
     // lib.rs:305-327: unweighted residuals at the final point, |r| < 1e-4 per component.  When every weight
     // is 1.0 and x still holds the bits r was evaluated at, r IS that residual vector and is reused.
     bool any_unsat = false;
@@ -312,60 +388,30 @@ __device__ __forceinline__ void lm_small_body(const SmallArgs& a, const DevCons*
             }
         }
     }
-    {
-        double* __restrict__ f = a.finals + b * a.n;
-        for (uint32_t j = 0; j < a.n; ++j) f[j] = V.ld(oX + j * sb);
-    }
-    if (a.jac) {  // Jacobian cached at the last accepted point (what freedom_analysis reads)
-        double* __restrict__ jo = a.jac + b * a.nnz;
-        for (uint32_t k = 0; k < a.nnz; ++k) jo[k] = V.ld(oJ + k * sb);
-    }
     a.iterations[b] = iterations;
     a.status[b] = (uint8_t)((converged ? EZPZ_ST_CONVERGED : 0u) | (any_unsat ? EZPZ_ST_UNSATISFIED : 0u) |
                             (any_degen ? EZPZ_ST_DEGENERATE : 0u));
 }
 
-// Variant 1: constraint records and tape travel in the kernel parameter (constant bank).  NW 32-bit words.
-template <int NW>
-struct ConstBlob {
-    alignas(8) uint32_t w[NW];
-};
-template <int NW>
-__global__ void __launch_bounds__(256) lm_small_kernel_const(const __grid_constant__ SmallArgs a,
-                                                             const __grid_constant__ ConstBlob<NW> blob) {
+// Thread layout: warp w of the CTA = role (w % R) of problem group (w / R); lane l of that warp works on the problem in
+// shared-memory column group * 32 + l.  The tables (RoleBlob) sit in shared memory behind the per-problem state when they
+// fit (STAGED), else they are read from global memory through L1.  MAXT bounds the registers ptxas may use.
+template <bool STAGED, int MAXT>
+__global__ void __launch_bounds__(MAXT) lm_small_kernel(const SmallArgs a) {
     extern __shared__ double smem[];
-    const uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= a.batch) return;  // no block-wide barrier: every thread owns its shared-memory column
-    const DevCons* cons = reinterpret_cast<const DevCons*>(blob.w);
-    const uint32_t* tape = blob.w + a.n_cons * (uint32_t)(sizeof(DevCons) / 4);
-    const VView V{reinterpret_cast<char*>(smem + threadIdx.x), blockDim.x * 8u};
-    lm_small_body(a, cons, tape, V, b);
-}
-
-// Variant 2 (tables too large for the parameter space): staged in shared memory behind the per-problem
-// state when they fit (STAGED), else read from global memory through L1.
-template <bool STAGED>
-__global__ void __launch_bounds__(256) lm_small_kernel(const SmallArgs a) {
-    extern __shared__ double smem[];
-    const uint32_t stride = blockDim.x;
-    const DevCons* cons = a.cons;
-    const uint32_t* tape = a.tape;
+    const uint32_t* tb = a.tables;
     if (STAGED) {
-        double* tail = smem + (size_t)a.W * stride;
-        uint32_t* s_cons = reinterpret_cast<uint32_t*>(tail);
-        const uint32_t cons_words = a.n_cons * (uint32_t)(sizeof(DevCons) / 4);
-        uint32_t* s_tape = s_cons + cons_words;
-        const uint32_t* g_cons = reinterpret_cast<const uint32_t*>(a.cons);
-        for (uint32_t i = threadIdx.x; i < cons_words; i += blockDim.x) s_cons[i] = g_cons[i];
-        for (uint32_t i = threadIdx.x; i < a.tape_words; i += blockDim.x) s_tape[i] = a.tape[i];
+        uint32_t* s_tb = reinterpret_cast<uint32_t*>(smem + (size_t)a.W * a.T);
+        for (uint32_t i = threadIdx.x; i < a.table_words; i += blockDim.x) s_tb[i] = a.tables[i];
         __syncthreads();
-        cons = reinterpret_cast<const DevCons*>(s_cons);
-        tape = s_tape;
+        tb = s_tb;
     }
-    const uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= a.batch) return;
-    const VView V{reinterpret_cast<char*>(smem + threadIdx.x), stride * 8u};
-    lm_small_body(a, cons, tape, V, b);
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const uint32_t group = warp / a.R, role = warp - group * a.R;
+    const uint32_t col = group * 32u + lane;
+    const uint64_t b = (uint64_t)blockIdx.x * a.T + col;
+    const VView V{reinterpret_cast<char*>(smem + col), a.T * 8u};
+    lm_roles_body(a, tb, V, b, b < a.batch, role, 1u + group);
 }
 
 // ---- assembly over one system in global memory ----------------------------------------------------
@@ -495,43 +541,119 @@ int32_t ensure_pin(ezpz_context* ctx, size_t bytes, ezpz_error_detail_t* detail)
     return EZPZ_OK;
 }
 
-// The small-system tape in device format (see run_tape) for a given shared-memory stride: byte offsets
-// slot * stride * 8.  Built once per stride; kept on the host (for the kernel-parameter path) and on the device.
-int32_t get_scaled_tape(ezpz_context* ctx, const ezpz_structure* cs, DeviceCopy* d, uint32_t stride, ScaledTape** out,
-                        ezpz_error_detail_t* detail) {
+// The small program compiled for (roles, stride) — see build_role_blob in structure.cpp — with its device copy.  Built
+// once per pair and kept with the structure's device copy.
+int32_t get_role_tables(ezpz_context* ctx, const ezpz_structure* cs, DeviceCopy* d, uint32_t roles, uint32_t stride,
+                        RoleTables** out, ezpz_error_detail_t* detail) {
     ezpz_structure* s = const_cast<ezpz_structure*>(cs);
     std::lock_guard<std::mutex> lock(s->dev_mutex);
-    for (ScaledTape* t : d->tapes)
-        if (t->stride == stride) {
+    for (RoleTables* t : d->roles)
+        if (t->blob.stride == stride && t->blob.R == roles) {
             *out = t;
             return EZPZ_OK;
         }
-    const std::vector<uint32_t>& src = s->small.tape;
-    ScaledTape* t = new (std::nothrow) ScaledTape();
+    RoleTables* t = new (std::nothrow) RoleTables();
     if (!t) return EZPZ_ERR_INVALID_ARGUMENT;
-    t->stride = stride;
-    const uint32_t sb = stride * 8u;
-    size_t i = 0;
-    while (i < src.size()) {
-        const uint32_t h0 = src[i], h1 = src[i + 1];
-        const uint32_t np = h0 >> 16;
-        t->words.push_back((h0 & 0xffffu) * sb);
-        t->words.push_back(np);
-        t->words.push_back(h1 >> 16);
-        t->words.push_back((h1 & 0xffffu) * sb);
-        for (uint32_t k = 0; k < np; ++k) {
-            const uint32_t w = src[i + 2 + k];
-            t->words.push_back((w & 0xffffu) * sb);
-            t->words.push_back((w >> 16) * sb);
-        }
-        i += 2 + np;
-    }
+    build_role_blob(*s, roles, stride, t->blob);
     EZ_CUDA(cudaSetDevice(ctx->device), "cudaSetDevice");
-    EZ_CUDA(cudaMalloc(&t->dev, sizeof(uint32_t) * std::max<size_t>(1, t->words.size())), "cudaMalloc(tape)");
-    EZ_CUDA(cudaMemcpy(t->dev, t->words.data(), sizeof(uint32_t) * t->words.size(), cudaMemcpyHostToDevice), "cudaMemcpy(tape)");
-    d->tapes.push_back(t);
+    EZ_CUDA(cudaMalloc(&t->dev, sizeof(uint32_t) * std::max<size_t>(1, t->blob.words.size())), "cudaMalloc(role tables)");
+    EZ_CUDA(cudaMemcpy(t->dev, t->blob.words.data(), sizeof(uint32_t) * t->blob.words.size(), cudaMemcpyHostToDevice),
+            "cudaMemcpy(role tables)");
+    if (const char* dbg = std::getenv("EZPZ_B200_DEBUG"); dbg && dbg[0] == '1')
+        std::fprintf(stderr, "[small] roles %u stride %u: %zu table bytes, %u barriers per tape, busiest role %.0f %% of the tape\n", roles,
+                     stride, t->blob.words.size() * 4, t->blob.tape_barriers, 100.0 * t->blob.busiest_share);
+    d->roles.push_back(t);
     *out = t;
     return EZPZ_OK;
+}
+
+struct SmallShape {
+    uint32_t T = 0, R = 0;
+    size_t smem = 0;
+    bool stage = false;
+};
+
+// Launch shape of the batched kernel for `batch` problems of a structure (pure host arithmetic; the device's SM count
+// and shared memory per block are parameters so that tests can ask without a device).
+//   R  roles = warps that cooperate on 32 problems (EZPZ_B200_ROLES overrides): the per-problem state fills the SM's
+//      shared memory at ~5 warps' worth of problems, far too few independent instruction streams to cover the latency of
+//      the dependent LDS -> DFMA chains; R warps per problem group multiply the streams without multiplying the state.
+//      Candidates R = 1..4 are scored by problem groups resident per SM over the modelled time of the busiest role
+//      (RoleBlob::critical_cost): more roles shorten the critical path when the work splits, but every group then
+//      occupies R of the SM's 16 warps (128 registers per thread), so a structure with little state per problem — or a
+//      batch that fills the SMs anyway — is better served by more groups, and a batch too small to fill them by more roles.
+//   T  problems per CTA: as many groups of 32 as fit in shared memory next to the tables (at most 15: one named barrier per
+//      group), but no more than an even split of the batch over the SMs needs — a small batch spreads over all SMs
+//      instead of filling a few.
+int32_t small_shape_host(const ezpz_structure* cs, uint64_t batch, uint32_t sm_count, size_t smem_optin, SmallShape* out) {
+    static const uint32_t env_roles = [] {
+        const char* e = std::getenv("EZPZ_B200_ROLES");
+        return e ? (uint32_t)std::min(8l, std::max(0l, std::strtol(e, nullptr, 10))) : 0u;
+    }();
+    static const uint32_t max_threads = [] {
+        const char* e = std::getenv("EZPZ_B200_SMALL_THREADS");
+        return e ? (uint32_t)std::min(768l, std::max(32l, std::strtol(e, nullptr, 10))) : 512u;
+    }();
+    if (!cs->small.valid || sm_count == 0) return EZPZ_ERR_UNSUPPORTED;
+    ezpz_structure* s = const_cast<ezpz_structure*>(cs);
+    const size_t per_group = (size_t)cs->small.W * sizeof(double) * 32u;
+    const uint64_t n_groups = batch == ~0ull ? ~0ull : (batch + 31) / 32;
+    const uint64_t need = n_groups == ~0ull ? ~0ull : std::max<uint64_t>(1, (n_groups + sm_count - 1) / sm_count);  // groups per SM, one wave
+    uint32_t R = 0;
+    uint64_t g_max = 0;
+    size_t tables = 0;
+    bool stage = false;
+    double best = -1.0;
+    for (uint32_t cand = (env_roles ? env_roles : 1u); cand <= (env_roles ? env_roles : 4u); ++cand) {
+        // The size of the tables does not depend on the stride: a stride-1 blob, built once per R, tells it (and the model's cost).
+        const RoleBlob* probe = nullptr;
+        {
+            std::lock_guard<std::mutex> lock(s->dev_mutex);
+            for (const RoleBlob* p : s->role_probes)
+                if (p->R == cand) probe = p;
+            if (!probe) {
+                RoleBlob* p = new RoleBlob();
+                build_role_blob(*s, cand, 1u, *p);
+                s->role_probes.push_back(p);
+                probe = p;
+            }
+        }
+        const size_t tb = probe->words.size() * sizeof(uint32_t);
+        const bool stg = tb <= 64 * 1024 && per_group + tb <= smem_optin;
+        if (per_group > smem_optin) continue;
+        const size_t avail = smem_optin - (stg ? tb : 0);
+        const uint64_t g = std::min<uint64_t>({avail / per_group, (uint64_t)15, (uint64_t)(max_threads / (32u * cand))});
+        if (g < 1) continue;
+        // modelled time: critical path x waves the batch takes x slowdown per resident warp (0.6 % each: the warps of an SM
+        // share its issue slots and shared-memory pipe); an open-ended batch (chunk sizing) is scored by throughput
+        const double contention = 1.0 + 0.0059 * (double)(std::min(g, need) * cand);
+        const double waves = n_groups == ~0ull ? 1.0 / (double)g : (double)((n_groups + (uint64_t)sm_count * g - 1) / ((uint64_t)sm_count * g));
+        const double score = 1.0 / (probe->critical_cost * waves * contention);
+        if (score > best) {
+            best = score;
+            R = cand;
+            g_max = g;
+            tables = tb;
+            stage = stg;
+        }
+    }
+    if (R == 0) return EZPZ_ERR_TOO_LARGE;
+    uint64_t g = g_max;
+    if (n_groups != ~0ull) {
+        const uint64_t per_wave = (uint64_t)sm_count * g_max;
+        const uint64_t waves = std::max<uint64_t>(1, (n_groups + per_wave - 1) / per_wave);
+        const uint64_t slots = (uint64_t)sm_count * waves;
+        g = std::min<uint64_t>(g_max, std::max<uint64_t>(1, (n_groups + slots - 1) / slots));
+    }
+    out->T = (uint32_t)(32 * g);
+    out->R = R;
+    out->stage = stage;
+    out->smem = per_group * g + (stage ? tables : 0);
+    return EZPZ_OK;
+}
+
+int32_t small_shape(ezpz_context* ctx, const ezpz_structure* cs, uint64_t batch, SmallShape* out) {
+    return small_shape_host(cs, batch, (uint32_t)ctx->sm_count, ctx->smem_optin, out);
 }
 
 void release_device_copies(ezpz_structure* s) {
@@ -539,7 +661,7 @@ void release_device_copies(ezpz_structure* s) {
     for (DeviceCopy* d : s->dev) {
         if (cudaSetDevice(d->device) == cudaSuccess) {
             if (d->cons) cudaFree(d->cons);
-            for (ScaledTape* t : d->tapes) {
+            for (RoleTables* t : d->roles) {
                 if (t->dev) cudaFree(t->dev);
                 delete t;
             }
@@ -593,13 +715,11 @@ int32_t ezpz_b200_context_create(int32_t device, ezpz_context_t** out, ezpz_erro
         delete ctx;
         return rc;
     }
-    e = cudaFuncSetAttribute(lm_small_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
-    if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(lm_small_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
-    if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(lm_small_kernel_const<2040>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
-    if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(lm_small_kernel_const<7680>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
+    e = cudaSuccess;
+    for (const void* fn : {(const void*)lm_small_kernel<true, 384>, (const void*)lm_small_kernel<false, 384>,
+                           (const void*)lm_small_kernel<true, 512>, (const void*)lm_small_kernel<false, 512>,
+                           (const void*)lm_small_kernel<true, 768>, (const void*)lm_small_kernel<false, 768>})
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
     if (e != cudaSuccess) {
         cudaStreamDestroy(ctx->stream);
         delete ctx;
@@ -650,9 +770,16 @@ int32_t ezpz_b200_solve_batch_device(ezpz_context_t* ctx, const ezpz_structure_t
     int32_t rc = get_device_copy(ctx, s, &dc, detail);
     if (rc != EZPZ_OK) return rc;
     const SmallProgram& P = s->small;
+    SmallShape shape;
+    rc = small_shape(ctx, s, batch, &shape);
+    if (rc != EZPZ_OK) return rc;
+    RoleTables* tables = nullptr;
+    rc = get_role_tables(ctx, s, dc, shape.R, shape.T, &tables, detail);
+    if (rc != EZPZ_OK) return rc;
     SmallArgs a;
-    a.cons = dc->cons;
-    a.tape = nullptr;
+    a.tables = tables->dev;
+    a.table_words = (uint32_t)tables->blob.words.size();
+    a.cons_word = tables->blob.cons_word;
     a.guesses = io->guesses;
     a.params = io->params;
     a.finals = io->final_values;
@@ -678,82 +805,37 @@ int32_t ezpz_b200_solve_batch_device(ezpz_context_t* ctx, const ezpz_structure_t
     a.L0 = P.L0;
     a.D0 = P.D0;
     a.S0 = P.S0;
-    a.n_ops = P.n_ops;
+    a.F0 = P.F0;
     a.unsat_words = (s->n_cons + 31) / 32;
-    // Threads per block: as many problems as fit the shared memory of one SM, in whole warps, at most 256.
-    // The constraint records and the tape go, in order of preference, into the kernel parameter (constant
-    // bank), into shared memory behind the per-problem state, or stay in global memory.
-    const size_t per_thread = (size_t)P.W * sizeof(double);
-    const size_t cons_bytes = (size_t)s->n_cons * sizeof(DevCons);
-    size_t tape_words_v3 = 0;
-    {
-        const std::vector<uint32_t>& src = P.tape;
-        for (size_t i = 0; i < src.size(); i += 2 + (src[i] >> 16)) tape_words_v3 += 4 + 2 * (size_t)(src[i] >> 16);
-    }
-    const size_t tables = cons_bytes + tape_words_v3 * sizeof(uint32_t);
-    constexpr int kBlobSmall = 2040, kBlobLarge = 7680;  // words: 8,160 B and 30,720 B of the 32,764 B parameter space
-    // Measured on B200 (profiles/r01d): the shared-memory copy is faster than the constant bank here (indexed
-    // LDC has a longer dependent latency than a broadcast LDS and the per-thread loop exits keep the decode off
-    // the uniform datapath), so shared memory is preferred and the parameter path is the fallback.
-    const bool stage = tables <= 64 * 1024 && per_thread * 32 + tables <= ctx->smem_optin &&
-                       (ctx->smem_optin - tables) / per_thread >= 64;
-    const bool in_param = !stage && tables <= (size_t)kBlobLarge * 4;
-    const size_t avail = ctx->smem_optin - (stage ? tables : 0);
-    uint32_t T = (uint32_t)std::min<size_t>(256, avail / per_thread);
-    T = T / 32 * 32;
-    if (T < 32) return EZPZ_ERR_TOO_LARGE;
-    if (batch < T) T = (uint32_t)((batch + 31) / 32 * 32);
-    const size_t smem = per_thread * T + (stage ? tables : 0);
-    const uint64_t grid = (batch + T - 1) / T;
-    if (grid > 0x7fffffffull) return EZPZ_ERR_TOO_LARGE;
-    ScaledTape* tape = nullptr;
-    rc = get_scaled_tape(ctx, s, dc, T, &tape, detail);
-    if (rc != EZPZ_OK) return rc;
-    a.tape = tape->dev;
-    a.tape_words = (uint32_t)tape->words.size();
-    a.stage_in_smem = stage ? 1u : 0u;
+    a.T = shape.T;
+    a.R = shape.R;
     a.weights_one = s->all_weights_one ? 1u : 0u;
+    const uint64_t grid = (batch + shape.T - 1) / shape.T;
+    if (grid > 0x7fffffffull) return EZPZ_ERR_TOO_LARGE;
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
-    if (in_param) {
-        auto fill = [&](uint32_t* w) {
-            std::memcpy(w, s->dev_cons.data(), cons_bytes);
-            std::memcpy(w + cons_bytes / 4, tape->words.data(), tape->words.size() * 4);
-        };
-        if (tables <= (size_t)kBlobSmall * 4) {
-            static thread_local ConstBlob<kBlobSmall> blob;
-            fill(blob.w);
-            lm_small_kernel_const<kBlobSmall><<<(unsigned)grid, T, smem, st>>>(a, blob);
-        } else {
-            static thread_local ConstBlob<kBlobLarge> blob;
-            fill(blob.w);
-            lm_small_kernel_const<kBlobLarge><<<(unsigned)grid, T, smem, st>>>(a, blob);
-        }
-    } else if (stage) {
-        lm_small_kernel<true><<<(unsigned)grid, T, smem, st>>>(a);
-    } else {
-        lm_small_kernel<false><<<(unsigned)grid, T, smem, st>>>(a);
-    }
+    const unsigned threads = shape.T * shape.R;
+#define EZ_LAUNCH_SMALL(MAXT)                                                                            \
+    do {                                                                                                 \
+        if (shape.stage) lm_small_kernel<true, MAXT><<<(unsigned)grid, threads, shape.smem, st>>>(a);    \
+        else lm_small_kernel<false, MAXT><<<(unsigned)grid, threads, shape.smem, st>>>(a);               \
+    } while (0)
+    if (threads <= 384) EZ_LAUNCH_SMALL(384);
+    else if (threads <= 512) EZ_LAUNCH_SMALL(512);
+    else EZ_LAUNCH_SMALL(768);
+#undef EZ_LAUNCH_SMALL
     ctx->launches += 1;
     EZ_CUDA(cudaGetLastError(), "lm_small_kernel launch");
     return EZPZ_OK;
 }
 
-// Problems per full wave of the batched kernel on this device: one CTA per SM (the per-problem state fills the
-// SM's shared memory), T problems per CTA — the same T ezpz_b200_solve_batch_device picks for a large batch.
-static uint64_t small_wave_problems(const ezpz_context* ctx, const ezpz_structure* s) {
-    const SmallProgram& P = s->small;
-    if (!P.valid) return 0;
-    const size_t per_thread = (size_t)P.W * sizeof(double);
-    size_t tape_words_v3 = 0;
-    for (size_t i = 0; i < P.tape.size(); i += 2 + (P.tape[i] >> 16)) tape_words_v3 += 4 + 2 * (size_t)(P.tape[i] >> 16);
-    const size_t tables = (size_t)s->n_cons * sizeof(DevCons) + tape_words_v3 * sizeof(uint32_t);
-    const bool stage = tables <= 64 * 1024 && per_thread * 32 + tables <= ctx->smem_optin &&
-                       (ctx->smem_optin - tables) / per_thread >= 64;
-    const size_t avail = ctx->smem_optin - (stage ? tables : 0);
-    const uint32_t T = (uint32_t)std::min<size_t>(256, avail / per_thread) / 32 * 32;
-    if (T < 32) return 0;
-    const size_t ctas_per_sm = std::max<size_t>(1, ctx->smem_optin / (per_thread * T + (stage ? tables : 0)));
-    return (uint64_t)ctx->sm_count * T * ctas_per_sm;
+// Problems per full wave of the batched kernel on this device (the chunks of the copy/compute pipeline are whole waves).
+static uint64_t small_wave_problems(ezpz_context* ctx, const ezpz_structure* s) {
+    if (!s->small.valid) return 0;
+    SmallShape shape;
+    if (small_shape(ctx, s, ~0ull, &shape) != EZPZ_OK) return 0;
+    const size_t by_smem = std::max<size_t>(1, ctx->smem_optin / std::max<size_t>(1, shape.smem));
+    const size_t by_threads = std::max<size_t>(1, 2048 / (shape.T * shape.R));
+    return (uint64_t)ctx->sm_count * shape.T * std::min(by_smem, by_threads);
 }
 
 int32_t ezpz_b200_solve_batch(ezpz_context_t* ctx, const ezpz_structure_t* s, const ezpz_config_t* config,
@@ -940,6 +1022,17 @@ int32_t ezpz_b200_eval(ezpz_context_t* ctx, const ezpz_structure_t* s, const dou
     }
     if (degen) EZ_CUDA(cudaMemcpyAsync(degen, d_d, nc, cudaMemcpyDeviceToHost, st), "D2H degen");
     EZ_CUDA(cudaStreamSynchronize(st), "cudaStreamSynchronize");
+    return EZPZ_OK;
+}
+
+int32_t ezpz_b200_structure_batch_shape(const ezpz_structure_t* s, uint64_t batch, uint32_t sm_count, uint64_t smem_per_block,
+                                        uint32_t* roles, uint32_t* problems_per_cta) {
+    if (!s) return EZPZ_ERR_INVALID_ARGUMENT;
+    SmallShape shape;
+    const int32_t rc = ezs::small_shape_host(s, batch, sm_count, (size_t)smem_per_block, &shape);
+    if (rc != EZPZ_OK) return rc;
+    if (roles) *roles = shape.R;
+    if (problems_per_cta) *problems_per_cta = shape.T;
     return EZPZ_OK;
 }
 

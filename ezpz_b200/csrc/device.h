@@ -11,18 +11,17 @@
 
 namespace ezs {
 
-// The small-system op tape in device format for one shared-memory stride (threads per CTA).
-struct ScaledTape {
-    uint32_t stride = 0;
-    std::vector<uint32_t> words;  // host copy (kernel-parameter path)
-    uint32_t* dev = nullptr;      // device copy (shared-memory / global paths)
+// The small program compiled for one (roles, shared-memory stride) pair (structure.h: RoleBlob) with its device copy.
+struct RoleTables {
+    RoleBlob blob;
+    uint32_t* dev = nullptr;
 };
 
 // Device-resident copy of an analysed structure (one per CUDA device, created lazily).
 struct DeviceCopy {
     int device = -1;
     DevCons* cons = nullptr;         // [n_cons]
-    std::vector<ScaledTape*> tapes;  // one per stride used so far
+    std::vector<RoleTables*> roles;  // one per (roles, stride) used so far
     uint32_t* csc_to_csr = nullptr;  // [nnz] position in CSR order of each CSC entry
     void* large = nullptr;           // LargeDevice (large.cu), created on first use
 };

@@ -139,6 +139,11 @@ struct TapeBuilder {
         t[head] += 1u << 16;
         ++n_pairs;
     }
+    // The `count` pairs pushed so far are ADDED whatever OP_NEGATE says (the assembly of A inside a factorisation op),
+    // and lambda is added behind them when `lambda` is set.  The count travels in bits 8..14 of the code.
+    void positive(uint32_t count, bool lambda) {
+        t[head + 1] |= ((count & OP_POS_MASK) << OP_POS_SHIFT | (lambda ? (uint32_t)OP_MID_LAMBDA : 0u)) << 16;
+    }
 };
 
 constexpr uint32_t kMaxSymbolicVars = 200000;
@@ -155,7 +160,7 @@ void build_small_program(ezpz_structure& S) {
     // The A/L region doubles as the buffer of the trial point's Jacobian (the factor is dead by the time the
     // tentative step is evaluated), so it is sized for whichever is larger.
     const uint32_t lt = std::max(nnz_l, nnz_j);
-    const uint64_t W = (uint64_t)n + 2ull * m + nnz_j + lt + n + S.n_side;
+    const uint64_t W = (uint64_t)n + 2ull * m + nnz_j + lt + n + S.n_side + 1;
     if (W > kMaxSmallW || n == 0) return;
     P.X0 = 0;
     P.R0 = n;
@@ -165,6 +170,7 @@ void build_small_program(ezpz_structure& S) {
     P.D0 = P.L0 + lt;
     P.S0 = P.D0 + n;
     P.n_side = S.n_side;
+    P.F0 = P.S0 + S.n_side;
     P.W = (uint32_t)W;
     TapeBuilder tb(P.tape);
 
@@ -179,42 +185,55 @@ void build_small_program(ezpz_structure& S) {
         for (uint32_t p = S.l_col_ptr[j] + 1; p < S.l_col_ptr[j + 1]; ++p) lrow[S.l_row_idx[p]].push_back({j, P.L0 + p});
     }
 
-    // (1) A = JtJ + lambda*I into the L slots; structural fill entries become +0.0.
-    for (uint32_t j = 0; j < n; ++j) {
-        uint32_t ap = S.a_col_ptr[j];
-        const uint32_t ae = S.a_col_ptr[j + 1];
-        for (uint32_t p = S.l_col_ptr[j]; p < S.l_col_ptr[j + 1]; ++p) {
-            const uint32_t i = S.l_row_idx[p];
-            tb.begin(P.L0 + p, 0u, i == j ? OP_FIN_LAMBDA : OP_FIN_NONE, 0u);
-            while (ap < ae && S.a_row_idx[ap] < i) ++ap;
-            if (ap < ae && S.a_row_idx[ap] == i) {
-                // rows shared by columns i and j of J, ascending
-                uint32_t pi = S.csc_col_ptr[i], pie = S.csc_col_ptr[i + 1];
-                uint32_t pj = S.csc_col_ptr[j], pje = S.csc_col_ptr[j + 1];
-                while (pi < pie && pj < pje) {
-                    const uint32_t ri = S.csc_row_idx[pi], rj = S.csc_row_idx[pj];
-                    if (ri == rj) {
-                        tb.pair(P.J0 + pi, P.J0 + pj);
-                        ++pi;
-                        ++pj;
-                    } else if (ri < rj) ++pi;
-                    else ++pj;
-                }
-            }
+    // The tape fuses what the reference does in separate passes wherever a value has exactly one consumer — same
+    // operations in the same order, without the store, the reload and the second op header in between:
+    //   A[i][j] = sum_r J[r][i] J[r][j] (+ lambda on the diagonal) is only ever read by the factorisation op of L[i][j]
+    //   (left-looking Cholesky), so that op starts with A's products (added, from +0.0), adds lambda, and goes on
+    //   subtracting the L[i][k] L[j][k];  b[i] = sum_r fma(-J[r][i], r[r]) is only read by the forward substitution op of
+    //   y[i], which therefore starts with b's products.
+    auto in_a = [&](uint32_t i, uint32_t j) {  // is (i, j), i >= j, an entry of lower(A)? (fill entries of L are not)
+        const uint32_t* b = S.a_row_idx.data() + S.a_col_ptr[j];
+        const uint32_t* e = S.a_row_idx.data() + S.a_col_ptr[j + 1];
+        return std::binary_search(b, e, i);
+    };
+    auto a_products = [&](uint32_t i, uint32_t j, bool emit) {  // rows shared by columns i and j of J, ascending
+        uint32_t count = 0;
+        uint32_t pi = S.csc_col_ptr[i], pie = S.csc_col_ptr[i + 1];
+        uint32_t pj = S.csc_col_ptr[j], pje = S.csc_col_ptr[j + 1];
+        while (pi < pie && pj < pje) {
+            const uint32_t ri = S.csc_row_idx[pi], rj = S.csc_row_idx[pj];
+            if (ri == rj) {
+                if (emit) tb.pair(P.J0 + pi, P.J0 + pj);
+                ++count;
+                ++pi;
+                ++pj;
+            } else if (ri < rj) ++pi;
+            else ++pj;
         }
-    }
-    // (2) b = Jt * (-r) into d
+        return count;
+    };
+    // Opens the factorisation op of L entry (i, j) at `slot` with the assembly of A[i][j] fused in front; an entry with
+    // more products than the header can count (OP_POS_MASK) gets its assembly as an op of its own, as the reference does.
+    auto begin_entry = [&](uint32_t slot, uint32_t i, uint32_t j, uint32_t fin_kind, uint32_t fin_slot) {
+        const bool has_a = i == j || in_a(i, j);
+        const uint32_t count = has_a ? a_products(i, j, false) : 0u;
+        if (count > OP_POS_MASK) {
+            tb.begin(slot, 0u, i == j ? OP_FIN_LAMBDA : OP_FIN_NONE, 0u);
+            a_products(i, j, true);
+            tb.begin(slot, OP_INIT_DST | OP_NEGATE, fin_kind, fin_slot);
+            return;
+        }
+        tb.begin(slot, OP_NEGATE, fin_kind, fin_slot);
+        if (has_a) a_products(i, j, true);
+        tb.positive(count, i == j);
+    };
+    // (1)+(3) A = JtJ + lambda*I and its left-looking Cholesky, column by column: pivot, then the sub-diagonal entries
     for (uint32_t j = 0; j < n; ++j) {
-        tb.begin(P.D0 + j, OP_NEGATE, OP_FIN_NONE, 0u);
-        for (uint32_t p = S.csc_col_ptr[j]; p < S.csc_col_ptr[j + 1]; ++p) tb.pair(P.J0 + p, P.R0 + S.csc_row_idx[p]);
-    }
-    // (3) left-looking Cholesky, column by column: pivot, then the sub-diagonal entries
-    for (uint32_t j = 0; j < n; ++j) {
-        tb.begin(diag_slot[j], OP_INIT_DST | OP_NEGATE, OP_FIN_PIVOT, 0u);
+        begin_entry(diag_slot[j], j, j, OP_FIN_PIVOT, 0u);
         for (const RowEnt& e : lrow[j]) tb.pair(e.slot, e.slot);
         for (uint32_t p = S.l_col_ptr[j] + 1; p < S.l_col_ptr[j + 1]; ++p) {
             const uint32_t i = S.l_row_idx[p];
-            tb.begin(P.L0 + p, OP_INIT_DST | OP_NEGATE, OP_FIN_MUL, diag_slot[j]);
+            begin_entry(P.L0 + p, i, j, OP_FIN_MUL, diag_slot[j]);
             // k < j present in both row i and row j, ascending
             const auto& ri = lrow[i];
             const auto& rj = lrow[j];
@@ -229,9 +248,10 @@ void build_small_program(ezpz_structure& S) {
             }
         }
     }
-    // (4) forward substitution L y = b (in place in d)
+    // (2)+(4) b = Jt * (-r) and the forward substitution L y = b (into d)
     for (uint32_t i = 0; i < n; ++i) {
-        tb.begin(P.D0 + i, OP_INIT_DST | OP_NEGATE, OP_FIN_MUL, diag_slot[i]);
+        tb.begin(P.D0 + i, OP_NEGATE, OP_FIN_MUL, diag_slot[i]);
+        for (uint32_t p = S.csc_col_ptr[i]; p < S.csc_col_ptr[i + 1]; ++p) tb.pair(P.J0 + p, P.R0 + S.csc_row_idx[p]);
         for (const RowEnt& e : lrow[i]) tb.pair(e.slot, P.D0 + e.col);
     }
     // (5) backward substitution Lt d = y, rows of every column DESCENDING (on the large path this lets the
@@ -246,6 +266,216 @@ void build_small_program(ezpz_structure& S) {
     P.valid = true;
 }
 
+
+// Relative cost of evaluating one constraint of each kind (residual + Jacobian), in units of a trivial kind; only used to
+// balance the constraint lists of the roles.
+constexpr uint8_t kEvalCost[EZPZ_K_COUNT] = {16, 12, 8, 9, 1, 1, 1, 1, 20, 1, 1, 2, 1, 16, 16, 16, 2, 20, 12, 12, 30, 50, 30, 20, 24};
+// ... in units of the tape's cost model: a flat part per constraint plus a little per unit of formula.
+constexpr uint32_t eval_cost(uint32_t kind) { return 100u + 3u * kEvalCost[kind]; }
+
+}  // namespace
+
+namespace ezs {
+
+// Compiles the sequential small program for R cooperating warps (see RoleBlob in structure.h).
+//   * constraints: longest-processing-time partition by kEvalCost; a constraint's residual rows and Jacobian entries
+//     belong to it alone, so the lists are independent.
+//   * tape: ops without a dependency inside the tape (the assembly of A and of the right-hand side) are dealt over all
+//     roles; the factorisation and the two substitutions go to the role that owns the connected component of their variable
+//     (components of the graph of A are independent linear systems), the components being dealt over the roles by cost.
+//     A single-component system therefore factorises on one role while the others wait.
+//   * barriers: ops are emitted in the order of the sequential tape (a topological order); whenever an op reads or
+//     overwrites a slot that ANOTHER role wrote or read since the last barrier, a barrier is put in front of it in every
+//     role's tape.  Hazards inside one role are ordered by that role's program order.
+void build_role_blob(const ezpz_structure& S, uint32_t R, uint32_t stride, RoleBlob& out) {
+    const SmallProgram& P = S.small;
+    out = RoleBlob();
+    out.R = R;
+    out.stride = stride;
+    const uint32_t n = S.n, m = S.m, nc = S.n_cons;
+    const uint32_t nnz_j = (uint32_t)S.csc_row_idx.size();
+    const uint32_t sb = stride * 8u;
+    // ---- constraint lists
+    std::vector<std::vector<uint32_t>> clist(R);
+    {
+        std::vector<uint32_t> order(nc);
+        std::iota(order.begin(), order.end(), 0u);
+        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return eval_cost(S.cons[a].kind) > eval_cost(S.cons[b].kind); });
+        std::vector<uint64_t> load(R, 0);
+        for (uint32_t c : order) {
+            const uint32_t r = (uint32_t)(std::min_element(load.begin(), load.end()) - load.begin());
+            load[r] += eval_cost(S.cons[c].kind);
+            clist[r].push_back(c);
+        }
+        for (auto& l : clist) std::sort(l.begin(), l.end());
+    }
+    // ---- ops of the sequential tape
+    struct Op {
+        uint32_t dst, fin, code, np;
+        size_t pairs;  // index of the first pair word in P.tape
+        uint32_t role = 0;
+        uint32_t cost() const { return 34 + 17 * np; }  // measured, see critical_cost below
+    };
+    std::vector<Op> ops;
+    for (size_t i = 0; i < P.tape.size();) {
+        const uint32_t h0 = P.tape[i], h1 = P.tape[i + 1];
+        Op o;
+        o.dst = h0 & 0xffffu;
+        o.np = h0 >> 16;
+        o.fin = h1 & 0xffffu;
+        o.code = h1 >> 16;
+        o.pairs = i + 2;
+        ops.push_back(o);
+        i += 2 + o.np;
+    }
+    const uint32_t W = P.W;
+    auto reads_of = [&](const Op& o, std::vector<uint32_t>& rd) {
+        rd.clear();
+        if (o.code & OP_INIT_DST) rd.push_back(o.dst);
+        if (((o.code >> OP_FIN_SHIFT) & 3u) == OP_FIN_MUL) rd.push_back(o.fin);
+        for (uint32_t k = 0; k < o.np; ++k) {
+            rd.push_back(P.tape[o.pairs + k] & 0xffffu);
+            rd.push_back(P.tape[o.pairs + k] >> 16);
+        }
+    };
+    // level 0 = no dependency on an earlier op of the tape
+    std::vector<uint8_t> written(W, 0), was_read(W, 0), level0(ops.size(), 0);
+    std::vector<uint32_t> rd;
+    for (size_t k = 0; k < ops.size(); ++k) {
+        reads_of(ops[k], rd);
+        bool dep = written[ops[k].dst] || was_read[ops[k].dst];
+        for (uint32_t s : rd) dep = dep || written[s];
+        level0[k] = dep ? 0 : 1;
+        for (uint32_t s : rd) was_read[s] = 1;
+        written[ops[k].dst] = 1;
+    }
+    // component of the variable an op's destination belongs to
+    std::vector<uint32_t> var_of_slot(W, UINT32_MAX);
+    for (uint32_t j = 0; j < n; ++j) {
+        var_of_slot[P.D0 + j] = j;
+        for (uint32_t p = S.l_col_ptr[j]; p < S.l_col_ptr[j + 1]; ++p) var_of_slot[P.L0 + p] = j;
+    }
+    std::vector<uint64_t> comp_cost(std::max<uint32_t>(1, S.n_components), 0);
+    for (size_t k = 0; k < ops.size(); ++k)
+        if (!level0[k] && var_of_slot[ops[k].dst] != UINT32_MAX) comp_cost[S.comp_of[var_of_slot[ops[k].dst]]] += ops[k].cost();
+    std::vector<uint32_t> comp_role(comp_cost.size(), 0);
+    std::vector<uint64_t> load(R, 0);
+    {
+        std::vector<uint32_t> order(comp_cost.size());
+        std::iota(order.begin(), order.end(), 0u);
+        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return comp_cost[a] > comp_cost[b]; });
+        for (uint32_t c : order) {
+            const uint32_t r = (uint32_t)(std::min_element(load.begin(), load.end()) - load.begin());
+            load[r] += comp_cost[c];
+            comp_role[c] = r;
+        }
+    }
+    {   // level-0 ops on top of that, largest first, to the least loaded role
+        std::vector<uint32_t> order;
+        for (size_t k = 0; k < ops.size(); ++k)
+            if (level0[k]) order.push_back((uint32_t)k);
+        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return ops[a].cost() > ops[b].cost(); });
+        std::vector<uint64_t> l0(R, 0);
+        for (uint32_t k : order) {
+            const uint32_t r = (uint32_t)(std::min_element(l0.begin(), l0.end()) - l0.begin());
+            l0[r] += ops[k].cost();
+            ops[k].role = r;
+        }
+        for (uint32_t r = 0; r < R; ++r) load[r] += l0[r];
+    }
+    for (size_t k = 0; k < ops.size(); ++k)
+        if (!level0[k]) ops[k].role = var_of_slot[ops[k].dst] == UINT32_MAX ? 0u : comp_role[S.comp_of[var_of_slot[ops[k].dst]]];
+    {
+        const uint64_t total = std::accumulate(load.begin(), load.end(), (uint64_t)0);
+        out.busiest_share = total ? (double)*std::max_element(load.begin(), load.end()) / (double)total : 1.0;
+    }
+    // ---- emission with barrier insertion
+    std::vector<std::vector<uint32_t>> tape(R);
+    std::vector<uint32_t> n_ops(R, 0);
+    constexpr uint32_t kNone = UINT32_MAX;
+    std::vector<uint32_t> w_role(W, kNone), w_epoch(W, 0);  // last writer of a slot: role, epoch
+    std::vector<uint32_t> r_mask(W, 0), r_epoch(W, 0);      // roles that read a slot in epoch r_epoch
+    uint32_t epoch = 1;
+    for (const Op& o : ops) {
+        reads_of(o, rd);
+        bool hazard = false;
+        for (uint32_t s : rd) hazard = hazard || (w_role[s] != kNone && w_role[s] != o.role && w_epoch[s] == epoch);      // RAW
+        hazard = hazard || (w_role[o.dst] != kNone && w_role[o.dst] != o.role && w_epoch[o.dst] == epoch);                // WAW
+        hazard = hazard || (r_epoch[o.dst] == epoch && (r_mask[o.dst] & ~(1u << o.role)) != 0);                           // WAR
+        if (hazard) {
+            ++epoch;
+            ++out.tape_barriers;
+            for (uint32_t r = 0; r < R; ++r) {
+                tape[r].insert(tape[r].end(), {0u, 0u, (uint32_t)OP_BARRIER, 0u});
+                ++n_ops[r];
+            }
+        }
+        std::vector<uint32_t>& t = tape[o.role];
+        t.insert(t.end(), {o.dst * sb, o.np, o.code, o.fin * sb});
+        for (uint32_t k = 0; k < o.np; ++k) {
+            const uint32_t w = P.tape[o.pairs + k];
+            t.push_back((w & 0xffffu) * sb);
+            t.push_back((w >> 16) * sb);
+        }
+        if (o.np & 1u) t.insert(t.end(), {0u, 0u});  // every header on 16 bytes: the device reads headers and pairs as 128-bit words
+        ++n_ops[o.role];
+        for (uint32_t s : rd) {
+            if (r_epoch[s] != epoch) {
+                r_epoch[s] = epoch;
+                r_mask[s] = 0;
+            }
+            r_mask[s] |= 1u << o.role;
+        }
+        w_role[o.dst] = o.role;
+        w_epoch[o.dst] = epoch;
+    }
+    {   // Cost model fitted to the measured kernel times of 8 structures x 1..4 roles on B200 (4.7 % rms,
+        // profiles/r02a_lm_small_roles.md): 34 per op + 17 per multiply-add, ~112 per constraint almost whatever its kind
+        // (record load, dispatch and scatter outweigh the formulas), 19.5 per element of the three folds every role
+        // repeats, 14 per barrier.
+        std::vector<uint64_t> tcost(R, 0), ecost(R, 0);
+        for (const Op& o : ops) tcost[o.role] += o.cost();
+        for (uint32_t r = 0; r < R; ++r)
+            for (uint32_t c : clist[r]) ecost[r] += eval_cost(S.cons[c].kind);
+        double crit = 0.0;
+        for (uint32_t r = 0; r < R; ++r) crit = std::max(crit, (double)tcost[r] + (double)ecost[r]);
+        out.critical_cost = crit + 19.5 * (2.0 * m + n) + (R > 1 ? 14.0 * (4 + out.tape_barriers) : 0.0);
+    }
+    // ---- the blob
+    std::vector<uint32_t>& w = out.words;
+    w.assign((size_t)kRoleHdrWords * R, 0u);
+    out.cons_word = (uint32_t)w.size();
+    w.resize(w.size() + (size_t)nc * (sizeof(DevCons) / 4));
+    if (nc) std::memcpy(w.data() + out.cons_word, S.dev_cons.data(), (size_t)nc * sizeof(DevCons));
+    auto split = [&](uint32_t total, uint32_t r, uint32_t& lo, uint32_t& hi) {
+        lo = (uint32_t)((uint64_t)total * r / R);
+        hi = (uint32_t)((uint64_t)total * (r + 1) / R);
+    };
+    for (uint32_t r = 0; r < R; ++r) {
+        uint32_t* h = nullptr;
+        const uint32_t cons_off = (uint32_t)w.size();
+        for (uint32_t c : clist[r]) {  // constraint index + what the scatter loop needs to know about its kind
+            const ezk::KindInfo& ki = ezk::kKinds[S.cons[c].kind];
+            w.push_back(c | (uint32_t)ki.rows << 16 | (uint32_t)ki.emit_len[0] << 20 | (uint32_t)ki.emit_len[1] << 24);
+        }
+        while (w.size() & 3u) w.push_back(0u);  // tapes start on 16 bytes
+        const uint32_t tape_off = (uint32_t)w.size();
+        w.insert(w.end(), tape[r].begin(), tape[r].end());
+        h = w.data() + (size_t)kRoleHdrWords * r;
+        h[0] = cons_off;
+        h[1] = (uint32_t)clist[r].size();
+        h[2] = tape_off;
+        h[3] = n_ops[r];
+        split(n, r, h[4], h[5]);
+        split(m, r, h[6], h[7]);
+        split(nnz_j, r, h[8], h[9]);
+    }
+    while (w.size() & 3u) w.push_back(0u);
+}
+
+}  // namespace ezs
+
+namespace {
 
 // Programme of the single-large-system path: assembly processing order, value-array layout, and the sparse
 // direct schedule (sparse_direct.cpp).
@@ -511,6 +741,7 @@ int32_t ezpz_b200_structure_create(const ezpz_constraint_t* cons, uint32_t n_con
 void ezpz_b200_structure_destroy(ezpz_structure_t* s) {
     if (!s) return;
     release_device_copies(s);
+    for (ezs::RoleBlob* p : s->role_probes) delete p;
     delete s;
 }
 
@@ -560,6 +791,24 @@ int32_t ezpz_b200_structure_ordering(const ezpz_structure_t* s, int32_t* path, c
     if (nnz_l) *nnz_l = direct ? P.nnz_l : 0;
     // large.cu: single-CTA systems (n + m + nnz <= 4,096) fold sequentially, larger ones (cluster or grid) in chunks of 1,024
     if (sum_chunk) *sum_chunk = P.built ? ezs::sum_chunk_for(s->n, s->m, s->csc_row_idx.size()) : 0u;
+    return EZPZ_OK;
+}
+
+int32_t ezpz_b200_structure_role_program(const ezpz_structure_t* s, uint32_t roles, uint32_t stride, uint32_t* words,
+                                         uint64_t cap, uint64_t* n_words, uint32_t* cons_word, uint32_t* dims) {
+    if (!s || roles == 0 || roles > 8 || stride == 0) return EZPZ_ERR_INVALID_ARGUMENT;
+    if (!s->small.valid) return EZPZ_ERR_UNSUPPORTED;
+    RoleBlob blob;
+    build_role_blob(*s, roles, stride, blob);
+    if (n_words) *n_words = blob.words.size();
+    if (cons_word) *cons_word = blob.cons_word;
+    if (dims) {
+        dims[0] = s->small.W;
+        dims[1] = s->n_cons;
+        dims[2] = blob.tape_barriers;
+        dims[3] = (uint32_t)blob.critical_cost;
+    }
+    if (words) std::memcpy(words, blob.words.data(), sizeof(uint32_t) * (size_t)std::min<uint64_t>(cap, blob.words.size()));
     return EZPZ_OK;
 }
 

@@ -13,6 +13,8 @@
 
 #include "../../include/ezpz_b200.h"
 
+struct ezpz_structure;
+
 namespace ezs {
 
 // Analysed constraint as the device reads it (112 bytes, 16-byte aligned).
@@ -33,7 +35,10 @@ enum : uint32_t {
     OP_INIT_DST = 1u,   // acc starts from V[dst] instead of +0.0
     OP_NEGATE = 2u,     // acc = fma(-V[a], V[b], acc) instead of fma(V[a], V[b], acc)
     OP_FIN_SHIFT = 2u,  // bits 2..3: 0 none, 1 acc += lambda, 2 acc *= V[fin], 3 pivot: fail unless acc > 0, acc = 1/sqrt(acc)
-    OP_FIN_NONE = 0u, OP_FIN_LAMBDA = 1u, OP_FIN_MUL = 2u, OP_FIN_PIVOT = 3u
+    OP_FIN_NONE = 0u, OP_FIN_LAMBDA = 1u, OP_FIN_MUL = 2u, OP_FIN_PIVOT = 3u,
+    OP_BARRIER = 16u,   // (role tapes only) not an op: the roles of a problem group synchronise here
+    OP_MID_LAMBDA = 32u,  // acc += lambda after the leading positive pairs (diagonal of A inside its pivot op)
+    OP_POS_SHIFT = 8u, OP_POS_MASK = 0x7fu  // bits 8..14: how many leading pairs are added although OP_NEGATE is set
 };
 
 // The batched small-system program: slot map of the per-problem value array V and the op tape.
@@ -41,11 +46,37 @@ struct SmallProgram {
     bool valid = false;       // false when the system does not fit the thread-per-problem kernel
     uint32_t W = 0;           // doubles per problem
     uint32_t X0 = 0, R0 = 0, RN0 = 0, J0 = 0, L0 = 0, D0 = 0, S0 = 0;
+    uint32_t F0 = 0;          // one slot of flags shared by the warps that cooperate on a problem (device.cu)
     uint32_t n_side = 0;
     uint32_t n_ops = 0;       // ops executed per LM iteration (assemble, rhs, factor, forward, backward)
     uint64_t n_pairs = 0;     // multiply-add pairs per LM iteration
     std::vector<uint32_t> tape;
 };
+
+// The small program compiled for R cooperating warps ("roles") per 32 problems and one shared-memory stride: what
+// lm_roles_kernel (device.cu) stages in shared memory.  32-bit words:
+//   [R x kRoleHdrWords]  per role: {cons list offset, count, tape offset, ops, x_lo, x_hi, r_lo, r_hi, j_lo, j_hi, 0, 0}
+//   [n_cons x DevCons]   the analysed constraints, input order
+//   per role             the constraints it evaluates (indices, ascending)
+//   per role             its tape: per op {dst byte offset, pairs, code, fin byte offset} + {a, b} byte offsets per pair
+//                        (+ two pad words after an odd number of pairs: headers and pair quads are 16-byte aligned);
+//                        code bit OP_BARRIER = all roles of the group meet here (a cross-role dependency follows)
+// Every op of the sequential tape (SmallProgram::tape) appears in exactly one role's tape with its pairs in the same order, so
+// every value is produced by the same chain of roundings whatever R is.
+constexpr uint32_t kRoleHdrWords = 12;
+struct RoleBlob {
+    uint32_t R = 0, stride = 0;
+    std::vector<uint32_t> words;
+    uint32_t cons_word = 0;       // word offset of the DevCons array
+    uint32_t tape_barriers = 0;   // barriers inside one execution of the tape
+    double busiest_share = 1.0;   // busiest role's share of the tape's cost (1/R = perfectly balanced)
+    // Cost model of one LM iteration on the busiest role, in units of one tape word pair (device.cu picks the number of
+    // roles with it): its tape (3 per op + 2 per multiply-add), its constraints (kEvalCost) and what every role repeats
+    // (the folds over r and d, the barriers).
+    double critical_cost = 0.0;
+};
+// structure.cpp
+void build_role_blob(const ezpz_structure& S, uint32_t R, uint32_t stride, RoleBlob& out);
 
 // The single-large-system programme (large.cu): the processing order of the assembly phase and, unless the
 // factor would be too large, the supernodal sparse direct solve built by sparse_direct.cpp.  Slots index one
@@ -109,6 +140,7 @@ struct ezpz_structure {
     // device copies, one per CUDA device ordinal, created lazily
     std::mutex dev_mutex;
     std::vector<ezs::DeviceCopy*> dev;
+    std::vector<ezs::RoleBlob*> role_probes;  // stride-1 role programmes, one per role count tried: table size and cost model
 };
 
 namespace ezs {

@@ -63,6 +63,10 @@ _SYMBOLS = [
     ("ezpz_b200_structure_pattern", C.c_int32, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)]),
     ("ezpz_b200_structure_pattern_a", C.c_int32, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)]),
     ("ezpz_b200_structure_rows", C.c_int32, [_P, C.POINTER(_P)]),
+    ("ezpz_b200_structure_batch_shape", C.c_int32, [_P, C.c_uint64, C.c_uint32, C.c_uint64, C.POINTER(C.c_uint32),
+                                                    C.POINTER(C.c_uint32)]),
+    ("ezpz_b200_structure_role_program", C.c_int32, [_P, C.c_uint32, C.c_uint32, _P, C.c_uint64, C.POINTER(C.c_uint64),
+                                                     C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     ("ezpz_b200_structure_ordering", C.c_int32, [_P, C.POINTER(C.c_int32), C.POINTER(_P), C.POINTER(C.c_int32),
                                                  C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]),
     ("ezpz_b200_context_create", C.c_int32, [C.c_int32, C.POINTER(_P), C.POINTER(ErrorDetail)]),

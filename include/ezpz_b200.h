@@ -195,6 +195,20 @@ int32_t ezpz_b200_structure_pattern(const ezpz_structure_t* s, const uint32_t** 
 int32_t ezpz_b200_structure_pattern_a(const ezpz_structure_t* s, const uint32_t** a_col_ptr,
                                       const uint32_t** a_row_idx, const uint32_t** l_col_ptr,
                                       const uint32_t** l_row_idx);
+/* Introspection of the batched kernel's programme (tests): the tables lm_small_kernel stages in shared memory for
+ * `roles` cooperating warps per 32 problems and `stride` problems per CTA.  Layout: ezpz_b200/csrc/structure.h (RoleBlob).
+ * Copies at most `cap` 32-bit words to `words`; *n_words is the full length, *cons_word the offset of the constraint
+ * array, *dims = {W (doubles of state per problem), n_cons, barriers inside one tape execution, modelled cost of the
+ * busiest role}.
+ * EZPZ_ERR_UNSUPPORTED when the structure does not run on the thread-per-problem kernel. */
+int32_t ezpz_b200_structure_role_program(const ezpz_structure_t* s, uint32_t roles, uint32_t stride,
+                                         uint32_t* words, uint64_t cap, uint64_t* n_words,
+                                         uint32_t* cons_word, uint32_t* dims);
+/* The launch shape the batched kernel would take for `batch` problems of this structure on a device with `sm_count` SMs
+ * and `smem_per_block` bytes of opt-in shared memory per block: cooperating warps per 32 problems and problems per CTA.
+ * Host arithmetic only (tests, tuning). */
+int32_t ezpz_b200_structure_batch_shape(const ezpz_structure_t* s, uint64_t batch, uint32_t sm_count,
+                                        uint64_t smem_per_block, uint32_t* roles, uint32_t* problems_per_cta);
 /* First row of each constraint in J (n_cons + 1 entries). */
 int32_t ezpz_b200_structure_rows(const ezpz_structure_t* s, const uint32_t** cons_row0);
 

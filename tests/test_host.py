@@ -227,3 +227,105 @@ def test_large_system_ordering_host_analysis():
     # a small system takes the batched kernel: no large programme
     recs, n, g, _ = wl.system_from_text(wl.fixture_text("square"))
     assert ez.Structure(recs, n).ordering()["path"] == 0
+
+
+def _check_role_program(st, roles):
+    """Invariants of build_role_blob (structure.cpp), checked exactly: every op of the sequential tape appears once, each
+    role's ops keep the sequential order, and between two barriers no role writes a slot another role reads or writes."""
+    seq = st.role_program(1)["roles"][0]["ops"]
+    assert not any("barrier" in o for o in seq)
+    rp = st.role_program(roles)
+    key = lambda o: (o["dst"], o["code"], o["positive"], o["fin"], tuple(o["pairs"]))
+    # the sequential tape writes a destination several times (A, then L); tell the ops apart by their rank among equals
+    rank, seen = {}, {}
+    for k, o in enumerate(seq):
+        seen[key(o)] = seen.get(key(o), 0) + 1
+        rank[(key(o), seen[key(o)])] = k
+    covered = []
+    n_bar = None
+    for role in rp["roles"]:
+        counts, last = {}, -1
+        bars = 0
+        for o in role["ops"]:
+            if "barrier" in o:
+                bars += 1
+                continue
+            counts[key(o)] = counts.get(key(o), 0) + 1
+            k = rank[(key(o), counts[key(o)])] if (key(o), counts[key(o)]) in rank else None
+            assert k is not None, "op not in the sequential tape"
+            covered.append(k)
+        assert n_bar in (None, bars), "every role must hold the same number of barriers"
+        n_bar = bars
+    assert n_bar == rp["barriers"]
+    # (equal ops executed by different roles may swap ranks; as a multiset the coverage must be exact)
+    assert sorted(covered) == list(range(len(seq)))
+    # per-role order: positions of a role's ops in the sequential tape must be increasing when ops are matched greedily
+    for role in rp["roles"]:
+        pos, used = 0, set()
+        for o in role["ops"]:
+            if "barrier" in o:
+                continue
+            while pos < len(seq) and (pos in used or key(seq[pos]) != key(o)):
+                pos += 1
+            assert pos < len(seq), "a role's ops are not a subsequence of the sequential tape"
+            used.add(pos)
+    # hazards inside an epoch
+    epochs = [[] for _ in range(n_bar + 1)]
+    for r, role in enumerate(rp["roles"]):
+        e = 0
+        for o in role["ops"]:
+            if "barrier" in o:
+                e += 1
+                continue
+            reads = {s for p in o["pairs"] for s in p}
+            if o["code"] & 1:
+                reads.add(o["dst"])
+            if (o["code"] >> 2) & 3 == 2:
+                reads.add(o["fin"])
+            epochs[e].append((r, reads, o["dst"]))
+    for e, ops in enumerate(epochs):
+        writes = {}
+        for r, reads, dst in ops:
+            writes.setdefault(dst, set()).add(r)
+        for dst, rs in writes.items():
+            assert len(rs) == 1, f"epoch {e}: slot {dst} written by roles {rs}"
+        for r, reads, dst in ops:
+            for s in reads:
+                assert writes.get(s, {r}) == {r}, f"epoch {e}: role {r} reads slot {s} written by {writes[s]}"
+    # constraint lists partition the constraints; the split ranges tile x, r and J
+    cons = sorted(c for role in rp["roles"] for c in role["constraints"])
+    assert cons == list(range(st.n_cons))
+    for what, total in (("x", st.n), ("r", st.m), ("j", st.nnz)):
+        edges = [role[what] for role in rp["roles"]]
+        assert edges[0][0] == 0 and edges[-1][1] == total and all(a[1] == b[0] for a, b in zip(edges, edges[1:]))
+    return rp
+
+
+@pytest.mark.parametrize("roles", [2, 3, 4])
+def test_role_programs_of_the_batched_kernel(roles):
+    """The batched kernel splits a problem's work over cooperating warps (device.cu); the split must be a pure
+    re-distribution of the sequential tape with a barrier in front of every cross-role dependency."""
+    import ezpz_b200 as ez
+    import workloads as wl
+    names = [n for n in sorted(wl.fixtures())]
+    for name in names:
+        recs, n, g, _ = wl.system_from_text(wl.fixture_text(name))
+        st = ez.Structure(recs, n)
+        rp = _check_role_program(st, roles)
+        if name == "two_rectangles" and roles == 2:
+            # two independent 8-variable blocks: each role assembles, factorises and solves one of them, no barrier at all
+            assert rp["barriers"] == 0
+            pairs = [sum(len(o.get("pairs", [])) for o in role["ops"]) for role in rp["roles"]]
+            assert pairs[0] == pairs[1]
+    from test_gpu_parity import random_constraints
+    rng = np.random.default_rng(31 + roles)
+    checked = 0
+    for trial in range(8):
+        cons = random_constraints(rng, 26 + 2 * trial, 20)[-(8 + 3 * trial):]  # (the first 25 are one of each kind)
+        st = ez.Structure(ez.records(cons), 20)
+        try:
+            _check_role_program(st, roles)
+            checked += 1
+        except ez.EzpzError as e:  # too large for the thread-per-problem kernel
+            assert e.name == "Unsupported"
+    assert checked >= 5
