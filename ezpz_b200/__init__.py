@@ -505,7 +505,7 @@ class Structure:
 
     def role_program(self, roles, stride=1):
         """The tables of the batched kernel for `roles` cooperating warps (structure.h: RoleBlob), parsed: per role its
-        constraint list and its tape as a list of ops {"dst", "code", "fin", "pairs": [(a, b)...]} or {"barrier": True}
+        constraint list and its tape as a list of ops {"dst", "shape", "added", "fin", "pairs": [(a, b)...]} or {"barrier": True}
         (slots, i.e. byte offsets divided by 8 * stride)."""
         L = native.lib()
         n_words, cons_word = C.c_uint64(0), C.c_uint32(0)
@@ -523,14 +523,16 @@ class Structure:
             h = words[12 * r:12 * r + 12]
             ops, w = [], int(h[2])
             for _ in range(int(h[3])):
-                dst, npairs, code, fin = (int(v) for v in words[w:w + 4])
-                w += 4
-                if code & 16:
+                dst, fin, counts, last = (int(v) for v in words[w:w + 4])
+                shape, n_words = last & 0xff, last >> 8
+                if shape == 0:
                     ops.append({"barrier": True})
+                    w += n_words
                     continue
-                pairs = [(int(words[w + 2 * k]) // sb, int(words[w + 2 * k + 1]) // sb) for k in range(npairs)]
-                w += 2 * npairs + (2 if npairs % 2 else 0)  # headers sit on 16 bytes
-                ops.append({"dst": dst // sb, "code": code & 0x3f, "positive": (code >> 8) & 0x7f, "fin": fin // sb, "pairs": pairs})
+                added, npairs = counts & 0xffff, (counts & 0xffff) + (counts >> 16)
+                pairs = [(int(words[w + 4 + 2 * k]) // sb, int(words[w + 5 + 2 * k]) // sb) for k in range(npairs)]
+                ops.append({"dst": dst // sb, "shape": shape, "added": added, "fin": fin // sb, "pairs": pairs})
+                w += n_words
             out["roles"].append({"constraints": (words[int(h[0]):int(h[0]) + int(h[1])] & 0xffff).tolist(), "ops": ops,
                                  "x": (int(h[4]), int(h[5])), "r": (int(h[6]), int(h[7])), "j": (int(h[8]), int(h[9]))})
         return out

@@ -160,52 +160,70 @@ __device__ __noinline__ void count_jacobian_degenerates(const SmallArgs& a, cons
     }
 }
 
+// A run of multiply-adds of one tape op: acc = fma(+-V[a], V[b], acc) over the {a, b} byte-offset pairs in tape words
+// [w, we).  One 64-bit load fetches a pair; the NEXT pair's offsets are requested before this pair's operands, so the
+// loop's dependent chain is operand load -> multiply-add, not offsets -> operands -> multiply-add (whatever follows the
+// last pair — pad words or the next header — is loaded and ignored; the tape is padded at the end).
+template <bool NEG>
+__device__ __forceinline__ double tape_run(const uint32_t* __restrict__ tape, uint32_t& w, uint32_t we, const VView& V, double acc) {
+    if (w < we) {
+        uint2 p = *reinterpret_cast<const uint2*>(tape + w);
+#pragma unroll 1
+        do {
+            w += 2;
+            const uint2 q = *reinterpret_cast<const uint2*>(tape + w);
+            const double x = V.ld(p.x), y = V.ld(p.y);
+            acc = __fma_rn(NEG ? -x : x, y, acc);
+            p = q;
+        } while (w < we);
+    }
+    return acc;
+}
+
 // This role's share of the linear-algebra tape of one LM iteration: A = JtJ + lambda*I, b = -Jt r, A = L Lt, L y = b,
-// Lt d = y.  Per op a 4-word header {dst byte offset, pair count, code, fin byte offset} followed by one {a, b}
-// byte-offset pair per multiply-add (padded to 16 bytes); a header with OP_BARRIER is the meeting point of the roles in
-// front of an op that depends on another role's work.  Offsets are uniform across the warp, so an operand access is
-// LDS [thread base + uniform].
-// Returns true when a pivot of this role was not positive and finite ("LltError::Numeric", newton.rs:96-99).
+// Lt d = y.  Per op a 4-word header {dst byte offset, fin byte offset, added pairs | subtracted pairs << 16, shape |
+// words to the next header << 8} followed by one {a, b} byte-offset pair per multiply-add, the added ones first
+// (padded to 16 bytes).  The shape names one of the few forms an op takes (structure.cpp), so that each is straight-line
+// code around its loops instead of a chain of flag tests; TAPE_BARRIER is the meeting point of the roles in front of an
+// op that depends on another role's work.  Offsets are uniform across the warp: an operand access is LDS [thread base +
+// uniform].  Returns true when a pivot of this role was not positive and finite ("LltError::Numeric", newton.rs:96-99).
 __device__ __forceinline__ bool run_role_tape(const uint32_t* __restrict__ tape, uint32_t n_ops, const VView& V, double lambda,
                                               bool act, uint32_t bar_id, uint32_t bar_threads) {
     bool fail = false;
     uint32_t w = 0;  // 32-bit word index: keeps the loop control out of 64-bit pointer arithmetic
+    // The warp issues in order and an op is a chain of dependent latencies, so whatever can be requested early is: the
+    // NEXT header while this op computes (the tape ends with a pad header), the finalisation operand with the first pairs.
+    uint4 h = *reinterpret_cast<const uint4*>(tape);
 #pragma unroll 1
     for (uint32_t op = 0; op < n_ops; ++op) {
-        const uint4 h = *reinterpret_cast<const uint4*>(tape + w);
-        const uint32_t dst = h.x, np = h.y, code = h.z, fin = h.w;
+        const uint32_t dst = h.x, fin = h.y, counts = h.z, shape = h.w & 0xffu;
+        const uint32_t w_next = w + (h.w >> 8);
+        h = *reinterpret_cast<const uint4*>(tape + w_next);
         w += 4;
-        if (code & OP_BARRIER) {
+        if (shape == TAPE_BARRIER) {
             group_sync(bar_id, bar_threads);
+            w = w_next;
             continue;
         }
-        double acc = (code & OP_INIT_DST) ? V.ld(dst) : 0.0;
-        // (Rolled on purpose: the ops are short — 1.7 pairs on average for two_rectangles — and a switch over fully
-        // unrolled bodies with all operands requested up front measured 9 % slower, profiles/r02a_lm_small_roles.md.)
-        const uint32_t we = w + 2 * np;
-        if (const uint32_t npos = (code >> OP_POS_SHIFT) & OP_POS_MASK) {  // the assembly of A[i][j] fused in front (structure.cpp)
-            const uint32_t wp = w + 2 * npos;
-#pragma unroll 1
-            for (; w < wp; w += 2) acc = __fma_rn(V.ld(tape[w]), V.ld(tape[w + 1]), acc);
-        }
-        if (code & OP_MID_LAMBDA) acc = __dadd_rn(acc, lambda);
-        if (code & OP_NEGATE) {
-#pragma unroll 1
-            for (; w < we; w += 2) acc = __fma_rn(-V.ld(tape[w]), V.ld(tape[w + 1]), acc);
-        } else {
-#pragma unroll 1
-            for (; w < we; w += 2) acc = __fma_rn(V.ld(tape[w]), V.ld(tape[w + 1]), acc);
-        }
-        w += (np & 1u) << 1;
-        const uint32_t fk = (code >> OP_FIN_SHIFT) & 3u;
-        if (fk == OP_FIN_MUL) {
-            acc = __dmul_rn(acc, V.ld(fin));
-        } else if (fk == OP_FIN_LAMBDA) {
+        const uint32_t wp = w + 2 * (counts & 0xffffu), we = wp + 2 * (counts >> 16);
+        double acc;
+        if (shape == TAPE_ENTRY) {  // L[i][j] = (A[i][j] - sum L[i][k] L[j][k]) / L[j][j]; y[i] = (b[i] - sum L[i][k] y[k]) / L[i][i]
+            const double fin_v = V.ld(fin);
+            acc = tape_run<false>(tape, w, wp, V, 0.0);
+            acc = tape_run<true>(tape, w, we, V, acc);
+            acc = __dmul_rn(acc, fin_v);
+        } else if (shape == TAPE_PIVOT) {  // 1 / sqrt(A[j][j] + lambda - sum L[j][k]^2)
+            acc = tape_run<false>(tape, w, wp, V, 0.0);
             acc = __dadd_rn(acc, lambda);
-        } else if (fk == OP_FIN_PIVOT) {
+            acc = tape_run<true>(tape, w, we, V, acc);
             if (!(acc > 0.0) || !ezm::ez_isfinite(acc)) fail = true;
             acc = __ddiv_rn(1.0, __dsqrt_rn(acc));
+        } else {  // TAPE_BACKWARD: d[j] = (y[j] - sum L[i][j] d[i]) / L[j][j], in place
+            const double fin_v = V.ld(fin);
+            acc = tape_run<true>(tape, w, we, V, V.ld(dst));
+            acc = __dmul_rn(acc, fin_v);
         }
+        w = w_next;
         V.stp(act, dst, acc);
     }
     return fail;
@@ -260,10 +278,17 @@ __device__ __forceinline__ void lm_roles_body(const SmallArgs& a, const uint32_t
         any_degen = rd || jd;
     }
     if (R > 1) group_sync(bar_id, bar_threads);
-    double S = 0.0;
+    // S = sum r^2 is a strictly sequential fold (Rust's iterator sum); max |r_i| with libm::fmax semantics
+    // (NaN-ignoring: NaN < x is false, so a NaN candidate never wins and a NaN incumbent is replaced by any number) is
+    // order-independent and rides along on the same loads.  Unrolled by four so that the loads and squares of four
+    // elements are in flight while the adds chain.
+    double S = 0.0, largest = ezm::ez_abs(V.ld(oR));
+#pragma unroll 4
     for (uint32_t i = 0; i < a.m; ++i) {
         const double r = V.ld(oR + i * sb);
         S = S + r * r;
+        const double v = ezm::ez_abs(r);
+        largest = (largest < v || largest != largest) ? v : largest;
     }
     uint32_t iterations = a.max_iterations;
     bool converged = false;
@@ -271,14 +296,8 @@ __device__ __forceinline__ void lm_roles_body(const SmallArgs& a, const uint32_t
     bool alive = valid;
 #pragma unroll 1
     for (uint32_t it = 0; it < a.max_iterations; ++it) {
-        // max |r_i| with libm::fmax semantics (NaN-ignoring): NaN < x is false, so a NaN candidate never wins
-        // and a NaN incumbent is replaced by any number.
-        double largest = ezm::ez_abs(V.ld(oR));
-        for (uint32_t i = 1; i < a.m; ++i) {
-            const double v = ezm::ez_abs(V.ld(oR + i * sb));
-            largest = (largest < v || largest != largest) ? v : largest;
-        }
-        if (alive && largest <= a.residual_tolerance) {
+        if (alive && largest <= a.residual_tolerance) {  // `largest` = max |r_i| of the current r, kept up to date below
+
             iterations = it;
             converged = true;
             alive = false;
@@ -296,6 +315,7 @@ __device__ __forceinline__ void lm_roles_body(const SmallArgs& a, const uint32_t
         const bool stepping = alive && !failed;
         if (alive && failed) lambda *= 10.0;  // newton.rs:96-99: the iteration is spent, no step test
         double step = ezm::ez_abs(V.ld(oD));
+#pragma unroll 4
         for (uint32_t j = 1; j < a.n; ++j) {
             const double v = ezm::ez_abs(V.ld(oD + j * sb));
             step = (step < v || step != step) ? v : step;
@@ -309,10 +329,13 @@ __device__ __forceinline__ void lm_roles_body(const SmallArgs& a, const uint32_t
         eval_list<true, true>(a, cons, list, n_list, V, a.RN0, a.L0, prow, degen_row, stepping, rd, jd);
         any_degen = any_degen || rd;
         if (R > 1) group_sync(bar_id, bar_threads);
-        double S2 = 0.0;
+        double S2 = 0.0, largest2 = ezm::ez_abs(V.ld(oRN));
+#pragma unroll 4
         for (uint32_t i = 0; i < a.m; ++i) {
             const double r = V.ld(oRN + i * sb);
             S2 = S2 + r * r;
+            const double v = ezm::ez_abs(r);
+            largest2 = (largest2 < v || largest2 != largest2) ? v : largest2;
         }
         const bool accept = stepping && (S2 < S);
         const bool reject = stepping && !accept;
@@ -325,6 +348,7 @@ __device__ __forceinline__ void lm_roles_body(const SmallArgs& a, const uint32_t
                 if (degen_row) count_jacobian_degenerates(a, cons, list, n_list, V, prow, degen_row);
             }
             S = S2;
+            largest = largest2;  // r_next becomes r
             lambda *= 0.1;
             x_dirty = false;
         } else if (reject) {
@@ -624,9 +648,9 @@ int32_t small_shape_host(const ezpz_structure* cs, uint64_t batch, uint32_t sm_c
         const size_t avail = smem_optin - (stg ? tb : 0);
         const uint64_t g = std::min<uint64_t>({avail / per_group, (uint64_t)15, (uint64_t)(max_threads / (32u * cand))});
         if (g < 1) continue;
-        // modelled time: critical path x waves the batch takes x slowdown per resident warp (0.6 % each: the warps of an SM
+        // modelled time: critical path x waves the batch takes x slowdown per resident warp (2.5 % each: the warps of an SM
         // share its issue slots and shared-memory pipe); an open-ended batch (chunk sizing) is scored by throughput
-        const double contention = 1.0 + 0.0059 * (double)(std::min(g, need) * cand);
+        const double contention = 1.0 + 0.025 * (double)(std::min(g, need) * cand);
         const double waves = n_groups == ~0ull ? 1.0 / (double)g : (double)((n_groups + (uint64_t)sm_count * g - 1) / ((uint64_t)sm_count * g));
         const double score = 1.0 / (probe->critical_cost * waves * contention);
         if (score > best) {

@@ -132,6 +132,7 @@ struct TapeBuilder {
         head = t.size();
         t.push_back(dst & 0xffffu);
         t.push_back((fin_slot & 0xffffu) | ((code | (fin_kind << OP_FIN_SHIFT)) << 16));
+        t.push_back(0u);
         ++n_ops;
     }
     void pair(uint32_t a, uint32_t b) {
@@ -139,10 +140,11 @@ struct TapeBuilder {
         t[head] += 1u << 16;
         ++n_pairs;
     }
-    // The `count` pairs pushed so far are ADDED whatever OP_NEGATE says (the assembly of A inside a factorisation op),
-    // and lambda is added behind them when `lambda` is set.  The count travels in bits 8..14 of the code.
-    void positive(uint32_t count, bool lambda) {
-        t[head + 1] |= ((count & OP_POS_MASK) << OP_POS_SHIFT | (lambda ? (uint32_t)OP_MID_LAMBDA : 0u)) << 16;
+    // The pairs pushed so far are the added ones (the assembly of A inside a factorisation op); lambda follows them
+    // when `lambda` is set.  Pairs pushed from now on are subtracted.
+    void added_done(bool lambda) {
+        t[head + 2] = t[head] >> 16;
+        if (lambda) t[head + 1] |= (uint32_t)OP_MID_LAMBDA << 16;
     }
 };
 
@@ -212,20 +214,11 @@ void build_small_program(ezpz_structure& S) {
         }
         return count;
     };
-    // Opens the factorisation op of L entry (i, j) at `slot` with the assembly of A[i][j] fused in front; an entry with
-    // more products than the header can count (OP_POS_MASK) gets its assembly as an op of its own, as the reference does.
+    // Opens the factorisation op of L entry (i, j) at `slot` with the assembly of A[i][j] fused in front.
     auto begin_entry = [&](uint32_t slot, uint32_t i, uint32_t j, uint32_t fin_kind, uint32_t fin_slot) {
-        const bool has_a = i == j || in_a(i, j);
-        const uint32_t count = has_a ? a_products(i, j, false) : 0u;
-        if (count > OP_POS_MASK) {
-            tb.begin(slot, 0u, i == j ? OP_FIN_LAMBDA : OP_FIN_NONE, 0u);
-            a_products(i, j, true);
-            tb.begin(slot, OP_INIT_DST | OP_NEGATE, fin_kind, fin_slot);
-            return;
-        }
-        tb.begin(slot, OP_NEGATE, fin_kind, fin_slot);
-        if (has_a) a_products(i, j, true);
-        tb.positive(count, i == j);
+        tb.begin(slot, 0u, fin_kind, fin_slot);
+        if (i == j || in_a(i, j)) a_products(i, j, true);
+        tb.added_done(i == j);
     };
     // (1)+(3) A = JtJ + lambda*I and its left-looking Cholesky, column by column: pivot, then the sub-diagonal entries
     for (uint32_t j = 0; j < n; ++j) {
@@ -250,14 +243,14 @@ void build_small_program(ezpz_structure& S) {
     }
     // (2)+(4) b = Jt * (-r) and the forward substitution L y = b (into d)
     for (uint32_t i = 0; i < n; ++i) {
-        tb.begin(P.D0 + i, OP_NEGATE, OP_FIN_MUL, diag_slot[i]);
+        tb.begin(P.D0 + i, 0u, OP_FIN_MUL, diag_slot[i]);
         for (uint32_t p = S.csc_col_ptr[i]; p < S.csc_col_ptr[i + 1]; ++p) tb.pair(P.J0 + p, P.R0 + S.csc_row_idx[p]);
         for (const RowEnt& e : lrow[i]) tb.pair(e.slot, P.D0 + e.col);
     }
     // (5) backward substitution Lt d = y, rows of every column DESCENDING (on the large path this lets the
     // columns of a supernode advance together, and one order serves both paths and the oracle)
     for (uint32_t ii = n; ii-- > 0;) {
-        tb.begin(P.D0 + ii, OP_INIT_DST | OP_NEGATE, OP_FIN_MUL, diag_slot[ii]);
+        tb.begin(P.D0 + ii, OP_INIT_DST, OP_FIN_MUL, diag_slot[ii]);
         for (uint32_t p = S.l_col_ptr[ii + 1]; p-- > S.l_col_ptr[ii] + 1;) tb.pair(P.L0 + p, P.D0 + S.l_row_idx[p]);
     }
     P.n_ops = tb.n_ops;
@@ -271,7 +264,7 @@ void build_small_program(ezpz_structure& S) {
 // balance the constraint lists of the roles.
 constexpr uint8_t kEvalCost[EZPZ_K_COUNT] = {16, 12, 8, 9, 1, 1, 1, 1, 20, 1, 1, 2, 1, 16, 16, 16, 2, 20, 12, 12, 30, 50, 30, 20, 24};
 // ... in units of the tape's cost model: a flat part per constraint plus a little per unit of formula.
-constexpr uint32_t eval_cost(uint32_t kind) { return 100u + 3u * kEvalCost[kind]; }
+constexpr uint32_t eval_cost(uint32_t kind) { return 650u + 6u * kEvalCost[kind]; }
 
 }  // namespace
 
@@ -311,10 +304,10 @@ void build_role_blob(const ezpz_structure& S, uint32_t R, uint32_t stride, RoleB
     }
     // ---- ops of the sequential tape
     struct Op {
-        uint32_t dst, fin, code, np;
+        uint32_t dst, fin, code, np, added, shape;
         size_t pairs;  // index of the first pair word in P.tape
         uint32_t role = 0;
-        uint32_t cost() const { return 34 + 17 * np; }  // measured, see critical_cost below
+        uint32_t cost() const { return 150 + 5 * np; }  // fitted, see critical_cost below
     };
     std::vector<Op> ops;
     for (size_t i = 0; i < P.tape.size();) {
@@ -324,15 +317,18 @@ void build_role_blob(const ezpz_structure& S, uint32_t R, uint32_t stride, RoleB
         o.np = h0 >> 16;
         o.fin = h1 & 0xffffu;
         o.code = h1 >> 16;
-        o.pairs = i + 2;
+        o.added = P.tape[i + 2];
+        o.pairs = i + 3;
+        const uint32_t fk = (o.code >> OP_FIN_SHIFT) & 3u;
+        o.shape = fk == OP_FIN_PIVOT ? TAPE_PIVOT : (o.code & OP_INIT_DST) ? TAPE_BACKWARD : TAPE_ENTRY;
         ops.push_back(o);
-        i += 2 + o.np;
+        i += 3 + o.np;
     }
     const uint32_t W = P.W;
     auto reads_of = [&](const Op& o, std::vector<uint32_t>& rd) {
         rd.clear();
-        if (o.code & OP_INIT_DST) rd.push_back(o.dst);
-        if (((o.code >> OP_FIN_SHIFT) & 3u) == OP_FIN_MUL) rd.push_back(o.fin);
+        if (o.shape == TAPE_BACKWARD) rd.push_back(o.dst);
+        if (o.shape != TAPE_PIVOT) rd.push_back(o.fin);
         for (uint32_t k = 0; k < o.np; ++k) {
             rd.push_back(P.tape[o.pairs + k] & 0xffffu);
             rd.push_back(P.tape[o.pairs + k] >> 16);
@@ -406,12 +402,13 @@ void build_role_blob(const ezpz_structure& S, uint32_t R, uint32_t stride, RoleB
             ++epoch;
             ++out.tape_barriers;
             for (uint32_t r = 0; r < R; ++r) {
-                tape[r].insert(tape[r].end(), {0u, 0u, (uint32_t)OP_BARRIER, 0u});
+                tape[r].insert(tape[r].end(), {0u, 0u, 0u, (uint32_t)TAPE_BARRIER | 4u << 8});
                 ++n_ops[r];
             }
         }
         std::vector<uint32_t>& t = tape[o.role];
-        t.insert(t.end(), {o.dst * sb, o.np, o.code, o.fin * sb});
+        const uint32_t n_words = 4u + 2u * o.np + ((o.np & 1u) << 1);
+        t.insert(t.end(), {o.dst * sb, o.fin * sb, o.added | (o.np - o.added) << 16, o.shape | n_words << 8});
         for (uint32_t k = 0; k < o.np; ++k) {
             const uint32_t w = P.tape[o.pairs + k];
             t.push_back((w & 0xffffu) * sb);
@@ -429,17 +426,18 @@ void build_role_blob(const ezpz_structure& S, uint32_t R, uint32_t stride, RoleB
         w_role[o.dst] = o.role;
         w_epoch[o.dst] = epoch;
     }
-    {   // Cost model fitted to the measured kernel times of 8 structures x 1..4 roles on B200 (4.7 % rms,
-        // profiles/r02a_lm_small_roles.md): 34 per op + 17 per multiply-add, ~112 per constraint almost whatever its kind
-        // (record load, dispatch and scatter outweigh the formulas), 19.5 per element of the three folds every role
-        // repeats, 14 per barrier.
+    {   // Cost model fitted to the measured kernel times of 8 structures x 1..4 roles on B200 (4 % rms,
+        // profiles/r02a_lm_small_roles.md): 150 per tape op and only ~5 per multiply-add (an op's fixed chain — header,
+        // first operands, finalisation, store — dwarfs its short loop), ~650 per constraint plus ~6 per unit of formula
+        // (record load, dispatch and scatter outweigh the arithmetic), 105 per element of the three folds every role
+        // repeats, a few units per barrier.
         std::vector<uint64_t> tcost(R, 0), ecost(R, 0);
         for (const Op& o : ops) tcost[o.role] += o.cost();
         for (uint32_t r = 0; r < R; ++r)
             for (uint32_t c : clist[r]) ecost[r] += eval_cost(S.cons[c].kind);
         double crit = 0.0;
         for (uint32_t r = 0; r < R; ++r) crit = std::max(crit, (double)tcost[r] + (double)ecost[r]);
-        out.critical_cost = crit + 19.5 * (2.0 * m + n) + (R > 1 ? 14.0 * (4 + out.tape_barriers) : 0.0);
+        out.critical_cost = crit + 105.0 * (2.0 * m + n) + (R > 1 ? 5.0 * (4 + out.tape_barriers) : 0.0);
     }
     // ---- the blob
     std::vector<uint32_t>& w = out.words;
@@ -461,6 +459,7 @@ void build_role_blob(const ezpz_structure& S, uint32_t R, uint32_t stride, RoleB
         while (w.size() & 3u) w.push_back(0u);  // tapes start on 16 bytes
         const uint32_t tape_off = (uint32_t)w.size();
         w.insert(w.end(), tape[r].begin(), tape[r].end());
+        w.insert(w.end(), {0u, 0u, 0u, 0u});  // the interpreter requests the next header before it knows there is none
         h = w.data() + (size_t)kRoleHdrWords * r;
         h[0] = cons_off;
         h[1] = (uint32_t)clist[r].size();

@@ -30,16 +30,21 @@ static_assert(sizeof(DevCons) == 136, "DevCons layout");
 
 constexpr uint32_t kAccumulate = 0x80000000u;
 
-// Tape op codes (see batch_small.cu: run_tape).
+// Ops of the sequential small-system tape (SmallProgram::tape), host format, 3 + pairs words each:
+//   {dst | pairs << 16, fin | code << 16, added}, then one word a | b << 16 per multiply-add.
+// acc starts from V[dst] (OP_INIT_DST) or +0.0; the first `added` pairs are accumulated as fma(V[a], V[b], acc); lambda is
+// added behind them when OP_MID_LAMBDA is set; the remaining pairs as fma(-V[a], V[b], acc); then the finalisation.
+// Three forms occur (build_small_program), which the device tape names as shapes:
+//   TAPE_PIVOT     +0.0, added pairs (A[j][j]), + lambda, subtracted pairs (L[j][k]^2), pivot: fail unless acc > 0, 1/sqrt
+//   TAPE_ENTRY     +0.0, added pairs, subtracted pairs, * V[fin]       (L[i][j] with its A[i][j]; y[i] with its b[i])
+//   TAPE_BACKWARD  V[dst], subtracted pairs, * V[fin]                  (backward substitution, in place)
 enum : uint32_t {
-    OP_INIT_DST = 1u,   // acc starts from V[dst] instead of +0.0
-    OP_NEGATE = 2u,     // acc = fma(-V[a], V[b], acc) instead of fma(V[a], V[b], acc)
-    OP_FIN_SHIFT = 2u,  // bits 2..3: 0 none, 1 acc += lambda, 2 acc *= V[fin], 3 pivot: fail unless acc > 0, acc = 1/sqrt(acc)
-    OP_FIN_NONE = 0u, OP_FIN_LAMBDA = 1u, OP_FIN_MUL = 2u, OP_FIN_PIVOT = 3u,
-    OP_BARRIER = 16u,   // (role tapes only) not an op: the roles of a problem group synchronise here
-    OP_MID_LAMBDA = 32u,  // acc += lambda after the leading positive pairs (diagonal of A inside its pivot op)
-    OP_POS_SHIFT = 8u, OP_POS_MASK = 0x7fu  // bits 8..14: how many leading pairs are added although OP_NEGATE is set
+    OP_INIT_DST = 1u,
+    OP_FIN_SHIFT = 2u,  // bits 2..3: finalisation
+    OP_FIN_NONE = 0u, OP_FIN_MUL = 2u, OP_FIN_PIVOT = 3u,
+    OP_MID_LAMBDA = 32u
 };
+enum : uint32_t { TAPE_BARRIER = 0u, TAPE_ENTRY = 1u, TAPE_PIVOT = 2u, TAPE_BACKWARD = 3u };
 
 // The batched small-system program: slot map of the per-problem value array V and the op tape.
 struct SmallProgram {
@@ -58,9 +63,10 @@ struct SmallProgram {
 //   [R x kRoleHdrWords]  per role: {cons list offset, count, tape offset, ops, x_lo, x_hi, r_lo, r_hi, j_lo, j_hi, 0, 0}
 //   [n_cons x DevCons]   the analysed constraints, input order
 //   per role             the constraints it evaluates (indices, ascending)
-//   per role             its tape: per op {dst byte offset, pairs, code, fin byte offset} + {a, b} byte offsets per pair
-//                        (+ two pad words after an odd number of pairs: headers and pair quads are 16-byte aligned);
-//                        code bit OP_BARRIER = all roles of the group meet here (a cross-role dependency follows)
+//   per role             its tape: per op {dst byte offset, fin byte offset, added | subtracted << 16, shape | words to the
+//                        next header << 8} + {a, b} byte offsets per pair (+ two pad words after an odd number of pairs:
+//                        headers and pair quads are 16-byte aligned), and one pad header at the end;
+//                        shape TAPE_BARRIER = all roles of the group meet here (a cross-role dependency follows)
 // Every op of the sequential tape (SmallProgram::tape) appears in exactly one role's tape with its pairs in the same order, so
 // every value is produced by the same chain of roundings whatever R is.
 constexpr uint32_t kRoleHdrWords = 12;

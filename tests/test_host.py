@@ -235,7 +235,7 @@ def _check_role_program(st, roles):
     seq = st.role_program(1)["roles"][0]["ops"]
     assert not any("barrier" in o for o in seq)
     rp = st.role_program(roles)
-    key = lambda o: (o["dst"], o["code"], o["positive"], o["fin"], tuple(o["pairs"]))
+    key = lambda o: (o["dst"], o["shape"], o["added"], o["fin"], tuple(o["pairs"]))
     # the sequential tape writes a destination several times (A, then L); tell the ops apart by their rank among equals
     rank, seen = {}, {}
     for k, o in enumerate(seq):
@@ -278,9 +278,9 @@ def _check_role_program(st, roles):
                 e += 1
                 continue
             reads = {s for p in o["pairs"] for s in p}
-            if o["code"] & 1:
+            if o["shape"] == 3:  # TAPE_BACKWARD starts from V[dst]
                 reads.add(o["dst"])
-            if (o["code"] >> 2) & 3 == 2:
+            if o["shape"] != 2:  # every shape but TAPE_PIVOT multiplies by V[fin]
                 reads.add(o["fin"])
             epochs[e].append((r, reads, o["dst"]))
     for e, ops in enumerate(epochs):
