@@ -590,29 +590,8 @@ class Context:
                     out=None):
         """ezpz_b200_solve_batch: host buffers in, host buffers out.  `out`: an earlier BatchResult (e.g. with
         pinned arrays) to reuse instead of allocating."""
-        g = np.ascontiguousarray(guesses, dtype=np.float64).reshape(-1, st.n_vars)
-        B = g.shape[0]
-        cfg = (config or Config())._native()
-        if out is None:
-            res = BatchResult()
-            res.final_values = np.empty_like(g)
-            res.iterations = np.empty(B, np.uint32)
-            res.status = np.empty(B, np.uint8)
-            uw = (st.n_cons + 31) // 32
-            res.unsat_mask = np.zeros((B, uw), np.uint32) if want_unsat else None
-            res.degen_count = np.zeros((B, st.n_cons), np.uint32) if want_degen else None
-            res.jacobian = np.zeros((B, st.nnz), np.float64) if want_jacobian else None
-        else:
-            res = out
-        p = None if params is None else np.ascontiguousarray(params, dtype=np.float64)
-        io = native.BatchIO(native.ptr(g), native.ptr(p), native.ptr(res.final_values), native.ptr(res.iterations),
-                            native.ptr(res.status), native.ptr(res.unsat_mask), native.ptr(res.degen_count),
-                            native.ptr(res.jacobian))
-        det = native.ErrorDetail()
-        rc = native.lib().ezpz_b200_solve_batch(self.handle, st.handle, C.byref(cfg), B, C.byref(io), C.byref(det))
-        if rc != 0:
-            raise EzpzError(rc, det)
-        return res
+        return _batch_call(native.lib().ezpz_b200_solve_batch, self.handle, st, guesses, params, config, want_unsat, want_degen,
+                           want_jacobian, out)
 
     def solve_batch_device(self, st, io_ptrs, batch, config=None, stream=0):
         """Device-pointer form.  io_ptrs: dict of int device addresses (guesses, final_values, iterations,
@@ -735,6 +714,117 @@ class Context:
         if rc != 0:
             raise EzpzError(rc, det)
         return mask
+
+
+def _batch_call(fn, handle, st, guesses, params, config, want_unsat, want_degen, want_jacobian, out):
+    g = np.ascontiguousarray(guesses, dtype=np.float64).reshape(-1, st.n_vars)
+    B = g.shape[0]
+    cfg = (config or Config())._native()
+    if out is None:
+        res = BatchResult()
+        res.final_values = np.empty_like(g)
+        res.iterations = np.empty(B, np.uint32)
+        res.status = np.empty(B, np.uint8)
+        uw = (st.n_cons + 31) // 32
+        res.unsat_mask = np.zeros((B, uw), np.uint32) if want_unsat else None
+        res.degen_count = np.zeros((B, st.n_cons), np.uint32) if want_degen else None
+        res.jacobian = np.zeros((B, st.nnz), np.float64) if want_jacobian else None
+    else:
+        res = out
+    p = None if params is None else np.ascontiguousarray(params, dtype=np.float64)
+    io = native.BatchIO(native.ptr(g), native.ptr(p), native.ptr(res.final_values), native.ptr(res.iterations),
+                        native.ptr(res.status), native.ptr(res.unsat_mask), native.ptr(res.degen_count),
+                        native.ptr(res.jacobian))
+    det = native.ErrorDetail()
+    rc = fn(handle, st.handle, C.byref(cfg), B, C.byref(io), C.byref(det))
+    if rc != 0:
+        raise EzpzError(rc, det)
+    return res
+
+
+class MultiContext:
+    """ezpz_b200_multi_*: one worker thread + context per GPU; solve_batch shards a batch over them in ONE call."""
+
+    def __init__(self, devices=None, n_devices=0):
+        h = C.c_void_p()
+        det = native.ErrorDetail()
+        if devices is None:
+            rc = native.lib().ezpz_b200_multi_create(None, int(n_devices), C.byref(h), C.byref(det))
+        else:
+            arr = np.ascontiguousarray(devices, dtype=np.int32)
+            rc = native.lib().ezpz_b200_multi_create(native.ptr(arr), len(arr), C.byref(h), C.byref(det))
+        if rc != 0:
+            raise EzpzError(rc, det)
+        self.handle = h
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                native.lib().ezpz_b200_multi_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    @property
+    def device_count(self):
+        return int(native.lib().ezpz_b200_multi_device_count(self.handle))
+
+    @property
+    def launches(self):
+        return int(native.lib().ezpz_b200_multi_launches(self.handle))
+
+    def solve_batch(self, st, guesses, params=None, config=None, want_unsat=True, want_degen=False, want_jacobian=False,
+                    out=None):
+        return _batch_call(native.lib().ezpz_b200_solve_batch_multi, self.handle, st, guesses, params, config, want_unsat,
+                           want_degen, want_jacobian, out)
+
+
+class PinnedArray:
+    """A numpy array in page-locked host memory every device can address (ezpz_b200_host_alloc); freed with the object."""
+
+    def __init__(self, shape, dtype):
+        self.dtype = np.dtype(dtype)
+        self.shape = tuple(shape) if hasattr(shape, "__len__") else (int(shape),)
+        nbytes = max(1, int(np.prod(self.shape)) * self.dtype.itemsize)
+        p = C.c_void_p()
+        rc = native.lib().ezpz_b200_host_alloc(nbytes, C.byref(p))
+        if rc != 0:
+            raise EzpzError(rc)
+        self._ptr = p
+        buf = (C.c_char * nbytes).from_address(p.value)
+        self.array = np.frombuffer(buf, dtype=self.dtype, count=int(np.prod(self.shape))).reshape(self.shape)
+
+    def __del__(self):
+        try:
+            if getattr(self, "_ptr", None):
+                self.array = None
+                native.lib().ezpz_b200_host_free(self._ptr)
+                self._ptr = None
+        except Exception:
+            pass
+
+
+def pinned_batch_buffers(st, batch, want_unsat=True):
+    """(guesses array, BatchResult) in page-locked memory for `batch` problems of `st`; keep the returned owner list alive."""
+    owners = [PinnedArray((batch, st.n_vars), np.float64), PinnedArray((batch, st.n_vars), np.float64),
+              PinnedArray(batch, np.uint32), PinnedArray(batch, np.uint8),
+              PinnedArray((batch, (st.n_cons + 31) // 32), np.uint32)]
+    res = BatchResult()
+    res.final_values, res.iterations, res.status = owners[1].array, owners[2].array, owners[3].array
+    res.unsat_mask = owners[4].array if want_unsat else None
+    res.degen_count = None
+    res.jacobian = None
+    return owners[0].array, res, owners
+
+
+def host_register(arr):
+    rc = native.lib().ezpz_b200_host_register(C.c_void_p(arr.ctypes.data), arr.nbytes)
+    if rc != 0:
+        raise EzpzError(rc)
+
+
+def host_unregister(arr):
+    native.lib().ezpz_b200_host_unregister(C.c_void_p(arr.ctypes.data))
 
 
 def shard_range(batch, rank, world):

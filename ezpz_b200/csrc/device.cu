@@ -69,7 +69,6 @@ struct VView {
     char* base;   // &V[0][problem]
     uint32_t sb;  // stride in bytes between consecutive slots (= problems per CTA * 8)
     __device__ __forceinline__ double ld(uint32_t off) const { return *reinterpret_cast<const double*>(base + off); }
-    __device__ __forceinline__ void st(uint32_t off, double v) const { *reinterpret_cast<double*>(base + off) = v; }
     __device__ __forceinline__ void stp(bool pred, uint32_t off, double v) const {
         if (pred) *reinterpret_cast<double*>(base + off) = v;
     }
@@ -229,6 +228,31 @@ __device__ __forceinline__ bool run_role_tape(const uint32_t* __restrict__ tape,
     return fail;
 }
 
+// Moves the rows of a problem group between global memory (row-major, `width` doubles per problem, the group's problems
+// consecutive) and shared memory ([slot][problem]) with the group's R warps side by side: flat element i of the
+// 32 x width block belongs to problem i / width, slot i % width, and consecutive lanes take consecutive elements, so a warp
+// instruction moves 256 contiguous bytes of global memory — full lines whether that memory is HBM or, for the
+// host-buffer entry point, pinned host memory read and written across PCIe by the kernel itself.
+template <bool LOAD>
+__device__ __forceinline__ void group_rows(char* gbase, uint32_t off0, uint32_t sb, double* __restrict__ rows, uint32_t width,
+                                           uint32_t n_valid, uint32_t role, uint32_t R, uint32_t lane) {
+    const uint32_t total = n_valid * width, stride = 32u * R;
+    const uint32_t dp = stride / width, dj = stride - dp * width;
+    uint32_t i = role * 32u + lane;
+    uint32_t p = i / width, j = i - p * width;
+    for (; i < total; i += stride) {
+        double* s = reinterpret_cast<double*>(gbase + off0 + j * sb + p * 8u);
+        if (LOAD) *s = rows[i];
+        else rows[i] = *s;
+        p += dp;
+        j += dj;
+        if (j >= width) {
+            j -= width;
+            ++p;
+        }
+    }
+}
+
 // The whole solve of one problem — newton.rs:29-145 + lib.rs:305-327 — by the R threads (one per role warp) that share
 // its shared-memory column.  Every role runs the same control flow on the same values (the sums of squares, maxima and
 // verdicts are recomputed by each role from shared memory, which is cheaper than broadcasting them), so the roles take
@@ -253,14 +277,17 @@ __device__ __forceinline__ void lm_roles_body(const SmallArgs& a, const uint32_t
     uint32_t* const flag = reinterpret_cast<uint32_t*>(V.base + a.F0 * sb);  // bit 0 degenerate, bits 1-2 failed pivot (by parity)
     bool any_degen = false;
 
-    if (valid) {  // initial guesses (lib.rs:275: values are positional == by id)
-        const double* __restrict__ g = a.guesses + b * a.n;
-        for (uint32_t j = x_lo; j < x_hi; ++j) V.st(oX + j * sb, g[j]);
-    }
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t b0 = b - lane;  // first problem of the group
+    const uint32_t n_valid = b0 < a.batch ? (uint32_t)(a.batch - b0 < 32u ? a.batch - b0 : 32u) : 0u;
+    char* const gbase = V.base - lane * 8u;  // column 0 of the group
+    // initial guesses (lib.rs:275: values are positional == by id)
+    group_rows<true>(gbase, oX, sb, const_cast<double*>(a.guesses) + b0 * a.n, a.n, n_valid, role, R, lane);
     if (degen_row)
         for (uint32_t q = 0; q < n_list; ++q) degen_row[list[q] & 0xffffu] = 0;
     if (role == 0) *flag = 0u;
     if (R > 1) group_sync(bar_id, bar_threads);
+    else __syncwarp();
     {  // Constraint::set_from_initial_values (lib.rs:183-186)
         const SmemX X{V, oX};
         for (uint32_t q = 0; q < n_list; ++q) {
@@ -363,14 +390,10 @@ __device__ __forceinline__ void lm_roles_body(const SmallArgs& a, const uint32_t
         }
     }
 
-    if (valid) {
-        double* __restrict__ f = a.finals + b * a.n;
-        for (uint32_t j = x_lo; j < x_hi; ++j) f[j] = V.ld(oX + j * sb);
-        if (a.jac) {  // Jacobian cached at the last accepted point (what freedom_analysis reads)
-            double* __restrict__ jo = a.jac + b * a.nnz;
-            for (uint32_t k = j_lo; k < j_hi; ++k) jo[k] = V.ld(oJ + k * sb);
-        }
-    }
+    if (R == 1) __syncwarp();  // (R > 1: every iteration ends at the group's barrier)
+    group_rows<false>(gbase, oX, sb, a.finals + b0 * a.n, a.n, n_valid, role, R, lane);
+    if (a.jac)  // Jacobian cached at the last accepted point (what freedom_analysis reads)
+        group_rows<false>(gbase, oJ, sb, a.jac + b0 * a.nnz, a.nnz, n_valid, role, R, lane);
     if (R > 1) {
         if (any_degen && valid) atomicOr(flag, 1u);
         group_sync(bar_id, bar_threads);
@@ -869,6 +892,44 @@ int32_t ezpz_b200_solve_batch(ezpz_context_t* ctx, const ezpz_structure_t* s, co
     if (batch == 0) return EZPZ_OK;
     if (!io->guesses || !io->final_values || !io->iterations || !io->status) return EZPZ_ERR_INVALID_ARGUMENT;
     EZ_CUDA(cudaSetDevice(ctx->device), "cudaSetDevice");
+    // Zero-copy form: when every buffer of the call is page-locked host memory the device can address (cudaHostAlloc /
+    // cudaHostRegister / ezpz_b200_host_register), the kernel reads the guesses and writes the results across PCIe
+    // itself, in coalesced 256-byte warp accesses (group_rows): no staging buffers, no copy calls, and the transfers of one
+    // CTA overlap the arithmetic of the others instead of being pipelined by hand.  EZPZ_B200_ZERO_COPY=0 disables it.
+    if (s->small.valid) {
+        const char* zc = std::getenv("EZPZ_B200_ZERO_COPY");  // (read per call: bench.py times both forms in one process)
+        const bool zero_copy = !(zc && zc[0] == '0');
+        ezpz_batch_io_t dio;
+        bool ok = zero_copy;
+        auto map = [&](const void* host, bool required) -> void* {
+            if (!host) {
+                if (required) ok = false;
+                return nullptr;
+            }
+            cudaPointerAttributes at;
+            if (cudaPointerGetAttributes(&at, host) != cudaSuccess) {
+                cudaGetLastError();
+                ok = false;
+                return nullptr;
+            }
+            if ((at.type != cudaMemoryTypeHost && at.type != cudaMemoryTypeManaged) || !at.devicePointer) ok = false;
+            return at.devicePointer;
+        };
+        dio.guesses = (const double*)map(io->guesses, true);
+        dio.params = (const double*)map(io->params, false);
+        dio.final_values = (double*)map(io->final_values, true);
+        dio.iterations = (uint32_t*)map(io->iterations, true);
+        dio.status = (uint8_t*)map(io->status, true);
+        dio.unsat_mask = (uint32_t*)map(io->unsat_mask, false);
+        dio.degen_count = (uint32_t*)map(io->degen_count, false);
+        dio.jacobian = (double*)map(io->jacobian, false);
+        if (ok) {
+            const int32_t rc = ezpz_b200_solve_batch_device(ctx, s, config, batch, &dio, ctx->stream, detail);
+            if (rc != EZPZ_OK) return rc;
+            EZ_CUDA(cudaStreamSynchronize(ctx->stream), "cudaStreamSynchronize");
+            return EZPZ_OK;
+        }
+    }
     const size_t n = s->n, nc = s->n_cons, uw = (s->n_cons + 31) / 32;
     const size_t b_x = align_up(batch * n * sizeof(double), 256);
     const size_t b_p = io->params ? align_up(batch * nc * sizeof(double), 256) : 0;

@@ -75,6 +75,16 @@ _SYMBOLS = [
     ("ezpz_b200_context_synchronize", C.c_int32, [_P]),
     ("ezpz_b200_solve_batch", C.c_int32, [_P, _P, C.POINTER(Config), C.c_uint64, C.POINTER(BatchIO), C.POINTER(ErrorDetail)]),
     ("ezpz_b200_solve_batch_device", C.c_int32, [_P, _P, C.POINTER(Config), C.c_uint64, C.POINTER(BatchIO), _P, C.POINTER(ErrorDetail)]),
+    ("ezpz_b200_multi_create", C.c_int32, [_P, C.c_int32, C.POINTER(_P), C.POINTER(ErrorDetail)]),
+    ("ezpz_b200_multi_destroy", None, [_P]),
+    ("ezpz_b200_multi_device_count", C.c_int32, [_P]),
+    ("ezpz_b200_multi_context", _P, [_P, C.c_int32]),
+    ("ezpz_b200_multi_launches", C.c_uint64, [_P]),
+    ("ezpz_b200_solve_batch_multi", C.c_int32, [_P, _P, C.POINTER(Config), C.c_uint64, C.POINTER(BatchIO), C.POINTER(ErrorDetail)]),
+    ("ezpz_b200_host_register", C.c_int32, [_P, C.c_uint64]),
+    ("ezpz_b200_host_unregister", C.c_int32, [_P]),
+    ("ezpz_b200_host_alloc", C.c_int32, [C.c_uint64, C.POINTER(_P)]),
+    ("ezpz_b200_host_free", None, [_P]),
     ("ezpz_b200_shard_range", None, [C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     ("ezpz_b200_solve_one", C.c_int32, [_P, _P, C.POINTER(Config), C.POINTER(OneIO), C.POINTER(ErrorDetail)]),
     ("ezpz_b200_large_bench", C.c_int32, [_P, _P, _P, C.c_int32, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double),

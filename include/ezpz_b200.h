@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define EZPZ_B200_ABI_VERSION 1
+#define EZPZ_B200_ABI_VERSION 2
 
 /* ---------------------------------------------------------------------------------------------
  * Constraint record.  One 64-byte record holds any of the 25 variants of `enum Constraint`
@@ -268,6 +268,35 @@ int32_t ezpz_b200_solve_batch_device(ezpz_context_t* ctx, const ezpz_structure_t
                                      const ezpz_config_t* config, uint64_t batch,
                                      const ezpz_batch_io_t* io, void* cuda_stream,
                                      ezpz_error_detail_t* detail);
+
+/* ---------------------------------------------------------------------------------------------
+ * One call, several GPUs.  The reference's seam is one synchronous in-process call (lib.rs:80-87), so the sharding of a
+ * batch over the GPUs of a box happens inside the library: a multi-context owns one worker thread + context per device;
+ * ezpz_b200_solve_batch_multi cuts the batch into contiguous shards of whole 32-problem groups, one per device, runs
+ * ezpz_b200_solve_batch on each shard of the CALLER's host buffers concurrently and returns when all are done.  Problems
+ * are independent: no exchange step, no collective, and a problem's result does not depend on the number of devices.
+ *   devices   [n_devices] CUDA ordinals, or NULL: the first n_devices visible devices (n_devices <= 0: all of them)
+ * Buffers as in ezpz_batch_io_t (host pointers).  Page-locked buffers (ezpz_b200_host_alloc / ezpz_b200_host_register,
+ * cudaHostAlloc, ...) are read and written by the kernels directly across PCIe; pageable buffers work through staged copies.
+ */
+typedef struct ezpz_multi ezpz_multi_t;
+int32_t ezpz_b200_multi_create(const int32_t* devices, int32_t n_devices, ezpz_multi_t** out,
+                               ezpz_error_detail_t* detail);
+void ezpz_b200_multi_destroy(ezpz_multi_t* mg);
+int32_t ezpz_b200_multi_device_count(const ezpz_multi_t* mg);
+/* The context of device `index` of the multi-context (for single-device calls on the same workspaces); NULL if out of range. */
+ezpz_context_t* ezpz_b200_multi_context(ezpz_multi_t* mg, int32_t index);
+/* Kernels launched so far by all devices of the multi-context. */
+uint64_t ezpz_b200_multi_launches(const ezpz_multi_t* mg);
+int32_t ezpz_b200_solve_batch_multi(ezpz_multi_t* mg, const ezpz_structure_t* s, const ezpz_config_t* config,
+                                    uint64_t batch, const ezpz_batch_io_t* io, ezpz_error_detail_t* detail);
+
+/* Page-locked host memory every device can address (what a Rust caller would wrap its Vec<f64> buffers with): register an
+ * existing allocation, or allocate one. */
+int32_t ezpz_b200_host_register(void* ptr, uint64_t bytes);
+int32_t ezpz_b200_host_unregister(void* ptr);
+int32_t ezpz_b200_host_alloc(uint64_t bytes, void** out);
+void ezpz_b200_host_free(void* ptr);
 
 /* Contiguous shard of a batch for rank `rank` of `world` (one process per GPU; no collective). */
 void ezpz_b200_shard_range(uint64_t batch, uint32_t rank, uint32_t world, uint64_t* begin,

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} is declared in include/ezpz_b200.h but not exported"
     assert sorted(native.SYMBOL_NAMES) == declared, "native.py must bind exactly the header's functions"
-    assert native.lib().ezpz_b200_abi_version() == 1
+    assert native.lib().ezpz_b200_abi_version() == 2
     assert C.sizeof(native.Constraint) == 64
 
 
