@@ -587,11 +587,12 @@ class Context:
         native.lib().ezpz_b200_context_synchronize(self.handle)
 
     def solve_batch(self, st, guesses, params=None, config=None, want_unsat=True, want_degen=False, want_jacobian=False,
-                    out=None):
+                    out=None, want_under=False):
         """ezpz_b200_solve_batch: host buffers in, host buffers out.  `out`: an earlier BatchResult (e.g. with
-        pinned arrays) to reuse instead of allocating."""
+        pinned arrays) to reuse instead of allocating.  want_under: the freedom analysis fused into the call
+        (BatchResult.under_mask: bit j of a problem's words = variable j underconstrained)."""
         return _batch_call(native.lib().ezpz_b200_solve_batch, self.handle, st, guesses, params, config, want_unsat, want_degen,
-                           want_jacobian, out)
+                           want_jacobian, out, want_under)
 
     def solve_batch_device(self, st, io_ptrs, batch, config=None, stream=0):
         """Device-pointer form.  io_ptrs: dict of int device addresses (guesses, final_values, iterations,
@@ -599,7 +600,7 @@ class Context:
         cfg = (config or Config())._native()
         io = native.BatchIO(*[C.c_void_p(io_ptrs.get(k) or None) for k in
                               ("guesses", "params", "final_values", "iterations", "status", "unsat_mask",
-                               "degen_count", "jacobian")])
+                               "degen_count", "jacobian", "under_mask")])
         det = native.ErrorDetail()
         rc = native.lib().ezpz_b200_solve_batch_device(self.handle, st.handle, C.byref(cfg), int(batch), C.byref(io),
                                                        C.c_void_p(stream or None), C.byref(det))
@@ -716,7 +717,7 @@ class Context:
         return mask
 
 
-def _batch_call(fn, handle, st, guesses, params, config, want_unsat, want_degen, want_jacobian, out):
+def _batch_call(fn, handle, st, guesses, params, config, want_unsat, want_degen, want_jacobian, out, want_under=False):
     g = np.ascontiguousarray(guesses, dtype=np.float64).reshape(-1, st.n_vars)
     B = g.shape[0]
     cfg = (config or Config())._native()
@@ -729,12 +730,13 @@ def _batch_call(fn, handle, st, guesses, params, config, want_unsat, want_degen,
         res.unsat_mask = np.zeros((B, uw), np.uint32) if want_unsat else None
         res.degen_count = np.zeros((B, st.n_cons), np.uint32) if want_degen else None
         res.jacobian = np.zeros((B, st.nnz), np.float64) if want_jacobian else None
+        res.under_mask = np.zeros((B, (st.n_vars + 31) // 32), np.uint32) if want_under else None
     else:
         res = out
     p = None if params is None else np.ascontiguousarray(params, dtype=np.float64)
     io = native.BatchIO(native.ptr(g), native.ptr(p), native.ptr(res.final_values), native.ptr(res.iterations),
                         native.ptr(res.status), native.ptr(res.unsat_mask), native.ptr(res.degen_count),
-                        native.ptr(res.jacobian))
+                        native.ptr(res.jacobian), native.ptr(getattr(res, "under_mask", None)))
     det = native.ErrorDetail()
     rc = fn(handle, st.handle, C.byref(cfg), B, C.byref(io), C.byref(det))
     if rc != 0:
@@ -774,9 +776,9 @@ class MultiContext:
         return int(native.lib().ezpz_b200_multi_launches(self.handle))
 
     def solve_batch(self, st, guesses, params=None, config=None, want_unsat=True, want_degen=False, want_jacobian=False,
-                    out=None):
+                    out=None, want_under=False):
         return _batch_call(native.lib().ezpz_b200_solve_batch_multi, self.handle, st, guesses, params, config, want_unsat,
-                           want_degen, want_jacobian, out)
+                           want_degen, want_jacobian, out, want_under)
 
 
 class PinnedArray:
@@ -804,7 +806,7 @@ class PinnedArray:
             pass
 
 
-def pinned_batch_buffers(st, batch, want_unsat=True):
+def pinned_batch_buffers(st, batch, want_unsat=True, want_under=False):
     """(guesses array, BatchResult) in page-locked memory for `batch` problems of `st`; keep the returned owner list alive."""
     owners = [PinnedArray((batch, st.n_vars), np.float64), PinnedArray((batch, st.n_vars), np.float64),
               PinnedArray(batch, np.uint32), PinnedArray(batch, np.uint8),
@@ -812,6 +814,10 @@ def pinned_batch_buffers(st, batch, want_unsat=True):
     res = BatchResult()
     res.final_values, res.iterations, res.status = owners[1].array, owners[2].array, owners[3].array
     res.unsat_mask = owners[4].array if want_unsat else None
+    res.under_mask = None
+    if want_under:
+        owners.append(PinnedArray((batch, (st.n_vars + 31) // 32), np.uint32))
+        res.under_mask = owners[-1].array
     res.degen_count = None
     res.jacobian = None
     return owners[0].array, res, owners

@@ -577,6 +577,16 @@ int32_t ensure_ws(ezpz_context* ctx, size_t bytes, ezpz_error_detail_t* detail) 
     return EZPZ_OK;
 }
 
+int32_t ensure_fa(ezpz_context* ctx, size_t bytes, ezpz_error_detail_t* detail) {
+    if (bytes <= ctx->fa_bytes) return EZPZ_OK;
+    if (ctx->fa_ws) cudaFree(ctx->fa_ws);  // (cudaFree waits for whatever still uses the old block)
+    ctx->fa_ws = nullptr;
+    ctx->fa_bytes = 0;
+    EZ_CUDA(cudaMalloc(&ctx->fa_ws, bytes), "cudaMalloc(freedom analysis scratch)");
+    ctx->fa_bytes = bytes;
+    return EZPZ_OK;
+}
+
 int32_t ensure_pin(ezpz_context* ctx, size_t bytes, ezpz_error_detail_t* detail) {
     if (bytes <= ctx->pin_bytes) return EZPZ_OK;
     if (ctx->pin) cudaFreeHost(ctx->pin);
@@ -713,6 +723,8 @@ void release_device_copies(ezpz_structure* s) {
                 delete t;
             }
             if (d->csc_to_csr) cudaFree(d->csc_to_csr);
+            if (d->csc_col_ptr) cudaFree(d->csc_col_ptr);
+            if (d->csc_row_idx) cudaFree(d->csc_row_idx);
             if (d->large) release_large(d);
         }
         delete d;
@@ -788,6 +800,9 @@ void ezpz_b200_context_destroy(ezpz_context_t* ctx) {
         if (ctx->pipe_done[k]) cudaEventDestroy(ctx->pipe_done[k]);
     }
     if (ctx->ws) cudaFree(ctx->ws);
+    if (ctx->fa_ws) cudaFree(ctx->fa_ws);
+    if (ctx->fa_jac) cudaFree(ctx->fa_jac);
+    if (ctx->fa_done) cudaEventDestroy(ctx->fa_done);
     if (ctx->pin) cudaFreeHost(ctx->pin);
     ezs::release_structure_cache(ctx);
     delete ctx;
@@ -802,6 +817,45 @@ int32_t ezpz_b200_context_synchronize(ezpz_context_t* ctx) {
     return EZPZ_OK;
 }
 
+// The solve + freedom analysis form of the batch call (io->under_mask set): the solve kernel leaves its cached Jacobians in a
+// device buffer of the context, freedom_device reads them there.  Batches whose Jacobians exceed 1 GiB go piece by piece.
+static int32_t solve_batch_with_analysis(ezpz_context_t* ctx, const ezpz_structure_t* s, const ezpz_config_t* config, uint64_t batch,
+                                         const ezpz_batch_io_t* io, cudaStream_t st, ezpz_error_detail_t* detail) {
+    const size_t nnz = s->csc_row_idx.size(), n = s->n, nc = s->n_cons, uw = (s->n_cons + 31) / 32, vw = (s->n + 31) / 32;
+    const uint64_t piece = std::max<uint64_t>(1, std::min<uint64_t>(batch, ((uint64_t)1 << 30) / std::max<size_t>(8, nnz * 8)));
+    EZ_CUDA(cudaSetDevice(ctx->device), "cudaSetDevice");
+    const size_t need = std::max<size_t>(256, piece * nnz * 8);
+    if (need > ctx->fa_jac_bytes) {
+        if (ctx->fa_jac) cudaFree(ctx->fa_jac);
+        ctx->fa_jac = nullptr;
+        ctx->fa_jac_bytes = 0;
+        EZ_CUDA(cudaMalloc(&ctx->fa_jac, need), "cudaMalloc(jacobians for the freedom analysis)");
+        ctx->fa_jac_bytes = need;
+    }
+    // the buffer is shared by every stream that solves with analysis on this context: they take turns
+    if (ctx->fa_busy && ctx->fa_last_stream != st) EZ_CUDA(cudaStreamWaitEvent(st, ctx->fa_done, 0), "cudaStreamWaitEvent");
+    for (uint64_t b0 = 0; b0 < batch; b0 += piece) {
+        const uint64_t cnt = std::min(piece, batch - b0);
+        ezpz_batch_io_t sub = *io;
+        sub.guesses = io->guesses + b0 * n;
+        sub.params = io->params ? io->params + b0 * nc : nullptr;
+        sub.final_values = io->final_values + b0 * n;
+        sub.iterations = io->iterations + b0;
+        sub.status = io->status + b0;
+        sub.unsat_mask = io->unsat_mask ? io->unsat_mask + b0 * uw : nullptr;
+        sub.degen_count = io->degen_count ? io->degen_count + b0 * nc : nullptr;
+        sub.jacobian = (double*)ctx->fa_jac;
+        sub.under_mask = nullptr;
+        int32_t rc = ezpz_b200_solve_batch_device(ctx, s, config, cnt, &sub, st, detail);
+        if (rc != EZPZ_OK) return rc;
+        if (io->jacobian && nnz)
+            EZ_CUDA(cudaMemcpyAsync(io->jacobian + b0 * nnz, ctx->fa_jac, cnt * nnz * 8, cudaMemcpyDefault, st), "copy of the jacobians");
+        rc = ezs::freedom_device(ctx, s, cnt, (const double*)ctx->fa_jac, io->under_mask + b0 * vw, st, detail);
+        if (rc != EZPZ_OK) return rc;
+    }
+    return EZPZ_OK;
+}
+
 int32_t ezpz_b200_solve_batch_device(ezpz_context_t* ctx, const ezpz_structure_t* s, const ezpz_config_t* config,
                                      uint64_t batch, const ezpz_batch_io_t* io, void* cuda_stream,
                                      ezpz_error_detail_t* detail) {
@@ -810,6 +864,8 @@ int32_t ezpz_b200_solve_batch_device(ezpz_context_t* ctx, const ezpz_structure_t
     if (batch == 0) return EZPZ_OK;
     if (!io->guesses || !io->final_values || !io->iterations || !io->status) return EZPZ_ERR_INVALID_ARGUMENT;
     if (s->n_cons == 0 || s->m == 0) return EZPZ_ERR_EMPTY_SYSTEM;
+    if (io->under_mask)
+        return solve_batch_with_analysis(ctx, s, config, batch, io, cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream, detail);
     if (!s->small.valid)  // beyond the thread-per-problem kernel: the persistent LM kernel, one CTA per problem
         return ezs::solve_large_batch(ctx, s, config, batch, io, cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream, detail);
     EZ_CUDA(cudaSetDevice(ctx->device), "cudaSetDevice");
@@ -923,6 +979,7 @@ int32_t ezpz_b200_solve_batch(ezpz_context_t* ctx, const ezpz_structure_t* s, co
         dio.unsat_mask = (uint32_t*)map(io->unsat_mask, false);
         dio.degen_count = (uint32_t*)map(io->degen_count, false);
         dio.jacobian = (double*)map(io->jacobian, false);
+        dio.under_mask = (uint32_t*)map(io->under_mask, false);
         if (ok) {
             const int32_t rc = ezpz_b200_solve_batch_device(ctx, s, config, batch, &dio, ctx->stream, detail);
             if (rc != EZPZ_OK) return rc;
@@ -939,7 +996,9 @@ int32_t ezpz_b200_solve_batch(ezpz_context_t* ctx, const ezpz_structure_t* s, co
     const size_t b_dg = io->degen_count ? align_up(batch * nc * sizeof(uint32_t), 256) : 0;
     const size_t nnz = s->csc_row_idx.size();
     const size_t b_jc = io->jacobian ? align_up(batch * nnz * sizeof(double), 256) : 0;
-    int32_t rc = ensure_ws(ctx, 2 * b_x + b_p + b_it + b_st + b_un + b_dg + b_jc, detail);
+    const size_t vw = (s->n + 31) / 32;
+    const size_t b_uc = io->under_mask ? align_up(batch * vw * sizeof(uint32_t), 256) : 0;
+    int32_t rc = ensure_ws(ctx, 2 * b_x + b_p + b_it + b_st + b_un + b_dg + b_jc + b_uc, detail);
     if (rc != EZPZ_OK) return rc;
     char* w = (char*)ctx->ws;
     double* d_g = (double*)w; w += b_x;
@@ -950,6 +1009,17 @@ int32_t ezpz_b200_solve_batch(ezpz_context_t* ctx, const ezpz_structure_t* s, co
     uint32_t* d_un = io->unsat_mask ? (uint32_t*)w : nullptr; w += b_un;
     uint32_t* d_dg = io->degen_count ? (uint32_t*)w : nullptr; w += b_dg;
     double* d_jc = io->jacobian ? (double*)w : nullptr; w += b_jc;
+    uint32_t* d_uc = io->under_mask ? (uint32_t*)w : nullptr; w += b_uc;
+    // whatever fails from here on, nothing of this call may still be reading or writing the caller's buffers on return
+    std::vector<cudaEvent_t> tev;  // (EZPZ_B200_DEBUG=3 trace events)
+    struct Drain {
+        ezpz_context* c;
+        std::vector<cudaEvent_t>* ev;
+        ~Drain() {
+            for (int k = 0; k < 3; ++k) cudaStreamSynchronize(c->pipe[k]);
+            for (cudaEvent_t e : *ev) cudaEventDestroy(e);
+        }
+    } drain{ctx, &tev};
     // Copy/compute pipeline: the batch is cut into chunks that rotate over three streams, so the H2D copy of
     // chunk k+1, the kernel of chunk k and the D2H copy of chunk k-1 overlap (with pinned host buffers the
     // copies are true DMA on the two copy engines; pageable buffers still work, just without the overlap).
@@ -972,7 +1042,6 @@ int32_t ezpz_b200_solve_batch(ezpz_context_t* ctx, const ezpz_structure_t* s, co
         const char* e = std::getenv("EZPZ_B200_DEBUG");
         return e && e[0] == '3';
     }();
-    std::vector<cudaEvent_t> tev;
     auto mark = [&](cudaStream_t st) {
         if (!trace) return;
         cudaEvent_t e;
@@ -998,15 +1067,18 @@ int32_t ezpz_b200_solve_batch(ezpz_context_t* ctx, const ezpz_structure_t* s, co
         dio.unsat_mask = d_un ? d_un + b0 * uw : nullptr;
         dio.degen_count = d_dg ? d_dg + b0 * nc : nullptr;
         dio.jacobian = d_jc ? d_jc + b0 * nnz : nullptr;
+        dio.under_mask = d_uc ? d_uc + b0 * vw : nullptr;
         rc = ezpz_b200_solve_batch_device(ctx, s, config, cnt, &dio, st, detail);
-        if (rc != EZPZ_OK) return rc;
+        if (rc != EZPZ_OK) break;
         mark(st);
         EZ_CUDA(cudaEventRecord(ctx->pipe_done[c % 3], st), "cudaEventRecord");  // this stream's kernels so far are done
         EZ_CUDA(cudaMemcpyAsync(io->final_values + b0 * n, d_f + b0 * n, cnt * n * sizeof(double), cudaMemcpyDeviceToHost, st), "D2H finals");
         if (d_dg) EZ_CUDA(cudaMemcpyAsync(io->degen_count + b0 * nc, d_dg + b0 * nc, cnt * nc * sizeof(uint32_t), cudaMemcpyDeviceToHost, st), "D2H degen");
         if (d_jc) EZ_CUDA(cudaMemcpyAsync(io->jacobian + b0 * nnz, d_jc + b0 * nnz, cnt * nnz * sizeof(double), cudaMemcpyDeviceToHost, st), "D2H jacobian");
+        if (d_uc) EZ_CUDA(cudaMemcpyAsync(io->under_mask + b0 * vw, d_uc + b0 * vw, cnt * vw * sizeof(uint32_t), cudaMemcpyDeviceToHost, st), "D2H underconstrained");
         mark(st);
     }
+    if (rc != EZPZ_OK) return rc;
     // The small per-problem outputs (9 bytes a problem: iterations, status, unsatisfied mask) leave in ONE copy each for the
     // whole batch once every chunk is done: per chunk they cost three more calls and copy-engine round trips than bytes.
     // They only wait for the KERNELS of all chunks (not for the last chunk's finals) and go out on the three streams side by side.
@@ -1029,7 +1101,6 @@ int32_t ezpz_b200_solve_batch(ezpz_context_t* ctx, const ezpz_structure_t* s, co
             std::fprintf(stderr, "%s%.0f", (k - 1) % 3 == 0 ? " | " : " ", ms * 1e3);
         }
         std::fprintf(stderr, "\n");
-        for (cudaEvent_t e : tev) cudaEventDestroy(e);
     }
     return EZPZ_OK;
 }
@@ -1050,6 +1121,7 @@ int32_t ezpz_b200_solve_one(ezpz_context_t* ctx, const ezpz_structure_t* s, cons
         b.unsat_mask = io->unsat_mask;
         b.degen_count = io->degen_count;
         b.jacobian = io->jacobian;
+        b.under_mask = nullptr;
         if (io->path_used) *io->path_used = 0;
         return ezpz_b200_solve_batch(ctx, s, config, 1, &b, detail);
     }

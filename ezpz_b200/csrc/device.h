@@ -23,6 +23,8 @@ struct DeviceCopy {
     DevCons* cons = nullptr;         // [n_cons]
     std::vector<RoleTables*> roles;  // one per (roles, stride) used so far
     uint32_t* csc_to_csr = nullptr;  // [nnz] position in CSR order of each CSC entry
+    uint32_t* csc_col_ptr = nullptr;  // [n + 1], [nnz]: the pattern of J for the freedom analysis (freedom.cu), on first use
+    uint32_t* csc_row_idx = nullptr;
     void* large = nullptr;           // LargeDevice (large.cu), created on first use
 };
 
@@ -30,6 +32,10 @@ int32_t cuda_fail(cudaError_t e, ezpz_error_detail_t* detail, const char* what);
 int32_t get_device_copy(ezpz_context* ctx, const ezpz_structure* s, DeviceCopy** out, ezpz_error_detail_t* detail);
 int32_t ensure_ws(ezpz_context* ctx, size_t bytes, ezpz_error_detail_t* detail);
 int32_t ensure_pin(ezpz_context* ctx, size_t bytes, ezpz_error_detail_t* detail);
+int32_t ensure_fa(ezpz_context* ctx, size_t bytes, ezpz_error_detail_t* detail);
+// Freedom analysis on device-resident Jacobians, enqueued on st, no host round trip (freedom.cu).
+int32_t freedom_device(ezpz_context* ctx, const ezpz_structure* s, uint64_t batch, const double* d_jac, uint32_t* d_mask,
+                       cudaStream_t st, ezpz_error_detail_t* detail);
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 void release_large(DeviceCopy* d);  // large.cu
 // Single system that does not fit the thread-per-problem kernel (large.cu).
@@ -60,6 +66,15 @@ struct ezpz_context {
     // grow-only pinned host staging buffer (small single-system solves: one DMA each way instead of pageable copies)
     void* pin = nullptr;
     size_t pin_bytes = 0;
+    // freedom analysis (freedom.cu): grow-only scratch of the dense factorisations, the Jacobians of a fused solve + analysis
+    // call, and the event that orders launches of different streams on them
+    void* fa_ws = nullptr;
+    size_t fa_bytes = 0;
+    void* fa_jac = nullptr;
+    size_t fa_jac_bytes = 0;
+    cudaEvent_t fa_done = nullptr;
+    bool fa_busy = false;
+    cudaStream_t fa_last_stream = nullptr;
     // topology cache of ezpz_b200_solve (host_api.cpp): analysed structures keyed by their constraint list
     void* structure_cache = nullptr;
 };

@@ -1,194 +1,498 @@
-// freedom.cu — the "underconstrained" verdict on the device: batched freedom analysis.
+// freedom.cu — the "underconstrained" verdict on the device: freedom analysis for any number of variables.
 //
 // Follows ezpz/src/solver/find_dof.rs:15-104: densify J (values cached at the last accepted point),
 // column-pivoted QR, rank = number of leading |R_ii| > 1e-8 * max|R_ii| (take_while), a basis of
 // null(J P^T) by back substitution, un-permute, orthonormalise, and flag variable j when the squared
 // norm of row j of the orthonormal basis exceeds (1e-3 * max)^2.  faer's ColPivQr / thin-Q are not in
-// tree; here: Householder QR with the largest-remaining-column-norm pivot rule and modified
-// Gram-Schmidt (twice).  The participation norms are the diagonal of the orthogonal projector onto
-// null(J), so they do not depend on which orthonormal basis is produced.
+// tree; here: Householder QR with the largest-remaining-column-norm pivot rule (first maximum wins) and
+// Gram-Schmidt with re-orthogonalisation.  The participation norms are the diagonal of the orthogonal
+// projector onto null(J), so they do not depend on which orthonormal basis is produced.
 //
-// One thread per problem; each thread's dense work arrays live in a global scratch buffer interleaved
-// [element][thread] so that a warp touching element e of its 32 problems reads one contiguous 256-byte
-// row.  This is a verdict pass run once per structure change (lib.rs:86-90 says so), not the inner loop.
+// One kernel, freedom_team_kernel, run by a TEAM of threads per problem; three deployments, by size:
+//   * a warp / CTA per problem with the dense matrix in SHARED memory (n up to ~64: batches of small sketches,
+//     config 5 of BASELINE.json) — tens of CTAs per SM, no global scratch traffic;
+//   * a CTA per problem with the matrix in a global (L2-resident) scratch slot (n up to 1,024, batches);
+//   * the whole grid on ONE problem (cooperative launch, grid barrier; single systems of any size — the
+//     reference benches its analysis at 200 variables and solves massive_parallel_system at 2,400).
+// The matrix is stored ROW-major and a thread owns a COLUMN: the sums of a column run over its rows in ascending
+// order in one thread — exactly the oracle's order (oracle/ezpz_oracle.cpp freedom_analysis), so the QR, its
+// pivot choices (ties included) and the rank decision are bit-identical to the oracle — while the 32 threads of
+// a warp read 32 consecutive doubles of a row.  A Householder step is two barriers: (swap the pivot column in and
+// form v) | (per column: dot with v, update, and the squared norm of what remains, fused in one sweep).
+// Orthonormalisation uses parallel dot products (not bit-identical to the oracle's sequential ones; the
+// verdict's thresholds are relative 1e-6).
+#include <cooperative_groups.h>
+
 #include <algorithm>
 #include <cstring>
+#include <mutex>
 
 #include "device.h"
 #include "dmath.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace {
 
 struct FreedomArgs {
     const uint32_t* csc_col_ptr;
     const uint32_t* csc_row_idx;
-    const double* jac;   // [count * nnz]
-    uint32_t* mask;      // [count * words]
-    double* scratch;     // [per_thread * threads]
-    uint32_t m, n, nnz, words, count, threads;
+    const double* jac;  // [count * nnz]
+    uint32_t* mask;     // [count * words]
+    double* scratch;    // [slots * per_problem] (global deployments)
+    uint64_t per_problem;  // doubles of scratch per problem
+    uint32_t m, n, nnz, words, count;
+    uint32_t in_smem;   // matrix and work vectors in dynamic shared memory
+    uint32_t v_smem;    // doubles of shared memory available for staging v in the global deployments (0 = none)
 };
 
-__global__ void __launch_bounds__(128) freedom_kernel(const FreedomArgs a) {
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= a.count) return;
-    const uint32_t m = a.m, n = a.n, TT = a.threads;
-    double* A = a.scratch + t;                        // A(i,j) = A[(j*m + i) * TT]
-    double* N = A + (size_t)m * n * TT;               // N(i,f) = N[(f*n + i) * TT]
-    double* perm = N + (size_t)n * n * TT;            // [n]
-    double* rdiag = perm + (size_t)n * TT;            // [min(m,n)]
-    double* part = rdiag + (size_t)(m < n ? m : n) * TT;  // [n]
-#define AE(i, j) A[((size_t)(j) * m + (i)) * TT]
-#define NE(i, f) N[((size_t)(f) * n + (i)) * TT]
-    for (uint32_t j = 0; j < n; ++j) {
-        for (uint32_t i = 0; i < m; ++i) AE(i, j) = 0.0;
-        for (uint32_t e = a.csc_col_ptr[j]; e < a.csc_col_ptr[j + 1]; ++e)
-            AE(a.csc_row_idx[e], j) = a.jac[(size_t)t * a.nnz + e];
-        perm[(size_t)j * TT] = (double)j;
-        part[(size_t)j * TT] = 0.0;
+// Work layout of one problem (doubles): A[m*n] row-major | N[n*n] row-major n x nullity | v[m] | norms[n] | dk[n] | perm[n] |
+// rdiag[n] | part[n] | s[n] | red[one per CTA of the team]
+constexpr uint32_t kMaxTeamCtas = 256;
+__host__ __device__ inline uint64_t freedom_doubles(uint64_t m, uint64_t n, bool grid) {
+    return m * n + n * n + m + 6 * n + (grid ? kMaxTeamCtas : 8);
+}
+
+template <bool GRID>
+struct Team {
+    uint32_t tid, size;
+    __device__ Team() {
+        if (GRID) {
+            tid = blockIdx.x * blockDim.x + threadIdx.x;
+            size = gridDim.x * blockDim.x;
+        } else {
+            tid = threadIdx.x;
+            size = blockDim.x;
+        }
     }
+    __device__ void sync() const {
+        if (GRID) cg::this_grid().sync();
+        else __syncthreads();
+    }
+};
+
+// Loads of data other CTAs of the team may have written go to L2 in the grid deployment.
+template <bool GRID>
+__device__ __forceinline__ double ld(const double* p) {
+    if (GRID) return __ldcg(p);
+    return *p;
+}
+
+template <bool GRID>
+__device__ void freedom_problem(const FreedomArgs& a, const Team<GRID>& team, double* W, const double* jac, uint32_t* mask,
+                                double* vstage, uint32_t* sh_u, double* sh_d) {
+    const uint32_t m = a.m, n = a.n;
     const uint32_t ndiag = m < n ? m : n;
+    double* A = W;
+    double* N = A + (size_t)m * n;
+    double* v = N + (size_t)n * n;
+    double* norms = v + m;
+    double* dk = norms + n;
+    double* perm = dk + n;
+    double* rdiag = perm + n;
+    double* part = rdiag + n;
+    double* sdot = part + n;
+    double* red = sdot + n;  // [256] per-CTA partial results of team-wide reductions
+    // ---- densify (thread per column; find_dof.rs:16-18)
+    for (uint32_t j = team.tid; j < n; j += team.size) {
+        for (uint32_t i = 0; i < m; ++i) A[(size_t)i * n + j] = 0.0;
+        for (uint32_t e = a.csc_col_ptr[j]; e < a.csc_col_ptr[j + 1]; ++e) A[(size_t)a.csc_row_idx[e] * n + j] = jac[e];
+        perm[j] = (double)j;
+    }
+    team.sync();
+    // ---- column-pivoted Householder QR
+    bool norms_valid = false;
     for (uint32_t k = 0; k < ndiag; ++k) {
-        uint32_t best = k;
+        if (!norms_valid) {  // squared norms of the remaining columns over rows k.. (first step, or after a zero pivot)
+            for (uint32_t j = k + team.tid; j < n; j += team.size) {
+                double s = 0.0;
+                for (uint32_t i = k; i < m; ++i) {
+                    const double x = ld<GRID>(&A[(size_t)i * n + j]);
+                    s += x * x;
+                }
+                norms[j] = s;
+                dk[j] = ld<GRID>(&A[(size_t)k * n + j]);
+            }
+            team.sync();
+        }
+        // pivot: the largest remaining norm, the first one among equals (every CTA computes it for itself)
         double bestn = -1.0;
-        for (uint32_t j = k; j < n; ++j) {
-            double s = 0.0;
-            for (uint32_t i = k; i < m; ++i) s += AE(i, j) * AE(i, j);
+        uint32_t best = k;
+        for (uint32_t j = k + threadIdx.x; j < n; j += blockDim.x) {
+            const double s = ld<GRID>(&norms[j]);
             if (s > bestn) {
                 bestn = s;
                 best = j;
             }
         }
-        if (best != k) {
-            for (uint32_t i = 0; i < m; ++i) {
-                const double tmp = AE(i, k);
-                AE(i, k) = AE(i, best);
-                AE(i, best) = tmp;
+        for (int off = 16; off > 0; off >>= 1) {
+            const double ob = __shfl_down_sync(0xffffffffu, bestn, off);
+            const uint32_t oj = __shfl_down_sync(0xffffffffu, best, off);
+            if (ob > bestn || (ob == bestn && oj < best)) {
+                bestn = ob;
+                best = oj;
             }
-            const double tp = perm[(size_t)k * TT];
-            perm[(size_t)k * TT] = perm[(size_t)best * TT];
-            perm[(size_t)best * TT] = tp;
+        }
+        if (blockDim.x > 32) {
+            __syncthreads();
+            if ((threadIdx.x & 31u) == 0) {
+                sh_d[threadIdx.x >> 5] = bestn;
+                sh_u[threadIdx.x >> 5] = best;
+            }
+            __syncthreads();
+            if (threadIdx.x < 32) {
+                const uint32_t nw = blockDim.x >> 5;
+                bestn = threadIdx.x < nw ? sh_d[threadIdx.x] : -2.0;
+                best = threadIdx.x < nw ? sh_u[threadIdx.x] : 0xffffffffu;
+                for (int off = 16; off > 0; off >>= 1) {
+                    const double ob = __shfl_down_sync(0xffffffffu, bestn, off);
+                    const uint32_t oj = __shfl_down_sync(0xffffffffu, best, off);
+                    if (ob > bestn || (ob == bestn && oj < best)) {
+                        bestn = ob;
+                        best = oj;
+                    }
+                }
+                if (threadIdx.x == 0) {
+                    sh_d[32] = bestn;
+                    sh_u[32] = best;
+                }
+            }
+            __syncthreads();
+            bestn = sh_d[32];
+            best = sh_u[32];
+        } else {
+            bestn = __shfl_sync(0xffffffffu, bestn, 0);
+            best = __shfl_sync(0xffffffffu, best, 0);
         }
         const double norm = sqrt(bestn);
-        if (norm == 0.0) {
-            rdiag[(size_t)k * TT] = 0.0;
-            continue;
-        }
-        const double akk = AE(k, k);
+        const bool zero = norm == 0.0;
+        const double akk = ld<GRID>(&dk[best]);  // A(k, best) before the swap
         const double alpha = akk > 0 ? -norm : norm;
         const double vk = akk - alpha;
-        for (uint32_t i = k + 1; i < m; ++i) AE(i, k) = AE(i, k) / vk;
         const double tau = -vk / alpha;
-        AE(k, k) = alpha;
-        rdiag[(size_t)k * TT] = alpha;
-        for (uint32_t j = k + 1; j < n; ++j) {
-            double s = AE(k, j);
-            for (uint32_t i = k + 1; i < m; ++i) s += AE(i, k) * AE(i, j);
-            s *= tau;
-            AE(k, j) -= s;
-            for (uint32_t i = k + 1; i < m; ++i) AE(i, j) -= s * AE(i, k);
+        // swap columns k and best in every row; form v below the diagonal (thread per row)
+        for (uint32_t i = team.tid; i < m; i += team.size) {
+            const double ab = ld<GRID>(&A[(size_t)i * n + best]);
+            if (best != k) A[(size_t)i * n + best] = ld<GRID>(&A[(size_t)i * n + k]);
+            if (zero || i < k) A[(size_t)i * n + k] = ab;
+            else if (i == k) A[(size_t)i * n + k] = alpha;
+            else v[i] = ab / vk;
         }
+        if (team.tid == 0) {
+            const double tp = perm[k];
+            perm[k] = perm[best];
+            perm[best] = tp;
+            rdiag[k] = zero ? 0.0 : alpha;
+        }
+        team.sync();
+        if (zero) {
+            norms_valid = false;
+            continue;
+        }
+        // per column j > k: s = (A(k,j) + sum_i v_i A(i,j)) tau;  A(k,j) -= s;  A(i,j) -= s v_i;  next norm over rows k+1..
+        const double* vv = v;
+        if (vstage) {  // global deployments: the CTA stages v in shared memory once per step
+            const uint32_t len = m - (k + 1);
+            if (len <= a.v_smem) {
+                for (uint32_t i = threadIdx.x; i < len; i += blockDim.x) vstage[i] = ld<GRID>(&v[k + 1 + i]);
+                __syncthreads();
+                vv = vstage - (k + 1);
+            }
+        }
+        const bool v_l2 = GRID && vv == v;
+        for (uint32_t j = k + 1 + team.tid; j < n; j += team.size) {
+            double* col = A + j;
+            double s = ld<GRID>(&col[(size_t)k * n]);
+            const double akj = s;
+            for (uint32_t i = k + 1; i < m; ++i) s += (v_l2 ? __ldcg(&vv[i]) : vv[i]) * ld<GRID>(&col[(size_t)i * n]);
+            s *= tau;
+            col[(size_t)k * n] = akj - s;
+            double nrm = 0.0, first = 0.0;
+            for (uint32_t i = k + 1; i < m; ++i) {
+                const double x = ld<GRID>(&col[(size_t)i * n]) - s * (v_l2 ? __ldcg(&vv[i]) : vv[i]);
+                col[(size_t)i * n] = x;
+                nrm += x * x;
+                if (i == k + 1) first = x;
+            }
+            norms[j] = nrm;
+            dk[j] = first;
+        }
+        norms_valid = true;
+        team.sync();
     }
-    uint32_t* mask = a.mask + (size_t)t * a.words;
-    for (uint32_t w = 0; w < a.words; ++w) mask[w] = 0;
-    double largest = ezm::ez_abs(rdiag[0]);
-    for (uint32_t i = 1; i < ndiag; ++i) largest = ezm::ez_fmax(largest, ezm::ez_abs(rdiag[(size_t)i * TT]));
+    // ---- rank (find_dof.rs:40-52)
+    double largest = ezm::ez_abs(ld<GRID>(&rdiag[0]));
+    for (uint32_t i = 1; i < ndiag; ++i) largest = ezm::ez_fmax(largest, ezm::ez_abs(ld<GRID>(&rdiag[i])));
     const double tolerance = 1e-8 * largest;
     uint32_t rank = 0;
-    while (rank < ndiag && ezm::ez_abs(rdiag[(size_t)rank * TT]) > tolerance) ++rank;
-    const uint32_t nullity = n - rank;
-    if (nullity == 0) return;
-    for (uint32_t f = 0; f < nullity; ++f) {
-        const uint32_t free_var = rank + f;
-        for (uint32_t i = 0; i < n; ++i) NE(i, f) = 0.0;
-        NE(free_var, f) = 1.0;
+    while (rank < ndiag && ezm::ez_abs(ld<GRID>(&rdiag[rank])) > tolerance) ++rank;
+    const uint32_t F = n - rank;
+    if (F == 0) {
+        for (uint32_t w = team.tid; w < a.words; w += team.size) mask[w] = 0;
+        team.sync();  // (the work area is reused by the next problem of this team)
+        return;
+    }
+    // ---- basis of null(J P^T): thread per free column f, back substitution over R11 (find_dof.rs:56-72)
+    for (uint32_t f = team.tid; f < F; f += team.size) {
+        for (uint32_t i = rank; i < n; ++i) N[(size_t)i * F + f] = (i == rank + f) ? 1.0 : 0.0;
         for (uint32_t ii = rank; ii-- > 0;) {
-            double rhs = AE(ii, free_var);
-            for (uint32_t j = ii + 1; j < rank; ++j) rhs += AE(ii, j) * NE(j, f);
-            NE(ii, f) = -rhs / AE(ii, ii);
+            const double* Rrow = A + (size_t)ii * n;
+            double rhs = ld<GRID>(&Rrow[rank + f]);
+            for (uint32_t j = ii + 1; j < rank; ++j) rhs += ld<GRID>(&Rrow[j]) * ld<GRID>(&N[(size_t)j * F + f]);
+            N[(size_t)ii * F + f] = -rhs / ld<GRID>(&Rrow[ii]);
         }
     }
-    for (uint32_t f = 0; f < nullity; ++f) {
-        for (int pass = 0; pass < 2; ++pass)
-            for (uint32_t g = 0; g < f; ++g) {
+    team.sync();
+    // ---- orthonormalise the columns of N: Gram-Schmidt against all earlier columns at once, twice, then normalise
+    const uint32_t cta = GRID ? blockIdx.x : 0, n_cta = GRID ? gridDim.x : 1;
+    for (uint32_t f = 0; f < F; ++f) {
+        for (int pass = 0; pass < 2 && f > 0; ++pass) {
+            for (uint32_t g = team.tid; g < f; g += team.size) {  // thread per earlier column
                 double s = 0.0;
-                for (uint32_t i = 0; i < n; ++i) s += NE(i, g) * NE(i, f);
-                for (uint32_t i = 0; i < n; ++i) NE(i, f) -= s * NE(i, g);
+                for (uint32_t i = 0; i < n; ++i) s += ld<GRID>(&N[(size_t)i * F + g]) * ld<GRID>(&N[(size_t)i * F + f]);
+                sdot[g] = s;
             }
-        double s = 0.0;
-        for (uint32_t i = 0; i < n; ++i) s += NE(i, f) * NE(i, f);
-        s = sqrt(s);
-        for (uint32_t i = 0; i < n; ++i) NE(i, f) = NE(i, f) / s;
-    }
-    for (uint32_t f = 0; f < nullity; ++f)
-        for (uint32_t i = 0; i < n; ++i) {
-            const uint32_t var = (uint32_t)perm[(size_t)i * TT];
-            part[(size_t)var * TT] += NE(i, f) * NE(i, f);
+            team.sync();
+            for (uint32_t i = team.tid; i < n; i += team.size) {  // thread per row
+                double* row = N + (size_t)i * F;
+                double z = ld<GRID>(&row[f]);
+                for (uint32_t g = 0; g < f; ++g) z -= ld<GRID>(&sdot[g]) * ld<GRID>(&row[g]);
+                row[f] = z;
+            }
+            team.sync();
         }
+        double s = 0.0;
+        for (uint32_t i = team.tid; i < n; i += team.size) {
+            const double z = ld<GRID>(&N[(size_t)i * F + f]);
+            s += z * z;
+        }
+        for (int off = 16; off > 0; off >>= 1) s += __shfl_down_sync(0xffffffffu, s, off);
+        __syncthreads();
+        if ((threadIdx.x & 31u) == 0) sh_d[threadIdx.x >> 5] = s;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+            for (uint32_t w = 0; w < (blockDim.x + 31) / 32; ++w) t += sh_d[w];
+            red[cta] = t;
+        }
+        team.sync();
+        double total = 0.0;
+        for (uint32_t c = 0; c < n_cta; ++c) total += ld<GRID>(&red[c]);
+        const double nrm = sqrt(total);
+        team.sync();  // (red is rewritten for the next column)
+        for (uint32_t i = team.tid; i < n; i += team.size) N[(size_t)i * F + f] = ld<GRID>(&N[(size_t)i * F + f]) / nrm;
+        team.sync();
+    }
+    // ---- participation of every ORIGINAL variable, threshold, mask (find_dof.rs:82-104)
+    double pmax = 0.0;
+    for (uint32_t i = team.tid; i < n; i += team.size) {
+        const double* row = N + (size_t)i * F;
+        double p = 0.0;
+        for (uint32_t f = 0; f < F; ++f) {
+            const double z = ld<GRID>(&row[f]);
+            p += z * z;
+        }
+        part[(uint32_t)ld<GRID>(&perm[i])] = p;
+        pmax = ezm::ez_fmax(pmax, p);
+    }
+    for (int off = 16; off > 0; off >>= 1) pmax = ezm::ez_fmax(pmax, __shfl_down_sync(0xffffffffu, pmax, off));
+    __syncthreads();
+    if ((threadIdx.x & 31u) == 0) sh_d[threadIdx.x >> 5] = pmax;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (uint32_t w = 0; w < (blockDim.x + 31) / 32; ++w) t = ezm::ez_fmax(t, sh_d[w]);
+        red[cta] = t;
+    }
+    team.sync();
     double max_p = 0.0;
-    for (uint32_t j = 0; j < n; ++j) max_p = ezm::ez_fmax(max_p, part[(size_t)j * TT]);
+    for (uint32_t c = 0; c < n_cta; ++c) max_p = ezm::ez_fmax(max_p, ld<GRID>(&red[c]));
     const double var_tol = 1e-3 * max_p;
     const double squared_tol = var_tol * var_tol;
-    for (uint32_t j = 0; j < n; ++j)
-        if (part[(size_t)j * TT] > squared_tol) mask[j >> 5] |= 1u << (j & 31u);
-#undef AE
-#undef NE
+    for (uint32_t w = team.tid; w < a.words; w += team.size) {
+        uint32_t bits = 0;
+        for (uint32_t b = 0; b < 32 && w * 32 + b < n; ++b)
+            if (ld<GRID>(&part[w * 32 + b]) > squared_tol) bits |= 1u << b;
+        mask[w] = bits;
+    }
+    team.sync();
 }
 
+template <bool GRID>
+__global__ void __launch_bounds__(1024) freedom_team_kernel(const FreedomArgs a) {
+    extern __shared__ double fsm[];
+    __shared__ double sh_d[33];
+    __shared__ uint32_t sh_u[33];
+    const Team<GRID> team;
+    if constexpr (GRID) {
+        for (uint32_t p = 0; p < a.count; ++p)
+            freedom_problem<true>(a, team, a.scratch, a.jac + (size_t)p * a.nnz, a.mask + (size_t)p * a.words,
+                                  a.v_smem ? fsm : nullptr, sh_u, sh_d);
+    } else {
+        for (uint32_t p = blockIdx.x; p < a.count; p += gridDim.x) {
+            double* W = a.in_smem ? fsm : a.scratch + (size_t)blockIdx.x * a.per_problem;
+            freedom_problem<false>(a, team, W, a.jac + (size_t)p * a.nnz, a.mask + (size_t)p * a.words,
+                                   (!a.in_smem && a.v_smem) ? fsm : nullptr, sh_u, sh_d);
+        }
+    }
+}
+
+std::mutex g_attr_mutex;
+
 }  // namespace
+
+namespace ezs {
+
+// Device-resident form: `d_jac` [batch * nnz] and `d_mask` [batch * ceil(n/32)] are device pointers on the context's device; the
+// kernels are enqueued on `st`, nothing is copied to or from the host and the call does not synchronise.
+int32_t freedom_device(ezpz_context* ctx, const ezpz_structure* s, uint64_t batch, const double* d_jac, uint32_t* d_mask,
+                       cudaStream_t st, ezpz_error_detail_t* detail) {
+    const uint32_t m = s->m, n = s->n;
+    if (std::min(m, n) == 0) return EZPZ_ERR_EMPTY_SYSTEM;  // find_dof.rs:41-44
+    if (batch == 0) return EZPZ_OK;
+    EZ_CUDA(cudaSetDevice(ctx->device), "cudaSetDevice");
+    DeviceCopy* dc = nullptr;
+    int32_t rc = get_device_copy(ctx, s, &dc, detail);
+    if (rc != EZPZ_OK) return rc;
+    const size_t nnz = s->csc_row_idx.size();
+    {
+        std::lock_guard<std::mutex> lock(const_cast<ezpz_structure*>(s)->dev_mutex);
+        if (!dc->csc_col_ptr) {
+            EZ_CUDA(cudaMalloc(&dc->csc_col_ptr, sizeof(uint32_t) * (n + 1)), "cudaMalloc(col_ptr)");
+            EZ_CUDA(cudaMemcpy(dc->csc_col_ptr, s->csc_col_ptr.data(), sizeof(uint32_t) * (n + 1), cudaMemcpyHostToDevice), "cudaMemcpy(col_ptr)");
+            EZ_CUDA(cudaMalloc(&dc->csc_row_idx, sizeof(uint32_t) * std::max<size_t>(1, nnz)), "cudaMalloc(row_idx)");
+            if (nnz) EZ_CUDA(cudaMemcpy(dc->csc_row_idx, s->csc_row_idx.data(), sizeof(uint32_t) * nnz, cudaMemcpyHostToDevice), "cudaMemcpy(row_idx)");
+        }
+    }
+    const uint64_t per_cta = freedom_doubles(m, n, false), per_grid = freedom_doubles(m, n, true);
+    uint64_t per = per_cta;
+    FreedomArgs a;
+    a.csc_col_ptr = dc->csc_col_ptr;
+    a.csc_row_idx = dc->csc_row_idx;
+    a.m = m;
+    a.n = n;
+    a.nnz = (uint32_t)nnz;
+    a.words = (n + 31) / 32;
+    a.scratch = nullptr;
+    // the work area of a team is reused launch after launch: launches of different streams take turns
+    if (ctx->fa_busy && ctx->fa_last_stream != st) EZ_CUDA(cudaStreamWaitEvent(st, ctx->fa_done, 0), "cudaStreamWaitEvent");
+    const size_t smem_cap = ctx->smem_optin - 1024;
+    const bool small = per * 8 <= (size_t)64 << 10;                       // matrix in shared memory
+    const bool cta_team = small || (n <= 1024 && batch >= (uint64_t)ctx->sm_count / 2);
+    if (!cta_team) per = per_grid;
+    a.per_problem = per;
+    {
+        std::lock_guard<std::mutex> lock(g_attr_mutex);
+        static bool attr_set[64] = {};
+        if (ctx->device < 64 && !attr_set[ctx->device]) {
+            EZ_CUDA(cudaFuncSetAttribute((const void*)freedom_team_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap), "cudaFuncSetAttribute");
+            EZ_CUDA(cudaFuncSetAttribute((const void*)freedom_team_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap), "cudaFuncSetAttribute");
+            attr_set[ctx->device] = true;
+        }
+    }
+    if (cta_team) {
+        const uint32_t threads = std::min<uint32_t>(1024, std::max<uint32_t>(32, (std::max(n, small ? 0u : std::min(m, 256u)) + 31) / 32 * 32));
+        uint64_t done = 0;
+        while (done < batch) {
+            uint64_t count = batch - done;
+            size_t smem = 0;
+            uint32_t grid;
+            if (small) {
+                a.in_smem = 1;
+                a.v_smem = 0;
+                smem = per * 8;
+                count = std::min<uint64_t>(count, 1u << 30);
+                grid = (uint32_t)count;
+            } else {
+                a.in_smem = 0;
+                a.v_smem = (uint32_t)std::min<size_t>(m, ((size_t)48 << 10) / 8);
+                smem = (size_t)a.v_smem * 8;
+                const uint64_t slots = std::max<uint64_t>(1, std::min<uint64_t>(count, ((uint64_t)1 << 30) / (per * 8)));
+                rc = ensure_fa(ctx, slots * per * 8, detail);
+                if (rc != EZPZ_OK) return rc;
+                a.scratch = (double*)ctx->fa_ws;
+                grid = (uint32_t)slots;
+            }
+            a.jac = d_jac + done * nnz;
+            a.mask = d_mask + done * a.words;
+            a.count = (uint32_t)std::min<uint64_t>(count, 0xffffffffu);
+            freedom_team_kernel<false><<<grid, threads, smem, st>>>(a);
+            ctx->launches += 1;
+            EZ_CUDA(cudaGetLastError(), "freedom_team_kernel launch");
+            done += a.count;
+        }
+    } else {
+        // the whole grid on one problem after the other: one warp per SM while the columns fit (every column's chain of sums is
+        // the critical path, and an SM's L2 bandwidth is shared by its warps), more warps per CTA beyond
+        rc = ensure_fa(ctx, per * 8, detail);
+        if (rc != EZPZ_OK) return rc;
+        a.scratch = (double*)ctx->fa_ws;
+        a.in_smem = 0;
+        uint32_t threads = (uint32_t)std::min<uint64_t>(1024, ((uint64_t)(n + ctx->sm_count - 1) / ctx->sm_count + 31) / 32 * 32);
+        threads = std::max(32u, threads);
+        a.v_smem = (uint32_t)std::min<size_t>(m, ((size_t)64 << 10) / 8);
+        const size_t smem = (size_t)a.v_smem * 8;
+        int per_sm = 0;
+        EZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, freedom_team_kernel<true>, (int)threads, smem), "occupancy");
+        const uint32_t grid = std::max(1u, std::min<uint32_t>(std::min<uint32_t>((uint32_t)std::max(1, per_sm) * ctx->sm_count, kMaxTeamCtas),
+                                                              (n + threads - 1) / threads));
+        uint64_t done = 0;
+        while (done < batch) {
+            a.jac = d_jac + done * nnz;
+            a.mask = d_mask + done * a.words;
+            a.count = (uint32_t)std::min<uint64_t>(batch - done, 1u << 20);
+            void* params[] = {(void*)&a};
+            EZ_CUDA(cudaLaunchCooperativeKernel((void*)freedom_team_kernel<true>, dim3(grid), dim3(threads), params, smem, st),
+                    "cudaLaunchCooperativeKernel(freedom_team_kernel)");
+            ctx->launches += 1;
+            done += a.count;
+        }
+    }
+    if (!ctx->fa_done) EZ_CUDA(cudaEventCreateWithFlags(&ctx->fa_done, cudaEventDisableTiming), "cudaEventCreate");
+    EZ_CUDA(cudaEventRecord(ctx->fa_done, st), "cudaEventRecord");
+    ctx->fa_busy = true;
+    ctx->fa_last_stream = st;
+    return EZPZ_OK;
+}
+
+}  // namespace ezs
+
+extern "C" int32_t ezpz_b200_freedom_analysis_device(ezpz_context_t* ctx, const ezpz_structure_t* s, uint64_t batch,
+                                                     const double* jacobian, uint32_t* under_mask, void* cuda_stream,
+                                                     ezpz_error_detail_t* detail) {
+    if (!ctx || !s || !under_mask || (batch && !jacobian)) return EZPZ_ERR_INVALID_ARGUMENT;
+    if (detail) std::memset(detail, 0, sizeof *detail);
+    return ezs::freedom_device(ctx, s, batch, jacobian, under_mask, cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream, detail);
+}
 
 extern "C" int32_t ezpz_b200_freedom_analysis(ezpz_context_t* ctx, const ezpz_structure_t* s, uint64_t batch,
                                               const double* jacobian, uint32_t* under_mask,
                                               ezpz_error_detail_t* detail) {
     if (!ctx || !s || !under_mask || (batch && !jacobian)) return EZPZ_ERR_INVALID_ARGUMENT;
     if (detail) std::memset(detail, 0, sizeof *detail);
-    const uint32_t m = s->m, n = s->n;
-    if (std::min(m, n) == 0) return EZPZ_ERR_EMPTY_SYSTEM;  // find_dof.rs:41-44
-    if (n > 256) {
-        if (detail) std::snprintf(detail->message, sizeof detail->message, "freedom analysis is dense O(m n^2); n = %u > 256", n);
-        return EZPZ_ERR_TOO_LARGE;
-    }
+    if (std::min(s->m, s->n) == 0) return EZPZ_ERR_EMPTY_SYSTEM;
     if (batch == 0) return EZPZ_OK;
     EZ_CUDA(cudaSetDevice(ctx->device), "cudaSetDevice");
-    const size_t nnz = s->csc_row_idx.size();
-    const uint32_t words = (n + 31) / 32;
-    const size_t per_thread = (size_t)m * n + (size_t)n * n + 2 * (size_t)n + std::min(m, n);
-    // chunk so that the scratch stays below 256 MiB
-    size_t chunk = std::max<size_t>(128, ((size_t)256 << 20) / (per_thread * 8) / 128 * 128);
-    chunk = std::min<size_t>(chunk, (batch + 127) / 128 * 128);
-    const size_t b_ptr = ezs::align_up((n + 1) * 4, 256), b_idx = ezs::align_up(nnz * 4, 256);
+    const size_t nnz = s->csc_row_idx.size(), words = (s->n + 31) / 32;
+    // host buffers: staged through the context's workspace in chunks of at most 256 MiB of Jacobian values
+    const uint64_t chunk = std::max<uint64_t>(1, std::min<uint64_t>(batch, ((uint64_t)256 << 20) / std::max<size_t>(8, nnz * 8)));
     const size_t b_jac = ezs::align_up(chunk * nnz * 8, 256), b_mask = ezs::align_up(chunk * words * 4, 256);
-    const size_t b_scr = ezs::align_up(per_thread * chunk * 8, 256);
-    int32_t rc = ezs::ensure_ws(ctx, b_ptr + b_idx + b_jac + b_mask + b_scr, detail);
+    int32_t rc = ezs::ensure_ws(ctx, b_jac + b_mask, detail);
     if (rc != EZPZ_OK) return rc;
-    char* w = (char*)ctx->ws;
-    uint32_t* d_ptr = (uint32_t*)w; w += b_ptr;
-    uint32_t* d_idx = (uint32_t*)w; w += b_idx;
-    double* d_jac = (double*)w; w += b_jac;
-    uint32_t* d_mask = (uint32_t*)w; w += b_mask;
-    double* d_scr = (double*)w;
+    double* d_jac = (double*)ctx->ws;
+    uint32_t* d_mask = (uint32_t*)((char*)ctx->ws + b_jac);
     cudaStream_t st = ctx->stream;
-    EZ_CUDA(cudaMemcpyAsync(d_ptr, s->csc_col_ptr.data(), (n + 1) * 4, cudaMemcpyHostToDevice, st), "H2D col_ptr");
-    if (nnz) EZ_CUDA(cudaMemcpyAsync(d_idx, s->csc_row_idx.data(), nnz * 4, cudaMemcpyHostToDevice, st), "H2D row_idx");
     for (uint64_t first = 0; first < batch; first += chunk) {
-        const uint32_t count = (uint32_t)std::min<uint64_t>(chunk, batch - first);
-        if (nnz) EZ_CUDA(cudaMemcpyAsync(d_jac, jacobian + first * nnz, (size_t)count * nnz * 8, cudaMemcpyHostToDevice, st), "H2D jacobian");
-        FreedomArgs a;
-        a.csc_col_ptr = d_ptr;
-        a.csc_row_idx = d_idx;
-        a.jac = d_jac;
-        a.mask = d_mask;
-        a.scratch = d_scr;
-        a.m = m;
-        a.n = n;
-        a.nnz = (uint32_t)nnz;
-        a.words = words;
-        a.count = count;
-        a.threads = (uint32_t)chunk;
-        freedom_kernel<<<(count + 127) / 128, 128, 0, st>>>(a);
-        ctx->launches += 1;
-        EZ_CUDA(cudaGetLastError(), "freedom_kernel launch");
-        EZ_CUDA(cudaMemcpyAsync(under_mask + first * words, d_mask, (size_t)count * words * 4, cudaMemcpyDeviceToHost, st), "D2H mask");
-        EZ_CUDA(cudaStreamSynchronize(st), "cudaStreamSynchronize");
+        const uint64_t count = std::min<uint64_t>(chunk, batch - first);
+        if (nnz) EZ_CUDA(cudaMemcpyAsync(d_jac, jacobian + first * nnz, count * nnz * 8, cudaMemcpyHostToDevice, st), "H2D jacobian");
+        rc = ezs::freedom_device(ctx, s, count, d_jac, d_mask, st, detail);
+        if (rc == EZPZ_OK) {
+            cudaError_t e = cudaMemcpyAsync(under_mask + first * words, d_mask, count * words * 4, cudaMemcpyDeviceToHost, st);
+            if (e != cudaSuccess) rc = ezs::cuda_fail(e, detail, "D2H mask");
+        }
+        cudaError_t e = cudaStreamSynchronize(st);  // (also on failure: nothing of this call is still in flight on return)
+        if (rc != EZPZ_OK) return rc;
+        if (e != cudaSuccess) return ezs::cuda_fail(e, detail, "cudaStreamSynchronize");
     }
     return EZPZ_OK;
 }

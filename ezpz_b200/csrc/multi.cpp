@@ -172,6 +172,7 @@ int32_t ezpz_b200_solve_batch_multi(ezpz_multi_t* mg, const ezpz_structure_t* s,
         job.io.unsat_mask = io->unsat_mask ? io->unsat_mask + b0 * uw : nullptr;
         job.io.degen_count = io->degen_count ? io->degen_count + b0 * nc : nullptr;
         job.io.jacobian = io->jacobian ? io->jacobian + b0 * nnz : nullptr;
+        job.io.under_mask = io->under_mask ? io->under_mask + b0 * ((s->n + 31) / 32) : nullptr;
         {
             std::lock_guard<std::mutex> lock(w->m);
             w->job = job;

@@ -27,7 +27,7 @@ class ErrorDetail(C.Structure):
 class BatchIO(C.Structure):
     _fields_ = [("guesses", C.c_void_p), ("params", C.c_void_p), ("final_values", C.c_void_p),
                 ("iterations", C.c_void_p), ("status", C.c_void_p), ("unsat_mask", C.c_void_p),
-                ("degen_count", C.c_void_p), ("jacobian", C.c_void_p)]
+                ("degen_count", C.c_void_p), ("jacobian", C.c_void_p), ("under_mask", C.c_void_p)]
 
 
 class OneIO(C.Structure):
@@ -91,6 +91,7 @@ _SYMBOLS = [
                                           C.POINTER(ErrorDetail)]),
     ("ezpz_b200_eval", C.c_int32, [_P, _P, _P, _P, _P, _P, _P, C.POINTER(ErrorDetail)]),
     ("ezpz_b200_freedom_analysis", C.c_int32, [_P, _P, C.c_uint64, _P, _P, C.POINTER(ErrorDetail)]),
+    ("ezpz_b200_freedom_analysis_device", C.c_int32, [_P, _P, C.c_uint64, _P, _P, _P, C.POINTER(ErrorDetail)]),
     ("ezpz_b200_solve", C.c_int32, [_P, _P, _P, _P, C.c_uint32, _P, _P, C.c_uint32, C.POINTER(Config), C.c_int32,
                                     C.POINTER(OutcomeRec), C.POINTER(ErrorDetail)]),
     ("ezpz_b200_solve_batch_priorities", C.c_int32, [_P, _P, _P, C.c_uint32, C.c_uint32, C.POINTER(Config), C.c_uint64, _P, _P, _P, _P,

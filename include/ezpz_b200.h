@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define EZPZ_B200_ABI_VERSION 2
+#define EZPZ_B200_ABI_VERSION 3
 
 /* ---------------------------------------------------------------------------------------------
  * Constraint record.  One 64-byte record holds any of the 25 variants of `enum Constraint`
@@ -245,6 +245,9 @@ int32_t ezpz_b200_context_synchronize(ezpz_context_t* ctx);
  *   jacobian       [batch * nnz]     optional: the cached Jacobian values (CSC order) at the last
  *                                    accepted point, i.e. what freedom_analysis reads
  *                                    (find_dof.rs:16-18)
+ *   under_mask     [batch * ceil(n/32)] u32 words, optional: bit j set = variable j underconstrained — the freedom analysis
+ *                                    of solve_analysis (lib.rs:134-144, find_dof.rs:15-104) fused into the call: it reads the
+ *                                    Jacobians the solve kernel left on the device, no host round trip in between
  */
 typedef struct ezpz_batch_io {
     const double* guesses;
@@ -255,6 +258,7 @@ typedef struct ezpz_batch_io {
     uint32_t* unsat_mask;
     uint32_t* degen_count;
     double* jacobian;
+    uint32_t* under_mask;
 } ezpz_batch_io_t;
 
 int32_t ezpz_b200_solve_batch(ezpz_context_t* ctx, const ezpz_structure_t* s,
@@ -362,12 +366,17 @@ int32_t ezpz_b200_eval(ezpz_context_t* ctx, const ezpz_structure_t* s, const dou
  * QR of each problem's Jacobian (`jacobian`: [batch * nnz] values in CSC order, as exported by the
  * solve calls), rank by |R_ii| > 1e-8 * max|R_ii|, nullspace participation per variable; variable j is
  * underconstrained iff its participation exceeds (1e-3 * max participation)^2.  Bit j of
- * under_mask[problem * ceil(n/32) + j/32] is set for underconstrained variables.  Host pointers; runs on
- * the device (one thread per problem); EZPZ_ERR_TOO_LARGE beyond 256 variables (the reference's dense
- * O(m n^2) analysis is itself unusable there, tests.rs:140-145). */
+ * under_mask[problem * ceil(n/32) + j/32] is set for underconstrained variables.  Runs on the device for any
+ * number of variables (dense, like the reference's: O(m n) memory, O(m n^2) work): a warp or CTA per problem for
+ * batches of small sketches, the whole GPU on one system after the other for large ones.  Host pointers. */
 int32_t ezpz_b200_freedom_analysis(ezpz_context_t* ctx, const ezpz_structure_t* s, uint64_t batch,
                                    const double* jacobian, uint32_t* under_mask,
                                    ezpz_error_detail_t* detail);
+/* Device-pointer form: `jacobian` and `under_mask` live on the context's device, the kernels are enqueued on
+ * `cuda_stream` (NULL = the context's own stream) and the call returns without synchronising. */
+int32_t ezpz_b200_freedom_analysis_device(ezpz_context_t* ctx, const ezpz_structure_t* s, uint64_t batch,
+                                          const double* jacobian, uint32_t* under_mask, void* cuda_stream,
+                                          ezpz_error_detail_t* detail);
 
 /* ---------------------------------------------------------------------------------------------
  * ezpz::solve / ezpz::solve_analysis (lib.rs:80-144) with flat arguments: the priority loop

@@ -952,9 +952,15 @@ int32_t orc_step(const orc::Rec* cons, uint32_t n_cons, uint32_t n_vars, const d
 //   hoist_analysis == 0: every solve repeats Model::new (what the reference does, lib.rs:279);
 //   hoist_analysis == 1: pattern + symbolic analysis done once per thread and reused.
 // status bit0 converged, bit1 unsatisfied, bit2 degenerate.
-int32_t orc_solve_batch(const orc::Rec* cons, uint32_t n_cons, uint32_t n_vars, const orc::Cfg* cfg, uint64_t batch,
-                        const double* guesses, const double* params, double* finals, uint32_t* iterations,
-                        uint8_t* status, uint32_t nthreads, int32_t hoist_analysis) {
+// Batch of solves on host threads.  Optional verdict outputs (bench.py / tests, full verdict parity of config 5):
+//   unsat_mask [batch * ceil(n_cons/32)]  bit c = constraint c unsatisfied (lib.rs:305-327)
+//   under_mask [batch * ceil(n_vars/32)]  bit j = variable j underconstrained (find_dof.rs:15-104); problems whose analysis
+//                                         errors (EmptySystemNotAllowed) get an all-ones first word marker 0xFFFFFFFF
+int32_t orc_solve_batch_verdicts(const orc::Rec* cons, uint32_t n_cons, uint32_t n_vars, const orc::Cfg* cfg, uint64_t batch,
+                                 const double* guesses, const double* params, double* finals, uint32_t* iterations,
+                                 uint8_t* status, uint32_t nthreads, int32_t hoist_analysis, uint32_t* unsat_mask,
+                                 uint32_t* under_mask) {
+    const uint32_t uw = (n_cons + 31) / 32, vw = (n_vars + 31) / 32;
     if (nthreads == 0) nthreads = std::max(1u, std::thread::hardware_concurrency());
     std::atomic<uint64_t> next(0);
     std::atomic<int32_t> err(0);
@@ -976,8 +982,8 @@ int32_t orc_solve_batch(const orc::Rec* cons, uint32_t n_cons, uint32_t n_vars, 
                 int32_t rc;
                 if (!hoist_analysis) {
                     orc::ErrDetail det;
-                    rc = orc::solve_inner(c.data(), nullptr, nullptr, n_cons, nullptr, g, n_vars, po, *cfg, false, o,
-                                          &det, nullptr);
+                    rc = orc::solve_inner(c.data(), nullptr, nullptr, n_cons, nullptr, g, n_vars, po, *cfg,
+                                          under_mask != nullptr, o, &det, nullptr);
                 } else {
                     if (!have_model) {
                         hoisted.n_cons = n_cons;
@@ -1003,9 +1009,20 @@ int32_t orc_solve_batch(const orc::Rec* cons, uint32_t n_cons, uint32_t n_vars, 
                             if (!sat) o.unsatisfied.push_back(ci);
                         }
                         o.degen_count = hoisted.degen_count;
+                        if (under_mask) rc = orc::freedom_analysis(hoisted, o.underconstrained);
                     }
                 }
                 if (rc != orc::OK) { err = rc; return; }
+                if (unsat_mask) {
+                    uint32_t* um = unsat_mask + b * uw;
+                    std::fill(um, um + uw, 0u);
+                    for (uint64_t ci : o.unsatisfied) um[ci >> 5] |= 1u << (ci & 31u);
+                }
+                if (under_mask) {
+                    uint32_t* vm = under_mask + b * vw;
+                    std::fill(vm, vm + vw, 0u);
+                    for (uint32_t v : o.underconstrained) vm[v >> 5] |= 1u << (v & 31u);
+                }
                 std::copy(o.final_values.begin(), o.final_values.end(), finals + b * n_vars);
                 iterations[b] = (uint32_t)o.iterations;
                 bool dg = false;
@@ -1019,6 +1036,13 @@ int32_t orc_solve_batch(const orc::Rec* cons, uint32_t n_cons, uint32_t n_vars, 
     worker();
     for (auto& t : th) t.join();
     return err.load();
+}
+
+int32_t orc_solve_batch(const orc::Rec* cons, uint32_t n_cons, uint32_t n_vars, const orc::Cfg* cfg, uint64_t batch,
+                        const double* guesses, const double* params, double* finals, uint32_t* iterations,
+                        uint8_t* status, uint32_t nthreads, int32_t hoist_analysis) {
+    return orc_solve_batch_verdicts(cons, n_cons, n_vars, cfg, batch, guesses, params, finals, iterations, status, nthreads,
+                                    hoist_analysis, nullptr, nullptr);
 }
 
 // Scalar functions, exported so tests can compare the device versions bit for bit.

@@ -236,7 +236,9 @@ def evaluate(recs, n_vars, x):
     return r, j, dg, pat
 
 
-def solve_batch(recs, n_vars, guesses, params=None, cfg=None, nthreads=0, hoist=False):
+def solve_batch(recs, n_vars, guesses, params=None, cfg=None, nthreads=0, hoist=False, verdicts=False):
+    """Batch of oracle solves on host threads -> (finals, iterations, status) [+ (unsat_mask, under_mask) with verdicts=True:
+    per problem the unsatisfied constraint bits and the underconstrained variable bits of solve_analysis]."""
     L = lib()
     recs = as_recs(recs)
     g = np.ascontiguousarray(guesses, dtype=np.float64).reshape(-1, n_vars)
@@ -246,11 +248,15 @@ def solve_batch(recs, n_vars, guesses, params=None, cfg=None, nthreads=0, hoist=
     fin = np.zeros_like(g)
     it = np.zeros(B, np.uint32)
     st = np.zeros(B, np.uint8)
-    rc = L.orc_solve_batch(recs.ctypes.data_as(C.c_void_p), C.c_uint32(len(recs)), C.c_uint32(n_vars),
-                           C.byref(cfg), C.c_uint64(B), _p(g, C.c_double), _p(po, C.c_double),
-                           _p(fin, C.c_double), _p(it, C.c_uint32), _p(st, C.c_uint8), C.c_uint32(nthreads),
-                           C.c_int32(1 if hoist else 0))
+    um = np.zeros((B, (len(recs) + 31) // 32), np.uint32) if verdicts else None
+    vm = np.zeros((B, (n_vars + 31) // 32), np.uint32) if verdicts else None
+    rc = L.orc_solve_batch_verdicts(recs.ctypes.data_as(C.c_void_p), C.c_uint32(len(recs)), C.c_uint32(n_vars),
+                                    C.byref(cfg), C.c_uint64(B), _p(g, C.c_double), _p(po, C.c_double),
+                                    _p(fin, C.c_double), _p(it, C.c_uint32), _p(st, C.c_uint8), C.c_uint32(nthreads),
+                                    C.c_int32(1 if hoist else 0), _p(um, C.c_uint32), _p(vm, C.c_uint32))
     assert rc == 0, rc
+    if verdicts:
+        return fin, it, st, um, vm
     return fin, it, st
 
 

@@ -41,7 +41,16 @@ def uniform_pm(seed, count, half_width):
 
 
 def system_from_text(text):
-    """(records, n_vars, guesses, ConstraintSystem) through the product's text pipeline."""
+    """(records, n_vars, guesses, system) through the ORACLE-side reader of the text format (tests/textual_twin.py, pure
+    Python, no product code): the oracle, the CPU arm of bench.py and the GPU path all receive these records, and
+    test_host.py::test_text_readers_agree holds the product's own parser (textual.cpp) to the same bytes."""
+    import textual_twin
+    cs = textual_twin.parse(text)
+    return cs.constraints, cs.num_vars, cs.initial_guesses.copy(), cs
+
+
+def product_system_from_text(text):
+    """The same through the product's text pipeline (ezpz_b200_problem_parse / ezpz_b200_problem_system)."""
     import ezpz_b200 as ez
     cs = ez.textual.Problem(text).to_constraint_system()
     return cs.constraints, cs.num_vars, cs.initial_guesses.copy(), cs
@@ -102,7 +111,7 @@ def chain_sketch(cells, seed=0xE2B20004, noise=0.05):
       R_i by PointsCoincident(R_i.start, B_i), ArcRadius, ArcLength, Arc and Fixed(centre.x).
     15-16 rows per 13 variables (consistent redundancy), one connected component.  `cells` must be a
     multiple of 8.  Returns (records, n_vars, guesses, exact_solution)."""
-    from ezpz_b200 import native
+    import textual_twin as native  # (record dtype only)
     assert cells % 8 == 0 and cells >= 8
     K = cells
     i = np.arange(K)
@@ -186,7 +195,7 @@ def grid_truss(N, seed=0xE2B20006, noise=0.03, weights=False):
     neighbour (a rigid triangulated truss), the first point Fixed in x and y and the second in y.  Its graph has
     separators of ~N points, so the large path's panels are hundreds of rows tall — the opposite regime of
     chain_sketch.  Returns (records, n_vars, guesses, exact_solution)."""
-    from ezpz_b200 import native
+    import textual_twin as native  # (record dtype only)
     gx, gy = np.meshgrid(np.arange(N, dtype=np.float64) * 2.0, np.arange(N, dtype=np.float64) * 1.5, indexing="xy")
     jitter = uniform_pm(seed, 2 * N * N, 0.3).reshape(N, N, 2)
     px, py = gx + jitter[:, :, 0], gy + jitter[:, :, 1]
