@@ -242,7 +242,7 @@ __device__ __forceinline__ void group_rows(char* gbase, uint32_t off0, uint32_t 
     uint32_t p = i / width, j = i - p * width;
     for (; i < total; i += stride) {
         double* s = reinterpret_cast<double*>(gbase + off0 + j * sb + p * 8u);
-        if (LOAD) *s = rows[i];
+        if (LOAD) *s = __ldcg(rows + i);  // (read once; and, streamed, written by the copy engine while the kernel runs)
         else rows[i] = *s;
         p += dp;
         j += dj;
@@ -624,6 +624,8 @@ int32_t get_role_tables(ezpz_context* ctx, const ezpz_structure* cs, DeviceCopy*
     return EZPZ_OK;
 }
 
+constexpr uint64_t kPipelineMinBatch = 32768;  // below: the kernel reads and writes page-locked caller buffers across PCIe itself
+
 struct SmallShape {
     uint32_t T = 0, R = 0;
     size_t smem = 0;
@@ -676,10 +678,12 @@ int32_t small_shape_host(const ezpz_structure* cs, uint64_t batch, uint32_t sm_c
             }
         }
         const size_t tb = probe->words.size() * sizeof(uint32_t);
-        const bool stg = tb <= 64 * 1024 && per_group + tb <= smem_optin;
+        bool stg = tb <= 64 * 1024 && per_group + tb <= smem_optin;
+        if (const char* e = std::getenv("EZPZ_B200_STAGE"); e && e[0] == '0') stg = false;
         if (per_group > smem_optin) continue;
         const size_t avail = smem_optin - (stg ? tb : 0);
-        const uint64_t g = std::min<uint64_t>({avail / per_group, (uint64_t)15, (uint64_t)(max_threads / (32u * cand))});
+        uint64_t g = std::min<uint64_t>({avail / per_group, (uint64_t)15, (uint64_t)(max_threads / (32u * cand))});
+        if (const char* e = std::getenv("EZPZ_B200_GROUPS")) g = std::min<uint64_t>(g, std::max<uint64_t>(1, std::strtoull(e, nullptr, 10)));
         if (g < 1) continue;
         // modelled time: critical path x waves the batch takes x slowdown per resident warp (2.5 % each: the warps of an SM
         // share its issue slots and shared-memory pipe); an open-ended batch (chunk sizing) is scored by throughput
@@ -817,6 +821,9 @@ int32_t ezpz_b200_context_synchronize(ezpz_context_t* ctx) {
     return EZPZ_OK;
 }
 
+static int32_t launch_small(ezpz_context_t* ctx, const ezpz_structure_t* s, const ezpz_config_t* config, uint64_t batch,
+                            const ezpz_batch_io_t* io, cudaStream_t st, ezpz_error_detail_t* detail);
+
 // The solve + freedom analysis form of the batch call (io->under_mask set): the solve kernel leaves its cached Jacobians in a
 // device buffer of the context, freedom_device reads them there.  Batches whose Jacobians exceed 1 GiB go piece by piece.
 static int32_t solve_batch_with_analysis(ezpz_context_t* ctx, const ezpz_structure_t* s, const ezpz_config_t* config, uint64_t batch,
@@ -868,6 +875,13 @@ int32_t ezpz_b200_solve_batch_device(ezpz_context_t* ctx, const ezpz_structure_t
         return solve_batch_with_analysis(ctx, s, config, batch, io, cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream, detail);
     if (!s->small.valid)  // beyond the thread-per-problem kernel: the persistent LM kernel, one CTA per problem
         return ezs::solve_large_batch(ctx, s, config, batch, io, cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream, detail);
+    return launch_small(ctx, s, config, batch, io, cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream, detail);
+}
+
+}  // extern "C"
+
+static int32_t launch_small(ezpz_context_t* ctx, const ezpz_structure_t* s, const ezpz_config_t* config, uint64_t batch,
+                            const ezpz_batch_io_t* io, cudaStream_t st, ezpz_error_detail_t* detail) {
     EZ_CUDA(cudaSetDevice(ctx->device), "cudaSetDevice");
     DeviceCopy* dc = nullptr;
     int32_t rc = get_device_copy(ctx, s, &dc, detail);
@@ -915,7 +929,6 @@ int32_t ezpz_b200_solve_batch_device(ezpz_context_t* ctx, const ezpz_structure_t
     a.weights_one = s->all_weights_one ? 1u : 0u;
     const uint64_t grid = (batch + shape.T - 1) / shape.T;
     if (grid > 0x7fffffffull) return EZPZ_ERR_TOO_LARGE;
-    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
     const unsigned threads = shape.T * shape.R;
 #define EZ_LAUNCH_SMALL(MAXT)                                                                            \
     do {                                                                                                 \
@@ -930,6 +943,8 @@ int32_t ezpz_b200_solve_batch_device(ezpz_context_t* ctx, const ezpz_structure_t
     EZ_CUDA(cudaGetLastError(), "lm_small_kernel launch");
     return EZPZ_OK;
 }
+
+extern "C" {
 
 // Problems per full wave of the batched kernel on this device (the chunks of the copy/compute pipeline are whole waves).
 static uint64_t small_wave_problems(ezpz_context* ctx, const ezpz_structure* s) {
@@ -980,6 +995,12 @@ int32_t ezpz_b200_solve_batch(ezpz_context_t* ctx, const ezpz_structure_t* s, co
         dio.degen_count = (uint32_t*)map(io->degen_count, false);
         dio.jacobian = (double*)map(io->jacobian, false);
         dio.under_mask = (uint32_t*)map(io->under_mask, false);
+        // Larger batches go through the copy/compute pipeline below instead: the copy engines move page-locked memory at link
+        // rate (54-56 GB/s each way), kernel-issued reads across PCIe reach about half of that and stall a wave of CTAs at a
+        // time (tools/time_e2e_split.py, tools/time_e2e_modes.py: 65,536 problems 433 us zero-copy, 347 us pipelined; 8,192
+        // problems 108 us against 147 us).  EZPZ_B200_HOST_MODE=zerocopy|pipeline forces a form.
+        const char* hm = std::getenv("EZPZ_B200_HOST_MODE");
+        if (hm ? hm[0] == 'p' : batch >= kPipelineMinBatch) ok = false;
         if (ok) {
             const int32_t rc = ezpz_b200_solve_batch_device(ctx, s, config, batch, &dio, ctx->stream, detail);
             if (rc != EZPZ_OK) return rc;

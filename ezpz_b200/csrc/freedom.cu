@@ -50,7 +50,7 @@ struct FreedomArgs {
 // rdiag[n] | part[n] | s[n] | red[one per CTA of the team]
 constexpr uint32_t kMaxTeamCtas = 256;
 __host__ __device__ inline uint64_t freedom_doubles(uint64_t m, uint64_t n, bool grid) {
-    return m * n + n * n + m + 6 * n + (grid ? kMaxTeamCtas : 8);
+    return m * n + n * n + m + 6 * n + 8 + (grid ? kMaxTeamCtas : 8);
 }
 
 template <bool GRID>
@@ -87,7 +87,7 @@ __device__ void freedom_problem(const FreedomArgs& a, const Team<GRID>& team, do
     double* N = A + (size_t)m * n;
     double* v = N + (size_t)n * n;
     double* norms = v + m;
-    double* dk = norms + n;
+    double* dk = norms + n + 8;  // (norms holds the pivot candidates: 2 * (n / 32 + 1) <= n + 8 values)
     double* perm = dk + n;
     double* rdiag = perm + n;
     double* part = rdiag + n;
@@ -101,26 +101,63 @@ __device__ void freedom_problem(const FreedomArgs& a, const Team<GRID>& team, do
     }
     team.sync();
     // ---- column-pivoted Householder QR
+    // Pivot candidates: every warp that produces the squared norms of 32 consecutive remaining columns leaves their maximum
+    // (first one among equals) in cand[]; a pivot search then reads (n - k) / 32 pairs instead of n - k norms.
+    const uint32_t lane = threadIdx.x & 31u, warp_first = team.tid - lane;
+    double* cand_v = norms;
+    double* cand_i = norms + (n + 31) / 32 + 1;
+    auto leave_candidate = [&](bool act, double nrm, uint32_t j, uint32_t slot) {
+        double bn = (act && nrm == nrm) ? nrm : -1.0;  // (a NaN norm never wins, as in `s > bestn`)
+        uint32_t bj = (act && nrm == nrm) ? j : 0xffffffffu;
+        for (int off = 16; off > 0; off >>= 1) {
+            const double ob = __shfl_down_sync(0xffffffffu, bn, off);
+            const uint32_t oj = __shfl_down_sync(0xffffffffu, bj, off);
+            if (ob > bn || (ob == bn && oj < bj)) {
+                bn = ob;
+                bj = oj;
+            }
+        }
+        if (lane == 0) {
+            cand_v[slot] = bn;
+            cand_i[slot] = (double)bj;
+        }
+    };
+    constexpr int U = GRID ? 16 : 8;  // loads in flight per thread in the column sweeps
     bool norms_valid = false;
     for (uint32_t k = 0; k < ndiag; ++k) {
         if (!norms_valid) {  // squared norms of the remaining columns over rows k.. (first step, or after a zero pivot)
-            for (uint32_t j = k + team.tid; j < n; j += team.size) {
+            for (uint32_t base = k + warp_first; base < n; base += team.size) {
+                const uint32_t j = base + lane;
+                const bool act = j < n;
                 double s = 0.0;
-                for (uint32_t i = k; i < m; ++i) {
-                    const double x = ld<GRID>(&A[(size_t)i * n + j]);
-                    s += x * x;
+                if (act) {
+                    const double* col = A + j;
+                    uint32_t i = k;
+                    for (; i + U <= m; i += U) {
+                        double x[U];
+#pragma unroll
+                        for (int u = 0; u < U; ++u) x[u] = ld<GRID>(&col[(size_t)(i + u) * n]);
+#pragma unroll
+                        for (int u = 0; u < U; ++u) s += x[u] * x[u];
+                    }
+                    for (; i < m; ++i) {
+                        const double x = ld<GRID>(&col[(size_t)i * n]);
+                        s += x * x;
+                    }
+                    dk[j] = ld<GRID>(&col[(size_t)k * n]);
                 }
-                norms[j] = s;
-                dk[j] = ld<GRID>(&A[(size_t)k * n + j]);
+                leave_candidate(act, s, j, (base - k) / 32);
             }
             team.sync();
         }
         // pivot: the largest remaining norm, the first one among equals (every CTA computes it for itself)
         double bestn = -1.0;
         uint32_t best = k;
-        for (uint32_t j = k + threadIdx.x; j < n; j += blockDim.x) {
-            const double s = ld<GRID>(&norms[j]);
-            if (s > bestn) {
+        const uint32_t n_cand = (n - k + 31) / 32;
+        for (uint32_t c = threadIdx.x; c < n_cand; c += blockDim.x) {
+            const double s = ld<GRID>(&cand_v[c]);
+            const uint32_t j = (uint32_t)ld<GRID>(&cand_i[c]);
+            if (s > bestn || (s == bestn && j < best)) {
                 bestn = s;
                 best = j;
             }
@@ -135,7 +172,7 @@ __device__ void freedom_problem(const FreedomArgs& a, const Team<GRID>& team, do
         }
         if (blockDim.x > 32) {
             __syncthreads();
-            if ((threadIdx.x & 31u) == 0) {
+            if (lane == 0) {
                 sh_d[threadIdx.x >> 5] = bestn;
                 sh_u[threadIdx.x >> 5] = best;
             }
@@ -200,22 +237,50 @@ __device__ void freedom_problem(const FreedomArgs& a, const Team<GRID>& team, do
             }
         }
         const bool v_l2 = GRID && vv == v;
-        for (uint32_t j = k + 1 + team.tid; j < n; j += team.size) {
-            double* col = A + j;
-            double s = ld<GRID>(&col[(size_t)k * n]);
-            const double akj = s;
-            for (uint32_t i = k + 1; i < m; ++i) s += (v_l2 ? __ldcg(&vv[i]) : vv[i]) * ld<GRID>(&col[(size_t)i * n]);
-            s *= tau;
-            col[(size_t)k * n] = akj - s;
-            double nrm = 0.0, first = 0.0;
-            for (uint32_t i = k + 1; i < m; ++i) {
-                const double x = ld<GRID>(&col[(size_t)i * n]) - s * (v_l2 ? __ldcg(&vv[i]) : vv[i]);
-                col[(size_t)i * n] = x;
-                nrm += x * x;
-                if (i == k + 1) first = x;
+        for (uint32_t base = k + 1 + warp_first; base < n; base += team.size) {
+            const uint32_t j = base + lane;
+            const bool act = j < n;
+            double nrm = 0.0;
+            if (act) {
+                double* col = A + j;
+                double s = ld<GRID>(&col[(size_t)k * n]);
+                const double akj = s;
+                uint32_t i = k + 1;
+                for (; i + U <= m; i += U) {
+                    double x[U], w[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        x[u] = ld<GRID>(&col[(size_t)(i + u) * n]);
+                        w[u] = v_l2 ? __ldcg(&vv[i + u]) : vv[i + u];
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; ++u) s += w[u] * x[u];
+                }
+                for (; i < m; ++i) s += (v_l2 ? __ldcg(&vv[i]) : vv[i]) * ld<GRID>(&col[(size_t)i * n]);
+                s *= tau;
+                col[(size_t)k * n] = akj - s;
+                double first = 0.0;
+                i = k + 1;
+                for (; i + U <= m; i += U) {
+                    double x[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) x[u] = ld<GRID>(&col[(size_t)(i + u) * n]) - s * (v_l2 ? __ldcg(&vv[i + u]) : vv[i + u]);
+                    if (i == k + 1) first = x[0];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        col[(size_t)(i + u) * n] = x[u];
+                        nrm += x[u] * x[u];
+                    }
+                }
+                for (; i < m; ++i) {
+                    const double x = ld<GRID>(&col[(size_t)i * n]) - s * (v_l2 ? __ldcg(&vv[i]) : vv[i]);
+                    col[(size_t)i * n] = x;
+                    nrm += x * x;
+                    if (i == k + 1) first = x;
+                }
+                dk[j] = first;
             }
-            norms[j] = nrm;
-            dk[j] = first;
+            leave_candidate(act, nrm, j, (base - (k + 1)) / 32);
         }
         norms_valid = true;
         team.sync();
@@ -319,7 +384,7 @@ __device__ void freedom_problem(const FreedomArgs& a, const Team<GRID>& team, do
 }
 
 template <bool GRID>
-__global__ void __launch_bounds__(1024) freedom_team_kernel(const FreedomArgs a) {
+__global__ void __launch_bounds__(GRID ? 256 : 1024) freedom_team_kernel(const FreedomArgs a) {
     extern __shared__ double fsm[];
     __shared__ double sh_d[33];
     __shared__ uint32_t sh_u[33];
@@ -428,7 +493,7 @@ int32_t freedom_device(ezpz_context* ctx, const ezpz_structure* s, uint64_t batc
         if (rc != EZPZ_OK) return rc;
         a.scratch = (double*)ctx->fa_ws;
         a.in_smem = 0;
-        uint32_t threads = (uint32_t)std::min<uint64_t>(1024, ((uint64_t)(n + ctx->sm_count - 1) / ctx->sm_count + 31) / 32 * 32);
+        uint32_t threads = (uint32_t)std::min<uint64_t>(256, ((uint64_t)(n + ctx->sm_count - 1) / ctx->sm_count + 31) / 32 * 32);
         threads = std::max(32u, threads);
         a.v_smem = (uint32_t)std::min<size_t>(m, ((size_t)64 << 10) / 8);
         const size_t smem = (size_t)a.v_smem * 8;

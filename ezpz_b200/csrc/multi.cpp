@@ -35,6 +35,8 @@ struct Worker {
     std::mutex m;
     std::condition_variable cv;
     bool has_job = false, done = true, quit = false;
+    std::atomic<uint32_t> posted{0};     // jobs handed to this worker so far (what a spinning worker watches)
+    std::atomic<uint32_t> completed{0};  // jobs it has finished (what the caller watches)
     Job job;
     int32_t rc = EZPZ_OK;
     ezpz_error_detail_t detail{};
@@ -49,9 +51,20 @@ struct ezpz_multi {
 
 namespace {
 
+// A wake-up through a condition variable costs tens of microseconds, as much as a shard's kernel.  A worker that has just
+// finished a job therefore watches its counter for a short while (callers solve batch after batch) before it goes to sleep,
+// and the caller watches the completion counters instead of sleeping on the workers' condition variables.
+constexpr int kSpinIterations = 20000;  // ~100-200 us
+
 void worker_main(Worker* w) {
     cudaSetDevice(w->device);
+    uint32_t seen = 0;
     for (;;) {
+        for (int k = 0; k < kSpinIterations && w->posted.load(std::memory_order_acquire) == seen; ++k) {
+#if defined(__x86_64__)
+            __builtin_ia32_pause();
+#endif
+        }
         std::unique_lock<std::mutex> lock(w->m);
         w->cv.wait(lock, [&] { return w->has_job || w->quit; });
         if (w->quit) return;
@@ -62,7 +75,9 @@ void worker_main(Worker* w) {
         lock.lock();
         w->rc = rc;
         w->done = true;
-        w->cv.notify_all();
+        seen = w->posted.load(std::memory_order_acquire);
+        lock.unlock();
+        w->completed.fetch_add(1, std::memory_order_release);
     }
 }
 
@@ -153,7 +168,13 @@ int32_t ezpz_b200_solve_batch_multi(ezpz_multi_t* mg, const ezpz_structure_t* s,
     const size_t nc = s->n_cons, uw = (s->n_cons + 31) / 32;
     // Shards are whole groups of 32 problems (the batched kernel's unit) except the last.
     const uint64_t groups = (batch + 31) / 32;
+    // The calling thread takes the first shard itself, on that worker's context (a context belongs to whoever solves with it,
+    // one at a time; the worker's own thread stays asleep): a one-device multi-context costs no hand-off at all, and with several
+    // devices the workers' wake-up latency hides behind the caller's own shard.
     std::vector<Worker*> used;
+    std::vector<uint32_t> target;
+    Job own;
+    Worker* own_worker = nullptr;
     for (uint32_t k = 0; k < world; ++k) {
         uint64_t g0 = 0, g1 = 0;
         ezpz_b200_shard_range(groups, k, world, &g0, &g1);
@@ -173,19 +194,35 @@ int32_t ezpz_b200_solve_batch_multi(ezpz_multi_t* mg, const ezpz_structure_t* s,
         job.io.degen_count = io->degen_count ? io->degen_count + b0 * nc : nullptr;
         job.io.jacobian = io->jacobian ? io->jacobian + b0 * nnz : nullptr;
         job.io.under_mask = io->under_mask ? io->under_mask + b0 * ((s->n + 31) / 32) : nullptr;
+        if (!own_worker) {
+            own_worker = w;
+            own = job;
+            continue;
+        }
         {
             std::lock_guard<std::mutex> lock(w->m);
             w->job = job;
             w->has_job = true;
             w->done = false;
+            target.push_back(w->completed.load(std::memory_order_relaxed) + 1);
+            w->posted.fetch_add(1, std::memory_order_release);
         }
         w->cv.notify_all();
         used.push_back(w);
     }
     int32_t rc = EZPZ_OK;
-    for (Worker* w : used) {
-        std::unique_lock<std::mutex> lock(w->m);
-        w->cv.wait(lock, [&] { return w->done; });
+    if (own_worker) {
+        rc = ezpz_b200_solve_batch(own_worker->ctx, own.s, own.config, own.count, &own.io, detail);
+    }
+    for (size_t k = 0; k < used.size(); ++k) {
+        Worker* w = used[k];
+        for (uint64_t spins = 0; w->completed.load(std::memory_order_acquire) != target[k]; ++spins) {
+            if (spins > 2000) std::this_thread::yield();
+#if defined(__x86_64__)
+            else __builtin_ia32_pause();
+#endif
+        }
+        std::lock_guard<std::mutex> lock(w->m);
         if (w->rc != EZPZ_OK && rc == EZPZ_OK) {
             rc = w->rc;
             if (detail) *detail = w->detail;
