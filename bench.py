@@ -453,10 +453,19 @@ def run_gpu(args):
         saved_stdout = os.dup(1)
         os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
+        host_group = dist.new_group(backend="gloo")
 
     def barrier():
         if world > 1:
             dist.barrier()
+
+    def host_barrier():
+        """A barrier on the host only (gloo): while rank 0 drives every GPU of the box through the multi-GPU call the other
+        ranks must leave their GPUs alone — a rank parked in an NCCL barrier keeps a kernel spinning on its device, and two
+        processes' work on one GPU is time-sliced, not concurrent."""
+        if world > 1:
+            torch.cuda.synchronize()
+            dist.barrier(group=host_group)
 
     def max_over_ranks(x):
         t = torch.tensor([x], dtype=torch.float64, device=dev)
@@ -508,9 +517,9 @@ def run_gpu(args):
                     "api": "ezpz_b200_solve_batch on ordinary numpy arrays (what a Rust Vec<f64> is): staged through the "
                            "library's pinned buffers, output arrays allocated per call"}
     del hg, res, owners
-    barrier()
+    host_barrier()
 
-    # ---- e2e, the headline: ONE call from ONE process drives all N GPUs (rank 0; the other ranks wait at the barrier)
+    # ---- e2e, the headline: ONE call from ONE process drives all N GPUs (rank 0; the other ranks wait at a host barrier)
     one_call = strong_one_call = sweep = None
     if rank == 0:
         multi = ez.MultiContext(devices=list(range(world)))
@@ -533,7 +542,7 @@ def run_gpu(args):
         if not args.no_extras:
             sizes = [1 << 10, 1 << 12, 1 << 14, 1 << 16, 1 << 18, 1 << 20] if world == 1 else [1 << 16, 1 << 20]
             sweep = mixed_sweep(multi, sizes)
-    barrier()
+    host_barrier()
     clocks = sampler.stop()
 
     if rank == 0:

@@ -63,6 +63,7 @@ EXPECT = {
     "chamfer_square": dict(src="tests.rs:731", satisfied=True, underconstrained=[],
                            points={"a": [0, 40], "b": [30, 40], "c": [40, 30], "d": [40, 0], "e": [0, 0]}),
     "arc_length": dict(src="tests.rs:743", satisfied=True),
+    # the assertions of these three live in tests/test_reference_arc_regressions.py
     "arc_line_coincident_bug": dict(src="tests.rs:1286"),
     "arc_line_coincident_bug/problem_without_arc_constraint": dict(src="tests.rs:1295"),
     "arc_center_point_coincident": dict(src="tests.rs:1399"),
