@@ -28,6 +28,31 @@ def test_library_exports_every_declared_symbol():
     assert C.sizeof(native.Constraint) == 64
 
 
+def test_rust_binding_declares_exactly_the_header():
+    """integration/gpu.rs (the extern "C" block a maintainer adds to the crate) and include/ezpz_b200.h name the same functions,
+    and the structs that cross the boundary have the same field lists."""
+    with open(os.path.join(ROOT, "include", "ezpz_b200.h")) as f:
+        header = f.read()
+    with open(os.path.join(ROOT, "integration", "gpu.rs")) as f:
+        rust = f.read()
+    declared = sorted(set(re.findall(r"\b(ezpz_b200_[a-z0-9_]+)\s*\(", header)))
+    bound = sorted(set(re.findall(r"pub fn (ezpz_b200_[a-z0-9_]+)\s*\(", rust)))
+    assert bound == declared
+    def c_fields(name):
+        body = re.search(r"typedef struct %s \{(.*?)\} %s_t;" % (name, name), header, re.S).group(1)
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        return [re.sub(r"\[.*\]", "", d.split()[-1].lstrip("*")) for stmt in body.split(";") if stmt.strip()
+                for d in [stmt.strip()] if d]
+    def rs_fields(name):
+        body = re.search(r"pub struct %s \{(.*?)\n\}" % name, rust, re.S).group(1)
+        return re.findall(r"pub ([a-z0-9_]+):", body)
+    assert c_fields("ezpz_batch_io") == rs_fields("EzpzBatchIo")
+    assert c_fields("ezpz_one_io") == rs_fields("EzpzOneIo")
+    assert c_fields("ezpz_config") == rs_fields("EzpzConfig")
+    assert c_fields("ezpz_outcome") == rs_fields("EzpzOutcome")
+    assert "EZPZ_B200_ABI_VERSION: u32 = %d" % native.lib().ezpz_b200_abi_version() in rust
+
+
 def test_config_default():
     cfg = native.Config()
     native.lib().ezpz_b200_config_default(C.byref(cfg))
