@@ -759,6 +759,15 @@ int32_t ezpz_b200_context_create(int32_t device, ezpz_context_t** out, ezpz_erro
     ctx->sm_count = v;
     cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     ctx->smem_optin = (size_t)v;
+    {  // freed structure tables stay in the device's pool for the next structure (large.cu: DevicePlan)
+        cudaMemPool_t pool = nullptr;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess && pool) {
+            uint64_t keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        } else {
+            cudaGetLastError();
+        }
+    }
     e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) {
         delete ctx;
@@ -1009,6 +1018,52 @@ int32_t ezpz_b200_solve_batch(ezpz_context_t* ctx, const ezpz_structure_t* s, co
         }
     }
     const size_t n = s->n, nc = s->n_cons, uw = (s->n_cons + 31) / 32;
+    // Small calls on ordinary (pageable) memory — a single sketch through ezpz_b200_solve_one above all: every pageable
+    // cudaMemcpyAsync is a staged, synchronising copy of ~10 us, and the call needs five of them.  Instead the buffers are
+    // copied by the CPU into the context's page-locked block, the kernel reads and writes that block across PCIe, and the CPU
+    // copies the results out: one launch and one synchronisation per call.
+    if (s->small.valid) {
+        const size_t nnz1 = s->csc_row_idx.size(), vw1 = (s->n + 31) / 32;
+        const size_t o_g = 0, o_p = o_g + align_up(batch * n * 8, 64), o_f = o_p + (io->params ? align_up(batch * nc * 8, 64) : 0);
+        const size_t o_it = o_f + align_up(batch * n * 8, 64), o_st = o_it + align_up(batch * 4, 64), o_un = o_st + align_up(batch, 64);
+        const size_t o_dg = o_un + (io->unsat_mask ? align_up(batch * uw * 4, 64) : 0);
+        const size_t o_jc = o_dg + (io->degen_count ? align_up(batch * nc * 4, 64) : 0);
+        const size_t o_uc = o_jc + (io->jacobian ? align_up(batch * nnz1 * 8, 64) : 0);
+        const size_t total = o_uc + (io->under_mask ? align_up(batch * vw1 * 4, 64) : 0);
+        const char* hm = std::getenv("EZPZ_B200_HOST_MODE");
+        if (total <= ((size_t)256 << 10) && !(hm && hm[0] == 'p')) {
+            int32_t rc = ensure_pin(ctx, total, detail);
+            if (rc != EZPZ_OK) return rc;
+            char* h = (char*)ctx->pin;
+            void* dv = nullptr;
+            EZ_CUDA(cudaHostGetDevicePointer(&dv, ctx->pin, 0), "cudaHostGetDevicePointer");
+            char* d = (char*)dv;
+            std::memcpy(h + o_g, io->guesses, batch * n * 8);
+            if (io->params) std::memcpy(h + o_p, io->params, batch * nc * 8);
+            ezpz_batch_io_t dio;
+            dio.guesses = (const double*)(d + o_g);
+            dio.params = io->params ? (const double*)(d + o_p) : nullptr;
+            dio.final_values = (double*)(d + o_f);
+            dio.iterations = (uint32_t*)(d + o_it);
+            dio.status = (uint8_t*)(d + o_st);
+            dio.unsat_mask = io->unsat_mask ? (uint32_t*)(d + o_un) : nullptr;
+            dio.degen_count = io->degen_count ? (uint32_t*)(d + o_dg) : nullptr;
+            dio.jacobian = io->jacobian ? (double*)(d + o_jc) : nullptr;
+            dio.under_mask = io->under_mask ? (uint32_t*)(d + o_uc) : nullptr;
+            rc = ezpz_b200_solve_batch_device(ctx, s, config, batch, &dio, ctx->stream, detail);
+            const cudaError_t e = cudaStreamSynchronize(ctx->stream);
+            if (rc != EZPZ_OK) return rc;
+            if (e != cudaSuccess) return cuda_fail(e, detail, "cudaStreamSynchronize");
+            std::memcpy(io->final_values, h + o_f, batch * n * 8);
+            std::memcpy(io->iterations, h + o_it, batch * 4);
+            std::memcpy(io->status, h + o_st, batch);
+            if (io->unsat_mask) std::memcpy(io->unsat_mask, h + o_un, batch * uw * 4);
+            if (io->degen_count) std::memcpy(io->degen_count, h + o_dg, batch * nc * 4);
+            if (io->jacobian) std::memcpy(io->jacobian, h + o_jc, batch * nnz1 * 8);
+            if (io->under_mask) std::memcpy(io->under_mask, h + o_uc, batch * vw1 * 4);
+            return EZPZ_OK;
+        }
+    }
     const size_t b_x = align_up(batch * n * sizeof(double), 256);
     const size_t b_p = io->params ? align_up(batch * nc * sizeof(double), 256) : 0;
     const size_t b_it = align_up(batch * sizeof(uint32_t), 256);

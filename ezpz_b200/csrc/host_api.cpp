@@ -39,10 +39,27 @@ struct StructureCache {
 };
 constexpr size_t kCacheEntries = 8;
 constexpr uint32_t kCacheMaxVars = 1u << 18;  // larger systems hold GBs of device tables: not cached
+// An analysed structure keeps device tables in proportion to its size (hundreds of bytes per variable on the large path):
+// the cache is bounded by the variables it holds, not only by its entry count.
+constexpr uint64_t kCacheVarBudget = 1u << 19;
 
-uint64_t fnv1a(const void* data, size_t bytes, uint64_t h) {
+// Multiply-xorshift over 64-bit words (the records are 64 bytes each, the id lists are padded by the tail loop): one
+// multiply per 8 bytes instead of FNV-1a's one per byte, which cost ~130 us on the 128 KB of massive_parallel_system.
+uint64_t mix_hash(const void* data, size_t bytes, uint64_t h) {
     const unsigned char* p = static_cast<const unsigned char*>(data);
-    for (size_t i = 0; i < bytes; ++i) h = (h ^ p[i]) * 0x100000001b3ull;
+    size_t i = 0;
+    for (; i + 8 <= bytes; i += 8) {
+        uint64_t w;
+        std::memcpy(&w, p + i, 8);
+        h = (h ^ w) * 0x9E3779B97F4A7C15ull;
+        h ^= h >> 32;
+    }
+    uint64_t tail = 0;
+    if (i < bytes) {
+        std::memcpy(&tail, p + i, bytes - i);
+        h = (h ^ tail) * 0x9E3779B97F4A7C15ull;
+        h ^= h >> 32;
+    }
     return h;
 }
 
@@ -58,9 +75,9 @@ int32_t cached_structure(ezpz_context_t* ctx, const std::vector<ezpz_constraint_
         return ezpz_b200_structure_create(cons.data(), (uint32_t)cons.size(), var_ids, n_vars, out, detail);
     if (!ctx->structure_cache) ctx->structure_cache = new StructureCache();
     StructureCache& C = *static_cast<StructureCache*>(ctx->structure_cache);
-    uint64_t h = fnv1a(cons.data(), cons.size() * sizeof(ezpz_constraint_t), 0xcbf29ce484222325ull);
-    h = fnv1a(&n_vars, sizeof n_vars, h);
-    if (var_ids) h = fnv1a(var_ids, n_vars * sizeof(uint32_t), h);
+    uint64_t h = mix_hash(cons.data(), cons.size() * sizeof(ezpz_constraint_t), 0xcbf29ce484222325ull);
+    h = mix_hash(&n_vars, sizeof n_vars, h);
+    if (var_ids) h = mix_hash(var_ids, n_vars * sizeof(uint32_t), h);
     for (CachedStructure& e : C.entries) {
         if (e.hash != h || e.n_vars != n_vars || e.cons.size() != cons.size() || e.has_var_ids != (var_ids != nullptr)) continue;
         if (std::memcmp(e.cons.data(), cons.data(), cons.size() * sizeof(ezpz_constraint_t)) != 0) continue;
@@ -74,7 +91,12 @@ int32_t cached_structure(ezpz_context_t* ctx, const std::vector<ezpz_constraint_
     ++C.misses;
     const int32_t rc = ezpz_b200_structure_create(cons.data(), (uint32_t)cons.size(), var_ids, n_vars, out, detail);
     if (rc != EZPZ_OK) return rc;
-    if (C.entries.size() >= kCacheEntries) {
+    auto held = [&] {
+        uint64_t v = 0;
+        for (const CachedStructure& e : C.entries) v += e.n_vars;
+        return v;
+    };
+    while (!C.entries.empty() && (C.entries.size() >= kCacheEntries || held() + n_vars > kCacheVarBudget)) {
         size_t oldest = 0;
         for (size_t k = 1; k < C.entries.size(); ++k)
             if (C.entries[k].last_use < C.entries[oldest].last_use) oldest = k;
@@ -178,9 +200,29 @@ int32_t solve_level(ezpz_context_t* ctx, const std::vector<ezpz_constraint_t>& c
     io.status = &status;
     io.unsat_mask = unsat.data();
     io.degen_count = degen.data();
-    io.jacobian = analysis ? jac.data() : nullptr;
-    io.path_used = &L.path;
-    rc = ezpz_b200_solve_one(ctx, S, config, &io, detail);
+    // structures of the batched kernel: the freedom analysis rides in the same call on the Jacobian the kernel leaves on the
+    // device (ezpz_batch_io_t::under_mask); large systems export the Jacobian and are analysed after the solve
+    int32_t path = -1;
+    ezpz_b200_structure_ordering(S, &path, nullptr, nullptr, nullptr, nullptr, nullptr);
+    const bool fused = analysis && path == 0;
+    std::vector<uint32_t> under_mask((n_vars + 31) / 32, 0);
+    if (fused) {
+        ezpz_batch_io_t b;
+        std::memset(&b, 0, sizeof b);
+        b.guesses = guesses;
+        b.final_values = L.finals.data();
+        b.iterations = &iterations;
+        b.status = &status;
+        b.unsat_mask = unsat.data();
+        b.degen_count = degen.data();
+        b.under_mask = under_mask.data();
+        L.path = 0;
+        rc = ezpz_b200_solve_batch(ctx, S, config, 1, &b, detail);
+    } else {
+        io.jacobian = analysis ? jac.data() : nullptr;
+        io.path_used = &L.path;
+        rc = ezpz_b200_solve_one(ctx, S, config, &io, detail);
+    }
     if (rc == EZPZ_OK) {
         L.iterations = iterations;
         L.converged = (status & EZPZ_ST_CONVERGED) != 0;
@@ -192,17 +234,18 @@ int32_t solve_level(ezpz_context_t* ctx, const std::vector<ezpz_constraint_t>& c
         if (status & EZPZ_ST_SOLVE_ERROR) rc = EZPZ_ERR_SOLVE;
     }
     if (rc == EZPZ_OK && analysis) {
-        std::vector<uint32_t> mask((n_vars + 31) / 32, 0);
-        rc = ezpz_b200_freedom_analysis(ctx, S, 1, jac.data(), mask.data(), detail);
+        if (!fused) rc = ezpz_b200_freedom_analysis(ctx, S, 1, jac.data(), under_mask.data(), detail);
         if (rc == EZPZ_OK)
             for (uint32_t j = 0; j < n_vars; ++j)
-                if (mask[j >> 5] & (1u << (j & 31u))) L.under.push_back(j);
+                if (under_mask[j >> 5] & (1u << (j & 31u))) L.under.push_back(j);
     }
     if (owned) ezpz_b200_structure_destroy(S);
     return rc;
 }
 
 }  // namespace
+
+extern "C" void ezpz_b200_context_clear_cache(ezpz_context_t* ctx) { ezs::release_structure_cache(ctx); }
 
 namespace ezs {
 void release_structure_cache(ezpz_context* ctx) {
@@ -243,6 +286,19 @@ extern "C" int32_t ezpz_b200_solve(ezpz_context_t* ctx, const ezpz_constraint_t*
     // resolves Undefined sides itself; with an explicit id list that is not the identity, resolve here so
     // that the by-id semantics is kept.
     std::vector<ezpz_constraint_t> all(cons, cons + n_cons);
+    // canonical records: whatever a caller left in the ids a kind does not use, or in p0 / p1 of a kind without a scalar,
+    // must not reach the kernels' tables nor split the topology cache into entries that differ only in garbage
+    for (auto& c : all) {
+        const ezk::KindInfo& ki = ezk::kKinds[c.kind];
+        for (uint32_t k = ki.n_ids; k < 8; ++k) c.ids[k] = 0;
+        const bool angle = c.kind == EZPZ_K_LINES_AT_ANGLE || c.kind == EZPZ_K_ARC_ANGLE || c.kind == EZPZ_K_POINTS_AT_ANGLE;
+        const bool scalar = c.kind == EZPZ_K_DISTANCE || c.kind == EZPZ_K_VERTICAL_DISTANCE || c.kind == EZPZ_K_HORIZONTAL_DISTANCE ||
+                            c.kind == EZPZ_K_FIXED || c.kind == EZPZ_K_CIRCLE_RADIUS || c.kind == EZPZ_K_ARC_RADIUS ||
+                            c.kind == EZPZ_K_POINT_LINE_DISTANCE || c.kind == EZPZ_K_VERTICAL_POINT_LINE_DISTANCE ||
+                            c.kind == EZPZ_K_HORIZONTAL_POINT_LINE_DISTANCE || c.kind == EZPZ_K_ARC_LENGTH;
+        if (!angle) c.p1 = 0.0;
+        if (!angle && !scalar) c.p0 = 0.0;
+    }
     bool identity = true;
     if (var_ids)
         for (uint32_t k = 0; k < n_vars; ++k) identity = identity && var_ids[k] == k;

@@ -1470,6 +1470,7 @@ struct LargeDevice {
     uint32_t *degen = nullptr, *unsat = nullptr;
     LargeCtrl* ctrl = nullptr;
     unsigned char* resblk = nullptr;  // [ctrl | unsat | degen], see get_large
+    void* arena = nullptr;            // the one allocation all of the above point into
     size_t resblk_bytes = 0;
     int grid = 0;
     bool cluster = false;
@@ -1484,16 +1485,46 @@ struct LargeDevice {
     } batch;
 };
 
-template <class T>
-int32_t upload(T** dst, const std::vector<T>& src, ezpz_error_detail_t* detail) {
-    if (src.empty()) {
-        EZ_CUDA(cudaMalloc(dst, sizeof(T)), "cudaMalloc");
+// The device tables of one structure live in ONE allocation: the uploads are packed into a host staging block as they are
+// produced and the work buffers are reserved behind them; finalize() allocates once, copies once, zeroes the work buffers once
+// and hands out the pointers.  (One cudaMalloc + synchronous cudaMemcpy per table — some thirty of each — made the first solve
+// of a 2,000-variable topology cost more than the CPU's whole solve.)
+struct DevicePlan {
+    struct Item {
+        void** dst;
+        size_t off;
+    };
+    std::vector<unsigned char> stage;
+    std::vector<Item> up, raw;
+    size_t reserve_bytes = 0;
+    template <class T>
+    int32_t upload(T** dst, const std::vector<T>& src) {
+        const size_t off = (stage.size() + 255) / 256 * 256, bytes = std::max<size_t>(sizeof(T), sizeof(T) * src.size());
+        stage.resize(off + bytes);
+        if (!src.empty()) std::memcpy(stage.data() + off, src.data(), sizeof(T) * src.size());
+        up.push_back({reinterpret_cast<void**>(dst), off});
         return EZPZ_OK;
     }
-    EZ_CUDA(cudaMalloc(dst, sizeof(T) * src.size()), "cudaMalloc");
-    EZ_CUDA(cudaMemcpy(*dst, src.data(), sizeof(T) * src.size(), cudaMemcpyHostToDevice), "cudaMemcpy");
-    return EZPZ_OK;
-}
+    template <class T>
+    void reserve(T** dst, size_t bytes) {  // zero-initialised
+        raw.push_back({reinterpret_cast<void**>(dst), reserve_bytes});
+        reserve_bytes += (std::max<size_t>(bytes, 8) + 255) / 256 * 256;
+    }
+    int32_t finalize(void** arena, cudaStream_t st, ezpz_error_detail_t* detail) {
+        const size_t up_bytes = (stage.size() + 255) / 256 * 256;
+        // stream-ordered allocation out of the device's default pool (its release threshold is lifted in context_create): a
+        // topology analysed again after its structure was destroyed gets the same memory back without a trip to the driver's
+        // physical allocator, which costs milliseconds for a block of a few MB
+        EZ_CUDA(cudaMallocAsync(arena, std::max<size_t>(256, up_bytes + reserve_bytes), st), "cudaMallocAsync(structure tables)");
+        unsigned char* base = static_cast<unsigned char*>(*arena);
+        if (!stage.empty()) EZ_CUDA(cudaMemcpyAsync(base, stage.data(), stage.size(), cudaMemcpyHostToDevice, st), "cudaMemcpy(structure tables)");
+        if (reserve_bytes) EZ_CUDA(cudaMemsetAsync(base + up_bytes, 0, reserve_bytes, st), "cudaMemset(work buffers)");
+        for (const Item& it : up) *it.dst = base + it.off;
+        for (const Item& it : raw) *it.dst = base + up_bytes + it.off;
+        EZ_CUDA(cudaStreamSynchronize(st), "cudaStreamSynchronize");  // (the staging block dies with the plan)
+        return EZPZ_OK;
+    }
+};
 #define EZ_TRY(x)                    \
     do {                             \
         int32_t rc__ = (x);          \
@@ -1509,6 +1540,7 @@ int32_t get_large(ezpz_context* ctx, const ezpz_structure* s, DeviceCopy* dc, La
     LargeDevice* L = new (std::nothrow) LargeDevice();
     if (!L) return EZPZ_ERR_INVALID_ARGUMENT;
     dc->large = L;  // owned by the device copy from here on (released with it)
+    DevicePlan plan;
     {
         // record tiles (see the comment above assemble_slot)
         static const uint8_t kHasP0[EZPZ_K_COUNT] = {0, 0, 1, 0, 1, 1, 0, 0, 1, 1, 0, 0, 1, 0, 1, 0, 0, 1, 1, 1, 0, 0, 1, 1, 1};
@@ -1577,47 +1609,38 @@ int32_t get_large(ezpz_context* ctx, const ezpz_structure* s, DeviceCopy* dc, La
             tiles[t].meta = kind | (n_valid << 8);
             if (base / 4 > 0xfffffff0ull) return EZPZ_ERR_TOO_LARGE;
         }
-        EZ_TRY(upload(&L->recs, recs, detail));
-        EZ_TRY(upload(&L->tiles, tiles, detail));
-        EZ_TRY(upload(&L->slot_orig, orig, detail));
-        EZ_TRY(upload(&L->side_flags, flags, detail));
+        EZ_TRY(plan.upload(&L->recs, recs));
+        EZ_TRY(plan.upload(&L->tiles, tiles));
+        EZ_TRY(plan.upload(&L->slot_orig, orig));
+        EZ_TRY(plan.upload(&L->side_flags, flags));
         L->n_slots = n_slots;
         L->n_tiles = n_tiles;
         for (uint32_t t = 0; t < n_tiles; ++t)
             L->tile_bytes_max = std::max<uint32_t>(L->tile_bytes_max, (uint32_t)L->layout[tiles[t].meta & 0xffu].n_words * 128u);
     }
-    EZ_TRY(upload(&L->csr_row_ptr, s->csr_row_ptr, detail));
-    EZ_TRY(upload(&L->csr_col_idx, s->csr_col_idx, detail));
-    EZ_TRY(upload(&L->csc_col_ptr, s->csc_col_ptr, detail));
-    EZ_TRY(upload(&L->csc_row_idx, s->csc_row_idx, detail));
+    EZ_TRY(plan.upload(&L->csr_row_ptr, s->csr_row_ptr));
+    EZ_TRY(plan.upload(&L->csr_col_idx, s->csr_col_idx));
+    EZ_TRY(plan.upload(&L->csc_col_ptr, s->csc_col_ptr));
+    EZ_TRY(plan.upload(&L->csc_row_idx, s->csc_row_idx));
     if (P.direct) {
         const std::vector<uint32_t>* src[11] = {&P.perm, &P.sn_rows, &P.upd_rel, &P.upd_rec, &P.stage_ptr, &P.stage_rec, &P.aent_slot,
                                                 &P.aprod_ptr, &P.aprod_a, &P.aprod_b, &P.diag_slot};
-        for (int k = 0; k < 11; ++k) EZ_TRY(upload(&L->direct_tables[k], *src[k], detail));
-        if (!P.jt_of_csc.empty()) EZ_TRY(upload(&L->jmap, P.jt_of_csc, detail));
+        for (int k = 0; k < 11; ++k) EZ_TRY(plan.upload(&L->direct_tables[k], *src[k]));
+        if (!P.jt_of_csc.empty()) EZ_TRY(plan.upload(&L->jmap, P.jt_of_csc));
     }
     const size_t nnz = s->csc_row_idx.size();
-    EZ_CUDA(cudaMalloc(&L->vg, sizeof(double) * std::max<size_t>(1, P.VG)), "cudaMalloc(vg)");
-    EZ_CUDA(cudaMemset(L->vg, 0, sizeof(double) * std::max<size_t>(1, P.VG)), "cudaMemset(vg)");
-    EZ_CUDA(cudaMalloc(&L->jr, sizeof(double) * std::max<size_t>(1, nnz)), "cudaMalloc(jr)");
-    EZ_CUDA(cudaMalloc(&L->cgv, sizeof(double) * (4 * (size_t)s->n + s->m + 1)), "cudaMalloc(cgv)");
-    if (const char* dbg = std::getenv("EZPZ_B200_DEBUG"); dbg && dbg[0] == '1' && dbg[1] == '2' && P.direct) {
-        EZ_CUDA(cudaMalloc(&L->lvl_ns, sizeof(unsigned long long) * 2 * std::max<size_t>(1, P.n_levels)), "cudaMalloc(lvl_ns)");
-        EZ_CUDA(cudaMemset(L->lvl_ns, 0, sizeof(unsigned long long) * 2 * std::max<size_t>(1, P.n_levels)), "cudaMemset(lvl_ns)");
-    }
-    EZ_CUDA(cudaMalloc(&L->sumsq, sizeof(double) * ((size_t)s->m / 64 + 2)), "cudaMalloc(sumsq)");
-    EZ_CUDA(cudaMalloc(&L->side, std::max<size_t>(1, L->n_slots)), "cudaMalloc(side)");
-    {
-        // control block, unsatisfied mask and degenerate counters in ONE allocation: a solve reads them back with one copy
-        const size_t b_ctrl = align_up(sizeof(LargeCtrl), 256), b_unsat = align_up(sizeof(uint32_t) * ((s->n_cons + 31) / 32 + 1), 256),
-                     b_degen = sizeof(uint32_t) * std::max<size_t>(1, s->n_cons);
-        L->resblk_bytes = b_ctrl + b_unsat + b_degen;
-        EZ_CUDA(cudaMalloc(&L->resblk, L->resblk_bytes), "cudaMalloc(result block)");
-        EZ_CUDA(cudaMemset(L->resblk, 0, L->resblk_bytes), "cudaMemset(result block)");  // not every field is written by every path
-        L->ctrl = reinterpret_cast<LargeCtrl*>(L->resblk);
-        L->unsat = reinterpret_cast<uint32_t*>(L->resblk + b_ctrl);
-        L->degen = reinterpret_cast<uint32_t*>(L->resblk + b_ctrl + b_unsat);
-    }
+    plan.reserve(&L->vg, sizeof(double) * std::max<size_t>(1, P.VG));
+    plan.reserve(&L->jr, sizeof(double) * std::max<size_t>(1, nnz));
+    plan.reserve(&L->cgv, sizeof(double) * (4 * (size_t)s->n + s->m + 1));
+    if (const char* dbg = std::getenv("EZPZ_B200_DEBUG"); dbg && dbg[0] == '1' && dbg[1] == '2' && P.direct)
+        plan.reserve(&L->lvl_ns, sizeof(unsigned long long) * 2 * std::max<size_t>(1, P.n_levels));
+    plan.reserve(&L->sumsq, sizeof(double) * ((size_t)s->m / 64 + 2));
+    plan.reserve(&L->side, std::max<size_t>(1, L->n_slots));
+    // control block, unsatisfied mask and degenerate counters side by side: a solve reads them back with one copy
+    const size_t b_ctrl = align_up(sizeof(LargeCtrl), 256), b_unsat = align_up(sizeof(uint32_t) * ((s->n_cons + 31) / 32 + 1), 256),
+                 b_degen = sizeof(uint32_t) * std::max<size_t>(1, s->n_cons);
+    L->resblk_bytes = b_ctrl + b_unsat + b_degen;
+    plan.reserve(&L->resblk, L->resblk_bytes);
     // grid: one CTA for small systems (barriers are __syncthreads), else every SM, co-resident
     const size_t work = (size_t)s->n + s->m + nnz;
     int per_sm = 0;
@@ -1628,7 +1651,11 @@ int32_t get_large(ezpz_context* ctx, const ezpz_structure* s, DeviceCopy* dc, La
     // tiny systems: one CTA; up to 65,536 values: one cluster of 8 CTAs; beyond: every SM, co-resident
     L->grid = work <= kSingleCtaWork ? 1 : (work <= 65536 ? (int)kClusterCtas : ctx->sm_count * std::min(per_sm, 2));
     L->cluster = work > kSingleCtaWork && work <= 65536;
-    EZ_CUDA(cudaMalloc(&L->partials, sizeof(double) * 3 * (size_t)L->grid), "cudaMalloc(partials)");
+    plan.reserve(&L->partials, sizeof(double) * 3 * (size_t)L->grid);
+    EZ_TRY(plan.finalize(&L->arena, ctx->stream, detail));
+    L->ctrl = reinterpret_cast<LargeCtrl*>(L->resblk);
+    L->unsat = reinterpret_cast<uint32_t*>(L->resblk + b_ctrl);
+    L->degen = reinterpret_cast<uint32_t*>(L->resblk + b_ctrl + b_unsat);
     uint8_t rows[EZPZ_K_COUNT], emit_len[EZPZ_K_COUNT][2], nids[EZPZ_K_COUNT];
     for (int k = 0; k < EZPZ_K_COUNT; ++k) {
         nids[k] = ezk::kKinds[k].n_ids;
@@ -1747,12 +1774,7 @@ namespace ezs {
 void release_large(DeviceCopy* d) {
     LargeDevice* L = (LargeDevice*)d->large;
     if (!L) return;
-    void* ptrs[] = {L->jmap, L->recs, L->tiles, L->slot_orig, L->side_flags, L->csr_row_ptr, L->csr_col_idx, L->csc_col_ptr, L->csc_row_idx,
-                    L->vg, L->jr, L->cgv, L->partials, L->sumsq, L->lvl_ns, L->side, L->resblk};
-    for (uint32_t* p : L->direct_tables)
-        if (p) cudaFree(p);
-    for (void* p : ptrs)
-        if (p) cudaFree(p);
+    if (L->arena) cudaFreeAsync(L->arena, nullptr);  // every table and work buffer of the structure (DevicePlan); back to the pool
     void* bptrs[] = {L->batch.vg, L->batch.jr, L->batch.cgv, L->batch.sumsq, L->batch.partials, L->batch.side,
                      L->batch.degen, L->batch.unsat, L->batch.ctrl};
     for (void* p : bptrs)

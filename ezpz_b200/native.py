@@ -91,6 +91,7 @@ _SYMBOLS = [
                                           C.POINTER(ErrorDetail)]),
     ("ezpz_b200_eval", C.c_int32, [_P, _P, _P, _P, _P, _P, _P, C.POINTER(ErrorDetail)]),
     ("ezpz_b200_freedom_analysis", C.c_int32, [_P, _P, C.c_uint64, _P, _P, C.POINTER(ErrorDetail)]),
+    ("ezpz_b200_context_clear_cache", None, [_P]),
     ("ezpz_b200_freedom_analysis_device", C.c_int32, [_P, _P, C.c_uint64, _P, _P, _P, C.POINTER(ErrorDetail)]),
     ("ezpz_b200_solve", C.c_int32, [_P, _P, _P, _P, C.c_uint32, _P, _P, C.c_uint32, C.POINTER(Config), C.c_int32,
                                     C.POINTER(OutcomeRec), C.POINTER(ErrorDetail)]),

@@ -221,6 +221,9 @@ void ezpz_b200_context_destroy(ezpz_context_t* ctx);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 uint64_t ezpz_b200_context_launches(const ezpz_context_t* ctx);
 int32_t ezpz_b200_context_synchronize(ezpz_context_t* ctx);
+/* Drops the analysed structures ezpz_b200_solve keeps for this context (its topology cache: the last 8 distinct
+ * constraint lists, at most 2^19 variables in total) together with their device tables. */
+void ezpz_b200_context_clear_cache(ezpz_context_t* ctx);
 
 /* ---------------------------------------------------------------------------------------------
  * Batched solve: `batch` independent problems sharing one structure, differing in their initial

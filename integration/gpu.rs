@@ -130,6 +130,7 @@ extern "C" {
     pub fn ezpz_b200_context_destroy(ctx: *mut EzpzContext);
     pub fn ezpz_b200_context_launches(ctx: *const EzpzContext) -> u64;
     pub fn ezpz_b200_context_synchronize(ctx: *mut EzpzContext) -> i32;
+    pub fn ezpz_b200_context_clear_cache(ctx: *mut EzpzContext);
 
     // ---- solves: replace model.solve_levenberg_marquardt + the unsatisfied check (lib.rs:292-327, newton.rs:29-145)
     pub fn ezpz_b200_solve_one(ctx: *mut EzpzContext, s: *const EzpzStructure, cfg: *const EzpzConfig, io: *const EzpzOneIo,
