@@ -101,14 +101,19 @@ struct LargeArgs {
     uint32_t sum_chunk;     // sum of squares folded in chunks of this many rows (ezs::sum_chunk_for); 0 = one sequential fold
     // CTAs cooperating on ONE system and this CTA's rank among them (set by the kernel: the whole grid, or 1 / 0 in
     // batch mode, where every CTA solves its own problem with CTA-level barriers)
-    uint32_t vgrid, vblock;
+    uint32_t vgrid;  // set by the host: the launch's grid size, or 1 in batch mode (this CTA's rank: vblock_of)
     // batch mode (ezpz_b200_solve_batch on structures beyond the thread-per-problem kernel): problem b = blockIdx.x uses
     // vg + b * vg_stride, jr + b * jr_stride, ... ; 0 = one system per launch
     uint32_t batch;
     size_t vg_stride, jr_stride, cgv_stride, sumsq_stride, side_stride, degen_stride, unsat_stride;
     uint32_t X0, R0, RN0, J0, L0, RV0, Y0, D0;
     uint32_t direct;
+    uint32_t* sn_flag;  // [n_sn] per supernode in stage order: the factorisation whose diagonal block is final (sn_factor_slice)
+    uint32_t n_sn;
 };
+
+// Rank of this CTA among the CTAs that cooperate on one system: the block index, or 0 in batch mode (one CTA per problem).
+__device__ __forceinline__ uint32_t vblock_of(const LargeArgs& a) { return a.batch ? 0u : blockIdx.x; }
 
 struct GX {
     const double* p;
@@ -840,6 +845,276 @@ __device__ __noinline__ void sn_factor(const LargeArgs& a, uint32_t pos, uint32_
     }
 }
 
+// ---- Tall panels of the upper tree, split by ROWS over several CTAs --------------------------------------------------
+// The upper stages of a 2D-lattice-like sketch hold a handful of panels of 16 columns x several hundred rows, each receiving
+// 50-200 updates: one CTA per panel left the other ~140 SMs idle (grid_truss(100): 97 % of the solve).  Every entry of a panel
+// is an independent fma chain (updates in order, k ascending), and a row below the diagonal block needs nothing but its own
+// entries and the finished diagonal block.  So a panel is cut into SLICES: slice 0 owns the w x w diagonal block (its updates,
+// the pivots, 1/pivot, the forward substitution of y) and publishes it with a release flag; slices 1.. own a range of the
+// rows below, apply the updates to them at once, wait for the flag, and divide their rows through.  Same chains per entry as
+// sn_factor, hence the same bits.  All CTAs of the launch are co-resident (cooperative / cluster launch), so waiting is safe.
+constexpr uint32_t kSlicePanelCap = 10240;  // doubles of a slice's rows held in shared memory
+constexpr uint32_t kSliceChunk = 32;        // update records per round
+constexpr uint32_t kSliceMinRows = 48;      // panels with fewer rows below the diagonal block stay on one CTA
+
+__device__ __noinline__ void sn_factor_slice(const LargeArgs& a, uint32_t pos, uint32_t slice, uint32_t n_slices, uint32_t epoch,
+                                             double* stage, uint32_t stage_doubles) {
+    const uint32_t lane = threadIdx.x, TEAM = blockDim.x;
+    double* const lv = a.vg + a.L0;
+    double* const y = a.vg + a.Y0;
+    const uint32_t* const upd_rec = a.upd_rec;
+    const uint32_t* const upd_rel = a.upd_rel;
+    const uint4 hdr = __ldg(reinterpret_cast<const uint4*>(a.stage_rec) + 2 * (size_t)pos);
+    const uint4 hdr2 = __ldg(reinterpret_cast<const uint4*>(a.stage_rec) + 2 * (size_t)pos + 1);
+    const uint32_t j0 = hdr.x, w = hdr.y, h = hdr.z, hb = h - w;
+    double* const G = lv + hdr2.x;
+    const bool diag = slice == 0;
+    // rows of this slice inside the panel: the diagonal block, or an even share of the rows below it
+    const uint32_t r0 = diag ? 0u : w + (uint32_t)((uint64_t)hb * (slice - 1) / (n_slices - 1));
+    const uint32_t r1 = diag ? w : w + (uint32_t)((uint64_t)hb * slice / (n_slices - 1));
+    const uint32_t rows = r1 - r0;
+    // shared memory: P[rows][w] | ys[16] | L11[w*w] + rinv[w] (slices 1..) | records | per update: offsets | blocks
+    double* P = stage;
+    double* ys = P + ((rows * w + 1u) & ~1u);
+    double* l11 = ys + kYCap;
+    double* rinv_s = l11 + 256;
+    uint32_t* srec = reinterpret_cast<uint32_t*>(rinv_s + 16);   // kSliceChunk * 8 words
+    uint32_t* meta = srec + kSliceChunk * 8;                      // per update: t_lo, t_hi, block offset (doubles), rel offset (words)
+    uint32_t* n_fit = meta + kSliceChunk * 4;                     // [0] updates of this round that fit
+    uint32_t* srel = n_fit + 4;                                   // relative positions of the staged rows (keeps kb 16-byte aligned)
+    const uint32_t rel_cap = 4096;
+    double* kb = reinterpret_cast<double*>(srel + rel_cap);
+    const uint32_t kb_cap = stage_doubles - (uint32_t)(kb - stage);
+    for (uint32_t t = lane; t < rows * w; t += TEAM) P[t] = G[(size_t)r0 * w + t];
+    if (diag)
+        for (uint32_t c = lane; c < w; c += TEAM) ys[c] = y[j0 + c];
+    __syncthreads();
+    // ---- 1. external updates
+    const uint32_t ub = hdr2.y, ue = hdr2.y + hdr2.z;
+    for (uint32_t u0 = ub; u0 < ue;) {
+        const uint32_t win_n = min(kSliceChunk, ue - u0);
+        for (uint32_t q = lane; q < win_n * 8; q += TEAM) srec[q] = __ldg(upd_rec + 8 * (size_t)u0 + q);
+        __syncthreads();
+        // the rows of every update's block that land in this slice: rel is ascending, so they are one range [t_lo, t_hi)
+        if (lane < win_n) {
+            const uint32_t* r = srec + 8 * lane;
+            const uint32_t T = r[1], nc = r[2] >> 8;
+            uint32_t lo = nc, hi = nc;
+            if (!diag) {
+                const uint32_t* rel = upd_rel + r[3];
+                uint32_t x0 = nc, x1 = T;  // first t >= nc with rel[t] >= r0
+                while (x0 < x1) {
+                    const uint32_t mid = (x0 + x1) >> 1;
+                    if (__ldg(rel + mid) < r0) x0 = mid + 1;
+                    else x1 = mid;
+                }
+                lo = x0;
+                x1 = T;  // first t >= lo with rel[t] >= r1
+                while (x0 < x1) {
+                    const uint32_t mid = (x0 + x1) >> 1;
+                    if (__ldg(rel + mid) < r1) x0 = mid + 1;
+                    else x1 = mid;
+                }
+                hi = x0;
+            }
+            meta[4 * lane] = lo;
+            meta[4 * lane + 1] = hi;
+        }
+        __syncthreads();
+        // inverse maps of the round, one per update: (rows + w) 16-bit positions — where each row of this slice sits in the
+        // update's staged rows, and where each column of the supernode sits among its first nc rows; 0xffff = not touched
+        const uint32_t inv_len = rows + w;  // 16-bit words per update
+        if (lane == 0) {  // how many updates of the window fit: inverse map + [first nc rows | own rows] x wK + y of K's columns
+            uint32_t tot_b = 0, tot_r = 0, cnt = 0;
+            for (; cnt < win_n; ++cnt) {
+                const uint32_t* r = srec + 8 * cnt;
+                const uint32_t wK = r[2] & 0xffu, nc = r[2] >> 8, own = meta[4 * cnt + 1] - meta[4 * cnt];
+                const uint32_t need_b = (nc + own) * wK + wK, need_r = nc + own;
+                const uint32_t inv_doubles = ((cnt + 1) * inv_len + 3u) / 4u;
+                if (tot_b + ((need_b + 1u) & ~1u) + ((inv_doubles + 1u) & ~1u) > kb_cap || tot_r + need_r > rel_cap || own >= 0xffffu) break;
+                meta[4 * cnt + 2] = tot_b;
+                meta[4 * cnt + 3] = tot_r;
+                tot_b += (need_b + 1u) & ~1u;
+                tot_r += need_r;
+            }
+            n_fit[0] = cnt;
+        }
+        __syncthreads();
+        const uint32_t cnt = n_fit[0];
+        if (cnt == 0) {
+            // one update that does not fit the stage: pair by pair straight from global memory (rare: a slice holds few rows)
+            const uint32_t* r = srec;
+            const uint32_t wK = r[2] & 0xffu, nc = r[2] >> 8, lo = meta[0], hi = meta[1];
+            const double* B = lv + r[0];
+            const uint32_t* rel = upd_rel + r[3];
+            if (diag) {
+                for (uint32_t p = lane; p < nc * nc; p += TEAM) {
+                    const uint32_t tj = p / nc, ti = p - tj * nc;
+                    if (ti < tj) continue;
+                    double* dst = P + __ldg(rel + ti) * w + __ldg(rel + tj);
+                    double acc = *dst;
+                    for (uint32_t k = 0; k < wK; ++k) acc = __fma_rn(-B[ti * wK + k], B[tj * wK + k], acc);
+                    *dst = acc;
+                }
+                for (uint32_t tj = lane; tj < nc; tj += TEAM) {
+                    const uint32_t c = __ldg(rel + tj);
+                    double acc = ys[c];
+                    for (uint32_t k = 0; k < wK; ++k) acc = __fma_rn(-B[tj * wK + k], y[r[4] + k], acc);
+                    ys[c] = acc;
+                }
+            } else {
+                for (uint32_t p = lane; p < (hi - lo) * nc; p += TEAM) {
+                    const uint32_t ti = lo + p / nc, tj = p % nc;
+                    double* dst = P + (__ldg(rel + ti) - r0) * w + __ldg(rel + tj);
+                    double acc = *dst;
+                    for (uint32_t k = 0; k < wK; ++k) acc = __fma_rn(-B[(size_t)ti * wK + k], B[tj * wK + k], acc);
+                    *dst = acc;
+                }
+            }
+            __syncthreads();
+            u0 += 1;
+            continue;
+        }
+        // the inverse maps sit at the END of the block area (the blocks grow from its start)
+        uint16_t* inv = reinterpret_cast<uint16_t*>(kb + kb_cap) - (size_t)cnt * inv_len;
+        for (uint32_t q = lane; q < cnt * inv_len; q += TEAM) inv[q] = 0xffffu;
+        // all staged rows of the round in flight together
+        for (uint32_t i = 0; i < cnt; ++i) {
+            const uint32_t* r = srec + 8 * i;
+            const uint32_t wK = r[2] & 0xffu, nc = r[2] >> 8, lo = meta[4 * i], hi = meta[4 * i + 1], own = hi - lo;
+            double* dst = kb + meta[4 * i + 2];
+            uint32_t* rdst = srel + meta[4 * i + 3];
+            const double* B = lv + r[0];
+            for (uint32_t q = lane; q < nc * wK; q += TEAM) cp_async8(dst + q, B + q);
+            for (uint32_t q = lane; q < own * wK; q += TEAM) cp_async8(dst + nc * wK + q, B + (size_t)lo * wK + q);
+            for (uint32_t q = lane; q < wK; q += TEAM) cp_async8(dst + (nc + own) * wK + q, y + r[4] + q);
+            for (uint32_t q = lane; q < nc; q += TEAM) cp_async4(rdst + q, upd_rel + r[3] + q);
+            for (uint32_t q = lane; q < own; q += TEAM) cp_async4(rdst + nc + q, upd_rel + r[3] + lo + q);
+        }
+        cp_async_wait_all();
+        __syncthreads();
+        for (uint32_t i = 0; i < cnt; ++i) {
+            const uint32_t nc = srec[8 * i + 2] >> 8, own = meta[4 * i + 1] - meta[4 * i];
+            const uint32_t* relc = srel + meta[4 * i + 3];
+            uint16_t* iv = inv + (size_t)i * inv_len;  // [0, rows): this slice's rows; [rows, rows + w): the supernode's columns
+            for (uint32_t t = lane; t < nc; t += TEAM) iv[rows + relc[t]] = (uint16_t)t;
+            if (!diag)
+                for (uint32_t t = lane; t < own; t += TEAM) iv[relc[nc + t] - r0] = (uint16_t)t;
+        }
+        __syncthreads();
+        // every entry of the slice is owned by one thread, which applies the round's updates to it in order: no barrier
+        // between updates
+        for (uint32_t e = lane; e < rows * w; e += TEAM) {
+            const uint32_t lr = e / w, c = e - lr * w;
+            if (diag && c > lr) continue;
+            double acc = P[e];
+            for (uint32_t i = 0; i < cnt; ++i) {
+                const uint16_t* iv = inv + (size_t)i * inv_len;
+                const uint32_t tj = iv[rows + c], ti = diag ? iv[rows + lr] : iv[lr];
+                if (ti == 0xffffu || tj == 0xffffu) continue;
+                const uint32_t wK = srec[8 * i + 2] & 0xffu, nc = srec[8 * i + 2] >> 8;
+                const double* Bc = kb + meta[4 * i + 2];
+                const double* bi = diag ? Bc + ti * wK : Bc + (nc + ti) * wK;
+                const double* bj = Bc + tj * wK;
+                if (wK == 16) {
+                    const double2* bi2 = reinterpret_cast<const double2*>(bi);
+                    const double2* bj2 = reinterpret_cast<const double2*>(bj);
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        double2 u[4], v[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            u[q] = bi2[4 * half + q];
+                            v[q] = bj2[4 * half + q];
+                        }
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            acc = __fma_rn(-u[q].x, v[q].x, acc);
+                            acc = __fma_rn(-u[q].y, v[q].y, acc);
+                        }
+                    }
+                } else {
+                    for (uint32_t k = 0; k < wK; ++k) acc = __fma_rn(-bi[k], bj[k], acc);
+                }
+            }
+            P[e] = acc;
+        }
+        if (diag)
+            for (uint32_t c = lane; c < w; c += TEAM) {  // forward substitution against y of the descendants' columns
+                double acc = ys[c];
+                for (uint32_t i = 0; i < cnt; ++i) {
+                    const uint32_t tj = inv[(size_t)i * inv_len + rows + c];
+                    if (tj == 0xffffu) continue;
+                    const uint32_t wK = srec[8 * i + 2] & 0xffu, nc = srec[8 * i + 2] >> 8;
+                    const double* Bc = kb + meta[4 * i + 2];
+                    const double* yK = Bc + nc * wK;  // (a diagonal slice stages no rows of its own)
+                    for (uint32_t k = 0; k < wK; ++k) acc = __fma_rn(-Bc[tj * wK + k], yK[k], acc);
+                    ys[c] = acc;
+                }
+            }
+        __syncthreads();
+        u0 += cnt;
+    }
+    uint32_t* const flag = a.sn_flag + pos;
+    if (diag) {
+        // ---- 2. the diagonal block's own columns, the pivots and y (sn_factor, part 2, on w rows)
+        double* const rinv_out = a.vg + a.RV0 + j0;
+        for (uint32_t c = 0; c < w; ++c) {
+            for (uint32_t r = c + lane; r <= w; r += TEAM) {
+                const bool yrow = r == w;
+                const double* pa = yrow ? P + c * w : P + r * w;
+                const double* pb = yrow ? ys : P + c * w;
+                double acc = yrow ? ys[c] : P[r * w + c], piv = P[c * w + c];
+                for (uint32_t k = 0; k < c; ++k) {
+                    const double lck = P[c * w + k];
+                    piv = __fma_rn(-lck, lck, piv);
+                    acc = __fma_rn(-pa[k], pb[k], acc);
+                }
+                const double rinv = __ddiv_rn(1.0, __dsqrt_rn(piv));
+                if (r == c) {
+                    if (!(piv > 0.0) || !ezm::ez_isfinite(piv)) a.ctrl->fail = 1;
+                    rinv_out[c] = rinv;
+                } else if (yrow) {
+                    ys[c] = __dmul_rn(acc, rinv);
+                } else {
+                    P[r * w + c] = __dmul_rn(acc, rinv);
+                }
+            }
+            __syncthreads();
+        }
+        for (uint32_t t = lane; t < w * w; t += TEAM) G[t] = P[t];
+        for (uint32_t c = lane; c < w; c += TEAM) y[j0 + c] = ys[c];
+        __threadfence();
+        __syncthreads();
+        if (lane == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flag), "r"(epoch) : "memory");
+    } else {
+        // ---- 2. wait for the diagonal block, then every row divides itself through (independent chains, c ascending)
+        if (lane == 0) {
+            uint32_t seen;
+            do {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(flag) : "memory");
+                if (seen != epoch) __nanosleep(64);
+            } while (seen != epoch);
+        }
+        __syncthreads();
+        for (uint32_t t = lane; t < w * w; t += TEAM) l11[t] = __ldcg(G + t);
+        for (uint32_t c = lane; c < w; c += TEAM) rinv_s[c] = __ldcg(a.vg + a.RV0 + j0 + c);
+        __syncthreads();
+        for (uint32_t r = lane; r < rows; r += TEAM) {
+            double* pr = P + r * w;
+            for (uint32_t c = 0; c < w; ++c) {
+                double acc = pr[c];
+                const double* pb = l11 + c * w;
+                for (uint32_t k = 0; k < c; ++k) acc = __fma_rn(-pr[k], pb[k], acc);
+                pr[c] = __dmul_rn(acc, rinv_s[c]);
+            }
+        }
+        __syncthreads();
+        for (uint32_t t = lane; t < rows * w; t += TEAM) G[(size_t)r0 * w + t] = P[t];
+    }
+    __syncthreads();
+}
+
 // Backward substitution of one supernode (stages descending): d[j] = (y[j] - sum_{i > j} L[i][j] d[i]) / L[j][j] with the
 // rows i DESCENDING — first the rows below the supernode's diagonal block (their d is final), then the block's own rows.
 // The columns of the supernode advance together: lane c of the team's first warp owns column c; the rows below the block
@@ -963,7 +1238,8 @@ __device__ __noinline__ void sn_backward(const LargeArgs& a, uint32_t pos, uint3
 // CTA.  Larger panels: always one per CTA (cta_stage = the CTA's whole dynamic shared memory; warp_stage = this warp's
 // slice of it).  (Four 8-lane teams per warp were measured slower on
 // the bottom stages: diverged teams of one warp execute one after the other.)
-__device__ void direct_factor_stage(const LargeArgs& a, uint32_t st, uint32_t tid, uint32_t nth, double* warp_stage, double* cta_stage) {
+__device__ void direct_factor_stage(const LargeArgs& a, uint32_t st, uint32_t tid, uint32_t nth, double* warp_stage, double* cta_stage,
+                                    uint32_t epoch) {
     const uint32_t b0 = __ldg(a.stage_ptr + 3 * st), b1 = __ldg(a.stage_ptr + 3 * st + 1), b2 = __ldg(a.stage_ptr + 3 * st + 2),
                    b3 = __ldg(a.stage_ptr + 3 * st + 3);
     for (uint32_t k = b0 + tid; k < b1; k += nth) sn_factor<1>(a, k, 0, nullptr);
@@ -971,21 +1247,41 @@ __device__ void direct_factor_stage(const LargeArgs& a, uint32_t st, uint32_t ti
         // Between one and eight panels per CTA (the middle of the tree: every panel receives 10-20 updates): QUADS of four
         // warps — a quad stages ~15 updates per round trip where a warp's stage holds two or three, and there are still
         // enough quads for every panel of the stage.
-        for (uint32_t k = b1 + (threadIdx.x >> 7) * a.vgrid + a.vblock; k < b2; k += 4 * a.vgrid)
+        for (uint32_t k = b1 + (threadIdx.x >> 7) * a.vgrid + vblock_of(a); k < b2; k += 4 * a.vgrid)
             sn_factor<128>(a, k, threadIdx.x & 127u, cta_stage + (threadIdx.x >> 7) * 4 * kWarpStageDoubles);
         __syncthreads();
-        for (uint32_t k = b2 + a.vblock; k < b3; k += a.vgrid) sn_factor<512>(a, k, threadIdx.x, cta_stage);
+        for (uint32_t k = b2 + vblock_of(a); k < b3; k += a.vgrid) sn_factor<512>(a, k, threadIdx.x, cta_stage);
     } else if (b2 - b1 > a.vgrid) {
         if ((threadIdx.x & 31u) == 0) reinterpret_cast<uint32_t*>(warp_stage + kCarryOffset)[0] = UINT32_MAX;  // no carry
         __syncwarp();
         // Panels are dealt warp-major ACROSS the CTAs (panel k of the stage's cost-sorted list to CTA k mod G): the most
         // expensive panels land on different SMs, and a stage with fewer panels than warps still uses every SM.
-        for (uint32_t k = b1 + (threadIdx.x >> 5) * a.vgrid + a.vblock, nw = nth >> 5; k < b2; k += nw)
+        for (uint32_t k = b1 + (threadIdx.x >> 5) * a.vgrid + vblock_of(a), nw = nth >> 5; k < b2; k += nw)
             sn_factor<32>(a, k, threadIdx.x & 31u, warp_stage, k + nw < b2 ? k + nw : UINT32_MAX, k + 2 * nw < b2 ? k + 2 * nw : UINT32_MAX);
         __syncthreads();  // the CTA panels below reuse the warps' shared memory
-        for (uint32_t k = b2 + a.vblock; k < b3; k += a.vgrid) sn_factor<512>(a, k, threadIdx.x, cta_stage);
+        for (uint32_t k = b2 + vblock_of(a); k < b3; k += a.vgrid) sn_factor<512>(a, k, threadIdx.x, cta_stage);
     } else {
-        for (uint32_t k = b1 + a.vblock; k < b3; k += a.vgrid) sn_factor<512>(a, k, threadIdx.x, cta_stage);
+        // At most one panel per CTA.  With CTAs to spare, tall panels are cut into row slices (sn_factor_slice): CTA v takes
+        // slice v / nP of panel v % nP.
+        const uint32_t nP = b3 - b1, vb = vblock_of(a);
+        const uint32_t s_max = nP ? a.vgrid / nP : 0u;
+        if (a.sn_flag && s_max >= 2 && !a.batch) {
+            const uint32_t k = b1 + vb % nP, slice = vb / nP;
+            if (slice < s_max) {
+                const uint4 hdr = __ldg(reinterpret_cast<const uint4*>(a.stage_rec) + 2 * (size_t)k);
+                const uint32_t w = hdr.y, hb = hdr.z - hdr.y;
+                // slices of at least 8 rows; slice 0 is the diagonal block
+                uint32_t S = 1u + min(s_max - 1u, (hb + 7u) / 8u);
+                if (hb < kSliceMinRows || ((hb + S - 2u) / (S - 1u)) * w > kSlicePanelCap) S = 1u;
+                if (S == 1u) {
+                    if (slice == 0) sn_factor<512>(a, k, threadIdx.x, cta_stage);
+                } else if (slice < S) {
+                    sn_factor_slice(a, k, slice, S, epoch, cta_stage, (512 / 32) * kWarpStageDoubles);
+                }
+            }
+        } else {
+            for (uint32_t k = b1 + vb; k < b3; k += a.vgrid) sn_factor<512>(a, k, threadIdx.x, cta_stage);
+        }
     }
 }
 __device__ void direct_backward_stage(const LargeArgs& a, uint32_t st, uint32_t tid, uint32_t nth, double* warp_stage, double* cta_stage) {
@@ -998,11 +1294,11 @@ __device__ void direct_backward_stage(const LargeArgs& a, uint32_t st, uint32_t 
         carry[1] = UINT32_MAX;
     }
     __syncwarp();
-    for (uint32_t k = b1 + (threadIdx.x >> 5) * a.vgrid + a.vblock, nw = nth >> 5; k < b2; k += nw)
+    for (uint32_t k = b1 + (threadIdx.x >> 5) * a.vgrid + vblock_of(a), nw = nth >> 5; k < b2; k += nw)
         sn_backward<32>(a, k, threadIdx.x & 31u, warp_stage, k + nw < b2 ? k + nw : UINT32_MAX, k + 2 * nw < b2 ? k + 2 * nw : UINT32_MAX);
     if (b3 > b2) {
         __syncthreads();
-        for (uint32_t k = b2 + a.vblock; k < b3; k += a.vgrid) sn_backward<512>(a, k, threadIdx.x, cta_stage);
+        for (uint32_t k = b2 + vblock_of(a); k < b3; k += a.vgrid) sn_backward<512>(a, k, threadIdx.x, cta_stage);
     }
 }
 
@@ -1046,25 +1342,9 @@ __device__ __forceinline__ unsigned long long now_ns() {
 
 constexpr size_t kLmDynamicSmem = (kBlock / 32) * kWarpStageDoubles * sizeof(double);  // 164 KB
 
-__global__ void __launch_bounds__(kBlock, 1) lm_large_kernel(const LargeArgs a_in) {
-    LargeArgs a = a_in;
-    if (a.batch) {  // one problem per CTA: this CTA's slices of the per-problem arrays
-        const size_t b = blockIdx.x;
-        a.vg += b * a.vg_stride;
-        a.jr += b * a.jr_stride;
-        a.cgv += b * a.cgv_stride;
-        a.sumsq += b * a.sumsq_stride;
-        a.side += b * a.side_stride;
-        a.degen += b * a.degen_stride;
-        a.unsat += b * a.unsat_stride;
-        a.partials += b * 3;
-        a.ctrl += b;
-        a.vgrid = 1;
-        a.vblock = 0;
-    } else {
-        a.vgrid = gridDim.x;
-        a.vblock = blockIdx.x;
-    }
+// The body of the persistent LM kernel; `a` is the kernel's argument block itself (single system: a __grid_constant__
+// parameter, read through the constant bank, never copied) or this CTA's adjusted copy of it (batch mode).
+__device__ __forceinline__ void lm_large_body(const LargeArgs& a) {
     __shared__ double sm[kSmDoubles];
     extern __shared__ double warp_stage_all[];  // (kBlock / 32) * kWarpStageDoubles, see kLmDynamicSmem
     double* warp_stage = warp_stage_all + (threadIdx.x >> 5) * kWarpStageDoubles;
@@ -1079,7 +1359,7 @@ __global__ void __launch_bounds__(kBlock, 1) lm_large_kernel(const LargeArgs a_i
             asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
         } else grid.sync();
     };
-    const uint32_t tid = a.vblock * blockDim.x + threadIdx.x, nth = a.vgrid * blockDim.x;
+    const uint32_t tid = vblock_of(a) * blockDim.x + threadIdx.x, nth = a.vgrid * blockDim.x;
     const uint32_t G = a.vgrid;
     LargeCtrl* ctrl = a.ctrl;
     double* vg = a.vg;
@@ -1095,8 +1375,11 @@ __global__ void __launch_bounds__(kBlock, 1) lm_large_kernel(const LargeArgs a_i
         t_mark = t;
     };
 
+    uint32_t fact_epoch = 0;  // factorisations so far in this launch: what a diagonal slice publishes (sn_factor_slice)
     // sides from the initial guesses (lib.rs:183-186), counters
     {
+        if (a.sn_flag)
+            for (uint32_t k = tid; k < a.n_sn; k += nth) a.sn_flag[k] = 0;
         resolve_sides(a, tid, nth);
         for (uint32_t c = tid; c < a.n_cons; c += nth) a.degen[c] = 0;
         for (uint32_t w = tid; w < (a.n_cons + 31) / 32; w += nth) a.unsat[w] = 0;
@@ -1132,7 +1415,7 @@ __global__ void __launch_bounds__(kBlock, 1) lm_large_kernel(const LargeArgs a_i
     bool converged = false;
     uint32_t lin_iters = 0;
     for (uint32_t it = 0; it < a.max_iterations; ++it) {
-        max_abs_partial(vg + a.R0, a.m, tid, nth, &pm[a.vblock], sm);
+        max_abs_partial(vg + a.R0, a.m, tid, nth, &pm[vblock_of(a)], sm);
         sync();
         const double largest = fold_max(pm, G, sm);
         lap(1);
@@ -1143,6 +1426,7 @@ __global__ void __launch_bounds__(kBlock, 1) lm_large_kernel(const LargeArgs a_i
         }
         bool fail = false;
         if (!use_cg) {
+            ++fact_epoch;  // (the same count in every CTA: the loop is uniform across the grid)
             direct_zero(a, tid, nth);
             sync();
             direct_assemble(a, lambda, tid, nth);
@@ -1150,7 +1434,7 @@ __global__ void __launch_bounds__(kBlock, 1) lm_large_kernel(const LargeArgs a_i
             lap(2);
             for (uint32_t st = 0; st < a.n_levels; ++st) {
                 const unsigned long long t0 = a.lvl_ns ? now_ns() : 0ull;
-                direct_factor_stage(a, st, tid, nth, warp_stage, warp_stage_all);
+                direct_factor_stage(a, st, tid, nth, warp_stage, warp_stage_all, fact_epoch);
                 sync();
                 if (a.lvl_ns && tid == 0) a.lvl_ns[2 * st] += now_ns() - t0;
             }
@@ -1190,8 +1474,8 @@ __global__ void __launch_bounds__(kBlock, 1) lm_large_kernel(const LargeArgs a_i
                 lrz += b * z;
                 lbb += b * b;
             }
-            block_sum(lrz, &ps1[a.vblock], sm);
-            block_sum(lbb, &ps2[a.vblock], sm);
+            block_sum(lrz, &ps1[vblock_of(a)], sm);
+            block_sum(lbb, &ps2[vblock_of(a)], sm);
             sync();
             double rz = fold_sum(ps1, G, sm);
             const double bb = fold_sum(ps2, G, sm);
@@ -1211,7 +1495,7 @@ __global__ void __launch_bounds__(kBlock, 1) lm_large_kernel(const LargeArgs a_i
                         ap[j] = s;
                         lpap += p[j] * s;
                     }
-                    block_sum(lpap, &pm[a.vblock], sm);
+                    block_sum(lpap, &pm[vblock_of(a)], sm);
                     sync();
                     const double pap = fold_sum(pm, G, sm);
                     ++lin_iters;
@@ -1228,8 +1512,8 @@ __global__ void __launch_bounds__(kBlock, 1) lm_large_kernel(const LargeArgs a_i
                         lrz2 += rj * (dinv[j] * rj);
                         lrr += rj * rj;
                     }
-                    block_sum(lrz2, &ps1[a.vblock], sm);
-                    block_sum(lrr, &ps2[a.vblock], sm);
+                    block_sum(lrz2, &ps1[vblock_of(a)], sm);
+                    block_sum(lrr, &ps2[vblock_of(a)], sm);
                     sync();
                     const double rz2 = fold_sum(ps1, G, sm);
                     const double rr = fold_sum(ps2, G, sm);
@@ -1250,7 +1534,7 @@ __global__ void __launch_bounds__(kBlock, 1) lm_large_kernel(const LargeArgs a_i
             sync();
             continue;
         }
-        max_abs_partial(vg + a.D0, a.n, tid, nth, &pm[a.vblock], sm);
+        max_abs_partial(vg + a.D0, a.n, tid, nth, &pm[vblock_of(a)], sm);
         sync();
         const double step = fold_max(pm, G, sm);
         for (uint32_t j = tid; j < a.n; j += nth) vg[a.X0 + j] += vg[a.D0 + j];
@@ -1314,6 +1598,26 @@ __global__ void __launch_bounds__(kBlock, 1) lm_large_kernel(const LargeArgs a_i
         ctrl->S = S;
         ctrl->lin_iters = lin_iters;
     }
+}
+
+// One system per launch (one CTA, one cluster, or the whole GPU): the argument block stays where the launch put it.
+__global__ void __launch_bounds__(kBlock, 1) lm_large_kernel(const __grid_constant__ LargeArgs a) { lm_large_body(a); }
+
+// One problem per CTA (batches of mid-size systems): this CTA's slices of the per-problem arrays.
+__global__ void __launch_bounds__(kBlock, 1) lm_large_batch_kernel(const LargeArgs a_in) {
+    LargeArgs a = a_in;
+    const size_t b = blockIdx.x;
+    a.vg += b * a.vg_stride;
+    a.jr += b * a.jr_stride;
+    a.cgv += b * a.cgv_stride;
+    a.sumsq += b * a.sumsq_stride;
+    a.side += b * a.side_stride;
+    a.degen += b * a.degen_stride;
+    a.unsat += b * a.unsat_stride;
+    a.partials += b * 3;
+    a.ctrl += b;
+    lm_large_body(a);
+
 }
 
 // ---- stand-alone kernels for throughput measurement (same device code as the phases above) ------------
@@ -1471,6 +1775,7 @@ struct LargeDevice {
     LargeCtrl* ctrl = nullptr;
     unsigned char* resblk = nullptr;  // [ctrl | unsat | degen], see get_large
     void* arena = nullptr;            // the one allocation all of the above point into
+    uint32_t* sn_flag = nullptr;      // [n_sn], see LargeArgs
     size_t resblk_bytes = 0;
     int grid = 0;
     bool cluster = false;
@@ -1635,6 +1940,7 @@ int32_t get_large(ezpz_context* ctx, const ezpz_structure* s, DeviceCopy* dc, La
     if (const char* dbg = std::getenv("EZPZ_B200_DEBUG"); dbg && dbg[0] == '1' && dbg[1] == '2' && P.direct)
         plan.reserve(&L->lvl_ns, sizeof(unsigned long long) * 2 * std::max<size_t>(1, P.n_levels));
     plan.reserve(&L->sumsq, sizeof(double) * ((size_t)s->m / 64 + 2));
+    if (P.direct) plan.reserve(&L->sn_flag, sizeof(uint32_t) * std::max<size_t>(1, P.stage_rec.size() / 8));
     plan.reserve(&L->side, std::max<size_t>(1, L->n_slots));
     // control block, unsatisfied mask and degenerate counters side by side: a solve reads them back with one copy
     const size_t b_ctrl = align_up(sizeof(LargeCtrl), 256), b_unsat = align_up(sizeof(uint32_t) * ((s->n_cons + 31) / 32 + 1), 256),
@@ -1646,6 +1952,8 @@ int32_t get_large(ezpz_context* ctx, const ezpz_structure* s, DeviceCopy* dc, La
     int per_sm = 0;
     EZ_CUDA(cudaFuncSetAttribute(lm_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLmDynamicSmem),
             "cudaFuncSetAttribute(lm_large_kernel)");
+    EZ_CUDA(cudaFuncSetAttribute(lm_large_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLmDynamicSmem),
+            "cudaFuncSetAttribute(lm_large_batch_kernel)");
     EZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lm_large_kernel, kBlock, kLmDynamicSmem), "occupancy");
     if (per_sm < 1) per_sm = 1;
     // tiny systems: one CTA; up to 65,536 values: one cluster of 8 CTAs; beyond: every SM, co-resident
@@ -1725,6 +2033,8 @@ void fill_args(LargeArgs& a, const ezpz_structure* s, const DeviceCopy* dc, cons
     a.Y0 = P.Y0;
     a.D0 = P.D0;
     a.direct = P.direct ? 1u : 0u;
+    a.sn_flag = L->sn_flag;
+    a.n_sn = (uint32_t)(P.stage_rec.size() / 8);
     // the summation order belongs to the structure, not to the launch shape: a system solved alone (cluster / grid) and
     // the same system solved as one CTA's problem in a batch fold S the same way
     a.sum_chunk = ezs::sum_chunk_for(s->n, s->m, s->csc_row_idx.size());
@@ -1846,8 +2156,10 @@ int32_t solve_large(ezpz_context* ctx, const ezpz_structure* s, const ezpz_confi
     void* params[] = {(void*)&a};
     a.cluster = L->cluster ? 1u : 0u;
     if (L->grid == 1) {
+        a.vgrid = 1;
         lm_large_kernel<<<1, kBlock, kLmDynamicSmem, st>>>(a);
     } else if (L->cluster) {
+        a.vgrid = kClusterCtas;
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(kClusterCtas);
         cfg.blockDim = dim3(kBlock);
@@ -1865,10 +2177,12 @@ int32_t solve_large(ezpz_context* ctx, const ezpz_structure* s, const ezpz_confi
             (void)cudaGetLastError();
             L->cluster = false;
             a.cluster = 0;
+            a.vgrid = (uint32_t)L->grid;
             EZ_CUDA(cudaLaunchCooperativeKernel((void*)lm_large_kernel, dim3(L->grid), dim3(kBlock), params, kLmDynamicSmem, st),
                     "cudaLaunchCooperativeKernel(lm_large_kernel)");
         }
     } else {
+        a.vgrid = (uint32_t)L->grid;
         EZ_CUDA(cudaLaunchCooperativeKernel((void*)lm_large_kernel, dim3(L->grid), dim3(kBlock), params, kLmDynamicSmem, st),
                 "cudaLaunchCooperativeKernel(lm_large_kernel)");
     }
@@ -2007,7 +2321,8 @@ int32_t solve_large_batch(ezpz_context* ctx, const ezpz_structure* s, const ezpz
     for (uint64_t b0 = 0; b0 < batch; b0 += B.cap) {
         const unsigned cnt = (unsigned)std::min<uint64_t>(B.cap, batch - b0);
         large_batch_scatter_kernel<<<cnt, 256, 0, st>>>(a, io->guesses + b0 * s->n);
-        lm_large_kernel<<<cnt, kBlock, kLmDynamicSmem, st>>>(a);
+        a.vgrid = 1;
+        lm_large_batch_kernel<<<cnt, kBlock, kLmDynamicSmem, st>>>(a);
         BatchOut o;
         o.finals = io->final_values + b0 * s->n;
         o.iterations = io->iterations + b0;
