@@ -859,7 +859,7 @@ constexpr uint32_t kSliceMinRows = 48;      // panels with fewer rows below the 
 
 __device__ __noinline__ void sn_factor_slice(const LargeArgs& a, uint32_t pos, uint32_t slice, uint32_t n_slices, uint32_t epoch,
                                              double* stage, uint32_t stage_doubles) {
-    const uint32_t lane = threadIdx.x, TEAM = blockDim.x;
+    const uint32_t lane = threadIdx.x, TEAM = blockDim.x, warp = lane >> 5, wl = lane & 31u, n_warps = TEAM >> 5;
     double* const lv = a.vg + a.L0;
     double* const y = a.vg + a.Y0;
     const uint32_t* const upd_rec = a.upd_rec;
@@ -895,30 +895,35 @@ __device__ __noinline__ void sn_factor_slice(const LargeArgs& a, uint32_t pos, u
         const uint32_t win_n = min(kSliceChunk, ue - u0);
         for (uint32_t q = lane; q < win_n * 8; q += TEAM) srec[q] = __ldg(upd_rec + 8 * (size_t)u0 + q);
         __syncthreads();
-        // the rows of every update's block that land in this slice: rel is ascending, so they are one range [t_lo, t_hi)
-        if (lane < win_n) {
-            const uint32_t* r = srec + 8 * lane;
+        // the rows of every update's block that land in this slice: rel is ascending, so they are one range [t_lo, t_hi).
+        // One WARP per update, 32-ary search (two or three round trips to memory instead of twenty dependent ones).
+        for (uint32_t i = warp; i < win_n; i += n_warps) {
+            const uint32_t* r = srec + 8 * i;
             const uint32_t T = r[1], nc = r[2] >> 8;
             uint32_t lo = nc, hi = nc;
             if (!diag) {
                 const uint32_t* rel = upd_rel + r[3];
-                uint32_t x0 = nc, x1 = T;  // first t >= nc with rel[t] >= r0
-                while (x0 < x1) {
-                    const uint32_t mid = (x0 + x1) >> 1;
-                    if (__ldg(rel + mid) < r0) x0 = mid + 1;
-                    else x1 = mid;
-                }
-                lo = x0;
-                x1 = T;  // first t >= lo with rel[t] >= r1
-                while (x0 < x1) {
-                    const uint32_t mid = (x0 + x1) >> 1;
-                    if (__ldg(rel + mid) < r1) x0 = mid + 1;
-                    else x1 = mid;
-                }
-                hi = x0;
+                auto lower_bound = [&](uint32_t from, uint32_t v) {  // first t in [from, T) with rel[t] >= v
+                    uint32_t x0 = from, x1 = T;
+                    while (x1 > x0) {
+                        const uint32_t span = x1 - x0;
+                        auto probe = [&](uint32_t l) { return x0 + (uint32_t)(((uint64_t)span * (l + 1)) / 33u); };
+                        const uint32_t pl = min(probe(wl), x1 - 1);
+                        const uint32_t k = __popc(__ballot_sync(0xffffffffu, __ldg(rel + pl) < v));
+                        const uint32_t n0 = k ? min(probe(k - 1), x1 - 1) + 1 : x0;
+                        const uint32_t n1 = k < 32 ? min(probe(k), x1 - 1) : x1;
+                        x0 = n0;
+                        x1 = n1;
+                    }
+                    return x0;
+                };
+                lo = lower_bound(nc, r0);
+                hi = lower_bound(lo, r1);
             }
-            meta[4 * lane] = lo;
-            meta[4 * lane + 1] = hi;
+            if (wl == 0) {
+                meta[4 * i] = lo;
+                meta[4 * i + 1] = hi;
+            }
         }
         __syncthreads();
         // inverse maps of the round, one per update: (rows + w) 16-bit positions — where each row of this slice sits in the
@@ -978,28 +983,28 @@ __device__ __noinline__ void sn_factor_slice(const LargeArgs& a, uint32_t pos, u
         // the inverse maps sit at the END of the block area (the blocks grow from its start)
         uint16_t* inv = reinterpret_cast<uint16_t*>(kb + kb_cap) - (size_t)cnt * inv_len;
         for (uint32_t q = lane; q < cnt * inv_len; q += TEAM) inv[q] = 0xffffu;
-        // all staged rows of the round in flight together
-        for (uint32_t i = 0; i < cnt; ++i) {
+        // all staged rows of the round in flight together (a warp per update)
+        for (uint32_t i = warp; i < cnt; i += n_warps) {
             const uint32_t* r = srec + 8 * i;
             const uint32_t wK = r[2] & 0xffu, nc = r[2] >> 8, lo = meta[4 * i], hi = meta[4 * i + 1], own = hi - lo;
             double* dst = kb + meta[4 * i + 2];
             uint32_t* rdst = srel + meta[4 * i + 3];
             const double* B = lv + r[0];
-            for (uint32_t q = lane; q < nc * wK; q += TEAM) cp_async8(dst + q, B + q);
-            for (uint32_t q = lane; q < own * wK; q += TEAM) cp_async8(dst + nc * wK + q, B + (size_t)lo * wK + q);
-            for (uint32_t q = lane; q < wK; q += TEAM) cp_async8(dst + (nc + own) * wK + q, y + r[4] + q);
-            for (uint32_t q = lane; q < nc; q += TEAM) cp_async4(rdst + q, upd_rel + r[3] + q);
-            for (uint32_t q = lane; q < own; q += TEAM) cp_async4(rdst + nc + q, upd_rel + r[3] + lo + q);
+            for (uint32_t q = wl; q < nc * wK; q += 32) cp_async8(dst + q, B + q);
+            for (uint32_t q = wl; q < own * wK; q += 32) cp_async8(dst + nc * wK + q, B + (size_t)lo * wK + q);
+            for (uint32_t q = wl; q < wK; q += 32) cp_async8(dst + (nc + own) * wK + q, y + r[4] + q);
+            for (uint32_t q = wl; q < nc; q += 32) cp_async4(rdst + q, upd_rel + r[3] + q);
+            for (uint32_t q = wl; q < own; q += 32) cp_async4(rdst + nc + q, upd_rel + r[3] + lo + q);
         }
         cp_async_wait_all();
         __syncthreads();
-        for (uint32_t i = 0; i < cnt; ++i) {
+        for (uint32_t i = warp; i < cnt; i += n_warps) {
             const uint32_t nc = srec[8 * i + 2] >> 8, own = meta[4 * i + 1] - meta[4 * i];
             const uint32_t* relc = srel + meta[4 * i + 3];
             uint16_t* iv = inv + (size_t)i * inv_len;  // [0, rows): this slice's rows; [rows, rows + w): the supernode's columns
-            for (uint32_t t = lane; t < nc; t += TEAM) iv[rows + relc[t]] = (uint16_t)t;
+            for (uint32_t t = wl; t < nc; t += 32) iv[rows + relc[t]] = (uint16_t)t;
             if (!diag)
-                for (uint32_t t = lane; t < own; t += TEAM) iv[relc[nc + t] - r0] = (uint16_t)t;
+                for (uint32_t t = wl; t < own; t += 32) iv[relc[nc + t] - r0] = (uint16_t)t;
         }
         __syncthreads();
         // every entry of the slice is owned by one thread, which applies the round's updates to it in order: no barrier
@@ -1272,7 +1277,10 @@ __device__ void direct_factor_stage(const LargeArgs& a, uint32_t st, uint32_t ti
                 const uint32_t w = hdr.y, hb = hdr.z - hdr.y;
                 // slices of at least 8 rows; slice 0 is the diagonal block
                 uint32_t S = 1u + min(s_max - 1u, (hb + 7u) / 8u);
-                if (hb < kSliceMinRows || ((hb + S - 2u) / (S - 1u)) * w > kSlicePanelCap) S = 1u;
+                const uint4 hdr2 = __ldg(reinterpret_cast<const uint4*>(a.stage_rec) + 2 * (size_t)k + 1);
+                // short panels stay on one CTA unless they receive many updates (the sliced code stages 32 updates per round)
+                const bool worth = hb >= kSliceMinRows || (hb >= 2u && hdr2.z >= 32u);
+                if (!worth || ((hb + S - 2u) / (S - 1u)) * w > kSlicePanelCap) S = 1u;
                 if (S == 1u) {
                     if (slice == 0) sn_factor<512>(a, k, threadIdx.x, cta_stage);
                 } else if (slice < S) {
