@@ -55,6 +55,7 @@ struct SmallArgs {
     uint32_t table_words;  // length of the blob in 32-bit words
     uint32_t cons_word;    // word offset of the DevCons array inside the blob
     uint32_t T, R;         // problems per CTA (a multiple of 32) and roles (warps per 32 problems)
+    uint32_t stride;       // doubles between consecutive slots of V: T + 1 (see small_stride)
     uint32_t weights_one;  // 1: every weight is exactly 1.0 (r == unweighted residuals)
 };
 
@@ -448,7 +449,7 @@ __global__ void __launch_bounds__(MAXT) lm_small_kernel(const SmallArgs a) {
     extern __shared__ double smem[];
     const uint32_t* tb = a.tables;
     if (STAGED) {
-        uint32_t* s_tb = reinterpret_cast<uint32_t*>(smem + (size_t)a.W * a.T);
+        uint32_t* s_tb = reinterpret_cast<uint32_t*>(smem + (((size_t)a.W * a.stride + 1u) & ~(size_t)1));  // 16-byte aligned: the tape is read in 128-bit words
         for (uint32_t i = threadIdx.x; i < a.table_words; i += blockDim.x) s_tb[i] = a.tables[i];
         __syncthreads();
         tb = s_tb;
@@ -457,7 +458,7 @@ __global__ void __launch_bounds__(MAXT) lm_small_kernel(const SmallArgs a) {
     const uint32_t group = warp / a.R, role = warp - group * a.R;
     const uint32_t col = group * 32u + lane;
     const uint64_t b = (uint64_t)blockIdx.x * a.T + col;
-    const VView V{reinterpret_cast<char*>(smem + col), a.T * 8u};
+    const VView V{reinterpret_cast<char*>(smem + col), a.stride * 8u};
     lm_roles_body(a, tb, V, b, b < a.batch, role, 1u + group);
 }
 
@@ -626,6 +627,13 @@ int32_t get_role_tables(ezpz_context* ctx, const ezpz_structure* cs, DeviceCopy*
 
 constexpr uint64_t kPipelineMinBatch = 32768;  // below: the kernel reads and writes page-locked caller buffers across PCIe itself
 
+// Slot stride of the shared-memory state V[slot][problem], in doubles: T + 1.  With a stride of T (a multiple of 32) the
+// 16 lanes that move the 16 variables of ONE problem between global memory and V (group_rows: consecutive lanes take
+// consecutive doubles of a row) all hit the same bank — a 16-way conflict on 13 % of the kernel's wavefronts (ncu, r02f);
+// an odd stride spreads them over 16 different 8-byte banks, and the arithmetic phases (a warp on one slot of 32 consecutive
+// problems) are conflict-free either way.
+inline uint32_t small_stride(uint32_t T) { return T + 1u; }
+
 struct SmallShape {
     uint32_t T = 0, R = 0;
     size_t smem = 0;
@@ -678,10 +686,11 @@ int32_t small_shape_host(const ezpz_structure* cs, uint64_t batch, uint32_t sm_c
             }
         }
         const size_t tb = probe->words.size() * sizeof(uint32_t);
-        bool stg = tb <= 64 * 1024 && per_group + tb <= smem_optin;
+        bool stg = tb <= 64 * 1024 && per_group + (size_t)cs->small.W * sizeof(double) + 8 + tb <= smem_optin;
         if (const char* e = std::getenv("EZPZ_B200_STAGE"); e && e[0] == '0') stg = false;
-        if (per_group > smem_optin) continue;
-        const size_t avail = smem_optin - (stg ? tb : 0);
+        if (per_group + (size_t)cs->small.W * sizeof(double) + 8 > smem_optin) continue;
+        const size_t pad = (size_t)cs->small.W * sizeof(double) + 8;  // the extra column of small_stride (+ alignment of the tables)
+        const size_t avail = smem_optin - (stg ? tb : 0) - std::min<size_t>(pad, smem_optin - (stg ? tb : 0));
         uint64_t g = std::min<uint64_t>({avail / per_group, (uint64_t)15, (uint64_t)(max_threads / (32u * cand))});
         if (const char* e = std::getenv("EZPZ_B200_GROUPS")) g = std::min<uint64_t>(g, std::max<uint64_t>(1, std::strtoull(e, nullptr, 10)));
         if (g < 1) continue;
@@ -709,7 +718,7 @@ int32_t small_shape_host(const ezpz_structure* cs, uint64_t batch, uint32_t sm_c
     out->T = (uint32_t)(32 * g);
     out->R = R;
     out->stage = stage;
-    out->smem = per_group * g + (stage ? tables : 0);
+    out->smem = per_group * g + (size_t)cs->small.W * sizeof(double) + 8 + (stage ? tables : 0);
     return EZPZ_OK;
 }
 
@@ -900,7 +909,7 @@ static int32_t launch_small(ezpz_context_t* ctx, const ezpz_structure_t* s, cons
     rc = small_shape(ctx, s, batch, &shape);
     if (rc != EZPZ_OK) return rc;
     RoleTables* tables = nullptr;
-    rc = get_role_tables(ctx, s, dc, shape.R, shape.T, &tables, detail);
+    rc = get_role_tables(ctx, s, dc, shape.R, small_stride(shape.T), &tables, detail);
     if (rc != EZPZ_OK) return rc;
     SmallArgs a;
     a.tables = tables->dev;
@@ -934,6 +943,7 @@ static int32_t launch_small(ezpz_context_t* ctx, const ezpz_structure_t* s, cons
     a.F0 = P.F0;
     a.unsat_words = (s->n_cons + 31) / 32;
     a.T = shape.T;
+    a.stride = small_stride(shape.T);
     a.R = shape.R;
     a.weights_one = s->all_weights_one ? 1u : 0u;
     const uint64_t grid = (batch + shape.T - 1) / shape.T;
