@@ -236,9 +236,10 @@ def st_pairs(st):
 
 
 def mixed_sweep(multi, sizes, reps=3):
-    """BASELINE.json configs[4]: per total batch size the eight structure-homogeneous sub-batches of the mix go through
-    ezpz_b200_solve_batch_multi on page-locked host buffers (verdict outputs on: unsatisfied masks and the underconstrained
-    masks of the fused freedom analysis) and EVERY problem is compared with the oracle."""
+    """BASELINE.json configs[4]: per total batch size the eight structure-homogeneous sub-batches of the mix go through ONE
+    ezpz_b200_solve_jobs_multi call on page-locked host buffers (four workers per GPU, so the sub-batches' kernels overlap;
+    verdict outputs on: unsatisfied masks and the underconstrained masks of the fused freedom analysis) and EVERY problem is
+    compared with the oracle.  `ms_per_pass_sequential_calls`: the same sub-batches as eight ezpz_b200_solve_batch_multi calls."""
     import numpy as np
 
     import ezpz_b200 as ez
@@ -256,10 +257,18 @@ def mixed_sweep(multi, sizes, reps=3):
             hg[:] = g
             subs.append((name, recs, n, g, st, hg, res, owners))
 
-        def one_pass():
+        def sequential_pass():
             for name, recs, n, g, st, hg, res, owners in subs:
-                multi.solve_batch(st, hg, out=res)
+                multi["one"].solve_batch(st, hg, out=res)
 
+        def one_pass():
+            multi["jobs"].solve_jobs([(st, hg, res) for name, recs, n, g, st, hg, res, owners in subs])
+
+        sequential_pass()
+        ts_seq = timed_calls(sequential_pass, reps, 1)
+        for name, recs, n, g, st, hg, res, owners in subs:  # the checked results below must come from the jobs call
+            res.final_values[:] = 0
+            res.under_mask[:] = 0xFFFFFFFF
         one_pass()
         ts = timed_calls(one_pass, reps, 1)
         n_total = sum(len(s[3]) for s in subs)
@@ -278,7 +287,8 @@ def mixed_sweep(multi, sizes, reps=3):
         cpu_s = time.perf_counter() - t0
         t = statistics.median(ts)
         out.append({"batch_total": n_total, "ms_per_pass_e2e": t * 1e3, "solves_per_s_e2e": n_total / t,
-                    "calls_per_pass": len(subs), "verdict_mismatches_vs_oracle": bad, "problems_checked": n_total,
+                    "ms_per_pass_sequential_calls": statistics.median(ts_seq) * 1e3,
+                    "jobs_per_call": len(subs), "verdict_mismatches_vs_oracle": bad, "problems_checked": n_total,
                     "oracle_with_analysis_s": cpu_s, "verdicts": verdicts})
         del subs
     return out
@@ -541,7 +551,9 @@ def run_gpu(args):
         del hg, res, owners
         if not args.no_extras:
             sizes = [1 << 10, 1 << 12, 1 << 14, 1 << 16, 1 << 18, 1 << 20] if world == 1 else [1 << 16, 1 << 20]
-            sweep = mixed_sweep(multi, sizes)
+            jobs_multi = ez.MultiContext(devices=[d for d in range(world) for _ in range(4)])
+            sweep = mixed_sweep({"one": multi, "jobs": jobs_multi}, sizes)
+            del jobs_multi
     host_barrier()
     clocks = sampler.stop()
 
@@ -601,8 +613,8 @@ def run_gpu(args):
         if sweep is not None:
             line["mixed_sweep"] = {"config": "BASELINE.json configs[4]: 50% two_rectangles, 15% square, 10% circle_tangent, 5% each "
                                              "arc_length, parc_coincident, inconsistent, underconstrained, perpendicular",
-                                   "api": "ezpz_b200_solve_batch_multi per structure on page-locked host buffers, unsatisfied and "
-                                          "underconstrained masks on", "sizes": sweep}
+                                   "api": "ONE ezpz_b200_solve_jobs_multi call per pass (eight structure-homogeneous jobs, four workers per "
+                                          "GPU) on page-locked host buffers, unsatisfied and underconstrained masks on", "sizes": sweep}
         if world == 1:
             cb = cpu_arm(3, 1, BATCH_PER_GPU)
             line["cpu_baseline"] = {k: v for k, v in cb.items() if k != "ms_per_step"}

@@ -781,6 +781,42 @@ class MultiContext:
                            want_degen, want_jacobian, out, want_under)
 
 
+def _multi_solve_jobs(self, jobs, config=None, want_unsat=True, want_under=False):
+    """ezpz_b200_solve_jobs_multi: several (structure, guesses[, out]) batches in ONE call — the sub-batches of a mixed
+    workload.  `jobs`: list of (Structure, guesses) or (Structure, guesses, BatchResult to fill).  Returns the BatchResults."""
+    cfg = (config or Config())._native()
+    arr = (native.BatchJob * max(1, len(jobs)))()
+    keep, results = [], []
+    for k, job in enumerate(jobs):
+        st, guesses = job[0], job[1]
+        g = np.ascontiguousarray(guesses, dtype=np.float64).reshape(-1, st.n_vars)
+        B = g.shape[0]
+        res = job[2] if len(job) > 2 and job[2] is not None else None
+        if res is None:
+            res = BatchResult()
+            res.final_values = np.empty_like(g)
+            res.iterations = np.empty(B, np.uint32)
+            res.status = np.empty(B, np.uint8)
+            res.unsat_mask = np.zeros((B, (st.n_cons + 31) // 32), np.uint32) if want_unsat else None
+            res.under_mask = np.zeros((B, (st.n_vars + 31) // 32), np.uint32) if want_under else None
+            res.degen_count = res.jacobian = None
+        arr[k].structure = st.handle
+        arr[k].batch = B
+        arr[k].io = native.BatchIO(native.ptr(g), None, native.ptr(res.final_values), native.ptr(res.iterations), native.ptr(res.status),
+                                   native.ptr(res.unsat_mask), native.ptr(getattr(res, "degen_count", None)),
+                                   native.ptr(getattr(res, "jacobian", None)), native.ptr(getattr(res, "under_mask", None)))
+        keep.append((g, st))
+        results.append(res)
+    det = native.ErrorDetail()
+    rc = native.lib().ezpz_b200_solve_jobs_multi(self.handle, C.byref(cfg), arr, len(jobs), C.byref(det))
+    if rc != 0:
+        raise EzpzError(rc, det)
+    return results
+
+
+MultiContext.solve_jobs = _multi_solve_jobs
+
+
 class PinnedArray:
     """A numpy array in page-locked host memory every device can address (ezpz_b200_host_alloc); freed with the object."""
 

@@ -6,6 +6,7 @@
 // no exchange step and hence no collective — SURVEY.md §8e), hands shard k to worker k and returns when all are done.
 // Every worker runs the same single-device entry point on its slice of the CALLER's buffers, so a problem's result does
 // not depend on how many devices took part.
+#include <algorithm>
 #include <atomic>
 #include <condition_variable>
 #include <cstdio>
@@ -26,7 +27,30 @@ struct Job {
     const ezpz_config_t* config = nullptr;
     uint64_t count = 0;
     ezpz_batch_io_t io{};
+    int32_t* status = nullptr;  // where the job's own status goes (ezpz_b200_solve_jobs_multi)
 };
+
+// A slice [b0, b1) of a batch call as a job of its own.
+Job slice_job(const ezpz_structure_t* s, const ezpz_config_t* config, const ezpz_batch_io_t* io, uint64_t b0, uint64_t b1) {
+    uint32_t m = 0, n = 0;
+    uint64_t nnz = 0;
+    ezpz_b200_structure_dims(s, &m, &n, &nnz, nullptr, nullptr, nullptr);
+    const size_t nc = s->n_cons, uw = (s->n_cons + 31) / 32, vw = (n + 31) / 32;
+    Job job;
+    job.s = s;
+    job.config = config;
+    job.count = b1 - b0;
+    job.io.guesses = io->guesses + b0 * n;
+    job.io.params = io->params ? io->params + b0 * nc : nullptr;
+    job.io.final_values = io->final_values + b0 * n;
+    job.io.iterations = io->iterations + b0;
+    job.io.status = io->status + b0;
+    job.io.unsat_mask = io->unsat_mask ? io->unsat_mask + b0 * uw : nullptr;
+    job.io.degen_count = io->degen_count ? io->degen_count + b0 * nc : nullptr;
+    job.io.jacobian = io->jacobian ? io->jacobian + b0 * nnz : nullptr;
+    job.io.under_mask = io->under_mask ? io->under_mask + b0 * vw : nullptr;
+    return job;
+}
 
 struct Worker {
     int device = 0;
@@ -37,7 +61,7 @@ struct Worker {
     bool has_job = false, done = true, quit = false;
     std::atomic<uint32_t> posted{0};     // jobs handed to this worker so far (what a spinning worker watches)
     std::atomic<uint32_t> completed{0};  // jobs it has finished (what the caller watches)
-    Job job;
+    std::vector<Job> jobs;  // what the worker runs next, in order
     int32_t rc = EZPZ_OK;
     ezpz_error_detail_t detail{};
 };
@@ -69,9 +93,19 @@ void worker_main(Worker* w) {
         w->cv.wait(lock, [&] { return w->has_job || w->quit; });
         if (w->quit) return;
         w->has_job = false;
-        Job job = w->job;
+        std::vector<Job> jobs;
+        jobs.swap(w->jobs);
         lock.unlock();
-        const int32_t rc = ezpz_b200_solve_batch(w->ctx, job.s, job.config, job.count, &job.io, &w->detail);
+        int32_t rc = EZPZ_OK;
+        for (Job& job : jobs) {
+            ezpz_error_detail_t det;
+            const int32_t r = ezpz_b200_solve_batch(w->ctx, job.s, job.config, job.count, &job.io, &det);
+            if (job.status) *job.status = r;
+            if (r != EZPZ_OK && rc == EZPZ_OK) {
+                rc = r;
+                w->detail = det;
+            }
+        }
         lock.lock();
         w->rc = rc;
         w->done = true;
@@ -154,54 +188,25 @@ uint64_t ezpz_b200_multi_launches(const ezpz_multi_t* mg) {
     return total;
 }
 
-int32_t ezpz_b200_solve_batch_multi(ezpz_multi_t* mg, const ezpz_structure_t* s, const ezpz_config_t* config, uint64_t batch,
-                                    const ezpz_batch_io_t* io, ezpz_error_detail_t* detail) {
-    if (!mg || !s || !config || !io || mg->workers.empty()) return EZPZ_ERR_INVALID_ARGUMENT;
-    if (detail) std::memset(detail, 0, sizeof *detail);
-    if (batch == 0) return EZPZ_OK;
-    if (!io->guesses || !io->final_values || !io->iterations || !io->status) return EZPZ_ERR_INVALID_ARGUMENT;
-    std::lock_guard<std::mutex> call(mg->call_mutex);
-    const uint32_t world = (uint32_t)mg->workers.size();
-    uint32_t m = 0, n = 0;
-    uint64_t nnz = 0;
-    ezpz_b200_structure_dims(s, &m, &n, &nnz, nullptr, nullptr, nullptr);
-    const size_t nc = s->n_cons, uw = (s->n_cons + 31) / 32;
-    // Shards are whole groups of 32 problems (the batched kernel's unit) except the last.
-    const uint64_t groups = (batch + 31) / 32;
-    // The calling thread takes the first shard itself, on that worker's context (a context belongs to whoever solves with it,
-    // one at a time; the worker's own thread stays asleep): a one-device multi-context costs no hand-off at all, and with several
-    // devices the workers' wake-up latency hides behind the caller's own shard.
+// Hands list k to worker k and waits for all of them.  The calling thread runs the first non-empty list itself, on that
+// worker's context (a context belongs to whoever solves with it, one at a time; the worker's own thread stays asleep): a
+// one-worker multi-context costs no hand-off at all, and the other workers' wake-up latency hides behind the caller's own work.
+static int32_t run_lists(ezpz_multi_t* mg, std::vector<std::vector<Job>>& lists, ezpz_error_detail_t* detail) {
     std::vector<Worker*> used;
     std::vector<uint32_t> target;
-    Job own;
     Worker* own_worker = nullptr;
-    for (uint32_t k = 0; k < world; ++k) {
-        uint64_t g0 = 0, g1 = 0;
-        ezpz_b200_shard_range(groups, k, world, &g0, &g1);
-        const uint64_t b0 = std::min<uint64_t>(batch, g0 * 32), b1 = std::min<uint64_t>(batch, g1 * 32);
-        if (b1 <= b0) continue;
+    std::vector<Job> own;
+    for (size_t k = 0; k < lists.size(); ++k) {
+        if (lists[k].empty()) continue;
         Worker* w = mg->workers[k];
-        Job job;
-        job.s = s;
-        job.config = config;
-        job.count = b1 - b0;
-        job.io.guesses = io->guesses + b0 * n;
-        job.io.params = io->params ? io->params + b0 * nc : nullptr;
-        job.io.final_values = io->final_values + b0 * n;
-        job.io.iterations = io->iterations + b0;
-        job.io.status = io->status + b0;
-        job.io.unsat_mask = io->unsat_mask ? io->unsat_mask + b0 * uw : nullptr;
-        job.io.degen_count = io->degen_count ? io->degen_count + b0 * nc : nullptr;
-        job.io.jacobian = io->jacobian ? io->jacobian + b0 * nnz : nullptr;
-        job.io.under_mask = io->under_mask ? io->under_mask + b0 * ((s->n + 31) / 32) : nullptr;
         if (!own_worker) {
             own_worker = w;
-            own = job;
+            own.swap(lists[k]);
             continue;
         }
         {
             std::lock_guard<std::mutex> lock(w->m);
-            w->job = job;
+            w->jobs.swap(lists[k]);
             w->has_job = true;
             w->done = false;
             target.push_back(w->completed.load(std::memory_order_relaxed) + 1);
@@ -211,8 +216,14 @@ int32_t ezpz_b200_solve_batch_multi(ezpz_multi_t* mg, const ezpz_structure_t* s,
         used.push_back(w);
     }
     int32_t rc = EZPZ_OK;
-    if (own_worker) {
-        rc = ezpz_b200_solve_batch(own_worker->ctx, own.s, own.config, own.count, &own.io, detail);
+    for (Job& job : own) {
+        ezpz_error_detail_t det;
+        const int32_t r = ezpz_b200_solve_batch(own_worker->ctx, job.s, job.config, job.count, &job.io, &det);
+        if (job.status) *job.status = r;
+        if (r != EZPZ_OK && rc == EZPZ_OK) {
+            rc = r;
+            if (detail) *detail = det;
+        }
     }
     for (size_t k = 0; k < used.size(); ++k) {
         Worker* w = used[k];
@@ -229,6 +240,75 @@ int32_t ezpz_b200_solve_batch_multi(ezpz_multi_t* mg, const ezpz_structure_t* s,
         }
     }
     return rc;
+}
+
+int32_t ezpz_b200_solve_batch_multi(ezpz_multi_t* mg, const ezpz_structure_t* s, const ezpz_config_t* config, uint64_t batch,
+                                    const ezpz_batch_io_t* io, ezpz_error_detail_t* detail) {
+    if (!mg || !s || !config || !io || mg->workers.empty()) return EZPZ_ERR_INVALID_ARGUMENT;
+    if (detail) std::memset(detail, 0, sizeof *detail);
+    if (batch == 0) return EZPZ_OK;
+    if (!io->guesses || !io->final_values || !io->iterations || !io->status) return EZPZ_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> call(mg->call_mutex);
+    const uint32_t world = (uint32_t)mg->workers.size();
+    // Shards are whole groups of 32 problems (the batched kernel's unit) except the last.
+    const uint64_t groups = (batch + 31) / 32;
+    std::vector<std::vector<Job>> lists(world);
+    for (uint32_t k = 0; k < world; ++k) {
+        uint64_t g0 = 0, g1 = 0;
+        ezpz_b200_shard_range(groups, k, world, &g0, &g1);
+        const uint64_t b0 = std::min<uint64_t>(batch, g0 * 32), b1 = std::min<uint64_t>(batch, g1 * 32);
+        if (b1 > b0) lists[k].push_back(slice_job(s, config, io, b0, b1));
+    }
+    return run_lists(mg, lists, detail);
+}
+
+// Several batches at once — the structure-homogeneous sub-batches of a mixed workload (BASELINE.json configs[4]).  Large jobs
+// are cut over the workers like a single batch call; the others go whole to the least loaded worker, largest first, and every
+// worker runs its list in order.  A multi-context may hold SEVERAL workers per device (ezpz_b200_multi_create with a device
+// listed more than once): their streams overlap on the GPU, which is what keeps it busy when the sub-batches are small.
+int32_t ezpz_b200_solve_jobs_multi(ezpz_multi_t* mg, const ezpz_config_t* config, ezpz_batch_job_t* jobs, uint32_t n_jobs,
+                                   ezpz_error_detail_t* detail) {
+    if (!mg || !config || (n_jobs && !jobs) || mg->workers.empty()) return EZPZ_ERR_INVALID_ARGUMENT;
+    if (detail) std::memset(detail, 0, sizeof *detail);
+    for (uint32_t j = 0; j < n_jobs; ++j) {
+        jobs[j].status = EZPZ_OK;
+        if (!jobs[j].structure) return EZPZ_ERR_INVALID_ARGUMENT;
+        if (jobs[j].batch && (!jobs[j].io.guesses || !jobs[j].io.final_values || !jobs[j].io.iterations || !jobs[j].io.status))
+            return EZPZ_ERR_INVALID_ARGUMENT;
+    }
+    std::lock_guard<std::mutex> call(mg->call_mutex);
+    const uint32_t world = (uint32_t)mg->workers.size();
+    std::vector<std::vector<Job>> lists(world);
+    std::vector<uint64_t> load(world, 0);  // modelled cost per worker: problems x constraints
+    std::vector<uint32_t> order;
+    for (uint32_t j = 0; j < n_jobs; ++j)
+        if (jobs[j].batch) order.push_back(j);
+    auto cost = [&](uint32_t j) { return jobs[j].batch * (uint64_t)std::max<uint32_t>(1, jobs[j].structure->n_cons); };
+    std::sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return cost(x) > cost(y); });
+    constexpr uint64_t kSplitProblems = 65536;  // jobs of this size and more are cut over all workers
+    for (uint32_t j : order) {
+        const ezpz_batch_job_t& jb = jobs[j];
+        if (world > 1 && jb.batch >= kSplitProblems) {
+            const uint64_t groups = (jb.batch + 31) / 32;
+            for (uint32_t k = 0; k < world; ++k) {
+                uint64_t g0 = 0, g1 = 0;
+                ezpz_b200_shard_range(groups, k, world, &g0, &g1);
+                const uint64_t b0 = std::min<uint64_t>(jb.batch, g0 * 32), b1 = std::min<uint64_t>(jb.batch, g1 * 32);
+                if (b1 <= b0) continue;
+                Job job = slice_job(jb.structure, config, &jb.io, b0, b1);
+                job.status = &jobs[j].status;  // (any failing slice marks the job)
+                lists[k].push_back(job);
+                load[k] += (b1 - b0) * (uint64_t)std::max<uint32_t>(1, jb.structure->n_cons);
+            }
+        } else {
+            const uint32_t k = (uint32_t)(std::min_element(load.begin(), load.end()) - load.begin());
+            Job job = slice_job(jb.structure, config, &jb.io, 0, jb.batch);
+            job.status = &jobs[j].status;
+            lists[k].push_back(job);
+            load[k] += cost(j);
+        }
+    }
+    return run_lists(mg, lists, detail);
 }
 
 int32_t ezpz_b200_host_register(void* ptr, uint64_t bytes) {

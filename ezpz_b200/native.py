@@ -30,6 +30,10 @@ class BatchIO(C.Structure):
                 ("degen_count", C.c_void_p), ("jacobian", C.c_void_p), ("under_mask", C.c_void_p)]
 
 
+class BatchJob(C.Structure):
+    _fields_ = [("structure", C.c_void_p), ("batch", C.c_uint64), ("io", BatchIO), ("status", C.c_int32), ("reserved", C.c_int32)]
+
+
 class OneIO(C.Structure):
     _fields_ = [("guesses", C.c_void_p), ("final_values", C.c_void_p), ("iterations", C.c_void_p),
                 ("status", C.c_void_p), ("unsat_mask", C.c_void_p), ("degen_count", C.c_void_p),
@@ -81,6 +85,7 @@ _SYMBOLS = [
     ("ezpz_b200_multi_context", _P, [_P, C.c_int32]),
     ("ezpz_b200_multi_launches", C.c_uint64, [_P]),
     ("ezpz_b200_solve_batch_multi", C.c_int32, [_P, _P, C.POINTER(Config), C.c_uint64, C.POINTER(BatchIO), C.POINTER(ErrorDetail)]),
+    ("ezpz_b200_solve_jobs_multi", C.c_int32, [_P, C.POINTER(Config), C.POINTER(BatchJob), C.c_uint32, C.POINTER(ErrorDetail)]),
     ("ezpz_b200_host_register", C.c_int32, [_P, C.c_uint64]),
     ("ezpz_b200_host_unregister", C.c_int32, [_P]),
     ("ezpz_b200_host_alloc", C.c_int32, [C.c_uint64, C.POINTER(_P)]),

@@ -298,6 +298,21 @@ uint64_t ezpz_b200_multi_launches(const ezpz_multi_t* mg);
 int32_t ezpz_b200_solve_batch_multi(ezpz_multi_t* mg, const ezpz_structure_t* s, const ezpz_config_t* config,
                                     uint64_t batch, const ezpz_batch_io_t* io, ezpz_error_detail_t* detail);
 
+/* Several batches in one call: the structure-homogeneous sub-batches of a MIXED workload (problems of different topologies
+ * cannot share a launch).  Jobs of 65,536 problems and more are cut over all workers like a single batch call, the others go
+ * whole to the least loaded worker (largest first); each worker runs its list in order.  A multi-context may hold several
+ * workers per device (list the device more than once in ezpz_b200_multi_create): their streams overlap on the GPU, which keeps
+ * it busy when the sub-batches are small.  `status` of every job is set; the call returns the first failure. */
+typedef struct ezpz_batch_job {
+    const ezpz_structure_t* structure;
+    uint64_t batch;
+    ezpz_batch_io_t io;  /* host pointers, as for ezpz_b200_solve_batch */
+    int32_t status;
+    int32_t reserved;
+} ezpz_batch_job_t;
+int32_t ezpz_b200_solve_jobs_multi(ezpz_multi_t* mg, const ezpz_config_t* config, ezpz_batch_job_t* jobs, uint32_t n_jobs,
+                                   ezpz_error_detail_t* detail);
+
 /* Page-locked host memory every device can address (what a Rust caller would wrap its Vec<f64> buffers with): register an
  * existing allocation, or allocate one. */
 int32_t ezpz_b200_host_register(void* ptr, uint64_t bytes);

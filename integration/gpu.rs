@@ -95,6 +95,15 @@ pub struct EzpzOutcome {
     pub reserved: u32,
 }
 
+#[repr(C)]
+pub struct EzpzBatchJob {
+    pub structure: *const EzpzStructure,
+    pub batch: u64,
+    pub io: EzpzBatchIo,
+    pub status: i32,
+    pub reserved: i32,
+}
+
 pub enum EzpzStructure {}
 pub enum EzpzContext {}
 pub enum EzpzMulti {}
@@ -147,6 +156,8 @@ extern "C" {
     pub fn ezpz_b200_multi_launches(mg: *const EzpzMulti) -> u64;
     pub fn ezpz_b200_solve_batch_multi(mg: *mut EzpzMulti, s: *const EzpzStructure, cfg: *const EzpzConfig, batch: u64,
                                        io: *const EzpzBatchIo, detail: *mut EzpzErrorDetail) -> i32;
+    pub fn ezpz_b200_solve_jobs_multi(mg: *mut EzpzMulti, cfg: *const EzpzConfig, jobs: *mut EzpzBatchJob, n_jobs: u32,
+                                      detail: *mut EzpzErrorDetail) -> i32;
     pub fn ezpz_b200_host_register(ptr: *mut c_void, bytes: u64) -> i32;
     pub fn ezpz_b200_host_unregister(ptr: *mut c_void) -> i32;
     pub fn ezpz_b200_host_alloc(bytes: u64, out: *mut *mut c_void) -> i32;

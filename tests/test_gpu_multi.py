@@ -107,3 +107,27 @@ def test_multi_mid_size_systems_and_errors(multi):
         multi.solve_batch(st, G, params=np.zeros((9, st.n_cons)))  # unsupported on this path: every worker says so
     out2 = multi.solve_batch(st, G)  # the workers are still alive
     assert np.array_equal(out2.final_values, out.final_values)
+
+
+def test_jobs_of_a_mixed_workload_in_one_call():
+    """ezpz_b200_solve_jobs_multi: the eight structure-homogeneous sub-batches of config 5 in ONE call, several workers per
+    device (their streams overlap on the GPU); every problem identical to the oracle, verdict masks included."""
+    n_dev = _device_count()
+    multi = ez.MultiContext(devices=[d for d in range(n_dev) for _ in range(4)])
+    assert multi.device_count == 4 * n_dev
+    subs = wl.mixed_batches(4096)
+    jobs = []
+    for name, recs, n, g in subs:
+        jobs.append((ez.Structure(recs, n), g))
+    results = multi.solve_jobs(jobs, want_unsat=True, want_under=True)
+    for (name, recs, n, g), res in zip(subs, results):
+        fin, it, status, um, vm = orc.solve_batch(recs, n, g, hoist=True, verdicts=True)
+        assert np.array_equal(res.iterations, it), name
+        assert np.array_equal(res.final_values.view(np.uint64), fin.view(np.uint64)), name
+        assert np.array_equal(res.unsat_mask, um) and np.array_equal(res.under_mask, vm), name
+    # a large job is cut over the workers, a failing job reports through its own status without hanging the others
+    recs, n, g = wl.two_rectangles_batch(70001)
+    st = ez.Structure(recs, n)
+    big = multi.solve_jobs([(st, g)])[0]
+    ref = multi.solve_batch(st, g)
+    assert np.array_equal(big.final_values.view(np.uint64), ref.final_values.view(np.uint64))
