@@ -26,6 +26,7 @@
 #include <algorithm>
 #include <cstring>
 #include <mutex>
+#include <utility>
 
 #include "device.h"
 #include "dmath.cuh"
@@ -402,6 +403,234 @@ __global__ void __launch_bounds__(GRID ? 256 : 1024) freedom_team_kernel(const F
     }
 }
 
+// One Householder step of the register-resident QR (freedom_warp_kernel); K is a template parameter so that every index
+// into the per-lane arrays is a compile-time constant (a runtime k would push the arrays into local memory).
+template <int K, int MAXD>
+__device__ __forceinline__ void qr_step(double (&A)[MAXD], double (&rd)[MAXD], uint32_t& pos, double& nrm, uint32_t lane, bool active,
+                                        uint32_t m, uint32_t ndiag, double* tile) {
+    const unsigned FULL = 0xffffffffu;
+    rd[K] = 0.0;
+    if ((uint32_t)K >= ndiag) return;
+    // pivot among the columns at positions >= K: largest norm, first position among equals; a NaN norm never wins
+    const bool cand = active && pos >= (uint32_t)K && nrm == nrm;
+    double bn = cand ? nrm : -1.0;
+    uint32_t bp = cand ? pos : 0xffffffffu;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const double ob = __shfl_xor_sync(FULL, bn, off);
+        const uint32_t op = __shfl_xor_sync(FULL, bp, off);
+        if (ob > bn || (ob == bn && op < bp)) {
+            bn = ob;
+            bp = op;
+        }
+    }
+    if (bp == 0xffffffffu) bp = (uint32_t)K;  // (nothing but NaNs: the oracle keeps column K)
+    const uint32_t best_lane = __ffs(__ballot_sync(FULL, active && pos == bp)) - 1u;
+    const uint32_t lane_k = __ffs(__ballot_sync(FULL, active && pos == (uint32_t)K)) - 1u;
+    if (lane == best_lane) pos = (uint32_t)K;
+    else if (lane == lane_k) pos = bp;
+    const double norm = sqrt(bn);
+    const double akk = __shfl_sync(FULL, A[K], best_lane);
+    if (norm == 0.0) {  // zero pivot: R_kk = 0, the remaining norms restart one row lower (find_dof: `continue`)
+        nrm = 0.0;
+#pragma unroll
+        for (int i = K + 1; i < MAXD; ++i)
+            if ((uint32_t)i < m) nrm += A[i] * A[i];
+        return;
+    }
+    const double alpha = akk > 0 ? -norm : norm;
+    const double vk = akk - alpha;
+    const double tau = -vk / alpha;
+    rd[K] = alpha;
+    // v_i = A(i, pivot column) / vk for the rows below K.  A division is some thirty instructions for the whole warp whether
+    // one lane or all of them divide: the pivot column goes through the warp's shared-memory tile so that LANE i divides
+    // row i — one division per step instead of one per row — and every lane reads the quotients back (broadcast loads).
+    double v[MAXD];
+    if (lane == best_lane) {
+#pragma unroll
+        for (int i = K + 1; i < MAXD; ++i) tile[i] = A[i];
+    }
+    __syncwarp();
+    const double vi = (lane > (uint32_t)K && lane < m) ? tile[lane] / vk : 0.0;
+    __syncwarp();
+    tile[lane] = vi;
+    __syncwarp();
+#pragma unroll
+    for (int i = K + 1; i < MAXD; ++i) v[i] = tile[i];
+    __syncwarp();
+    if (lane == best_lane) {
+        A[K] = alpha;
+    } else if (active && pos > (uint32_t)K) {
+        double s = A[K];
+#pragma unroll
+        for (int i = K + 1; i < MAXD; ++i)
+            if ((uint32_t)i < m) s += v[i] * A[i];
+        s *= tau;
+        A[K] -= s;
+        nrm = 0.0;
+#pragma unroll
+        for (int i = K + 1; i < MAXD; ++i)
+            if ((uint32_t)i < m) {
+                A[i] -= s * v[i];
+                nrm += A[i] * A[i];
+            }
+    }
+}
+template <int MAXD, int... Ks>
+__device__ __forceinline__ void qr_steps(std::integer_sequence<int, Ks...>, double (&A)[MAXD], double (&rd)[MAXD], uint32_t& pos, double& nrm,
+                                         uint32_t lane, bool active, uint32_t m, uint32_t ndiag, double* tile) {
+    (qr_step<Ks, MAXD>(A, rd, pos, nrm, lane, active, m, ndiag, tile), ...);
+}
+
+// Back substitution row II of the null-space basis (freedom_warp_kernel), II a compile-time constant for the same reason.
+template <int II, int MAXD>
+__device__ __forceinline__ void back_row(const double (&A)[MAXD], double (&z)[MAXD], const uint32_t (&lop)[MAXD], uint32_t rank) {
+    const unsigned FULL = 0xffffffffu;
+    if ((uint32_t)II >= rank) return;
+    double rhs = A[II];
+#pragma unroll
+    for (int j = II + 1; j < MAXD; ++j)
+        if ((uint32_t)j < rank) rhs += __shfl_sync(FULL, A[II], lop[j]) * z[j];
+    const double diagonal = __shfl_sync(FULL, A[II], lop[II]);
+    z[II] = -rhs / diagonal;
+}
+template <int MAXD, int... Is>
+__device__ __forceinline__ void back_rows(std::integer_sequence<int, Is...>, const double (&A)[MAXD], double (&z)[MAXD],
+                                          const uint32_t (&lop)[MAXD], uint32_t rank) {
+    (back_row<MAXD - 1 - Is, MAXD>(A, z, lop, rank), ...);  // rows descending
+}
+
+// ---- Small sketches: a WARP per problem, the matrix in REGISTERS --------------------------------------------------------
+// For m, n <= 16 (the sketches of BASELINE.json's config 5) lane j holds column j of the Jacobian in registers; a
+// Householder step is a handful of shuffles (the pivot column's entries broadcast as v) and each lane's own fma-free
+// chains — no shared memory, no barriers, ~10x fewer instructions than the team kernel, which spent 73 % of its issue slots
+// on index arithmetic and barriers for 16 x 16 matrices.  Columns are never moved: a lane tracks the POSITION of its column
+// in the oracle's swapped order, so ties between equal norms break exactly as the oracle's "first maximum" does.  Every
+// sum runs in the oracle's order (rows ascending, free columns ascending, modified Gram-Schmidt g ascending), so the whole
+// analysis — not only the QR — is bit-identical to oracle/ezpz_oracle.cpp freedom_analysis.
+template <int MAXD>
+__global__ void __launch_bounds__(128) freedom_warp_kernel(const FreedomArgs a) {
+    extern __shared__ double fsm[];  // per warp: MAXD x 32 doubles, only to densify the sparse columns
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t p = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (p >= a.count) return;
+    const uint32_t m = a.m, n = a.n, ndiag = m < n ? m : n;
+    const bool active = lane < n;
+    const unsigned FULL = 0xffffffffu;
+    double* tile = fsm + (size_t)warp * MAXD * 32;
+    const double* jac = a.jac + (size_t)p * a.nnz;
+#pragma unroll
+    for (int i = 0; i < MAXD; ++i) tile[i * 32 + lane] = 0.0;
+    __syncwarp();
+    if (active)
+        for (uint32_t e = a.csc_col_ptr[lane]; e < a.csc_col_ptr[lane + 1]; ++e) tile[a.csc_row_idx[e] * 32 + lane] = jac[e];
+    __syncwarp();
+    double A[MAXD];
+#pragma unroll
+    for (int i = 0; i < MAXD; ++i) A[i] = tile[i * 32 + lane];
+    uint32_t pos = lane;  // position of this lane's column in the oracle's (swapped) column order
+    double rd[MAXD];
+    double nrm = 0.0;
+#pragma unroll
+    for (int i = 0; i < MAXD; ++i)
+        if ((uint32_t)i < m) nrm += A[i] * A[i];
+    __syncwarp();
+    qr_steps<MAXD>(std::make_integer_sequence<int, MAXD>{}, A, rd, pos, nrm, lane, active, m, ndiag, tile);
+    // ---- rank (find_dof.rs:40-52)
+    double largest = ezm::ez_abs(rd[0]);
+#pragma unroll
+    for (int i = 1; i < MAXD; ++i)
+        if ((uint32_t)i < ndiag) largest = ezm::ez_fmax(largest, ezm::ez_abs(rd[i]));
+    const double tolerance = 1e-8 * largest;
+    uint32_t rank = 0;
+    {
+        bool run = true;
+#pragma unroll
+        for (int i = 0; i < MAXD; ++i) {
+            run = run && (uint32_t)i < ndiag && ezm::ez_abs(rd[i]) > tolerance;
+            if (run) rank = (uint32_t)i + 1u;
+        }
+    }
+    uint32_t* mask = a.mask + (size_t)p * a.words;
+    if (rank == n) {
+        if (lane == 0) mask[0] = 0;
+        return;
+    }
+    uint32_t lop[MAXD];  // lane that holds the column at each position
+#pragma unroll
+    for (int q = 0; q < MAXD; ++q) lop[q] = (uint32_t)q < n ? __ffs(__ballot_sync(FULL, active && pos == (uint32_t)q)) - 1u : 0u;
+    // ---- basis of null(J P^T): back substitution over R11 for this lane's column (meaningful in the free lanes)
+    double z[MAXD];
+#pragma unroll
+    for (int i = 0; i < MAXD; ++i) z[i] = 0.0;
+    back_rows<MAXD>(std::make_integer_sequence<int, MAXD>{}, A, z, lop, rank);
+#pragma unroll
+    for (int i = 0; i < MAXD; ++i)
+        if ((uint32_t)i >= rank) z[i] = ((uint32_t)i == pos) ? 1.0 : 0.0;
+    // ---- modified Gram-Schmidt (twice) over the free columns in position order, then normalise
+#pragma unroll 1
+    for (uint32_t pf = rank; pf < n; ++pf) {
+        uint32_t cur = 0;
+#pragma unroll
+        for (int q = 0; q < MAXD; ++q)
+            if ((uint32_t)q == pf) cur = lop[q];
+        double zc[MAXD];  // the column being orthonormalised, replicated in every lane
+#pragma unroll
+        for (int i = 0; i < MAXD; ++i) zc[i] = (uint32_t)i < n ? __shfl_sync(FULL, z[i], cur) : 0.0;
+        for (int pass = 0; pass < 2; ++pass)
+#pragma unroll 1
+            for (uint32_t pg = rank; pg < pf; ++pg) {
+                uint32_t gl = 0;
+#pragma unroll
+                for (int q = 0; q < MAXD; ++q)
+                    if ((uint32_t)q == pg) gl = lop[q];
+                double s = 0.0;
+#pragma unroll
+                for (int i = 0; i < MAXD; ++i)
+                    if ((uint32_t)i < n) s += z[i] * zc[i];  // (the value of lane gl is the one used)
+                s = __shfl_sync(FULL, s, gl);
+#pragma unroll
+                for (int i = 0; i < MAXD; ++i)
+                    if ((uint32_t)i < n) zc[i] -= s * __shfl_sync(FULL, z[i], gl);
+            }
+        double s = 0.0;
+#pragma unroll
+        for (int i = 0; i < MAXD; ++i)
+            if ((uint32_t)i < n) s += zc[i] * zc[i];
+        s = sqrt(s);
+        if (lane == cur) {
+#pragma unroll
+            for (int i = 0; i < MAXD; ++i)
+                if ((uint32_t)i < n) z[i] = zc[i] / s;
+        }
+    }
+    // ---- participation of the variable at every position: sum over the free columns, ascending (find_dof.rs:82-104)
+    double my_part = 0.0;
+#pragma unroll
+    for (int i = 0; i < MAXD; ++i)
+        if ((uint32_t)i < n) {
+            const double sq = z[i] * z[i];
+            double total = 0.0;
+#pragma unroll 1
+            for (uint32_t pf = rank; pf < n; ++pf) {
+                uint32_t fl = 0;
+#pragma unroll
+                for (int q = 0; q < MAXD; ++q)
+                    if ((uint32_t)q == pf) fl = lop[q];
+                total += __shfl_sync(FULL, sq, fl);
+            }
+            if (pos == (uint32_t)i) my_part = total;
+        }
+    double max_p = active ? my_part : 0.0;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) max_p = ezm::ez_fmax(max_p, __shfl_xor_sync(FULL, max_p, off));
+    max_p = ezm::ez_fmax(0.0, max_p);
+    const double var_tol = 1e-3 * max_p;
+    const double squared_tol = var_tol * var_tol;
+    const uint32_t bits = __ballot_sync(FULL, active && my_part > squared_tol);
+    if (lane == 0) mask[0] = bits;
+}
+
 std::mutex g_attr_mutex;
 
 }  // namespace
@@ -441,6 +670,25 @@ int32_t freedom_device(ezpz_context* ctx, const ezpz_structure* s, uint64_t batc
     a.scratch = nullptr;
     // the work area of a team is reused launch after launch: launches of different streams take turns
     if (ctx->fa_busy && ctx->fa_last_stream != st) EZ_CUDA(cudaStreamWaitEvent(st, ctx->fa_done, 0), "cudaStreamWaitEvent");
+    // m, n <= 16: a warp per problem, matrix in registers
+    if (m <= 16 && n <= 16 && !std::getenv("EZPZ_B200_FREEDOM_TEAM")) {
+        a.per_problem = 0;
+        a.in_smem = a.v_smem = 0;
+        uint64_t done = 0;
+        while (done < batch) {
+            const uint64_t count = std::min<uint64_t>(batch - done, (uint64_t)1 << 30);
+            a.jac = d_jac + done * nnz;
+            a.mask = d_mask + done * a.words;
+            a.count = (uint32_t)count;
+            const uint32_t grid = (uint32_t)((count + 3) / 4);
+            if (m <= 8 && n <= 8) freedom_warp_kernel<8><<<grid, 128, 4 * 8 * 32 * sizeof(double), st>>>(a);
+            else freedom_warp_kernel<16><<<grid, 128, 4 * 16 * 32 * sizeof(double), st>>>(a);
+            ctx->launches += 1;
+            EZ_CUDA(cudaGetLastError(), "freedom_warp_kernel launch");
+            done += count;
+        }
+        return EZPZ_OK;
+    }
     const size_t smem_cap = ctx->smem_optin - 1024;
     const bool small = per * 8 <= (size_t)64 << 10;                       // matrix in shared memory
     const bool cta_team = small || (n <= 1024 && batch >= (uint64_t)ctx->sm_count / 2);
