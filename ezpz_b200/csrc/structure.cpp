@@ -17,6 +17,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <numeric>
+#include <thread>
 
 #include "kinds.h"
 
@@ -32,31 +33,66 @@ void set_detail(ezpz_error_detail_t* d, const char* msg) {
 // lower(A) by columns from the patterns of J: column j holds every i >= j that shares a row with j (and j itself:
 // lambda*I puts every diagonal in).  For each column its rows are walked in CSC order and their CSR entries >= j
 // collected with a marker array; the short list is then sorted.
+// Runs fn(begin, end, part) over [0, n) cut into contiguous parts on host threads; one part (the caller's thread, no
+// thread is started) below `grain` items per part.  Host analysis of systems with 10^5..10^6 variables.
+template <class F>
+static void parallel_ranges(uint32_t n, uint32_t grain, F&& fn, uint32_t* parts_out = nullptr) {
+    uint32_t nt = std::max(1u, std::min({std::thread::hardware_concurrency(), 16u, n / std::max(1u, grain)}));
+    if (const char* e = std::getenv("EZPZ_B200_HOST_THREADS")) nt = std::max(1u, std::min(nt, (uint32_t)std::strtoul(e, nullptr, 10)));
+    if (parts_out) *parts_out = nt;
+    if (nt <= 1) {
+        fn(0u, n, 0u);
+        return;
+    }
+    std::vector<std::thread> th;
+    for (uint32_t t = 1; t < nt; ++t)
+        th.emplace_back([&, t] { fn((uint32_t)((uint64_t)n * t / nt), (uint32_t)((uint64_t)n * (t + 1) / nt), t); });
+    fn(0u, (uint32_t)((uint64_t)n / nt), 0u);
+    for (auto& x : th) x.join();
+}
+constexpr uint32_t kHostGrain = 1u << 15;  // items per host thread before a phase is worth splitting
+
 void build_a_pattern(ezpz_structure& S) {
     const uint32_t n = S.n;
     S.a_col_ptr.assign((size_t)n + 1, 0);
     S.a_row_idx.clear();
-    S.a_row_idx.reserve(S.csc_row_idx.size() * 3 + n);
-    std::vector<uint32_t> mark(n, UINT32_MAX), col;
-    for (uint32_t j = 0; j < n; ++j) {
-        col.clear();
-        col.push_back(j);
-        mark[j] = j;
-        for (uint32_t p = S.csc_col_ptr[j]; p < S.csc_col_ptr[j + 1]; ++p) {
-            const uint32_t r = S.csc_row_idx[p];
-            for (uint32_t q = S.csr_row_ptr[r + 1]; q-- > S.csr_row_ptr[r];) {  // columns descending: stop below j
-                const uint32_t i = S.csr_col_idx[q];
-                if (i <= j) break;
-                if (mark[i] != j) {
-                    mark[i] = j;
-                    col.push_back(i);
+    // columns are independent: ranges of columns on host threads, each into its own list, concatenated in column order
+    struct Part {
+        std::vector<uint32_t> rows;
+        uint32_t c0 = 0, c1 = 0;
+    };
+    std::vector<Part> parts(16);
+    uint32_t n_parts = 1;
+    parallel_ranges(n, kHostGrain, [&](uint32_t c0, uint32_t c1, uint32_t t) {
+        Part& part = parts[t];
+        part.c0 = c0;
+        part.c1 = c1;
+        part.rows.reserve((size_t)(c1 - c0) * 8);
+        std::vector<uint32_t> mark(n, UINT32_MAX), col;
+        for (uint32_t j = c0; j < c1; ++j) {
+            col.clear();
+            col.push_back(j);
+            mark[j] = j;
+            for (uint32_t p = S.csc_col_ptr[j]; p < S.csc_col_ptr[j + 1]; ++p) {
+                const uint32_t r = S.csc_row_idx[p];
+                for (uint32_t q = S.csr_row_ptr[r + 1]; q-- > S.csr_row_ptr[r];) {  // columns descending: stop below j
+                    const uint32_t i = S.csr_col_idx[q];
+                    if (i <= j) break;
+                    if (mark[i] != j) {
+                        mark[i] = j;
+                        col.push_back(i);
+                    }
                 }
             }
+            std::sort(col.begin(), col.end());
+            part.rows.insert(part.rows.end(), col.begin(), col.end());
+            S.a_col_ptr[j + 1] = (uint32_t)col.size();  // (counts; turned into offsets below)
         }
-        std::sort(col.begin(), col.end());
-        S.a_row_idx.insert(S.a_row_idx.end(), col.begin(), col.end());
-        S.a_col_ptr[j + 1] = (uint32_t)S.a_row_idx.size();
-    }
+    }, &n_parts);
+    for (uint32_t j = 0; j < n; ++j) S.a_col_ptr[j + 1] += S.a_col_ptr[j];
+    S.a_row_idx.resize(S.a_col_ptr[n]);
+    for (uint32_t t = 0; t < n_parts; ++t)
+        if (!parts[t].rows.empty()) std::copy(parts[t].rows.begin(), parts[t].rows.end(), S.a_row_idx.begin() + S.a_col_ptr[parts[t].c0]);
 }
 
 // Natural-order symbolic Cholesky: struct(L_j) = struct(A_j) U (struct(L_c) \ {c}) over the children c of
@@ -685,39 +721,45 @@ int32_t ezpz_b200_structure_create(const ezpz_constraint_t* cons, uint32_t n_con
     S->n_side = 0;
     S->all_weights_one = true;
     for (uint32_t c = 0; c < n_cons; ++c) S->all_weights_one = S->all_weights_one && cons[c].weight == 1.0;
-    for (uint32_t c = 0; c < n_cons; ++c) {
-        const ezpz_constraint_t& src = cons[c];
-        const ezk::KindInfo& ki = ezk::kKinds[src.kind];
-        DevCons& dc = S->dev_cons[c];
-        std::memset(&dc, 0, sizeof dc);
-        dc.p0 = src.p0;
-        dc.p1 = src.p1;
-        dc.weight = src.weight;
-        dc.kind = src.kind;
-        dc.flags = src.flags;
-        dc.row0 = S->cons_row0[c];
-        dc.side_slot = UINT32_MAX;
-        if ((src.kind == EZPZ_K_LINE_TANGENT_TO_CIRCLE || src.kind == EZPZ_K_CIRCLE_TANGENT_TO_CIRCLE) &&
-            src.flags == EZPZ_SIDE_UNDEFINED)
-            dc.side_slot = S->n_side++;
-        std::memcpy(dc.ids, src.ids, sizeof dc.ids);
-        for (int row = 0; row < ki.rows; ++row) {
-            const uint32_t r = dc.row0 + row;
-            for (int k = 0; k < ki.emit_len[row]; ++k) {
-                const uint32_t col = src.ids[ki.emit[row][k]];
-                const uint32_t* b = S->csc_row_idx.data() + S->csc_col_ptr[col];
-                const uint32_t* e = S->csc_row_idx.data() + S->csc_col_ptr[col + 1];
-                const uint32_t* it = std::lower_bound(b, e, r);
-                uint32_t slot = (uint32_t)(it - S->csc_row_idx.data());
-                for (int q = 0; q < k; ++q)
-                    if ((dc.slot[row][q] & ~kAccumulate) == slot) {
-                        slot |= kAccumulate;
-                        break;
-                    }
-                dc.slot[row][k] = slot;
+    // side slots count the constraints with an Undefined side in input order (sequential); everything else per constraint
+    // is independent and runs on host threads for large systems
+    std::vector<uint32_t> side_slot(n_cons, UINT32_MAX);
+    for (uint32_t c = 0; c < n_cons; ++c)
+        if ((cons[c].kind == EZPZ_K_LINE_TANGENT_TO_CIRCLE || cons[c].kind == EZPZ_K_CIRCLE_TANGENT_TO_CIRCLE) &&
+            cons[c].flags == EZPZ_SIDE_UNDEFINED)
+            side_slot[c] = S->n_side++;
+    parallel_ranges(n_cons, kHostGrain, [&](uint32_t cb, uint32_t ce, uint32_t) {
+        for (uint32_t c = cb; c < ce; ++c) {
+            const ezpz_constraint_t& src = cons[c];
+            const ezk::KindInfo& ki = ezk::kKinds[src.kind];
+            DevCons& dc = S->dev_cons[c];
+            std::memset(&dc, 0, sizeof dc);
+            dc.p0 = src.p0;
+            dc.p1 = src.p1;
+            dc.weight = src.weight;
+            dc.kind = src.kind;
+            dc.flags = src.flags;
+            dc.row0 = S->cons_row0[c];
+            dc.side_slot = side_slot[c];
+            std::memcpy(dc.ids, src.ids, sizeof dc.ids);
+            for (int row = 0; row < ki.rows; ++row) {
+                const uint32_t r = dc.row0 + row;
+                for (int k = 0; k < ki.emit_len[row]; ++k) {
+                    const uint32_t col = src.ids[ki.emit[row][k]];
+                    const uint32_t* b = S->csc_row_idx.data() + S->csc_col_ptr[col];
+                    const uint32_t* e = S->csc_row_idx.data() + S->csc_col_ptr[col + 1];
+                    const uint32_t* it = std::lower_bound(b, e, r);
+                    uint32_t slot = (uint32_t)(it - S->csc_row_idx.data());
+                    for (int q = 0; q < k; ++q)
+                        if ((dc.slot[row][q] & ~kAccumulate) == slot) {
+                            slot |= kAccumulate;
+                            break;
+                        }
+                    dc.slot[row][k] = slot;
+                }
             }
         }
-    }
+    });
     lap("scatter slots");
     build_a_pattern(*S);
     lap("pattern of A");
