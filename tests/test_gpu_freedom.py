@@ -156,3 +156,22 @@ def test_batch_of_mid_size_systems(ctx):
             assert all(bits(w, n) == [5, 6, 83, 84] for w in out.under_mask)
         else:
             assert not out.under_mask.any()
+
+
+def test_fused_analysis_through_the_copy_pipeline_under_load():
+    """Shards of 32,768 problems and more take the three-stream copy / compute pipeline; the analysis of chunk k reads the
+    context's Jacobian buffer while chunk k + 1 is already queued on another stream, and several workers share the device.
+    (Regression: the warp-per-problem analysis once skipped the event the next chunk waits for — wrong masks on a loaded
+    8-GPU box.)"""
+    multi = ez.MultiContext(devices=[0, 0, 0, 0])
+    names = ["parc_coincident", "underconstrained", "arc_radius", "perpdist"]
+    subs = []
+    for k, name in enumerate(names):
+        recs, n, g = wl.perturbed_batch(name, 40000, 0xE2B200D5EED00000 + ((20 + k) << 40), half_width=0.05)
+        subs.append((name, recs, n, g, ez.Structure(recs, n)))
+    want = [orc.solve_batch(recs, n, g, hoist=True, verdicts=True) for name, recs, n, g, st in subs]
+    for rep in range(4):
+        results = multi.solve_jobs([(st, g) for name, recs, n, g, st in subs], want_unsat=True, want_under=True)
+        for (name, recs, n, g, st), res, (fin, it, status, um, vm) in zip(subs, results, want):
+            assert np.array_equal(res.under_mask, vm), (name, rep, int((res.under_mask != vm).any(axis=1).sum()))
+            assert np.array_equal(res.final_values.view(np.uint64), fin.view(np.uint64)), (name, rep)
