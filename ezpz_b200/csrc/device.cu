@@ -738,7 +738,7 @@ void release_device_copies(ezpz_structure* s) {
             if (d->csc_to_csr) cudaFree(d->csc_to_csr);
             if (d->csc_col_ptr) cudaFree(d->csc_col_ptr);
             if (d->csc_row_idx) cudaFree(d->csc_row_idx);
-            if (d->large) release_large(d);
+            if (!d->large.empty()) release_large(d);
         }
         delete d;
     }

@@ -25,7 +25,9 @@ struct DeviceCopy {
     uint32_t* csc_to_csr = nullptr;  // [nnz] position in CSR order of each CSC entry
     uint32_t* csc_col_ptr = nullptr;  // [n + 1], [nnz]: the pattern of J for the freedom analysis (freedom.cu), on first use
     uint32_t* csc_row_idx = nullptr;
-    void* large = nullptr;           // LargeDevice (large.cu), created on first use
+    // LargeDevice (large.cu: the structure's tables AND the work buffers of a solve), one per CONTEXT that solved with this
+    // structure on this device: two contexts (threads) may solve the same structure on one device at the same time
+    std::vector<std::pair<const void*, void*>> large;
 };
 
 int32_t cuda_fail(cudaError_t e, ezpz_error_detail_t* detail, const char* what);

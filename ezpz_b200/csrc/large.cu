@@ -1845,14 +1845,18 @@ struct DevicePlan {
     } while (0)
 
 int32_t get_large(ezpz_context* ctx, const ezpz_structure* s, DeviceCopy* dc, LargeDevice** out, ezpz_error_detail_t* detail) {
-    if (dc->large) {
-        *out = (LargeDevice*)dc->large;
-        return EZPZ_OK;
-    }
+    // one LargeDevice per context (it holds the work buffers of a solve, not only the tables); creation under the structure's
+    // lock, the creating context's stream does the upload
+    std::lock_guard<std::mutex> lock(const_cast<ezpz_structure*>(s)->dev_mutex);
+    for (auto& e : dc->large)
+        if (e.first == ctx) {
+            *out = (LargeDevice*)e.second;
+            return EZPZ_OK;
+        }
     const LargeProgram& P = s->large;
     LargeDevice* L = new (std::nothrow) LargeDevice();
     if (!L) return EZPZ_ERR_INVALID_ARGUMENT;
-    dc->large = L;  // owned by the device copy from here on (released with it)
+    dc->large.emplace_back(ctx, L);  // owned by the device copy from here on (released with it)
     DevicePlan plan;
     {
         // record tiles (see the comment above assemble_slot)
@@ -2090,15 +2094,17 @@ __global__ void __launch_bounds__(256) large_batch_gather_kernel(const LargeArgs
 namespace ezs {
 
 void release_large(DeviceCopy* d) {
-    LargeDevice* L = (LargeDevice*)d->large;
-    if (!L) return;
+    for (auto& entry : d->large) {
+    LargeDevice* L = (LargeDevice*)entry.second;
+    if (!L) continue;
     if (L->arena) cudaFreeAsync(L->arena, nullptr);  // every table and work buffer of the structure (DevicePlan); back to the pool
     void* bptrs[] = {L->batch.vg, L->batch.jr, L->batch.cgv, L->batch.sumsq, L->batch.partials, L->batch.side,
                      L->batch.degen, L->batch.unsat, L->batch.ctrl};
     for (void* p : bptrs)
         if (p) cudaFree(p);
     delete L;
-    d->large = nullptr;
+    }
+    d->large.clear();
 }
 
 // One residual + Jacobian evaluation at x through the large path's own assembly kernel (ezpz_b200_eval).

@@ -167,7 +167,8 @@ typedef struct ezpz_error_detail {
  * Model::new, solver.rs:192-300): validation, the deduplicated sorted sparsity pattern of J in
  * CSC and CSR, per-partial scatter slots, the pattern of A = JtJ + lambda*I, its symbolic Cholesky
  * and the operation tapes the device executes.  Immutable after creation; may be shared by
- * threads and contexts.
+ * threads and contexts (device tables are created per device on first use, the work buffers of the
+ * single-large-system path per context, and both live until the structure is destroyed).
  */
 typedef struct ezpz_structure ezpz_structure_t;
 

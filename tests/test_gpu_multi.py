@@ -131,3 +131,18 @@ def test_jobs_of_a_mixed_workload_in_one_call():
     big = multi.solve_jobs([(st, g)])[0]
     ref = multi.solve_batch(st, g)
     assert np.array_equal(big.final_values.view(np.uint64), ref.final_values.view(np.uint64))
+
+
+def test_two_contexts_on_one_device_share_a_mid_size_structure(ctx):
+    """The large path keeps its work buffers per CONTEXT: two workers on the same device solving shards of one mid-size
+    structure at the same time (one CTA per problem) must not see each other's state."""
+    multi = ez.MultiContext(devices=[0, 0, 0])
+    recs, n, g, exact = wl.chain_sketch(16)
+    st = ez.Structure(recs, n)
+    rng = np.random.default_rng(9)
+    G = g[None, :] + rng.uniform(-0.02, 0.02, (600, n))
+    ref = ctx.solve_batch(st, G)
+    for _ in range(3):
+        out = multi.solve_batch(st, G)
+        assert np.array_equal(out.final_values.view(np.uint64), ref.final_values.view(np.uint64))
+        assert np.array_equal(out.iterations, ref.iterations) and np.array_equal(out.status, ref.status)
