@@ -395,6 +395,86 @@ def large_system_report(ctx, peaks):
     return out
 
 
+def reference_benches(ctx):
+    """The reference's own criterion benches (ezpz/benches/solver_bench.rs:42-209), one solve per call through
+    ezpz_b200_solve (priority loop, lint, topology cache warm — the reference re-analyses every call) next to the CPU port:
+    solve_inconsistent, solve_nonsquare, solve_two_rectangles, solve_two_rectangles_dependent (14 variables),
+    solve_massive (200 and 600 lines), solve_massive_analysis (200 lines), solve_nonsquare_analysis."""
+    import ctypes as C
+
+    import numpy as np
+
+    import ezpz_b200 as ez
+    import orc
+    import textual_twin
+    import workloads as wl
+    from ezpz_b200 import native
+
+    def rec(kind, ids, p0=0.0):
+        r = np.zeros(1, dtype=textual_twin.REC_DTYPE)
+        r["kind"], r["p0"], r["weight"] = kind, p0, 1.0
+        r["ids"][0, :len(ids)] = ids
+        return r
+
+    def c_solve(recs, g, analysis):
+        n_cons, n_vars = len(recs), len(g)
+        fv, un, uc = np.zeros(n_vars), np.zeros(n_cons, np.uint64), np.zeros(n_vars, np.uint32)
+        warr = (native.WarningRec * (2 * n_cons + 8))()
+        out = native.OutcomeRec()
+        out.final_values, out.unsatisfied, out.underconstrained = fv.ctypes.data, un.ctypes.data, uc.ctypes.data
+        out.warnings, out.warnings_cap = C.addressof(warr), 2 * n_cons + 8
+        det = native.ErrorDetail()
+        cfg = ez.Config()._native()
+        args = (ctx.handle, native.ptr(recs), None, None, n_cons, None, native.ptr(g), n_vars, C.byref(cfg), 1 if analysis else 0,
+                C.byref(out), C.byref(det))
+        keep = (fv, un, uc, warr, out, det, cfg, recs, g)
+
+        def go():
+            rc = native.lib().ezpz_b200_solve(*args)
+            assert rc == 0 and keep
+            return out
+        return go
+
+    def case(recs, g, analysis, reps):
+        recs = np.ascontiguousarray(recs)
+        g = np.ascontiguousarray(g, dtype=np.float64)
+        go = c_solve(recs, g, analysis)
+        o = go()
+        gpu = statistics.median(timed_calls(go, reps, 3)) * 1e6
+        cpu_reps = max(1, min(reps, 20))
+        ref = orc.solve(recs, g, analysis=analysis)
+        cpu = statistics.median(timed_calls(lambda: orc.solve(recs, g, analysis=analysis), cpu_reps, 1)) * 1e6
+        d = {"gpu_us": gpu, "cpu_port_us": cpu, "lm_iterations": int(o.iterations), "cpu_lm_iterations": int(ref.iterations),
+             "n_vars": len(g), "n_eqs": int(o.num_eqs)}
+        if analysis:
+            d["underconstrained_agrees"] = int(o.n_underconstrained) == len(ref.underconstrained)
+        return d
+
+    out = {}
+    for name in ("inconsistent", "nonsquare", "two_rectangles"):
+        recs, n, g, _ = wl.system_from_text(wl.fixture_text(name))
+        out[f"solve_{name}"] = case(recs, g, False, 50)
+    # solve_two_rectangles_dependent: points p0..p3 = ids 0..7, p5..p7 = ids 8..13; the second rectangle hangs on p2
+    P = lambda k: [2 * k, 2 * k + 1]
+    p0, p1, p2, p3, p5, p6, p7 = P(0), P(1), P(2), P(3), P(4), P(5), P(6)
+    dep = [rec(9, [0], 1.0), rec(9, [1], 1.0), rec(7, p0 + p1), rec(7, p2 + p3), rec(6, p3 + p0), rec(6, p1 + p2),
+           rec(2, p0 + p1, 4.0), rec(2, p0 + p3, 3.0),
+           rec(7, p2 + p5), rec(7, p6 + p7), rec(6, p7 + p2), rec(6, p5 + p6), rec(2, p2 + p5, 4.0), rec(2, p2 + p7, 4.0)]
+    g_dep = [1.0, 1.0, 4.5, 1.5, 4.0, 3.5, 1.5, 3.0, 5.5, 3.5, 5.0, 4.5, 2.5, 4.0]
+    out["solve_two_rectangles_dependent"] = case(np.concatenate(dep), g_dep, False, 50)
+    for lines in (200, 600):
+        recs, n, g, _ = wl.system_from_text(wl.massive_problem_text(lines, False))
+        out[f"solve_massive_{lines}_lines"] = case(recs, g, False, 30)
+    recs, n, g, _ = wl.system_from_text(wl.massive_problem_text(200, False))
+    out["solve_massive_analysis_200_lines"] = case(recs, g, True, 3)
+    recs, n, g, _ = wl.system_from_text(wl.fixture_text("nonsquare"))
+    out["solve_nonsquare_analysis"] = case(recs, g, True, 50)
+    out["note"] = ("one sketch per call is launch-latency bound on a GPU (the batched call is the product's answer to many small "
+                   "sketches); the CPU port re-analyses the structure every call as the reference does, the GPU side hits its "
+                   "topology cache")
+    return out
+
+
 def freedom_report(ctx):
     """Freedom analysis (find_dof.rs:15-104) throughput: batched small sketches fused into the solve call, and the
     reference's own analysis bench sizes (solver_bench.rs:146-171: massive with analysis)."""
@@ -626,6 +706,7 @@ def run_gpu(args):
                                         "the like-for-like one"}
             if not args.no_extras:
                 line["freedom_analysis"] = freedom_report(ctx)
+                line["reference_benches"] = reference_benches(ctx)
             if not args.no_large and not args.no_extras:
                 line["large_system"] = large_system_report(ctx, peaks)
         if saved_stdout is not None:
