@@ -132,15 +132,19 @@ static inline void nonzeroes(const Rec& c, std::vector<uint32_t>& row0, std::vec
 }
 
 // constraints.rs:146-193 — resolve Undefined sides from values indexed BY ID.
-static inline void set_from_initial_values(Rec& c, const double* iv) {
+// constraints.rs:146-193.  `n_values` = length of the id-indexed table (max guessed id + 1, lib.rs:172-178).  The reference
+// indexes it unchecked and would PANIC on an id beyond it (which its own fuzz target forbids); such ids read 0.0 here and the
+// solve then fails with MissingGuess in validate_variables, as it does for every other kind.
+static inline void set_from_initial_values(Rec& c, const double* values, size_t n_values = (size_t)-1) {
+    auto iv = [&](uint32_t id) { return (size_t)id < n_values ? values[id] : 0.0; };
     if (c.kind == K_LTC && c.flags == SIDE_UNDEFINED) {
-        V p0{iv[c.ids[0]], iv[c.ids[1]]}, p1{iv[c.ids[2]], iv[c.ids[3]]}, ce{iv[c.ids[4]], iv[c.ids[5]]};
+        V p0{iv(c.ids[0]), iv(c.ids[1])}, p1{iv(c.ids[2]), iv(c.ids[3])}, ce{iv(c.ids[4]), iv(c.ids[5])};
         c.flags = (cross_2d(p1 - p0, ce - p0) >= 0.0) ? LINE_LEFT : LINE_RIGHT;
     } else if (c.kind == K_CTC && c.flags == SIDE_UNDEFINED) {
-        V a_c{iv[c.ids[0]], iv[c.ids[1]]};
-        double a_r = iv[c.ids[2]];
-        V b_c{iv[c.ids[3]], iv[c.ids[4]]};
-        double b_r = iv[c.ids[5]];
+        V a_c{iv(c.ids[0]), iv(c.ids[1])};
+        double a_r = iv(c.ids[2]);
+        V b_c{iv(c.ids[3]), iv(c.ids[4])};
+        double b_r = iv(c.ids[5]);
         double dist = magnitude(a_c - b_c);
         double r_int = std::fabs(std::fabs(a_r - b_r) - dist);
         double r_ext = std::fabs(a_r + b_r - dist);

@@ -697,16 +697,12 @@ static int32_t solve_priority(const Rec* cons_in, const uint32_t* prios, uint32_
     }
     uint32_t max_id = 0;
     for (uint32_t k = 0; k < n_vars; ++k) max_id = std::max(max_id, var_ids ? var_ids[k] : k);
-    // Values indexed by id.  Ids referenced by a constraint but missing from the guesses read 0.0 here and are
-    // rejected later by validate_variables; ids beyond max_id would panic in the reference (index out of
-    // bounds) — the oracle extends the table with zeros instead.
-    uint32_t table = max_id + 1;
-    for (uint32_t ci = 0; ci < n_cons; ++ci)
-        for (int k = 0; k < 8; ++k) table = std::max(table, cons_in[ci].ids[k] + 1);
-    std::vector<double> initial_values(table, 0.0);
+    // Values indexed by id (lib.rs:172-178).  Ids referenced by a constraint but missing from the guesses read 0.0 and are
+    // rejected later by validate_variables (set_from_initial_values checks the bound the reference does not).
+    std::vector<double> initial_values((size_t)max_id + 1, 0.0);
     for (uint32_t k = 0; k < n_vars; ++k) initial_values[var_ids ? var_ids[k] : k] = guesses[k];
     std::vector<Rec> cons(cons_in, cons_in + n_cons);
-    for (Rec& c : cons) set_from_initial_values(c, initial_values.data());
+    for (Rec& c : cons) set_from_initial_values(c, initial_values.data(), initial_values.size());
     std::vector<uint32_t> levels;
     for (uint32_t ci = 0; ci < n_cons; ++ci) levels.push_back(prios ? prios[ci] : 0u);
     std::sort(levels.begin(), levels.end());
