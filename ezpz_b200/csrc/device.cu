@@ -553,15 +553,8 @@ int32_t get_device_copy(ezpz_context* ctx, const ezpz_structure* cs, DeviceCopy*
     if (!d) return EZPZ_ERR_INVALID_ARGUMENT;
     d->device = ctx->device;
     EZ_CUDA(cudaSetDevice(ctx->device), "cudaSetDevice");
-    if (s->n_cons) {
-        EZ_CUDA(cudaMalloc(&d->cons, sizeof(DevCons) * s->n_cons), "cudaMalloc(cons)");
-        EZ_CUDA(cudaMemcpy(d->cons, s->dev_cons.data(), sizeof(DevCons) * s->n_cons, cudaMemcpyHostToDevice), "cudaMemcpy(cons)");
-    }
-    if (!s->csc_to_csr.empty()) {
-        EZ_CUDA(cudaMalloc(&d->csc_to_csr, sizeof(uint32_t) * s->csc_to_csr.size()), "cudaMalloc(perm)");
-        EZ_CUDA(cudaMemcpy(d->csc_to_csr, s->csc_to_csr.data(), sizeof(uint32_t) * s->csc_to_csr.size(), cudaMemcpyHostToDevice),
-                "cudaMemcpy(perm)");
-    }
+    // (the analysed constraints and the CSC -> CSR permutation are only read by ezpz_b200_eval: uploaded on its first call, so
+    // that the first SOLVE of a new topology does not pay for them)
     s->dev.push_back(d);
     *out = d;
     return EZPZ_OK;
@@ -1223,6 +1216,18 @@ int32_t ezpz_b200_eval(ezpz_context_t* ctx, const ezpz_structure_t* s, const dou
     DeviceCopy* dc = nullptr;
     int32_t rc = get_device_copy(ctx, s, &dc, detail);
     if (rc != EZPZ_OK) return rc;
+    {
+        std::lock_guard<std::mutex> lock(const_cast<ezpz_structure*>(s)->dev_mutex);
+        if (!dc->cons) {
+            EZ_CUDA(cudaMalloc(&dc->cons, sizeof(DevCons) * s->n_cons), "cudaMalloc(cons)");
+            EZ_CUDA(cudaMemcpy(dc->cons, s->dev_cons.data(), sizeof(DevCons) * s->n_cons, cudaMemcpyHostToDevice), "cudaMemcpy(cons)");
+        }
+        if (!dc->csc_to_csr && !s->csc_to_csr.empty()) {
+            EZ_CUDA(cudaMalloc(&dc->csc_to_csr, sizeof(uint32_t) * s->csc_to_csr.size()), "cudaMalloc(perm)");
+            EZ_CUDA(cudaMemcpy(dc->csc_to_csr, s->csc_to_csr.data(), sizeof(uint32_t) * s->csc_to_csr.size(), cudaMemcpyHostToDevice),
+                    "cudaMemcpy(perm)");
+        }
+    }
     const size_t n = s->n, m = s->m, nnz = s->csc_row_idx.size(), nc = s->n_cons;
     const size_t b_x = align_up(n * 8, 256), b_r = align_up(m * 8, 256), b_j = align_up(nnz * 8, 256), b_d = align_up(nc, 256);
     rc = ensure_ws(ctx, b_x + b_r + 2 * b_j + b_d, detail);

@@ -98,28 +98,38 @@ void build_a_pattern(ezpz_structure& S) {
 // Natural-order symbolic Cholesky: struct(L_j) = struct(A_j) U (struct(L_c) \ {c}) over the children c of
 // j in the elimination tree, parent(j) = min(struct(L_j) \ {j}).
 void build_l_pattern(ezpz_structure& S) {
+    // Column-merge symbolic Cholesky in natural order: pattern(L_j) = pattern(A_j) united with the patterns of j's children in
+    // the elimination tree (minus the children themselves).  Flat arrays throughout — children as linked lists, the union
+    // through a marker array, each column sorted in place: no allocation per column (two vectors per column cost ~0.2 ms of
+    // malloc on a 2,000-variable system, a third of its whole analysis).
     const uint32_t n = S.n;
-    std::vector<std::vector<uint32_t>> lcol(n);
-    std::vector<std::vector<uint32_t>> children(n);
-    std::vector<uint32_t> tmp;
-    for (uint32_t j = 0; j < n; ++j) {
-        std::vector<uint32_t>& cur = lcol[j];
-        cur.assign(S.a_row_idx.begin() + S.a_col_ptr[j], S.a_row_idx.begin() + S.a_col_ptr[j + 1]);
-        for (uint32_t c : children[j]) {
-            tmp.clear();
-            // merge cur with lcol[c] minus entries <= j... lcol[c] = {c, parent=j, ...}; skip c itself
-            const std::vector<uint32_t>& lc = lcol[c];
-            std::set_union(cur.begin(), cur.end(), lc.begin() + 1, lc.end(), std::back_inserter(tmp));
-            cur.swap(tmp);
-        }
-        // cur[0] == j always (diagonal present)
-        if (cur.size() > 1) children[cur[1]].push_back(j);
-    }
-    S.l_col_ptr.assign(n + 1, 0);
+    constexpr uint32_t kNone = UINT32_MAX;
+    std::vector<uint32_t> first_child(n, kNone), next_sibling(n, kNone), mark(n, kNone);
+    S.l_col_ptr.assign((size_t)n + 1, 0);
     S.l_row_idx.clear();
+    S.l_row_idx.reserve(S.a_row_idx.size() * 2);
     for (uint32_t j = 0; j < n; ++j) {
-        S.l_row_idx.insert(S.l_row_idx.end(), lcol[j].begin(), lcol[j].end());
+        const size_t start = S.l_row_idx.size();
+        for (uint32_t p = S.a_col_ptr[j]; p < S.a_col_ptr[j + 1]; ++p) {  // sorted, the diagonal first
+            mark[S.a_row_idx[p]] = j;
+            S.l_row_idx.push_back(S.a_row_idx[p]);
+        }
+        const size_t own = S.l_row_idx.size();
+        for (uint32_t c = first_child[j]; c != kNone; c = next_sibling[c])
+            for (uint32_t p = S.l_col_ptr[c] + 1; p < S.l_col_ptr[c + 1]; ++p) {  // (skip c itself; the rest is >= j)
+                const uint32_t row = S.l_row_idx[p];
+                if (mark[row] != j) {
+                    mark[row] = j;
+                    S.l_row_idx.push_back(row);
+                }
+            }
+        if (S.l_row_idx.size() > own) std::sort(S.l_row_idx.begin() + start, S.l_row_idx.end());
         S.l_col_ptr[j + 1] = (uint32_t)S.l_row_idx.size();
+        if (S.l_row_idx.size() - start > 1) {  // parent = the first row below the diagonal
+            const uint32_t parent = S.l_row_idx[start + 1];
+            next_sibling[j] = first_child[parent];
+            first_child[parent] = j;
+        }
     }
 }
 
