@@ -856,6 +856,8 @@ __device__ __noinline__ void sn_factor(const LargeArgs& a, uint32_t pos, uint32_
 constexpr uint32_t kSlicePanelCap = 10240;  // doubles of a slice's rows held in shared memory
 constexpr uint32_t kSliceChunk = 32;        // update records per round
 constexpr uint32_t kSliceMinRows = 48;      // panels with fewer rows below the diagonal block stay on one CTA
+// doubles between staged rows of an update block of width wK (even: rows of 16 stay 16-byte aligned for the 128-bit loads)
+__device__ __forceinline__ uint32_t slice_row_stride(uint32_t wK) { return (wK + 3u) & ~1u; }
 
 __device__ __noinline__ void sn_factor_slice(const LargeArgs& a, uint32_t pos, uint32_t slice, uint32_t n_slices, uint32_t epoch,
                                              double* stage, uint32_t stage_doubles) {
@@ -934,7 +936,7 @@ __device__ __noinline__ void sn_factor_slice(const LargeArgs& a, uint32_t pos, u
             for (; cnt < win_n; ++cnt) {
                 const uint32_t* r = srec + 8 * cnt;
                 const uint32_t wK = r[2] & 0xffu, nc = r[2] >> 8, own = meta[4 * cnt + 1] - meta[4 * cnt];
-                const uint32_t need_b = (nc + own) * wK + wK, need_r = nc + own;
+                const uint32_t need_b = (nc + own) * slice_row_stride(wK) + wK, need_r = nc + own;
                 const uint32_t inv_doubles = ((cnt + 1) * inv_len + 3u) / 4u;
                 if (tot_b + ((need_b + 1u) & ~1u) + ((inv_doubles + 1u) & ~1u) > kb_cap || tot_r + need_r > rel_cap || own >= 0xffffu) break;
                 meta[4 * cnt + 2] = tot_b;
@@ -990,9 +992,26 @@ __device__ __noinline__ void sn_factor_slice(const LargeArgs& a, uint32_t pos, u
             double* dst = kb + meta[4 * i + 2];
             uint32_t* rdst = srel + meta[4 * i + 3];
             const double* B = lv + r[0];
-            for (uint32_t q = wl; q < nc * wK; q += 32) cp_async8(dst + q, B + q);
-            for (uint32_t q = wl; q < own * wK; q += 32) cp_async8(dst + nc * wK + q, B + (size_t)lo * wK + q);
-            for (uint32_t q = wl; q < wK; q += 32) cp_async8(dst + (nc + own) * wK + q, y + r[4] + q);
+            // staged rows sit at a stride of wK + 2 doubles: at a stride of 16 the sixteen rows a warp reads for the sixteen
+            // columns of the panel all start in the same bank (16-way conflicts on every operand of the apply loop)
+            const uint32_t ws = slice_row_stride(wK);
+            for (uint32_t q = wl, t = wl / wK, k = wl - t * wK; q < nc * wK; q += 32) {
+                cp_async8(dst + t * ws + k, B + q);
+                k += 32;
+                while (k >= wK) {
+                    k -= wK;
+                    ++t;
+                }
+            }
+            for (uint32_t q = wl, t = wl / wK, k = wl - t * wK; q < own * wK; q += 32) {
+                cp_async8(dst + (nc + t) * ws + k, B + (size_t)lo * wK + q);
+                k += 32;
+                while (k >= wK) {
+                    k -= wK;
+                    ++t;
+                }
+            }
+            for (uint32_t q = wl; q < wK; q += 32) cp_async8(dst + (nc + own) * ws + q, y + r[4] + q);
             for (uint32_t q = wl; q < nc; q += 32) cp_async4(rdst + q, upd_rel + r[3] + q);
             for (uint32_t q = wl; q < own; q += 32) cp_async4(rdst + nc + q, upd_rel + r[3] + lo + q);
         }
@@ -1017,10 +1036,10 @@ __device__ __noinline__ void sn_factor_slice(const LargeArgs& a, uint32_t pos, u
                 const uint16_t* iv = inv + (size_t)i * inv_len;
                 const uint32_t tj = iv[rows + c], ti = diag ? iv[rows + lr] : iv[lr];
                 if (ti == 0xffffu || tj == 0xffffu) continue;
-                const uint32_t wK = srec[8 * i + 2] & 0xffu, nc = srec[8 * i + 2] >> 8;
+                const uint32_t wK = srec[8 * i + 2] & 0xffu, nc = srec[8 * i + 2] >> 8, ws = slice_row_stride(wK);
                 const double* Bc = kb + meta[4 * i + 2];
-                const double* bi = diag ? Bc + ti * wK : Bc + (nc + ti) * wK;
-                const double* bj = Bc + tj * wK;
+                const double* bi = diag ? Bc + ti * ws : Bc + (nc + ti) * ws;
+                const double* bj = Bc + tj * ws;
                 if (wK == 16) {
                     const double2* bi2 = reinterpret_cast<const double2*>(bi);
                     const double2* bj2 = reinterpret_cast<const double2*>(bj);
@@ -1050,10 +1069,10 @@ __device__ __noinline__ void sn_factor_slice(const LargeArgs& a, uint32_t pos, u
                 for (uint32_t i = 0; i < cnt; ++i) {
                     const uint32_t tj = inv[(size_t)i * inv_len + rows + c];
                     if (tj == 0xffffu) continue;
-                    const uint32_t wK = srec[8 * i + 2] & 0xffu, nc = srec[8 * i + 2] >> 8;
+                    const uint32_t wK = srec[8 * i + 2] & 0xffu, nc = srec[8 * i + 2] >> 8, ws = slice_row_stride(wK);
                     const double* Bc = kb + meta[4 * i + 2];
-                    const double* yK = Bc + nc * wK;  // (a diagonal slice stages no rows of its own)
-                    for (uint32_t k = 0; k < wK; ++k) acc = __fma_rn(-Bc[tj * wK + k], yK[k], acc);
+                    const double* yK = Bc + nc * ws;  // (a diagonal slice stages no rows of its own)
+                    for (uint32_t k = 0; k < wK; ++k) acc = __fma_rn(-Bc[tj * ws + k], yK[k], acc);
                     ys[c] = acc;
                 }
             }
