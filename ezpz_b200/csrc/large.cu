@@ -108,6 +108,7 @@ struct LargeArgs {
     size_t vg_stride, jr_stride, cgv_stride, sumsq_stride, side_stride, degen_stride, unsat_stride;
     uint32_t X0, R0, RN0, J0, L0, RV0, Y0, D0;
     uint32_t direct;
+    uint32_t pipe_asm;  // in-kernel assembly through the bulk-copy pipeline (assemble_phase_pipe)
     uint32_t* sn_flag;  // [n_sn] per supernode in stage order: the factorisation whose diagonal block is final (sn_factor_slice)
     uint32_t n_sn;
 };
@@ -295,6 +296,105 @@ constexpr uint32_t kTileBytesMax = kMaxRecWords * 128;    // 4352
 
 // NaN-ignoring max |v[i]| over the grid: per-block partial to partials[blockIdx.x]; caller syncs, then every
 // thread folds the partials (same order everywhere).
+// The assembly phase INSIDE the persistent LM kernel, pipelined like the stand-alone kernel below: every warp keeps two to
+// three record tiles in flight with cp.async.bulk + one mbarrier per stage (its slice of the CTA's dynamic shared memory, the
+// stage the factorisation teams use in their phases), its tile descriptors come through a 64-entry ring one block ahead, and
+// the variable gathers of tile k + 1 are issued before tile k is evaluated.  Out of line on purpose (its own register
+// allocation; the solver phases of the kernel are at the register cap).  Falls back to assemble_phase when a warp's slice does
+// not hold two tiles.
+template <bool RES, bool JAC>
+__device__ __noinline__ void assemble_phase_pipe(const LargeArgs& a, uint32_t rdst, uint32_t tid, uint32_t nth, bool write_jr,
+                                                 double* warp_stage, uint32_t warp_stage_bytes) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t gw = tid >> 5, nw = nth >> 5;
+    const uint32_t kStageBytes = a.tile_bytes_max;
+    constexpr uint32_t kTail = kAsmStagesMax * 8u + 64u * 8u;  // mbarriers + descriptor ring
+    const uint32_t kAsmStages = min(kAsmStagesMax, (warp_stage_bytes - kTail) / max(kStageBytes, 128u));
+    unsigned char* stage_base = reinterpret_cast<unsigned char*>(warp_stage);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(stage_base + warp_stage_bytes - kTail);
+    uint2* ring = reinterpret_cast<uint2*>(bars + kAsmStagesMax);
+    if (lane == 0) {
+        for (uint32_t st = 0; st < kAsmStages; ++st) mbar_init(&bars[st], 1);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncwarp();
+    const uint32_t count = gw < a.n_tiles ? (a.n_tiles - gw + nw - 1) / nw : 0u;
+    const TileDesc* const tiles = a.tiles;
+    const uint32_t* const recs = a.recs;
+    const uint8_t* const sides = a.side;
+    auto load_block = [&](uint32_t b) {
+        const uint32_t k = b * 32 + lane;
+        return k < count ? *reinterpret_cast<const uint2*>(&tiles[gw + k * nw]) : make_uint2(0u, 0u);
+    };
+    auto desc = [&](uint32_t k) {
+        const uint2 v = ring[k & 63u];
+        return TileDesc{v.x, v.y};
+    };
+    ring[lane] = load_block(0);
+    ring[32 + lane] = load_block(1);
+    uint2 pf = load_block(2);
+    __syncwarp();
+    auto issue = [&](uint32_t st, const TileDesc td) {  // lane 0: start the copy of a tile into stage st
+        const uint32_t bytes = (uint32_t)a.layout[td.meta & 0xffu].n_words * 128u;
+        mbar_expect_tx(&bars[st], bytes);
+        bulk_copy_g2s(stage_base + (size_t)st * kStageBytes, recs + (size_t)td.off16 * 4, bytes, &bars[st]);
+    };
+    if (lane == 0)
+        for (uint32_t k = 0; k < kAsmStages && k < count; ++k) issue(k, desc(k));
+    auto is_tangent = [](uint32_t kind) { return kind == EZPZ_K_LINE_TANGENT_TO_CIRCLE || kind == EZPZ_K_CIRCLE_TANGENT_TO_CIRCLE; };
+    double xv[8], xn[8];
+    uint32_t side = 0, side_n = 0;
+    TileDesc td = desc(0);
+    if (count) {
+        mbar_wait(&bars[0], 0);
+        if (lane < (td.meta >> 8)) {
+            gather_x(a, a.layout[td.meta & 0xffu], td.meta & 0xffu, reinterpret_cast<const uint32_t*>(stage_base) + lane, xv);
+            if (is_tangent(td.meta & 0xffu)) side = sides[gw * 32 + lane];
+        }
+    }
+    uint32_t st = 0, sn = kAsmStages > 1 ? 1u : 0u, par_n = kAsmStages > 1 ? 0u : 1u;
+    for (uint32_t k = 0, t = gw; k < count; ++k, t += nw) {
+        if ((k & 31u) == 0 && k) {
+            const uint32_t b = k >> 5;
+            ring[((b + 1) & 1u) * 32 + lane] = pf;
+            pf = load_block(b + 2);
+            __syncwarp();
+        }
+        const uint32_t kind = td.meta & 0xffu, n_valid = td.meta >> 8;
+        TileDesc tn{0, 0};
+        if (k + 1 < count) {
+            tn = desc(k + 1);
+            mbar_wait(&bars[sn], par_n);
+            if (lane < (tn.meta >> 8)) {
+                gather_x(a, a.layout[tn.meta & 0xffu], tn.meta & 0xffu,
+                         reinterpret_cast<const uint32_t*>(stage_base + (size_t)sn * kStageBytes) + lane, xn);
+                if (is_tangent(tn.meta & 0xffu)) side_n = sides[(t + nw) * 32 + lane];
+            }
+        }
+        if (lane < n_valid)
+            assemble_slot<RES, JAC>(a, a.layout[kind], kind, reinterpret_cast<const uint32_t*>(stage_base + (size_t)st * kStageBytes) + lane,
+                                    t * 32 + lane, rdst, write_jr, xv, side);
+        __syncwarp();
+        if (lane == 0 && k + kAsmStages < count) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            issue(st, desc(k + kAsmStages));
+        }
+        td = tn;
+        side = side_n;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) xv[q] = xn[q];
+        st = sn;
+        if (++sn == kAsmStages) {
+            sn = 0;
+            par_n ^= 1u;
+        }
+    }
+    __syncwarp();
+    if (lane == 0)  // the shared memory goes back to the factorisation teams: the barrier objects end here
+        for (uint32_t s2 = 0; s2 < kAsmStages; ++s2) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(&bars[s2])) : "memory");
+    __syncwarp();
+}
+
 __device__ void max_abs_partial(const double* v, uint32_t count, uint32_t tid, uint32_t nth, double* partial_out,
                                 double* sm) {
     double mx = __longlong_as_double(0x7ff8000000000000LL);  // NaN: identity of the NaN-ignoring max
@@ -1402,6 +1502,11 @@ __device__ __forceinline__ void lm_large_body(const LargeArgs& a) {
         t_mark = t;
     };
 
+    // pipelined assembly when a warp's slice of the dynamic shared memory holds at least two record tiles and every warp has a
+    // few tiles to stream (below that the set-up of the pipeline costs more than it hides: massive 2,000 variables, 8 CTAs, 35 ->
+    // 45 us; 1M-variable chain 842 -> 564 us over the 9 phases of a solve).  EZPZ_B200_PIPE_ASM=0 switches it off.
+    const bool pipe_asm = a.pipe_asm && a.n_tiles >= 4u * (nth >> 5) &&
+                          2u * a.tile_bytes_max + kAsmStagesMax * 8u + 512u <= kWarpStageDoubles * 8u;
     uint32_t fact_epoch = 0;  // factorisations so far in this launch: what a diagonal slice publishes (sn_factor_slice)
     // sides from the initial guesses (lib.rs:183-186), counters
     {
@@ -1421,7 +1526,8 @@ __device__ __forceinline__ void lm_large_body(const LargeArgs& a) {
         }
     }
     sync();
-    assemble_phase<true, true>(a, a.R0, tid, nth, use_cg);
+    if (pipe_asm) assemble_phase_pipe<true, true>(a, a.R0, tid, nth, use_cg, warp_stage, kWarpStageDoubles * 8u);
+    else assemble_phase<true, true>(a, a.R0, tid, nth, use_cg);
     sync();
     lap(0);
     // S = sum r^2 (see the header comment for the two summation orders)
@@ -1567,14 +1673,16 @@ __device__ __forceinline__ void lm_large_body(const LargeArgs& a) {
         for (uint32_t j = tid; j < a.n; j += nth) vg[a.X0 + j] += vg[a.D0 + j];
         sync();
         lap(1);
-        assemble_phase<true, false>(a, a.RN0, tid, nth, false);
+        if (pipe_asm) assemble_phase_pipe<true, false>(a, a.RN0, tid, nth, false, warp_stage, kWarpStageDoubles * 8u);
+        else assemble_phase<true, false>(a, a.RN0, tid, nth, false);
         sync();
         lap(0);
         const double S2 = sum_squares(vg + a.RN0, &ctrl->S2);
         lap(1);
         if (S2 < S) {
             for (uint32_t i = tid; i < a.m; i += nth) vg[a.R0 + i] = vg[a.RN0 + i];
-            assemble_phase<false, true>(a, a.R0, tid, nth, use_cg);
+            if (pipe_asm) assemble_phase_pipe<false, true>(a, a.R0, tid, nth, use_cg, warp_stage, kWarpStageDoubles * 8u);
+            else assemble_phase<false, true>(a, a.R0, tid, nth, use_cg);
             S = S2;
             lambda *= 0.1;
         } else {
@@ -2065,6 +2173,10 @@ void fill_args(LargeArgs& a, const ezpz_structure* s, const DeviceCopy* dc, cons
     a.D0 = P.D0;
     a.direct = P.direct ? 1u : 0u;
     a.sn_flag = L->sn_flag;
+    {
+        const char* e = std::getenv("EZPZ_B200_PIPE_ASM");
+        a.pipe_asm = e ? (e[0] != '0') : 1u;
+    }
     a.n_sn = (uint32_t)(P.stage_rec.size() / 8);
     // the summation order belongs to the structure, not to the launch shape: a system solved alone (cluster / grid) and
     // the same system solved as one CTA's problem in a batch fold S the same way
