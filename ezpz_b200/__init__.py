@@ -469,9 +469,18 @@ class Structure:
             raise EzpzError(rc, det)
         self.handle = h
         m, n, nj, na, nl, ncomp = C.c_uint32(), C.c_uint32(), C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint32()
-        L.ezpz_b200_structure_dims(h, C.byref(m), C.byref(n), C.byref(nj), C.byref(na), C.byref(nl), C.byref(ncomp))
-        self.m, self.n, self.nnz, self.nnz_a, self.nnz_l, self.n_components = (m.value, n.value, nj.value, na.value,
-                                                                               nl.value, ncomp.value)
+        L.ezpz_b200_structure_dims(h, C.byref(m), C.byref(n), C.byref(nj), C.byref(na), None, C.byref(ncomp))
+        self.m, self.n, self.nnz, self.nnz_a, self.n_components = m.value, n.value, nj.value, na.value, ncomp.value
+        self._nnz_l = None
+
+    @property
+    def nnz_l(self):
+        """nnz of the natural-order Cholesky factor (computed on first request for systems of the large path)."""
+        if self._nnz_l is None:
+            nl = C.c_uint64()
+            native.lib().ezpz_b200_structure_dims(self.handle, None, None, None, None, C.byref(nl), None)
+            self._nnz_l = nl.value
+        return self._nnz_l
 
     def __del__(self):
         try:
@@ -502,6 +511,10 @@ class Structure:
         return dict(a_col_ptr=self._arr(a, self.n + 1), a_row_idx=self._arr(b, self.nnz_a),
                     l_col_ptr=self._arr(c, self.n + 1), l_row_idx=self._arr(d, self.nnz_l))
 
+
+    def fingerprint(self):
+        """64-bit hash of everything the host analysis produced."""
+        return int(native.lib().ezpz_b200_structure_fingerprint(self.handle))
 
     def role_program(self, roles, stride=1):
         """The tables of the batched kernel for `roles` cooperating warps (structure.h: RoleBlob), parsed: per role its

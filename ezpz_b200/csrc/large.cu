@@ -1937,8 +1937,8 @@ struct DevicePlan {
     std::vector<unsigned char> stage;
     std::vector<Item> up, raw;
     size_t reserve_bytes = 0;
-    template <class T>
-    int32_t upload(T** dst, const std::vector<T>& src) {
+    template <class T, class A>
+    int32_t upload(T** dst, const std::vector<T, A>& src) {
         const size_t off = (stage.size() + 255) / 256 * 256, bytes = std::max<size_t>(sizeof(T), sizeof(T) * src.size());
         stage.resize(off + bytes);
         if (!src.empty()) std::memcpy(stage.data() + off, src.data(), sizeof(T) * src.size());

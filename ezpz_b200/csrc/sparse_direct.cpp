@@ -30,6 +30,7 @@
 #include <thread>
 #include <vector>
 
+#include "host_parallel.h"
 #include "structure.h"
 
 namespace ezs {
@@ -209,6 +210,62 @@ void nested_dissection(const Graph& g, uint32_t n, std::vector<uint32_t>& perm) 
     }
 }
 
+// The elimination tree cut into independent pieces for the host threads: owner[j] = the thread that owns column j's
+// subtree, or n_threads for the columns above the cut.  The largest subtree is split (its root goes above the cut, its
+// children become subtrees of their own) until there are several subtrees per thread and none holds more than a small share
+// of the columns; subtrees are dealt to the threads largest first, each to the least loaded thread.
+struct TreeTasks {
+    uint32_t n_threads = 1;
+    std::vector<uint8_t> owner;
+};
+
+TreeTasks cut_tree(const std::vector<uint32_t>& parent, uint32_t n_threads) {
+    const uint32_t n = (uint32_t)parent.size();
+    TreeTasks T;
+    T.n_threads = std::max(1u, std::min(n_threads, 64u));
+    if (T.n_threads == 1) {
+        T.owner.assign(n, 0);
+        return T;
+    }
+    std::vector<uint32_t> size(n, 1), child_head(n, kNone), child_next(n, kNone);
+    for (uint32_t j = 0; j < n; ++j)
+        if (parent[j] != kNone) {
+            size[parent[j]] += size[j];
+            child_next[j] = child_head[parent[j]];
+            child_head[parent[j]] = j;
+        }
+    std::vector<std::pair<uint32_t, uint32_t>> heap;  // (columns, root)
+    for (uint32_t j = 0; j < n; ++j)
+        if (parent[j] == kNone) heap.push_back({size[j], j});
+    std::make_heap(heap.begin(), heap.end());
+    constexpr uint8_t kUnset = 255;
+    T.owner.assign(n, kUnset);
+    const uint32_t target = 8 * T.n_threads, small = std::max(1024u, n / (8 * T.n_threads));
+    uint32_t splits = 0;
+    while (!heap.empty() && heap.front().first > small && (heap.size() < target || heap.front().first > n / T.n_threads) &&
+           splits < (1u << 16)) {
+        std::pop_heap(heap.begin(), heap.end());
+        const uint32_t r = heap.back().second;
+        heap.pop_back();
+        T.owner[r] = (uint8_t)T.n_threads;  // above the cut
+        ++splits;
+        for (uint32_t c = child_head[r]; c != kNone; c = child_next[c]) {
+            heap.push_back({size[c], c});
+            std::push_heap(heap.begin(), heap.end());
+        }
+    }
+    std::sort(heap.begin(), heap.end(), [](const auto& x, const auto& y) { return x.first != y.first ? x.first > y.first : x.second < y.second; });
+    std::vector<uint64_t> load(T.n_threads, 0);
+    for (const auto& task : heap) {
+        const uint32_t t = (uint32_t)(std::min_element(load.begin(), load.end()) - load.begin());
+        load[t] += task.first;
+        T.owner[task.second] = (uint8_t)t;
+    }
+    for (uint32_t j = n; j-- > 0;)  // parents first: a column below a subtree's root belongs to that root's thread
+        if (T.owner[j] == kUnset) T.owner[j] = T.owner[parent[j]];
+    return T;
+}
+
 }  // namespace
 
 // Fills the sparse-direct part of S.large.  Leaves P.direct false when the factor would be too large.
@@ -255,45 +312,103 @@ void build_sparse_direct(ezpz_structure& S) {
     lap("ordering");
     // ---- 3. symbolic factorisation, by columns -----------------------------------------------------
     // struct(L_j) = {i > j : A_perm(i, j) != 0}  U  (struct(L_c) \ {j}) over the etree children c of j.
-    std::vector<uint32_t> lc_ptr((size_t)n + 1, 0), lc_row;
-    std::vector<uint8_t> lc_in_a;
-    lc_row.reserve((size_t)g.adj.size() * 2);
-    lc_in_a.reserve((size_t)g.adj.size() * 2);
+    // A column needs its children only, so disjoint subtrees of the elimination tree are independent: the tree is cut below
+    // its top (TreeTasks), every host thread merges the columns of its subtrees in ascending order into a store of its own,
+    // the columns above the cut follow on the calling thread, and the stores are copied into column order at the end.
+    // An entry is kept as row * 2 + (A has it): one 32-bit sort key per entry.
+    uvec<uint32_t> lc_ptr((size_t)n + 1), lc_row;
+    uvec<uint8_t> lc_in_a;
+    if (n >= (1u << 31)) return;
     {
-        std::vector<uint32_t> child_head(n, kNone), child_next(n, kNone), mark(n, kNone);
-        std::vector<std::pair<uint32_t, uint8_t>> col;
-        for (uint32_t j = 0; j < n; ++j) {
-            col.clear();
-            mark[j] = j;
-            const uint32_t v = perm[j];
-            for (uint32_t p = g.ptr[v]; p < g.ptr[v + 1]; ++p) {
-                const uint32_t i = iperm[g.adj[p]];
-                if (i > j && mark[i] != j) {
-                    mark[i] = j;
-                    col.push_back({i, 1});
-                }
+        const TreeTasks tasks = cut_tree(parent, host_threads(n, kHostGrain));
+        const uint32_t nt = tasks.n_threads;
+        std::vector<uvec<uint32_t>> store(nt + 1);  // [nt] = the columns above the cut
+        uvec<size_t> col_off(n);                    // offset of column j in its owner's store
+        std::vector<uint32_t> child_head(n, kNone), child_next(n, kNone);
+        for (uint32_t j = n; j-- > 0;)  // (descending: every list ends up ascending)
+            if (parent[j] != kNone) {
+                child_next[j] = child_head[parent[j]];
+                child_head[parent[j]] = j;
             }
-            for (uint32_t c = child_head[j]; c != kNone; c = child_next[c])
-                for (uint32_t p = lc_ptr[c]; p < lc_ptr[c + 1]; ++p) {
-                    const uint32_t i = lc_row[p];
-                    if (mark[i] != j) {  // i == j is marked already
+        std::vector<uint8_t> too_large(nt + 1, 0);
+        auto run = [&](uint32_t t) {
+            uvec<uint32_t>& out = store[t];
+            std::vector<uint32_t> mark(n, kNone);
+            uvec<uint32_t> base, extra;
+            out.reserve(t == nt ? 1024 : (size_t)g.adj.size() * 2 / nt);
+            for (uint32_t j = 0; j < n; ++j) {
+                if (tasks.owner[j] != t) continue;
+                const size_t start = out.size();
+                col_off[j] = start;
+                mark[j] = j;
+                // The tallest child's column is sorted already: what it contributes stays in order (base), everything else
+                // (A's own entries, what the other children add) is collected, sorted and merged into it.
+                extra.clear();
+                const uint32_t v = perm[j];
+                for (uint32_t p = g.ptr[v]; p < g.ptr[v + 1]; ++p) {
+                    const uint32_t i = iperm[g.adj[p]];
+                    if (i > j && mark[i] != j) {
                         mark[i] = j;
-                        col.push_back({i, 0});
+                        extra.push_back(i * 2 + 1);
                     }
                 }
-            std::sort(col.begin(), col.end());
-            for (const auto& e : col) {
-                lc_row.push_back(e.first);
-                lc_in_a.push_back(e.second);
+                uint32_t tallest = kNone;
+                for (uint32_t c = child_head[j]; c != kNone; c = child_next[c])
+                    if (tallest == kNone || lc_ptr[c + 1] > lc_ptr[tallest + 1]) tallest = c;
+                base.clear();
+                auto take = [&](uint32_t c, uvec<uint32_t>& into) {
+                    const uvec<uint32_t>& from = store[tasks.owner[c]];  // this thread's own store below the cut
+                    const uint32_t* f = from.data() + col_off[c];
+                    for (uint32_t p = 0, e = lc_ptr[c + 1]; p < e; ++p) {
+                        const uint32_t i = f[p] >> 1;
+                        if (mark[i] != j) {  // i == j is marked already
+                            mark[i] = j;
+                            into.push_back(i * 2);
+                        }
+                    }
+                };
+                if (tallest != kNone) take(tallest, base);
+                for (uint32_t c = child_head[j]; c != kNone; c = child_next[c])
+                    if (c != tallest) take(c, extra);
+                std::sort(extra.begin(), extra.end());
+                out.resize(start + base.size() + extra.size());
+                std::merge(base.begin(), base.end(), extra.begin(), extra.end(), out.begin() + start);
+                lc_ptr[j + 1] = (uint32_t)(out.size() - start);  // (lengths; offsets after the prefix sum below)
+                if (out.size() > kMaxFactorEntries) {
+                    too_large[t] = 1;
+                    return;
+                }
             }
-            lc_ptr[j + 1] = (uint32_t)lc_row.size();
-            if (lc_row.size() > kMaxFactorEntries) return;
-            if (!col.empty()) {  // parent(j) = first sub-diagonal row
-                const uint32_t par = col.front().first;
-                child_next[j] = child_head[par];
-                child_head[par] = j;
-            }
+        };
+        if (nt <= 1) run(0);
+        else {
+            std::vector<std::thread> pool;
+            for (uint32_t t = 1; t < nt; ++t) pool.emplace_back(run, t);
+            run(0);
+            for (auto& th : pool) th.join();
         }
+        for (uint32_t t = 0; t < nt; ++t)
+            if (too_large[t]) return;
+        run(nt);
+        if (too_large[nt]) return;
+        lc_ptr[0] = 0;
+        uint64_t total = 0;
+        for (uint32_t j = 0; j < n; ++j) {
+            total += lc_ptr[j + 1];
+            if (total > kMaxFactorEntries) return;
+            lc_ptr[j + 1] = (uint32_t)total;
+        }
+        lc_row.resize(total);
+        lc_in_a.resize(total);
+        parallel_ranges(n, kHostGrain, [&](uint32_t jb, uint32_t je, uint32_t) {
+            for (uint32_t j = jb; j < je; ++j) {
+                const uint32_t* from = store[tasks.owner[j]].data() + col_off[j];
+                for (uint32_t q = lc_ptr[j], k = 0; q < lc_ptr[j + 1]; ++q, ++k) {
+                    lc_row[q] = from[k] >> 1;
+                    lc_in_a[q] = (uint8_t)(from[k] & 1u);
+                }
+            }
+        });
     }
     const size_t nnz_l_true = lc_row.size();
 

@@ -19,6 +19,7 @@
 #include <numeric>
 #include <thread>
 
+#include "host_parallel.h"
 #include "kinds.h"
 
 using namespace ezs;
@@ -33,25 +34,6 @@ void set_detail(ezpz_error_detail_t* d, const char* msg) {
 // lower(A) by columns from the patterns of J: column j holds every i >= j that shares a row with j (and j itself:
 // lambda*I puts every diagonal in).  For each column its rows are walked in CSC order and their CSR entries >= j
 // collected with a marker array; the short list is then sorted.
-// Runs fn(begin, end, part) over [0, n) cut into contiguous parts on host threads; one part (the caller's thread, no
-// thread is started) below `grain` items per part.  Host analysis of systems with 10^5..10^6 variables.
-template <class F>
-static void parallel_ranges(uint32_t n, uint32_t grain, F&& fn, uint32_t* parts_out = nullptr) {
-    uint32_t nt = std::max(1u, std::min({std::thread::hardware_concurrency(), 16u, n / std::max(1u, grain)}));
-    if (const char* e = std::getenv("EZPZ_B200_HOST_THREADS")) nt = std::max(1u, std::min(nt, (uint32_t)std::strtoul(e, nullptr, 10)));
-    if (parts_out) *parts_out = nt;
-    if (nt <= 1) {
-        fn(0u, n, 0u);
-        return;
-    }
-    std::vector<std::thread> th;
-    for (uint32_t t = 1; t < nt; ++t)
-        th.emplace_back([&, t] { fn((uint32_t)((uint64_t)n * t / nt), (uint32_t)((uint64_t)n * (t + 1) / nt), t); });
-    fn(0u, (uint32_t)((uint64_t)n / nt), 0u);
-    for (auto& x : th) x.join();
-}
-constexpr uint32_t kHostGrain = 1u << 15;  // items per host thread before a phase is worth splitting
-
 void build_a_pattern(ezpz_structure& S) {
     const uint32_t n = S.n;
     S.a_col_ptr.assign((size_t)n + 1, 0);
@@ -617,10 +599,29 @@ int32_t ezpz_b200_structure_create(const ezpz_constraint_t* cons, uint32_t n_con
     *out = nullptr;
     if (detail) std::memset(detail, 0, sizeof *detail);
     if (n_cons > 0 && !cons) return EZPZ_ERR_INVALID_ARGUMENT;
-    for (uint32_t c = 0; c < n_cons; ++c) {
-        if (cons[c].kind >= EZPZ_K_COUNT) {
+    // Every pass below runs over ranges of constraints (or columns) on host threads for large systems and inline on the
+    // caller's thread for small ones; a pass that can fail records the FIRST offender of its range and the lowest range wins,
+    // so errors are the ones a sequential walk reports.
+    struct FirstBad {
+        uint32_t c = UINT32_MAX, v = 0;
+    };
+    auto first_bad = [](const std::vector<FirstBad>& parts) {
+        for (const FirstBad& f : parts)
+            if (f.c != UINT32_MAX) return f;
+        return FirstBad();
+    };
+    {
+        std::vector<FirstBad> bad(16);
+        parallel_ranges(n_cons, kHostGrain, [&](uint32_t cb, uint32_t ce, uint32_t t) {
+            for (uint32_t c = cb; c < ce; ++c)
+                if (cons[c].kind >= EZPZ_K_COUNT) {
+                    bad[t].c = c;
+                    return;
+                }
+        });
+        if (const FirstBad f = first_bad(bad); f.c != UINT32_MAX) {
             set_detail(detail, "constraint kind out of range");
-            if (detail) detail->constraint_id = c;
+            if (detail) detail->constraint_id = f.c;
             return EZPZ_ERR_INVALID_ARGUMENT;
         }
     }
@@ -633,25 +634,32 @@ int32_t ezpz_b200_structure_create(const ezpz_constraint_t* cons, uint32_t n_con
             present.assign((size_t)mx + 1, 0);
             for (uint32_t k = 0; k < n_vars; ++k) present[var_ids[k]] = 1;
         }
-        for (uint32_t c = 0; c < n_cons; ++c) {
-            const ezk::KindInfo& ki = ezk::kKinds[cons[c].kind];
-            for (int row = 0; row < 2; ++row) {
-                for (int k = 0; k < ki.nz_len[row]; ++k) {
-                    const uint32_t v = cons[c].ids[ki.nz[row][k]];
-                    const bool found = var_ids ? (v < present.size() && present[v]) : (v < n_vars);
-                    if (!found) {
-                        if (detail) {
-                            detail->constraint_id = c;
-                            detail->variable = v;
-                            std::snprintf(detail->message, sizeof detail->message,
-                                          "Constraint %u references variable %u but no such variable appears in "
-                                          "your initial guesses.",
-                                          c, v);
+        std::vector<FirstBad> bad(16);
+        parallel_ranges(n_cons, kHostGrain, [&](uint32_t cb, uint32_t ce, uint32_t t) {
+            for (uint32_t c = cb; c < ce; ++c) {
+                const ezk::KindInfo& ki = ezk::kKinds[cons[c].kind];
+                for (int row = 0; row < 2; ++row)
+                    for (int k = 0; k < ki.nz_len[row]; ++k) {
+                        const uint32_t v = cons[c].ids[ki.nz[row][k]];
+                        const bool found = var_ids ? (v < present.size() && present[v]) : (v < n_vars);
+                        if (!found) {
+                            bad[t].c = c;
+                            bad[t].v = v;
+                            return;
                         }
-                        return EZPZ_ERR_MISSING_GUESS;
                     }
-                }
             }
+        });
+        if (const FirstBad f = first_bad(bad); f.c != UINT32_MAX) {
+            if (detail) {
+                detail->constraint_id = f.c;
+                detail->variable = f.v;
+                std::snprintf(detail->message, sizeof detail->message,
+                              "Constraint %u references variable %u but no such variable appears in "
+                              "your initial guesses.",
+                              f.c, f.v);
+            }
+            return EZPZ_ERR_MISSING_GUESS;
         }
     }
     ezpz_structure* S = new (std::nothrow) ezpz_structure();
@@ -665,79 +673,130 @@ int32_t ezpz_b200_structure_create(const ezpz_constraint_t* cons, uint32_t n_con
     };
     S->n_cons = n_cons;
     S->n = n_vars;
-    S->cons.assign(cons, cons + n_cons);
-    // 2. rows and pairs
-    S->cons_row0.assign(n_cons + 1, 0);
-    // Pairs (row, col) are generated row by row, so a STABLE counting sort by column leaves every column's rows
-    // ascending and duplicates (a variable named twice by one row) adjacent: sort + dedup in O(nnz), which is what
-    // faer's try_new_from_indices does with a comparison sort (solver.rs:255-256).
-    std::vector<uint32_t> pr, pc;  // row, col of every named (row, variable)
-    uint32_t row_num = 0;
-    for (uint32_t c = 0; c < n_cons; ++c) {
-        const ezk::KindInfo& ki = ezk::kKinds[cons[c].kind];
-        S->cons_row0[c] = row_num;
-        for (int row = 0; row < ki.rows; ++row) {
-            for (int k = 0; k < ki.nz_len[row]; ++k) {
-                const uint32_t v = cons[c].ids[ki.nz[row][k]];
-                if (v >= n_vars) {  // column index outside the matrix: faer's CreationError (solver.rs:256-260)
-                    set_detail(detail, "Could not create matrix: index out of bounds");
-                    delete S;
-                    return EZPZ_ERR_MATRIX;
-                }
-                pr.push_back(row_num);
-                pc.push_back(v);
-            }
-            ++row_num;
-        }
-    }
-    S->cons_row0[n_cons] = row_num;
-    S->m = row_num;
-    std::vector<uint64_t> pairs(pr.size());  // (col << 32) | row in CSC order
+    S->cons.resize(n_cons);
+    parallel_copy(S->cons.data(), cons, n_cons);
+    // 2. rows: first row of every constraint, and the side slots (constraints with an Undefined side in input order)
+    S->cons_row0.resize((size_t)n_cons + 1);
+    std::vector<uint32_t> side_slot;
+    S->n_side = 0;
     {
-        std::vector<uint32_t> start((size_t)n_vars + 1, 0);
-        for (uint32_t v : pc) start[v + 1]++;
-        for (uint32_t j = 0; j < n_vars; ++j) start[j + 1] += start[j];
-        for (size_t k = 0; k < pr.size(); ++k) pairs[start[pc[k]]++] = ((uint64_t)pc[k] << 32) | pr[k];
+        uint32_t row_num = 0;
+        for (uint32_t c = 0; c < n_cons; ++c) {
+            S->cons_row0[c] = row_num;
+            row_num += ezk::kKinds[cons[c].kind].rows;
+            if ((cons[c].kind == EZPZ_K_LINE_TANGENT_TO_CIRCLE || cons[c].kind == EZPZ_K_CIRCLE_TANGENT_TO_CIRCLE) &&
+                cons[c].flags == EZPZ_SIDE_UNDEFINED) {
+                if (side_slot.empty()) side_slot.assign(n_cons, UINT32_MAX);
+                side_slot[c] = S->n_side++;
+            }
+        }
+        S->cons_row0[n_cons] = row_num;
+        S->m = row_num;
     }
-    pairs.erase(std::unique(pairs.begin(), pairs.end()), pairs.end());
-    const size_t nnz = pairs.size();
-    S->csc_col_ptr.assign((size_t)n_vars + 1, 0);
+    // Pattern of J by columns: what faer's try_new_from_indices does with a comparison sort over all named (row, variable)
+    // pairs (solver.rs:255-256) is a bucket pass here — count the pairs of every column, scatter the rows into the columns'
+    // buckets, sort and deduplicate each (short) bucket, compact.  Counts and cursors are bumped with relaxed atomics so that
+    // ranges of constraints run on host threads; the bucket sort makes the result independent of the order of arrival.
+    const uint32_t m = S->m;
+    uvec<uint32_t> col_start((size_t)n_vars + 2);
+    parallel_fill(col_start.data(), col_start.size(), 0u);
+    {
+        std::vector<FirstBad> bad(16);
+        std::vector<uint8_t> weights_one(16, 1);
+        parallel_ranges(n_cons, kHostGrain, [&](uint32_t cb, uint32_t ce, uint32_t t) {
+            bool one = true;
+            for (uint32_t c = cb; c < ce; ++c) {
+                const ezk::KindInfo& ki = ezk::kKinds[cons[c].kind];
+                one = one && cons[c].weight == 1.0;
+                for (int row = 0; row < ki.rows; ++row)
+                    for (int k = 0; k < ki.nz_len[row]; ++k) {
+                        const uint32_t v = cons[c].ids[ki.nz[row][k]];
+                        if (v >= n_vars) {  // column index outside the matrix: faer's CreationError (solver.rs:256-260)
+                            if (bad[t].c == UINT32_MAX) bad[t].c = c;
+                            continue;
+                        }
+                        __atomic_fetch_add(&col_start[v + 2], 1u, __ATOMIC_RELAXED);
+                    }
+            }
+            weights_one[t] = one;
+        });
+        if (first_bad(bad).c != UINT32_MAX) {
+            set_detail(detail, "Could not create matrix: index out of bounds");
+            delete S;
+            return EZPZ_ERR_MATRIX;
+        }
+        S->all_weights_one = true;
+        for (uint8_t w : weights_one) S->all_weights_one = S->all_weights_one && w;
+    }
+    for (uint32_t j = 0; j < n_vars; ++j) col_start[j + 2] += col_start[j + 1];  // col_start[j + 1] = cursor of column j
+    const size_t n_pairs = col_start[(size_t)n_vars + 1];
+    uvec<uint32_t> bucket(n_pairs);
+    parallel_ranges(n_cons, kHostGrain, [&](uint32_t cb, uint32_t ce, uint32_t) {
+        for (uint32_t c = cb; c < ce; ++c) {
+            const ezk::KindInfo& ki = ezk::kKinds[cons[c].kind];
+            for (int row = 0; row < ki.rows; ++row)
+                for (int k = 0; k < ki.nz_len[row]; ++k)
+                    bucket[__atomic_fetch_add(&col_start[cons[c].ids[ki.nz[row][k]] + 1], 1u, __ATOMIC_RELAXED)] = S->cons_row0[c] + row;
+        }
+    });
+    // (the cursors have advanced by one column: col_start[j] .. col_start[j + 1] is column j's bucket now)
+    S->csc_col_ptr.resize((size_t)n_vars + 1);
+    S->csc_col_ptr[0] = 0;
+    parallel_ranges(n_vars, kHostGrain, [&](uint32_t jb, uint32_t je, uint32_t) {
+        for (uint32_t j = jb; j < je; ++j) {
+            uint32_t* b = bucket.data() + col_start[j];
+            uint32_t* e = bucket.data() + col_start[j + 1];
+            if (!std::is_sorted(b, e)) std::sort(b, e);
+            S->csc_col_ptr[j + 1] = (uint32_t)(std::unique(b, e) - b);
+        }
+    });
+    prefix_sum(S->csc_col_ptr);
+    const size_t nnz = S->csc_col_ptr[n_vars];
     S->csc_row_idx.resize(nnz);
-    S->csr_row_ptr.assign((size_t)S->m + 1, 0);
-    for (size_t k = 0; k < nnz; ++k) {
-        const uint32_t col = (uint32_t)(pairs[k] >> 32), row = (uint32_t)pairs[k];
-        S->csc_col_ptr[col + 1]++;
-        S->csr_row_ptr[row + 1]++;
-        S->csc_row_idx[k] = row;
-    }
-    for (uint32_t j = 0; j < n_vars; ++j) S->csc_col_ptr[j + 1] += S->csc_col_ptr[j];
-    for (uint32_t r = 0; r < S->m; ++r) S->csr_row_ptr[r + 1] += S->csr_row_ptr[r];
+    parallel_ranges(n_vars, kHostGrain, [&](uint32_t jb, uint32_t je, uint32_t) {
+        for (uint32_t j = jb; j < je; ++j)
+            std::copy(bucket.data() + col_start[j], bucket.data() + col_start[j] + (S->csc_col_ptr[j + 1] - S->csc_col_ptr[j]),
+                      S->csc_row_idx.data() + S->csc_col_ptr[j]);
+    });
+    // CSR = transpose: a row's columns are the distinct ids of its list, ascending; its entries find their CSC positions
+    // by a binary search in their (short) columns.
+    S->csr_row_ptr.resize((size_t)m + 1);
+    S->csr_row_ptr[0] = 0;
+    auto row_cols = [&](uint32_t c, int row, uint32_t* cols) {
+        const ezk::KindInfo& ki = ezk::kKinds[cons[c].kind];
+        const uint32_t len = ki.nz_len[row];
+        for (uint32_t k = 0; k < len; ++k) cols[k] = cons[c].ids[ki.nz[row][k]];
+        std::sort(cols, cols + len);
+        return (uint32_t)(std::unique(cols, cols + len) - cols);
+    };
+    parallel_ranges(n_cons, kHostGrain, [&](uint32_t cb, uint32_t ce, uint32_t) {
+        uint32_t cols[16];  // (8 used; std::sort's unrolled insertion pass is bounds-checked against 16 by gcc)
+        for (uint32_t c = cb; c < ce; ++c)
+            for (int row = 0; row < ezk::kKinds[cons[c].kind].rows; ++row) S->csr_row_ptr[S->cons_row0[c] + row + 1] = row_cols(c, row, cols);
+    });
+    prefix_sum(S->csr_row_ptr);
     S->csr_col_idx.resize(nnz);
     S->csr_to_csc.resize(nnz);
     S->csc_to_csr.resize(nnz);
-    {
-        std::vector<uint32_t> cursor(S->csr_row_ptr.begin(), S->csr_row_ptr.end() - 1);
-        for (size_t k = 0; k < nnz; ++k) {
-            const uint32_t col = (uint32_t)(pairs[k] >> 32), row = (uint32_t)pairs[k];
-            const uint32_t pos = cursor[row]++;
-            S->csr_col_idx[pos] = col;
-            S->csr_to_csc[pos] = (uint32_t)k;
-            S->csc_to_csr[k] = pos;
-        }
-    }
+    parallel_ranges(n_cons, kHostGrain, [&](uint32_t cb, uint32_t ce, uint32_t) {
+        uint32_t cols[16];  // (8 used; std::sort's unrolled insertion pass is bounds-checked against 16 by gcc)
+        for (uint32_t c = cb; c < ce; ++c)
+            for (int row = 0; row < ezk::kKinds[cons[c].kind].rows; ++row) {
+                const uint32_t r = S->cons_row0[c] + row, len = row_cols(c, row, cols);
+                uint32_t pos = S->csr_row_ptr[r];
+                for (uint32_t k = 0; k < len; ++k, ++pos) {
+                    const uint32_t* b = S->csc_row_idx.data() + S->csc_col_ptr[cols[k]];
+                    const uint32_t* e = S->csc_row_idx.data() + S->csc_col_ptr[cols[k] + 1];
+                    const uint32_t at = (uint32_t)(std::lower_bound(b, e, r) - S->csc_row_idx.data());
+                    S->csr_col_idx[pos] = cols[k];
+                    S->csr_to_csc[pos] = at;
+                    S->csc_to_csr[at] = pos;
+                }
+            }
+    });
     lap("pattern of J (sort, CSC, CSR)");
-    // 3. analysed constraints with scatter slots
+    // 3. analysed constraints with scatter slots: independent per constraint
     S->dev_cons.resize(n_cons);
-    S->n_side = 0;
-    S->all_weights_one = true;
-    for (uint32_t c = 0; c < n_cons; ++c) S->all_weights_one = S->all_weights_one && cons[c].weight == 1.0;
-    // side slots count the constraints with an Undefined side in input order (sequential); everything else per constraint
-    // is independent and runs on host threads for large systems
-    std::vector<uint32_t> side_slot(n_cons, UINT32_MAX);
-    for (uint32_t c = 0; c < n_cons; ++c)
-        if ((cons[c].kind == EZPZ_K_LINE_TANGENT_TO_CIRCLE || cons[c].kind == EZPZ_K_CIRCLE_TANGENT_TO_CIRCLE) &&
-            cons[c].flags == EZPZ_SIDE_UNDEFINED)
-            side_slot[c] = S->n_side++;
     parallel_ranges(n_cons, kHostGrain, [&](uint32_t cb, uint32_t ce, uint32_t) {
         for (uint32_t c = cb; c < ce; ++c) {
             const ezpz_constraint_t& src = cons[c];
@@ -750,7 +809,7 @@ int32_t ezpz_b200_structure_create(const ezpz_constraint_t* cons, uint32_t n_con
             dc.kind = src.kind;
             dc.flags = src.flags;
             dc.row0 = S->cons_row0[c];
-            dc.side_slot = side_slot[c];
+            dc.side_slot = side_slot.empty() ? UINT32_MAX : side_slot[c];
             std::memcpy(dc.ids, src.ids, sizeof dc.ids);
             for (int row = 0; row < ki.rows; ++row) {
                 const uint32_t r = dc.row0 + row;
@@ -773,16 +832,19 @@ int32_t ezpz_b200_structure_create(const ezpz_constraint_t* cons, uint32_t n_con
     lap("scatter slots");
     build_a_pattern(*S);
     lap("pattern of A");
-    // The symbolic factorisation is skipped for very large systems (they take the PCG path, large.cu).
+    // The natural-order symbolic factorisation feeds the tape of the batched kernel.  A system whose state cannot fit that
+    // kernel whatever the fill (W >= 3n + 2m + nnz(J) + nnz(A), build_small_program) takes the large path, which orders
+    // and factorises on its own (sparse_direct.cpp): its natural L pattern is computed only if somebody asks
+    // (ezpz_b200_structure_dims / _pattern_a; on a 20,000-variable lattice it cost a third of the analysis).
     S->have_l_pattern = n_vars <= kMaxSymbolicVars;
-    if (S->have_l_pattern) build_l_pattern(*S);
-    else {
-        S->l_col_ptr.assign((size_t)n_vars + 1, 0);
-        S->l_row_idx.clear();
+    const bool may_be_small = 3ull * n_vars + 2ull * S->m + nnz + std::max(S->a_row_idx.size(), nnz) + S->n_side + 1 <= kMaxSmallW;
+    if (S->have_l_pattern && may_be_small) {
+        build_l_pattern(*S);
+        S->l_pattern_built = true;
     }
     build_components(*S);
     lap("natural L pattern, components");
-    if (S->have_l_pattern) build_small_program(*S);
+    if (S->l_pattern_built) build_small_program(*S);
     if (!S->small.valid) build_large_program(*S);
     lap("programme");
     *out = S;
@@ -796,9 +858,23 @@ void ezpz_b200_structure_destroy(ezpz_structure_t* s) {
     delete s;
 }
 
+// The natural-order L pattern of a structure that did not need it at creation, on first request.
+static void ensure_l_pattern(const ezpz_structure_t* cs) {
+    ezpz_structure* s = const_cast<ezpz_structure*>(cs);
+    std::lock_guard<std::mutex> lock(s->dev_mutex);
+    if (s->l_pattern_built) return;
+    if (s->have_l_pattern) build_l_pattern(*s);
+    else {
+        s->l_col_ptr.assign((size_t)s->n + 1, 0);
+        s->l_row_idx.clear();
+    }
+    s->l_pattern_built = true;
+}
+
 int32_t ezpz_b200_structure_dims(const ezpz_structure_t* s, uint32_t* m, uint32_t* n, uint64_t* nnz_j,
                                  uint64_t* nnz_a, uint64_t* nnz_l, uint32_t* n_components) {
     if (!s) return EZPZ_ERR_INVALID_ARGUMENT;
+    if (nnz_l) ensure_l_pattern(s);
     if (m) *m = s->m;
     if (n) *n = s->n;
     if (nnz_j) *nnz_j = s->csc_row_idx.size();
@@ -823,6 +899,7 @@ int32_t ezpz_b200_structure_pattern_a(const ezpz_structure_t* s, const uint32_t*
                                       const uint32_t** a_row_idx, const uint32_t** l_col_ptr,
                                       const uint32_t** l_row_idx) {
     if (!s) return EZPZ_ERR_INVALID_ARGUMENT;
+    if (l_col_ptr || l_row_idx) ensure_l_pattern(s);
     if (a_col_ptr) *a_col_ptr = s->a_col_ptr.data();
     if (a_row_idx) *a_row_idx = s->a_row_idx.data();
     if (l_col_ptr) *l_col_ptr = s->l_col_ptr.data();
@@ -867,6 +944,45 @@ int32_t ezpz_b200_structure_rows(const ezpz_structure_t* s, const uint32_t** con
     if (!s || !cons_row0) return EZPZ_ERR_INVALID_ARGUMENT;
     *cons_row0 = s->cons_row0.data();
     return EZPZ_OK;
+}
+
+// Hash of everything the host analysis produced (patterns, scatter slots, tapes, the large programme): two structures with
+// the same fingerprint drive the device through the same arithmetic.  Used by the tests of the threaded analysis phases and
+// of ezpz_b200_structure_extend.
+uint64_t ezpz_b200_structure_fingerprint(const ezpz_structure_t* s) {
+    if (!s) return 0;
+    uint64_t h = 0x9e3779b97f4a7c15ull;
+    auto mix = [&](uint64_t v) {
+        h ^= v;
+        h *= 0xff51afd7ed558ccdull;
+        h ^= h >> 29;
+    };
+    auto vec = [&](const auto& v) {
+        mix(v.size());
+        for (uint32_t x : v) mix(x);
+    };
+    mix(s->n_cons), mix(s->n), mix(s->m), mix(s->n_side), mix(s->all_weights_one), mix(s->have_l_pattern);
+    vec(s->cons_row0), vec(s->csc_col_ptr), vec(s->csc_row_idx), vec(s->csr_row_ptr), vec(s->csr_col_idx);
+    vec(s->csr_to_csc), vec(s->csc_to_csr), vec(s->a_col_ptr), vec(s->a_row_idx);
+    if (s->l_pattern_built) vec(s->l_col_ptr), vec(s->l_row_idx);  // (computed on request for systems of the large path)
+    vec(s->comp_of), mix(s->n_components), mix(s->max_component);
+    mix(s->dev_cons.size());
+    for (const DevCons& dc : s->dev_cons) {
+        uint64_t w[sizeof(DevCons) / 8];
+        std::memcpy(w, &dc, sizeof dc);
+        for (uint64_t x : w) mix(x);
+    }
+    const SmallProgram& sp = s->small;
+    mix(sp.valid), mix(sp.W), mix(sp.X0), mix(sp.R0), mix(sp.RN0), mix(sp.J0), mix(sp.L0), mix(sp.D0), mix(sp.S0), mix(sp.F0);
+    mix(sp.n_side), mix(sp.n_ops), mix(sp.n_pairs), vec(sp.tape);
+    const LargeProgram& P = s->large;
+    mix(P.built), mix(P.direct), mix(P.nested), mix(P.X0), mix(P.R0), mix(P.RN0), mix(P.J0), mix(P.L0), mix(P.RV0), mix(P.Y0);
+    mix(P.D0), mix(P.VG), mix(P.n_levels), mix(P.nnz_l), mix(P.n_j);
+    vec(P.cons_order), vec(P.perm), vec(P.jt_of_csc), vec(P.sn_ptr), vec(P.sn_row_ptr), vec(P.sn_rows), vec(P.panel_off);
+    vec(P.upd_ptr), vec(P.upd_sn), vec(P.upd_rbegin), vec(P.upd_ncols), vec(P.upd_rel_ptr), vec(P.upd_rel), vec(P.upd_rec);
+    vec(P.stage_ptr), vec(P.stage_sn), vec(P.stage_rec), vec(P.aent_slot), vec(P.aprod_ptr), vec(P.aprod_a), vec(P.aprod_b);
+    vec(P.diag_slot);
+    return h;
 }
 
 void ezpz_b200_shard_range(uint64_t batch, uint32_t rank, uint32_t world, uint64_t* begin, uint64_t* end) {

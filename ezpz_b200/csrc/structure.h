@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "../../include/ezpz_b200.h"
+#include "host_parallel.h"
 
 struct ezpz_structure;
 
@@ -127,22 +128,24 @@ struct DeviceCopy;  // defined in device.h
 
 struct ezpz_structure {
     uint32_t n_cons = 0, n = 0, m = 0;
-    std::vector<ezpz_constraint_t> cons;
+    ezs::uvec<ezpz_constraint_t> cons;  // (uvec: filled by host threads, host_parallel.h)
     std::vector<uint32_t> cons_row0;  // n_cons + 1
     // J pattern, both orientations, and the permutations between their value orders
-    std::vector<uint32_t> csc_col_ptr, csc_row_idx, csr_row_ptr, csr_col_idx, csr_to_csc, csc_to_csr;
+    std::vector<uint32_t> csc_col_ptr, csr_row_ptr;
+    ezs::uvec<uint32_t> csc_row_idx, csr_col_idx, csr_to_csc, csc_to_csr;
     // lower(A) and L patterns, CSC with the diagonal first in every column
     std::vector<uint32_t> a_col_ptr, a_row_idx, l_col_ptr, l_row_idx;
     // connected components of the graph of A: comp_of[var]
     std::vector<uint32_t> comp_of;
     uint32_t n_components = 0;
     uint32_t max_component = 0;  // vars in the largest component
-    std::vector<ezs::DevCons> dev_cons;
+    ezs::uvec<ezs::DevCons> dev_cons;
     uint32_t n_side = 0;
     bool all_weights_one = true;
     ezs::SmallProgram small;
     ezs::LargeProgram large;
     bool have_l_pattern = false;  // false when the symbolic factorisation was skipped (very large systems)
+    bool l_pattern_built = false; // l_col_ptr / l_row_idx are filled (at creation when the batched kernel may run, else on request)
     // device copies, one per CUDA device ordinal, created lazily
     std::mutex dev_mutex;
     std::vector<ezs::DeviceCopy*> dev;

@@ -67,6 +67,7 @@ _SYMBOLS = [
     ("ezpz_b200_structure_pattern", C.c_int32, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)]),
     ("ezpz_b200_structure_pattern_a", C.c_int32, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)]),
     ("ezpz_b200_structure_rows", C.c_int32, [_P, C.POINTER(_P)]),
+    ("ezpz_b200_structure_fingerprint", C.c_uint64, [_P]),
     ("ezpz_b200_structure_batch_shape", C.c_int32, [_P, C.c_uint64, C.c_uint32, C.c_uint64, C.POINTER(C.c_uint32),
                                                     C.POINTER(C.c_uint32)]),
     ("ezpz_b200_structure_role_program", C.c_int32, [_P, C.c_uint32, C.c_uint32, _P, C.c_uint64, C.POINTER(C.c_uint64),

@@ -212,6 +212,10 @@ int32_t ezpz_b200_structure_batch_shape(const ezpz_structure_t* s, uint64_t batc
                                         uint64_t smem_per_block, uint32_t* roles, uint32_t* problems_per_cta);
 /* First row of each constraint in J (n_cons + 1 entries). */
 int32_t ezpz_b200_structure_rows(const ezpz_structure_t* s, const uint32_t** cons_row0);
+/* A 64-bit hash of everything the host analysis produced (patterns, scatter slots, operation tapes, elimination order,
+ * supernode schedule, product lists): structures with equal fingerprints drive the device through the same arithmetic.
+ * Tests hold the threaded analysis phases and ezpz_b200_structure_extend to it.  0 for NULL. */
+uint64_t ezpz_b200_structure_fingerprint(const ezpz_structure_t* s);
 
 /* ---------------------------------------------------------------------------------------------
  * Context: one CUDA device + stream + workspace pool.  One per thread that solves.

@@ -130,6 +130,7 @@ extern "C" {
     pub fn ezpz_b200_structure_batch_shape(s: *const EzpzStructure, batch: u64, sm_count: u32, smem_per_block: u64,
                                            roles: *mut u32, problems_per_cta: *mut u32) -> i32;
     pub fn ezpz_b200_structure_rows(s: *const EzpzStructure, cons_row0: *mut *const u32) -> i32;
+    pub fn ezpz_b200_structure_fingerprint(s: *const EzpzStructure) -> u64;
     // what faer's SymbolicLlt::try_new decides (solver.rs:289-300), reported
     pub fn ezpz_b200_structure_ordering(s: *const EzpzStructure, path: *mut i32, elim_order: *mut *const u32, nested: *mut i32,
                                         n_levels: *mut u32, nnz_l: *mut u64, sum_chunk: *mut u32) -> i32;
