@@ -62,6 +62,13 @@ inline void parallel_ranges(uint32_t n, uint32_t grain, F&& fn, uint32_t* parts_
     for (auto& x : th) x.join();
 }
 
+// counter[0]++ returning the old value: a relaxed atomic when several host threads share the counters, a plain increment on
+// the single-thread path of small systems (a locked instruction per pair is most of their pattern pass).
+inline uint32_t bump(uint32_t* counter, bool shared) {
+    if (shared) return __atomic_fetch_add(counter, 1u, __ATOMIC_RELAXED);
+    return (*counter)++;
+}
+
 // Exclusive prefix sum in place over counts stored at v[1..n] (v[0] = 0 on entry): v[i + 1] += v[i].
 template <class V>
 inline void prefix_sum(V& v) {

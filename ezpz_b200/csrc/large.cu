@@ -2067,7 +2067,7 @@ int32_t get_large(ezpz_context* ctx, const ezpz_structure* s, DeviceCopy* dc, La
     EZ_TRY(plan.upload(&L->csc_col_ptr, s->csc_col_ptr));
     EZ_TRY(plan.upload(&L->csc_row_idx, s->csc_row_idx));
     if (P.direct) {
-        const std::vector<uint32_t>* src[11] = {&P.perm, &P.sn_rows, &P.upd_rel, &P.upd_rec, &P.stage_ptr, &P.stage_rec, &P.aent_slot,
+        const ezs::uvec<uint32_t>* src[11] = {&P.perm, &P.sn_rows, &P.upd_rel, &P.upd_rec, &P.stage_ptr, &P.stage_rec, &P.aent_slot,
                                                 &P.aprod_ptr, &P.aprod_a, &P.aprod_b, &P.diag_slot};
         for (int k = 0; k < 11; ++k) EZ_TRY(plan.upload(&L->direct_tables[k], *src[k]));
         if (!P.jt_of_csc.empty()) EZ_TRY(plan.upload(&L->jmap, P.jt_of_csc));

@@ -46,32 +46,42 @@ constexpr uint32_t kWarpPanelCap = 576;         // doubles of panel a warp team 
 constexpr uint32_t kLanePanel = 8;              // panels of at most this many doubles are factorised by a single thread
 
 struct Graph {
-    std::vector<uint32_t> ptr, adj;  // symmetric adjacency without self loops
+    uvec<uint32_t> ptr, adj;  // symmetric adjacency without self loops
 };
 
 Graph build_graph(const ezpz_structure& S) {
+    // bucket pass over ranges of columns of lower(A) on host threads: count both ends of every off-diagonal entry, scatter,
+    // sort every (short) neighbour list
     const uint32_t n = S.n;
+    const bool shared = host_threads(n, kHostGrain) > 1;
     Graph g;
-    g.ptr.assign((size_t)n + 1, 0);
-    for (uint32_t j = 0; j < n; ++j)
-        for (uint32_t p = S.a_col_ptr[j]; p < S.a_col_ptr[j + 1]; ++p) {
-            const uint32_t i = S.a_row_idx[p];
-            if (i == j) continue;
-            g.ptr[i + 1]++;
-            g.ptr[j + 1]++;
-        }
-    for (uint32_t v = 0; v < n; ++v) g.ptr[v + 1] += g.ptr[v];
-    g.adj.resize(g.ptr[n]);
-    std::vector<uint32_t> cur(g.ptr.begin(), g.ptr.end() - 1);
-    for (uint32_t j = 0; j < n; ++j)
-        for (uint32_t p = S.a_col_ptr[j]; p < S.a_col_ptr[j + 1]; ++p) {
-            const uint32_t i = S.a_row_idx[p];
-            if (i == j) continue;
-            g.adj[cur[i]++] = j;
-            g.adj[cur[j]++] = i;
-        }
-    // ascending neighbour lists (columns are visited in ascending j, rows ascending inside a column)
-    for (uint32_t v = 0; v < n; ++v) std::sort(g.adj.begin() + g.ptr[v], g.adj.begin() + g.ptr[v + 1]);
+    g.ptr.resize((size_t)n + 2);
+    parallel_fill(g.ptr.data(), g.ptr.size(), 0u);
+    parallel_ranges(n, kHostGrain, [&](uint32_t jb, uint32_t je, uint32_t) {
+        for (uint32_t j = jb; j < je; ++j)
+            for (uint32_t p = S.a_col_ptr[j]; p < S.a_col_ptr[j + 1]; ++p) {
+                const uint32_t i = S.a_row_idx[p];
+                if (i == j) continue;
+                bump(&g.ptr[i + 2], shared);
+                bump(&g.ptr[j + 2], shared);
+            }
+    });
+    for (uint32_t v = 0; v < n; ++v) g.ptr[v + 2] += g.ptr[v + 1];  // g.ptr[v + 1] = cursor of v's list
+    g.adj.resize(g.ptr[(size_t)n + 1]);
+    parallel_ranges(n, kHostGrain, [&](uint32_t jb, uint32_t je, uint32_t) {
+        for (uint32_t j = jb; j < je; ++j)
+            for (uint32_t p = S.a_col_ptr[j]; p < S.a_col_ptr[j + 1]; ++p) {
+                const uint32_t i = S.a_row_idx[p];
+                if (i == j) continue;
+                g.adj[bump(&g.ptr[i + 1], shared)] = j;
+                g.adj[bump(&g.ptr[j + 1], shared)] = i;
+            }
+    });
+    g.ptr.pop_back();  // (the cursors have advanced by one vertex: ptr[v] .. ptr[v + 1] is v's list)
+    parallel_ranges(n, kHostGrain, [&](uint32_t vb, uint32_t ve, uint32_t) {
+        for (uint32_t v = vb; v < ve; ++v)
+            if (!std::is_sorted(g.adj.begin() + g.ptr[v], g.adj.begin() + g.ptr[v + 1])) std::sort(g.adj.begin() + g.ptr[v], g.adj.begin() + g.ptr[v + 1]);
+    });
     return g;
 }
 
@@ -281,7 +291,7 @@ void build_sparse_direct(ezpz_structure& S) {
         const char* dbg = std::getenv("EZPZ_B200_DEBUG");
         if (!(dbg && dbg[0] == '1')) return;
         const auto now = std::chrono::steady_clock::now();
-        std::fprintf(stderr, "[sparse_direct] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(now - last).count());
+        std::fprintf(stderr, "[sparse_direct] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - last).count());
         last = now;
     };
     const Graph g = build_graph(S);
@@ -291,15 +301,18 @@ void build_sparse_direct(ezpz_structure& S) {
     std::vector<uint32_t> perm(n), iperm(n), parent, level;
     std::iota(perm.begin(), perm.end(), 0u);
     std::iota(iperm.begin(), iperm.end(), 0u);
-    uint32_t n_levels = etree_levels(g, perm, iperm, parent, level);
+    uint32_t n_levels = 0;
     P.nested = false;
     const char* force_nd = std::getenv("EZPZ_B200_FORCE_ND");
-    if (n_levels > kNaturalMaxHeight || (force_nd && force_nd[0] == '1')) {
-        std::vector<uint32_t> nd, ind(n), nparent, nlevel;
+    const bool forced = force_nd && force_nd[0] == '1';
+    auto dissect = [&](std::vector<uint32_t>& nd, std::vector<uint32_t>& ind, std::vector<uint32_t>& nparent, std::vector<uint32_t>& nlevel) {
         nested_dissection(g, n, nd);
+        ind.resize(n);
         for (uint32_t j = 0; j < n; ++j) ind[nd[j]] = j;
-        const uint32_t h = etree_levels(g, nd, ind, nparent, nlevel);
-        if (h < n_levels || (force_nd && force_nd[0] == '1')) {
+        return etree_levels(g, nd, ind, nparent, nlevel);
+    };
+    auto adopt = [&](std::vector<uint32_t>& nd, std::vector<uint32_t>& ind, std::vector<uint32_t>& nparent, std::vector<uint32_t>& nlevel, uint32_t h) {
+        if (h < n_levels || forced) {
             perm.swap(nd);
             iperm.swap(ind);
             parent.swap(nparent);
@@ -307,6 +320,17 @@ void build_sparse_direct(ezpz_structure& S) {
             n_levels = h;
             P.nested = true;
         }
+    };
+    std::vector<uint32_t> nd, ind, nparent, nlevel;
+    if (host_threads(n, 2 * kHostGrain) > 1) {
+        // large systems: the natural-order tree (almost always too deep to keep) on a second thread while this one dissects
+        std::thread natural([&] { n_levels = etree_levels(g, perm, iperm, parent, level); });
+        const uint32_t h = dissect(nd, ind, nparent, nlevel);
+        natural.join();
+        if (n_levels > kNaturalMaxHeight || forced) adopt(nd, ind, nparent, nlevel, h);
+    } else {
+        n_levels = etree_levels(g, perm, iperm, parent, level);
+        if (n_levels > kNaturalMaxHeight || forced) adopt(nd, ind, nparent, nlevel, dissect(nd, ind, nparent, nlevel));
     }
 
     lap("ordering");
@@ -389,7 +413,7 @@ void build_sparse_direct(ezpz_structure& S) {
         }
         for (uint32_t t = 0; t < nt; ++t)
             if (too_large[t]) return;
-        run(nt);
+        if (nt > 1) run(nt);  // (a single thread owns every column)
         if (too_large[nt]) return;
         lc_ptr[0] = 0;
         uint64_t total = 0;
@@ -437,104 +461,164 @@ void build_sparse_direct(ezpz_structure& S) {
     std::vector<uint32_t> sn_of(n);
     for (uint32_t s = 0; s < n_sn; ++s)
         for (uint32_t j = P.sn_ptr[s]; j < P.sn_ptr[s + 1]; ++j) sn_of[j] = s;
-    // panel rows: own columns, then the sorted union of the columns' sub-diagonal rows outside the supernode
-    P.sn_row_ptr.assign((size_t)n_sn + 1, 0);
-    P.sn_rows.clear();
-    P.panel_off.assign((size_t)n_sn + 1, 0);
+    // panel rows: own columns, then the sorted union of the columns' sub-diagonal rows outside the supernode.  Supernodes
+    // are independent: ranges of them on host threads, each into a list of its own, copied into place afterwards.
+    P.sn_row_ptr.resize((size_t)n_sn + 1);
+    P.sn_row_ptr[0] = 0;
+    P.panel_off.resize((size_t)n_sn + 1);
     {
-        std::vector<uint32_t> mark(n, kNone), below;
-        uint64_t off = 0;
-        for (uint32_t s = 0; s < n_sn; ++s) {
-            const uint32_t j0 = P.sn_ptr[s], j1 = P.sn_ptr[s + 1];
-            below.clear();
-            for (uint32_t j = j0; j < j1; ++j)
-                for (uint32_t q = lc_ptr[j]; q < lc_ptr[j + 1]; ++q) {
-                    const uint32_t i = lc_row[q];
-                    if (i >= j1 && mark[i] != s) {
-                        mark[i] = s;
-                        below.push_back(i);
+        struct Part {
+            uvec<uint32_t> rows;
+            uint32_t s0 = 0;
+        };
+        std::vector<Part> parts(64);
+        uint32_t n_parts = 1;
+        parallel_ranges(n_sn, kHostGrain / 4, [&](uint32_t sb, uint32_t se, uint32_t t) {
+            Part& part = parts[t];
+            part.s0 = sb;
+            std::vector<uint32_t> mark(n, kNone);
+            uvec<uint32_t> below;
+            part.rows.reserve((size_t)(lc_ptr[P.sn_ptr[se]] - lc_ptr[P.sn_ptr[sb]]) / 2 + 1024);
+            for (uint32_t s = sb; s < se; ++s) {
+                const uint32_t j0 = P.sn_ptr[s], j1 = P.sn_ptr[s + 1];
+                below.clear();
+                for (uint32_t j = j0; j < j1; ++j)
+                    for (uint32_t q = lc_ptr[j]; q < lc_ptr[j + 1]; ++q) {
+                        const uint32_t i = lc_row[q];
+                        if (i >= j1 && mark[i] != s) {
+                            mark[i] = s;
+                            below.push_back(i);
+                        }
                     }
-                }
-            std::sort(below.begin(), below.end());
-            for (uint32_t j = j0; j < j1; ++j) P.sn_rows.push_back(j);
-            P.sn_rows.insert(P.sn_rows.end(), below.begin(), below.end());
-            P.sn_row_ptr[s + 1] = (uint32_t)P.sn_rows.size();
+                // (a one-column supernode's rows are its column: sorted already)
+                if (j1 - j0 > 1) std::sort(below.begin(), below.end());
+                for (uint32_t j = j0; j < j1; ++j) part.rows.push_back(j);
+                part.rows.insert(part.rows.end(), below.begin(), below.end());
+                P.sn_row_ptr[s + 1] = (j1 - j0) + (uint32_t)below.size();  // (heights; offsets after the prefix sum)
+            }
+        }, &n_parts);
+        uint64_t off = 0, rows_total = 0;
+        for (uint32_t s = 0; s < n_sn; ++s) {
+            const uint64_t h = P.sn_row_ptr[s + 1], w = P.sn_ptr[s + 1] - P.sn_ptr[s];
             P.panel_off[s] = (uint32_t)off;
-            off += (uint64_t)(j1 - j0) * (j1 - j0 + below.size());
-            if (off > kMaxFactorEntries) return;  // leave P.direct false: PCG path
+            off += w * h;
+            rows_total += h;
+            if (off > kMaxFactorEntries || rows_total > UINT32_MAX) return;  // leave P.direct false: PCG path
+            P.sn_row_ptr[s + 1] = (uint32_t)rows_total;
         }
         P.panel_off[n_sn] = (uint32_t)off;
+        P.sn_rows.resize(rows_total);
+        parallel_ranges(n_parts, 1, [&](uint32_t tb, uint32_t te, uint32_t) {
+            for (uint32_t t = tb; t < te; ++t)
+                std::copy(parts[t].rows.begin(), parts[t].rows.end(), P.sn_rows.begin() + P.sn_row_ptr[parts[t].s0]);
+        });
     }
     const uint32_t nnz_l = P.panel_off[n_sn];  // doubles of panel storage (explicit zeros included)
     auto panel_h = [&](uint32_t s) { return P.sn_row_ptr[s + 1] - P.sn_row_ptr[s]; };
     auto panel_w = [&](uint32_t s) { return P.sn_ptr[s + 1] - P.sn_ptr[s]; };
     bool inconsistent = false;  // a row that should be in a panel is not: never expected; falls back to the PCG path
-    auto pos_in = [&](uint32_t s, uint32_t row) {  // position of a global row in supernode s's row list
-        const uint32_t* b = P.sn_rows.data() + P.sn_row_ptr[s];
-        const uint32_t* e = P.sn_rows.data() + P.sn_row_ptr[s + 1];
-        const uint32_t* it = std::lower_bound(b + panel_w(s), e, row);  // only used for rows below the diagonal block
-        if (it == e || *it != row) {
-            inconsistent = true;
-            return 0u;
-        }
-        return (uint32_t)(it - b);
-    };
     lap("supernodes and panels");
     // ---- 5. update lists: which descendant supernodes K update supernode J, and where K's rows land in J ----
     // K's rows below its own columns, grouped by the supernode that owns them: every group is one (J <- K) update;
     // the rows of K from the group's start to the end of K's list all lie inside J's panel (elimination tree).
+    // Bucket pass on host threads (like the pattern of J): count the updates every J receives, scatter (K, first row, rows)
+    // into J's bucket, sort each bucket by K; the relative positions are then filled update by update, K's rows and J's
+    // rows walked together (both ascending).
     {
-        std::vector<std::vector<uint32_t>> upd(n_sn);  // per J: indices into the flat update arrays
-        std::vector<uint32_t> uK, uB, uC;
-        for (uint32_t K = 0; K < n_sn; ++K) {
+        auto groups_of = [&](uint32_t K, auto&& fn) {  // fn(J, first row of the group in K's list, rows in the group)
             const uint32_t rb = P.sn_row_ptr[K], w = panel_w(K), h = panel_h(K);
             uint32_t t = w;
             while (t < h) {
                 const uint32_t J = sn_of[P.sn_rows[rb + t]];
                 uint32_t t2 = t;
                 while (t2 < h && sn_of[P.sn_rows[rb + t2]] == J) ++t2;
-                upd[J].push_back((uint32_t)uK.size());
-                uK.push_back(K);
-                uB.push_back(t);
-                uC.push_back(t2 - t);
+                fn(J, t, t2 - t);
                 t = t2;
             }
-        }
-        P.upd_ptr.assign((size_t)n_sn + 1, 0);
-        P.upd_sn.clear();
-        P.upd_rbegin.clear();
-        P.upd_ncols.clear();
-        P.upd_rel_ptr.clear();
-        P.upd_rel.clear();
-        for (uint32_t J = 0; J < n_sn; ++J) {
-            const uint32_t j0 = P.sn_ptr[J];
-            for (uint32_t u : upd[J]) {  // ascending K by construction
-                const uint32_t K = uK[u], rb = P.sn_row_ptr[K], h = panel_h(K);
-                P.upd_sn.push_back(K);
-                P.upd_rbegin.push_back(uB[u]);
-                P.upd_ncols.push_back(uC[u]);
-                P.upd_rel_ptr.push_back((uint32_t)P.upd_rel.size());
-                for (uint32_t t = uB[u]; t < h; ++t) {
-                    const uint32_t row = P.sn_rows[rb + t];
-                    P.upd_rel.push_back(t < uB[u] + uC[u] ? row - j0 : pos_in(J, row));
+        };
+        const bool shared = host_threads(n_sn, kHostGrain / 4) > 1;
+        uvec<uint32_t> cursor((size_t)n_sn + 2);
+        parallel_fill(cursor.data(), cursor.size(), 0u);
+        parallel_ranges(n_sn, kHostGrain / 4, [&](uint32_t kb, uint32_t ke, uint32_t) {
+            for (uint32_t K = kb; K < ke; ++K)
+                groups_of(K, [&](uint32_t J, uint32_t, uint32_t) { bump(&cursor[J + 2], shared); });
+        });
+        for (uint32_t J = 0; J < n_sn; ++J) cursor[J + 2] += cursor[J + 1];  // cursor[J + 1] = start of J's bucket
+        const uint32_t n_upd = cursor[(size_t)n_sn + 1];
+        struct Upd {
+            uint32_t K, begin, ncols;
+        };
+        uvec<Upd> bucket(n_upd);
+        parallel_ranges(n_sn, kHostGrain / 4, [&](uint32_t kb, uint32_t ke, uint32_t) {
+            for (uint32_t K = kb; K < ke; ++K)
+                groups_of(K, [&](uint32_t J, uint32_t t, uint32_t cnt) {
+                    bucket[bump(&cursor[J + 1], shared)] = Upd{K, t, cnt};
+                });
+        });
+        // (the cursors have advanced by one supernode: cursor[J] .. cursor[J + 1] is J's bucket now)
+        P.upd_ptr.assign(cursor.begin(), cursor.begin() + n_sn + 1);
+        P.upd_sn.resize(n_upd);
+        P.upd_rbegin.resize(n_upd);
+        P.upd_ncols.resize(n_upd);
+        P.upd_rel_ptr.resize((size_t)n_upd + 1);
+        P.upd_rel_ptr[0] = 0;
+        parallel_ranges(n_sn, kHostGrain / 4, [&](uint32_t jb, uint32_t je, uint32_t) {
+            for (uint32_t J = jb; J < je; ++J) {
+                std::sort(bucket.begin() + P.upd_ptr[J], bucket.begin() + P.upd_ptr[J + 1],
+                          [](const Upd& x, const Upd& y) { return x.K < y.K; });  // a K updates a J at most once
+                for (uint32_t u = P.upd_ptr[J]; u < P.upd_ptr[J + 1]; ++u) {
+                    P.upd_sn[u] = bucket[u].K;
+                    P.upd_rbegin[u] = bucket[u].begin;
+                    P.upd_ncols[u] = bucket[u].ncols;
+                    P.upd_rel_ptr[u + 1] = panel_h(bucket[u].K) - bucket[u].begin;
                 }
             }
-            P.upd_ptr[J + 1] = (uint32_t)P.upd_sn.size();
+        });
+        {
+            uint64_t total = 0;
+            for (uint32_t u = 0; u < n_upd; ++u) {
+                total += P.upd_rel_ptr[u + 1];
+                if (total > UINT32_MAX) return;  // leave P.direct false: PCG path
+                P.upd_rel_ptr[u + 1] = (uint32_t)total;
+            }
         }
-        P.upd_rel_ptr.push_back((uint32_t)P.upd_rel.size());
+        P.upd_rel.resize(P.upd_rel_ptr[n_upd]);
         // where each update's block of K's panel lives: rows upd_rbegin.. to the end, all w_K columns, contiguous
         // one 32-byte record per update, what the device reads: {block start slot, T = rows in the block, w_K | ncols << 8,
         // offset of the relative positions, first column of K, 0, 0, 0}
-        P.upd_rec.assign(P.upd_sn.size() * 8, 0u);
-        for (size_t u = 0; u < P.upd_sn.size(); ++u) {
-            const uint32_t K = P.upd_sn[u];
-            uint32_t* r = P.upd_rec.data() + u * 8;
-            r[0] = P.panel_off[K] + P.upd_rbegin[u] * panel_w(K);
-            r[1] = panel_h(K) - P.upd_rbegin[u];
-            r[2] = panel_w(K) | (P.upd_ncols[u] << 8);
-            r[3] = P.upd_rel_ptr[u];
-            r[4] = P.sn_ptr[K];
-        }
+        P.upd_rec.resize((size_t)n_upd * 8);
+        std::vector<uint8_t> bad(64, 0);
+        parallel_ranges(n_sn, kHostGrain / 4, [&](uint32_t jb, uint32_t je, uint32_t part) {
+            for (uint32_t J = jb; J < je; ++J) {
+                const uint32_t j0 = P.sn_ptr[J], wJ = panel_w(J);
+                const uint32_t* jrow = P.sn_rows.data() + P.sn_row_ptr[J];
+                const uint32_t hJ = panel_h(J);
+                for (uint32_t u = P.upd_ptr[J]; u < P.upd_ptr[J + 1]; ++u) {
+                    const uint32_t K = P.upd_sn[u], rb = P.sn_row_ptr[K], h = panel_h(K), tb = P.upd_rbegin[u], nc = P.upd_ncols[u];
+                    uint32_t* rel = P.upd_rel.data() + P.upd_rel_ptr[u];
+                    uint32_t pp = wJ;  // position in J's row list, below the diagonal block
+                    for (uint32_t t = tb; t < h; ++t) {
+                        const uint32_t row = P.sn_rows[rb + t];
+                        if (t < tb + nc) rel[t - tb] = row - j0;
+                        else {
+                            while (pp < hJ && jrow[pp] < row) ++pp;
+                            if (pp >= hJ || jrow[pp] != row) {
+                                bad[part] = 1;
+                                rel[t - tb] = 0;
+                            } else rel[t - tb] = pp;
+                        }
+                    }
+                    uint32_t* r = P.upd_rec.data() + (size_t)u * 8;
+                    r[0] = P.panel_off[K] + tb * panel_w(K);
+                    r[1] = h - tb;
+                    r[2] = panel_w(K) | (nc << 8);
+                    r[3] = P.upd_rel_ptr[u];
+                    r[4] = P.sn_ptr[K];
+                    r[5] = r[6] = r[7] = 0;
+                }
+            }
+        });
+        for (uint8_t f : bad) inconsistent = inconsistent || f;
     }
     lap("update lists");
     // ---- 6. stages: height of every supernode in the supernode tree; small panels and large panels apart ----
@@ -597,19 +681,37 @@ void build_sparse_direct(ezpz_structure& S) {
     }
     lap("stages and records");
     // ---- 7. A = JtJ: products of every entry A has, addressed to its panel slot; diagonal slots ---------------
-    // Independent per column: column ranges are processed by a few threads into private lists that are then
-    // concatenated in column order.
+    // Independent per column, two passes over ranges of columns on host threads: the first finds every entry's panel slot
+    // and counts its products (the rows its two columns of J share), the second writes the products at their final places.
     {
         P.diag_slot.resize(n);
-        struct Part {
-            std::vector<uint32_t> slot, cnt, pa, pb;
-            bool bad = false;
+        uvec<uint32_t> ent_ptr((size_t)n + 1);
+        ent_ptr[0] = 0;
+        parallel_ranges(n, kHostGrain, [&](uint32_t c0, uint32_t c1, uint32_t) {
+            for (uint32_t j = c0; j < c1; ++j) {
+                uint32_t cnt = 0;
+                for (uint32_t q = lc_ptr[j]; q < lc_ptr[j + 1]; ++q) cnt += lc_in_a[q];
+                ent_ptr[j + 1] = cnt;
+            }
+        });
+        prefix_sum(ent_ptr);
+        const size_t n_ent = ent_ptr[n];
+        P.aent_slot.resize(n_ent);
+        P.aprod_ptr.resize(n_ent + 1);
+        P.aprod_ptr[0] = 0;
+        std::vector<uint8_t> bad(64, 0);
+        // shared rows of the columns ci and cj of J, ascending: fn(position in ci, position in cj)
+        auto shared_rows = [&](uint32_t ci, uint32_t cj, auto&& fn) {
+            uint32_t pi = S.csc_col_ptr[ci], pj = S.csc_col_ptr[cj];
+            const uint32_t pie = S.csc_col_ptr[ci + 1], pje = S.csc_col_ptr[cj + 1];
+            while (pi < pie && pj < pje) {
+                const uint32_t ri = S.csc_row_idx[pi], rj = S.csc_row_idx[pj];
+                if (ri == rj) fn(pi++, pj++);
+                else if (ri < rj) ++pi;
+                else ++pj;
+            }
         };
-        const uint32_t nt = n < (1u << 16) ? 1u : std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
-        std::vector<Part> parts(nt);
-        auto work = [&](uint32_t t) {
-            Part& part = parts[t];
-            const uint32_t c0 = (uint32_t)((uint64_t)n * t / nt), c1 = (uint32_t)((uint64_t)n * (t + 1) / nt);
+        parallel_ranges(n, kHostGrain, [&](uint32_t c0, uint32_t c1, uint32_t t) {
             for (uint32_t j = c0; j < c1; ++j) {
                 const uint32_t J = sn_of[j], j0 = P.sn_ptr[J], j1 = P.sn_ptr[J + 1], w = j1 - j0;
                 P.diag_slot[j] = P.panel_off[J] + (j - j0) * w + (j - j0);
@@ -617,65 +719,42 @@ void build_sparse_direct(ezpz_structure& S) {
                 // rows of the panel below the diagonal block, walked together with the column's (ascending) rows
                 const uint32_t* prow = P.sn_rows.data() + P.sn_row_ptr[J];
                 const uint32_t ph = P.sn_row_ptr[J + 1] - P.sn_row_ptr[J];
-                uint32_t pp = w;
+                uint32_t pp = w, e = ent_ptr[j];
                 for (uint32_t q = lc_ptr[j]; q < lc_ptr[j + 1]; ++q) {
                     if (!lc_in_a[q]) continue;
-                    const uint32_t i = lc_row[q], ci = perm[i];
-                    uint32_t pos;
+                    const uint32_t i = lc_row[q];
+                    uint32_t pos = 0, found = 0;
                     if (i < j1) pos = i - j0;
                     else {
                         while (pp < ph && prow[pp] < i) ++pp;
-                        if (pp >= ph || prow[pp] != i) {
-                            part.bad = true;
-                            continue;
-                        }
-                        pos = pp;
+                        if (pp >= ph || prow[pp] != i) bad[t] = 1;
+                        else pos = pp;
                     }
-                    uint32_t pi = S.csc_col_ptr[ci], pj = S.csc_col_ptr[cj], found = 0;
-                    const uint32_t pie = S.csc_col_ptr[ci + 1], pje = S.csc_col_ptr[cj + 1];
-                    while (pi < pie && pj < pje) {
-                        const uint32_t ri = S.csc_row_idx[pi], rj = S.csc_row_idx[pj];
-                        if (ri == rj) {
-                            part.pa.push_back(pi);
-                            part.pb.push_back(pj);
-                            ++found;
-                            ++pi;
-                            ++pj;
-                        } else if (ri < rj) ++pi;
-                        else ++pj;
-                    }
-                    part.slot.push_back(P.panel_off[J] + pos * w + (j - j0));
-                    part.cnt.push_back(found);
+                    shared_rows(perm[i], cj, [&](uint32_t, uint32_t) { ++found; });
+                    P.aent_slot[e] = P.panel_off[J] + pos * w + (j - j0);
+                    P.aprod_ptr[++e] = found;
                 }
             }
-        };
-        if (nt == 1) work(0);
-        else {
-            std::vector<std::thread> pool;
-            for (uint32_t t = 0; t < nt; ++t) pool.emplace_back(work, t);
-            for (auto& th : pool) th.join();
-        }
-        size_t n_ent = 0, n_prod = 0;
-        for (const Part& part : parts) {
-            n_ent += part.slot.size();
-            n_prod += part.pa.size();
-            inconsistent = inconsistent || part.bad;
-        }
-        P.aent_slot.clear();
-        P.aent_slot.reserve(n_ent);
-        P.aprod_ptr.assign(1, 0u);
-        P.aprod_ptr.reserve(n_ent + 1);
-        P.aprod_a.clear();
-        P.aprod_a.reserve(n_prod);
-        P.aprod_b.clear();
-        P.aprod_b.reserve(n_prod);
-        for (const Part& part : parts) {
-            P.aent_slot.insert(P.aent_slot.end(), part.slot.begin(), part.slot.end());
-            P.aprod_a.insert(P.aprod_a.end(), part.pa.begin(), part.pa.end());
-            P.aprod_b.insert(P.aprod_b.end(), part.pb.begin(), part.pb.end());
-            uint32_t run = P.aprod_ptr.back();
-            for (uint32_t c : part.cnt) P.aprod_ptr.push_back(run += c);
-        }
+        });
+        for (uint8_t f : bad) inconsistent = inconsistent || f;
+        prefix_sum(P.aprod_ptr);
+        const size_t n_prod = P.aprod_ptr[n_ent];
+        P.aprod_a.resize(n_prod);
+        P.aprod_b.resize(n_prod);
+        parallel_ranges(n, kHostGrain, [&](uint32_t c0, uint32_t c1, uint32_t) {
+            for (uint32_t j = c0; j < c1; ++j) {
+                const uint32_t cj = perm[j];
+                uint32_t e = ent_ptr[j];
+                for (uint32_t q = lc_ptr[j]; q < lc_ptr[j + 1]; ++q) {
+                    if (!lc_in_a[q]) continue;
+                    uint32_t at = P.aprod_ptr[e++];
+                    shared_rows(perm[lc_row[q]], cj, [&](uint32_t pi, uint32_t pj) {
+                        P.aprod_a[at] = pi;
+                        P.aprod_b[at++] = pj;
+                    });
+                }
+            }
+        });
     }
     lap("products of A");
     if (inconsistent) {
@@ -706,7 +785,7 @@ void build_sparse_direct(ezpz_structure& S) {
                          (double)sum_u / std::max<uint32_t>(1, P.stage_ptr[3 * st + 3] - P.stage_ptr[3 * st]), u4, u8, u16);
         }
     }
-    P.perm = perm;
+    P.perm.assign(perm.begin(), perm.end());
     P.n_levels = n_levels;
     P.nnz_l = nnz_l;
     P.direct = true;

@@ -40,7 +40,7 @@ void build_a_pattern(ezpz_structure& S) {
     S.a_row_idx.clear();
     // columns are independent: ranges of columns on host threads, each into its own list, concatenated in column order
     struct Part {
-        std::vector<uint32_t> rows;
+        uvec<uint32_t> rows;
         uint32_t c0 = 0, c1 = 0;
     };
     std::vector<Part> parts(16);
@@ -73,8 +73,10 @@ void build_a_pattern(ezpz_structure& S) {
     }, &n_parts);
     for (uint32_t j = 0; j < n; ++j) S.a_col_ptr[j + 1] += S.a_col_ptr[j];
     S.a_row_idx.resize(S.a_col_ptr[n]);
-    for (uint32_t t = 0; t < n_parts; ++t)
-        if (!parts[t].rows.empty()) std::copy(parts[t].rows.begin(), parts[t].rows.end(), S.a_row_idx.begin() + S.a_col_ptr[parts[t].c0]);
+    parallel_ranges(n_parts, 1, [&](uint32_t tb, uint32_t te, uint32_t) {
+        for (uint32_t t = tb; t < te; ++t)
+            if (!parts[t].rows.empty()) std::copy(parts[t].rows.begin(), parts[t].rows.end(), S.a_row_idx.begin() + S.a_col_ptr[parts[t].c0]);
+    });
 }
 
 // Natural-order symbolic Cholesky: struct(L_j) = struct(A_j) U (struct(L_c) \ {c}) over the children c of
@@ -517,22 +519,41 @@ void build_large_program(ezpz_structure& S) {
     // 1M-variable sketch: 595 MB of DRAM traffic for 231 MB algorithmic); plain input order keeps locality
     // but runs 6 of 32 lanes per instruction (every warp holds a dozen kinds).  Tiles give both.
     {
+        // (a stable counting sort by kind per tile; tiles are independent: sizes first, then every tile fills its own span)
         constexpr uint32_t kAssemblyTile = 4096;
-        P.cons_order.clear();
-        P.cons_order.reserve((size_t)S.n_cons + S.n_cons / 8 + 32 * EZPZ_K_COUNT);
-        std::vector<uint32_t> tile;
-        for (uint32_t t0 = 0; t0 < S.n_cons; t0 += kAssemblyTile) {
-            const uint32_t t1 = std::min(S.n_cons, t0 + kAssemblyTile);
-            tile.resize(t1 - t0);
-            std::iota(tile.begin(), tile.end(), t0);
-            std::stable_sort(tile.begin(), tile.end(), [&](uint32_t a, uint32_t b) { return S.cons[a].kind < S.cons[b].kind; });
-            for (size_t q = 0; q < tile.size(); ++q) {
-                if (q > 0 && S.cons[tile[q]].kind != S.cons[tile[q - 1]].kind)
-                    while (P.cons_order.size() % 32) P.cons_order.push_back(UINT32_MAX);
-                P.cons_order.push_back(tile[q]);
+        const uint32_t n_tiles = (S.n_cons + kAssemblyTile - 1) / kAssemblyTile;
+        uvec<uint32_t> tile_off((size_t)n_tiles + 1);
+        tile_off[0] = 0;
+        auto kind_counts = [&](uint32_t t, uint32_t* cnt) {
+            const uint32_t t0 = t * kAssemblyTile, t1 = std::min(S.n_cons, t0 + kAssemblyTile);
+            std::fill(cnt, cnt + EZPZ_K_COUNT, 0u);
+            for (uint32_t c = t0; c < t1; ++c) cnt[S.cons[c].kind]++;
+        };
+        parallel_ranges(n_tiles, 8, [&](uint32_t tb, uint32_t te, uint32_t) {
+            uint32_t cnt[EZPZ_K_COUNT];
+            for (uint32_t t = tb; t < te; ++t) {
+                kind_counts(t, cnt);
+                uint32_t size = 0;
+                for (uint32_t k = 0; k < EZPZ_K_COUNT; ++k) size += (cnt[k] + 31u) / 32u * 32u;
+                tile_off[t + 1] = size;
             }
-            while (P.cons_order.size() % 32) P.cons_order.push_back(UINT32_MAX);
-        }
+        });
+        prefix_sum(tile_off);
+        P.cons_order.resize(tile_off[n_tiles]);
+        parallel_ranges(n_tiles, 8, [&](uint32_t tb, uint32_t te, uint32_t) {
+            uint32_t cnt[EZPZ_K_COUNT], at[EZPZ_K_COUNT];
+            for (uint32_t t = tb; t < te; ++t) {
+                kind_counts(t, cnt);
+                uint32_t off = tile_off[t];
+                for (uint32_t k = 0; k < EZPZ_K_COUNT; ++k) {
+                    at[k] = off;
+                    off += (cnt[k] + 31u) / 32u * 32u;
+                    for (uint32_t q = at[k] + cnt[k]; q < off; ++q) P.cons_order[q] = UINT32_MAX;
+                }
+                const uint32_t t0 = t * kAssemblyTile, t1 = std::min(S.n_cons, t0 + kAssemblyTile);
+                for (uint32_t c = t0; c < t1; ++c) P.cons_order[at[S.cons[c].kind]++] = c;
+            }
+        });
     }
     build_sparse_direct(S);
     // Direct path: J in tile order.  Every record tile owns 32 x (partials the kind emits) consecutive doubles; partial q
@@ -542,27 +563,41 @@ void build_large_program(ezpz_structure& S) {
     P.jt_of_csc.clear();
     P.n_j = nnz_j;
     if (P.direct) {
-        P.jt_of_csc.assign(nnz_j, UINT32_MAX);
-        uint64_t base = 0;
-        for (size_t t = 0; t * 32 < P.cons_order.size(); ++t) {
-            const ezk::KindInfo& ki = ezk::kKinds[S.cons[P.cons_order[t * 32]].kind];  // a tile's first slot is never padding
-            for (uint32_t l = 0; l < 32; ++l) {
-                const uint32_t c = P.cons_order[t * 32 + l];
-                if (c == UINT32_MAX) continue;
-                const DevCons& dc = S.dev_cons[c];
-                for (int row = 0; row < ki.rows; ++row)
-                    for (int q = 0; q < ki.emit_len[row]; ++q)
-                        if (!(dc.slot[row][q] & kAccumulate))
-                            P.jt_of_csc[dc.slot[row][q]] = (uint32_t)(base + (uint64_t)((row ? ki.emit_len[0] : 0) + q) * 32 + l);
-            }
-            base += 32ull * (ki.emit_len[0] + ki.emit_len[1]);
+        P.jt_of_csc.resize(nnz_j);
+        parallel_fill(P.jt_of_csc.data(), (size_t)nnz_j, UINT32_MAX);
+        const uint32_t n_rec_tiles = (uint32_t)(P.cons_order.size() / 32);
+        uvec<uint64_t> tile_base((size_t)n_rec_tiles + 1);
+        tile_base[0] = 0;
+        for (uint32_t t = 0; t < n_rec_tiles; ++t) {  // a tile's first slot is never padding
+            const ezk::KindInfo& ki = ezk::kKinds[S.cons[P.cons_order[(size_t)t * 32]].kind];
+            tile_base[t + 1] = tile_base[t] + 32ull * (ki.emit_len[0] + ki.emit_len[1]);
         }
+        parallel_ranges(n_rec_tiles, kHostGrain / 32, [&](uint32_t tb, uint32_t te, uint32_t) {
+            for (uint32_t t = tb; t < te; ++t) {
+                const ezk::KindInfo& ki = ezk::kKinds[S.cons[P.cons_order[(size_t)t * 32]].kind];
+                for (uint32_t l = 0; l < 32; ++l) {
+                    const uint32_t c = P.cons_order[(size_t)t * 32 + l];
+                    if (c == UINT32_MAX) continue;
+                    const DevCons& dc = S.dev_cons[c];
+                    for (int row = 0; row < ki.rows; ++row)
+                        for (int q = 0; q < ki.emit_len[row]; ++q)
+                            if (!(dc.slot[row][q] & kAccumulate))
+                                P.jt_of_csc[dc.slot[row][q]] =
+                                    (uint32_t)(tile_base[t] + (uint64_t)((row ? ki.emit_len[0] : 0) + q) * 32 + l);
+                }
+            }
+        });
+        uint64_t base = tile_base[n_rec_tiles];
         for (uint32_t e = 0; e < nnz_j; ++e)  // pattern entries no partial ever writes stay zero: park them behind the tiles
             if (P.jt_of_csc[e] == UINT32_MAX) P.jt_of_csc[e] = (uint32_t)std::min<uint64_t>(base++, 0x7ffffffeull);
         if (base < 0x7fffffffull) {
             P.n_j = (uint32_t)base;
-            for (uint32_t& v : P.aprod_a) v = P.jt_of_csc[v];
-            for (uint32_t& v : P.aprod_b) v = P.jt_of_csc[v];
+            parallel_ranges((uint32_t)P.aprod_a.size(), 8 * kHostGrain, [&](uint32_t b, uint32_t e, uint32_t) {
+                for (uint32_t k = b; k < e; ++k) {
+                    P.aprod_a[k] = P.jt_of_csc[P.aprod_a[k]];
+                    P.aprod_b[k] = P.jt_of_csc[P.aprod_b[k]];
+                }
+            });
         } else {
             P.direct = false;  // positions must leave bit 31 free for the accumulate flag
             P.nnz_l = 0;
@@ -668,7 +703,7 @@ int32_t ezpz_b200_structure_create(const ezpz_constraint_t* cons, uint32_t n_con
         const char* dbg = std::getenv("EZPZ_B200_DEBUG");
         if (!(dbg && dbg[0] == '1')) return;
         const auto now = std::chrono::steady_clock::now();
-        std::fprintf(stderr, "[structure]     %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(now - last).count());
+        std::fprintf(stderr, "[structure]     %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - last).count());
         last = now;
     };
     S->n_cons = n_cons;
@@ -698,6 +733,7 @@ int32_t ezpz_b200_structure_create(const ezpz_constraint_t* cons, uint32_t n_con
     // buckets, sort and deduplicate each (short) bucket, compact.  Counts and cursors are bumped with relaxed atomics so that
     // ranges of constraints run on host threads; the bucket sort makes the result independent of the order of arrival.
     const uint32_t m = S->m;
+    const bool shared = host_threads(n_cons, kHostGrain) > 1;
     uvec<uint32_t> col_start((size_t)n_vars + 2);
     parallel_fill(col_start.data(), col_start.size(), 0u);
     {
@@ -715,7 +751,7 @@ int32_t ezpz_b200_structure_create(const ezpz_constraint_t* cons, uint32_t n_con
                             if (bad[t].c == UINT32_MAX) bad[t].c = c;
                             continue;
                         }
-                        __atomic_fetch_add(&col_start[v + 2], 1u, __ATOMIC_RELAXED);
+                        bump(&col_start[v + 2], shared);
                     }
             }
             weights_one[t] = one;
@@ -736,7 +772,7 @@ int32_t ezpz_b200_structure_create(const ezpz_constraint_t* cons, uint32_t n_con
             const ezk::KindInfo& ki = ezk::kKinds[cons[c].kind];
             for (int row = 0; row < ki.rows; ++row)
                 for (int k = 0; k < ki.nz_len[row]; ++k)
-                    bucket[__atomic_fetch_add(&col_start[cons[c].ids[ki.nz[row][k]] + 1], 1u, __ATOMIC_RELAXED)] = S->cons_row0[c] + row;
+                    bucket[bump(&col_start[cons[c].ids[ki.nz[row][k]] + 1], shared)] = S->cons_row0[c] + row;
         }
     });
     // (the cursors have advanced by one column: col_start[j] .. col_start[j + 1] is column j's bucket now)
@@ -765,12 +801,20 @@ int32_t ezpz_b200_structure_create(const ezpz_constraint_t* cons, uint32_t n_con
     auto row_cols = [&](uint32_t c, int row, uint32_t* cols) {
         const ezk::KindInfo& ki = ezk::kKinds[cons[c].kind];
         const uint32_t len = ki.nz_len[row];
-        for (uint32_t k = 0; k < len; ++k) cols[k] = cons[c].ids[ki.nz[row][k]];
-        std::sort(cols, cols + len);
-        return (uint32_t)(std::unique(cols, cols + len) - cols);
+        uint32_t out = 0;
+        for (uint32_t k = 0; k < len; ++k) {  // insertion sort with duplicates dropped (at most 8 ids)
+            const uint32_t v = cons[c].ids[ki.nz[row][k]];
+            uint32_t at = out;
+            while (at > 0 && cols[at - 1] > v) --at;
+            if (at > 0 && cols[at - 1] == v) continue;
+            for (uint32_t q = out; q > at; --q) cols[q] = cols[q - 1];
+            cols[at] = v;
+            ++out;
+        }
+        return out;
     };
     parallel_ranges(n_cons, kHostGrain, [&](uint32_t cb, uint32_t ce, uint32_t) {
-        uint32_t cols[16];  // (8 used; std::sort's unrolled insertion pass is bounds-checked against 16 by gcc)
+        uint32_t cols[8];
         for (uint32_t c = cb; c < ce; ++c)
             for (int row = 0; row < ezk::kKinds[cons[c].kind].rows; ++row) S->csr_row_ptr[S->cons_row0[c] + row + 1] = row_cols(c, row, cols);
     });
@@ -779,7 +823,7 @@ int32_t ezpz_b200_structure_create(const ezpz_constraint_t* cons, uint32_t n_con
     S->csr_to_csc.resize(nnz);
     S->csc_to_csr.resize(nnz);
     parallel_ranges(n_cons, kHostGrain, [&](uint32_t cb, uint32_t ce, uint32_t) {
-        uint32_t cols[16];  // (8 used; std::sort's unrolled insertion pass is bounds-checked against 16 by gcc)
+        uint32_t cols[8];
         for (uint32_t c = cb; c < ce; ++c)
             for (int row = 0; row < ezk::kKinds[cons[c].kind].rows; ++row) {
                 const uint32_t r = S->cons_row0[c] + row, len = row_cols(c, row, cols);

@@ -91,6 +91,7 @@ void build_role_blob(const ezpz_structure& S, uint32_t R, uint32_t stride, RoleB
 // SpMVs walk columns) and in TILE ORDER on the direct path (jt_of_csc): the partial q of lane l of record tile t lives at
 // jt_base(t) + q * 32 + l, so a warp's store of one partial is 256 contiguous bytes instead of 32 scattered sectors.
 struct LargeProgram {
+    using u32v = uvec<uint32_t>;  // (filled by host threads: no serial zero-fill, host_parallel.h)
     bool built = false;
     bool direct = false;          // sparse direct solve available (otherwise the PCG path runs)
     bool nested = false;          // perm is a nested-dissection order (false: natural order 0..n-1)
@@ -98,28 +99,28 @@ struct LargeProgram {
     uint64_t VG = 0;
     uint32_t n_levels = 0;        // stages = height of the supernode tree
     uint32_t nnz_l = 0;           // doubles of panel storage
-    std::vector<uint32_t> cons_order;                      // processing slots of the assembly phase -> constraint
+    u32v cons_order;                      // processing slots of the assembly phase -> constraint
                                                            // index (tile-local kind sort, UINT32_MAX = padding)
-    std::vector<uint32_t> perm;                            // elimination position -> variable
-    std::vector<uint32_t> jt_of_csc;                       // direct path: position in the J region of each CSC entry (empty = CSC order)
+    u32v perm;                            // elimination position -> variable
+    u32v jt_of_csc;                       // direct path: position in the J region of each CSC entry (empty = CSC order)
     uint32_t n_j = 0;                                      // doubles of the J region (nnz in CSC order; more in tile order: idle lanes)
     // Supernode s = columns [sn_ptr[s], sn_ptr[s+1]) (a chain of the elimination tree, <= 16 columns).  Its panel is
     // dense, row-major, h x w doubles at VG[L0 + panel_off[s]]: rows sn_rows[sn_row_ptr[s] ...) = the w own columns
     // (the diagonal block) followed by the sorted union of the columns' sub-diagonal rows.
-    std::vector<uint32_t> sn_ptr, sn_row_ptr, sn_rows, panel_off;
+    u32v sn_ptr, sn_row_ptr, sn_rows, panel_off;
     // Updates of supernode J by its descendants, ascending: upd_sn[u] = K, whose panel rows upd_rbegin[u].. (to the end
     // of K's row list) all lie in J's panel; the first upd_ncols[u] of them are columns of J.  upd_rel[upd_rel_ptr[u] + t]
     // = position in J's row list of K's row upd_rbegin[u] + t.
     // The block of K's panel an update reads (rows upd_rbegin[u] to the end, all of K's columns) is contiguous.
     // upd_rec = the 8-word record per update the device reads (sparse_direct.cpp).
-    std::vector<uint32_t> upd_ptr, upd_sn, upd_rbegin, upd_ncols, upd_rel_ptr, upd_rel, upd_rec;
+    u32v upd_ptr, upd_sn, upd_rbegin, upd_ncols, upd_rel_ptr, upd_rel, upd_rec;
     // Stage k (height in the supernode tree): stage_sn[stage_ptr[3k] .. stage_ptr[3k+1]) = panels of a few doubles (one
     // thread each), [3k+1 .. 3k+2) = panels that fit a warp's shared-memory stage, [3k+2 .. 3k+3) = larger ones (one CTA each).
     // stage_rec = the 8-word record per supernode in stage order that the device reads (sparse_direct.cpp).
-    std::vector<uint32_t> stage_ptr, stage_sn, stage_rec;
+    u32v stage_ptr, stage_sn, stage_rec;
     // A = JtJ: for every entry A has (strictly lower), its panel slot and the products J[r][i] * J[r][j] over shared
     // rows r ascending as pairs of positions in the CSC value array of J; diag_slot[j] = panel slot of A[j][j].
-    std::vector<uint32_t> aent_slot, aprod_ptr, aprod_a, aprod_b, diag_slot;
+    u32v aent_slot, aprod_ptr, aprod_a, aprod_b, diag_slot;
 };
 
 struct DeviceCopy;  // defined in device.h
@@ -134,7 +135,8 @@ struct ezpz_structure {
     std::vector<uint32_t> csc_col_ptr, csr_row_ptr;
     ezs::uvec<uint32_t> csc_row_idx, csr_col_idx, csr_to_csc, csc_to_csr;
     // lower(A) and L patterns, CSC with the diagonal first in every column
-    std::vector<uint32_t> a_col_ptr, a_row_idx, l_col_ptr, l_row_idx;
+    std::vector<uint32_t> a_col_ptr, l_col_ptr, l_row_idx;
+    ezs::uvec<uint32_t> a_row_idx;
     // connected components of the graph of A: comp_of[var]
     std::vector<uint32_t> comp_of;
     uint32_t n_components = 0;
