@@ -467,6 +467,10 @@ class Structure:
                                           C.byref(h), C.byref(det))
         if rc != 0:
             raise EzpzError(rc, det)
+        self._adopt(h)
+
+    def _adopt(self, h):
+        L = native.lib()
         self.handle = h
         m, n, nj, na, nl, ncomp = C.c_uint32(), C.c_uint32(), C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint32()
         L.ezpz_b200_structure_dims(h, C.byref(m), C.byref(n), C.byref(nj), C.byref(na), None, C.byref(ncomp))
@@ -511,6 +515,23 @@ class Structure:
         return dict(a_col_ptr=self._arr(a, self.n + 1), a_row_idx=self._arr(b, self.nnz_a),
                     l_col_ptr=self._arr(c, self.n + 1), l_row_idx=self._arr(d, self.nnz_l))
 
+
+    def extend(self, extra):
+        """The structure of this one's constraints followed by `extra` (ezpz_b200_structure_extend): a large-path system keeps
+        this structure's elimination order."""
+        if not isinstance(extra, np.ndarray):
+            extra = records(extra)
+        extra = np.ascontiguousarray(extra)
+        h = C.c_void_p()
+        det = native.ErrorDetail()
+        rc = native.lib().ezpz_b200_structure_extend(self.handle, native.ptr(extra), len(extra), C.byref(h), C.byref(det))
+        if rc != 0:
+            raise EzpzError(rc, det)
+        st = Structure.__new__(Structure)
+        st.recs = np.concatenate([self.recs, extra])
+        st.n_cons, st.n_vars = len(st.recs), self.n_vars
+        st._adopt(h)
+        return st
 
     def fingerprint(self):
         """64-bit hash of everything the host analysis produced."""

@@ -38,11 +38,9 @@ using uvec = std::vector<T, default_init_allocator<T>>;
 constexpr uint32_t kHostGrain = 1u << 15;  // items per host thread before a phase is worth splitting
 
 inline uint32_t host_threads(uint32_t n, uint32_t grain) {
-    static const uint32_t cap = [] {
-        uint32_t c = std::max(1u, std::min(std::thread::hardware_concurrency(), 16u));
-        if (const char* e = std::getenv("EZPZ_B200_HOST_THREADS")) c = std::max(1u, std::min(c, (uint32_t)std::strtoul(e, nullptr, 10)));
-        return c;
-    }();
+    static const uint32_t cores = std::max(1u, std::min(std::thread::hardware_concurrency(), 16u));
+    uint32_t cap = cores;  // EZPZ_B200_HOST_THREADS lowers it (read per call: tests compare 1 thread against many)
+    if (const char* e = std::getenv("EZPZ_B200_HOST_THREADS")) cap = std::max(1u, std::min(cap, (uint32_t)std::strtoul(e, nullptr, 10)));
     return std::max(1u, std::min(cap, n / std::max(1u, grain)));
 }
 

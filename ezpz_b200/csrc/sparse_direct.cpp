@@ -279,7 +279,7 @@ TreeTasks cut_tree(const std::vector<uint32_t>& parent, uint32_t n_threads) {
 }  // namespace
 
 // Fills the sparse-direct part of S.large.  Leaves P.direct false when the factor would be too large.
-void build_sparse_direct(ezpz_structure& S) {
+void build_sparse_direct(ezpz_structure& S, const uint32_t* order_hint, bool hint_nested) {
     LargeProgram& P = S.large;
     const uint32_t n = S.n;
     P.direct = false;
@@ -322,7 +322,15 @@ void build_sparse_direct(ezpz_structure& S) {
         }
     };
     std::vector<uint32_t> nd, ind, nparent, nlevel;
-    if (host_threads(n, 2 * kHostGrain) > 1) {
+    if (order_hint) {
+        // an order to keep (constraints were added to an analysed structure: new entries of A, the same variables; any order
+        // of the variables is a valid elimination order and the dissection of the old graph still separates the new one as
+        // long as the additions are local)
+        perm.assign(order_hint, order_hint + n);
+        for (uint32_t j = 0; j < n; ++j) iperm[perm[j]] = j;
+        n_levels = etree_levels(g, perm, iperm, parent, level);
+        P.nested = hint_nested;
+    } else if (host_threads(n, 2 * kHostGrain) > 1) {
         // large systems: the natural-order tree (almost always too deep to keep) on a second thread while this one dissects
         std::thread natural([&] { n_levels = etree_levels(g, perm, iperm, parent, level); });
         const uint32_t h = dissect(nd, ind, nparent, nlevel);

@@ -508,7 +508,7 @@ namespace {
 
 // Programme of the single-large-system path: assembly processing order, value-array layout, and the sparse
 // direct schedule (sparse_direct.cpp).
-void build_large_program(ezpz_structure& S) {
+void build_large_program(ezpz_structure& S, const uint32_t* order_hint = nullptr, bool hint_nested = false) {
     LargeProgram& P = S.large;
     P = LargeProgram();
     const uint32_t n = S.n, m = S.m;
@@ -555,7 +555,7 @@ void build_large_program(ezpz_structure& S) {
             }
         });
     }
-    build_sparse_direct(S);
+    build_sparse_direct(S, order_hint, hint_nested);
     // Direct path: J in tile order.  Every record tile owns 32 x (partials the kind emits) consecutive doubles; partial q
     // of the constraint in lane l sits at base + q * 32 + l.  A partial that accumulates into an entry the same constraint
     // already wrote (bit 31 of its slot) shares that entry's position.  Consumers that think in CSC positions (the product
@@ -626,10 +626,11 @@ void build_large_program(ezpz_structure& S) {
 
 }  // namespace
 
-extern "C" {
-
-int32_t ezpz_b200_structure_create(const ezpz_constraint_t* cons, uint32_t n_cons, const uint32_t* var_ids,
-                                   uint32_t n_vars, ezpz_structure_t** out, ezpz_error_detail_t* detail) {
+// The analysis behind ezpz_b200_structure_create and ezpz_b200_structure_extend.  The ids of the guesses come as a list
+// (`var_ids`, create) or as the membership table of an analysed structure (`present`, extend); both null = ids 0..n_vars-1.
+static int32_t analyse(const ezpz_constraint_t* cons, uint32_t n_cons, const uint32_t* var_ids, const std::vector<uint8_t>* present_in,
+                       uint32_t n_vars, const uint32_t* order_hint, bool hint_nested, ezpz_structure_t** out,
+                       ezpz_error_detail_t* detail) {
     if (!out) return EZPZ_ERR_INVALID_ARGUMENT;
     *out = nullptr;
     if (detail) std::memset(detail, 0, sizeof *detail);
@@ -661,14 +662,15 @@ int32_t ezpz_b200_structure_create(const ezpz_constraint_t* cons, uint32_t n_con
         }
     }
     // 1. validate_variables: every id named by a row list must be among the guess ids.
+    std::vector<uint8_t> present;
     {
-        std::vector<uint8_t> present;
         if (var_ids) {
             uint32_t mx = 0;
             for (uint32_t k = 0; k < n_vars; ++k) mx = std::max(mx, var_ids[k]);
             present.assign((size_t)mx + 1, 0);
             for (uint32_t k = 0; k < n_vars; ++k) present[var_ids[k]] = 1;
-        }
+        } else if (present_in) present = *present_in;
+        const bool listed = !present.empty() || var_ids;
         std::vector<FirstBad> bad(16);
         parallel_ranges(n_cons, kHostGrain, [&](uint32_t cb, uint32_t ce, uint32_t t) {
             for (uint32_t c = cb; c < ce; ++c) {
@@ -676,7 +678,7 @@ int32_t ezpz_b200_structure_create(const ezpz_constraint_t* cons, uint32_t n_con
                 for (int row = 0; row < 2; ++row)
                     for (int k = 0; k < ki.nz_len[row]; ++k) {
                         const uint32_t v = cons[c].ids[ki.nz[row][k]];
-                        const bool found = var_ids ? (v < present.size() && present[v]) : (v < n_vars);
+                        const bool found = listed ? (v < present.size() && present[v]) : (v < n_vars);
                         if (!found) {
                             bad[t].c = c;
                             bad[t].v = v;
@@ -708,6 +710,7 @@ int32_t ezpz_b200_structure_create(const ezpz_constraint_t* cons, uint32_t n_con
     };
     S->n_cons = n_cons;
     S->n = n_vars;
+    S->var_present.swap(present);
     S->cons.resize(n_cons);
     parallel_copy(S->cons.data(), cons, n_cons);
     // 2. rows: first row of every constraint, and the side slots (constraints with an Undefined side in input order)
@@ -889,10 +892,31 @@ int32_t ezpz_b200_structure_create(const ezpz_constraint_t* cons, uint32_t n_con
     build_components(*S);
     lap("natural L pattern, components");
     if (S->l_pattern_built) build_small_program(*S);
-    if (!S->small.valid) build_large_program(*S);
+    if (!S->small.valid) build_large_program(*S, order_hint, hint_nested);
     lap("programme");
     *out = S;
     return EZPZ_OK;
+}
+
+extern "C" {
+
+int32_t ezpz_b200_structure_create(const ezpz_constraint_t* cons, uint32_t n_cons, const uint32_t* var_ids,
+                                   uint32_t n_vars, ezpz_structure_t** out, ezpz_error_detail_t* detail) {
+    return analyse(cons, n_cons, var_ids, nullptr, n_vars, nullptr, false, out, detail);
+}
+
+int32_t ezpz_b200_structure_extend(const ezpz_structure_t* base, const ezpz_constraint_t* extra, uint32_t n_extra,
+                                   ezpz_structure_t** out, ezpz_error_detail_t* detail) {
+    if (!out) return EZPZ_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    if (!base || (n_extra > 0 && !extra) || (uint64_t)base->n_cons + n_extra > UINT32_MAX) return EZPZ_ERR_INVALID_ARGUMENT;
+    uvec<ezpz_constraint_t> all((size_t)base->n_cons + n_extra);
+    parallel_copy(all.data(), base->cons.data(), base->n_cons);
+    std::copy(extra, extra + n_extra, all.data() + base->n_cons);
+    const LargeProgram& P = base->large;
+    const bool keep = P.built && P.direct && P.perm.size() == base->n;
+    return analyse(all.data(), (uint32_t)all.size(), nullptr, &base->var_present, base->n, keep ? P.perm.data() : nullptr,
+                   keep && P.nested, out, detail);
 }
 
 void ezpz_b200_structure_destroy(ezpz_structure_t* s) {

@@ -147,6 +147,9 @@ struct ezpz_structure {
     ezs::SmallProgram small;
     ezs::LargeProgram large;
     bool have_l_pattern = false;  // false when the symbolic factorisation was skipped (very large systems)
+    // ids of the initial guesses (ezpz_b200_structure_create's var_ids) as a membership table, empty when the ids were 0..n-1:
+    // what validate_variables needs again when constraints are added (ezpz_b200_structure_extend)
+    std::vector<uint8_t> var_present;
     bool l_pattern_built = false; // l_col_ptr / l_row_idx are filled (at creation when the batched kernel may run, else on request)
     // device copies, one per CUDA device ordinal, created lazily
     std::mutex dev_mutex;
@@ -167,5 +170,7 @@ inline uint32_t sum_chunk_for(uint32_t n, uint32_t m, size_t nnz) {
 // Implemented in device.cu; called by ezpz_b200_structure_destroy.
 void release_device_copies(ezpz_structure* s);
 // sparse_direct.cpp: ordering, symbolic factorisation and level schedule of the large-system direct solve.
-void build_sparse_direct(ezpz_structure& S);
+// `order_hint` (n entries, elimination position -> variable, or nullptr): an elimination order to keep instead of choosing one
+// (ezpz_b200_structure_extend hands over the base structure's).
+void build_sparse_direct(ezpz_structure& S, const uint32_t* order_hint = nullptr, bool hint_nested = false);
 }  // namespace ezs

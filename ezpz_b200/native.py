@@ -62,6 +62,7 @@ _P = C.c_void_p
 _SYMBOLS = [
     ("ezpz_b200_structure_create", C.c_int32, [_P, C.c_uint32, _P, C.c_uint32, C.POINTER(_P), C.POINTER(ErrorDetail)]),
     ("ezpz_b200_structure_destroy", None, [_P]),
+    ("ezpz_b200_structure_extend", C.c_int32, [_P, _P, C.c_uint32, C.POINTER(_P), C.POINTER(ErrorDetail)]),
     ("ezpz_b200_structure_dims", C.c_int32, [_P, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64),
                                              C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]),
     ("ezpz_b200_structure_pattern", C.c_int32, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)]),

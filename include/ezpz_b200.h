@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define EZPZ_B200_ABI_VERSION 3
+#define EZPZ_B200_ABI_VERSION 4
 
 /* ---------------------------------------------------------------------------------------------
  * Constraint record.  One 64-byte record holds any of the 25 variants of `enum Constraint`
@@ -180,6 +180,15 @@ int32_t ezpz_b200_structure_create(const ezpz_constraint_t* cons, uint32_t n_con
                                    const uint32_t* var_ids, uint32_t n_vars,
                                    ezpz_structure_t** out, ezpz_error_detail_t* detail);
 void ezpz_b200_structure_destroy(ezpz_structure_t* s);
+/* A structure for the constraints of `base` followed by `extra` over the same variables: what a caller that adds a
+ * constraint to a solved sketch and solves again needs (the trim workflows of the reference's tests, tests.rs:748-897; the
+ * reference re-runs Model::new on the longer list, lib.rs:279).  Patterns, scatter slots and tapes are those
+ * ezpz_b200_structure_create gives for the concatenated list; a system of the sparse-direct path KEEPS base's elimination
+ * order instead of dissecting the graph again (any order of the variables is valid; the arithmetic is the oracle's in that
+ * order, as ezpz_b200_structure_ordering reports it).  Ids are validated against the guess ids `base` was created with.
+ * `base` is not modified and may be destroyed afterwards. */
+int32_t ezpz_b200_structure_extend(const ezpz_structure_t* base, const ezpz_constraint_t* extra, uint32_t n_extra,
+                                   ezpz_structure_t** out, ezpz_error_detail_t* detail);
 
 /* Sizes: rows m (= sum residual_dim, constraints.rs:954-993), vars n, nnz(J), nnz(lower A),
  * nnz(L), number of connected components of A. */

@@ -8,7 +8,7 @@
 
 use std::os::raw::{c_char, c_void};
 
-pub const EZPZ_B200_ABI_VERSION: u32 = 3;
+pub const EZPZ_B200_ABI_VERSION: u32 = 4;
 
 /// One `Constraint` in the flat 64-byte form (constraints.rs:37-93; layout table in the header).
 #[repr(C)]
@@ -119,6 +119,8 @@ extern "C" {
     pub fn ezpz_b200_structure_create(cons: *const EzpzConstraint, n_cons: u32, var_ids: *const u32, n_vars: u32,
                                       out: *mut *mut EzpzStructure, detail: *mut EzpzErrorDetail) -> i32;
     pub fn ezpz_b200_structure_destroy(s: *mut EzpzStructure);
+    pub fn ezpz_b200_structure_extend(base: *const EzpzStructure, extra: *const EzpzConstraint, n_extra: u32,
+                                      out: *mut *mut EzpzStructure, detail: *mut EzpzErrorDetail) -> i32;
     pub fn ezpz_b200_structure_dims(s: *const EzpzStructure, m: *mut u32, n: *mut u32, nnz_j: *mut u64, nnz_a: *mut u64,
                                     nnz_l: *mut u64, n_components: *mut u32) -> i32;
     pub fn ezpz_b200_structure_pattern(s: *const EzpzStructure, csc_col_ptr: *mut *const u32, csc_row_idx: *mut *const u32,

@@ -85,6 +85,27 @@ def test_grid_truss_direct(ctx, N, weights):
     assert od["nested"]
 
 
+@pytest.mark.parametrize("system", ["chain", "truss"])
+def test_extended_structure_solves_like_the_oracle_in_the_kept_order(ctx, system):
+    """ezpz_b200_structure_extend on the sparse direct path: constraints added to an analysed sketch, the base's elimination
+    order kept; the solve through the extended structure is bit-exact against the oracle run in that order and agrees with a
+    freshly analysed structure's solve (identical iterations and verdict, 1e-9)."""
+    recs, n, g, exact = wl.chain_sketch(1024) if system == "chain" else wl.grid_truss(30)
+    k = len(recs) - 11
+    base = ez.Structure(recs[:k], n)
+    ext = base.extend(recs[k:])
+    od = ext.ordering()
+    assert od["path"] == 1 and np.array_equal(od["elim_order"], base.ordering()["elim_order"])
+    out = ctx.solve_one(ext, g)
+    o = orc.solve_inner_ordered(recs, g, od["elim_order"], od["sum_chunk"])
+    assert out.iterations == o.iterations and out.converged == o.converged and out.unsatisfied == o.unsatisfied
+    assert_bitwise(out.final_values, o.final_values, "final values")
+    fresh = ctx.solve_one(ez.Structure(recs, n), g)
+    assert out.iterations == fresh.iterations and out.converged == fresh.converged and out.unsatisfied == fresh.unsatisfied
+    scale = np.maximum(1.0, np.abs(fresh.final_values))
+    assert (np.abs(out.final_values - fresh.final_values) <= 1e-9 * scale).all()
+
+
 def test_chain_sketch_pcg_path(ctx):
     """PCG path forced on a 13,312-variable sketch: the step is solved iteratively to 1e-13 relative residual,
     so results agree with the oracle's direct solve to 1e-9 and the LM trajectory has the same length."""

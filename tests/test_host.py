@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} is declared in include/ezpz_b200.h but not exported"
     assert sorted(native.SYMBOL_NAMES) == declared, "native.py must bind exactly the header's functions"
-    assert native.lib().ezpz_b200_abi_version() == 3
+    assert native.lib().ezpz_b200_abi_version() == 4
     assert C.sizeof(native.Constraint) == 64
 
 
@@ -380,3 +380,74 @@ def test_role_programs_of_the_batched_kernel(roles):
         except ez.EzpzError as e:  # too large for the thread-per-problem kernel
             assert e.name == "Unsupported"
     assert checked >= 5
+
+
+def test_threaded_host_analysis_equals_sequential(monkeypatch):
+    """every phase of the host analysis that runs on host threads for large systems (pattern of J as an
+    atomic bucket pass, scatter slots, pattern of A, adjacency, symbolic factorisation over independent subtrees of the
+    elimination tree, supernode panels, update lists, products of A, tile order) produces exactly what one thread does:
+    the fingerprint hashes every array the device reads."""
+    cases = [wl.chain_sketch(20000)[:2], wl.grid_truss(120)[:2]]
+    recs, n = wl.system_from_text(wl.massive_problem_text(500, False))[:2]  # natural-order system: 80 disjoint copies
+    copies = []
+    for k in range(80):
+        c = recs.copy()
+        c["ids"] += np.uint32(k * n)
+        copies.append(c)
+    cases.append((np.concatenate(copies), 80 * n))
+    for recs, n in cases:
+        fps = {}
+        for threads in ("1", "3", "16"):
+            monkeypatch.setenv("EZPZ_B200_HOST_THREADS", threads)
+            st = ez.Structure(recs, n)
+            fps[threads] = (st.fingerprint(), st.ordering()["path"])
+        assert fps["1"] == fps["3"] == fps["16"], fps
+        assert fps["1"][1] == 1
+
+
+def test_structure_extend_equals_analysis_of_the_longer_list():
+    """ezpz_b200_structure_extend (add constraints to an analysed sketch, tests.rs:748-897): for systems of the batched
+    kernel and for natural-order systems the result is the structure ezpz_b200_structure_create gives for the concatenated
+    list, array for array; errors name the constraint by its index in the concatenated list."""
+    for name in sorted(wl.fixtures()):
+        recs, n, g, _ = wl.system_from_text(wl.fixture_text(name))
+        if len(recs) < 2:
+            continue
+        for cut in {1, len(recs) // 2, len(recs) - 1}:
+            ext = ez.Structure(recs[:cut], n).extend(recs[cut:])
+            full = ez.Structure(recs, n)
+            assert ext.fingerprint() == full.fingerprint(), (name, cut)
+            assert (ext.m, ext.n, ext.nnz, ext.n_cons) == (full.m, full.n, full.nnz, full.n_cons)
+    recs, n, g, _ = wl.system_from_text(wl.massive_problem_text(500, False))
+    assert ez.Structure(recs[:1000], n).extend(recs[1000:]).fingerprint() == ez.Structure(recs, n).fingerprint()
+    assert ez.Structure(recs, n).extend(recs[:0]).fingerprint() == ez.Structure(recs, n).fingerprint()
+    Cn = ez.Constraint
+    base = ez.Structure(ez.records([Cn.Fixed(0, 0.0), Cn.Fixed(2, 1.0)]), 3, var_ids=[0, 2, 5])
+    with pytest.raises(ez.EzpzError) as e:  # id 1 is not among the guesses the base was created with
+        base.extend(ez.records([Cn.Fixed(0, 0.5), Cn.Fixed(1, 1.0)]))
+    assert e.value.name == "MissingGuess" and e.value.constraint_id == 3 and e.value.variable == 1
+    with pytest.raises(ez.EzpzError) as e:  # among the guesses but beyond the matrix
+        base.extend(ez.records([Cn.Fixed(5, 0.5)]))
+    assert e.value.name == "FaerMatrix"
+
+
+def test_structure_extend_keeps_the_elimination_order():
+    """Large-path systems: the extended structure keeps the base's elimination order (no second dissection), its patterns
+    are those of the longer list, the factor stays about as sparse as a fresh analysis makes it, and the oracle solves to
+    the same answer in that order (identical iterations, 1e-9) as in the natural one."""
+    import orc
+    for recs, n, g, exact in (wl.chain_sketch(304), wl.grid_truss(20)):
+        k = len(recs) - 9
+        base = ez.Structure(recs[:k], n)
+        ext, full = base.extend(recs[k:]), ez.Structure(recs, n)
+        ob, oe, of = base.ordering(), ext.ordering(), full.ordering()
+        assert ob["path"] == oe["path"] == of["path"] == 1 and ob["nested"] and oe["nested"]
+        assert np.array_equal(oe["elim_order"], ob["elim_order"])
+        pe, pf = ext.pattern(), full.pattern()
+        for key in pe:
+            assert np.array_equal(pe[key], pf[key]), key
+        assert oe["nnz_l"] <= 1.25 * of["nnz_l"] and oe["sum_chunk"] == of["sum_chunk"]
+        a = orc.solve_inner(recs, g)
+        b = orc.solve_inner_ordered(recs, g, oe["elim_order"], oe["sum_chunk"])
+        assert a.iterations == b.iterations and a.converged == b.converged
+        assert np.abs(a.final_values - b.final_values).max() < 1e-9
