@@ -370,6 +370,10 @@ def large_system_report(ctx, peaks):
     d["gpu_solve_ms"], d["cpu_port_solve_ms"] = d.pop("gpu_solve_us") / 1e3, d.pop("cpu_port_solve_us") / 1e3
     od = st.ordering()
     d["elimination_tree_levels"], d["nnz_l"] = od["n_levels"], od["nnz_l"]
+    t0 = time.perf_counter()
+    st2 = st.extend(recs[-1:])  # ezpz_b200_structure_extend: one constraint added, the elimination order kept
+    d["host_reanalysis_us_after_adding_one_constraint"] = (time.perf_counter() - t0) * 1e6
+    del st2
     out["synthetic_1M_variable_sketch"] = d
     del st
     # a 2D lattice (separators of ~N points: tall panels, the opposite regime of the chain)

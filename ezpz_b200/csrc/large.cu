@@ -1933,35 +1933,47 @@ struct DevicePlan {
     struct Item {
         void** dst;
         size_t off;
+        const void* src;
+        size_t bytes;
     };
-    std::vector<unsigned char> stage;
     std::vector<Item> up, raw;
-    size_t reserve_bytes = 0;
+    size_t up_bytes = 0, reserve_bytes = 0;
+    // (the source must stay alive and unchanged until finalize() returns)
     template <class T, class A>
     int32_t upload(T** dst, const std::vector<T, A>& src) {
-        const size_t off = (stage.size() + 255) / 256 * 256, bytes = std::max<size_t>(sizeof(T), sizeof(T) * src.size());
-        stage.resize(off + bytes);
-        if (!src.empty()) std::memcpy(stage.data() + off, src.data(), sizeof(T) * src.size());
-        up.push_back({reinterpret_cast<void**>(dst), off});
+        up.push_back({reinterpret_cast<void**>(dst), up_bytes, src.data(), sizeof(T) * src.size()});
+        up_bytes += (std::max<size_t>(sizeof(T), sizeof(T) * src.size()) + 255) / 256 * 256;
         return EZPZ_OK;
     }
     template <class T>
     void reserve(T** dst, size_t bytes) {  // zero-initialised
-        raw.push_back({reinterpret_cast<void**>(dst), reserve_bytes});
+        raw.push_back({reinterpret_cast<void**>(dst), reserve_bytes, nullptr, 0});
         reserve_bytes += (std::max<size_t>(bytes, 8) + 255) / 256 * 256;
     }
     int32_t finalize(void** arena, cudaStream_t st, ezpz_error_detail_t* detail) {
-        const size_t up_bytes = (stage.size() + 255) / 256 * 256;
         // stream-ordered allocation out of the device's default pool (its release threshold is lifted in context_create): a
         // topology analysed again after its structure was destroyed gets the same memory back without a trip to the driver's
         // physical allocator, which costs milliseconds for a block of a few MB
         EZ_CUDA(cudaMallocAsync(arena, std::max<size_t>(256, up_bytes + reserve_bytes), st), "cudaMallocAsync(structure tables)");
         unsigned char* base = static_cast<unsigned char*>(*arena);
-        if (!stage.empty()) EZ_CUDA(cudaMemcpyAsync(base, stage.data(), stage.size(), cudaMemcpyHostToDevice, st), "cudaMemcpy(structure tables)");
+        // Small structures: the tables are packed into one host block and leave with ONE copy (some thirty copies of a few
+        // hundred bytes cost more than the solve of a 2,000-variable system).  Large ones: every table is copied from where
+        // it lies (packing 400 MB of tables of a 1M-variable sketch into a staging block first cost more than the copies).
+        std::vector<unsigned char> stage;
+        if (up_bytes <= (4u << 20)) {
+            stage.resize(up_bytes);
+            for (const Item& it : up)
+                if (it.bytes) std::memcpy(stage.data() + it.off, it.src, it.bytes);
+            if (up_bytes) EZ_CUDA(cudaMemcpyAsync(base, stage.data(), up_bytes, cudaMemcpyHostToDevice, st), "cudaMemcpy(structure tables)");
+        } else {
+            EZ_CUDA(cudaMemsetAsync(base, 0, up_bytes, st), "cudaMemset(structure tables)");  // (the alignment gaps read as zero)
+            for (const Item& it : up)
+                if (it.bytes) EZ_CUDA(cudaMemcpyAsync(base + it.off, it.src, it.bytes, cudaMemcpyHostToDevice, st), "cudaMemcpy(structure table)");
+        }
         if (reserve_bytes) EZ_CUDA(cudaMemsetAsync(base + up_bytes, 0, reserve_bytes, st), "cudaMemset(work buffers)");
         for (const Item& it : up) *it.dst = base + it.off;
         for (const Item& it : raw) *it.dst = base + up_bytes + it.off;
-        EZ_CUDA(cudaStreamSynchronize(st), "cudaStreamSynchronize");  // (the staging block dies with the plan)
+        EZ_CUDA(cudaStreamSynchronize(st), "cudaStreamSynchronize");  // (the sources may go after this)
         return EZPZ_OK;
     }
 };
@@ -1985,6 +1997,9 @@ int32_t get_large(ezpz_context* ctx, const ezpz_structure* s, DeviceCopy* dc, La
     if (!L) return EZPZ_ERR_INVALID_ARGUMENT;
     dc->large.emplace_back(ctx, L);  // owned by the device copy from here on (released with it)
     DevicePlan plan;
+    ezs::uvec<uint32_t> recs, orig;  // (sources of uploads: alive until plan.finalize())
+    ezs::uvec<uint8_t> flags;
+    ezs::uvec<TileDesc> tiles;
     {
         // record tiles (see the comment above assemble_slot)
         static const uint8_t kHasP0[EZPZ_K_COUNT] = {0, 0, 1, 0, 1, 1, 0, 0, 1, 1, 0, 0, 1, 0, 1, 0, 0, 1, 1, 1, 0, 0, 1, 1, 1};
@@ -2004,21 +2019,33 @@ int32_t get_large(ezpz_context* ctx, const ezpz_structure* s, DeviceCopy* dc, La
             ly.n_words = w;
         }
         const uint32_t n_slots = (uint32_t)P.cons_order.size(), n_tiles = n_slots / 32;  // cons_order is padded to whole warps
-        std::vector<TileDesc> tiles(n_tiles);
-        std::vector<uint32_t> recs, orig(n_slots, 0u);
-        std::vector<uint8_t> flags(std::max<uint32_t>(1, n_slots), 0);
-        recs.reserve((size_t)n_slots * 16);
-        for (uint32_t t = 0; t < n_tiles; ++t) {
-            const uint32_t c0 = P.cons_order[(size_t)t * 32];  // first slot of a tile is never padding
+        tiles.resize(n_tiles);
+        orig.resize(n_slots);
+        flags.resize(std::max<uint32_t>(1, n_slots));
+        flags[0] = 0;
+        // offsets first (a tile's size follows from its kind), then ranges of tiles on host threads, each writing its own span
+        ezs::uvec<uint64_t> tile_base((size_t)n_tiles + 1);
+        tile_base[0] = 0;
+        for (uint32_t t = 0; t < n_tiles; ++t)  // first slot of a tile is never padding
+            tile_base[t + 1] = tile_base[t] + (uint64_t)L->layout[s->dev_cons[P.cons_order[(size_t)t * 32]].kind].n_words * 32;
+        if (tile_base[n_tiles] / 4 > 0xfffffff0ull) return EZPZ_ERR_TOO_LARGE;
+        recs.resize(tile_base[n_tiles]);
+        ezs::parallel_ranges(n_tiles, 256, [&](uint32_t tb, uint32_t te, uint32_t) {
+        for (uint32_t t = tb; t < te; ++t) {
+            const uint32_t c0 = P.cons_order[(size_t)t * 32];
             const uint32_t kind = s->dev_cons[c0].kind;
             const KindLayout& ly = L->layout[kind];
             const ezk::KindInfo& ki = ezk::kKinds[kind];
-            const size_t base = recs.size();  // multiple of 32 words = 128 bytes
-            recs.resize(base + (size_t)ly.n_words * 32, 0u);
+            const size_t base = tile_base[t];  // multiple of 32 words = 128 bytes
+            std::fill(recs.begin() + base, recs.begin() + tile_base[t + 1], 0u);
             uint32_t n_valid = 0;
             for (uint32_t l = 0; l < 32; ++l) {
                 const uint32_t c = P.cons_order[(size_t)t * 32 + l];
-                if (c == UINT32_MAX) continue;  // padding sits at the end of the kind group
+                if (c == UINT32_MAX) {  // padding sits at the end of the kind group
+                    orig[(size_t)t * 32 + l] = 0;
+                    flags[(size_t)t * 32 + l] = 0;
+                    continue;
+                }
                 n_valid = l + 1;
                 const DevCons& dc = s->dev_cons[c];
                 auto put = [&](uint32_t word, uint32_t v) { recs[base + (size_t)word * 32 + l] = v; };
@@ -2051,8 +2078,8 @@ int32_t get_large(ezpz_context* ctx, const ezpz_structure* s, DeviceCopy* dc, La
             }
             tiles[t].off16 = (uint32_t)(base / 4);
             tiles[t].meta = kind | (n_valid << 8);
-            if (base / 4 > 0xfffffff0ull) return EZPZ_ERR_TOO_LARGE;
         }
+        });
         EZ_TRY(plan.upload(&L->recs, recs));
         EZ_TRY(plan.upload(&L->tiles, tiles));
         EZ_TRY(plan.upload(&L->slot_orig, orig));

@@ -276,14 +276,79 @@ TreeTasks cut_tree(const std::vector<uint32_t>& parent, uint32_t n_threads) {
     return T;
 }
 
+// aprod_ptr / aprod_a / aprod_b from the entries A has (aent_colptr, aent_row; elimination numbering, `perm` = position ->
+// variable): for every entry the rows its two columns of J share, ascending, as pairs of CSC positions.  Count, prefix, fill;
+// ranges of columns on host threads.
+void fill_products(ezpz_structure& S, const uint32_t* perm) {
+    LargeProgram& P = S.large;
+    const uint32_t n = S.n;
+    const size_t n_ent = P.aent_row.size();
+    auto shared_rows = [&](uint32_t ci, uint32_t cj, auto&& fn) {  // fn(position in ci, position in cj)
+        uint32_t pi = S.csc_col_ptr[ci], pj = S.csc_col_ptr[cj];
+        const uint32_t pie = S.csc_col_ptr[ci + 1], pje = S.csc_col_ptr[cj + 1];
+        while (pi < pie && pj < pje) {
+            const uint32_t ri = S.csc_row_idx[pi], rj = S.csc_row_idx[pj];
+            if (ri == rj) fn(pi++, pj++);
+            else if (ri < rj) ++pi;
+            else ++pj;
+        }
+    };
+    P.aprod_ptr.resize(n_ent + 1);
+    P.aprod_ptr[0] = 0;
+    parallel_ranges(n, kHostGrain, [&](uint32_t c0, uint32_t c1, uint32_t) {
+        for (uint32_t j = c0; j < c1; ++j)
+            for (uint32_t e = P.aent_colptr[j]; e < P.aent_colptr[j + 1]; ++e) {
+                uint32_t found = 0;
+                shared_rows(perm[P.aent_row[e]], perm[j], [&](uint32_t, uint32_t) { ++found; });
+                P.aprod_ptr[e + 1] = found;
+            }
+    });
+    prefix_sum(P.aprod_ptr);
+    const size_t n_prod = P.aprod_ptr[n_ent];
+    P.aprod_a.resize(n_prod);
+    P.aprod_b.resize(n_prod);
+    parallel_ranges(n, kHostGrain, [&](uint32_t c0, uint32_t c1, uint32_t) {
+        for (uint32_t j = c0; j < c1; ++j)
+            for (uint32_t e = P.aent_colptr[j]; e < P.aent_colptr[j + 1]; ++e) {
+                uint32_t at = P.aprod_ptr[e];
+                shared_rows(perm[P.aent_row[e]], perm[j], [&](uint32_t pi, uint32_t pj) {
+                    P.aprod_a[at] = pi;
+                    P.aprod_b[at++] = pj;
+                });
+            }
+    });
+}
+
 }  // namespace
 
 // Fills the sparse-direct part of S.large.  Leaves P.direct false when the factor would be too large.
-void build_sparse_direct(ezpz_structure& S, const uint32_t* order_hint, bool hint_nested) {
+void build_sparse_direct(ezpz_structure& S, const uint32_t* order_hint, bool hint_nested, const ezpz_structure* same_a) {
     LargeProgram& P = S.large;
     const uint32_t n = S.n;
     P.direct = false;
     if (n == 0) return;
+    if (same_a && same_a->large.direct && same_a->n == n) {
+        // Constraints were added that couple no new pair of variables (ezpz_b200_structure_extend): A has the pattern it had,
+        // so the order, the symbolic factorisation, the supernodes, their updates and stages are the base's; only the
+        // products behind the entries of A = JtJ run over new rows.
+        const LargeProgram& B = same_a->large;
+        P.nested = B.nested;
+        P.n_levels = B.n_levels;
+        P.nnz_l = B.nnz_l;
+        const LargeProgram::u32v* from[] = {&B.perm, &B.sn_ptr, &B.sn_row_ptr, &B.sn_rows, &B.panel_off, &B.upd_ptr, &B.upd_sn, &B.upd_rbegin,
+                                            &B.upd_ncols, &B.upd_rel_ptr, &B.upd_rel, &B.upd_rec, &B.stage_ptr, &B.stage_sn, &B.stage_rec,
+                                            &B.aent_slot, &B.aent_row, &B.aent_colptr, &B.diag_slot};
+        LargeProgram::u32v* to[] = {&P.perm, &P.sn_ptr, &P.sn_row_ptr, &P.sn_rows, &P.panel_off, &P.upd_ptr, &P.upd_sn, &P.upd_rbegin,
+                                    &P.upd_ncols, &P.upd_rel_ptr, &P.upd_rel, &P.upd_rec, &P.stage_ptr, &P.stage_sn, &P.stage_rec,
+                                    &P.aent_slot, &P.aent_row, &P.aent_colptr, &P.diag_slot};
+        for (size_t k = 0; k < sizeof(from) / sizeof(from[0]); ++k) {
+            to[k]->resize(from[k]->size());
+            parallel_copy(to[k]->data(), from[k]->data(), from[k]->size());
+        }
+        fill_products(S, P.perm.data());
+        P.direct = true;
+        return;
+    }
     const char* force = std::getenv("EZPZ_B200_FORCE_PCG");
     if (force && force[0] == '1') return;
     const auto t_start = std::chrono::steady_clock::now();
@@ -689,80 +754,49 @@ void build_sparse_direct(ezpz_structure& S, const uint32_t* order_hint, bool hin
     }
     lap("stages and records");
     // ---- 7. A = JtJ: products of every entry A has, addressed to its panel slot; diagonal slots ---------------
-    // Independent per column, two passes over ranges of columns on host threads: the first finds every entry's panel slot
-    // and counts its products (the rows its two columns of J share), the second writes the products at their final places.
+    // Independent per column, ranges of columns on host threads: the entries A has in every column (elimination numbering)
+    // with their panel slots first, then their products (fill_products).
     {
         P.diag_slot.resize(n);
-        uvec<uint32_t> ent_ptr((size_t)n + 1);
-        ent_ptr[0] = 0;
+        P.aent_colptr.resize((size_t)n + 1);
+        P.aent_colptr[0] = 0;
         parallel_ranges(n, kHostGrain, [&](uint32_t c0, uint32_t c1, uint32_t) {
             for (uint32_t j = c0; j < c1; ++j) {
                 uint32_t cnt = 0;
                 for (uint32_t q = lc_ptr[j]; q < lc_ptr[j + 1]; ++q) cnt += lc_in_a[q];
-                ent_ptr[j + 1] = cnt;
+                P.aent_colptr[j + 1] = cnt;
             }
         });
-        prefix_sum(ent_ptr);
-        const size_t n_ent = ent_ptr[n];
+        prefix_sum(P.aent_colptr);
+        const size_t n_ent = P.aent_colptr[n];
         P.aent_slot.resize(n_ent);
-        P.aprod_ptr.resize(n_ent + 1);
-        P.aprod_ptr[0] = 0;
+        P.aent_row.resize(n_ent);
         std::vector<uint8_t> bad(64, 0);
-        // shared rows of the columns ci and cj of J, ascending: fn(position in ci, position in cj)
-        auto shared_rows = [&](uint32_t ci, uint32_t cj, auto&& fn) {
-            uint32_t pi = S.csc_col_ptr[ci], pj = S.csc_col_ptr[cj];
-            const uint32_t pie = S.csc_col_ptr[ci + 1], pje = S.csc_col_ptr[cj + 1];
-            while (pi < pie && pj < pje) {
-                const uint32_t ri = S.csc_row_idx[pi], rj = S.csc_row_idx[pj];
-                if (ri == rj) fn(pi++, pj++);
-                else if (ri < rj) ++pi;
-                else ++pj;
-            }
-        };
         parallel_ranges(n, kHostGrain, [&](uint32_t c0, uint32_t c1, uint32_t t) {
             for (uint32_t j = c0; j < c1; ++j) {
                 const uint32_t J = sn_of[j], j0 = P.sn_ptr[J], j1 = P.sn_ptr[J + 1], w = j1 - j0;
                 P.diag_slot[j] = P.panel_off[J] + (j - j0) * w + (j - j0);
-                const uint32_t cj = perm[j];
                 // rows of the panel below the diagonal block, walked together with the column's (ascending) rows
                 const uint32_t* prow = P.sn_rows.data() + P.sn_row_ptr[J];
                 const uint32_t ph = P.sn_row_ptr[J + 1] - P.sn_row_ptr[J];
-                uint32_t pp = w, e = ent_ptr[j];
+                uint32_t pp = w, e = P.aent_colptr[j];
                 for (uint32_t q = lc_ptr[j]; q < lc_ptr[j + 1]; ++q) {
                     if (!lc_in_a[q]) continue;
                     const uint32_t i = lc_row[q];
-                    uint32_t pos = 0, found = 0;
+                    uint32_t pos = 0;
                     if (i < j1) pos = i - j0;
                     else {
                         while (pp < ph && prow[pp] < i) ++pp;
                         if (pp >= ph || prow[pp] != i) bad[t] = 1;
                         else pos = pp;
                     }
-                    shared_rows(perm[i], cj, [&](uint32_t, uint32_t) { ++found; });
-                    P.aent_slot[e] = P.panel_off[J] + pos * w + (j - j0);
-                    P.aprod_ptr[++e] = found;
+                    P.aent_row[e] = i;
+                    P.aent_slot[e++] = P.panel_off[J] + pos * w + (j - j0);
                 }
             }
         });
         for (uint8_t f : bad) inconsistent = inconsistent || f;
-        prefix_sum(P.aprod_ptr);
-        const size_t n_prod = P.aprod_ptr[n_ent];
-        P.aprod_a.resize(n_prod);
-        P.aprod_b.resize(n_prod);
-        parallel_ranges(n, kHostGrain, [&](uint32_t c0, uint32_t c1, uint32_t) {
-            for (uint32_t j = c0; j < c1; ++j) {
-                const uint32_t cj = perm[j];
-                uint32_t e = ent_ptr[j];
-                for (uint32_t q = lc_ptr[j]; q < lc_ptr[j + 1]; ++q) {
-                    if (!lc_in_a[q]) continue;
-                    uint32_t at = P.aprod_ptr[e++];
-                    shared_rows(perm[lc_row[q]], cj, [&](uint32_t pi, uint32_t pj) {
-                        P.aprod_a[at] = pi;
-                        P.aprod_b[at++] = pj;
-                    });
-                }
-            }
-        });
+        fill_products(S, perm.data());
     }
     lap("products of A");
     if (inconsistent) {

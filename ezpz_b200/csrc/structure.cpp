@@ -508,7 +508,8 @@ namespace {
 
 // Programme of the single-large-system path: assembly processing order, value-array layout, and the sparse
 // direct schedule (sparse_direct.cpp).
-void build_large_program(ezpz_structure& S, const uint32_t* order_hint = nullptr, bool hint_nested = false) {
+void build_large_program(ezpz_structure& S, const uint32_t* order_hint = nullptr, bool hint_nested = false,
+                         const ezpz_structure* same_a = nullptr) {
     LargeProgram& P = S.large;
     P = LargeProgram();
     const uint32_t n = S.n, m = S.m;
@@ -555,7 +556,7 @@ void build_large_program(ezpz_structure& S, const uint32_t* order_hint = nullptr
             }
         });
     }
-    build_sparse_direct(S, order_hint, hint_nested);
+    build_sparse_direct(S, order_hint, hint_nested, same_a);
     // Direct path: J in tile order.  Every record tile owns 32 x (partials the kind emits) consecutive doubles; partial q
     // of the constraint in lane l sits at base + q * 32 + l.  A partial that accumulates into an entry the same constraint
     // already wrote (bit 31 of its slot) shares that entry's position.  Consumers that think in CSC positions (the product
@@ -629,8 +630,7 @@ void build_large_program(ezpz_structure& S, const uint32_t* order_hint = nullptr
 // The analysis behind ezpz_b200_structure_create and ezpz_b200_structure_extend.  The ids of the guesses come as a list
 // (`var_ids`, create) or as the membership table of an analysed structure (`present`, extend); both null = ids 0..n_vars-1.
 static int32_t analyse(const ezpz_constraint_t* cons, uint32_t n_cons, const uint32_t* var_ids, const std::vector<uint8_t>* present_in,
-                       uint32_t n_vars, const uint32_t* order_hint, bool hint_nested, ezpz_structure_t** out,
-                       ezpz_error_detail_t* detail) {
+                       uint32_t n_vars, const ezpz_structure* base, ezpz_structure_t** out, ezpz_error_detail_t* detail) {
     if (!out) return EZPZ_ERR_INVALID_ARGUMENT;
     *out = nullptr;
     if (detail) std::memset(detail, 0, sizeof *detail);
@@ -892,7 +892,14 @@ static int32_t analyse(const ezpz_constraint_t* cons, uint32_t n_cons, const uin
     build_components(*S);
     lap("natural L pattern, components");
     if (S->l_pattern_built) build_small_program(*S);
-    if (!S->small.valid) build_large_program(*S, order_hint, hint_nested);
+    if (!S->small.valid) {
+        // constraints added to an analysed structure of the sparse-direct path (ezpz_b200_structure_extend): its elimination
+        // order is kept, and its whole schedule when A did not gain an entry (EZPZ_B200_EXTEND_FULL=1: always re-derive it)
+        const bool keep = base && base->large.built && base->large.direct && base->large.perm.size() == n_vars;
+        const char* full = std::getenv("EZPZ_B200_EXTEND_FULL");
+        const bool same_a = keep && !(full && full[0] == '1') && base->a_col_ptr == S->a_col_ptr && base->a_row_idx == S->a_row_idx;
+        build_large_program(*S, keep ? base->large.perm.data() : nullptr, keep && base->large.nested, same_a ? base : nullptr);
+    }
     lap("programme");
     *out = S;
     return EZPZ_OK;
@@ -902,7 +909,7 @@ extern "C" {
 
 int32_t ezpz_b200_structure_create(const ezpz_constraint_t* cons, uint32_t n_cons, const uint32_t* var_ids,
                                    uint32_t n_vars, ezpz_structure_t** out, ezpz_error_detail_t* detail) {
-    return analyse(cons, n_cons, var_ids, nullptr, n_vars, nullptr, false, out, detail);
+    return analyse(cons, n_cons, var_ids, nullptr, n_vars, nullptr, out, detail);
 }
 
 int32_t ezpz_b200_structure_extend(const ezpz_structure_t* base, const ezpz_constraint_t* extra, uint32_t n_extra,
@@ -913,10 +920,7 @@ int32_t ezpz_b200_structure_extend(const ezpz_structure_t* base, const ezpz_cons
     uvec<ezpz_constraint_t> all((size_t)base->n_cons + n_extra);
     parallel_copy(all.data(), base->cons.data(), base->n_cons);
     std::copy(extra, extra + n_extra, all.data() + base->n_cons);
-    const LargeProgram& P = base->large;
-    const bool keep = P.built && P.direct && P.perm.size() == base->n;
-    return analyse(all.data(), (uint32_t)all.size(), nullptr, &base->var_present, base->n, keep ? P.perm.data() : nullptr,
-                   keep && P.nested, out, detail);
+    return analyse(all.data(), (uint32_t)all.size(), nullptr, &base->var_present, base->n, base, out, detail);
 }
 
 void ezpz_b200_structure_destroy(ezpz_structure_t* s) {
@@ -1049,7 +1053,7 @@ uint64_t ezpz_b200_structure_fingerprint(const ezpz_structure_t* s) {
     vec(P.cons_order), vec(P.perm), vec(P.jt_of_csc), vec(P.sn_ptr), vec(P.sn_row_ptr), vec(P.sn_rows), vec(P.panel_off);
     vec(P.upd_ptr), vec(P.upd_sn), vec(P.upd_rbegin), vec(P.upd_ncols), vec(P.upd_rel_ptr), vec(P.upd_rel), vec(P.upd_rec);
     vec(P.stage_ptr), vec(P.stage_sn), vec(P.stage_rec), vec(P.aent_slot), vec(P.aprod_ptr), vec(P.aprod_a), vec(P.aprod_b);
-    vec(P.diag_slot);
+    vec(P.diag_slot), vec(P.aent_colptr), vec(P.aent_row);
     return h;
 }
 

@@ -121,6 +121,9 @@ struct LargeProgram {
     // A = JtJ: for every entry A has (strictly lower), its panel slot and the products J[r][i] * J[r][j] over shared
     // rows r ascending as pairs of positions in the CSC value array of J; diag_slot[j] = panel slot of A[j][j].
     u32v aent_slot, aprod_ptr, aprod_a, aprod_b, diag_slot;
+    // host only: the entries of A per column of the elimination numbering (aent_colptr, n + 1) and their rows (aent_row), from
+    // which the product lists are rebuilt when constraints are added without a new coupling (ezpz_b200_structure_extend)
+    u32v aent_colptr, aent_row;
 };
 
 struct DeviceCopy;  // defined in device.h
@@ -172,5 +175,8 @@ void release_device_copies(ezpz_structure* s);
 // sparse_direct.cpp: ordering, symbolic factorisation and level schedule of the large-system direct solve.
 // `order_hint` (n entries, elimination position -> variable, or nullptr): an elimination order to keep instead of choosing one
 // (ezpz_b200_structure_extend hands over the base structure's).
-void build_sparse_direct(ezpz_structure& S, const uint32_t* order_hint = nullptr, bool hint_nested = false);
+// `same_a`: an analysed structure over the same variables whose A has exactly this structure's pattern: its sparse-direct
+// schedule is taken over and only the product lists are rebuilt.
+void build_sparse_direct(ezpz_structure& S, const uint32_t* order_hint = nullptr, bool hint_nested = false,
+                         const ezpz_structure* same_a = nullptr);
 }  // namespace ezs

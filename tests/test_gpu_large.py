@@ -104,6 +104,17 @@ def test_extended_structure_solves_like_the_oracle_in_the_kept_order(ctx, system
     assert out.iterations == fresh.iterations and out.converged == fresh.converged and out.unsatisfied == fresh.unsatisfied
     scale = np.maximum(1.0, np.abs(fresh.final_values))
     assert (np.abs(out.final_values - fresh.final_values) <= 1e-9 * scale).all()
+    # repeats of existing constraints: no new coupling, the base's whole schedule is taken over (only the products of A = JtJ
+    # are rebuilt); still the oracle's arithmetic on the longer list in the kept order
+    again = np.concatenate([recs[3:5], recs[k:k + 2]])
+    ext2 = ext.extend(again)
+    recs2 = np.concatenate([recs, again])
+    od2 = ext2.ordering()
+    assert np.array_equal(od2["elim_order"], od["elim_order"])
+    out2 = ctx.solve_one(ext2, g)
+    o2 = orc.solve_inner_ordered(recs2, g, od2["elim_order"], od2["sum_chunk"])
+    assert out2.iterations == o2.iterations and out2.converged == o2.converged and out2.unsatisfied == o2.unsatisfied
+    assert_bitwise(out2.final_values, o2.final_values, "final values")
 
 
 def test_chain_sketch_pcg_path(ctx):

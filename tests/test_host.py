@@ -431,7 +431,7 @@ def test_structure_extend_equals_analysis_of_the_longer_list():
     assert e.value.name == "FaerMatrix"
 
 
-def test_structure_extend_keeps_the_elimination_order():
+def test_structure_extend_keeps_the_elimination_order(monkeypatch):
     """Large-path systems: the extended structure keeps the base's elimination order (no second dissection), its patterns
     are those of the longer list, the factor stays about as sparse as a fresh analysis makes it, and the oracle solves to
     the same answer in that order (identical iterations, 1e-9) as in the natural one."""
@@ -451,3 +451,13 @@ def test_structure_extend_keeps_the_elimination_order():
         b = orc.solve_inner_ordered(recs, g, oe["elim_order"], oe["sum_chunk"])
         assert a.iterations == b.iterations and a.converged == b.converged
         assert np.abs(a.final_values - b.final_values).max() < 1e-9
+        # constraints that couple no new pair of variables (here: repeats of existing ones) leave A's pattern alone: the whole
+        # sparse-direct schedule is taken over from the base and only the product lists of A = JtJ are rebuilt; the result is
+        # what the full re-derivation in the kept order gives
+        again = np.concatenate([recs[3:5], recs[k:k + 2]])
+        fast = full.extend(again)
+        monkeypatch.setenv("EZPZ_B200_EXTEND_FULL", "1")
+        slow = full.extend(again)
+        monkeypatch.delenv("EZPZ_B200_EXTEND_FULL")
+        assert fast.fingerprint() == slow.fingerprint()
+        assert np.array_equal(fast.ordering()["elim_order"], of["elim_order"]) and fast.m == full.m + slow.m - full.m > full.m

@@ -15,9 +15,16 @@ ctx = ez.Context(0)
 which = sys.argv[1:] or ["chain", "truss", "massive"]
 if "chain" in which:
     recs, n, g, _ = wl.chain_sketch(77000)
+    t0 = time.perf_counter()
     st = ez.Structure(recs, n)
+    t_an = time.perf_counter() - t0
     ts, it, status, path = ctx.time_solve_one(st, g, reps=5)
-    print(f"chain sketch n={n}: {statistics.median(ts[1:]) * 1e3:.2f} ms per solve, {it} iterations", flush=True)
+    print(f"chain sketch n={n}: {statistics.median(ts[1:]) * 1e3:.2f} ms per solve, {it} iterations; host analysis {t_an * 1e3:.0f} ms, "
+          f"first solve (device tables uploaded) {ts[0] * 1e3:.0f} ms", flush=True)
+    t0 = time.perf_counter()
+    st2 = st.extend(recs[-1:])
+    print(f"  one constraint added (ezpz_b200_structure_extend, elimination order kept): {(time.perf_counter() - t0) * 1e3:.0f} ms", flush=True)
+    del st2
     del st
 if "truss" in which:
     for N in (50, 100):
