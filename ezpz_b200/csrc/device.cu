@@ -814,6 +814,7 @@ void ezpz_b200_context_destroy(ezpz_context_t* ctx) {
         if (ctx->pipe[k]) cudaStreamDestroy(ctx->pipe[k]);
         if (ctx->pipe_done[k]) cudaEventDestroy(ctx->pipe_done[k]);
     }
+    for (cudaEvent_t e : ctx->lane_ev) cudaEventDestroy(e);
     if (ctx->ws) cudaFree(ctx->ws);
     if (ctx->fa_ws) cudaFree(ctx->fa_ws);
     if (ctx->fa_jac) cudaFree(ctx->fa_jac);
@@ -899,7 +900,7 @@ static int32_t launch_small(ezpz_context_t* ctx, const ezpz_structure_t* s, cons
     if (rc != EZPZ_OK) return rc;
     const SmallProgram& P = s->small;
     SmallShape shape;
-    rc = small_shape(ctx, s, batch, &shape);
+    rc = small_shape(ctx, s, ctx->shape_batch ? ctx->shape_batch : batch, &shape);
     if (rc != EZPZ_OK) return rc;
     RoleTables* tables = nullptr;
     rc = get_role_tables(ctx, s, dc, shape.R, small_stride(shape.T), &tables, detail);
@@ -1096,6 +1097,7 @@ int32_t ezpz_b200_solve_batch(ezpz_context_t* ctx, const ezpz_structure_t* s, co
         std::vector<cudaEvent_t>* ev;
         ~Drain() {
             for (int k = 0; k < 3; ++k) cudaStreamSynchronize(c->pipe[k]);
+            cudaStreamSynchronize(c->stream);
             for (cudaEvent_t e : *ev) cudaEventDestroy(e);
         }
     } drain{ctx, &tev};
@@ -1128,6 +1130,79 @@ int32_t ezpz_b200_solve_batch(ezpz_context_t* ctx, const ezpz_structure_t* s, co
         cudaEventRecord(e, st);
         tev.push_back(e);
     };
+    // Lane form of the pipeline (batched-kernel structures without the fused analysis): ONE stream carries every copy-in back
+    // to back, one every copy-out, two carry the kernels alternately, events link a chunk's three steps.  Each copy engine
+    // then streams without gaps (with the steps of a chunk on one stream, copy-in k + 3 queues behind copy-out k), and chunks
+    // smaller than a kernel wave overlap on the SMs.  EZPZ_B200_PIPE_LANES=<chunks> (0 = the three-stream form below).
+    uint64_t lane_chunks = 0;
+    // Measured (profiles/r02s_e2e_lane_pipeline.log): 65,536 problems 329 us with six lane chunks against 350 us for three
+    // whole-wave chunks; no gain at 32,768 and at 262,144, so the lane form is the default in between only.
+    if (s->small.valid && !d_jc && !d_uc && batch >= 16384) {
+        lane_chunks = batch >= 49152 && batch <= 131072 ? 6 : 0;
+        if (const char* env = std::getenv("EZPZ_B200_PIPE_LANES")) lane_chunks = std::strtoull(env, nullptr, 10);
+    }
+    if (lane_chunks > 0) {
+        uint64_t per = (batch + lane_chunks - 1) / lane_chunks;
+        per = (per + 31) / 32 * 32;  // whole 32-problem groups
+        const uint64_t nl = (batch + per - 1) / per;
+        while (ctx->lane_ev.size() < 2 * nl) {
+            cudaEvent_t e;
+            EZ_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate");
+            ctx->lane_ev.push_back(e);
+        }
+        // chunks keep the CTA shape of the whole batch (full CTAs on a part of the SMs: the kernels of two chunks run side by side)
+        struct Shape {
+            ezpz_context* c;
+            ~Shape() { c->shape_batch = 0; }
+        } shape_guard{ctx};
+        if (const char* env = std::getenv("EZPZ_B200_LANE_PACK"); !env || env[0] != '0') ctx->shape_batch = batch;
+        cudaStream_t s_in = ctx->pipe[0], s_out = ctx->pipe[1], s_k[2] = {ctx->pipe[2], ctx->stream};
+        if (trace) mark(s_in);
+        for (uint64_t c = 0; c < nl; ++c) {
+            const uint64_t b0 = c * per, cnt = std::min(per, batch - b0);
+            EZ_CUDA(cudaMemcpyAsync(d_g + b0 * n, io->guesses + b0 * n, cnt * n * sizeof(double), cudaMemcpyHostToDevice, s_in), "H2D guesses");
+            if (d_p) EZ_CUDA(cudaMemcpyAsync(d_p + b0 * nc, io->params + b0 * nc, cnt * nc * sizeof(double), cudaMemcpyHostToDevice, s_in), "H2D params");
+            EZ_CUDA(cudaEventRecord(ctx->lane_ev[2 * c], s_in), "cudaEventRecord");
+            cudaStream_t sk = s_k[c & 1];
+            EZ_CUDA(cudaStreamWaitEvent(sk, ctx->lane_ev[2 * c], 0), "cudaStreamWaitEvent");
+            ezpz_batch_io_t dio;
+            dio.guesses = d_g + b0 * n;
+            dio.params = d_p ? d_p + b0 * nc : nullptr;
+            dio.final_values = d_f + b0 * n;
+            dio.iterations = d_it + b0;
+            dio.status = d_st + b0;
+            dio.unsat_mask = d_un ? d_un + b0 * uw : nullptr;
+            dio.degen_count = d_dg ? d_dg + b0 * nc : nullptr;
+            dio.jacobian = nullptr;
+            dio.under_mask = nullptr;
+            rc = ezpz_b200_solve_batch_device(ctx, s, config, cnt, &dio, sk, detail);
+            if (rc != EZPZ_OK) return rc;
+            EZ_CUDA(cudaEventRecord(ctx->lane_ev[2 * c + 1], sk), "cudaEventRecord");
+            EZ_CUDA(cudaStreamWaitEvent(s_out, ctx->lane_ev[2 * c + 1], 0), "cudaStreamWaitEvent");
+            EZ_CUDA(cudaMemcpyAsync(io->final_values + b0 * n, d_f + b0 * n, cnt * n * sizeof(double), cudaMemcpyDeviceToHost, s_out), "D2H finals");
+            if (d_dg) EZ_CUDA(cudaMemcpyAsync(io->degen_count + b0 * nc, d_dg + b0 * nc, cnt * nc * sizeof(uint32_t), cudaMemcpyDeviceToHost, s_out), "D2H degen");
+            if (trace) mark(s_out);
+        }
+        // the small per-problem outputs in one copy each behind the last chunk's finals (the copy-out lane has waited for
+        // every kernel); the copy-in lane is idle by now and takes two of them once the last kernel is done
+        EZ_CUDA(cudaStreamWaitEvent(s_in, ctx->lane_ev[2 * (nl - 1) + 1], 0), "cudaStreamWaitEvent");
+        if (nl > 1) EZ_CUDA(cudaStreamWaitEvent(s_in, ctx->lane_ev[2 * (nl - 2) + 1], 0), "cudaStreamWaitEvent");
+        EZ_CUDA(cudaMemcpyAsync(io->iterations, d_it, batch * sizeof(uint32_t), cudaMemcpyDeviceToHost, s_in), "D2H iterations");
+        EZ_CUDA(cudaMemcpyAsync(io->status, d_st, batch, cudaMemcpyDeviceToHost, s_in), "D2H status");
+        if (d_un) EZ_CUDA(cudaMemcpyAsync(io->unsat_mask, d_un, batch * uw * sizeof(uint32_t), cudaMemcpyDeviceToHost, s_in), "D2H unsat");
+        EZ_CUDA(cudaStreamSynchronize(s_out), "cudaStreamSynchronize");
+        EZ_CUDA(cudaStreamSynchronize(s_in), "cudaStreamSynchronize");
+        if (trace && tev.size() >= 2) {
+            std::fprintf(stderr, "[solve_batch lanes] us since call start, copy-out of every chunk done:");
+            for (size_t k = 1; k < tev.size(); ++k) {
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, tev[0], tev[k]);
+                std::fprintf(stderr, " %.0f", ms * 1e3);
+            }
+            std::fprintf(stderr, "\n");
+        }
+        return EZPZ_OK;
+    }
     if (trace) mark(ctx->pipe[0]);
     for (uint64_t c = 0; c < n_chunks; ++c) {
         const uint64_t b0 = c * chunk;

@@ -59,6 +59,8 @@ struct ezpz_context {
     cudaStream_t stream = nullptr;
     cudaStream_t pipe[3] = {nullptr, nullptr, nullptr};  // copy/compute pipeline of the host-buffer batch call
     cudaEvent_t pipe_done[3] = {nullptr, nullptr, nullptr};
+    uint64_t shape_batch = 0;  // nonzero: launch_small sizes its CTAs for a batch of this many problems instead of the call's (lane pipeline)
+    std::vector<cudaEvent_t> lane_ev;  // events of the lane pipeline (copy-in lane -> kernel lanes -> copy-out lane), made on demand
     int sm_count = 0;
     size_t smem_optin = 0;
     uint64_t launches = 0;
