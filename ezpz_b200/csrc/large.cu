@@ -313,6 +313,11 @@ __device__ __noinline__ void assemble_phase_pipe(const LargeArgs& a, uint32_t rd
     unsigned char* stage_base = reinterpret_cast<unsigned char*>(warp_stage);
     uint64_t* bars = reinterpret_cast<uint64_t*>(stage_base + warp_stage_bytes - kTail);
     uint2* ring = reinterpret_cast<uint2*>(bars + kAsmStagesMax);
+    // The stage was last written with ordinary stores by the factorisation teams (any warp of the CTA, CTA teams span the
+    // warps' slices) and is about to be written by the async proxy: every thread orders its own stores in front of the
+    // async proxy, then the CTA meets, then the copies are issued.
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
     if (lane == 0) {
         for (uint32_t st = 0; st < kAsmStages; ++st) mbar_init(&bars[st], 1);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -1505,7 +1510,8 @@ __device__ __forceinline__ void lm_large_body(const LargeArgs& a) {
     // pipelined assembly when a warp's slice of the dynamic shared memory holds at least two record tiles and every warp has a
     // few tiles to stream (below that the set-up of the pipeline costs more than it hides: massive 2,000 variables, 8 CTAs, 35 ->
     // 45 us; 1M-variable chain 842 -> 564 us over the 9 phases of a solve).  EZPZ_B200_PIPE_ASM=0 switches it off.
-    const bool pipe_asm = a.pipe_asm && a.n_tiles >= 4u * (nth >> 5) &&
+    // EZPZ_B200_PIPE_ASM=2 forces it for every size (tests, compute-sanitizer on small systems).
+    const bool pipe_asm = a.pipe_asm && (a.pipe_asm == 2u || a.n_tiles >= 4u * (nth >> 5)) &&
                           2u * a.tile_bytes_max + kAsmStagesMax * 8u + 512u <= kWarpStageDoubles * 8u;
     uint32_t fact_epoch = 0;  // factorisations so far in this launch: what a diagonal slice publishes (sn_factor_slice)
     // sides from the initial guesses (lib.rs:183-186), counters
@@ -2202,7 +2208,7 @@ void fill_args(LargeArgs& a, const ezpz_structure* s, const DeviceCopy* dc, cons
     a.sn_flag = L->sn_flag;
     {
         const char* e = std::getenv("EZPZ_B200_PIPE_ASM");
-        a.pipe_asm = e ? (e[0] != '0') : 1u;
+        a.pipe_asm = e ? (e[0] == '2' ? 2u : (e[0] != '0' ? 1u : 0u)) : 1u;
     }
     a.n_sn = (uint32_t)(P.stage_rec.size() / 8);
     // the summation order belongs to the structure, not to the launch shape: a system solved alone (cluster / grid) and

@@ -6,7 +6,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "libezpz_b200.so")
+LIB_PATH = os.environ.get("EZPZ_B200_LIB") or os.path.join(_HERE, "_lib", "libezpz_b200.so")  # (EZPZ_B200_LIB: A/B timing of two builds)
 
 
 class Constraint(C.Structure):

@@ -117,6 +117,26 @@ def test_extended_structure_solves_like_the_oracle_in_the_kept_order(ctx, system
     assert_bitwise(out2.final_values, o2.final_values, "final values")
 
 
+@pytest.mark.parametrize("system", ["chain104", "chain13312", "truss40", "massive"])
+def test_pipelined_assembly_inside_the_lm_kernel(ctx, system, monkeypatch):
+    """The assembly phases inside lm_large_kernel through the per-warp cp.async.bulk tile pipeline (assemble_phase_pipe; by
+    default only when every warp has at least four record tiles, i.e. beyond ~300,000 constraints) forced on systems of every
+    launch shape — one CTA, a cluster of eight, the whole grid: the same bits as the oracle."""
+    monkeypatch.setenv("EZPZ_B200_PIPE_ASM", "2")
+    if system == "massive":
+        recs, n, g, _ = wl.system_from_text(wl.massive_problem_text(500, False))
+        st = ez.Structure(recs, n)
+        od = st.ordering()
+        out = ctx.solve_one(st, g)
+        o = orc.solve_inner_ordered(recs, g, None, od["sum_chunk"])
+        assert out.iterations == o.iterations == 2 and out.converged
+        assert_bitwise(out.final_values, o.final_values, "final values")
+    elif system == "truss40":
+        _check_direct(ctx, 0, wl.grid_truss(40), exact_tol=1e-4)
+    else:
+        _check_direct(ctx, int(system[5:]) // 13)
+
+
 def test_chain_sketch_pcg_path(ctx):
     """PCG path forced on a 13,312-variable sketch: the step is solved iteratively to 1e-13 relative residual,
     so results agree with the oracle's direct solve to 1e-9 and the LM trajectory has the same length."""
