@@ -405,10 +405,22 @@ __global__ void __launch_bounds__(GRID ? 256 : 1024) freedom_team_kernel(const F
 
 // One Householder step of the register-resident QR (freedom_warp_kernel); K is a template parameter so that every index
 // into the per-lane arrays is a compile-time constant (a runtime k would push the arrays into local memory).
+// A warp holds 32 / MAXD problems side by side: SUB-WARPS of MAXD lanes (lane `sl` of the sub-warp = column sl and, in the
+// division exchange, row sl).  Every shuffle, ballot and barrier is confined to the sub-warp (`seg` = its lane mask, `shift`
+// = its first lane), so sub-warps may take different data-dependent paths (zero pivots, ranks) without waiting for each other.
+struct SubWarp {
+    unsigned seg;    // lane mask of this sub-warp
+    uint32_t shift;  // its first lane
+    uint32_t sl;     // this lane's index inside it
+};
+template <int MAXD>
+__device__ __forceinline__ uint32_t sub_ballot(const SubWarp& w, bool pred) {
+    return (__ballot_sync(w.seg, pred) >> w.shift) & ((MAXD >= 32) ? 0xffffffffu : ((1u << MAXD) - 1u));
+}
 template <int K, int MAXD>
-__device__ __forceinline__ void qr_step(double (&A)[MAXD], double (&rd)[MAXD], uint32_t& pos, double& nrm, uint32_t lane, bool active,
+__device__ __forceinline__ void qr_step(double (&A)[MAXD], double (&rd)[MAXD], uint32_t& pos, double& nrm, const SubWarp& w, bool active,
                                         uint32_t m, uint32_t ndiag, double* tile) {
-    const unsigned FULL = 0xffffffffu;
+    const uint32_t lane = w.sl;
     rd[K] = 0.0;
     if ((uint32_t)K >= ndiag) return;
     // pivot among the columns at positions >= K: largest norm, first position among equals; a NaN norm never wins
@@ -416,21 +428,21 @@ __device__ __forceinline__ void qr_step(double (&A)[MAXD], double (&rd)[MAXD], u
     double bn = cand ? nrm : -1.0;
     uint32_t bp = cand ? pos : 0xffffffffu;
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        const double ob = __shfl_xor_sync(FULL, bn, off);
-        const uint32_t op = __shfl_xor_sync(FULL, bp, off);
+    for (int off = MAXD / 2; off > 0; off >>= 1) {
+        const double ob = __shfl_xor_sync(w.seg, bn, off, MAXD);
+        const uint32_t op = __shfl_xor_sync(w.seg, bp, off, MAXD);
         if (ob > bn || (ob == bn && op < bp)) {
             bn = ob;
             bp = op;
         }
     }
     if (bp == 0xffffffffu) bp = (uint32_t)K;  // (nothing but NaNs: the oracle keeps column K)
-    const uint32_t best_lane = __ffs(__ballot_sync(FULL, active && pos == bp)) - 1u;
-    const uint32_t lane_k = __ffs(__ballot_sync(FULL, active && pos == (uint32_t)K)) - 1u;
+    const uint32_t best_lane = __ffs(sub_ballot<MAXD>(w, active && pos == bp)) - 1u;
+    const uint32_t lane_k = __ffs(sub_ballot<MAXD>(w, active && pos == (uint32_t)K)) - 1u;
     if (lane == best_lane) pos = (uint32_t)K;
     else if (lane == lane_k) pos = bp;
     const double norm = sqrt(bn);
-    const double akk = __shfl_sync(FULL, A[K], best_lane);
+    const double akk = __shfl_sync(w.seg, A[K], best_lane, MAXD);
     if (norm == 0.0) {  // zero pivot: R_kk = 0, the remaining norms restart one row lower (find_dof: `continue`)
         nrm = 0.0;
 #pragma unroll
@@ -443,21 +455,21 @@ __device__ __forceinline__ void qr_step(double (&A)[MAXD], double (&rd)[MAXD], u
     const double tau = -vk / alpha;
     rd[K] = alpha;
     // v_i = A(i, pivot column) / vk for the rows below K.  A division is some thirty instructions for the whole warp whether
-    // one lane or all of them divide: the pivot column goes through the warp's shared-memory tile so that LANE i divides
+    // one lane or all of them divide: the pivot column goes through the sub-warp's row of the shared-memory tile so that LANE i divides
     // row i — one division per step instead of one per row — and every lane reads the quotients back (broadcast loads).
     double v[MAXD];
     if (lane == best_lane) {
 #pragma unroll
         for (int i = K + 1; i < MAXD; ++i) tile[i] = A[i];
     }
-    __syncwarp();
+    __syncwarp(w.seg);
     const double vi = (lane > (uint32_t)K && lane < m) ? tile[lane] / vk : 0.0;
-    __syncwarp();
+    __syncwarp(w.seg);
     tile[lane] = vi;
-    __syncwarp();
+    __syncwarp(w.seg);
 #pragma unroll
     for (int i = K + 1; i < MAXD; ++i) v[i] = tile[i];
-    __syncwarp();
+    __syncwarp(w.seg);
     if (lane == best_lane) {
         A[K] = alpha;
     } else if (active && pos > (uint32_t)K) {
@@ -478,26 +490,26 @@ __device__ __forceinline__ void qr_step(double (&A)[MAXD], double (&rd)[MAXD], u
 }
 template <int MAXD, int... Ks>
 __device__ __forceinline__ void qr_steps(std::integer_sequence<int, Ks...>, double (&A)[MAXD], double (&rd)[MAXD], uint32_t& pos, double& nrm,
-                                         uint32_t lane, bool active, uint32_t m, uint32_t ndiag, double* tile) {
-    (qr_step<Ks, MAXD>(A, rd, pos, nrm, lane, active, m, ndiag, tile), ...);
+                                         const SubWarp& w, bool active, uint32_t m, uint32_t ndiag, double* tile) {
+    (qr_step<Ks, MAXD>(A, rd, pos, nrm, w, active, m, ndiag, tile), ...);
 }
 
 // Back substitution row II of the null-space basis (freedom_warp_kernel), II a compile-time constant for the same reason.
 template <int II, int MAXD>
-__device__ __forceinline__ void back_row(const double (&A)[MAXD], double (&z)[MAXD], const uint32_t (&lop)[MAXD], uint32_t rank) {
-    const unsigned FULL = 0xffffffffu;
+__device__ __forceinline__ void back_row(const double (&A)[MAXD], double (&z)[MAXD], const uint32_t (&lop)[MAXD], uint32_t rank,
+                                         const SubWarp& w) {
     if ((uint32_t)II >= rank) return;
     double rhs = A[II];
 #pragma unroll
     for (int j = II + 1; j < MAXD; ++j)
-        if ((uint32_t)j < rank) rhs += __shfl_sync(FULL, A[II], lop[j]) * z[j];
-    const double diagonal = __shfl_sync(FULL, A[II], lop[II]);
+        if ((uint32_t)j < rank) rhs += __shfl_sync(w.seg, A[II], lop[j], MAXD) * z[j];
+    const double diagonal = __shfl_sync(w.seg, A[II], lop[II], MAXD);
     z[II] = -rhs / diagonal;
 }
 template <int MAXD, int... Is>
 __device__ __forceinline__ void back_rows(std::integer_sequence<int, Is...>, const double (&A)[MAXD], double (&z)[MAXD],
-                                          const uint32_t (&lop)[MAXD], uint32_t rank) {
-    (back_row<MAXD - 1 - Is, MAXD>(A, z, lop, rank), ...);  // rows descending
+                                          const uint32_t (&lop)[MAXD], uint32_t rank, const SubWarp& w) {
+    (back_row<MAXD - 1 - Is, MAXD>(A, z, lop, rank, w), ...);  // rows descending
 }
 
 // ---- Small sketches: a WARP per problem, the matrix in REGISTERS --------------------------------------------------------
@@ -511,20 +523,24 @@ __device__ __forceinline__ void back_rows(std::integer_sequence<int, Is...>, con
 template <int MAXD>
 __global__ void __launch_bounds__(128) freedom_warp_kernel(const FreedomArgs a) {
     extern __shared__ double fsm[];  // per warp: MAXD x 32 doubles, only to densify the sparse columns
-    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const uint32_t p = blockIdx.x * (blockDim.x >> 5) + warp;
+    constexpr uint32_t kPerWarp = 32u / MAXD;  // problems per warp: sub-warps of MAXD lanes
+    const uint32_t wlane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t sub = wlane / MAXD;
+    const SubWarp w{MAXD >= 32 ? 0xffffffffu : (((1u << MAXD) - 1u) << (sub * MAXD)), sub * MAXD, wlane % MAXD};
+    const uint32_t lane = w.sl;
+    const uint32_t p = (blockIdx.x * (blockDim.x >> 5) + warp) * kPerWarp + sub;
     if (p >= a.count) return;
     const uint32_t m = a.m, n = a.n, ndiag = m < n ? m : n;
     const bool active = lane < n;
-    const unsigned FULL = 0xffffffffu;
-    double* tile = fsm + (size_t)warp * MAXD * 32;
+    // the sub-warp's MAXD columns of the warp's [MAXD][32] block; its row 0 doubles as the exchange row of the QR steps
+    double* tile = fsm + (size_t)warp * MAXD * 32 + w.shift;
     const double* jac = a.jac + (size_t)p * a.nnz;
 #pragma unroll
     for (int i = 0; i < MAXD; ++i) tile[i * 32 + lane] = 0.0;
-    __syncwarp();
+    __syncwarp(w.seg);
     if (active)
         for (uint32_t e = a.csc_col_ptr[lane]; e < a.csc_col_ptr[lane + 1]; ++e) tile[a.csc_row_idx[e] * 32 + lane] = jac[e];
-    __syncwarp();
+    __syncwarp(w.seg);
     double A[MAXD];
 #pragma unroll
     for (int i = 0; i < MAXD; ++i) A[i] = tile[i * 32 + lane];
@@ -534,8 +550,8 @@ __global__ void __launch_bounds__(128) freedom_warp_kernel(const FreedomArgs a) 
 #pragma unroll
     for (int i = 0; i < MAXD; ++i)
         if ((uint32_t)i < m) nrm += A[i] * A[i];
-    __syncwarp();
-    qr_steps<MAXD>(std::make_integer_sequence<int, MAXD>{}, A, rd, pos, nrm, lane, active, m, ndiag, tile);
+    __syncwarp(w.seg);
+    qr_steps<MAXD>(std::make_integer_sequence<int, MAXD>{}, A, rd, pos, nrm, w, active, m, ndiag, tile);
     // ---- rank (find_dof.rs:40-52)
     double largest = ezm::ez_abs(rd[0]);
 #pragma unroll
@@ -558,12 +574,12 @@ __global__ void __launch_bounds__(128) freedom_warp_kernel(const FreedomArgs a) 
     }
     uint32_t lop[MAXD];  // lane that holds the column at each position
 #pragma unroll
-    for (int q = 0; q < MAXD; ++q) lop[q] = (uint32_t)q < n ? __ffs(__ballot_sync(FULL, active && pos == (uint32_t)q)) - 1u : 0u;
+    for (int q = 0; q < MAXD; ++q) lop[q] = (uint32_t)q < n ? __ffs(sub_ballot<MAXD>(w, active && pos == (uint32_t)q)) - 1u : 0u;
     // ---- basis of null(J P^T): back substitution over R11 for this lane's column (meaningful in the free lanes)
     double z[MAXD];
 #pragma unroll
     for (int i = 0; i < MAXD; ++i) z[i] = 0.0;
-    back_rows<MAXD>(std::make_integer_sequence<int, MAXD>{}, A, z, lop, rank);
+    back_rows<MAXD>(std::make_integer_sequence<int, MAXD>{}, A, z, lop, rank, w);
 #pragma unroll
     for (int i = 0; i < MAXD; ++i)
         if ((uint32_t)i >= rank) z[i] = ((uint32_t)i == pos) ? 1.0 : 0.0;
@@ -576,7 +592,7 @@ __global__ void __launch_bounds__(128) freedom_warp_kernel(const FreedomArgs a) 
             if ((uint32_t)q == pf) cur = lop[q];
         double zc[MAXD];  // the column being orthonormalised, replicated in every lane
 #pragma unroll
-        for (int i = 0; i < MAXD; ++i) zc[i] = (uint32_t)i < n ? __shfl_sync(FULL, z[i], cur) : 0.0;
+        for (int i = 0; i < MAXD; ++i) zc[i] = (uint32_t)i < n ? __shfl_sync(w.seg, z[i], cur, MAXD) : 0.0;
         for (int pass = 0; pass < 2; ++pass)
 #pragma unroll 1
             for (uint32_t pg = rank; pg < pf; ++pg) {
@@ -588,10 +604,10 @@ __global__ void __launch_bounds__(128) freedom_warp_kernel(const FreedomArgs a) 
 #pragma unroll
                 for (int i = 0; i < MAXD; ++i)
                     if ((uint32_t)i < n) s += z[i] * zc[i];  // (the value of lane gl is the one used)
-                s = __shfl_sync(FULL, s, gl);
+                s = __shfl_sync(w.seg, s, gl, MAXD);
 #pragma unroll
                 for (int i = 0; i < MAXD; ++i)
-                    if ((uint32_t)i < n) zc[i] -= s * __shfl_sync(FULL, z[i], gl);
+                    if ((uint32_t)i < n) zc[i] -= s * __shfl_sync(w.seg, z[i], gl, MAXD);
             }
         double s = 0.0;
 #pragma unroll
@@ -617,17 +633,17 @@ __global__ void __launch_bounds__(128) freedom_warp_kernel(const FreedomArgs a) 
 #pragma unroll
                 for (int q = 0; q < MAXD; ++q)
                     if ((uint32_t)q == pf) fl = lop[q];
-                total += __shfl_sync(FULL, sq, fl);
+                total += __shfl_sync(w.seg, sq, fl, MAXD);
             }
             if (pos == (uint32_t)i) my_part = total;
         }
     double max_p = active ? my_part : 0.0;
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) max_p = ezm::ez_fmax(max_p, __shfl_xor_sync(FULL, max_p, off));
+    for (int off = MAXD / 2; off > 0; off >>= 1) max_p = ezm::ez_fmax(max_p, __shfl_xor_sync(w.seg, max_p, off, MAXD));
     max_p = ezm::ez_fmax(0.0, max_p);
     const double var_tol = 1e-3 * max_p;
     const double squared_tol = var_tol * var_tol;
-    const uint32_t bits = __ballot_sync(FULL, active && my_part > squared_tol);
+    const uint32_t bits = sub_ballot<MAXD>(w, active && my_part > squared_tol);
     if (lane == 0) mask[0] = bits;
 }
 
@@ -691,9 +707,9 @@ int32_t freedom_device(ezpz_context* ctx, const ezpz_structure* s, uint64_t batc
             a.jac = d_jac + done * nnz;
             a.mask = d_mask + done * a.words;
             a.count = (uint32_t)count;
-            const uint32_t grid = (uint32_t)((count + 3) / 4);
-            if (m <= 8 && n <= 8) freedom_warp_kernel<8><<<grid, 128, 4 * 8 * 32 * sizeof(double), st>>>(a);
-            else freedom_warp_kernel<16><<<grid, 128, 4 * 16 * 32 * sizeof(double), st>>>(a);
+            // four warps per block, 32 / MAXD problems per warp (sub-warps of MAXD lanes)
+            if (m <= 8 && n <= 8) freedom_warp_kernel<8><<<(uint32_t)((count + 15) / 16), 128, 4 * 8 * 32 * sizeof(double), st>>>(a);
+            else freedom_warp_kernel<16><<<(uint32_t)((count + 7) / 8), 128, 4 * 16 * 32 * sizeof(double), st>>>(a);
             ctx->launches += 1;
             EZ_CUDA(cudaGetLastError(), "freedom_warp_kernel launch");
             done += count;
