@@ -35,7 +35,7 @@ struct CachedStructure {
 };
 struct StructureCache {
     std::vector<CachedStructure> entries;
-    uint64_t clock = 0, hits = 0, misses = 0;
+    uint64_t clock = 0, hits = 0, misses = 0, extended = 0;
 };
 constexpr size_t kCacheEntries = 8;
 constexpr uint32_t kCacheMaxVars = 1u << 18;  // larger systems hold GBs of device tables: not cached
@@ -89,7 +89,24 @@ int32_t cached_structure(ezpz_context_t* ctx, const std::vector<ezpz_constraint_
         return EZPZ_OK;
     }
     ++C.misses;
-    const int32_t rc = ezpz_b200_structure_create(cons.data(), (uint32_t)cons.size(), var_ids, n_vars, out, detail);
+    // A miss whose list continues a cached one (a constraint added to a sketch that was just solved: the trim and drag
+    // workflows, tests.rs:748-897) extends that structure instead of analysing from scratch: same patterns and tapes, and a
+    // sparse-direct system keeps its elimination order (ezpz_b200_structure_extend).  The longest cached prefix wins.
+    const CachedStructure* base = nullptr;
+    for (const CachedStructure& e : C.entries) {
+        if (e.n_vars != n_vars || e.cons.size() >= cons.size() || e.cons.empty() || e.has_var_ids != (var_ids != nullptr)) continue;
+        if (base && e.cons.size() <= base->cons.size()) continue;
+        if (std::memcmp(e.cons.data(), cons.data(), e.cons.size() * sizeof(ezpz_constraint_t)) != 0) continue;
+        if (var_ids && std::memcmp(e.var_ids.data(), var_ids, n_vars * sizeof(uint32_t)) != 0) continue;
+        base = &e;
+    }
+    int32_t rc;
+    if (base) {
+        ++C.extended;
+        rc = ezpz_b200_structure_extend(base->S, cons.data() + base->cons.size(), (uint32_t)(cons.size() - base->cons.size()), out, detail);
+    } else {
+        rc = ezpz_b200_structure_create(cons.data(), (uint32_t)cons.size(), var_ids, n_vars, out, detail);
+    }
     if (rc != EZPZ_OK) return rc;
     auto held = [&] {
         uint64_t v = 0;

@@ -384,6 +384,25 @@ def test_solve_topology_cache(ctx):
         assert_bitwise(np.array(out.final_values()), o.final_values, f"call {k}")
 
 
+def test_solve_extends_a_cached_topology(ctx):
+    """A constraint list that continues one ezpz_b200_solve has analysed (a constraint added to a solved sketch — the trim
+    workflow of tests.rs:748-897: two arcs, then PointArcCoincident on one of them) goes through ezpz_b200_structure_extend:
+    the answers are the oracle's for the longer list, call after call, as constraints are added one at a time."""
+    C, R = ez.Constraint, ez.ConstraintRequest
+    pts = [ez.DatumPoint.new_xy(2 * k, 2 * k + 1) for k in range(7)]
+    arc1 = ez.DatumCircularArc(center=pts[0], start=pts[1], end=pts[2])
+    arc2 = ez.DatumCircularArc(center=pts[3], start=pts[4], end=pts[5])
+    g = np.array([30.2, 0.1, 0.3, 5.2, -0.1, -5.3, 0.2, -30.1, 5.1, 0.2, -5.2, -0.1, 0.2, 0.1])
+    cons = [C.Arc(arc1), C.Arc(arc2), C.Fixed(0, 30.0), C.Fixed(1, 0.0), C.Fixed(6, 0.0), C.Fixed(7, -30.0),
+            C.PointArcCoincident(arc2, pts[6]), C.PointArcCoincident(arc1, pts[6]), C.Fixed(2, 0.0)]
+    for k in range(2, len(cons) + 1):
+        reqs = [R.highest_priority(c) for c in cons[:k]]
+        out = ez.solve(reqs, list(enumerate(g)), ctx=ctx)
+        o = orc.solve(ez.records(cons[:k]), g)
+        assert out.iterations() == o.iterations and out.is_satisfied() == (len(o.unsatisfied) == 0), k
+        assert_bitwise(np.array(out.final_values()), o.final_values, f"{k} constraints")
+
+
 def _undefined_sides_system():
     """Circles A (ids 0,1,2) and B (3,4,5), line p (6,7) - q (8,9).  A is pinned at the origin with radius 2, B has radius 1
     and its centre on the x axis, the line is horizontal between x = -5 and x = 5.  Both tangencies are given with
