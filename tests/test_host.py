@@ -461,3 +461,39 @@ def test_structure_extend_keeps_the_elimination_order(monkeypatch):
         monkeypatch.delenv("EZPZ_B200_EXTEND_FULL")
         assert fast.fingerprint() == slow.fingerprint()
         assert np.array_equal(fast.ordering()["elim_order"], of["elim_order"]) and fast.m == full.m + slow.m - full.m > full.m
+
+
+def test_structure_extend_random_lists():
+    """Random constraint lists of every kind, cut at random points: the extended structure has the patterns and row numbering of
+    the whole list; where no elimination order is carried over (batched-kernel and natural-order systems) it IS the fresh
+    analysis, array for array; where one is, it is a permutation and the schedule re-derived in that order (EZPZ_B200_EXTEND_FULL)
+    is the schedule taken over when A kept its pattern."""
+    from test_gpu_parity import random_constraints
+    rng = np.random.default_rng(11)
+    kept = 0
+    for trial in range(40):
+        n = int(rng.integers(6, 120))
+        recs = ez.records(random_constraints(rng, int(rng.integers(4, 3 * n)), n))
+        cut = int(rng.integers(1, len(recs)))
+        base, full = ez.Structure(recs[:cut], n), ez.Structure(recs, n)
+        ext = base.extend(recs[cut:])
+        pe, pf = ext.pattern(), full.pattern()
+        for key in pe:
+            assert np.array_equal(pe[key], pf[key]), (trial, key)
+        ob, oe = base.ordering(), ext.ordering()
+        if ob["path"] == 1 and oe["path"] == 1:
+            kept += 1
+            assert np.array_equal(oe["elim_order"], ob["elim_order"]) and sorted(oe["elim_order"].tolist()) == list(range(n))
+            if not ob["nested"]:
+                assert ext.fingerprint() == full.fingerprint(), trial
+        else:
+            assert ext.fingerprint() == full.fingerprint(), trial
+        again = recs[rng.integers(0, len(recs), 3)]
+        fast = full.extend(again)
+        os.environ["EZPZ_B200_EXTEND_FULL"] = "1"
+        try:
+            slow = full.extend(again)
+        finally:
+            del os.environ["EZPZ_B200_EXTEND_FULL"]
+        assert fast.fingerprint() == slow.fingerprint(), trial
+    assert kept >= 5
