@@ -520,8 +520,10 @@ __device__ __forceinline__ void back_rows(std::integer_sequence<int, Is...>, con
 // in the oracle's swapped order, so ties between equal norms break exactly as the oracle's "first maximum" does.  Every
 // sum runs in the oracle's order (rows ascending, free columns ascending, modified Gram-Schmidt g ascending), so the whole
 // analysis — not only the QR — is bit-identical to oracle/ezpz_oracle.cpp freedom_analysis.
+// (16 x 16: six blocks per SM = 24 warps at 80 registers and 144 bytes of spills measured 353 us against 387 us for four blocks at
+// 114 registers; the 8 x 8 instance needs 79 registers anyway)
 template <int MAXD>
-__global__ void __launch_bounds__(128) freedom_warp_kernel(const FreedomArgs a) {
+__global__ void __launch_bounds__(128, MAXD >= 16 ? 6 : 1) freedom_warp_kernel(const FreedomArgs a) {
     extern __shared__ double fsm[];  // per warp: MAXD x 32 doubles, only to densify the sparse columns
     constexpr uint32_t kPerWarp = 32u / MAXD;  // problems per warp: sub-warps of MAXD lanes
     const uint32_t wlane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
