@@ -32,6 +32,7 @@
 using namespace ezs;
 
 #include "device.h"
+#include "host_parallel.h"
 
 namespace {
 
@@ -980,6 +981,7 @@ int32_t ezpz_b200_solve_batch(ezpz_context_t* ctx, const ezpz_structure_t* s, co
     // cudaHostRegister / ezpz_b200_host_register), the kernel reads the guesses and writes the results across PCIe
     // itself, in coalesced 256-byte warp accesses (group_rows): no staging buffers, no copy calls, and the transfers of one
     // CTA overlap the arithmetic of the others instead of being pipelined by hand.  EZPZ_B200_ZERO_COPY=0 disables it.
+    bool all_pinned = true;  // every buffer of the call is page-locked host memory
     if (s->small.valid) {
         const char* zc = std::getenv("EZPZ_B200_ZERO_COPY");  // (read per call: bench.py times both forms in one process)
         const bool zero_copy = !(zc && zc[0] == '0');
@@ -993,10 +995,10 @@ int32_t ezpz_b200_solve_batch(ezpz_context_t* ctx, const ezpz_structure_t* s, co
             cudaPointerAttributes at;
             if (cudaPointerGetAttributes(&at, host) != cudaSuccess) {
                 cudaGetLastError();
-                ok = false;
+                ok = all_pinned = false;
                 return nullptr;
             }
-            if ((at.type != cudaMemoryTypeHost && at.type != cudaMemoryTypeManaged) || !at.devicePointer) ok = false;
+            if ((at.type != cudaMemoryTypeHost && at.type != cudaMemoryTypeManaged) || !at.devicePointer) ok = all_pinned = false;
             return at.devicePointer;
         };
         dio.guesses = (const double*)map(io->guesses, true);
@@ -1013,7 +1015,7 @@ int32_t ezpz_b200_solve_batch(ezpz_context_t* ctx, const ezpz_structure_t* s, co
         // time (tools/time_e2e_split.py, tools/time_e2e_modes.py: 65,536 problems 433 us zero-copy, 347 us pipelined; 8,192
         // problems 108 us against 147 us).  EZPZ_B200_HOST_MODE=zerocopy|pipeline forces a form.
         const char* hm = std::getenv("EZPZ_B200_HOST_MODE");
-        if (hm ? hm[0] == 'p' : batch >= kPipelineMinBatch) ok = false;
+        if ((hm && (hm[0] == 'p' || hm[0] == 'z')) ? hm[0] == 'p' : batch >= kPipelineMinBatch) ok = false;
         if (ok) {
             const int32_t rc = ezpz_b200_solve_batch_device(ctx, s, config, batch, &dio, ctx->stream, detail);
             if (rc != EZPZ_OK) return rc;
@@ -1065,6 +1067,49 @@ int32_t ezpz_b200_solve_batch(ezpz_context_t* ctx, const ezpz_structure_t* s, co
             if (io->degen_count) std::memcpy(io->degen_count, h + o_dg, batch * nc * 4);
             if (io->jacobian) std::memcpy(io->jacobian, h + o_jc, batch * nnz1 * 8);
             if (io->under_mask) std::memcpy(io->under_mask, h + o_uc, batch * vw1 * 4);
+            return EZPZ_OK;
+        }
+        // Large calls on ordinary (pageable) memory — what a Rust Vec<f64> is: the copy engines cannot read it, and a pageable
+        // cudaMemcpyAsync is a synchronous copy staged by the driver on one thread (65,536 problems: 1.6 ms against 0.35 ms on
+        // page-locked buffers).  The host pool's threads (host_parallel.h) copy the inputs into the context's page-locked
+        // block, the call runs there in its page-locked form (zero-copy / pipeline), the threads copy the results out.
+        // Measured on the pool's boxes (tools/time_pageable.py, caller's buffers reused): 8,192 problems 147 us against 284 us
+        // for the driver's own staging, 262,144 problems 4.2 against 5.3 ms, but 65,536 problems 1.66 against 1.63 ms — between
+        // the size that stays in the host caches and the size at which the driver's single thread falls behind, both are
+        // bound by the host's ~20 GB/s of copy bandwidth — so calls of 8-32 MB are left to the driver.
+        // EZPZ_B200_HOST_MODE=direct | staged forces a form.
+        const bool stage_here = hm && hm[0] == 's' ? true : (hm && hm[0] == 'd' ? false : (total <= ((size_t)8 << 20) || total >= ((size_t)32 << 20)));
+        if (!all_pinned && total <= ((size_t)1 << 31) && stage_here) {
+            int32_t rc = ensure_pin(ctx, total, detail);
+            if (rc != EZPZ_OK) return rc;
+            char* h = (char*)ctx->pin;
+            constexpr uint32_t kGrain = 1u << 18;  // bytes per host thread before a copy is worth splitting
+            auto copy = [&](void* dst, const void* src, size_t bytes) {
+                if (bytes) ezs::parallel_ranges((uint32_t)((bytes + 63) / 64), kGrain / 64, [&](uint32_t b, uint32_t e, uint32_t) {
+                    std::memcpy((char*)dst + (size_t)b * 64, (const char*)src + (size_t)b * 64, std::min((size_t)e * 64, bytes) - (size_t)b * 64);
+                });
+            };
+            copy(h + o_g, io->guesses, batch * n * 8);
+            if (io->params) copy(h + o_p, io->params, batch * nc * 8);
+            ezpz_batch_io_t pio;
+            pio.guesses = (const double*)(h + o_g);
+            pio.params = io->params ? (const double*)(h + o_p) : nullptr;
+            pio.final_values = (double*)(h + o_f);
+            pio.iterations = (uint32_t*)(h + o_it);
+            pio.status = (uint8_t*)(h + o_st);
+            pio.unsat_mask = io->unsat_mask ? (uint32_t*)(h + o_un) : nullptr;
+            pio.degen_count = io->degen_count ? (uint32_t*)(h + o_dg) : nullptr;
+            pio.jacobian = io->jacobian ? (double*)(h + o_jc) : nullptr;
+            pio.under_mask = io->under_mask ? (uint32_t*)(h + o_uc) : nullptr;
+            rc = ezpz_b200_solve_batch(ctx, s, config, batch, &pio, detail);  // (every buffer page-locked now: no second staging)
+            if (rc != EZPZ_OK) return rc;
+            copy(io->final_values, h + o_f, batch * n * 8);
+            copy(io->iterations, h + o_it, batch * 4);
+            copy(io->status, h + o_st, batch);
+            if (io->unsat_mask) copy(io->unsat_mask, h + o_un, batch * uw * 4);
+            if (io->degen_count) copy(io->degen_count, h + o_dg, batch * nc * 4);
+            if (io->jacobian) copy(io->jacobian, h + o_jc, batch * nnz1 * 8);
+            if (io->under_mask) copy(io->under_mask, h + o_uc, batch * vw1 * 4);
             return EZPZ_OK;
         }
     }

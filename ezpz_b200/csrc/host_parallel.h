@@ -1,17 +1,25 @@
 // host_parallel.h — the two tools of the host analysis of systems with 10^5..10^6 variables:
 //
-//   parallel_ranges   runs fn(begin, end, part) over [0, n) cut into contiguous parts on host threads; one part (the caller's
-//                     thread, no thread is started) below `grain` items per part, so small sketches pay nothing;
+//   parallel_ranges   runs fn(begin, end, part) over [0, n) cut into contiguous parts on the threads of a persistent pool
+//                     (HostPool); one part (the caller's thread, the pool is not touched) below `grain` items per part, so
+//                     small sketches pay nothing;
 //   uvec<T>           a std::vector that does not zero what resize() adds.  On a fresh mapping the zero-fill of a
 //                     std::vector is a SERIAL walk over pages nobody has touched yet (about 0.5 ms per MB of page faults on
 //                     the boxes measured: the 177 MB of analysed constraints of a 1M-variable sketch cost 90 ms before a
 //                     single slot was computed); a uvec leaves the first touch to the threads that fill it.
 #pragma once
+#include <unistd.h>
+
 #include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
 #include <cstdint>
 #include <cstdlib>
 #include <memory>
+#include <mutex>
 #include <thread>
+#include <type_traits>
 #include <vector>
 
 namespace ezs {
@@ -44,6 +52,96 @@ inline uint32_t host_threads(uint32_t n, uint32_t grain) {
     return std::max(1u, std::min(cap, n / std::max(1u, grain)));
 }
 
+// The threads behind parallel_ranges: a process-wide pool created on first use (min(cores, 16) - 1 workers; the caller is
+// the last one).  Starting and joining 15 threads costs ~300 us — more than most phases of the analysis of a mid-size sketch and
+// as much as copying 9 MB — so the workers persist: they spin for a moment after a job (the phases of an analysis follow each
+// other within microseconds) and then sleep on a condition variable.  One job at a time, in lockstep: every worker checks in
+// for every job, so none can be late into the next one; a second caller (or a worker) that finds the pool busy runs its
+// parts on its own thread.  A forked child starts a pool of its own.
+class HostPool {
+   public:
+    static HostPool& get() {
+        static std::atomic<HostPool*> inst{nullptr};
+        static std::mutex make;
+        HostPool* p = inst.load(std::memory_order_acquire);
+        if (p && p->pid_ == getpid()) return *p;
+        std::lock_guard<std::mutex> lock(make);
+        p = inst.load(std::memory_order_acquire);
+        if (!p || p->pid_ != getpid()) {  // (a forked child inherits the object but not its threads: the old one is abandoned)
+            p = new HostPool();
+            inst.store(p, std::memory_order_release);
+        }
+        return *p;
+    }
+    uint32_t workers() const { return (uint32_t)threads_.size(); }
+    // fn(part) for part in [0, parts): on the pool and the caller; returns when every part is done.
+    template <class F>
+    void run(uint32_t parts, F&& fn) {
+        if (parts == 0) return;
+        if (parts == 1 || threads_.empty() || in_worker() || !busy_.try_lock()) {
+            for (uint32_t i = 0; i < parts; ++i) fn(i);
+            return;
+        }
+        using Fn = typename std::remove_reference<F>::type;
+        call_ = [](void* a, uint32_t i) { (*static_cast<Fn*>(a))(i); };
+        arg_ = const_cast<void*>(static_cast<const void*>(&fn));
+        parts_ = parts;
+        next_.store(0, std::memory_order_relaxed);
+        arrived_.store(0, std::memory_order_relaxed);
+        {
+            std::lock_guard<std::mutex> lock(mu_);
+            generation_.fetch_add(1, std::memory_order_release);
+        }
+        cv_.notify_all();
+        for (uint32_t i; (i = next_.fetch_add(1, std::memory_order_relaxed)) < parts;) fn(i);
+        const uint32_t n = (uint32_t)threads_.size();
+        for (uint32_t spins = 0; arrived_.load(std::memory_order_acquire) < n; ++spins)
+            if (spins > 2000) std::this_thread::yield();
+        busy_.unlock();
+    }
+
+   private:
+    static bool& in_worker() {
+        static thread_local bool flag = false;
+        return flag;
+    }
+    HostPool() : pid_(getpid()) {
+        const uint32_t cores = std::max(1u, std::min(std::thread::hardware_concurrency(), 16u));
+        for (uint32_t t = 1; t < cores; ++t) {
+            threads_.emplace_back([this] { loop(); });
+            threads_.back().detach();
+        }
+    }
+    void loop() {
+        in_worker() = true;
+        uint64_t last = 0;
+        for (;;) {
+            // a short spin (the next phase usually follows at once), then sleep
+            const auto t0 = std::chrono::steady_clock::now();
+            while (generation_.load(std::memory_order_acquire) == last) {
+                if (std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(200)) {
+                    std::unique_lock<std::mutex> lock(mu_);
+                    cv_.wait(lock, [&] { return generation_.load(std::memory_order_acquire) != last; });
+                    break;
+                }
+            }
+            last = generation_.load(std::memory_order_acquire);
+            const uint32_t parts = parts_;
+            for (uint32_t i; (i = next_.fetch_add(1, std::memory_order_relaxed)) < parts;) call_(arg_, i);
+            arrived_.fetch_add(1, std::memory_order_release);
+        }
+    }
+    pid_t pid_;
+    std::vector<std::thread> threads_;
+    std::mutex mu_, busy_;
+    std::condition_variable cv_;
+    std::atomic<uint64_t> generation_{0};
+    std::atomic<uint32_t> next_{0}, arrived_{0};
+    void (*call_)(void*, uint32_t) = nullptr;
+    void* arg_ = nullptr;
+    uint32_t parts_ = 0;
+};
+
 template <class F>
 inline void parallel_ranges(uint32_t n, uint32_t grain, F&& fn, uint32_t* parts_out = nullptr) {
     const uint32_t nt = host_threads(n, grain);
@@ -52,12 +150,8 @@ inline void parallel_ranges(uint32_t n, uint32_t grain, F&& fn, uint32_t* parts_
         fn(0u, n, 0u);
         return;
     }
-    std::vector<std::thread> th;
-    th.reserve(nt - 1);
-    for (uint32_t t = 1; t < nt; ++t)
-        th.emplace_back([&, t] { fn((uint32_t)((uint64_t)n * t / nt), (uint32_t)((uint64_t)n * (t + 1) / nt), t); });
-    fn(0u, (uint32_t)((uint64_t)n / nt), 0u);
-    for (auto& x : th) x.join();
+    // (the partition depends on n, the grain and the thread cap only — not on who executes the parts)
+    HostPool::get().run(nt, [&](uint32_t t) { fn((uint32_t)((uint64_t)n * t / nt), (uint32_t)((uint64_t)n * (t + 1) / nt), t); });
 }
 
 // counter[0]++ returning the old value: a relaxed atomic when several host threads share the counters, a plain increment on

@@ -477,13 +477,7 @@ void build_sparse_direct(ezpz_structure& S, const uint32_t* order_hint, bool hin
                 }
             }
         };
-        if (nt <= 1) run(0);
-        else {
-            std::vector<std::thread> pool;
-            for (uint32_t t = 1; t < nt; ++t) pool.emplace_back(run, t);
-            run(0);
-            for (auto& th : pool) th.join();
-        }
+        HostPool::get().run(nt, run);  // (nt == 1: the caller alone)
         for (uint32_t t = 0; t < nt; ++t)
             if (too_large[t]) return;
         if (nt > 1) run(nt);  // (a single thread owns every column)
