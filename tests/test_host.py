@@ -497,3 +497,24 @@ def test_structure_extend_random_lists():
             del os.environ["EZPZ_B200_EXTEND_FULL"]
         assert fast.fingerprint() == slow.fingerprint(), trial
     assert kept >= 5
+
+
+@pytest.mark.filterwarnings("ignore::DeprecationWarning")  # (Python's generic warning about fork() in a threaded process)
+def test_host_pool_survives_fork():
+    """The host analysis runs its phases on a persistent pool of threads (host_parallel.h).  A forked child inherits the pool
+    object but none of its threads: it must start a pool of its own instead of waiting for workers that do not exist."""
+    import multiprocessing as mp
+    recs, n = wl.chain_sketch(20000)[:2]
+    fp = ez.Structure(recs, n).fingerprint()  # (the parent's pool exists from here on)
+
+    def child(q):
+        q.put(ez.Structure(recs, n).fingerprint())
+
+    ctx = mp.get_context("fork")
+    q = ctx.Queue()
+    p = ctx.Process(target=child, args=(q,))
+    p.start()
+    got = q.get(timeout=120)
+    p.join(timeout=30)
+    assert got == fp and p.exitcode == 0
+    assert ez.Structure(recs, n).fingerprint() == fp  # and the parent's pool still works
