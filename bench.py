@@ -608,8 +608,9 @@ def run_gpu(args):
     if world == 1:
         tp = timed_calls(lambda: ctx.solve_batch(st, g), steps, 3)
         pageable = {"value": B * len(tp) / sum(tp), "unit": "solves/s", "ms_per_step": sum(tp) / len(tp) * 1e3,
-                    "api": "ezpz_b200_solve_batch on ordinary numpy arrays (what a Rust Vec<f64> is): staged through the "
-                           "library's pinned buffers, output arrays allocated per call"}
+                    "api": "ezpz_b200_solve_batch on ordinary numpy arrays (what a Rust Vec<f64> is), output arrays allocated "
+                           "per call: at this size (17 MB per call) the copies are the driver's staged ones; calls of up to 8 MB go "
+                           "through the library's page-locked block on its host threads (profiles/r02v_pageable_buffers.log)"}
     del hg, res, owners
     host_barrier()
 

@@ -20,6 +20,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -1069,28 +1070,36 @@ int32_t ezpz_b200_solve_batch(ezpz_context_t* ctx, const ezpz_structure_t* s, co
             if (io->under_mask) std::memcpy(io->under_mask, h + o_uc, batch * vw1 * 4);
             return EZPZ_OK;
         }
-        // Large calls on ordinary (pageable) memory — what a Rust Vec<f64> is: the copy engines cannot read it, and a pageable
-        // cudaMemcpyAsync is a synchronous copy staged by the driver on one thread (65,536 problems: 1.6 ms against 0.35 ms on
-        // page-locked buffers).  The host pool's threads (host_parallel.h) copy the inputs into the context's page-locked
-        // block, the call runs there in its page-locked form (zero-copy / pipeline), the threads copy the results out.
-        // Measured on the pool's boxes (tools/time_pageable.py, caller's buffers reused): 8,192 problems 147 us against 284 us
-        // for the driver's own staging, 262,144 problems 4.2 against 5.3 ms, but 65,536 problems 1.66 against 1.63 ms — between
-        // the size that stays in the host caches and the size at which the driver's single thread falls behind, both are
-        // bound by the host's ~20 GB/s of copy bandwidth — so calls of 8-32 MB are left to the driver.
-        // EZPZ_B200_HOST_MODE=direct | staged forces a form.
-        const bool stage_here = hm && hm[0] == 's' ? true : (hm && hm[0] == 'd' ? false : (total <= ((size_t)8 << 20) || total >= ((size_t)32 << 20)));
+        // Mid-size calls on ordinary (pageable) memory — what a Rust Vec<f64> is: the copy engines cannot read it, and a pageable
+        // cudaMemcpyAsync is a synchronous copy staged by the driver on one thread.  While the call fits the host's caches
+        // (up to 8 MB: 16,384 two_rectangles problems) the host pool's threads (host_parallel.h) copy the inputs into the
+        // context's page-locked block, the call runs there in its page-locked form, and the threads copy the results out:
+        // 16,384 problems 196 us against 450 us, 4,096 problems 124 against 202 us (tools/time_pageable.py).  Larger calls
+        // stay with the driver: behind sixteen copy threads the DMA of the freshly touched block crawls (the same pipeline
+        // 1.5 ms instead of 0.34 ms at 65,536 problems; 1.1 ms in all with two copy threads against 1.6 ms for the driver, but
+        // slower again at 32,768 and 131,072 — profiles/r02v_pageable_buffers.log), so only the clear case is taken.
+        // EZPZ_B200_HOST_MODE=direct | staged forces a form, EZPZ_B200_STAGE_THREADS the copy threads of the forced form.
+        const bool stage_here = hm && hm[0] == 's' ? true : (hm && hm[0] == 'd' ? false : total <= ((size_t)8 << 20));
         if (!all_pinned && total <= ((size_t)1 << 31) && stage_here) {
             int32_t rc = ensure_pin(ctx, total, detail);
             if (rc != EZPZ_OK) return rc;
             char* h = (char*)ctx->pin;
-            constexpr uint32_t kGrain = 1u << 18;  // bytes per host thread before a copy is worth splitting
+            static const uint32_t stage_threads = [] {  // (0 = as many as the pool has)
+                const char* e = std::getenv("EZPZ_B200_STAGE_THREADS");
+                return e ? (uint32_t)std::strtoul(e, nullptr, 10) : 0u;
+            }();
             auto copy = [&](void* dst, const void* src, size_t bytes) {
-                if (bytes) ezs::parallel_ranges((uint32_t)((bytes + 63) / 64), kGrain / 64, [&](uint32_t b, uint32_t e, uint32_t) {
+                const uint32_t units = (uint32_t)((bytes + 63) / 64);
+                const uint32_t grain = std::max<uint32_t>((1u << 18) / 64, stage_threads ? (units + stage_threads - 1) / stage_threads : 0u);
+                if (bytes) ezs::parallel_ranges(units, grain, [&](uint32_t b, uint32_t e, uint32_t) {
                     std::memcpy((char*)dst + (size_t)b * 64, (const char*)src + (size_t)b * 64, std::min((size_t)e * 64, bytes) - (size_t)b * 64);
                 });
             };
+            static const bool trace4 = [] { const char* e = std::getenv("EZPZ_B200_DEBUG"); return e && e[0] == '4'; }();
+            const auto t_a = std::chrono::steady_clock::now();
             copy(h + o_g, io->guesses, batch * n * 8);
             if (io->params) copy(h + o_p, io->params, batch * nc * 8);
+            const auto t_b = std::chrono::steady_clock::now();
             ezpz_batch_io_t pio;
             pio.guesses = (const double*)(h + o_g);
             pio.params = io->params ? (const double*)(h + o_p) : nullptr;
@@ -1103,6 +1112,7 @@ int32_t ezpz_b200_solve_batch(ezpz_context_t* ctx, const ezpz_structure_t* s, co
             pio.under_mask = io->under_mask ? (uint32_t*)(h + o_uc) : nullptr;
             rc = ezpz_b200_solve_batch(ctx, s, config, batch, &pio, detail);  // (every buffer page-locked now: no second staging)
             if (rc != EZPZ_OK) return rc;
+            const auto t_c = std::chrono::steady_clock::now();
             copy(io->final_values, h + o_f, batch * n * 8);
             copy(io->iterations, h + o_it, batch * 4);
             copy(io->status, h + o_st, batch);
@@ -1110,6 +1120,11 @@ int32_t ezpz_b200_solve_batch(ezpz_context_t* ctx, const ezpz_structure_t* s, co
             if (io->degen_count) copy(io->degen_count, h + o_dg, batch * nc * 4);
             if (io->jacobian) copy(io->jacobian, h + o_jc, batch * nnz1 * 8);
             if (io->under_mask) copy(io->under_mask, h + o_uc, batch * vw1 * 4);
+            if (trace4) {
+                const auto t_d = std::chrono::steady_clock::now();
+                auto us = [](auto x, auto y) { return std::chrono::duration<double, std::micro>(y - x).count(); };
+                std::fprintf(stderr, "[solve_batch staged] copy in %.0f us, solve %.0f us, copy out %.0f us\n", us(t_a, t_b), us(t_b, t_c), us(t_c, t_d));
+            }
             return EZPZ_OK;
         }
     }

@@ -106,6 +106,7 @@ class HostPool {
         return flag;
     }
     HostPool() : pid_(getpid()) {
+        if (const char* e = std::getenv("EZPZ_B200_POOL_SPIN_US")) spin_us_ = std::strtol(e, nullptr, 10);
         const uint32_t cores = std::max(1u, std::min(std::thread::hardware_concurrency(), 16u));
         for (uint32_t t = 1; t < cores; ++t) {
             threads_.emplace_back([this] { loop(); });
@@ -119,7 +120,7 @@ class HostPool {
             // a short spin (the next phase usually follows at once), then sleep
             const auto t0 = std::chrono::steady_clock::now();
             while (generation_.load(std::memory_order_acquire) == last) {
-                if (std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(200)) {
+                if (std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(spin_us_)) {
                     std::unique_lock<std::mutex> lock(mu_);
                     cv_.wait(lock, [&] { return generation_.load(std::memory_order_acquire) != last; });
                     break;
@@ -132,6 +133,7 @@ class HostPool {
         }
     }
     pid_t pid_;
+    long spin_us_ = 200;  // how long a worker spins for the next job before it sleeps (EZPZ_B200_POOL_SPIN_US)
     std::vector<std::thread> threads_;
     std::mutex mu_, busy_;
     std::condition_variable cv_;

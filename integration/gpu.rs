@@ -247,8 +247,8 @@ impl Structure {
 
 /// The additive batch API: `batch` problems of one topology in one call, sharded over every GPU of the box.
 /// `guesses` is row-major `batch x n_vars`; results come back as flat vectors (finals, iterations, EZPZ_ST_* bits).
-/// (`Vec` memory is pageable: the library stages it — with its own host threads up to 8 MB and from 32 MB per call, through the
-/// driver in between.  A caller that re-solves at full rate keeps its buffers in `ezpz_b200_host_alloc` memory or registers them
+/// (`Vec` memory is pageable: the library stages it — with its own host threads up to 8 MB per call, through the driver's
+/// staged copies above.  A caller that re-solves at full rate keeps its buffers in `ezpz_b200_host_alloc` memory or registers them
 /// once with `ezpz_b200_host_register`: 0.35 ms instead of 1.6 ms per 65,536 sketches.)
 pub fn solve_batch(mg: *mut EzpzMulti, st: &Structure, n_vars: usize, guesses: &[f64], config: crate::Config)
     -> Result<(Vec<f64>, Vec<u32>, Vec<u8>), i32> {
